@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- grid-point updates/s of the 3-D isotropic C-PML time loop on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload ...]
+
+One "step" = one full time step of the loop body (stress + velocity + source + Dirichlet
++ seismogram sample + energy) over the rank's z-slab.  Workloads (BASELINE.json configs):
+  cfg3  seismic_CPML_3D_isotropic_MPI_OpenMP default grid 101 x 641 x 640 per GPU
+        (N = 1: exactly the reference grid; N > 1: weak scaling, NZ = 640 N)   [default]
+  cfg4  1024 x 1024 x 128 per GPU (N = 8: 1024^3), weak scaling
+  cfg2  2-D fourth order 4096 x 4096 (single GPU only)
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the
+reference loop (oracle/, OpenMP, all host threads): the Fortran reference itself cannot be
+built in this image (no Fortran compiler, no MPI).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "grid-point updates/s, 3-D isotropic C-PML time loop (FP64)"
+UNIT = "Gpts/s"
+
+
+def measured_peak():
+    """HBM roofline denominator: the driver-measured copy bandwidth, else the recipe's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        for ts, line in self.lines:
+            if t0 is not None and not (t0 <= ts <= t1 + 0.2):
+                continue
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); smax.append(float(p[2])); power.append(float(p[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def workload_params(name, n_gpus, nstep):
+    from seismic_cpml_b200 import programs as P
+    if name == "cfg3":
+        return P.Params3DIso(NZ=640 * n_gpus, NSTEP=nstep), "3d"
+    if name == "cfg4":
+        return P.Params3DIso(NX=1024, NY=1024, NZ=128 * n_gpus, NSTEP=nstep), "3d"
+    if name == "cfg2":
+        if n_gpus != 1:
+            raise SystemExit("cfg2 (2-D) runs on one GPU")
+        return P.Params2DIso(order=4, NX=4096, NY=4096, NSTEP=nstep), "2d"
+    raise SystemExit(f"unknown workload {name}")
+
+
+def workload_label(name, p, kind, n_gpus):
+    if kind == "2d":
+        return f"seismic_CPML_2D_isotropic_fourth_order {p.NX}x{p.NY}"
+    per = f"{p.NX}x{p.NY}x{p.NZ // n_gpus} per GPU"
+    tag = "default grid" if name == "cfg3" else "~1024^3 scaled grid"
+    return f"seismic_CPML_3D_isotropic_MPI_OpenMP {tag}: {p.NX}x{p.NY}x{p.NZ} ({per}, z-slabs)"
+
+
+# ------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's OpenMP build on the host cores
+# ------------------------------------------------------------------------------------
+
+def oracle_3d_gpts(p, nz_sample, steps, warmup):
+    """Times `steps` time steps (after `warmup`) of the CPU restatement on a z-reduced sample
+    of the workload: NX x NY x nz_sample, same spacing / time step / PML / source law."""
+    from oracle import oracle as O
+    from seismic_cpml_b200 import programs as P
+    q = P.Params3DIso(NX=p.NX, NY=p.NY, NZ=nz_sample, NSTEP=steps + warmup, DELTAX=p.DELTAX, DELTAT=p.DELTAT)
+    s = P.setup_3d(q)
+    O.set_ftz(True)                 # cf. reference Makefile:18 (-ftz "critical for performance")
+    O.set_warmup_steps(warmup)
+    O.run_3d_iso(nx=q.NX, ny=q.NY, nz=q.NZ, nproc=2, deltax=q.DELTAX, deltay=q.DELTAY, deltaz=q.DELTAZ,
+                 deltat=q.DELTAT, lam=q.lam, mu=q.mu, lambdaplustwomu=q.lambdaplustwomu, rho=q.rho,
+                 nstep=q.NSTEP, npoints_pml=q.NPOINTS_PML, isource=q.ISOURCE, jsource=q.JSOURCE,
+                 prof_x=s.prof_x, prof_y=s.prof_y, prof_z=s.prof_z, force_x=s.force_x, force_y=s.force_y,
+                 ix_rec=s.ix_rec, iy_rec=s.iy_rec, kind="timed")
+    sec = O.last_loop_seconds()
+    O.set_warmup_steps(0)
+    pts = float(q.NX) * q.NY * q.NZ * steps
+    return pts / sec / 1e9, sec, O.num_threads()
+
+
+def oracle_2d_gpts(p, n_sample, steps, warmup):
+    from oracle import oracle as O
+    from seismic_cpml_b200 import programs as P
+    q = P.Params2DIso(order=p.order, NX=n_sample, NY=n_sample, NSTEP=steps + warmup)
+    s = P.setup_2d(q)
+    O.set_ftz(True)
+    O.set_warmup_steps(warmup)
+    O.run_2d(order=q.order, nx=q.NX, ny=q.NY, deltax=q.DELTAX, deltay=q.DELTAY, deltat=q.DELTAT, nstep=q.NSTEP,
+             npoints_pml=q.NPOINTS_PML, isource=q.ISOURCE, jsource=q.JSOURCE, lam=s.material[0], mu=s.material[1],
+             rho=s.material[2], prof_x=s.prof_x, prof_y=s.prof_y, force_x=s.force_x, force_y=s.force_y,
+             ix_rec=s.ix_rec, iy_rec=s.iy_rec, kind="timed")
+    sec = O.last_loop_seconds()
+    O.set_warmup_steps(0)
+    return float(q.NX) * q.NY * steps / sec / 1e9, sec, 1      # the 2-D programs are serial
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    p, kind = workload_params(args.workload, args.gpus, args.steps + args.warmup)
+    if kind == "3d":
+        nz_s = 160
+        v, sec, cores = oracle_3d_gpts(p, nz_s, args.steps, args.warmup)
+        sample = (f"{p.NX}x{p.NY}x{nz_s} z-reduced sample of the workload grid (2 emulated MPI slabs), "
+                  f"{args.steps} timed steps after {args.warmup}; full-grid memory variables and separate "
+                  "Dirichlet/energy passes as in the reference; FTZ/DAZ on")
+    else:
+        n_s = 2048
+        v, sec, cores = oracle_2d_gpts(p, n_s, args.steps, args.warmup)
+        sample = f"{n_s}x{n_s} sample grid, {args.steps} timed steps after {args.warmup}, serial like the reference"
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (fields start at zero, analytic source; no RNG)",
+            "config": {"workload": workload_label(args.workload, p, kind, args.gpus)},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "note": "C/OpenMP restatement of the reference loops (oracle/cpml_oracle.c, "
+                                     "gcc -O3 -march=x86-64-v3 -fopenmp); the Fortran reference cannot be "
+                                     "compiled in this image"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from seismic_cpml_b200 import lib as L
+    from seismic_cpml_b200 import programs as P
+    from seismic_cpml_b200.slab import GpuSlab, SlabDriver, owner_of_plane
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N "
+                             "--master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    K, W = args.steps, max(args.warmup, 3)
+    nstep_total = W + K + K + 8          # warm-up + device-timed + e2e-timed (+ slack)
+    p, kind = workload_params(args.workload, world, nstep_total)
+    s = P.setup_3d(p) if kind == "3d" else P.setup_2d(p)
+    if kind == "3d":
+        sol = P.make_solver_3d(p, s, nslabs=world, slab_rank=rank, device=local_rank)
+        pts_step_rank = float(p.NX) * p.NY * (p.NZ // world)
+    else:
+        sol = P.make_solver_2d(p, s, device=local_rank)
+        pts_step_rank = float(p.NX) * p.NY
+    slab = GpuSlab(sol) if kind == "3d" else sol
+    drv = SlabDriver(slab, rank, world, sol.nzl) if (kind == "3d" and world > 1) else None
+    if kind != "3d":
+        sol.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def do_steps(a, b):
+        if drv is not None:
+            for it in range(a, b + 1):
+                drv.step(it)
+        else:
+            for it in range(a, b + 1):
+                sol.step_stress(it); sol.step_velocity(it); sol.step_finish(it)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    do_steps(1, W)
+    barrier()
+
+    # ---- device-timed region: K steps, fields resident in HBM, CUDA events, max over ranks
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    sol.get_kernel_times(reset=True)
+    sol.enable_kernel_timing(True)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    do_steps(W + 1, W + K)
+    ev1.record()
+    barrier()
+    t1 = time.perf_counter()
+    ms = ev0.elapsed_time(ev1)
+    ms_stress, ms_velocity, n_launch = sol.get_kernel_times(reset=True)
+    sol.enable_kernel_timing(False)
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    value = pts_step_rank * world * K / (ms_max * 1e-3) / 1e9
+
+    # ---- e2e: the same K steps through the public driver API with HOST buffers: upload the
+    # source series, run with the reference's display schedule (it == 5 and every IT_DISPLAY
+    # steps: max norm, seismograms, two snapshot planes come back), then pull the traces.
+    h2d = d2h = 0
+    barrier()
+    te0 = time.perf_counter()
+    fx = np.ascontiguousarray(s.force_x)
+    fy = np.ascontiguousarray(s.force_y)
+    sol.set_source_series(fx, fy)                       # H2D (pageable -> staged by the driver)
+    h2d += fx.nbytes + fy.nbytes
+    a0 = W + K + 1
+    for rel in range(1, K + 1):
+        it = a0 + rel - 1
+        do_steps(it, it)
+        if rel == 5 or rel % p.IT_DISPLAY == 0:          # :1183
+            vn = drv.maxnorm() if drv is not None else sol.get_maxnorm()
+            d2h += 8
+            if vn > P.STABILITY_THRESHOLD:
+                raise SystemExit("code became unstable and blew up")
+            if kind == "3d":
+                own = owner_of_plane(p.NZ // 2, p.NZ, world)
+                if rank == own:
+                    sx, sy = sol.get_seismograms()
+                    pv = sol.get_plane(0, p.NZ // 2), sol.get_plane(1, p.NZ // 2)
+                    d2h += sx.nbytes + sy.nbytes + pv[0].nbytes + pv[1].nbytes
+            else:
+                sx, sy = sol.get_seismograms()
+                pv = sol.get_plane(0), sol.get_plane(1)
+                d2h += sx.nbytes + sy.nbytes + pv[0].nbytes + pv[1].nbytes
+    sx, sy = sol.get_seismograms()
+    en = sol.get_energy()
+    d2h += sx.nbytes + sy.nbytes + 3 * en[0].nbytes
+    barrier()
+    te1 = time.perf_counter()
+    te = torch.tensor([te1 - te0], dtype=torch.float64, device="cuda")
+    td = torch.tensor([float(d2h)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(td, op=dist.ReduceOp.MAX)
+    e2e_value = pts_step_rank * world * K / float(te.item()) / 1e9
+    finite = bool(np.isfinite(en[0]).all() and np.isfinite(sx).all())
+
+    # ---- roofline of the dominant kernel (stress: 15 of the 27 words per point)
+    b_stress, b_velocity = sol.algorithmic_bytes()
+    peak, peak_src = measured_peak()
+    ach = b_stress / (ms_stress / K * 1e-3) / 1e9 if ms_stress > 0 else None
+    ach_v = b_velocity / (ms_velocity / K * 1e-3) / 1e9 if ms_velocity > 0 else None
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(args.workload, {}).get("stress_dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic (fields start at zero, analytic source; no RNG)",
+            "config": {"workload": workload_label(args.workload, p, kind, world),
+                       "grid": [p.NX, p.NY, getattr(p, "NZ", 1)], "npoints_pml": p.NPOINTS_PML,
+                       "deltat": p.DELTAT, "l2": "fields (>= 3 GB per rank) are far larger than the 126 MB L2; no flush needed",
+                       "parallelism": f"z-slabs x{world}" if world > 1 else "single GPU",
+                       "halo": "NCCL send/recv of 6 planes per step and interface" if world > 1 else None,
+                       "fmad": False, "finite": finite},
+            "roofline": {"bound": "hbm", "kernel": "k_stress3d" if kind == "3d" else "k_stress2d",
+                         "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": (ach / peak) if ach else None, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": b_stress,
+                         "avg_launch_ms": ms_stress / K,
+                         "velocity_kernel": {"achieved": ach_v, "frac": (ach_v / peak) if ach_v else None,
+                                             "algorithmic_bytes_per_launch": b_velocity,
+                                             "avg_launch_ms": ms_velocity / K},
+                         "step": {"algorithmic_bytes": b_stress + b_velocity,
+                                  "achieved": (b_stress + b_velocity) / (ms_max / K * 1e-3) / 1e9,
+                                  "frac": (b_stress + b_velocity) / (ms_max / K * 1e-3) / 1e9 / peak}},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / K,
+                    "d2h_bytes_per_step": float(td.item()) / K,
+                    "what": "cpml_set_source_series + K steps with the reference display schedule "
+                            "(max norm, seismograms, 2 snapshot planes at it==5 and every IT_DISPLAY) + final traces, host buffers"},
+            "gpu_launches": int(n_launch),
+            "clocks": clocks,
+        }
+        if args.cpu_baseline and world == 1:
+            try:
+                if kind == "3d":
+                    v, sec, cores = oracle_3d_gpts(p, 80, 6, 2)
+                    sample = f"{p.NX}x{p.NY}x80 z-reduced sample, 6 timed steps after 2, 2 emulated MPI slabs, FTZ/DAZ on"
+                else:
+                    v, sec, cores = oracle_2d_gpts(p, 1024, 6, 2)
+                    sample = "1024x1024 sample grid, 6 timed steps after 2, serial like the reference"
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            except Exception as exc:   # the oracle is only the yardstick; never fail the GPU number on it
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
+        print(json.dumps(line), flush=True)
+    sol.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg4", "cfg2"])
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,247 @@
+/*
+ * cpml_b200.h -- C ABI of libcpml_b200.so, the B200 (sm_100a) implementation of the
+ * SEISMIC_CPML staggered-grid velocity-stress C-PML time loop.
+ *
+ * The reference (geodynamics/seismic_cpml) has no library/FFI boundary: every solver
+ * is one Fortran `program` whose hot loop `do it = 1,NSTEP` is inline.  This header
+ * IS the boundary a maintainer cuts at that line:
+ *     seismic_CPML_3D_isotropic_MPI_OpenMP.f90:802      (3-D isotropic)
+ *     seismic_CPML_2D_isotropic_second_order.f90:550    (2-D, 2nd order)
+ *     seismic_CPML_2D_isotropic_fourth_order.f90:551    (2-D, 4th order)
+ * Everything above that line (parameters, C-PML profiles, source law, receiver
+ * search, CFL check) stays in the driver and is handed over through the setters;
+ * everything the loop body touches lives on the GPU behind an opaque handle; the
+ * output phase pulls seismograms / energy / snapshot planes back through getters.
+ * The Fortran binding (module cpml_b200, ISO_C_BINDING) is in drivers/fortran/ and
+ * INTEGRATION.md.
+ *
+ * Conventions: extern "C", plain pointers and sizes, int32/double only, every
+ * function returns 0 on success or a CPML_E* code (message via cpml_last_error);
+ * no exceptions, no global state; the caller owns every host buffer; the library
+ * owns all device memory.  All array arguments are Fortran-ordered (i fastest) and
+ * all grid indices are 1-based, exactly like the reference's arrays, so a Fortran
+ * driver passes its arrays as they are.  One host thread per handle.
+ * There is NO CPU fallback: without a CUDA device cpml_create fails.
+ */
+#ifndef CPML_B200_H
+#define CPML_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPML_B200_ABI_VERSION 1
+
+/* error codes */
+#define CPML_OK            0
+#define CPML_EINVAL        1   /* bad argument / inconsistent configuration            */
+#define CPML_ETOPOLOGY     2   /* slab checks of 3D-iso :381-394 failed                */
+#define CPML_ECFL          3   /* Courant number > 1 (3D-iso :717, 2D-2nd :516)        */
+#define CPML_ECUDA         4   /* CUDA runtime error / no usable device                */
+#define CPML_ESTATE        5   /* call order (e.g. run before profiles were set)       */
+#define CPML_ENOMEM        6
+
+/* axes for cpml_set_profiles */
+#define CPML_AXIS_X 0
+#define CPML_AXIS_Y 1
+#define CPML_AXIS_Z 2
+
+/* field ids for cpml_get_plane / cpml_get_field / cpml_halo_plane */
+#define CPML_F_VX       0
+#define CPML_F_VY       1
+#define CPML_F_VZ       2
+#define CPML_F_SIGMAXX  3
+#define CPML_F_SIGMAYY  4
+#define CPML_F_SIGMAZZ  5
+#define CPML_F_SIGMAXY  6
+#define CPML_F_SIGMAXZ  7
+#define CPML_F_SIGMAYZ  8
+
+typedef struct cpml_handle cpml_handle;
+
+/* Mirrors the compile-time `parameter` block of the reference programs
+ * (3D-iso :124-218, 2D-2nd :138-218); names follow the Fortran names.
+ * bind(C)-friendly: int32 and double only. */
+typedef struct cpml_config {
+    int32_t ndim;            /* 2 or 3                                                   */
+    int32_t order;           /* spatial order: 2 or 4 (ndim==2), 2 (ndim==3)             */
+    int32_t nx, ny, nz;      /* NX, NY, NZ: GLOBAL grid; nz ignored when ndim==2         */
+    int32_t nstep;           /* NSTEP: capacity of the seismogram / energy traces        */
+    int32_t npoints_pml;     /* NPOINTS_PML: only used for the energy box (:1135-1145)   */
+    int32_t nrec;            /* NREC                                                     */
+    int32_t isource, jsource;/* ISOURCE, JSOURCE (1-based)                               */
+    int32_t ksource;         /* 3-D: global k of source AND receiver plane; 0 => NZ/2,
+                                the reference's cut plane (:346,1080,1126)               */
+    int32_t nslabs;          /* number of z-slabs = reference NPROC (1 = whole grid)     */
+    int32_t slab_rank;       /* which slab this handle owns, 0-based = MPI rank          */
+    int32_t device;          /* CUDA device ordinal, -1 = current device                 */
+    int32_t energy_bug_compat; /* 1 = reference 3-D potential energy (yy counted twice,
+                                zz omitted, :1169-1172); 0 = physical formula            */
+    int32_t reserved_i[4];
+    double deltax, deltay, deltaz;   /* DELTAX, DELTAY, DELTAZ                           */
+    double deltat;                   /* DELTAT                                           */
+    /* homogeneous medium of the 3-D program (:139-144); the 2-D programs take arrays
+       through cpml_set_material_2d and ignore these four */
+    double lambda, mu, lambdaplustwomu, rho;
+    double cp;                       /* P velocity, only for the Courant check           */
+    double reserved_d[4];
+} cpml_config;
+
+/* ---- life cycle ---------------------------------------------------------- */
+
+int32_t cpml_abi_version(void);
+
+/* Validates (topology checks of 3D-iso :381-394, CFL check :712-717), allocates and
+ * zeroes the device state (:720-756).  *out is NULL on failure; the reason is then
+ * available from cpml_last_error(NULL). */
+int32_t cpml_create(const cpml_config *cfg, cpml_handle **out);
+int32_t cpml_destroy(cpml_handle *h);
+const char *cpml_last_error(const cpml_handle *h);
+
+/* Re-zero fields, memory variables, seismograms and energy (== :720-756). */
+int32_t cpml_reset(cpml_handle *h);
+
+/* Run the kernels on this CUDA stream (cudaStream_t passed as void*); default 0. */
+int32_t cpml_set_stream(cpml_handle *h, void *cuda_stream);
+
+/* ---- inputs (driver -> device), replacing the arrays built before the loop -- */
+
+/* 1-D damping profiles of one axis, built by the driver at :425-667.  n must be
+ * NX, NY or the GLOBAL NZ.  The library stores C-PML memory variables only where a
+ * profile is non-trivial (a != 0 or K != 1); elsewhere they are identically zero
+ * in the reference too, so this is exact. */
+int32_t cpml_set_profiles(cpml_handle *h, int32_t axis,
+                          const double *a, const double *b, const double *K,
+                          const double *a_half, const double *b_half, const double *K_half,
+                          int32_t n);
+
+/* 2-D only: lambda, mu, rho as filled at 2D-2nd :468-474, NX*NY values each. */
+int32_t cpml_set_material_2d(cpml_handle *h, const double *lambda, const double *mu,
+                             const double *rho);
+
+/* force_x(it), force_y(it) of :1058-1071 for it = 1..n (n <= NSTEP).  The kernel
+ * adds force*DELTAT/rho like :1080-1081. */
+int32_t cpml_set_source_series(cpml_handle *h, const double *force_x, const double *force_y,
+                               int32_t n);
+
+/* ix_rec, iy_rec of :691-706 (1-based), n == NREC. */
+int32_t cpml_set_receivers(cpml_handle *h, const int32_t *ix_rec, const int32_t *iy_rec,
+                           int32_t n);
+
+/* ---- the loop body -------------------------------------------------------- */
+
+/* Executes time steps it_begin..it_end (inclusive, 1-based) == the body of
+ * `do it` (:804-1180): stress update, velocity update, source, Dirichlet, seismogram
+ * sample, energy.  Single-slab handles only (nslabs == 1, or after cpml_attach_*).
+ * Returns after the stream has drained. */
+int32_t cpml_run(cpml_handle *h, int32_t it_begin, int32_t it_end);
+
+/* The same body in the pieces a slab-decomposed driver interleaves with its plane
+ * exchange (the MPI_SENDRECV calls at :811-823 and :951-963).  Asynchronous: they
+ * only enqueue work on the handle's stream.
+ *   cpml_step_stress   == :825-944
+ *   cpml_step_velocity == :965-1129 (+ per-block energy partials of :1131-1177)
+ *   cpml_step_finish   == finishes step `it`: energy sum of this slab, seismogram sample */
+int32_t cpml_step_stress(cpml_handle *h, int32_t it);
+int32_t cpml_step_velocity(cpml_handle *h, int32_t it);
+int32_t cpml_step_finish(cpml_handle *h, int32_t it);
+int32_t cpml_synchronize(cpml_handle *h);
+
+/* Device address and size of one z-plane of a field in the library's internal
+ * (padded) layout, klocal = 0..NZ_LOCAL+1 (0 and NZ_LOCAL+1 are the halo planes,
+ * 3D-iso :273).  Identical layout on every slab of the same grid, so a plane can be
+ * moved slab-to-slab with ncclSend/ncclRecv, cudaMemcpyPeer or CUDA-aware MPI. */
+int32_t cpml_halo_plane(cpml_handle *h, int32_t field, int32_t klocal,
+                        void **device_ptr, int64_t *nbytes);
+
+/* Copies plane klocal_src of `field` in slab `src` into plane klocal_dst of the same
+ * field in slab `dst` (device to device, cudaMemcpyPeerAsync on dst's stream after
+ * src's stream has drained).  This is one MPI_SENDRECV of :811-823 / :951-963 for a
+ * single-process driver that owns several slab handles (on one or several GPUs). */
+int32_t cpml_copy_plane(cpml_handle *dst, int32_t klocal_dst, cpml_handle *src, int32_t klocal_src,
+                        int32_t field);
+
+/* ---- outputs (device -> driver) ------------------------------------------- */
+
+/* sisvx, sisvy as declared at :286: (NSTEP,NREC) column-major, zero beyond the
+ * last executed step.  On a slab that does not own the receiver plane they are zero. */
+int32_t cpml_get_seismograms(cpml_handle *h, double *sisvx, double *sisvy);
+
+/* Energy traces, length NSTEP.  3-D: total = this slab's share of total_energy(it)
+ * (:1179 sums the shares); kinetic/potential may be NULL.  2-D: kinetic and
+ * potential are total_energy_kinetic/potential of 2D-2nd :211. */
+int32_t cpml_get_energy(cpml_handle *h, double *total, double *kinetic, double *potential);
+
+/* One (NX,NY) plane of a field at GLOBAL k (3-D) -- e.g. vx(:,:,NZ_LOCAL) handed to
+ * create_color_image at :1236 -- or the whole field (ndim==2, kglobal ignored).
+ * Returns CPML_EINVAL if this slab does not hold that plane. */
+int32_t cpml_get_plane(cpml_handle *h, int32_t field, int32_t kglobal, double *out);
+
+/* Whole field of this slab, (NX,NY,NZ_LOCAL) (3-D) or (NX,NY) (2-D), dense. */
+int32_t cpml_get_field(cpml_handle *h, int32_t field, double *out);
+
+/* maxval(sqrt(vx**2+vy**2+vz**2)) over this slab (:1185); the driver keeps the
+ * STABILITY_THRESHOLD test (:1195). */
+int32_t cpml_get_maxnorm(cpml_handle *h, double *out);
+
+/* Device time (ms, CUDA events on the handle's stream) spent in the stress and
+ * velocity kernels since the last call with reset != 0; n_launches counts kernels. */
+int32_t cpml_get_kernel_times(cpml_handle *h, double *ms_stress, double *ms_velocity,
+                              int64_t *n_launches, int32_t reset);
+int32_t cpml_enable_kernel_timing(cpml_handle *h, int32_t on);
+
+/* Algorithmic HBM bytes one full time step of this slab must move (each field read
+ * once / written once where updated, memory variables only inside the PML shells);
+ * DESIGN.md states the formula.  Also split per kernel. */
+int32_t cpml_algorithmic_bytes(cpml_handle *h, double *bytes_stress, double *bytes_velocity);
+
+/* ---- host-side helpers that mirror the reference's set-up phase ------------- */
+/* (pure host code, no device needed; the drivers in drivers/ use them)          */
+
+/* One axis of damping profiles, 3D-iso :399-667.  origin_top_uses_n=1 reproduces
+ * `yorigintop = NY*DELTAY - L` of 2D-4th :401; clamp_alpha=1 the x-axis clamp :514. */
+int32_t cpml_host_pml_profile(int32_t n, double delta, double deltat, int32_t npoints_pml,
+                              int32_t use_pml_min, int32_t use_pml_max,
+                              double cp, double rcoef, double npower,
+                              double k_max_pml, double alpha_max_pml,
+                              int32_t origin_top_uses_n, int32_t clamp_alpha,
+                              double *a, double *b, double *K,
+                              double *a_half, double *b_half, double *K_half);
+
+/* First-derivative-of-Gaussian source of :1058-1071 for it = 1..nstep. */
+int32_t cpml_host_source_series(int32_t nstep, double deltat, double f0, double t0,
+                                double factor, double angle_force_deg,
+                                double *force_x, double *force_y);
+
+/* Receiver line + nearest-grid-point search of :683-706. */
+int32_t cpml_host_find_receivers(int32_t nx, int32_t ny, double deltax, double deltay,
+                                 int32_t nrec, double xdeb, double ydeb, double xfin,
+                                 double yfin, int32_t *ix_rec, int32_t *iy_rec, double *dist);
+
+/* Courant number of :712 (deltaz <= 0 => 2-D form of 2D-2nd :513). */
+double cpml_host_courant(double cp, double deltat, double deltax, double deltay, double deltaz);
+
+/* Output writers with the reference's file names and column layout
+ * (write_seismograms :1330-1364; energy.dat :1253-1257 / 2D-2nd :741-746;
+ * create_color_image :1371-1509).  List-directed Fortran formatting is compiler
+ * specific; these write gnuplot-parsable text with the same columns. */
+int32_t cpml_host_write_seismograms(const char *dir, const double *sisvx, const double *sisvy,
+                                    int32_t nt, int32_t nrec, double deltat);
+int32_t cpml_host_write_energy_3d(const char *path, const double *total, int32_t nt,
+                                  double deltat);
+int32_t cpml_host_write_energy_2d(const char *path, const double *kinetic,
+                                  const double *potential, int32_t nt, double deltat);
+int32_t cpml_host_create_color_image(const char *dir, const double *image_data_2d,
+                                     int32_t nx, int32_t ny, int32_t it,
+                                     int32_t isource, int32_t jsource,
+                                     const int32_t *ix_rec, const int32_t *iy_rec, int32_t nrec,
+                                     int32_t npoints_pml, int32_t use_pml_xmin,
+                                     int32_t use_pml_xmax, int32_t use_pml_ymin,
+                                     int32_t use_pml_ymax, int32_t field_number);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPML_B200_H */

@@ -8,8 +8,9 @@
  *   /root/reference/seismic_CPML_3D_isotropic_MPI_OpenMP.f90     (3D-iso)
  * Golden build:  gcc -O2 -ffp-contract=off  (no FMA contraction: the reference
  * Makefile:36 builds with plain -O3 for baseline x86-64, which has no FMA).
- * Timed build:   gcc -O3 -march=native -fopenmp (cpu_baseline in bench.py).
+ * Timed build:   gcc -O3 -march=x86-64-v3 -fopenmp (cpu_baseline in bench.py).
  */
+#define _POSIX_C_SOURCE 199309L
 #include "cpml_oracle.h"
 
 #include <math.h>
@@ -24,6 +25,18 @@
 #endif
 
 #define PI 3.141592653589793238462643 /* 3D-iso :199 */
+
+#include <time.h>
+static int g_warmup_steps = 0;
+static double g_loop_seconds = 0.0;
+static double now_seconds(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+void oracle_set_warmup_steps(int w) { g_warmup_steps = w > 0 ? w : 0; }
+double oracle_last_loop_seconds(void) { return g_loop_seconds; }
 
 int oracle_num_threads(void)
 {
@@ -229,7 +242,9 @@ int oracle_run_2d(const oracle2d_config *cfg,
     const int eby0 = fourth ? NPOINTS_PML : NPOINTS_PML + 1;
     const int eby1 = fourth ? NY - NPOINTS_PML + 1 : NY - NPOINTS_PML;
 
+    double t_loop_start = now_seconds();
     for (int it = 1; it <= NSTEP; it++) {          /* 2D-2nd :550 */
+        if (it == g_warmup_steps + 1) t_loop_start = now_seconds();
 
         /* ---- sigma_xx, sigma_yy : 2D-2nd :556-580 ; 2D-4th :557-581 */
         for (int j = 2; j <= NY; j++) {
@@ -390,6 +405,8 @@ int oracle_run_2d(const oracle2d_config *cfg,
         }
     }
 
+    g_loop_seconds = now_seconds() - t_loop_start;
+
     if (velocnorm_final) {                          /* 2D-2nd :719 */
         double vmax = 0.0;
         for (size_t s = 0; s < N; s++) {
@@ -500,7 +517,9 @@ int oracle_run_3d_iso(const oracle3d_config *cfg,
     const int src_rank = NPROC > 1 ? rank_cut_plane : 0;
     const int src_klocal = NPROC > 1 ? NZ_LOCAL : NZ / 2;
 
+    double t_loop_start = now_seconds();
     for (int it = 1; it <= NSTEP; it++) {          /* :802 */
+        if (it == g_warmup_steps + 1) t_loop_start = now_seconds();
 
         /* ---- halo exchange of v : :810-823.  MPI_SENDRECV with MPI_PROC_NULL at the
          * ends leaves the end halos untouched (zero). */
@@ -756,6 +775,7 @@ int oracle_run_3d_iso(const oracle3d_config *cfg,
         }
         total_energy[it - 1] = energy_sum;
     }
+    g_loop_seconds = now_seconds() - t_loop_start;
 
     /* ---- results */
     if (plane_vx) memcpy(plane_vx, &F3(S[src_rank].vx, 1, 1, src_klocal), PLANE * sizeof(double)); /* :1236 */

@@ -127,6 +127,11 @@ int oracle_run_3d_iso(const oracle3d_config *cfg,
                       double *plane_vx, double *plane_vy,
                       double *fields_final, double *vnorm_final);
 
+/* Timing of the last oracle_run_* call: wall seconds of its time loop only (set-up and
+ * allocation excluded), not counting the first `w` warm-up steps. */
+void oracle_set_warmup_steps(int w);
+double oracle_last_loop_seconds(void);
+
 /* Number of OpenMP threads the timed build will use (1 if built without). */
 int oracle_num_threads(void);
 /* Flush-to-zero / denormals-are-zero for the timed CPU baseline (cf. the

@@ -5,7 +5,7 @@ legs may import this module.  PARITY UNPINNED -- see oracle/cpml_oracle.h.
 
 Two builds of the same C file (oracle/Makefile):
   golden -- gcc -O2 -ffp-contract=off, serial: the parity checker;
-  timed  -- gcc -O3 -march=native -fopenmp: the CPU baseline that is timed.
+  timed  -- gcc -O3 -march=x86-64-v3 -fopenmp: the CPU baseline that is timed.
 """
 from __future__ import annotations
 
@@ -72,6 +72,8 @@ def lib(kind: str = "golden") -> C.CDLL:
         L.oracle_run_3d_iso.argtypes = [C.POINTER(Oracle3DConfig)] + [_dp] * 18 + [_dp] * 2 + [_ip] * 2 \
             + [_dp] * 3 + [_dp] * 2 + [_dp] * 2
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_set_warmup_steps.argtypes = [C.c_int]
+        L.oracle_last_loop_seconds.restype = C.c_double
         L.oracle_set_ftz.argtypes = [C.c_int]
         _LIBS[kind] = L
     return _LIBS[kind]
@@ -196,3 +198,12 @@ def num_threads(kind="timed") -> int:
 
 def set_ftz(on: bool, kind="timed") -> None:
     lib(kind).oracle_set_ftz(int(on))
+
+
+def set_warmup_steps(w: int, kind="timed") -> None:
+    """The next run_* call excludes its first w steps from last_loop_seconds()."""
+    lib(kind).oracle_set_warmup_steps(int(w))
+
+
+def last_loop_seconds(kind="timed") -> float:
+    return lib(kind).oracle_last_loop_seconds()

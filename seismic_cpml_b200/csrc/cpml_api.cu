@@ -1,0 +1,767 @@
+// C ABI of libcpml_b200 (include/cpml_b200.h): handle life cycle, setters, the step
+// loop and the getters.  Host logic only; the device code is in kernels_{2d,3d}.cu.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cpml_internal.h"
+
+using namespace cpml;
+
+namespace {
+thread_local std::string g_create_error;
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+int env_int(const char *name, int dflt)
+{
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+}  // namespace
+
+struct cpml_handle {
+    cpml_config cfg{};
+    std::string err;
+    cudaStream_t stream = nullptr;
+    int device = 0;
+    int sm_count = 148;
+
+    // geometry of this slab
+    int nzl = 1, koff = 0, pitch = 0, ksrc_global = 0;
+    long long plane = 0;       // doubles per z plane (3-D) / whole padded field (2-D)
+    size_t field_doubles = 0;  // allocation size of one field
+    long long origin = 0;      // offset of element (1,1,0) / (1,1) inside the allocation
+    int nfields = 0;
+    double *field_alloc[9] = {};
+    double *f0[9] = {};        // element (1,1,0) / (1,1)
+
+    // profiles
+    bool have_prof[3] = {false, false, false};
+    std::vector<double> hprof[3][6];
+    double *dprof[3][6] = {};  // device copies, 0-based
+    Shell shell[3] = {};
+    int nz_own[3][2] = {};     // per axis: count of a != 0 (integer, half) -- algorithmic bytes
+
+    // memory variables
+    bool finalized = false;
+    int sxp = 0, sy = 0, zbase = 0, sz_local = 0;
+    double *mx[6] = {}, *my[6] = {}, *mz[6] = {};
+    size_t mx_doubles = 0, my_doubles = 0, mz_doubles = 0;
+
+    // 2-D material
+    double *mat[3] = {};       // lambda, mu, rho allocations (same layout as fields)
+    bool have_material = false;
+
+    // source / receivers / traces
+    double *d_src_x = nullptr, *d_src_y = nullptr;
+    bool have_source = false;
+    int *d_ix_rec = nullptr, *d_iy_rec = nullptr;
+    bool have_receivers = false;
+    double *d_sisvx = nullptr, *d_sisvy = nullptr, *d_ek = nullptr, *d_ep = nullptr;
+    double *d_partials = nullptr;
+    unsigned long long *d_maxbits = nullptr;
+
+    // launch geometry
+    dim3 grid, block;
+    int kchunk = 1, nblocks = 0;
+
+    // kernel timing
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;   // triples: start, after stress / start, after velocity
+    std::vector<int> ev_kind;
+    double ms_stress = 0, ms_velocity = 0;
+    long long n_launches = 0;
+};
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e__);                 \
+            return CPML_ECUDA;                                                            \
+        }                                                                                 \
+    } while (0)
+
+#define FAIL(code, msg)            \
+    do {                           \
+        h->err = (msg);            \
+        return (code);             \
+    } while (0)
+
+static Shell find_shell(const std::vector<double> *p, int n)
+{
+    // indices (1-based) where any coefficient is non-trivial: a != 0 or K != 1
+    std::vector<char> nt(n + 2, 0);
+    bool any = false;
+    for (int i = 1; i <= n; i++) {
+        nt[i] = (p[0][i - 1] != 0.0) || (p[3][i - 1] != 0.0) || (p[2][i - 1] != 1.0) || (p[5][i - 1] != 1.0);
+        any = any || nt[i];
+    }
+    Shell s{0, n + 1, n};
+    if (!any) return s;
+    // the longest run of trivial indices separates the low shell from the high shell
+    int best_len = -1, best_start = 1, run_start = -1;
+    for (int i = 1; i <= n + 1; i++) {
+        const bool triv = (i <= n) && !nt[i];
+        if (triv && run_start < 0) run_start = i;
+        if (!triv && run_start >= 0) {
+            if (i - run_start > best_len) { best_len = i - run_start; best_start = run_start; }
+            run_start = -1;
+        }
+    }
+    if (best_len <= 0) { s.lo = n; s.hi = n + 1; return s; }   // no trivial index at all
+    s.lo = best_start - 1;
+    s.hi = best_start + best_len;
+    return s;
+}
+
+extern "C" int32_t cpml_abi_version(void) { return CPML_B200_ABI_VERSION; }
+
+extern "C" const char *cpml_last_error(const cpml_handle *h)
+{
+    return h ? h->err.c_str() : g_create_error.c_str();
+}
+
+static int32_t create_impl(cpml_handle *h)
+{
+    const cpml_config &c = h->cfg;
+    if (c.ndim != 2 && c.ndim != 3) FAIL(CPML_EINVAL, "ndim must be 2 or 3");
+    if (c.ndim == 3 && c.order != 2) FAIL(CPML_EINVAL, "3-D isotropic solver is second order (order must be 2)");
+    if (c.ndim == 2 && c.order != 2 && c.order != 4) FAIL(CPML_EINVAL, "order must be 2 or 4");
+    if (c.nx < 4 || c.ny < 4 || (c.ndim == 3 && c.nz < 4)) FAIL(CPML_EINVAL, "grid too small");
+    if (c.nstep < 1 || c.nrec < 0 || c.npoints_pml < 0) FAIL(CPML_EINVAL, "bad nstep / nrec / npoints_pml");
+    if (c.isource < 1 || c.isource > c.nx || c.jsource < 1 || c.jsource > c.ny) FAIL(CPML_EINVAL, "source outside the grid");
+    if (!(c.deltax > 0) || !(c.deltay > 0) || !(c.deltat > 0)) FAIL(CPML_EINVAL, "DELTAX, DELTAY, DELTAT must be positive");
+
+    if (c.ndim == 3) {
+        if (!(c.deltaz > 0)) FAIL(CPML_EINVAL, "DELTAZ must be positive");
+        if (!(c.rho > 0) || !(c.mu > 0)) FAIL(CPML_EINVAL, "rho and mu must be positive");
+        // topology checks of 3D-iso :381-394 (evenness only matters for the default
+        // cut plane, so it is required only when ksource is left to NZ/2)
+        if (c.nslabs < 1 || c.slab_rank < 0 || c.slab_rank >= c.nslabs) FAIL(CPML_ETOPOLOGY, "bad nslabs / slab_rank");
+        if (c.nz % c.nslabs != 0) FAIL(CPML_ETOPOLOGY, "NZ must be a multiple of nb_procs");
+        h->nzl = c.nz / c.nslabs;
+        if (h->nzl < c.npoints_pml) FAIL(CPML_ETOPOLOGY, "NZ_LOCAL must be greater than NPOINTS_PML");
+        if (c.ksource == 0 && c.nslabs > 1 && c.nslabs % 2 != 0) FAIL(CPML_ETOPOLOGY, "nb_procs must be even");
+        h->ksrc_global = c.ksource == 0 ? c.nz / 2 : c.ksource;
+        if (h->ksrc_global < 1 || h->ksrc_global > c.nz) FAIL(CPML_EINVAL, "ksource outside the grid");
+        h->koff = c.slab_rank * h->nzl;
+    } else {
+        if (c.nslabs > 1) FAIL(CPML_ETOPOLOGY, "2-D solvers are not decomposed");
+        h->nzl = 1;
+        h->koff = 0;
+    }
+    if (c.cp > 0) {   // Courant check, 3D-iso :712-717 / 2D-2nd :513-516
+        const double cn = cpml_host_courant(c.cp, c.deltat, c.deltax, c.deltay, c.ndim == 3 ? c.deltaz : 0.0);
+        if (cn > 1.0) FAIL(CPML_ECFL, "time step is too large, simulation will be unstable");
+    }
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        FAIL(CPML_ECUDA, "no CUDA device: libcpml_b200 has no CPU fallback");
+    if (c.device >= 0) { CK(cudaSetDevice(c.device)); }
+    CK(cudaGetDevice(&h->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    h->sm_count = prop.multiProcessorCount;
+
+    // ---- field layout
+    if (c.ndim == 3) {
+        h->pitch = round_up(c.nx, 16);
+        h->plane = (long long)h->pitch * c.ny;
+        h->origin = 16;   // leading pad so that (i-1) at the first element stays inside
+        h->field_doubles = (size_t)h->plane * (h->nzl + 2) + 32 + (size_t)h->pitch;
+        h->nfields = 9;
+    } else {
+        const int xo = 16, gy = 2;
+        h->pitch = round_up(xo + c.nx + 2, 16);
+        h->plane = (long long)h->pitch * (c.ny + 2 * gy);
+        h->origin = (long long)gy * h->pitch + xo;
+        h->field_doubles = (size_t)h->plane + 16;
+        h->nfields = 5;
+    }
+    for (int f = 0; f < h->nfields; f++) {
+        CK(cudaMalloc(&h->field_alloc[f], h->field_doubles * sizeof(double)));
+        h->f0[f] = h->field_alloc[f] + h->origin;
+    }
+    if (c.ndim == 2)
+        for (int m = 0; m < 3; m++) CK(cudaMalloc(&h->mat[m], h->field_doubles * sizeof(double)));
+
+    const size_t nt = (size_t)c.nstep;
+    CK(cudaMalloc(&h->d_src_x, nt * sizeof(double)));
+    CK(cudaMalloc(&h->d_src_y, nt * sizeof(double)));
+    CK(cudaMalloc(&h->d_ek, nt * sizeof(double)));
+    CK(cudaMalloc(&h->d_ep, nt * sizeof(double)));
+    const size_t ns = std::max<size_t>(1, nt * (size_t)c.nrec);
+    CK(cudaMalloc(&h->d_sisvx, ns * sizeof(double)));
+    CK(cudaMalloc(&h->d_sisvy, ns * sizeof(double)));
+    CK(cudaMalloc(&h->d_ix_rec, std::max(1, c.nrec) * sizeof(int)));
+    CK(cudaMalloc(&h->d_iy_rec, std::max(1, c.nrec) * sizeof(int)));
+    CK(cudaMalloc(&h->d_maxbits, sizeof(unsigned long long)));
+
+    // ---- launch geometry (CPML_TX / CPML_TY / CPML_ZCHUNKS override for tuning)
+    if (c.ndim == 3) {
+        const int tx = env_int("CPML_TX", 32), ty = env_int("CPML_TY", 8);
+        h->block = dim3(tx, ty, 1);
+        const int gx = (c.nx + tx - 1) / tx, gy = (c.ny + ty - 1) / ty;
+        int zch = env_int("CPML_ZCHUNKS", 0);
+        if (zch <= 0) {
+            // enough blocks for ~4 waves of resident CTAs, but keep chunks >= 16 planes so
+            // that the register-carried z reuse pays for the extra plane at chunk starts
+            const int resident = h->sm_count * std::max(1, 2048 / (tx * ty));
+            zch = (4 * resident + gx * gy - 1) / (gx * gy);
+            zch = std::max(1, std::min(zch, std::max(1, h->nzl / 16)));
+        }
+        zch = std::max(1, std::min(zch, h->nzl));
+        h->kchunk = (h->nzl + zch - 1) / zch;
+        zch = (h->nzl + h->kchunk - 1) / h->kchunk;
+        h->grid = dim3(gx, gy, zch);
+    } else {
+        h->block = dim3(32, 8, 1);
+        h->grid = dim3((c.nx + 31) / 32, (c.ny + 7) / 8, 1);
+        h->kchunk = 1;
+    }
+    h->nblocks = h->grid.x * h->grid.y * h->grid.z;
+    CK(cudaMalloc(&h->d_partials, 2 * (size_t)h->nblocks * sizeof(double)));
+    return cpml_reset(h);
+}
+
+extern "C" int32_t cpml_create(const cpml_config *cfg, cpml_handle **out)
+{
+    if (out) *out = nullptr;
+    if (!cfg || !out) { g_create_error = "null argument"; return CPML_EINVAL; }
+    cpml_handle *h = new (std::nothrow) cpml_handle();
+    if (!h) { g_create_error = "out of host memory"; return CPML_ENOMEM; }
+    h->cfg = *cfg;
+    const int32_t rc = create_impl(h);
+    if (rc != CPML_OK) {
+        g_create_error = h->err;
+        cpml_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_destroy(cpml_handle *h)
+{
+    if (!h) return CPML_OK;
+    cudaSetDevice(h->device);
+    for (auto &p : h->field_alloc) cudaFree(p);
+    for (auto &p : h->mat) cudaFree(p);
+    for (auto &ax : h->dprof) for (auto &p : ax) cudaFree(p);
+    for (auto &p : h->mx) cudaFree(p);
+    for (auto &p : h->my) cudaFree(p);
+    for (auto &p : h->mz) cudaFree(p);
+    cudaFree(h->d_src_x); cudaFree(h->d_src_y); cudaFree(h->d_ix_rec); cudaFree(h->d_iy_rec);
+    cudaFree(h->d_sisvx); cudaFree(h->d_sisvy); cudaFree(h->d_ek); cudaFree(h->d_ep);
+    cudaFree(h->d_partials); cudaFree(h->d_maxbits);
+    for (auto e : h->ev) cudaEventDestroy(e);
+    delete h;
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_reset(cpml_handle *h)
+{
+    if (!h) return CPML_EINVAL;
+    const cpml_config &c = h->cfg;
+    CK(cudaSetDevice(h->device));
+    for (int f = 0; f < h->nfields; f++)
+        CK(cudaMemsetAsync(h->field_alloc[f], 0, h->field_doubles * sizeof(double), h->stream));
+    if (h->finalized) {
+        for (int m = 0; m < 6; m++) {
+            if (h->mx[m]) CK(cudaMemsetAsync(h->mx[m], 0, h->mx_doubles * sizeof(double), h->stream));
+            if (h->my[m]) CK(cudaMemsetAsync(h->my[m], 0, h->my_doubles * sizeof(double), h->stream));
+            if (h->mz[m]) CK(cudaMemsetAsync(h->mz[m], 0, h->mz_doubles * sizeof(double), h->stream));
+        }
+    }
+    const size_t nt = (size_t)c.nstep;
+    CK(cudaMemsetAsync(h->d_ek, 0, nt * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->d_ep, 0, nt * sizeof(double), h->stream));
+    const size_t ns = std::max<size_t>(1, nt * (size_t)c.nrec);
+    CK(cudaMemsetAsync(h->d_sisvx, 0, ns * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->d_sisvy, 0, ns * sizeof(double), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_set_stream(cpml_handle *h, void *cuda_stream)
+{
+    if (!h) return CPML_EINVAL;
+    h->stream = (cudaStream_t)cuda_stream;
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_set_profiles(cpml_handle *h, int32_t axis, const double *a, const double *b,
+                                     const double *K, const double *a_half, const double *b_half,
+                                     const double *K_half, int32_t n)
+{
+    if (!h) return CPML_EINVAL;
+    const cpml_config &c = h->cfg;
+    if (axis < 0 || axis > 2 || (axis == 2 && c.ndim == 2)) FAIL(CPML_EINVAL, "bad axis");
+    const int want = axis == 0 ? c.nx : axis == 1 ? c.ny : c.nz;
+    if (n != want) FAIL(CPML_EINVAL, "profile length must be NX, NY or the global NZ");
+    if (!a || !b || !K || !a_half || !b_half || !K_half) FAIL(CPML_EINVAL, "null profile");
+    if (h->finalized) FAIL(CPML_ESTATE, "profiles cannot change after the first time step (cpml_reset keeps them)");
+    CK(cudaSetDevice(h->device));
+    const double *src[6] = {a, b, K, a_half, b_half, K_half};
+    for (int q = 0; q < 6; q++) {
+        h->hprof[axis][q].assign(src[q], src[q] + n);
+        for (int i = 0; i < n; i++)
+            if (!std::isfinite(src[q][i])) FAIL(CPML_EINVAL, "non-finite profile value");
+        if (q == 2 || q == 5)
+            for (int i = 0; i < n; i++)
+                if (src[q][i] == 0.0) FAIL(CPML_EINVAL, "K profile contains zero");
+        if (!h->dprof[axis][q]) CK(cudaMalloc(&h->dprof[axis][q], (size_t)n * sizeof(double)));
+        CK(cudaMemcpy(h->dprof[axis][q], src[q], (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    h->shell[axis] = find_shell(h->hprof[axis], n);
+    h->have_prof[axis] = true;
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_set_material_2d(cpml_handle *h, const double *lambda, const double *mu, const double *rho)
+{
+    if (!h) return CPML_EINVAL;
+    const cpml_config &c = h->cfg;
+    if (c.ndim != 2) FAIL(CPML_EINVAL, "cpml_set_material_2d is for the 2-D solvers");
+    if (!lambda || !mu || !rho) FAIL(CPML_EINVAL, "null material array");
+    CK(cudaSetDevice(h->device));
+    const double *src[3] = {lambda, mu, rho};
+    for (int m = 0; m < 3; m++) {
+        CK(cudaMemset(h->mat[m], 0, h->field_doubles * sizeof(double)));
+        CK(cudaMemcpy2D(h->mat[m] + h->origin, (size_t)h->pitch * sizeof(double), src[m],
+                        (size_t)c.nx * sizeof(double), (size_t)c.nx * sizeof(double), c.ny,
+                        cudaMemcpyHostToDevice));
+    }
+    h->have_material = true;
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_set_source_series(cpml_handle *h, const double *force_x, const double *force_y, int32_t n)
+{
+    if (!h) return CPML_EINVAL;
+    const cpml_config &c = h->cfg;
+    if (!force_x || !force_y || n < 1 || n > c.nstep) FAIL(CPML_EINVAL, "bad source series");
+    CK(cudaSetDevice(h->device));
+    std::vector<double> sx(force_x, force_x + n), sy(force_y, force_y + n);
+    if (c.ndim == 3) {
+        // the increment of :1080-1081, force * DELTAT / rho, in the reference's order
+        for (int q = 0; q < n; q++) {
+            sx[q] = force_x[q] * c.deltat / c.rho;
+            sy[q] = force_y[q] * c.deltat / c.rho;
+        }
+    }
+    CK(cudaMemcpyAsync(h->d_src_x, sx.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_src_y, sy.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_source = true;
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_set_receivers(cpml_handle *h, const int32_t *ix_rec, const int32_t *iy_rec, int32_t n)
+{
+    if (!h) return CPML_EINVAL;
+    const cpml_config &c = h->cfg;
+    if (n != c.nrec) FAIL(CPML_EINVAL, "n must equal NREC");
+    if (n > 0 && (!ix_rec || !iy_rec)) FAIL(CPML_EINVAL, "null receiver arrays");
+    for (int r = 0; r < n; r++)
+        if (ix_rec[r] < 1 || ix_rec[r] > c.nx || iy_rec[r] < 1 || iy_rec[r] > c.ny)
+            FAIL(CPML_EINVAL, "receiver outside the grid");
+    CK(cudaSetDevice(h->device));
+    if (n > 0) {
+        CK(cudaMemcpy(h->d_ix_rec, ix_rec, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->d_iy_rec, iy_rec, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    h->have_receivers = true;
+    return CPML_OK;
+}
+
+// Allocates the shell-only memory variables once every input is known.
+static int32_t finalize(cpml_handle *h)
+{
+    if (h->finalized) return CPML_OK;
+    const cpml_config &c = h->cfg;
+    const int naxes = c.ndim;
+    for (int ax = 0; ax < naxes; ax++)
+        if (!h->have_prof[ax]) FAIL(CPML_ESTATE, "cpml_set_profiles has not been called for every axis");
+    if (!h->have_source) FAIL(CPML_ESTATE, "cpml_set_source_series has not been called");
+    if (c.nrec > 0 && !h->have_receivers) FAIL(CPML_ESTATE, "cpml_set_receivers has not been called");
+    if (c.ndim == 2 && !h->have_material) FAIL(CPML_ESTATE, "cpml_set_material_2d has not been called");
+    CK(cudaSetDevice(h->device));
+
+    const Shell &sx = h->shell[0], &sy = h->shell[1];
+    h->sxp = std::max(4, round_up(sx.size(), 4));
+    h->sy = std::max(1, sy.size());
+    const int nmem = c.ndim == 3 ? 6 : 4;
+    h->mx_doubles = (size_t)h->sxp * c.ny * h->nzl;
+    h->my_doubles = (size_t)h->pitch * h->sy * h->nzl;
+    for (int m = 0; m < nmem; m++) {
+        CK(cudaMalloc(&h->mx[m], h->mx_doubles * sizeof(double)));
+        CK(cudaMalloc(&h->my[m], h->my_doubles * sizeof(double)));
+        CK(cudaMemset(h->mx[m], 0, h->mx_doubles * sizeof(double)));
+        CK(cudaMemset(h->my[m], 0, h->my_doubles * sizeof(double)));
+    }
+    if (c.ndim == 3) {
+        const Shell &sz = h->shell[2];
+        int first = -1, last = -2;
+        for (int k = 1; k <= h->nzl; k++) {
+            const int kg = k + h->koff;
+            if (kg <= sz.lo || kg >= sz.hi) {
+                const int s = kg <= sz.lo ? kg - 1 : sz.lo + (kg - sz.hi);
+                if (first < 0) first = s;
+                last = s;
+            }
+        }
+        h->zbase = std::max(0, first);
+        h->sz_local = first < 0 ? 0 : last - first + 1;
+        h->mz_doubles = (size_t)h->pitch * c.ny * std::max(1, h->sz_local);
+        for (int m = 0; m < 6; m++) {
+            CK(cudaMalloc(&h->mz[m], h->mz_doubles * sizeof(double)));
+            CK(cudaMemset(h->mz[m], 0, h->mz_doubles * sizeof(double)));
+        }
+    }
+    // own non-zero counts per axis (for cpml_algorithmic_bytes)
+    for (int ax = 0; ax < naxes; ax++) {
+        int n0 = 0, n1 = 0;
+        const int n = (int)h->hprof[ax][0].size();
+        int lo = 1, hi = n;
+        if (ax == 2) { lo = h->koff + 1; hi = h->koff + h->nzl; }
+        for (int i = lo; i <= hi; i++) {
+            n0 += (h->hprof[ax][0][i - 1] != 0.0) || (h->hprof[ax][2][i - 1] != 1.0);
+            n1 += (h->hprof[ax][3][i - 1] != 0.0) || (h->hprof[ax][5][i - 1] != 1.0);
+        }
+        h->nz_own[ax][0] = n0;
+        h->nz_own[ax][1] = n1;
+    }
+    h->finalized = true;
+    return CPML_OK;
+}
+
+static AxisCoef coef_view(cpml_handle *h, int ax)
+{
+    // 1-based views: index i addresses element i-1 of the device array
+    AxisCoef c;
+    c.a = h->dprof[ax][0] - 1; c.b = h->dprof[ax][1] - 1; c.K = h->dprof[ax][2] - 1;
+    c.a_half = h->dprof[ax][3] - 1; c.b_half = h->dprof[ax][4] - 1; c.K_half = h->dprof[ax][5] - 1;
+    return c;
+}
+
+static Params3D make_p3(cpml_handle *h, int it)
+{
+    const cpml_config &c = h->cfg;
+    Params3D p{};
+    p.nx = c.nx; p.ny = c.ny; p.nzl = h->nzl; p.nz = c.nz; p.koff = h->koff;
+    p.pitch = h->pitch; p.plane = h->plane; p.kchunk = h->kchunk;
+    p.vx = h->f0[0]; p.vy = h->f0[1]; p.vz = h->f0[2];
+    p.sxx = h->f0[3]; p.syy = h->f0[4]; p.szz = h->f0[5];
+    p.sxy = h->f0[6]; p.sxz = h->f0[7]; p.syz = h->f0[8];
+    p.xlo = h->shell[0].lo; p.xhi = h->shell[0].hi; p.sxp = h->sxp;
+    p.ylo = h->shell[1].lo; p.yhi = h->shell[1].hi; p.sy = h->sy;
+    p.zlo = h->shell[2].lo; p.zhi = h->shell[2].hi; p.zbase = h->zbase;
+    for (int m = 0; m < 6; m++) { p.mx[m] = h->mx[m]; p.my[m] = h->my[m]; p.mz[m] = h->mz[m]; }
+    p.cx = coef_view(h, 0); p.cy = coef_view(h, 1); p.cz = coef_view(h, 2);
+    p.odx = 1.0 / c.deltax; p.ody = 1.0 / c.deltay; p.odz = 1.0 / c.deltaz;   // :134-136
+    p.dt_lambda = c.deltat * c.lambda;                                        // :296-300
+    p.dt_mu = c.deltat * c.mu;
+    p.dt_lambdaplus2mu = c.deltat * c.lambdaplustwomu;
+    p.dt_over_rho = c.deltat / c.rho;
+    p.it = it;
+    p.isrc = c.isource; p.jsrc = c.jsource;
+    const int kl = h->ksrc_global - h->koff;
+    p.ksrc = (kl >= 1 && kl <= h->nzl) ? kl : 0;
+    p.src_x = h->d_src_x; p.src_y = h->d_src_y;
+    p.npml = c.npoints_pml; p.energy_bug_compat = c.energy_bug_compat;
+    p.rho = c.rho; p.lambda = c.lambda; p.mu = c.mu;
+    p.partials = h->d_partials; p.nblocks = h->nblocks;
+    return p;
+}
+
+static Params2D make_p2(cpml_handle *h, int it)
+{
+    const cpml_config &c = h->cfg;
+    Params2D p{};
+    p.nx = c.nx; p.ny = c.ny; p.pitch = h->pitch; p.order = c.order;
+    p.vx = h->f0[0]; p.vy = h->f0[1]; p.sxx = h->f0[2]; p.syy = h->f0[3]; p.sxy = h->f0[4];
+    p.lambda = h->mat[0] + h->origin; p.mu = h->mat[1] + h->origin; p.rho = h->mat[2] + h->origin;
+    p.xlo = h->shell[0].lo; p.xhi = h->shell[0].hi; p.sxp = h->sxp;
+    p.ylo = h->shell[1].lo; p.yhi = h->shell[1].hi; p.sy = h->sy;
+    for (int m = 0; m < 4; m++) { p.mx[m] = h->mx[m]; p.my[m] = h->my[m]; }
+    p.cx = coef_view(h, 0); p.cy = coef_view(h, 1);
+    p.deltax = c.deltax; p.deltay = c.deltay; p.deltat = c.deltat;
+    p.it = it; p.isrc = c.isource; p.jsrc = c.jsource;
+    p.force_x = h->d_src_x; p.force_y = h->d_src_y;
+    p.npml = c.npoints_pml;
+    p.partials = h->d_partials; p.nblocks = h->nblocks;
+    return p;
+}
+
+static int32_t time_begin(cpml_handle *h, int kind)
+{
+    if (!h->timing) return CPML_OK;
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    h->ev.push_back(a); h->ev.push_back(b); h->ev_kind.push_back(kind);
+    CK(cudaEventRecord(a, h->stream));
+    return CPML_OK;
+}
+static int32_t time_end(cpml_handle *h)
+{
+    if (!h->timing) return CPML_OK;
+    CK(cudaEventRecord(h->ev.back(), h->stream));
+    return CPML_OK;
+}
+
+static int32_t check_it(cpml_handle *h, int it)
+{
+    if (it < 1 || it > h->cfg.nstep) FAIL(CPML_EINVAL, "time step outside 1..NSTEP");
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_step_stress(cpml_handle *h, int32_t it)
+{
+    if (!h) return CPML_EINVAL;
+    int32_t rc = check_it(h, it); if (rc) return rc;
+    rc = finalize(h); if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    rc = time_begin(h, 0); if (rc) return rc;
+    if (h->cfg.ndim == 3) launch_stress3d(make_p3(h, it), h->grid, h->block, h->stream);
+    else                  launch_stress2d(make_p2(h, it), h->grid, h->block, h->stream);
+    h->n_launches++;
+    rc = time_end(h); if (rc) return rc;
+    CK(cudaGetLastError());
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_step_velocity(cpml_handle *h, int32_t it)
+{
+    if (!h) return CPML_EINVAL;
+    int32_t rc = check_it(h, it); if (rc) return rc;
+    rc = finalize(h); if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    rc = time_begin(h, 1); if (rc) return rc;
+    if (h->cfg.ndim == 3) launch_velocity3d(make_p3(h, it), h->grid, h->block, h->stream);
+    else                  launch_velocity2d(make_p2(h, it), h->grid, h->block, h->stream);
+    h->n_launches++;
+    rc = time_end(h); if (rc) return rc;
+    CK(cudaGetLastError());
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_step_finish(cpml_handle *h, int32_t it)
+{
+    if (!h) return CPML_EINVAL;
+    int32_t rc = check_it(h, it); if (rc) return rc;
+    rc = finalize(h); if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    const cpml_config &c = h->cfg;
+    Post3D p{};
+    p.partials = h->d_partials; p.nblocks = h->nblocks;
+    p.energy_k = h->d_ek; p.energy_p = h->d_ep;
+    p.it = it; p.nstep = c.nstep; p.nrec = c.nrec;
+    p.ix_rec = h->d_ix_rec; p.iy_rec = h->d_iy_rec;
+    p.vx = h->f0[0]; p.vy = h->f0[1];
+    p.pitch = h->pitch;
+    if (c.ndim == 3) {
+        p.plane = h->plane;
+        const int kl = h->ksrc_global - h->koff;
+        p.krec = (kl >= 1 && kl <= h->nzl) ? kl : 0;
+    } else {
+        p.plane = 0;
+        p.krec = 1;
+    }
+    p.sisvx = h->d_sisvx; p.sisvy = h->d_sisvy;
+    launch_post3d(p, h->stream);
+    h->n_launches++;
+    CK(cudaGetLastError());
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_synchronize(cpml_handle *h)
+{
+    if (!h) return CPML_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_run(cpml_handle *h, int32_t it_begin, int32_t it_end)
+{
+    if (!h) return CPML_EINVAL;
+    if (h->cfg.nslabs != 1) FAIL(CPML_ESTATE, "cpml_run needs the whole grid on one device; slab drivers interleave cpml_step_* with their plane exchange");
+    if (it_begin < 1 || it_end > h->cfg.nstep || it_begin > it_end) FAIL(CPML_EINVAL, "bad time step range");
+    for (int it = it_begin; it <= it_end; it++) {
+        int32_t rc = cpml_step_stress(h, it); if (rc) return rc;
+        rc = cpml_step_velocity(h, it); if (rc) return rc;
+        rc = cpml_step_finish(h, it); if (rc) return rc;
+    }
+    return cpml_synchronize(h);
+}
+
+extern "C" int32_t cpml_halo_plane(cpml_handle *h, int32_t field, int32_t klocal, void **device_ptr, int64_t *nbytes)
+{
+    if (!h) return CPML_EINVAL;
+    if (h->cfg.ndim != 3) FAIL(CPML_EINVAL, "halo planes exist only in 3-D");
+    if (field < 0 || field >= 9 || klocal < 0 || klocal > h->nzl + 1 || !device_ptr || !nbytes) FAIL(CPML_EINVAL, "bad halo plane request");
+    *device_ptr = (void *)(h->f0[field] + (long long)klocal * h->plane);
+    *nbytes = (int64_t)h->plane * (int64_t)sizeof(double);
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_copy_plane(cpml_handle *dst, int32_t klocal_dst, cpml_handle *src, int32_t klocal_src, int32_t field)
+{
+    if (!dst || !src) return CPML_EINVAL;
+    cpml_handle *h = dst;
+    if (dst->cfg.ndim != 3 || src->cfg.ndim != 3) FAIL(CPML_EINVAL, "plane copies exist only in 3-D");
+    if (dst->plane != src->plane || dst->cfg.nx != src->cfg.nx || dst->cfg.ny != src->cfg.ny) FAIL(CPML_EINVAL, "slabs of different grids");
+    if (field < 0 || field >= 9 || klocal_dst < 0 || klocal_dst > dst->nzl + 1 || klocal_src < 0 || klocal_src > src->nzl + 1)
+        FAIL(CPML_EINVAL, "bad plane copy request");
+    CK(cudaSetDevice(src->device));
+    CK(cudaStreamSynchronize(src->stream));
+    CK(cudaSetDevice(dst->device));
+    CK(cudaMemcpyPeerAsync(dst->f0[field] + (long long)klocal_dst * dst->plane, dst->device,
+                           src->f0[field] + (long long)klocal_src * src->plane, src->device,
+                           (size_t)dst->plane * sizeof(double), dst->stream));
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_get_seismograms(cpml_handle *h, double *sisvx, double *sisvy)
+{
+    if (!h || !sisvx || !sisvy) return CPML_EINVAL;
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->cfg.nstep * (size_t)h->cfg.nrec;
+    if (n == 0) return CPML_OK;
+    CK(cudaMemcpyAsync(sisvx, h->d_sisvx, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(sisvy, h->d_sisvy, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_get_energy(cpml_handle *h, double *total, double *kinetic, double *potential)
+{
+    if (!h) return CPML_EINVAL;
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->cfg.nstep;
+    std::vector<double> ek(n), ep(n);
+    CK(cudaMemcpyAsync(ek.data(), h->d_ek, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(ep.data(), h->d_ep, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (size_t q = 0; q < n; q++) {
+        if (total) total[q] = ek[q] + ep[q];       // :1179 sums kinetic + potential
+        if (kinetic) kinetic[q] = ek[q];
+        if (potential) potential[q] = ep[q];
+    }
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_get_plane(cpml_handle *h, int32_t field, int32_t kglobal, double *out)
+{
+    if (!h || !out) return CPML_EINVAL;
+    const cpml_config &c = h->cfg;
+    if (field < 0 || field >= h->nfields) FAIL(CPML_EINVAL, "bad field id");
+    CK(cudaSetDevice(h->device));
+    long long off = 0;
+    if (c.ndim == 3) {
+        const int kl = kglobal - h->koff;
+        if (kl < 1 || kl > h->nzl) FAIL(CPML_EINVAL, "this slab does not hold that plane");
+        off = (long long)kl * h->plane;
+    }
+    CK(cudaMemcpy2DAsync(out, (size_t)c.nx * sizeof(double), h->f0[field] + off, (size_t)h->pitch * sizeof(double),
+                         (size_t)c.nx * sizeof(double), c.ny, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_get_field(cpml_handle *h, int32_t field, double *out)
+{
+    if (!h || !out) return CPML_EINVAL;
+    const cpml_config &c = h->cfg;
+    if (field < 0 || field >= h->nfields) FAIL(CPML_EINVAL, "bad field id");
+    CK(cudaSetDevice(h->device));
+    if (c.ndim == 2) return cpml_get_plane(h, field, 0, out);
+    // rows of all owned planes are equally spaced (plane = pitch * ny): one 2-D copy
+    CK(cudaMemcpy2DAsync(out, (size_t)c.nx * sizeof(double), h->f0[field] + h->plane, (size_t)h->pitch * sizeof(double),
+                         (size_t)c.nx * sizeof(double), (size_t)c.ny * h->nzl, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_get_maxnorm(cpml_handle *h, double *out)
+{
+    if (!h || !out) return CPML_EINVAL;
+    const cpml_config &c = h->cfg;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemsetAsync(h->d_maxbits, 0, sizeof(unsigned long long), h->stream));
+    if (c.ndim == 3)
+        launch_maxnorm(h->f0[0] + h->plane, h->f0[1] + h->plane, h->f0[2] + h->plane, h->plane * h->nzl, h->d_maxbits, h->stream);
+    else
+        launch_maxnorm(h->field_alloc[0], h->field_alloc[1], nullptr, (long long)h->field_doubles, h->d_maxbits, h->stream);
+    h->n_launches++;
+    unsigned long long bits = 0;
+    CK(cudaMemcpyAsync(&bits, h->d_maxbits, sizeof(bits), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(out, &bits, sizeof(double));
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_enable_kernel_timing(cpml_handle *h, int32_t on)
+{
+    if (!h) return CPML_EINVAL;
+    h->timing = on != 0;
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_get_kernel_times(cpml_handle *h, double *ms_stress, double *ms_velocity, int64_t *n_launches, int32_t reset)
+{
+    if (!h) return CPML_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    for (size_t q = 0; q < h->ev_kind.size(); q++) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->ev[2 * q], h->ev[2 * q + 1]));
+        (h->ev_kind[q] == 0 ? h->ms_stress : h->ms_velocity) += ms;
+    }
+    for (auto e : h->ev) cudaEventDestroy(e);
+    h->ev.clear(); h->ev_kind.clear();
+    if (ms_stress) *ms_stress = h->ms_stress;
+    if (ms_velocity) *ms_velocity = h->ms_velocity;
+    if (n_launches) *n_launches = h->n_launches;
+    if (reset) { h->ms_stress = h->ms_velocity = 0; h->n_launches = 0; }
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_algorithmic_bytes(cpml_handle *h, double *bytes_stress, double *bytes_velocity)
+{
+    if (!h) return CPML_EINVAL;
+    int32_t rc = finalize(h); if (rc) return rc;
+    const cpml_config &c = h->cfg;
+    const double N = (double)c.nx * c.ny * h->nzl;
+    const int (*nz)[2] = h->nz_own;
+    double ws, wv;   // words
+    if (c.ndim == 3) {
+        // stress: read vx,vy,vz; read+write 6 sigma; memory variables per direction:
+        //   x: dvx_dx (half), dvy_dx, dvz_dx (integer)   y: dvy_dy (int), dvx_dy, dvz_dy (half)
+        //   z: dvz_dz (int), dvx_dz, dvy_dz (half)        -- each read + written
+        const double px = (double)c.ny * h->nzl, py = (double)c.nx * h->nzl, pz = (double)c.nx * c.ny;
+        ws = 15.0 * N + 2.0 * (px * (nz[0][1] + 2 * nz[0][0]) + py * (nz[1][0] + 2 * nz[1][1]) + pz * (nz[2][0] + 2 * nz[2][1]));
+        // velocity: read 6 sigma; read+write vx,vy,vz; memory variables:
+        //   x: dsxx_dx (int), dsxy_dx, dsxz_dx (half)    y: dsxy_dy, dsyz_dy (int), dsyy_dy (half)
+        //   z: dsxz_dz, dsyz_dz (int), dszz_dz (half)
+        wv = 12.0 * N + 2.0 * (px * (nz[0][0] + 2 * nz[0][1]) + py * (2 * nz[1][0] + nz[1][1]) + pz * (2 * nz[2][0] + nz[2][1]));
+    } else {
+        // stress: read vx,vy, lambda, mu; read+write 3 sigma; x: dvx_dx (half), dvy_dx (int); y: dvy_dy (int), dvx_dy (half)
+        const double px = (double)c.ny, py = (double)c.nx;
+        ws = 10.0 * N + 2.0 * (px * (nz[0][0] + nz[0][1]) + py * (nz[1][0] + nz[1][1]));
+        // velocity: read 3 sigma, rho, (lambda, mu for the energy); read+write vx,vy
+        wv = 10.0 * N + 2.0 * (px * (nz[0][0] + nz[0][1]) + py * (nz[1][0] + nz[1][1]));
+    }
+    if (bytes_stress) *bytes_stress = 8.0 * ws;
+    if (bytes_velocity) *bytes_velocity = 8.0 * wv;
+    return CPML_OK;
+}

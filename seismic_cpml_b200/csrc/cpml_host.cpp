@@ -1,0 +1,230 @@
+// Host-side helpers of libcpml_b200: the set-up and output phases that stay in the
+// driver (profiles, source law, receiver search, Courant number, file writers).
+// Pure host code; mirrors the behaviour of the reference's inline set-up code so that
+// the C++ / Python / Fortran drivers in this repo all hand the same numbers to the GPU.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/cpml_b200.h"
+
+namespace {
+
+constexpr double kPi = 3.141592653589793238462643;   // 3D-iso :199
+
+// Damping value set of one point of one side of the PML (3D-iso :466-484).
+struct Damp { double d = 0.0, K = 1.0, alpha = 0.0; };
+
+inline void damp_at(double depth_in_pml, double thickness, double d0, double npower,
+                    double k_max, double alpha_max, Damp &out)
+{
+    if (depth_in_pml < 0.0) return;                  // outside this side's layer
+    const double s = depth_in_pml / thickness;       // abscissa_normalized
+    const double sp = std::pow(s, npower);
+    out.d = d0 * sp;
+    out.K = 1.0 + (k_max - 1.0) * sp;
+    out.alpha = alpha_max * (1.0 - s);
+}
+
+inline void recursion_coefs(const Damp &p, double deltat, double &a, double &b)
+{
+    b = std::exp(-(p.d / p.K + p.alpha) * deltat);                       // :517
+    a = 0.0;
+    if (std::fabs(p.d) > 1.e-6) a = p.d * (b - 1.0) / (p.K * (p.d + p.K * p.alpha));   // :521
+}
+
+std::string join(const char *dir, const char *name)
+{
+    std::string s = (dir && *dir) ? dir : ".";
+    if (s.back() != '/') s += '/';
+    return s + name;
+}
+
+}  // namespace
+
+extern "C" int32_t cpml_host_pml_profile(int32_t n, double delta, double deltat, int32_t npoints_pml,
+                                         int32_t use_pml_min, int32_t use_pml_max, double cp, double rcoef,
+                                         double npower, double k_max_pml, double alpha_max_pml,
+                                         int32_t origin_top_uses_n, int32_t clamp_alpha,
+                                         double *a, double *b, double *K,
+                                         double *a_half, double *b_half, double *K_half)
+{
+    if (n < 1 || !(delta > 0) || !(deltat > 0) || npoints_pml < 1 || !a || !b || !K || !a_half || !b_half || !K_half)
+        return CPML_EINVAL;
+    if (npower < 1) return CPML_EINVAL;                                   // :410
+    const double thickness = npoints_pml * delta;                        // :402
+    const double d0 = -(npower + 1) * cp * std::log(rcoef) / (2.0 * thickness);   // :413
+    const double origin_min = thickness;                                  // :455
+    const double origin_max = (origin_top_uses_n ? n : n - 1) * delta - thickness;   // :456 / 2D-4th :401
+
+    for (int32_t idx = 0; idx < n; idx++) {
+        const double pos = delta * static_cast<double>(idx);              // :461
+        Damp full, half;
+        if (use_pml_min) {
+            damp_at(origin_min - pos, thickness, d0, npower, k_max_pml, alpha_max_pml, full);
+            damp_at(origin_min - (pos + delta / 2.0), thickness, d0, npower, k_max_pml, alpha_max_pml, half);
+        }
+        if (use_pml_max) {   // a max-side hit overrides the min side, like the sequential ifs of :489-511
+            damp_at(pos - origin_max, thickness, d0, npower, k_max_pml, alpha_max_pml, full);
+            damp_at(pos + delta / 2.0 - origin_max, thickness, d0, npower, k_max_pml, alpha_max_pml, half);
+        }
+        if (clamp_alpha) {                                                // :514-515
+            full.alpha = std::max(full.alpha, 0.0);
+            half.alpha = std::max(half.alpha, 0.0);
+        }
+        recursion_coefs(full, deltat, a[idx], b[idx]);
+        recursion_coefs(half, deltat, a_half[idx], b_half[idx]);
+        K[idx] = full.K;
+        K_half[idx] = half.K;
+    }
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_host_source_series(int32_t nstep, double deltat, double f0, double t0, double factor,
+                                           double angle_force_deg, double *force_x, double *force_y)
+{
+    if (nstep < 1 || !force_x || !force_y) return CPML_EINVAL;
+    const double a = kPi * kPi * f0 * f0;                                 // :1058
+    const double rad = angle_force_deg * (kPi / 180.0);                   // :202
+    const double sx = std::sin(rad), cy = std::cos(rad);
+    for (int32_t it = 1; it <= nstep; it++) {
+        const double t = static_cast<double>(it - 1) * deltat;           // :1059
+        const double tau = t - t0;
+        const double source_term = -factor * 2.0 * a * tau * std::exp(-a * (tau * tau));   // :1065
+        force_x[it - 1] = sx * source_term;                               // :1070-1071
+        force_y[it - 1] = cy * source_term;
+    }
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_host_find_receivers(int32_t nx, int32_t ny, double deltax, double deltay, int32_t nrec,
+                                            double xdeb, double ydeb, double xfin, double yfin,
+                                            int32_t *ix_rec, int32_t *iy_rec, double *dist)
+{
+    if (nx < 1 || ny < 1 || nrec < 1 || !ix_rec || !iy_rec) return CPML_EINVAL;
+    const double xstep = nrec > 1 ? (xfin - xdeb) / static_cast<double>(nrec - 1) : 0.0;   // :683
+    const double ystep = nrec > 1 ? (yfin - ydeb) / static_cast<double>(nrec - 1) : 0.0;
+    for (int32_t r = 0; r < nrec; r++) {
+        const double xr = xdeb + static_cast<double>(r) * xstep;          // :686-687
+        const double yr = ydeb + static_cast<double>(r) * ystep;
+        double best = 1.e+30;                                             // HUGEVAL :208
+        // strict '<' with j outer, i inner: the first minimum wins (quirk B9)
+        for (int32_t j = 1; j <= ny; j++)
+            for (int32_t i = 1; i <= nx; i++) {
+                const double ex = deltax * static_cast<double>(i - 1) - xr;
+                const double ey = deltay * static_cast<double>(j - 1) - yr;
+                const double dv = std::sqrt(ex * ex + ey * ey);
+                if (dv < best) { best = dv; ix_rec[r] = i; iy_rec[r] = j; }
+            }
+        if (dist) dist[r] = best;
+    }
+    return CPML_OK;
+}
+
+extern "C" double cpml_host_courant(double cp, double deltat, double deltax, double deltay, double deltaz)
+{
+    double s = 1.0 / (deltax * deltax) + 1.0 / (deltay * deltay);        // :712 / 2D-2nd :513
+    if (deltaz > 0.0) s += 1.0 / (deltaz * deltaz);
+    return cp * deltat * std::sqrt(s);
+}
+
+// ---- writers ---------------------------------------------------------------------
+
+extern "C" int32_t cpml_host_write_seismograms(const char *dir, const double *sisvx, const double *sisvy,
+                                               int32_t nt, int32_t nrec, double deltat)
+{
+    if (!sisvx || !sisvy || nt < 1 || nrec < 0) return CPML_EINVAL;
+    for (int comp = 0; comp < 2; comp++) {
+        const double *sis = comp == 0 ? sisvx : sisvy;
+        for (int32_t r = 1; r <= nrec; r++) {
+            char name[64];
+            snprintf(name, sizeof name, comp == 0 ? "Vx_file_%03d.dat" : "Vy_file_%03d.dat", r);   // :1346,1356
+            FILE *f = fopen(join(dir, name).c_str(), "w");
+            if (!f) return CPML_EINVAL;
+            // time and amplitude, both demoted to single precision like sngl(...) :1349
+            for (int32_t it = 1; it <= nt; it++)
+                fprintf(f, "  %.8E   %.8E\n", (double)(float)((double)(it - 1) * deltat),
+                        (double)(float)sis[(size_t)(r - 1) * nt + (it - 1)]);
+            fclose(f);
+        }
+    }
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_host_write_energy_3d(const char *path, const double *total, int32_t nt, double deltat)
+{
+    if (!path || !total) return CPML_EINVAL;
+    FILE *f = fopen(path, "w");
+    if (!f) return CPML_EINVAL;
+    for (int32_t it = 1; it <= nt; it++)                                  // :1254-1256
+        fprintf(f, "  %.8E   %.16E\n", (double)(float)((double)(it - 1) * deltat), total[it - 1]);
+    fclose(f);
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_host_write_energy_2d(const char *path, const double *kinetic, const double *potential,
+                                             int32_t nt, double deltat)
+{
+    if (!path || !kinetic || !potential) return CPML_EINVAL;
+    FILE *f = fopen(path, "w");
+    if (!f) return CPML_EINVAL;
+    for (int32_t it = 1; it <= nt; it++)                                  // 2D-2nd :742-745
+        fprintf(f, "  %.8E   %.8E   %.8E   %.8E\n", (double)(float)((double)(it - 1) * deltat),
+                (double)(float)kinetic[it - 1], (double)(float)potential[it - 1],
+                (double)(float)(kinetic[it - 1] + potential[it - 1]));
+    fclose(f);
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_host_create_color_image(const char *dir, const double *img, int32_t nx, int32_t ny,
+                                                int32_t it, int32_t isource, int32_t jsource,
+                                                const int32_t *ix_rec, const int32_t *iy_rec, int32_t nrec,
+                                                int32_t npoints_pml, int32_t use_pml_xmin, int32_t use_pml_xmax,
+                                                int32_t use_pml_ymin, int32_t use_pml_ymax, int32_t field_number)
+{
+    if (!img || nx < 1 || ny < 1 || (field_number != 1 && field_number != 2)) return CPML_EINVAL;
+    // display constants of create_color_image, 3D-iso :1377-1386
+    const double power_display = 0.30, cutvect = 0.01;
+    const int width_cross = 5, thickness_cross = 1, size_square = 3;
+
+    char name[64];
+    snprintf(name, sizeof name, field_number == 1 ? "image%06d_Vx.pnm" : "image%06d_Vy.pnm", it);   // :1406,1409
+    FILE *f = fopen(join(dir, name).c_str(), "w");
+    if (!f) return CPML_EINVAL;
+    fprintf(f, "P3\n%d %d\n255\n", nx, ny);                                // :1415-1418
+
+    double max_amplitude = 0.0;                                           // :1421
+    for (size_t q = 0; q < (size_t)nx * ny; q++) max_amplitude = std::max(max_amplitude, std::fabs(img[q]));
+
+    auto near = [](int v, int c, int w) { return v >= c - w && v <= c + w; };
+    for (int iy = ny; iy >= 1; iy--) {                                    // top row first, :1424
+        for (int ix = 1; ix <= nx; ix++) {
+            const double v = img[(size_t)(iy - 1) * nx + (ix - 1)];
+            double nv = v / max_amplitude;
+            nv = std::min(1.0, std::max(-1.0, nv));
+            int R, G, B;
+            if ((near(ix, isource, width_cross) && near(iy, jsource, thickness_cross)) ||
+                (near(ix, isource, thickness_cross) && near(iy, jsource, width_cross))) {
+                R = 255; G = 157; B = 0;                                  // source cross
+            } else if (ix <= 2 || ix >= nx - 1 || iy <= 2 || iy >= ny - 1) {
+                R = G = B = 0;                                            // frame
+            } else if ((use_pml_xmin && ix == npoints_pml) || (use_pml_xmax && ix == nx - npoints_pml) ||
+                       (use_pml_ymin && iy == npoints_pml) || (use_pml_ymax && iy == ny - npoints_pml)) {
+                R = 255; G = 150; B = 0;                                  // PML edges
+            } else if (std::fabs(v) <= max_amplitude * cutvect) {
+                R = G = B = 255;                                          // white background
+            } else if (nv >= 0.0) {
+                R = (int)std::lround(255.0 * std::pow(nv, power_display)); G = 0; B = 0;
+            } else {
+                R = 0; G = 0; B = (int)std::lround(255.0 * std::pow(std::fabs(nv), power_display));
+            }
+            for (int r = 0; r < nrec; r++)
+                if (near(ix, ix_rec[r], size_square) && near(iy, iy_rec[r], size_square)) { R = 30; G = 180; B = 60; }
+            fprintf(f, "%3d %3d %3d\n", R, G, B);                          // :1498
+        }
+    }
+    fclose(f);
+    return CPML_OK;
+}

@@ -1,0 +1,122 @@
+// Internal declarations of libcpml_b200 (not part of the C ABI).
+//
+// Data layout in HBM (DESIGN.md "Data layout"):
+//   * every wavefield is one padded array, x fastest, row pitch a multiple of 16
+//     doubles (128 B) so that a warp row starts on a cache line;
+//   * 3-D fields carry the two z halo planes of the reference (k = 0 and
+//     k = NZ_LOCAL+1, 3D-iso :273); 2-D fields carry a 2-cell zero ghost ring (the
+//     fourth-order program's (0:NX+1,0:NY+1) arrays, 2D-4th :205, widened to 2 so
+//     that discarded lanes never read out of bounds);
+//   * the 18 (3-D) / 8 (2-D) C-PML memory variables exist only inside the thin
+//     shells where their damping profile is non-trivial: x-shell arrays
+//     [k][j][sx], y-shell arrays [k][sy][i], z-shell arrays [sz][j][i].
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/cpml_b200.h"
+
+namespace cpml {
+
+// Index set of one axis where C-PML coefficients are non-trivial: [1..lo] U [hi..n].
+struct Shell {
+    int lo;   // last index of the low shell (0: none)
+    int hi;   // first index of the high shell (n+1: none)
+    int n;
+    int size() const { return lo + (n - hi + 1); }
+};
+
+// 1-based device views of the six coefficient arrays of one axis.
+struct AxisCoef {
+    const double *a, *b, *K, *a_half, *b_half, *K_half;
+};
+
+// ------------------------------------------------------------------ 3-D
+struct Params3D {
+    int nx, ny, nzl;          // local slab extent
+    int nz;                   // global NZ
+    int koff;                 // offset_k = rank * NZ_LOCAL (3D-iso :397)
+    int pitch;                // row pitch in doubles
+    long long plane;          // plane pitch in doubles (= pitch * ny)
+    int kchunk;               // planes marched by one block
+    // fields: pointer to element (i=1, j=1, k=0)
+    double *vx, *vy, *vz, *sxx, *syy, *szz, *sxy, *sxz, *syz;
+    // shells
+    int xlo, xhi, sxp;        // sxp: padded x-shell row length
+    int ylo, yhi, sy;         // sy: number of y-shell rows
+    int zlo, zhi;             // global z shell
+    int zbase;                // global shell index of this slab's first stored z-shell plane
+    // memory variables, see kernels_3d.cu for the order inside each group
+    double *mx[6], *my[6], *mz[6];
+    AxisCoef cx, cy, cz;      // cz is indexed by GLOBAL k
+    double odx, ody, odz;     // ONE_OVER_DELTAX.. (:134-136)
+    double dt_lambda, dt_mu, dt_lambdaplus2mu, dt_over_rho;   // :296-300
+    // velocity kernel extras
+    int it;                   // time step (1-based)
+    int isrc, jsrc, ksrc;     // source point, ksrc local (0: not on this slab)
+    const double *src_x, *src_y;   // force*DELTAT/rho per step (:1080-1081)
+    int npml;                 // energy box (:1135-1145)
+    int energy_bug_compat;
+    double rho, lambda, mu;
+    double *partials;         // [2][nblocks] kinetic / potential per block
+    int nblocks;
+};
+
+struct Post3D {
+    const double *partials;
+    int nblocks;
+    double *energy_k, *energy_p;   // traces, slot it-1 is written
+    int it, nstep, nrec;
+    const int *ix_rec, *iy_rec;
+    const double *vx, *vy;         // element (1,1,0)
+    int pitch;
+    long long plane;
+    int krec;                      // local k of the receiver plane, 0: not here
+    double *sisvx, *sisvy;
+};
+
+// ------------------------------------------------------------------ 2-D
+struct Params2D {
+    int nx, ny, pitch;
+    int order;                // 2 or 4
+    double *vx, *vy, *sxx, *syy, *sxy;       // pointer to element (i=1, j=1)
+    const double *lambda, *mu, *rho;         // same layout, zero ghost ring
+    int xlo, xhi, sxp;
+    int ylo, yhi, sy;
+    double *mx[4], *my[4];
+    AxisCoef cx, cy;
+    double deltax, deltay, deltat;
+    int it;
+    int isrc, jsrc;
+    const double *force_x, *force_y;         // raw force series (2D-2nd :656-657)
+    int npml;
+    double *partials;
+    int nblocks;
+};
+
+struct Post2D {
+    const double *partials;
+    int nblocks;
+    double *energy_k, *energy_p;
+    int it, nstep, nrec;
+    const int *ix_rec, *iy_rec;
+    const double *vx, *vy;
+    int pitch;
+    double *sisvx, *sisvy;
+};
+
+// launchers (kernels_3d.cu / kernels_2d.cu)
+struct LaunchCfg { int tx, ty; };
+void launch_stress3d(const Params3D &p, dim3 grid, dim3 block, cudaStream_t s);
+void launch_velocity3d(const Params3D &p, dim3 grid, dim3 block, cudaStream_t s);
+void launch_post3d(const Post3D &p, cudaStream_t s);
+void launch_stress2d(const Params2D &p, dim3 grid, dim3 block, cudaStream_t s);
+void launch_velocity2d(const Params2D &p, dim3 grid, dim3 block, cudaStream_t s);
+void launch_post2d(const Post2D &p, cudaStream_t s);
+void launch_maxnorm(const double *vx, const double *vy, const double *vz, long long n,
+                    unsigned long long *out_bits, cudaStream_t s);
+
+}  // namespace cpml

@@ -1,0 +1,190 @@
+// 2-D isotropic C-PML kernels for sm_100a, second and fourth order in space.
+//
+//   k_stress2d<ORDER>    sigma_xx/yy (2D-2nd :556-580, 2D-4th :557-581),
+//                        sigma_xy    (2D-2nd :582-600, 2D-4th :583-601)
+//   k_velocity2d<ORDER>  vx, vy (2D-2nd :606-641), source (:643-667), Dirichlet
+//                        (:669-680), per-block kinetic / potential energy (:688-713)
+// The step is finished by k_post3d (energy sum + seismogram sample), shared with 3-D.
+//
+// One thread per grid point, x across the warp; the radius-1 (2nd order) or radius-2
+// (4th order) neighbours come through L1/L2.  Heterogeneous lambda, mu, rho arrays are
+// streamed and averaged on the fly exactly as the reference does.  Fields carry a
+// two-cell zero ghost ring (the reference's fourth-order arrays are (0:NX+1,0:NY+1)),
+// so the fourth-order taps at the edges read the same zeros the reference reads.
+// Compiled with -fmad=false, divisions kept as divisions: bit-identical fields.
+#include "cpml_internal.h"
+
+namespace cpml {
+
+__device__ __forceinline__ double cpml_apply2(double *__restrict__ mem, long long q,
+                                              double b, double a, double K, double value)
+{
+    double m = mem[q];
+    m = b * m + a * value;
+    mem[q] = m;
+    return value / K + m;
+}
+
+__device__ __forceinline__ int shell_index2(int i, int lo, int hi)
+{
+    return i <= lo ? i - 1 : lo + (i - hi);
+}
+
+// forward difference u(n+1)-u(n): `s` is the element stride along the axis
+template <int ORDER>
+__device__ __forceinline__ double d_fwd(const double *f, long long q, long long s, double delta)
+{
+    if (ORDER == 2) return (f[q + s] - f[q]) / delta;
+    return (27.0 * f[q + s] - 27.0 * f[q] - f[q + 2 * s] + f[q - s]) / (24.0 * delta);
+}
+// backward difference u(n)-u(n-1)
+template <int ORDER>
+__device__ __forceinline__ double d_bwd(const double *f, long long q, long long s, double delta)
+{
+    if (ORDER == 2) return (f[q] - f[q - s]) / delta;
+    return (27.0 * f[q] - 27.0 * f[q - s] - f[q + s] + f[q - 2 * s]) / (24.0 * delta);
+}
+
+template <int ORDER, int TX, int TY>
+__global__ void __launch_bounds__(TX *TY)
+k_stress2d(const __grid_constant__ Params2D p)
+{
+    const int i = blockIdx.x * TX + threadIdx.x + 1;
+    const int j = blockIdx.y * TY + threadIdx.y + 1;
+    if (i > p.nx || j > p.ny) return;
+    const int pitch = p.pitch;
+    const long long q = (long long)(j - 1) * pitch + (i - 1);
+    const bool in_x = (i <= p.xlo) || (i >= p.xhi);
+    const bool in_y = (j <= p.ylo) || (j >= p.yhi);
+    const long long qx = in_x ? (long long)(j - 1) * p.sxp + shell_index2(i, p.xlo, p.xhi) : 0;
+    const long long qy = in_y ? (long long)shell_index2(j, p.ylo, p.yhi) * pitch + (i - 1) : 0;
+    const double DELTAT = p.deltat;
+
+    if (i <= p.nx - 1 && j >= 2) {
+        const double lambda_half_x = 0.5 * (p.lambda[q + 1] + p.lambda[q]);
+        const double mu_half_x = 0.5 * (p.mu[q + 1] + p.mu[q]);
+        const double lambda_plus_two_mu_half_x = lambda_half_x + 2.0 * mu_half_x;
+        double value_dvx_dx = d_fwd<ORDER>(p.vx, q, 1, p.deltax);
+        double value_dvy_dy = d_bwd<ORDER>(p.vy, q, pitch, p.deltay);
+        if (in_x) value_dvx_dx = cpml_apply2(p.mx[0], qx, p.cx.b_half[i], p.cx.a_half[i], p.cx.K_half[i], value_dvx_dx);
+        if (in_y) value_dvy_dy = cpml_apply2(p.my[0], qy, p.cy.b[j], p.cy.a[j], p.cy.K[j], value_dvy_dy);
+        p.sxx[q] = p.sxx[q] + (lambda_plus_two_mu_half_x * value_dvx_dx + lambda_half_x * value_dvy_dy) * DELTAT;
+        p.syy[q] = p.syy[q] + (lambda_half_x * value_dvx_dx + lambda_plus_two_mu_half_x * value_dvy_dy) * DELTAT;
+    }
+    if (i >= 2 && j <= p.ny - 1) {
+        const double mu_half_y = 0.5 * (p.mu[q + pitch] + p.mu[q]);
+        double value_dvy_dx = d_bwd<ORDER>(p.vy, q, 1, p.deltax);
+        double value_dvx_dy = d_fwd<ORDER>(p.vx, q, pitch, p.deltay);
+        if (in_x) value_dvy_dx = cpml_apply2(p.mx[1], qx, p.cx.b[i], p.cx.a[i], p.cx.K[i], value_dvy_dx);
+        // quirk B3: the fourth-order program divides by K_y(j) here (2D-4th :596), the
+        // second-order one by K_y_half(j) (2D-2nd :595)
+        if (in_y) value_dvx_dy = cpml_apply2(p.my[1], qy, p.cy.b_half[j], p.cy.a_half[j],
+                                             ORDER == 4 ? p.cy.K[j] : p.cy.K_half[j], value_dvx_dy);
+        p.sxy[q] = p.sxy[q] + mu_half_y * (value_dvy_dx + value_dvx_dy) * DELTAT;
+    }
+}
+
+template <int NT>
+__device__ __forceinline__ void block_sum2_2d(double &a, double &b, double *smem)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, o);
+        b += __shfl_down_sync(0xffffffffu, b, o);
+    }
+    const int t = threadIdx.y * blockDim.x + threadIdx.x;
+    const int w = t >> 5, l = t & 31;
+    if (l == 0) { smem[w] = a; smem[NT / 32 + w] = b; }
+    __syncthreads();
+    if (w == 0) {
+        a = (l < NT / 32) ? smem[l] : 0.0;
+        b = (l < NT / 32) ? smem[NT / 32 + l] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_down_sync(0xffffffffu, a, o);
+            b += __shfl_down_sync(0xffffffffu, b, o);
+        }
+    }
+}
+
+template <int ORDER, int TX, int TY>
+__global__ void __launch_bounds__(TX *TY)
+k_velocity2d(const __grid_constant__ Params2D p)
+{
+    __shared__ double red[2 * TX * TY / 32];
+    const int i = blockIdx.x * TX + threadIdx.x + 1;
+    const int j = blockIdx.y * TY + threadIdx.y + 1;
+    double ekin = 0.0, epot = 0.0;
+
+    if (i <= p.nx && j <= p.ny) {
+        const int pitch = p.pitch;
+        const long long q = (long long)(j - 1) * pitch + (i - 1);
+        const bool in_x = (i <= p.xlo) || (i >= p.xhi);
+        const bool in_y = (j <= p.ylo) || (j >= p.yhi);
+        const long long qx = in_x ? (long long)(j - 1) * p.sxp + shell_index2(i, p.xlo, p.xhi) : 0;
+        const long long qy = in_y ? (long long)shell_index2(j, p.ylo, p.yhi) * pitch + (i - 1) : 0;
+        const double DELTAT = p.deltat;
+        const double rho = p.rho[q];
+        const double rho_half_x_half_y = 0.25 * (rho + p.rho[q + 1] + p.rho[q + 1 + pitch] + p.rho[q + pitch]);
+        double vx = p.vx[q], vy = p.vy[q];
+
+        if (i >= 2 && j >= 2) {
+            double value_dsigmaxx_dx = d_bwd<ORDER>(p.sxx, q, 1, p.deltax);
+            double value_dsigmaxy_dy = d_bwd<ORDER>(p.sxy, q, pitch, p.deltay);
+            if (in_x) value_dsigmaxx_dx = cpml_apply2(p.mx[2], qx, p.cx.b[i], p.cx.a[i], p.cx.K[i], value_dsigmaxx_dx);
+            if (in_y) value_dsigmaxy_dy = cpml_apply2(p.my[2], qy, p.cy.b[j], p.cy.a[j], p.cy.K[j], value_dsigmaxy_dy);
+            vx = vx + (value_dsigmaxx_dx + value_dsigmaxy_dy) * DELTAT / rho;
+        }
+        if (i <= p.nx - 1 && j <= p.ny - 1) {
+            double value_dsigmaxy_dx = d_fwd<ORDER>(p.sxy, q, 1, p.deltax);
+            double value_dsigmayy_dy = d_fwd<ORDER>(p.syy, q, pitch, p.deltay);
+            if (in_x) value_dsigmaxy_dx = cpml_apply2(p.mx[3], qx, p.cx.b_half[i], p.cx.a_half[i], p.cx.K_half[i], value_dsigmaxy_dx);
+            if (in_y) value_dsigmayy_dy = cpml_apply2(p.my[3], qy, p.cy.b_half[j], p.cy.a_half[j], p.cy.K_half[j], value_dsigmayy_dy);
+            vy = vy + (value_dsigmaxy_dx + value_dsigmayy_dy) * DELTAT / rho_half_x_half_y;
+        }
+        if (i == p.isrc && j == p.jsrc) {               // 2D-2nd :663-667
+            vx = vx + p.force_x[p.it - 1] * DELTAT / rho;
+            vy = vy + p.force_y[p.it - 1] * DELTAT / rho_half_x_half_y;
+        }
+        if (i == 1 || i == p.nx || j == 1 || j == p.ny) { vx = 0.0; vy = 0.0; }   // :669-680
+        p.vx[q] = vx;
+        p.vy[q] = vy;
+
+        // energy box: 2D-2nd :695-704 (NPML+1..N-NPML), 2D-4th :696-705 (NPML..N-NPML+1)
+        const int e0 = ORDER == 4 ? p.npml : p.npml + 1;
+        const int ex1 = ORDER == 4 ? p.nx - p.npml + 1 : p.nx - p.npml;
+        const int ey1 = ORDER == 4 ? p.ny - p.npml + 1 : p.ny - p.npml;
+        if (i >= e0 && i <= ex1 && j >= e0 && j <= ey1) {
+            const double l = p.lambda[q], m = p.mu[q];
+            const double sxx = p.sxx[q], syy = p.syy[q], sxy = p.sxy[q];
+            ekin = 0.5 * (rho * (vx * vx + vy * vy));
+            const double inv4 = 1.0 / (4.0 * m * (l + m));
+            const double epsilon_xx = ((l + 2.0 * m) * sxx - l * syy) * inv4;
+            const double epsilon_yy = ((l + 2.0 * m) * syy - l * sxx) * inv4;
+            const double epsilon_xy = sxy / (2.0 * m);
+            epot = 0.5 * (epsilon_xx * sxx + epsilon_yy * syy + 2.0 * epsilon_xy * sxy);
+        }
+    }
+    block_sum2_2d<TX * TY>(ekin, epot, red);
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        const int b = blockIdx.y * gridDim.x + blockIdx.x;
+        p.partials[b] = ekin;
+        p.partials[p.nblocks + b] = epot;
+    }
+}
+
+void launch_stress2d(const Params2D &p, dim3 grid, dim3 block, cudaStream_t s)
+{
+    (void)block;
+    if (p.order == 4) k_stress2d<4, 32, 8><<<grid, dim3(32, 8), 0, s>>>(p);
+    else              k_stress2d<2, 32, 8><<<grid, dim3(32, 8), 0, s>>>(p);
+}
+
+void launch_velocity2d(const Params2D &p, dim3 grid, dim3 block, cudaStream_t s)
+{
+    (void)block;
+    if (p.order == 4) k_velocity2d<4, 32, 8><<<grid, dim3(32, 8), 0, s>>>(p);
+    else              k_velocity2d<2, 32, 8><<<grid, dim3(32, 8), 0, s>>>(p);
+}
+
+}  // namespace cpml

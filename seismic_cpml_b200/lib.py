@@ -1,0 +1,307 @@
+"""ctypes binding of libcpml_b200.so (the C ABI of include/cpml_b200.h).
+
+This is the Python stand-in for the Fortran ISO_C_BINDING module a maintainer of the
+reference would add (drivers/fortran/cpml_b200_mod.f90): same entry points, same
+argument meaning, same error codes.  There is no CPU fallback: if the CUDA library is
+missing or no device is usable, calls raise CpmlError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcpml_b200.so")
+
+CPML_OK, CPML_EINVAL, CPML_ETOPOLOGY, CPML_ECFL, CPML_ECUDA, CPML_ESTATE, CPML_ENOMEM = range(7)
+ERROR_NAMES = {0: "CPML_OK", 1: "CPML_EINVAL", 2: "CPML_ETOPOLOGY", 3: "CPML_ECFL", 4: "CPML_ECUDA",
+               5: "CPML_ESTATE", 6: "CPML_ENOMEM"}
+AXIS_X, AXIS_Y, AXIS_Z = 0, 1, 2
+FIELDS_3D = ("vx", "vy", "vz", "sigmaxx", "sigmayy", "sigmazz", "sigmaxy", "sigmaxz", "sigmayz")
+FIELDS_2D = ("vx", "vy", "sigmaxx", "sigmayy", "sigmaxy")
+PROFILE_KEYS = ("a", "b", "K", "a_half", "b_half", "K_half")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+class CpmlError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"{ERROR_NAMES.get(code, code)}: {message}")
+        self.code = code
+
+
+class CpmlConfig(C.Structure):
+    """struct cpml_config of include/cpml_b200.h (field for field)."""
+    _fields_ = [("ndim", C.c_int32), ("order", C.c_int32),
+                ("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32),
+                ("nstep", C.c_int32), ("npoints_pml", C.c_int32), ("nrec", C.c_int32),
+                ("isource", C.c_int32), ("jsource", C.c_int32), ("ksource", C.c_int32),
+                ("nslabs", C.c_int32), ("slab_rank", C.c_int32), ("device", C.c_int32),
+                ("energy_bug_compat", C.c_int32), ("reserved_i", C.c_int32 * 4),
+                ("deltax", C.c_double), ("deltay", C.c_double), ("deltaz", C.c_double),
+                ("deltat", C.c_double),
+                ("lambda_", C.c_double), ("mu", C.c_double), ("lambdaplustwomu", C.c_double),
+                ("rho", C.c_double), ("cp", C.c_double), ("reserved_d", C.c_double * 4)]
+
+
+# every symbol include/cpml_b200.h declares: name -> (restype, argtypes)
+_H = C.c_void_p
+SYMBOLS = {
+    "cpml_abi_version": (C.c_int32, []),
+    "cpml_create": (C.c_int32, [C.POINTER(CpmlConfig), C.POINTER(_H)]),
+    "cpml_destroy": (C.c_int32, [_H]),
+    "cpml_last_error": (C.c_char_p, [_H]),
+    "cpml_reset": (C.c_int32, [_H]),
+    "cpml_set_stream": (C.c_int32, [_H, C.c_void_p]),
+    "cpml_set_profiles": (C.c_int32, [_H, C.c_int32] + [_dp] * 6 + [C.c_int32]),
+    "cpml_set_material_2d": (C.c_int32, [_H, _dp, _dp, _dp]),
+    "cpml_set_source_series": (C.c_int32, [_H, _dp, _dp, C.c_int32]),
+    "cpml_set_receivers": (C.c_int32, [_H, _ip, _ip, C.c_int32]),
+    "cpml_run": (C.c_int32, [_H, C.c_int32, C.c_int32]),
+    "cpml_step_stress": (C.c_int32, [_H, C.c_int32]),
+    "cpml_step_velocity": (C.c_int32, [_H, C.c_int32]),
+    "cpml_step_finish": (C.c_int32, [_H, C.c_int32]),
+    "cpml_synchronize": (C.c_int32, [_H]),
+    "cpml_halo_plane": (C.c_int32, [_H, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "cpml_copy_plane": (C.c_int32, [_H, C.c_int32, _H, C.c_int32, C.c_int32]),
+    "cpml_get_seismograms": (C.c_int32, [_H, _dp, _dp]),
+    "cpml_get_energy": (C.c_int32, [_H, _dp, _dp, _dp]),
+    "cpml_get_plane": (C.c_int32, [_H, C.c_int32, C.c_int32, _dp]),
+    "cpml_get_field": (C.c_int32, [_H, C.c_int32, _dp]),
+    "cpml_get_maxnorm": (C.c_int32, [_H, _dp]),
+    "cpml_get_kernel_times": (C.c_int32, [_H, _dp, _dp, C.POINTER(C.c_int64), C.c_int32]),
+    "cpml_enable_kernel_timing": (C.c_int32, [_H, C.c_int32]),
+    "cpml_algorithmic_bytes": (C.c_int32, [_H, _dp, _dp]),
+    "cpml_host_pml_profile": (C.c_int32, [C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                          C.c_int32, C.c_int32] + [_dp] * 6),
+    "cpml_host_source_series": (C.c_int32, [C.c_int32] + [C.c_double] * 5 + [_dp, _dp]),
+    "cpml_host_find_receivers": (C.c_int32, [C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32,
+                                             C.c_double, C.c_double, C.c_double, C.c_double, _ip, _ip, _dp]),
+    "cpml_host_courant": (C.c_double, [C.c_double] * 5),
+    "cpml_host_write_seismograms": (C.c_int32, [C.c_char_p, _dp, _dp, C.c_int32, C.c_int32, C.c_double]),
+    "cpml_host_write_energy_3d": (C.c_int32, [C.c_char_p, _dp, C.c_int32, C.c_double]),
+    "cpml_host_write_energy_2d": (C.c_int32, [C.c_char_p, _dp, _dp, C.c_int32, C.c_double]),
+    "cpml_host_create_color_image": (C.c_int32, [C.c_char_p, _dp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                                 C.c_int32, _ip, _ip, C.c_int32, C.c_int32, C.c_int32,
+                                                 C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads libcpml_b200.so; fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CpmlError(CPML_ECUDA, f"{LIB_PATH} is missing: run `python -m seismic_cpml_b200.build` "
+                            "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)   # AttributeError if the library does not export it
+            fn.restype = res
+            fn.argtypes = args
+        if L.cpml_abi_version() != 1:
+            raise CpmlError(CPML_EINVAL, "libcpml_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+# ---------------------------------------------------------------- host helpers
+
+def host_pml_profile(n, delta, deltat, npoints_pml, use_pml_min=True, use_pml_max=True, *, cp,
+                     rcoef=0.001, npower=2.0, k_max_pml=1.0, alpha_max_pml,
+                     origin_top_uses_n=False, clamp_alpha=False):
+    out = {k: np.zeros(n) for k in PROFILE_KEYS}
+    rc = load().cpml_host_pml_profile(n, delta, deltat, npoints_pml, int(use_pml_min), int(use_pml_max),
+                                      cp, rcoef, npower, k_max_pml, alpha_max_pml,
+                                      int(origin_top_uses_n), int(clamp_alpha),
+                                      *[_d(out[k]) for k in PROFILE_KEYS])
+    if rc:
+        raise CpmlError(rc, "cpml_host_pml_profile")
+    return out
+
+
+def host_source_series(nstep, deltat, f0, t0, factor, angle_force_deg):
+    fx, fy = np.zeros(nstep), np.zeros(nstep)
+    rc = load().cpml_host_source_series(nstep, deltat, f0, t0, factor, angle_force_deg, _d(fx), _d(fy))
+    if rc:
+        raise CpmlError(rc, "cpml_host_source_series")
+    return fx, fy
+
+
+def host_find_receivers(nx, ny, deltax, deltay, nrec, xdeb, ydeb, xfin, yfin):
+    ix, iy = np.zeros(nrec, dtype=np.int32), np.zeros(nrec, dtype=np.int32)
+    dist = np.zeros(nrec)
+    rc = load().cpml_host_find_receivers(nx, ny, deltax, deltay, nrec, xdeb, ydeb, xfin, yfin,
+                                         _i(ix), _i(iy), _d(dist))
+    if rc:
+        raise CpmlError(rc, "cpml_host_find_receivers")
+    return ix, iy, dist
+
+
+def host_courant(cp, deltat, deltax, deltay, deltaz=0.0):
+    return load().cpml_host_courant(cp, deltat, deltax, deltay, deltaz)
+
+
+# ---------------------------------------------------------------- handle
+
+class Solver:
+    """One cpml_handle: a whole 2-D grid, a whole 3-D grid, or one z-slab of a 3-D grid."""
+
+    def __init__(self, *, ndim, order=2, nx, ny, nz=1, nstep, npoints_pml, nrec, isource, jsource,
+                 ksource=0, nslabs=1, slab_rank=0, device=-1, energy_bug_compat=True,
+                 deltax, deltay, deltaz=0.0, deltat, lam=0.0, mu=0.0, lambdaplustwomu=0.0, rho=0.0,
+                 cp=0.0):
+        self._L = load()
+        self.cfg = CpmlConfig(ndim=ndim, order=order, nx=nx, ny=ny, nz=nz, nstep=nstep,
+                              npoints_pml=npoints_pml, nrec=nrec, isource=isource, jsource=jsource,
+                              ksource=ksource, nslabs=nslabs, slab_rank=slab_rank, device=device,
+                              energy_bug_compat=int(energy_bug_compat),
+                              deltax=deltax, deltay=deltay, deltaz=deltaz, deltat=deltat,
+                              lambda_=lam, mu=mu, lambdaplustwomu=lambdaplustwomu, rho=rho, cp=cp)
+        self._h = _H()
+        rc = self._L.cpml_create(C.byref(self.cfg), C.byref(self._h))
+        if rc:
+            msg = self._L.cpml_last_error(None)
+            self._h = _H()
+            raise CpmlError(rc, msg.decode() if msg else "cpml_create")
+        self.nzl = nz // nslabs if ndim == 3 else 1
+        self.koff = slab_rank * self.nzl
+
+    # -- plumbing
+    def _ck(self, rc):
+        if rc:
+            msg = self._L.cpml_last_error(self._h)
+            raise CpmlError(rc, msg.decode() if msg else "")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.cpml_destroy(self._h)
+            self._h = _H()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- inputs
+    def set_stream(self, cuda_stream: int):
+        self._ck(self._L.cpml_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def set_profiles(self, axis, prof):
+        arrs = [_f64(prof[k]) for k in PROFILE_KEYS]
+        self._ck(self._L.cpml_set_profiles(self._h, axis, *[_d(a) for a in arrs], arrs[0].size))
+
+    def set_material_2d(self, lam, mu, rho):
+        lam, mu, rho = _f64(lam).ravel(), _f64(mu).ravel(), _f64(rho).ravel()
+        n = self.cfg.nx * self.cfg.ny
+        if lam.size != n or mu.size != n or rho.size != n:
+            raise CpmlError(CPML_EINVAL, "material arrays must hold NX*NY values")
+        self._ck(self._L.cpml_set_material_2d(self._h, _d(lam), _d(mu), _d(rho)))
+
+    def set_source_series(self, force_x, force_y):
+        fx, fy = _f64(force_x), _f64(force_y)
+        if fx.size != fy.size:
+            raise CpmlError(CPML_EINVAL, "force_x and force_y differ in length")
+        self._ck(self._L.cpml_set_source_series(self._h, _d(fx), _d(fy), fx.size))
+
+    def set_receivers(self, ix_rec, iy_rec):
+        ix = np.ascontiguousarray(ix_rec, dtype=np.int32)
+        iy = np.ascontiguousarray(iy_rec, dtype=np.int32)
+        self._ck(self._L.cpml_set_receivers(self._h, _i(ix), _i(iy), ix.size))
+
+    def reset(self):
+        self._ck(self._L.cpml_reset(self._h))
+
+    # -- the loop
+    def run(self, it_begin, it_end):
+        self._ck(self._L.cpml_run(self._h, it_begin, it_end))
+
+    def step_stress(self, it):
+        self._ck(self._L.cpml_step_stress(self._h, it))
+
+    def step_velocity(self, it):
+        self._ck(self._L.cpml_step_velocity(self._h, it))
+
+    def step_finish(self, it):
+        self._ck(self._L.cpml_step_finish(self._h, it))
+
+    def synchronize(self):
+        self._ck(self._L.cpml_synchronize(self._h))
+
+    def halo_plane(self, field, klocal):
+        ptr, nbytes = C.c_void_p(), C.c_int64()
+        self._ck(self._L.cpml_halo_plane(self._h, field, klocal, C.byref(ptr), C.byref(nbytes)))
+        return ptr.value, nbytes.value
+
+    def copy_plane_from(self, klocal_dst, src: "Solver", klocal_src, field):
+        """One MPI_SENDRECV of the reference: plane klocal_src of `src` -> plane klocal_dst here."""
+        self._ck(self._L.cpml_copy_plane(self._h, klocal_dst, src._h, klocal_src, field))
+
+    # -- outputs
+    def get_seismograms(self):
+        """(sisvx, sisvy), each shaped (NREC, NSTEP): row r is the trace of receiver r+1
+        (the reference's sisvx(:, irec))."""
+        nrec, nstep = self.cfg.nrec, self.cfg.nstep
+        sx, sy = np.zeros((nrec, nstep)), np.zeros((nrec, nstep))
+        self._ck(self._L.cpml_get_seismograms(self._h, _d(sx), _d(sy)))
+        return sx, sy
+
+    def get_energy(self):
+        n = self.cfg.nstep
+        tot, ek, ep = np.zeros(n), np.zeros(n), np.zeros(n)
+        self._ck(self._L.cpml_get_energy(self._h, _d(tot), _d(ek), _d(ep)))
+        return tot, ek, ep
+
+    def get_plane(self, field, kglobal=0):
+        out = np.zeros((self.cfg.ny, self.cfg.nx))
+        self._ck(self._L.cpml_get_plane(self._h, field, kglobal, _d(out)))
+        return out
+
+    def get_field(self, field):
+        shape = (self.nzl, self.cfg.ny, self.cfg.nx) if self.cfg.ndim == 3 else (self.cfg.ny, self.cfg.nx)
+        out = np.zeros(shape)
+        self._ck(self._L.cpml_get_field(self._h, field, _d(out)))
+        return out
+
+    def get_maxnorm(self):
+        v = C.c_double()
+        self._ck(self._L.cpml_get_maxnorm(self._h, C.byref(v)))
+        return v.value
+
+    def enable_kernel_timing(self, on=True):
+        self._ck(self._L.cpml_enable_kernel_timing(self._h, int(on)))
+
+    def get_kernel_times(self, reset=True):
+        a, b, n = C.c_double(), C.c_double(), C.c_int64()
+        self._ck(self._L.cpml_get_kernel_times(self._h, C.byref(a), C.byref(b), C.byref(n), int(reset)))
+        return a.value, b.value, n.value
+
+    def algorithmic_bytes(self):
+        a, b = C.c_double(), C.c_double()
+        self._ck(self._L.cpml_algorithmic_bytes(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value

@@ -1,0 +1,73 @@
+"""Reference configurations used by the tests, built with the ORACLE's own set-up
+functions (oracle/cpml_oracle.c) so that oracle tests do not depend on the product."""
+import math
+
+import numpy as np
+
+from oracle import oracle as O
+
+PI = 3.141592653589793238462643
+
+
+def cfg2d(order=2, nx=101, ny=641, nstep=None, npml=10, material="homogeneous", nrec=2,
+          ydeb=2300.0, yfin=300.0, k_max=1.0):
+    """seismic_CPML_2D_isotropic_{second,fourth}_order.f90 defaults (:138-218)."""
+    dx = 10.0
+    dt = 2e-3 if order == 2 else 2e-3 / 2
+    if nstep is None:
+        nstep = 2000 if order == 2 else 4000
+    cp = 3300.0
+    cs = cp / 1.732
+    rho = 2800.0
+    f0 = 7.0
+    t0 = 1.2 / f0
+    amax = 2.0 * PI * (f0 / 2.0)
+    px = O.pml_profile(nx, dx, dt, npml, cp=cp, alpha_max_pml=amax, clamp_alpha=True, k_max_pml=k_max)
+    py = O.pml_profile(ny, dx, dt, npml, cp=cp, alpha_max_pml=amax, origin_top_uses_n=(order == 4),
+                       k_max_pml=k_max)
+    fx, fy = O.source_series(nstep, dt, f0, t0, 1e7, 135.0)
+    isrc = nx - 2 * npml - 1
+    jsrc = 2 * ny // 3 + 1
+    xs = (isrc - 1) * dx
+    ix, iy, _ = O.find_receivers(nx, ny, dx, dx, nrec, xs - 100.0, ydeb, xs, yfin)
+    lam = np.full((ny, nx), rho * (cp * cp - 2.0 * cs * cs))
+    mu = np.full((ny, nx), rho * cs * cs)
+    r = np.full((ny, nx), rho)
+    if material == "layered":     # slower, lighter layer in the upper third + a smooth gradient in x
+        jj, ii = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+        scale = np.where(jj > 2 * ny // 3, 0.64, 1.0) * (1.0 + 0.1 * ii / nx)
+        lam, mu = lam * scale, mu * scale
+        r = r * np.where(jj > 2 * ny // 3, 0.9, 1.0)
+    return dict(order=order, nx=nx, ny=ny, deltax=dx, deltay=dx, deltat=dt, nstep=nstep,
+                npoints_pml=npml, isource=isrc, jsource=jsrc, lam=lam.ravel(), mu=mu.ravel(),
+                rho=r.ravel(), prof_x=px, prof_y=py, force_x=fx, force_y=fy, ix_rec=ix, iy_rec=iy)
+
+
+def cfg3d(nx=37, ny=45, nz=40, nstep=150, npml=6, nrec=2, dt=1.6e-3, k_max=1.0):
+    """seismic_CPML_3D_isotropic_MPI_OpenMP.f90 (:124-218) on a reduced grid."""
+    dx = 10.0
+    cp = 3300.0
+    cs = cp / 1.732
+    rho = 2800.0
+    f0 = 7.0
+    t0 = 1.2 / f0
+    amax = 2.0 * PI * (f0 / 2.0)
+    px = O.pml_profile(nx, dx, dt, npml, cp=cp, alpha_max_pml=amax, clamp_alpha=True, k_max_pml=k_max)
+    py = O.pml_profile(ny, dx, dt, npml, cp=cp, alpha_max_pml=amax, k_max_pml=k_max)
+    pz = O.pml_profile(nz, dx, dt, npml, cp=cp, alpha_max_pml=amax, k_max_pml=k_max)
+    fx, fy = O.source_series(nstep, dt, f0, t0, 1e7, 135.0)
+    isrc = nx - 2 * npml - 1
+    jsrc = 2 * ny // 3 + 1
+    xs = (isrc - 1) * dx
+    ix, iy, _ = O.find_receivers(nx, ny, dx, dx, nrec, xs - 100.0, (ny // 3) * dx, xs, 3 * dx)
+    return dict(nx=nx, ny=ny, nz=nz, deltax=dx, deltay=dx, deltaz=dx, deltat=dt,
+                lam=rho * (cp * cp - 2.0 * cs * cs), mu=rho * cs * cs, lambdaplustwomu=rho * cp * cp,
+                rho=rho, nstep=nstep, npoints_pml=npml, isource=isrc, jsource=jsrc,
+                prof_x=px, prof_y=py, prof_z=pz, force_x=fx, force_y=fy, ix_rec=ix, iy_rec=iy)
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    den = math.sqrt(float(np.sum(b * b)))
+    num = math.sqrt(float(np.sum((a - b) ** 2)))
+    return num / den if den > 0 else num
