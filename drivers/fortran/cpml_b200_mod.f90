@@ -1,0 +1,333 @@
+!
+! cpml_b200_mod.f90 -- ISO_C_BINDING interface to libcpml_b200.so (include/cpml_b200.h).
+!
+! This is the whole "reference-side binding": a SEISMIC_CPML program keeps its parameter
+! block, its set-up phase and its output phase, and replaces the body of
+! "do it = 1,NSTEP" by calls to the routines below.
+!
+! NOTE: no Fortran compiler exists in the image this repository is built in, so this file
+! is shipped UNCOMPILED; it is a literal transcription of the C header (same order, same
+! types).  tests/test_drivers.py checks it against the header symbol by symbol.
+!
+! Build (on a machine with gfortran and the CUDA runtime):
+!   gfortran -O3 -c cpml_b200_mod.f90
+!   gfortran -O3 seismic_CPML_3D_isotropic_b200.f90 cpml_b200_mod.o -L<repo>/seismic_cpml_b200 -lcpml_b200
+!
+module cpml_b200
+
+  use, intrinsic :: iso_c_binding
+  implicit none
+
+  integer(c_int32_t), parameter :: CPML_OK = 0, CPML_EINVAL = 1, CPML_ETOPOLOGY = 2, CPML_ECFL = 3, &
+                                   CPML_ECUDA = 4, CPML_ESTATE = 5, CPML_ENOMEM = 6
+  integer(c_int32_t), parameter :: CPML_AXIS_X = 0, CPML_AXIS_Y = 1, CPML_AXIS_Z = 2
+  integer(c_int32_t), parameter :: CPML_F_VX = 0, CPML_F_VY = 1, CPML_F_VZ = 2, CPML_F_SIGMAXX = 3, &
+                                   CPML_F_SIGMAYY = 4, CPML_F_SIGMAZZ = 5, CPML_F_SIGMAXY = 6, &
+                                   CPML_F_SIGMAXZ = 7, CPML_F_SIGMAYZ = 8
+
+! struct cpml_config, field for field
+  type, bind(C) :: cpml_config
+    integer(c_int32_t) :: ndim, order
+    integer(c_int32_t) :: nx, ny, nz
+    integer(c_int32_t) :: nstep
+    integer(c_int32_t) :: npoints_pml
+    integer(c_int32_t) :: nrec
+    integer(c_int32_t) :: isource, jsource
+    integer(c_int32_t) :: ksource
+    integer(c_int32_t) :: nslabs
+    integer(c_int32_t) :: slab_rank
+    integer(c_int32_t) :: device
+    integer(c_int32_t) :: energy_bug_compat
+    integer(c_int32_t) :: reserved_i(4)
+    real(c_double) :: deltax, deltay, deltaz
+    real(c_double) :: deltat
+    real(c_double) :: lambda, mu, lambdaplustwomu, rho
+    real(c_double) :: cp
+    real(c_double) :: reserved_d(4)
+  end type cpml_config
+
+  interface
+
+    function cpml_abi_version() bind(C, name='cpml_abi_version') result(v)
+      import :: c_int32_t
+      integer(c_int32_t) :: v
+    end function
+
+    function cpml_create(cfg, handle) bind(C, name='cpml_create') result(ierr)
+      import :: c_int32_t, c_ptr, cpml_config
+      type(cpml_config), intent(in) :: cfg
+      type(c_ptr), intent(out) :: handle
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_destroy(handle) bind(C, name='cpml_destroy') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_last_error(handle) bind(C, name='cpml_last_error') result(msg)
+      import :: c_ptr
+      type(c_ptr), value :: handle
+      type(c_ptr) :: msg
+    end function
+
+    function cpml_reset(handle) bind(C, name='cpml_reset') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_set_stream(handle, cuda_stream) bind(C, name='cpml_set_stream') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: handle, cuda_stream
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_set_profiles(handle, axis, a, b, K, a_half, b_half, K_half, n) &
+        bind(C, name='cpml_set_profiles') result(ierr)
+      import :: c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: axis, n
+      real(c_double), intent(in) :: a(*), b(*), K(*), a_half(*), b_half(*), K_half(*)
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_set_material_2d(handle, lambda, mu, rho) bind(C, name='cpml_set_material_2d') result(ierr)
+      import :: c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), intent(in) :: lambda(*), mu(*), rho(*)
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_set_source_series(handle, force_x, force_y, n) bind(C, name='cpml_set_source_series') result(ierr)
+      import :: c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), intent(in) :: force_x(*), force_y(*)
+      integer(c_int32_t), value :: n
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_set_receivers(handle, ix_rec, iy_rec, n) bind(C, name='cpml_set_receivers') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int32_t), intent(in) :: ix_rec(*), iy_rec(*)
+      integer(c_int32_t), value :: n
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_run(handle, it_begin, it_end) bind(C, name='cpml_run') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: it_begin, it_end
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_step_stress(handle, it) bind(C, name='cpml_step_stress') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: it
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_step_velocity(handle, it) bind(C, name='cpml_step_velocity') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: it
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_step_finish(handle, it) bind(C, name='cpml_step_finish') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: it
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_synchronize(handle) bind(C, name='cpml_synchronize') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_halo_plane(handle, field, klocal, device_ptr, nbytes) bind(C, name='cpml_halo_plane') result(ierr)
+      import :: c_int32_t, c_int64_t, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: field, klocal
+      type(c_ptr), intent(out) :: device_ptr
+      integer(c_int64_t), intent(out) :: nbytes
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_copy_plane(dst, klocal_dst, src, klocal_src, field) bind(C, name='cpml_copy_plane') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: dst, src
+      integer(c_int32_t), value :: klocal_dst, klocal_src, field
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_get_seismograms(handle, sisvx, sisvy) bind(C, name='cpml_get_seismograms') result(ierr)
+      import :: c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), intent(out) :: sisvx(*), sisvy(*)
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_get_energy(handle, total, kinetic, potential) bind(C, name='cpml_get_energy') result(ierr)
+      import :: c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), intent(out) :: total(*), kinetic(*), potential(*)
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_get_plane(handle, field, kglobal, plane) bind(C, name='cpml_get_plane') result(ierr)
+      import :: c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: field, kglobal
+      real(c_double), intent(out) :: plane(*)
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_get_field(handle, field, values) bind(C, name='cpml_get_field') result(ierr)
+      import :: c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: field
+      real(c_double), intent(out) :: values(*)
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_get_maxnorm(handle, vnorm) bind(C, name='cpml_get_maxnorm') result(ierr)
+      import :: c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), intent(out) :: vnorm
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_get_kernel_times(handle, ms_stress, ms_velocity, n_launches, reset) &
+        bind(C, name='cpml_get_kernel_times') result(ierr)
+      import :: c_int32_t, c_int64_t, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), intent(out) :: ms_stress, ms_velocity
+      integer(c_int64_t), intent(out) :: n_launches
+      integer(c_int32_t), value :: reset
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_enable_kernel_timing(handle, on) bind(C, name='cpml_enable_kernel_timing') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: on
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_algorithmic_bytes(handle, bytes_stress, bytes_velocity) &
+        bind(C, name='cpml_algorithmic_bytes') result(ierr)
+      import :: c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), intent(out) :: bytes_stress, bytes_velocity
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_host_pml_profile(n, delta, deltat, npoints_pml, use_pml_min, use_pml_max, cp, rcoef, npower, &
+        k_max_pml, alpha_max_pml, origin_top_uses_n, clamp_alpha, a, b, K, a_half, b_half, K_half) &
+        bind(C, name='cpml_host_pml_profile') result(ierr)
+      import :: c_int32_t, c_double
+      integer(c_int32_t), value :: n, npoints_pml, use_pml_min, use_pml_max, origin_top_uses_n, clamp_alpha
+      real(c_double), value :: delta, deltat, cp, rcoef, npower, k_max_pml, alpha_max_pml
+      real(c_double), intent(out) :: a(*), b(*), K(*), a_half(*), b_half(*), K_half(*)
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_host_source_series(nstep, deltat, f0, t0, factor, angle_force_deg, force_x, force_y) &
+        bind(C, name='cpml_host_source_series') result(ierr)
+      import :: c_int32_t, c_double
+      integer(c_int32_t), value :: nstep
+      real(c_double), value :: deltat, f0, t0, factor, angle_force_deg
+      real(c_double), intent(out) :: force_x(*), force_y(*)
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_host_find_receivers(nx, ny, deltax, deltay, nrec, xdeb, ydeb, xfin, yfin, ix_rec, iy_rec, dist) &
+        bind(C, name='cpml_host_find_receivers') result(ierr)
+      import :: c_int32_t, c_double
+      integer(c_int32_t), value :: nx, ny, nrec
+      real(c_double), value :: deltax, deltay, xdeb, ydeb, xfin, yfin
+      integer(c_int32_t), intent(out) :: ix_rec(*), iy_rec(*)
+      real(c_double), intent(out) :: dist(*)
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_host_courant(cp, deltat, deltax, deltay, deltaz) bind(C, name='cpml_host_courant') result(c)
+      import :: c_double
+      real(c_double), value :: cp, deltat, deltax, deltay, deltaz
+      real(c_double) :: c
+    end function
+
+    function cpml_host_write_seismograms(dir, sisvx, sisvy, nt, nrec, deltat) &
+        bind(C, name='cpml_host_write_seismograms') result(ierr)
+      import :: c_int32_t, c_double, c_char
+      character(kind=c_char), intent(in) :: dir(*)
+      real(c_double), intent(in) :: sisvx(*), sisvy(*)
+      integer(c_int32_t), value :: nt, nrec
+      real(c_double), value :: deltat
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_host_write_energy_3d(path, total, nt, deltat) bind(C, name='cpml_host_write_energy_3d') result(ierr)
+      import :: c_int32_t, c_double, c_char
+      character(kind=c_char), intent(in) :: path(*)
+      real(c_double), intent(in) :: total(*)
+      integer(c_int32_t), value :: nt
+      real(c_double), value :: deltat
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_host_write_energy_2d(path, kinetic, potential, nt, deltat) &
+        bind(C, name='cpml_host_write_energy_2d') result(ierr)
+      import :: c_int32_t, c_double, c_char
+      character(kind=c_char), intent(in) :: path(*)
+      real(c_double), intent(in) :: kinetic(*), potential(*)
+      integer(c_int32_t), value :: nt
+      real(c_double), value :: deltat
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_host_create_color_image(dir, image_data_2d, nx, ny, it, isource, jsource, ix_rec, iy_rec, nrec, &
+        npoints_pml, use_pml_xmin, use_pml_xmax, use_pml_ymin, use_pml_ymax, field_number) &
+        bind(C, name='cpml_host_create_color_image') result(ierr)
+      import :: c_int32_t, c_double, c_char
+      character(kind=c_char), intent(in) :: dir(*)
+      real(c_double), intent(in) :: image_data_2d(*)
+      integer(c_int32_t), value :: nx, ny, it, isource, jsource, nrec, npoints_pml
+      integer(c_int32_t), intent(in) :: ix_rec(*), iy_rec(*)
+      integer(c_int32_t), value :: use_pml_xmin, use_pml_xmax, use_pml_ymin, use_pml_ymax, field_number
+      integer(c_int32_t) :: ierr
+    end function
+
+  end interface
+
+contains
+
+! stop with the library's message, like the reference's "stop '...'" statements
+  subroutine cpml_check(ierr, handle, where)
+    integer(c_int32_t), intent(in) :: ierr
+    type(c_ptr), intent(in) :: handle
+    character(len=*), intent(in) :: where
+    type(c_ptr) :: msg
+    character(kind=c_char), pointer :: chars(:)
+    integer :: n
+    if (ierr == CPML_OK) return
+    msg = cpml_last_error(handle)
+    if (c_associated(msg)) then
+      call c_f_pointer(msg, chars, [512])
+      n = 0
+      do while (n < 512)
+        if (chars(n+1) == c_null_char) exit
+        n = n + 1
+      enddo
+      print *,'libcpml_b200 error in ',where,': ',chars(1:n)
+    endif
+    stop 'libcpml_b200 call failed'
+  end subroutine cpml_check
+
+end module cpml_b200

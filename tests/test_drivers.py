@@ -1,0 +1,111 @@
+"""Host drivers over the C ABI: the Fortran ISO_C_BINDING module is checked against the
+header symbol by symbol (it cannot be compiled here: no Fortran compiler), the C++ driver
+is built, and -- on a GPU -- run end to end and compared with the oracle through its
+output files."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import refcfg
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRV = os.path.join(ROOT, "drivers")
+
+
+def _header_functions():
+    h = open(os.path.join(ROOT, "include", "cpml_b200.h")).read()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(?:int32_t|double|const char \*)\s*(cpml_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", h, flags=re.S):
+        args = [a.strip() for a in m.group(2).split(",") if a.strip() and a.strip() != "void"]
+        out[m.group(1)] = len(args)
+    return out
+
+
+def test_fortran_module_binds_every_symbol_with_matching_arity():
+    funcs = _header_functions()
+    assert len(funcs) >= 33
+    f90 = open(os.path.join(DRV, "fortran", "cpml_b200_mod.f90")).read()
+    f90 = re.sub(r"&\s*\n\s*", " ", f90)          # join continuation lines
+    bound = {}
+    for m in re.finditer(r"function\s+(cpml_[a-z0-9_]+)\s*\(([^)]*)\)\s*bind\(C,\s*name='([a-z0-9_]+)'\)", f90):
+        assert m.group(1) == m.group(3)
+        bound[m.group(1)] = len([a for a in m.group(2).split(",") if a.strip()])
+    assert set(bound) == set(funcs), set(bound) ^ set(funcs)
+    for name, n in funcs.items():
+        assert bound[name] == n, (name, bound[name], n)
+    # the derived type mirrors struct cpml_config: 15 + 4 int32, then 9 + 4 doubles
+    t = f90[f90.index("type, bind(C) :: cpml_config"):f90.index("end type cpml_config")]
+    ints = re.findall(r"integer\(c_int32_t\)\s*::\s*(.*)", t)
+    reals = re.findall(r"real\(c_double\)\s*::\s*(.*)", t)
+    assert sum(len(x.split(",")) for x in ints) == 16      # 15 named + reserved_i(4)
+    assert sum(len(x.split(",")) for x in reals) == 10     # 9 named + reserved_d(4)
+
+
+def test_fortran_driver_keeps_the_reference_parameter_surface():
+    src = open(os.path.join(DRV, "fortran", "seismic_CPML_3D_isotropic_b200.f90")).read()
+    for name in ("NX = 101", "NY = 641", "NZ = 640", "DELTAX = 10.d0", "NSTEP = 2500", "DELTAT = 1.6d-3",
+                 "NPOINTS_PML = 10", "ISOURCE = NX - 2*NPOINTS_PML - 1", "JSOURCE = 2 * NY / 3 + 1",
+                 "ANGLE_FORCE = 135.d0", "NREC = 2", "IT_DISPLAY = 100", "f0 = 7.d0", "factor = 1.d7"):
+        assert name in src, name
+    for call in ("cpml_create", "cpml_set_profiles", "cpml_set_source_series", "cpml_set_receivers", "cpml_run",
+                 "cpml_get_seismograms", "cpml_get_energy", "cpml_get_plane", "cpml_get_maxnorm", "cpml_destroy"):
+        assert call in src, call
+
+
+@pytest.fixture(scope="module")
+def driver_exe():
+    subprocess.run(["make", "-C", DRV, "-s"], check=True)
+    exe = os.path.join(DRV, "xseismic_cpml")
+    assert os.path.exists(exe)
+    return exe
+
+
+def test_cpp_driver_builds_and_fails_loudly_without_gpu(driver_exe, tmp_path):
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    r = subprocess.run([driver_exe, "--program", "2d_second", "NSTEP=4", "--out", str(tmp_path), "--no-images"],
+                       capture_output=True, text=True)
+    assert "Courant number is 0.933380951166243" in r.stdout
+    if not has_gpu:
+        assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("program,order", [("2d_second", 2), ("2d_fourth", 4)])
+def test_cpp_driver_2d_output_files_match_oracle(driver_exe, tmp_path, program, order):
+    nstep = 400
+    r = subprocess.run([driver_exe, "--program", program, f"NSTEP={nstep}", "--out", str(tmp_path)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "End of the simulation" in r.stdout and f"Time step # 5 out of {nstep}" in r.stdout
+    c = refcfg.cfg2d(order, nstep=nstep)
+    o = O.run_2d(**c)
+    for rec in (1, 2):
+        for comp, key in (("Vx", "sisvx"), ("Vy", "sisvy")):
+            d = np.loadtxt(tmp_path / f"{comp}_file_{rec:03d}.dat")
+            assert d.shape == (nstep, 2)
+            # the files hold single-precision values, like the reference's sngl(...)
+            assert np.array_equal(d[:, 1].astype(np.float32), o[key][rec - 1].astype(np.float32))
+    e = np.loadtxt(tmp_path / "energy.dat")
+    assert e.shape == (nstep, 4)
+    assert np.allclose(e[:, 1], o["energy_kinetic"], rtol=1e-6, atol=0)
+    assert os.path.exists(tmp_path / f"image{(200 if order == 4 else 100):06d}_Vx.pnm")
+
+
+@pytest.mark.gpu
+def test_cpp_driver_3d_small_grid(driver_exe, tmp_path):
+    r = subprocess.run([driver_exe, "--program", "3d_iso", "NX=48", "NY=60", "NZ=40", "NSTEP=120", "NPOINTS_PML=6",
+                        "ydeb=300", "yfin=100", "IT_DISPLAY=50", "--out", str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    d = np.loadtxt(tmp_path / "Vx_file_001.dat")
+    e = np.loadtxt(tmp_path / "energy.dat")
+    assert d.shape == (120, 2) and e.shape == (120, 2) and np.abs(d[:, 1]).max() > 0 and np.all(np.isfinite(e))
+    assert os.path.exists(tmp_path / "image000100_Vy.pnm")
