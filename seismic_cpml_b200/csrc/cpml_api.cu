@@ -66,9 +66,10 @@ struct cpml_handle {
     double *d_partials = nullptr;
     unsigned long long *d_maxbits = nullptr;
 
-    // launch geometry
-    dim3 grid, block;
-    int kchunk = 1, nblocks = 0;
+    // launch geometry: 3-D kernels run once per region (interior box + PML shell boxes)
+    std::vector<Box3D> regions;
+    dim3 grid, block;          // 2-D kernels
+    int nblocks = 0;           // energy partial slots
 
     // kernel timing
     bool timing = false;
@@ -204,31 +205,83 @@ static int32_t create_impl(cpml_handle *h)
     CK(cudaMalloc(&h->d_iy_rec, std::max(1, c.nrec) * sizeof(int)));
     CK(cudaMalloc(&h->d_maxbits, sizeof(unsigned long long)));
 
-    // ---- launch geometry (CPML_TX / CPML_TY / CPML_ZCHUNKS override for tuning)
-    if (c.ndim == 3) {
-        const int tx = env_int("CPML_TX", 32), ty = env_int("CPML_TY", 8);
-        h->block = dim3(tx, ty, 1);
-        const int gx = (c.nx + tx - 1) / tx, gy = (c.ny + ty - 1) / ty;
-        int zch = env_int("CPML_ZCHUNKS", 0);
-        if (zch <= 0) {
-            // enough blocks for ~4 waves of resident CTAs, but keep chunks >= 16 planes so
-            // that the register-carried z reuse pays for the extra plane at chunk starts
-            const int resident = h->sm_count * std::max(1, 2048 / (tx * ty));
-            zch = (4 * resident + gx * gy - 1) / (gx * gy);
-            zch = std::max(1, std::min(zch, std::max(1, h->nzl / 16)));
-        }
-        zch = std::max(1, std::min(zch, h->nzl));
-        h->kchunk = (h->nzl + zch - 1) / zch;
-        zch = (h->nzl + h->kchunk - 1) / h->kchunk;
-        h->grid = dim3(gx, gy, zch);
-    } else {
+    // ---- launch geometry of the 2-D kernels (the 3-D regions need the shells: finalize())
+    if (c.ndim == 2) {
         h->block = dim3(32, 8, 1);
         h->grid = dim3((c.nx + 31) / 32, (c.ny + 7) / 8, 1);
-        h->kchunk = 1;
+        h->nblocks = h->grid.x * h->grid.y;
+        CK(cudaMalloc(&h->d_partials, 2 * (size_t)h->nblocks * sizeof(double)));
     }
-    h->nblocks = h->grid.x * h->grid.y * h->grid.z;
-    CK(cudaMalloc(&h->d_partials, 2 * (size_t)h->nblocks * sizeof(double)));
     return cpml_reset(h);
+}
+
+// Adds the box [i0,i1] x [j0,j1] x [k0,k1] (k local) to the region list, if non-empty.
+static void add_region(cpml_handle *h, int i0, int i1, int j0, int j1, int k0, int k1, bool pml, int tx, int ty)
+{
+    if (i0 > i1 || j0 > j1 || k0 > k1) return;
+    Box3D b{};
+    b.i0 = i0; b.i1 = i1; b.j0 = j0; b.j1 = j1; b.k0 = k0; b.k1 = k1;
+    b.ia = ((i0 - 1) / 16) * 16 + 1;        // 128-byte line aligned start of the thread grid
+    b.pml = pml ? 1 : 0;
+    b.tx = tx; b.ty = ty;
+    b.gx = (i1 - b.ia + 1 + tx - 1) / tx;
+    b.gy = (j1 - j0 + 1 + ty - 1) / ty;
+    // z chunks: enough blocks for ~4 waves of resident CTAs (the kernels are latency-bound
+    // with fewer), but chunks of >= 8 planes so that the register-carried z reuse pays for
+    // the extra plane fetched at every chunk start.  CPML_ZCHUNKS overrides.
+    const int nk = k1 - k0 + 1;
+    int zch = env_int("CPML_ZCHUNKS", 0);
+    if (zch <= 0) {
+        const int resident = h->sm_count * std::max(1, 2048 / (tx * ty));
+        zch = (4 * resident + b.gx * b.gy - 1) / (b.gx * b.gy);
+        zch = std::min(zch, std::max(1, nk / 8));
+    }
+    zch = std::max(1, std::min(zch, nk));
+    b.kchunk = (nk + zch - 1) / zch;
+    b.gz = (nk + b.kchunk - 1) / b.kchunk;
+    b.pbase = h->nblocks;
+    h->nblocks += b.gx * b.gy * b.gz;
+    h->regions.push_back(b);
+}
+
+// Splits the slab into the PML-free interior box and up to six shell boxes; every grid
+// point falls in exactly one region.
+static void build_regions(cpml_handle *h)
+{
+    const cpml_config &c = h->cfg;
+    const Shell &sx = h->shell[0], &sy = h->shell[1], &sz = h->shell[2];
+    // thread tile: half-warp rows waste fewer lanes on narrow grids (NX = 101: 112 of 128
+    // lanes instead of 101 of 128); measured in profiles/r01_v2_tile_sweep.txt
+    int tx = env_int("CPML_TX", c.nx <= 160 ? 16 : 32), ty = env_int("CPML_TY", 8);
+    if (!tile_supported(tx, ty)) { tx = 32; ty = 8; }
+    int ptx = env_int("CPML_PML_TX", 16), pty = env_int("CPML_PML_TY", 8);   // thin x shells: half-warp rows
+    if (!tile_supported(ptx, pty)) { ptx = 16; pty = 8; }
+    h->regions.clear();
+    h->nblocks = 0;
+    // local k range outside the z shells
+    const int kz0 = std::max(1, sz.lo + 1 - h->koff), kz1 = std::min(h->nzl, sz.hi - 1 - h->koff);
+    const int jy0 = sy.lo + 1, jy1 = sy.hi - 1;
+    const int ix0 = sx.lo + 1, ix1 = sx.hi - 1;
+    // Default: ONE launch over the whole slab.  Splitting into an interior launch plus six
+    // shell launches (CPML_REGIONS=1) was measured slower on B200 (profiles/r01_v2_region_sweep.txt:
+    // 12.1 vs 16.5 Gpts/s on 101x641x640): the <PML=true> kernel is as fast per byte as the lean
+    // one once its loads are hoisted, and seven serial launches add tails.
+    if (!env_int("CPML_REGIONS", 0)) {
+        const bool any_shell = sx.size() + sy.size() + sz.size() > 0;
+        add_region(h, 1, c.nx, 1, c.ny, 1, h->nzl, any_shell, tx, ty);
+        return;
+    }
+    add_region(h, ix0, ix1, jy0, jy1, kz0, kz1, false, tx, ty);                    // interior
+    add_region(h, 1, c.nx, 1, c.ny, 1, std::min(h->nzl, kz0 - 1), true, tx, ty);   // z-
+    add_region(h, 1, c.nx, 1, c.ny, std::max(1, kz1 + 1), h->nzl, true, tx, ty);   // z+
+    if (kz0 <= kz1) {
+        add_region(h, 1, c.nx, 1, std::min(c.ny, jy0 - 1), kz0, kz1, true, tx, ty);    // y-
+        add_region(h, 1, c.nx, std::max(1, jy1 + 1), c.ny, kz0, kz1, true, tx, ty);    // y+
+        if (jy0 <= jy1) {
+            add_region(h, 1, std::min(c.nx, ix0 - 1), jy0, jy1, kz0, kz1, true, ptx, pty);   // x-
+            add_region(h, std::max(1, ix1 + 1), c.nx, jy0, jy1, kz0, kz1, true, ptx, pty);   // x+
+        }
+    }
 }
 
 extern "C" int32_t cpml_create(const cpml_config *cfg, cpml_handle **out)
@@ -439,6 +492,11 @@ static int32_t finalize(cpml_handle *h)
         h->nz_own[ax][0] = n0;
         h->nz_own[ax][1] = n1;
     }
+    if (c.ndim == 3) {
+        build_regions(h);
+        CK(cudaMalloc(&h->d_partials, 2 * (size_t)std::max(1, h->nblocks) * sizeof(double)));
+        CK(cudaMemset(h->d_partials, 0, 2 * (size_t)std::max(1, h->nblocks) * sizeof(double)));
+    }
     h->finalized = true;
     return CPML_OK;
 }
@@ -457,7 +515,7 @@ static Params3D make_p3(cpml_handle *h, int it)
     const cpml_config &c = h->cfg;
     Params3D p{};
     p.nx = c.nx; p.ny = c.ny; p.nzl = h->nzl; p.nz = c.nz; p.koff = h->koff;
-    p.pitch = h->pitch; p.plane = h->plane; p.kchunk = h->kchunk;
+    p.pitch = h->pitch; p.plane = h->plane;
     p.vx = h->f0[0]; p.vy = h->f0[1]; p.vz = h->f0[2];
     p.sxx = h->f0[3]; p.syy = h->f0[4]; p.szz = h->f0[5];
     p.sxy = h->f0[6]; p.sxz = h->f0[7]; p.syz = h->f0[8];
@@ -479,6 +537,11 @@ static Params3D make_p3(cpml_handle *h, int it)
     p.npml = c.npoints_pml; p.energy_bug_compat = c.energy_bug_compat;
     p.rho = c.rho; p.lambda = c.lambda; p.mu = c.mu;
     p.partials = h->d_partials; p.nblocks = h->nblocks;
+    p.kunit = 1;
+    for (int ax = 0; ax < 3; ax++)
+        for (int q : {2, 5})
+            for (double K : h->hprof[ax][q])
+                if (K != 1.0) p.kunit = 0;
     return p;
 }
 
@@ -531,9 +594,13 @@ extern "C" int32_t cpml_step_stress(cpml_handle *h, int32_t it)
     rc = finalize(h); if (rc) return rc;
     CK(cudaSetDevice(h->device));
     rc = time_begin(h, 0); if (rc) return rc;
-    if (h->cfg.ndim == 3) launch_stress3d(make_p3(h, it), h->grid, h->block, h->stream);
-    else                  launch_stress2d(make_p2(h, it), h->grid, h->block, h->stream);
-    h->n_launches++;
+    if (h->cfg.ndim == 3) {
+        const Params3D p = make_p3(h, it);
+        for (const Box3D &b : h->regions) { launch_stress3d(p, b, h->stream); h->n_launches++; }
+    } else {
+        launch_stress2d(make_p2(h, it), h->grid, h->block, h->stream);
+        h->n_launches++;
+    }
     rc = time_end(h); if (rc) return rc;
     CK(cudaGetLastError());
     return CPML_OK;
@@ -546,9 +613,13 @@ extern "C" int32_t cpml_step_velocity(cpml_handle *h, int32_t it)
     rc = finalize(h); if (rc) return rc;
     CK(cudaSetDevice(h->device));
     rc = time_begin(h, 1); if (rc) return rc;
-    if (h->cfg.ndim == 3) launch_velocity3d(make_p3(h, it), h->grid, h->block, h->stream);
-    else                  launch_velocity2d(make_p2(h, it), h->grid, h->block, h->stream);
-    h->n_launches++;
+    if (h->cfg.ndim == 3) {
+        const Params3D p = make_p3(h, it);
+        for (const Box3D &b : h->regions) { launch_velocity3d(p, b, h->stream); h->n_launches++; }
+    } else {
+        launch_velocity2d(make_p2(h, it), h->grid, h->block, h->stream);
+        h->n_launches++;
+    }
     rc = time_end(h); if (rc) return rc;
     CK(cudaGetLastError());
     return CPML_OK;

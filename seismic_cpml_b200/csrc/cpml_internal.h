@@ -41,7 +41,6 @@ struct Params3D {
     int koff;                 // offset_k = rank * NZ_LOCAL (3D-iso :397)
     int pitch;                // row pitch in doubles
     long long plane;          // plane pitch in doubles (= pitch * ny)
-    int kchunk;               // planes marched by one block
     // fields: pointer to element (i=1, j=1, k=0)
     double *vx, *vy, *vz, *sxx, *syy, *szz, *sxy, *sxz, *syz;
     // shells
@@ -63,6 +62,20 @@ struct Params3D {
     double rho, lambda, mu;
     double *partials;         // [2][nblocks] kinetic / potential per block
     int nblocks;
+    int kunit;                // every K profile == 1: the value/K division is dropped (exact)
+};
+
+// One launch region of a 3-D kernel: the box [i0,i1] x [j0,j1] x [k0,k1] (1-based, k local).
+// The thread grid starts at ia <= i0 (ia-1 a multiple of 4, so warp rows stay 32-byte
+// sector aligned); lanes with i < i0 idle.
+struct Box3D {
+    int i0, i1, j0, j1, k0, k1;
+    int ia;
+    int kchunk;               // planes marched by one block
+    int pbase;                // offset of this region's blocks in the energy partials
+    int pml;                  // 1: region touches a PML shell -> <PML=true> instantiation
+    int tx, ty;               // thread tile
+    int gx, gy, gz;           // grid
 };
 
 struct Post3D {
@@ -109,9 +122,9 @@ struct Post2D {
 };
 
 // launchers (kernels_3d.cu / kernels_2d.cu)
-struct LaunchCfg { int tx, ty; };
-void launch_stress3d(const Params3D &p, dim3 grid, dim3 block, cudaStream_t s);
-void launch_velocity3d(const Params3D &p, dim3 grid, dim3 block, cudaStream_t s);
+void launch_stress3d(const Params3D &p, const Box3D &b, cudaStream_t s);
+void launch_velocity3d(const Params3D &p, const Box3D &b, cudaStream_t s);
+bool tile_supported(int tx, int ty);
 void launch_post3d(const Post3D &p, cudaStream_t s);
 void launch_stress2d(const Params2D &p, dim3 grid, dim3 block, cudaStream_t s);
 void launch_velocity2d(const Params2D &p, dim3 grid, dim3 block, cudaStream_t s);

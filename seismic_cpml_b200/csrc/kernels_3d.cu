@@ -8,20 +8,29 @@
 //                 Dirichlet faces (:1087-1121), per-block energy partials (:1131-1177)
 //   k_post3d      energy sum of the step (:1179) + seismogram sample (:1124-1129)
 //
-// Mapping: one thread per (i,j) column, x across the warp (coalesced 256 B rows), each
-// block marches a chunk of z planes.  Values reused along z (vx,vy at k / k+1, vz at
-// k-1 / k; sigmaxz, sigmayz at k-1 / k, sigmazz at k / k+1) stay in registers, so every
-// field plane is fetched from HBM once per kernel; in-plane neighbours (radius 1) are
-// re-read through L1, which holds them from the loads of the neighbouring threads.
+// Each kernel is launched once per REGION of the slab (cpml_api.cu builds the list): the
+// PML-free interior box runs the <PML=false> instantiation, which contains no memory-
+// variable code at all (lean registers, no divergence); the up to six shell boxes
+// (z-, z+, y-, y+, x-, x+) run <PML=true>.  Every grid point belongs to exactly one region,
+// and both instantiations evaluate the same expressions in the same order, so the split
+// does not change a single bit.  Outside the shells the reference recursion is the
+// identity (a = 0, K = 1, memory variable == 0), which is why skipping it is exact.
+//
+// Mapping: one thread per (i,j) column, x across the warp (coalesced rows), each block
+// marches a chunk of z planes.  Values reused along z (vx,vy at k / k+1, vz at k-1 / k;
+// sigmaxz, sigmayz at k-1 / k, sigmazz at k / k+1) stay in registers, so every field
+// plane is fetched from HBM once per kernel; in-plane neighbours (radius 1) are re-read
+// through L1, which holds them from the loads of the neighbouring threads.  ALL loads of
+// an iteration are issued before the first use (the kernels are latency-bound otherwise:
+// ncu showed 16.9 long-scoreboard stalls per issue with loads behind the PML branches).
 // Streamed read-modify-write traffic (the six stresses in k_stress3d, the three
-// velocities in k_velocity3d) uses evict-first loads/stores so that it does not push
-// the reused planes out of L1.  C-PML memory variables are touched only by threads
-// inside a PML shell; elsewhere the reference recursion is the identity (a = 0, K = 1,
-// memory variable == 0), so skipping it is exact.
+// velocities in k_velocity3d) uses evict-first loads/stores so that it does not push the
+// reused planes out of L1.
 //
 // Compiled with -fmad=false: every product and sum is rounded separately, in the order
 // the Fortran source writes them, so fields are bit-identical to an IEEE (non-FMA)
-// build of the reference loops.
+// build of the reference loops.  KUNIT instantiations (all K profiles == 1, the
+// isotropic programs' K_MAX_PML = 1) drop the value/K division, which is exact.
 #include "cpml_internal.h"
 
 namespace cpml {
@@ -30,13 +39,14 @@ __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p);
 __device__ __forceinline__ void st_stream(double *p, double v) { __stcs(p, v); }
 
 // memory_x = b * memory_x + a * value ; value = value / K + memory_x   (e.g. :845-851)
-__device__ __forceinline__ double cpml_apply(double *__restrict__ mem, long long q,
+// `m` is the old memory variable (already loaded); the new one is stored at mem[q].
+template <bool KUNIT>
+__device__ __forceinline__ double cpml_apply(double *__restrict__ mem, long long q, double m,
                                              double b, double a, double K, double value)
 {
-    double m = mem[q];
     m = b * m + a * value;
     mem[q] = m;
-    return value / K + m;
+    return KUNIT ? value + m : value / K + m;
 }
 
 __device__ __forceinline__ int shell_index(int i, int lo, int hi)
@@ -48,21 +58,21 @@ __device__ __forceinline__ int shell_index(int i, int lo, int hi)
 // my: 0 dvy_dy  1 dvx_dy  2 dvz_dy  3 dsigmaxy_dy  4 dsigmayy_dy  5 dsigmayz_dy
 // mz: 0 dvz_dz  1 dvx_dz  2 dvy_dz  3 dsigmaxz_dz  4 dsigmayz_dz  5 dsigmazz_dz
 
-template <int TX, int TY>
-__global__ void __launch_bounds__(TX *TY)
-k_stress3d(const __grid_constant__ Params3D p)
+template <bool PML, bool KUNIT, int TX, int TY, int MINB>
+__global__ void __launch_bounds__(TX *TY, MINB)
+k_stress3d(const __grid_constant__ Params3D p, const __grid_constant__ Box3D bx)
 {
-    const int i = blockIdx.x * TX + threadIdx.x + 1;
-    const int j = blockIdx.y * TY + threadIdx.y + 1;
-    if (i > p.nx || j > p.ny) return;
-    const int kb = 1 + blockIdx.z * p.kchunk;
-    const int ke = min(p.nzl, kb + p.kchunk - 1);
+    const int i = bx.ia + blockIdx.x * TX + threadIdx.x;
+    const int j = bx.j0 + blockIdx.y * TY + threadIdx.y;
+    if (i < bx.i0 || i > bx.i1 || j > bx.j1) return;
+    const int kb = bx.k0 + blockIdx.z * bx.kchunk;
+    const int ke = min(bx.k1, kb + bx.kchunk - 1);
     const int pitch = p.pitch;
     const long long pl = p.plane;
     long long q = (long long)kb * pl + (long long)(j - 1) * pitch + (i - 1);
 
-    const bool in_x = (i <= p.xlo) || (i >= p.xhi);
-    const bool in_y = (j <= p.ylo) || (j >= p.yhi);
+    const bool in_x = PML && ((i <= p.xlo) || (i >= p.xhi));
+    const bool in_y = PML && ((j <= p.ylo) || (j >= p.yhi));
     const int sx = in_x ? shell_index(i, p.xlo, p.xhi) : 0;
     const int sy = in_y ? shell_index(j, p.ylo, p.yhi) : 0;
 
@@ -75,60 +85,93 @@ k_stress3d(const __grid_constant__ Params3D p)
     const double odx = p.odx, ody = p.ody, odz = p.odz;
     const double dt_l = p.dt_lambda, dt_m = p.dt_mu, dt_l2m = p.dt_lambdaplus2mu;
 
+    // x / y coefficients of this column (PML only)
+    double ax = 0, bxc = 0, Kx = 1, axh = 0, bxh = 0, Kxh = 1, ay = 0, by = 0, Ky = 1, ayh = 0, byh = 0, Kyh = 1;
+    if (PML) {
+        if (in_x) { ax = p.cx.a[i]; bxc = p.cx.b[i]; axh = p.cx.a_half[i]; bxh = p.cx.b_half[i];
+                    if (!KUNIT) { Kx = p.cx.K[i]; Kxh = p.cx.K_half[i]; } }
+        if (in_y) { ay = p.cy.a[j]; by = p.cy.b[j]; ayh = p.cy.a_half[j]; byh = p.cy.b_half[j];
+                    if (!KUNIT) { Ky = p.cy.K[j]; Kyh = p.cy.K_half[j]; } }
+    }
+
     double vx_c = p.vx[q], vy_c = p.vy[q];
     double vz_m = p.vz[q - pl], vz_c = p.vz[q];
 
     for (int k = kb; k <= ke; ++k, q += pl) {
         const int kg = k + p.koff;                      // :837
-        // next plane (kept in registers for the next iteration)
-        const double vx_n = p.vx[q + pl];
+        // ---- every load of this plane, issued back to back
+        const double vx_n = p.vx[q + pl];               // next plane, kept for the next iteration
         const double vy_n = p.vy[q + pl];
         const double vz_n = p.vz[q + pl];
-        // in-plane neighbours (L1)
-        const double vx_ip = p.vx[q + 1], vx_jp = p.vx[q + pitch];
+        const double vx_ip = p.vx[q + 1], vx_jp = p.vx[q + pitch];      // in-plane neighbours (L1)
         const double vy_im = p.vy[q - 1], vy_jm = p.vy[q - pitch];
         const double vz_im = p.vz[q - 1], vz_jp = p.vz[q + pitch];
+        const double sxx = ld_stream(p.sxx + q), syy = ld_stream(p.syy + q), szz = ld_stream(p.szz + q);
+        const double sxy = ld_stream(p.sxy + q), sxz = ld_stream(p.sxz + q), syz = ld_stream(p.syz + q);
 
-        const bool in_z = (kg <= p.zlo) || (kg >= p.zhi);
-        const long long qx = ((long long)(k - 1) * p.ny + (j - 1)) * p.sxp + sx;
-        const long long qy = ((long long)(k - 1) * p.sy + sy) * pitch + (i - 1);
-        const long long qz = in_z ? ((long long)(shell_index(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1) : 0;
+        const bool in_z = PML && ((kg <= p.zlo) || (kg >= p.zhi));
+        long long qx = 0, qy = 0, qz = 0;
+        double m_x0 = 0, m_x1 = 0, m_x2 = 0, m_y0 = 0, m_y1 = 0, m_y2 = 0, m_z0 = 0, m_z1 = 0, m_z2 = 0;
+        double az = 0, bz = 0, Kz = 1, azh = 0, bzh = 0, Kzh = 1;
+        if (PML) {
+            if (in_x) {
+                qx = ((long long)(k - 1) * p.ny + (j - 1)) * p.sxp + sx;
+                m_x0 = p.mx[0][qx]; m_x1 = p.mx[1][qx]; m_x2 = p.mx[2][qx];
+            }
+            if (in_y) {
+                qy = ((long long)(k - 1) * p.sy + sy) * pitch + (i - 1);
+                m_y0 = p.my[0][qy]; m_y1 = p.my[1][qy]; m_y2 = p.my[2][qy];
+            }
+            if (in_z) {
+                qz = ((long long)(shell_index(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1);
+                m_z0 = p.mz[0][qz]; m_z1 = p.mz[1][qz]; m_z2 = p.mz[2][qz];
+                az = p.cz.a[kg]; bz = p.cz.b[kg]; azh = p.cz.a_half[kg]; bzh = p.cz.b_half[kg];
+                if (!KUNIT) { Kz = p.cz.K[kg]; Kzh = p.cz.K_half[kg]; }
+            }
+        }
 
+        // ---- sigmaxx, sigmayy, sigmazz  (:836-863)
         if (do_n && kg >= 2) {                          // k2begin, :792-793
             double value_dvx_dx = (vx_ip - vx_c) * odx;
             double value_dvy_dy = (vy_c - vy_jm) * ody;
             double value_dvz_dz = (vz_c - vz_m) * odz;
-            if (in_x) value_dvx_dx = cpml_apply(p.mx[0], qx, p.cx.b_half[i], p.cx.a_half[i], p.cx.K_half[i], value_dvx_dx);
-            if (in_y) value_dvy_dy = cpml_apply(p.my[0], qy, p.cy.b[j], p.cy.a[j], p.cy.K[j], value_dvy_dy);
-            if (in_z) value_dvz_dz = cpml_apply(p.mz[0], qz, p.cz.b[kg], p.cz.a[kg], p.cz.K[kg], value_dvz_dz);
-            const double sxx = ld_stream(p.sxx + q), syy = ld_stream(p.syy + q), szz = ld_stream(p.szz + q);
+            if (PML) {
+                if (in_x) value_dvx_dx = cpml_apply<KUNIT>(p.mx[0], qx, m_x0, bxh, axh, Kxh, value_dvx_dx);
+                if (in_y) value_dvy_dy = cpml_apply<KUNIT>(p.my[0], qy, m_y0, by, ay, Ky, value_dvy_dy);
+                if (in_z) value_dvz_dz = cpml_apply<KUNIT>(p.mz[0], qz, m_z0, bz, az, Kz, value_dvz_dz);
+            }
             st_stream(p.sxx + q, dt_l2m * value_dvx_dx + dt_l * (value_dvy_dy + value_dvz_dz) + sxx);
             st_stream(p.syy + q, dt_l * (value_dvx_dx + value_dvz_dz) + dt_l2m * value_dvy_dy + syy);
             st_stream(p.szz + q, dt_l * (value_dvx_dx + value_dvy_dy) + dt_l2m * value_dvz_dz + szz);
         }
+        // ---- sigmaxy  (:877-894)
         if (do_xy) {
             double value_dvy_dx = (vy_c - vy_im) * odx;
             double value_dvx_dy = (vx_jp - vx_c) * ody;
-            if (in_x) value_dvy_dx = cpml_apply(p.mx[1], qx, p.cx.b[i], p.cx.a[i], p.cx.K[i], value_dvy_dx);
-            if (in_y) value_dvx_dy = cpml_apply(p.my[1], qy, p.cy.b_half[j], p.cy.a_half[j], p.cy.K_half[j], value_dvx_dy);
-            const double sxy = ld_stream(p.sxy + q);
+            if (PML) {
+                if (in_x) value_dvy_dx = cpml_apply<KUNIT>(p.mx[1], qx, m_x1, bxc, ax, Kx, value_dvy_dx);
+                if (in_y) value_dvx_dy = cpml_apply<KUNIT>(p.my[1], qy, m_y1, byh, ayh, Kyh, value_dvx_dy);
+            }
             st_stream(p.sxy + q, dt_m * (value_dvy_dx + value_dvx_dy) + sxy);
         }
+        // ---- sigmaxz, sigmayz  (:908-943)
         if (kg <= p.nz - 1) {                           // kminus1end, :795-796
             if (do_xz) {
                 double value_dvz_dx = (vz_c - vz_im) * odx;
                 double value_dvx_dz = (vx_n - vx_c) * odz;
-                if (in_x) value_dvz_dx = cpml_apply(p.mx[2], qx, p.cx.b[i], p.cx.a[i], p.cx.K[i], value_dvz_dx);
-                if (in_z) value_dvx_dz = cpml_apply(p.mz[1], qz, p.cz.b_half[kg], p.cz.a_half[kg], p.cz.K_half[kg], value_dvx_dz);
-                const double sxz = ld_stream(p.sxz + q);
+                if (PML) {
+                    if (in_x) value_dvz_dx = cpml_apply<KUNIT>(p.mx[2], qx, m_x2, bxc, ax, Kx, value_dvz_dx);
+                    if (in_z) value_dvx_dz = cpml_apply<KUNIT>(p.mz[1], qz, m_z1, bzh, azh, Kzh, value_dvx_dz);
+                }
                 st_stream(p.sxz + q, dt_m * (value_dvz_dx + value_dvx_dz) + sxz);
             }
             if (do_yz) {
                 double value_dvz_dy = (vz_jp - vz_c) * ody;
                 double value_dvy_dz = (vy_n - vy_c) * odz;
-                if (in_y) value_dvz_dy = cpml_apply(p.my[2], qy, p.cy.b_half[j], p.cy.a_half[j], p.cy.K_half[j], value_dvz_dy);
-                if (in_z) value_dvy_dz = cpml_apply(p.mz[2], qz, p.cz.b_half[kg], p.cz.a_half[kg], p.cz.K_half[kg], value_dvy_dz);
-                const double syz = ld_stream(p.syz + q);
+                if (PML) {
+                    if (in_y) value_dvz_dy = cpml_apply<KUNIT>(p.my[2], qy, m_y2, byh, ayh, Kyh, value_dvz_dy);
+                    if (in_z) value_dvy_dz = cpml_apply<KUNIT>(p.mz[2], qz, m_z2, bzh, azh, Kzh, value_dvy_dz);
+                }
                 st_stream(p.syz + q, dt_m * (value_dvz_dy + value_dvy_dz) + syz);
             }
         }
@@ -159,25 +202,25 @@ __device__ __forceinline__ void block_sum2(double &a, double &b, double *smem /*
     }
 }
 
-template <int TX, int TY>
-__global__ void __launch_bounds__(TX *TY)
-k_velocity3d(const __grid_constant__ Params3D p)
+template <bool PML, bool KUNIT, int TX, int TY, int MINB>
+__global__ void __launch_bounds__(TX *TY, MINB)
+k_velocity3d(const __grid_constant__ Params3D p, const __grid_constant__ Box3D bx)
 {
     __shared__ double red[2 * TX * TY / 32];
-    const int i = blockIdx.x * TX + threadIdx.x + 1;
-    const int j = blockIdx.y * TY + threadIdx.y + 1;
-    const bool active = (i <= p.nx) && (j <= p.ny);
+    const int i = bx.ia + blockIdx.x * TX + threadIdx.x;
+    const int j = bx.j0 + blockIdx.y * TY + threadIdx.y;
+    const bool active = (i >= bx.i0) && (i <= bx.i1) && (j <= bx.j1);
     double ekin = 0.0, epot = 0.0;
 
     if (active) {
-        const int kb = 1 + blockIdx.z * p.kchunk;
-        const int ke = min(p.nzl, kb + p.kchunk - 1);
+        const int kb = bx.k0 + blockIdx.z * bx.kchunk;
+        const int ke = min(bx.k1, kb + bx.kchunk - 1);
         const int pitch = p.pitch;
         const long long pl = p.plane;
         long long q = (long long)kb * pl + (long long)(j - 1) * pitch + (i - 1);
 
-        const bool in_x = (i <= p.xlo) || (i >= p.xhi);
-        const bool in_y = (j <= p.ylo) || (j >= p.yhi);
+        const bool in_x = PML && ((i <= p.xlo) || (i >= p.xhi));
+        const bool in_y = PML && ((j <= p.ylo) || (j >= p.yhi));
         const int sx = in_x ? shell_index(i, p.xlo, p.xhi) : 0;
         const int sy = in_y ? shell_index(j, p.ylo, p.yhi) : 0;
 
@@ -198,11 +241,20 @@ k_velocity3d(const __grid_constant__ Params3D p)
         const double inv_2mu = 1.0 / (2.0 * mu);
         const double half_rho = 0.5 * p.rho;
 
+        double ax = 0, bxc = 0, Kx = 1, axh = 0, bxh = 0, Kxh = 1, ay = 0, by = 0, Ky = 1, ayh = 0, byh = 0, Kyh = 1;
+        if (PML) {
+            if (in_x) { ax = p.cx.a[i]; bxc = p.cx.b[i]; axh = p.cx.a_half[i]; bxh = p.cx.b_half[i];
+                        if (!KUNIT) { Kx = p.cx.K[i]; Kxh = p.cx.K_half[i]; } }
+            if (in_y) { ay = p.cy.a[j]; by = p.cy.b[j]; ayh = p.cy.a_half[j]; byh = p.cy.b_half[j];
+                        if (!KUNIT) { Ky = p.cy.K[j]; Kyh = p.cy.K_half[j]; } }
+        }
+
         double sxz_m = p.sxz[q - pl], syz_m = p.syz[q - pl];
         double szz_c = p.szz[q];
 
         for (int k = kb; k <= ke; ++k, q += pl) {
             const int kg = k + p.koff;
+            // ---- every load of this plane, issued back to back
             const double szz_n = p.szz[q + pl];
             const double sxx_c = p.sxx[q], sxx_im = p.sxx[q - 1];
             const double syy_c = p.syy[q], syy_jp = p.syy[q + pitch];
@@ -211,38 +263,60 @@ k_velocity3d(const __grid_constant__ Params3D p)
             const double syz_c = p.syz[q], syz_jm = p.syz[q - pitch];
             double vx = ld_stream(p.vx + q), vy = ld_stream(p.vy + q), vz = ld_stream(p.vz + q);
 
-            const bool in_z = (kg <= p.zlo) || (kg >= p.zhi);
-            const long long qx = ((long long)(k - 1) * p.ny + (j - 1)) * p.sxp + sx;
-            const long long qy = ((long long)(k - 1) * p.sy + sy) * pitch + (i - 1);
-            const long long qz = in_z ? ((long long)(shell_index(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1) : 0;
+            const bool in_z = PML && ((kg <= p.zlo) || (kg >= p.zhi));
+            long long qx = 0, qy = 0, qz = 0;
+            double m_x3 = 0, m_x4 = 0, m_x5 = 0, m_y3 = 0, m_y4 = 0, m_y5 = 0, m_z3 = 0, m_z4 = 0, m_z5 = 0;
+            double az = 0, bz = 0, Kz = 1, azh = 0, bzh = 0, Kzh = 1;
+            if (PML) {
+                if (in_x) {
+                    qx = ((long long)(k - 1) * p.ny + (j - 1)) * p.sxp + sx;
+                    m_x3 = p.mx[3][qx]; m_x4 = p.mx[4][qx]; m_x5 = p.mx[5][qx];
+                }
+                if (in_y) {
+                    qy = ((long long)(k - 1) * p.sy + sy) * pitch + (i - 1);
+                    m_y3 = p.my[3][qy]; m_y4 = p.my[4][qy]; m_y5 = p.my[5][qy];
+                }
+                if (in_z) {
+                    qz = ((long long)(shell_index(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1);
+                    m_z3 = p.mz[3][qz]; m_z4 = p.mz[4][qz]; m_z5 = p.mz[5][qz];
+                    az = p.cz.a[kg]; bz = p.cz.b[kg]; azh = p.cz.a_half[kg]; bzh = p.cz.b_half[kg];
+                    if (!KUNIT) { Kz = p.cz.K[kg]; Kzh = p.cz.K_half[kg]; }
+                }
+            }
 
             if (kg >= 2) {                                           // k2begin
-                if (do_vx) {
+                if (do_vx) {                                         // :976-996
                     double value_dsigmaxx_dx = (sxx_c - sxx_im) * odx;
                     double value_dsigmaxy_dy = (sxy_c - sxy_jm) * ody;
                     double value_dsigmaxz_dz = (sxz_c - sxz_m) * odz;
-                    if (in_x) value_dsigmaxx_dx = cpml_apply(p.mx[3], qx, p.cx.b[i], p.cx.a[i], p.cx.K[i], value_dsigmaxx_dx);
-                    if (in_y) value_dsigmaxy_dy = cpml_apply(p.my[3], qy, p.cy.b[j], p.cy.a[j], p.cy.K[j], value_dsigmaxy_dy);
-                    if (in_z) value_dsigmaxz_dz = cpml_apply(p.mz[3], qz, p.cz.b[kg], p.cz.a[kg], p.cz.K[kg], value_dsigmaxz_dz);
+                    if (PML) {
+                        if (in_x) value_dsigmaxx_dx = cpml_apply<KUNIT>(p.mx[3], qx, m_x3, bxc, ax, Kx, value_dsigmaxx_dx);
+                        if (in_y) value_dsigmaxy_dy = cpml_apply<KUNIT>(p.my[3], qy, m_y3, by, ay, Ky, value_dsigmaxy_dy);
+                        if (in_z) value_dsigmaxz_dz = cpml_apply<KUNIT>(p.mz[3], qz, m_z3, bz, az, Kz, value_dsigmaxz_dz);
+                    }
                     vx = dt_r * (value_dsigmaxx_dx + value_dsigmaxy_dy + value_dsigmaxz_dz) + vx;
                 }
-                if (do_vy) {
+                if (do_vy) {                                         // :998-1016
                     double value_dsigmaxy_dx = (sxy_ip - sxy_c) * odx;
                     double value_dsigmayy_dy = (syy_jp - syy_c) * ody;
                     double value_dsigmayz_dz = (syz_c - syz_m) * odz;
-                    if (in_x) value_dsigmaxy_dx = cpml_apply(p.mx[4], qx, p.cx.b_half[i], p.cx.a_half[i], p.cx.K_half[i], value_dsigmaxy_dx);
-                    if (in_y) value_dsigmayy_dy = cpml_apply(p.my[4], qy, p.cy.b_half[j], p.cy.a_half[j], p.cy.K_half[j], value_dsigmayy_dy);
-                    if (in_z) value_dsigmayz_dz = cpml_apply(p.mz[4], qz, p.cz.b[kg], p.cz.a[kg], p.cz.K[kg], value_dsigmayz_dz);
+                    if (PML) {
+                        if (in_x) value_dsigmaxy_dx = cpml_apply<KUNIT>(p.mx[4], qx, m_x4, bxh, axh, Kxh, value_dsigmaxy_dx);
+                        if (in_y) value_dsigmayy_dy = cpml_apply<KUNIT>(p.my[4], qy, m_y4, byh, ayh, Kyh, value_dsigmayy_dy);
+                        if (in_z) value_dsigmayz_dz = cpml_apply<KUNIT>(p.mz[4], qz, m_z4, bz, az, Kz, value_dsigmayz_dz);
+                    }
                     vy = dt_r * (value_dsigmaxy_dx + value_dsigmayy_dy + value_dsigmayz_dz) + vy;
                 }
             }
-            if (do_vz && kg <= p.nz - 1) {                           // kminus1end
+            if (do_vz && kg <= p.nz - 1) {                           // kminus1end, :1031-1052
                 double value_dsigmaxz_dx = (sxz_ip - sxz_c) * odx;
                 double value_dsigmayz_dy = (syz_c - syz_jm) * ody;
                 double value_dsigmazz_dz = (szz_n - szz_c) * odz;
-                if (in_x) value_dsigmaxz_dx = cpml_apply(p.mx[5], qx, p.cx.b_half[i], p.cx.a_half[i], p.cx.K_half[i], value_dsigmaxz_dx);
-                if (in_y) value_dsigmayz_dy = cpml_apply(p.my[5], qy, p.cy.b[j], p.cy.a[j], p.cy.K[j], value_dsigmayz_dy);
-                if (in_z) value_dsigmazz_dz = cpml_apply(p.mz[5], qz, p.cz.b_half[kg], p.cz.a_half[kg], p.cz.K_half[kg], value_dsigmazz_dz);
+                if (PML) {
+                    if (in_x) value_dsigmaxz_dx = cpml_apply<KUNIT>(p.mx[5], qx, m_x5, bxh, axh, Kxh, value_dsigmaxz_dx);
+                    if (in_y) value_dsigmayz_dy = cpml_apply<KUNIT>(p.my[5], qy, m_y5, by, ay, Ky, value_dsigmayz_dy);
+                    if (in_z) value_dsigmazz_dz = cpml_apply<KUNIT>(p.mz[5], qz, m_z5, bzh, azh, Kzh, value_dsigmazz_dz);
+                }
                 vz = dt_r * (value_dsigmaxz_dx + value_dsigmayz_dy + value_dsigmazz_dz) + vz;
             }
 
@@ -280,7 +354,7 @@ k_velocity3d(const __grid_constant__ Params3D p)
 
     block_sum2<TX * TY>(ekin, epot, red);
     if (threadIdx.x == 0 && threadIdx.y == 0) {
-        const int b = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        const int b = bx.pbase + (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
         p.partials[b] = ekin;
         p.partials[p.nblocks + b] = epot;
     }
@@ -330,34 +404,49 @@ __global__ void __launch_bounds__(256) k_maxnorm(const double *vx, const double 
     if ((threadIdx.x & 31) == 0) atomicMax(out_bits, (unsigned long long)__double_as_longlong(m));
 }
 
-template <int TX, int TY>
-static void launch_pair(const Params3D &p, dim3 grid, cudaStream_t s, bool stress)
+// ---- launch dispatch ---------------------------------------------------------------
+
+template <bool PML, bool KUNIT, int TX, int TY, int MINB>
+static void launch_one(const Params3D &p, const Box3D &b, cudaStream_t s, bool stress)
 {
-    if (stress) k_stress3d<TX, TY><<<grid, dim3(TX, TY), 0, s>>>(p);
-    else        k_velocity3d<TX, TY><<<grid, dim3(TX, TY), 0, s>>>(p);
+    const dim3 grid(b.gx, b.gy, b.gz), block(TX, TY);
+    if (stress) k_stress3d<PML, KUNIT, TX, TY, MINB><<<grid, block, 0, s>>>(p, b);
+    else        k_velocity3d<PML, KUNIT, TX, TY, MINB><<<grid, block, 0, s>>>(p, b);
 }
 
-static void dispatch3d(const Params3D &p, dim3 grid, dim3 block, cudaStream_t s, bool stress)
+template <bool PML, bool KUNIT>
+static bool dispatch_tile(const Params3D &p, const Box3D &b, cudaStream_t s, bool stress)
 {
-    const int key = block.x * 100 + block.y;
-    switch (key) {
-    case 32 * 100 + 4:  launch_pair<32, 4>(p, grid, s, stress); break;
-    case 32 * 100 + 8:  launch_pair<32, 8>(p, grid, s, stress); break;
-    case 32 * 100 + 16: launch_pair<32, 16>(p, grid, s, stress); break;
-    case 64 * 100 + 2:  launch_pair<64, 2>(p, grid, s, stress); break;
-    case 64 * 100 + 4:  launch_pair<64, 4>(p, grid, s, stress); break;
-    case 64 * 100 + 8:  launch_pair<64, 8>(p, grid, s, stress); break;
-    case 128 * 100 + 1: launch_pair<128, 1>(p, grid, s, stress); break;
-    case 128 * 100 + 2: launch_pair<128, 2>(p, grid, s, stress); break;
-    case 128 * 100 + 4: launch_pair<128, 4>(p, grid, s, stress); break;
-    case 16 * 100 + 16: launch_pair<16, 16>(p, grid, s, stress); break;
-    case 16 * 100 + 8:  launch_pair<16, 8>(p, grid, s, stress); break;
-    default:            launch_pair<32, 8>(p, dim3((p.nx + 31) / 32, (p.ny + 7) / 8, grid.z), s, stress); break;
+    // MINB (min resident blocks per SM) caps registers: 65536 / (threads * MINB)
+    switch (b.tx * 100 + b.ty) {
+    case 32 * 100 + 8:  launch_one<PML, KUNIT, 32, 8, PML ? 2 : 3>(p, b, s, stress); return true;
+    case 32 * 100 + 4:  launch_one<PML, KUNIT, 32, 4, PML ? 4 : 6>(p, b, s, stress); return true;
+    case 64 * 100 + 4:  launch_one<PML, KUNIT, 64, 4, PML ? 2 : 3>(p, b, s, stress); return true;
+    case 64 * 100 + 2:  launch_one<PML, KUNIT, 64, 2, PML ? 4 : 6>(p, b, s, stress); return true;
+    case 128 * 100 + 2: launch_one<PML, KUNIT, 128, 2, PML ? 2 : 3>(p, b, s, stress); return true;
+    case 128 * 100 + 1: launch_one<PML, KUNIT, 128, 1, PML ? 4 : 6>(p, b, s, stress); return true;
+    case 16 * 100 + 16: launch_one<PML, KUNIT, 16, 16, PML ? 2 : 3>(p, b, s, stress); return true;
+    case 16 * 100 + 8:  launch_one<PML, KUNIT, 16, 8, PML ? 4 : 6>(p, b, s, stress); return true;
+    default: return false;
     }
 }
 
-void launch_stress3d(const Params3D &p, dim3 grid, dim3 block, cudaStream_t s) { dispatch3d(p, grid, block, s, true); }
-void launch_velocity3d(const Params3D &p, dim3 grid, dim3 block, cudaStream_t s) { dispatch3d(p, grid, block, s, false); }
+bool tile_supported(int tx, int ty)
+{
+    switch (tx * 100 + ty) {
+    case 3208: case 3204: case 6404: case 6402: case 12802: case 12801: case 1616: case 1608: return true;
+    default: return false;
+    }
+}
+
+static void dispatch3d(const Params3D &p, const Box3D &b, cudaStream_t s, bool stress)
+{
+    if (b.pml) { if (p.kunit) dispatch_tile<true, true>(p, b, s, stress); else dispatch_tile<true, false>(p, b, s, stress); }
+    else       dispatch_tile<false, true>(p, b, s, stress);     // no PML code inside: KUNIT is moot
+}
+
+void launch_stress3d(const Params3D &p, const Box3D &b, cudaStream_t s) { dispatch3d(p, b, s, true); }
+void launch_velocity3d(const Params3D &p, const Box3D &b, cudaStream_t s) { dispatch3d(p, b, s, false); }
 void launch_post3d(const Post3D &p, cudaStream_t s) { k_post3d<<<1, 256, 0, s>>>(p); }
 void launch_maxnorm(const double *vx, const double *vy, const double *vz, long long n,
                     unsigned long long *out_bits, cudaStream_t s)
