@@ -326,7 +326,8 @@ def run_b200(args):
                        "deltat": p.DELTAT, "l2": "fields (>= 3 GB per rank) are far larger than the 126 MB L2; no flush needed",
                        "parallelism": f"z-slabs x{world}" if world > 1 else "single GPU",
                        "halo": "NCCL send/recv of 6 planes per step and interface" if world > 1 else None,
-                       "fmad": False, "finite": finite},
+                       "fmad": False, "finite": finite,
+                       "launch": sol.launch_info() if kind == "3d" else None},
             "roofline": {"bound": "hbm", "kernel": "k_stress3d" if kind == "3d" else "k_stress2d",
                          "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": (ach / peak) if ach else None, "traffic": traffic, "peak_source": peak_src,

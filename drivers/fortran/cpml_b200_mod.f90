@@ -166,6 +166,45 @@ module cpml_b200
       integer(c_int32_t) :: ierr
     end function
 
+    function cpml_p2p_export(handle, blob, blob_capacity, nbytes) bind(C, name='cpml_p2p_export') result(ierr)
+      import :: c_int32_t, c_int64_t, c_ptr, c_char
+      type(c_ptr), value :: handle
+      character(kind=c_char), intent(out) :: blob(*)
+      integer(c_int64_t), value :: blob_capacity
+      integer(c_int64_t), intent(out) :: nbytes
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_p2p_attach_ipc(handle, side, blob, nbytes) bind(C, name='cpml_p2p_attach_ipc') result(ierr)
+      import :: c_int32_t, c_int64_t, c_ptr, c_char
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: side
+      character(kind=c_char), intent(in) :: blob(*)
+      integer(c_int64_t), value :: nbytes
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_p2p_attach_local(handle, side, neighbour) bind(C, name='cpml_p2p_attach_local') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: handle, neighbour
+      integer(c_int32_t), value :: side
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_p2p_detach(handle) bind(C, name='cpml_p2p_detach') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_get_launch_info(handle, info, n) bind(C, name='cpml_get_launch_info') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int32_t), intent(out) :: info(*)
+      integer(c_int32_t), value :: n
+      integer(c_int32_t) :: ierr
+    end function
+
     function cpml_get_seismograms(handle, sisvx, sisvy) bind(C, name='cpml_get_seismograms') result(ierr)
       import :: c_int32_t, c_ptr, c_double
       type(c_ptr), value :: handle

@@ -163,6 +163,28 @@ int32_t cpml_halo_plane(cpml_handle *h, int32_t field, int32_t klocal,
 int32_t cpml_copy_plane(cpml_handle *dst, int32_t klocal_dst, cpml_handle *src, int32_t klocal_src,
                         int32_t field);
 
+/* Direct slab-to-slab stores over NVLink: once a neighbour is attached, cpml_step_stress /
+ * cpml_step_velocity write the boundary planes that neighbour needs (the six planes of the
+ * MPI_SENDRECV calls at 3D-iso :811-823 and :951-963) straight into its halo planes from
+ * inside the update kernels, and order the steps of the two slabs with device-side flags
+ * (no host synchronisation, no separate copy).  side 0 = slab rank-1, side 1 = slab rank+1.
+ * The end slabs have no outer neighbour (MPI_PROC_NULL, :775-790).
+ *   one process per GPU : cpml_p2p_export on every rank, exchange the 64-byte blobs through
+ *                         the launcher (MPI_Sendrecv / torch.distributed / a file), then
+ *                         cpml_p2p_attach_ipc (CUDA IPC);
+ *   one process, N GPUs : cpml_p2p_attach_local with the neighbour's handle.
+ * Every slab must be attached on both sides it has a neighbour on before the first step, and
+ * all slabs must call cpml_reset / start at the same `it` together. */
+int32_t cpml_p2p_export(cpml_handle *h, void *blob, int64_t blob_capacity, int64_t *nbytes);
+int32_t cpml_p2p_attach_ipc(cpml_handle *h, int32_t side, const void *blob, int64_t nbytes);
+int32_t cpml_p2p_attach_local(cpml_handle *h, int32_t side, cpml_handle *neighbour);
+int32_t cpml_p2p_detach(cpml_handle *h);
+
+/* Launch geometry chosen for the 3-D kernels (diagnostics for bench.py / profiles):
+ * info[0..9] = uses_tma, tile_x, tile_y, stages, planes per work item, z chunks, work items,
+ * CTAs of the stress kernel, CTAs of the velocity kernel, attached sides bit mask. */
+int32_t cpml_get_launch_info(cpml_handle *h, int32_t *info, int32_t n);
+
 /* ---- outputs (device -> driver) ------------------------------------------- */
 
 /* sisvx, sisvy as declared at :286: (NSTEP,NREC) column-major, zero beyond the

@@ -37,8 +37,23 @@ struct cpml_handle {
     size_t field_doubles = 0;  // allocation size of one field
     long long origin = 0;      // offset of element (1,1,0) / (1,1) inside the allocation
     int nfields = 0;
+    double *arena = nullptr;   // ONE allocation: nfields * field_doubles + the slab flags (so that a
+                               // neighbour process maps everything with a single IPC handle)
+    size_t arena_doubles = 0;
     double *field_alloc[9] = {};
     double *f0[9] = {};        // element (1,1,0) / (1,1)
+
+    // TMA path (3-D): descriptors of the two kernels' plane tiles, work decomposition
+    bool use_tma = false;
+    TmaMaps maps_stress{}, maps_velocity{};
+    Tile3D tile{};
+
+    // slab neighbours reached by direct peer stores (cpml_p2p_*): side 0 = rank-1, 1 = rank+1
+    bool peer_on[2] = {false, false};
+    double *peer_arena[2] = {nullptr, nullptr};
+    bool peer_ipc[2] = {false, false};
+    unsigned long long *flags = nullptr;     // [0] v from lo, [1] v from hi, [2] sigma from lo, [3] sigma from hi
+    unsigned int *d_timeout = nullptr;
 
     // profiles
     bool have_prof[3] = {false, false, false};
@@ -186,10 +201,16 @@ static int32_t create_impl(cpml_handle *h)
         h->field_doubles = (size_t)h->plane + 16;
         h->nfields = 5;
     }
+    h->field_doubles = (h->field_doubles + 15) / 16 * 16;      // every field starts on a 128-byte line
+    h->arena_doubles = (size_t)h->nfields * h->field_doubles + 16;
+    CK(cudaMalloc(&h->arena, h->arena_doubles * sizeof(double)));
     for (int f = 0; f < h->nfields; f++) {
-        CK(cudaMalloc(&h->field_alloc[f], h->field_doubles * sizeof(double)));
+        h->field_alloc[f] = h->arena + (size_t)f * h->field_doubles;
         h->f0[f] = h->field_alloc[f] + h->origin;
     }
+    h->flags = (unsigned long long *)(h->arena + (size_t)h->nfields * h->field_doubles);
+    CK(cudaMalloc(&h->d_timeout, sizeof(unsigned int)));
+    CK(cudaMemset(h->d_timeout, 0, sizeof(unsigned int)));
     if (c.ndim == 2)
         for (int m = 0; m < 3; m++) CK(cudaMalloc(&h->mat[m], h->field_doubles * sizeof(double)));
 
@@ -305,7 +326,9 @@ extern "C" int32_t cpml_destroy(cpml_handle *h)
 {
     if (!h) return CPML_OK;
     cudaSetDevice(h->device);
-    for (auto &p : h->field_alloc) cudaFree(p);
+    cpml_p2p_detach(h);
+    cudaFree(h->arena);
+    cudaFree(h->d_timeout);
     for (auto &p : h->mat) cudaFree(p);
     for (auto &ax : h->dprof) for (auto &p : ax) cudaFree(p);
     for (auto &p : h->mx) cudaFree(p);
@@ -324,8 +347,7 @@ extern "C" int32_t cpml_reset(cpml_handle *h)
     if (!h) return CPML_EINVAL;
     const cpml_config &c = h->cfg;
     CK(cudaSetDevice(h->device));
-    for (int f = 0; f < h->nfields; f++)
-        CK(cudaMemsetAsync(h->field_alloc[f], 0, h->field_doubles * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->arena, 0, h->arena_doubles * sizeof(double), h->stream));   // fields and slab flags
     if (h->finalized) {
         for (int m = 0; m < 6; m++) {
             if (h->mx[m]) CK(cudaMemsetAsync(h->mx[m], 0, h->mx_doubles * sizeof(double), h->stream));
@@ -435,6 +457,107 @@ extern "C" int32_t cpml_set_receivers(cpml_handle *h, const int32_t *ix_rec, con
     return CPML_OK;
 }
 
+
+// ---- TMA path: descriptors and work decomposition -------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int32_t encode_plane_map(cpml_handle *h, EncodeTiledFn enc, CUtensorMap *out, int field, int bx, int by)
+{
+    const cpml_config &c = h->cfg;
+    // tensor = the field as (x, y, plane) with the grid's own extents: whatever a box covers
+    // beyond NX / NY (or before index 1) is zero-filled by the TMA unit, never read
+    const cuuint64_t dims[3] = {(cuuint64_t)c.nx, (cuuint64_t)c.ny, (cuuint64_t)(h->nzl + 2)};
+    const cuuint64_t strides[2] = {(cuuint64_t)h->pitch * sizeof(double), (cuuint64_t)h->plane * sizeof(double)};
+    const cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)h->f0[field], dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        h->err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+        return CPML_ECUDA;
+    }
+    return CPML_OK;
+}
+
+static int32_t setup_tma(cpml_handle *h)
+{
+    const cpml_config &c = h->cfg;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) FAIL(CPML_ECUDA, "driver does not export cuTensorMapEncodeTiled");
+    const EncodeTiledFn enc = (EncodeTiledFn)fn;
+
+    // thread tile = TMA box.  Narrow grids (the reference's NX = 101) take one 104-wide tile
+    // per row; wide grids 64 x 8.  CPML_TX / CPML_TY / CPML_STAGES override (bench sweeps).
+    Tile3D &t = h->tile;
+    t.tx = env_int("CPML_TX", c.nx <= 104 ? 104 : 64);
+    t.ty = env_int("CPML_TY", c.nx <= 104 ? 4 : 8);
+    if (!tma_tile_supported(t.tx, t.ty)) FAIL(CPML_EINVAL, "unsupported CPML_TX x CPML_TY tile");
+    t.stages = std::max(2, std::min(16, env_int("CPML_STAGES", 4)));
+    t.minb = std::max(1, std::min(3, env_int("CPML_MINB", 1)));
+    t.ntx = (c.nx + t.tx - 1) / t.tx;
+    t.nty = (c.ny + t.ty - 1) / t.ty;
+
+    // descriptors: 0 vx 1 vy 2 vz 3 sxx 4 syy 5 szz 6 sxy 7 sxz 8 syz
+    const int hx = t.tx + 2, hy = t.ty + 1;
+    const int stress_field[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};
+    const int velocity_field[9] = {3, 4, 6, 7, 8, 5, 0, 1, 2};
+    for (int m = 0; m < 9; m++) {
+        int32_t rc = encode_plane_map(h, enc, &h->maps_stress.m[m], stress_field[m], m < 3 ? hx : t.tx, m < 3 ? hy : t.ty);
+        if (rc) return rc;
+        rc = encode_plane_map(h, enc, &h->maps_velocity.m[m], velocity_field[m], m < 5 ? hx : t.tx, m < 5 ? hy : t.ty);
+        if (rc) return rc;
+    }
+
+    // resident CTAs per SM; shrink the ring if a stage set does not fit at all
+    Params3D p{};
+    p.kunit = 1;
+    for (int ax = 0; ax < 3; ax++)
+        for (int q : {2, 5})
+            for (double K : h->hprof[ax][q])
+                if (K != 1.0) p.kunit = 0;
+    int occ_s = 0, occ_v = 0;
+    while (true) {
+        cudaError_t e1 = tma_occupancy(p, t, true, &occ_s), e2 = tma_occupancy(p, t, false, &occ_v);
+        if (e1 == cudaSuccess && e2 == cudaSuccess && occ_s >= 1 && occ_v >= 1) break;
+        cudaGetLastError();
+        if (t.stages <= 2) FAIL(CPML_ECUDA, "TMA kernels do not fit on this device");
+        t.stages--;
+    }
+    const int cap = env_int("CPML_CTAS_PER_SM", 0);
+    if (cap > 0) { occ_s = std::min(occ_s, cap); occ_v = std::min(occ_v, cap); }
+
+    // z chunks: minimise rounds x (planes per item + pipeline fill) over the persistent grid
+    const int tiles = t.ntx * t.nty;
+    const int resident = h->sm_count * std::min(occ_s, occ_v);
+    int best = 1;
+    double best_cost = 1e300;
+    const int cmax = std::max(1, h->nzl / 8);
+    for (int nc = 1; nc <= cmax; nc++) {
+        const int kc = (h->nzl + nc - 1) / nc;
+        const int ncr = (h->nzl + kc - 1) / kc;
+        const long long items = (long long)tiles * ncr;
+        const double rounds = (double)((items + resident - 1) / resident);
+        const double cost = rounds * (kc + 3.0);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = ncr; }
+    }
+    int nzc = env_int("CPML_ZCHUNKS", 0);
+    if (nzc <= 0) nzc = best;
+    nzc = std::max(1, std::min(nzc, h->nzl));
+    t.kchunk = (h->nzl + nzc - 1) / nzc;
+    t.nzc = (h->nzl + t.kchunk - 1) / t.kchunk;
+    t.nitems = tiles * t.nzc;
+    t.grid_stress = std::min(t.nitems, h->sm_count * occ_s);
+    t.grid_velocity = std::min(t.nitems, h->sm_count * occ_v);
+    h->nblocks = t.nitems;
+    return CPML_OK;
+}
+
 // Allocates the shell-only memory variables once every input is known.
 static int32_t finalize(cpml_handle *h)
 {
@@ -493,7 +616,11 @@ static int32_t finalize(cpml_handle *h)
         h->nz_own[ax][1] = n1;
     }
     if (c.ndim == 3) {
-        build_regions(h);
+        // CPML_KERNEL=reg selects the register-marching kernels of kernels_3d.cu (A/B runs)
+        const char *kv = getenv("CPML_KERNEL");
+        h->use_tma = !(kv && std::string(kv) == "reg");
+        if (h->use_tma) { const int32_t rc = setup_tma(h); if (rc) return rc; }
+        else build_regions(h);
         CK(cudaMalloc(&h->d_partials, 2 * (size_t)std::max(1, h->nblocks) * sizeof(double)));
         CK(cudaMemset(h->d_partials, 0, 2 * (size_t)std::max(1, h->nblocks) * sizeof(double)));
     }
@@ -542,6 +669,13 @@ static Params3D make_p3(cpml_handle *h, int it)
         for (int q : {2, 5})
             for (double K : h->hprof[ax][q])
                 if (K != 1.0) p.kunit = 0;
+    // neighbour halo planes (3D-iso :811-823, :951-963): lo gets vx, vy, sigmazz of my plane 1
+    // in its plane NZ_LOCAL+1; hi gets vz, sigmaxz, sigmayz of my plane NZ_LOCAL in its plane 0
+    const int lo_f[3] = {0, 1, 5}, hi_f[3] = {2, 7, 8};
+    for (int q = 0; q < 3; q++) {
+        p.peer_lo[q] = h->peer_on[0] ? h->peer_arena[0] + (size_t)lo_f[q] * h->field_doubles + h->origin + (long long)(h->nzl + 1) * h->plane : nullptr;
+        p.peer_hi[q] = h->peer_on[1] ? h->peer_arena[1] + (size_t)hi_f[q] * h->field_doubles + h->origin : nullptr;
+    }
     return p;
 }
 
@@ -562,6 +696,11 @@ static Params2D make_p2(cpml_handle *h, int it)
     p.npml = c.npoints_pml;
     p.partials = h->d_partials; p.nblocks = h->nblocks;
     return p;
+}
+
+static unsigned long long *peer_flags(cpml_handle *h, int side)
+{
+    return (unsigned long long *)(h->peer_arena[side] + (size_t)h->nfields * h->field_doubles);
 }
 
 static int32_t time_begin(cpml_handle *h, int kind)
@@ -587,42 +726,63 @@ static int32_t check_it(cpml_handle *h, int it)
     return CPML_OK;
 }
 
-extern "C" int32_t cpml_step_stress(cpml_handle *h, int32_t it)
+// One half step: [wait for the neighbours' planes] kernel [publish my planes].
+// phase 0 = stress update (needs the velocity planes of step it-1, produces sigma planes of
+// step it), phase 1 = velocity update (needs the sigma planes of step it, produces velocity
+// planes of step it).  Flag words of a slab: [0] v from lo, [1] v from hi, [2] sigma from lo,
+// [3] sigma from hi; a slab writes into its lo neighbour's "from hi" word and vice versa.
+static int32_t half_step(cpml_handle *h, int32_t it, int phase)
 {
-    if (!h) return CPML_EINVAL;
     int32_t rc = check_it(h, it); if (rc) return rc;
     rc = finalize(h); if (rc) return rc;
     CK(cudaSetDevice(h->device));
-    rc = time_begin(h, 0); if (rc) return rc;
+    const bool peers = h->cfg.ndim == 3 && (h->peer_on[0] || h->peer_on[1]);
+    if (peers) {
+        if (!h->use_tma) FAIL(CPML_ESTATE, "peer stores need the TMA kernels (unset CPML_KERNEL=reg)");
+        const int w = phase == 0 ? 0 : 2;
+        launch_wait(h->peer_on[0] ? h->flags + w : nullptr, h->peer_on[1] ? h->flags + w + 1 : nullptr,
+                    (unsigned long long)(phase == 0 ? it - 1 : it), h->d_timeout, h->stream);
+        h->n_launches++;
+    }
+    rc = time_begin(h, phase); if (rc) return rc;
     if (h->cfg.ndim == 3) {
         const Params3D p = make_p3(h, it);
-        for (const Box3D &b : h->regions) { launch_stress3d(p, b, h->stream); h->n_launches++; }
+        if (h->use_tma) {
+            if (phase == 0) CK(launch_stress3d_tma(p, h->maps_stress, h->tile, h->stream));
+            else CK(launch_velocity3d_tma(p, h->maps_velocity, h->tile, h->stream));
+            h->n_launches++;
+        } else {
+            for (const Box3D &b : h->regions) {
+                if (phase == 0) launch_stress3d(p, b, h->stream); else launch_velocity3d(p, b, h->stream);
+                h->n_launches++;
+            }
+        }
     } else {
-        launch_stress2d(make_p2(h, it), h->grid, h->block, h->stream);
+        if (phase == 0) launch_stress2d(make_p2(h, it), h->grid, h->block, h->stream);
+        else launch_velocity2d(make_p2(h, it), h->grid, h->block, h->stream);
         h->n_launches++;
     }
     rc = time_end(h); if (rc) return rc;
+    if (peers) {
+        const int w = phase == 0 ? 2 : 0;
+        launch_signal(h->peer_on[0] ? peer_flags(h, 0) + w + 1 : nullptr, h->peer_on[1] ? peer_flags(h, 1) + w : nullptr,
+                      (unsigned long long)it, h->stream);
+        h->n_launches++;
+    }
     CK(cudaGetLastError());
     return CPML_OK;
+}
+
+extern "C" int32_t cpml_step_stress(cpml_handle *h, int32_t it)
+{
+    if (!h) return CPML_EINVAL;
+    return half_step(h, it, 0);
 }
 
 extern "C" int32_t cpml_step_velocity(cpml_handle *h, int32_t it)
 {
     if (!h) return CPML_EINVAL;
-    int32_t rc = check_it(h, it); if (rc) return rc;
-    rc = finalize(h); if (rc) return rc;
-    CK(cudaSetDevice(h->device));
-    rc = time_begin(h, 1); if (rc) return rc;
-    if (h->cfg.ndim == 3) {
-        const Params3D p = make_p3(h, it);
-        for (const Box3D &b : h->regions) { launch_velocity3d(p, b, h->stream); h->n_launches++; }
-    } else {
-        launch_velocity2d(make_p2(h, it), h->grid, h->block, h->stream);
-        h->n_launches++;
-    }
-    rc = time_end(h); if (rc) return rc;
-    CK(cudaGetLastError());
-    return CPML_OK;
+    return half_step(h, it, 1);
 }
 
 extern "C" int32_t cpml_step_finish(cpml_handle *h, int32_t it)
@@ -659,6 +819,11 @@ extern "C" int32_t cpml_synchronize(cpml_handle *h)
     if (!h) return CPML_EINVAL;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
+    if (h->peer_on[0] || h->peer_on[1]) {
+        unsigned int timed_out = 0;
+        CK(cudaMemcpy(&timed_out, h->d_timeout, sizeof(timed_out), cudaMemcpyDeviceToHost));
+        if (timed_out) FAIL(CPML_ESTATE, "a neighbour slab never published its boundary planes (wait kernel timed out)");
+    }
     return CPML_OK;
 }
 
@@ -699,6 +864,96 @@ extern "C" int32_t cpml_copy_plane(cpml_handle *dst, int32_t klocal_dst, cpml_ha
     CK(cudaMemcpyPeerAsync(dst->f0[field] + (long long)klocal_dst * dst->plane, dst->device,
                            src->f0[field] + (long long)klocal_src * src->plane, src->device,
                            (size_t)dst->plane * sizeof(double), dst->stream));
+    return CPML_OK;
+}
+
+// ---- direct slab-to-slab stores (replaces MPI_SENDRECV, 3D-iso :811-823, :951-963) ------
+
+extern "C" int32_t cpml_p2p_export(cpml_handle *h, void *blob, int64_t blob_capacity, int64_t *nbytes)
+{
+    if (!h || !blob || !nbytes) return CPML_EINVAL;
+    if (h->cfg.ndim != 3) FAIL(CPML_EINVAL, "slabs exist only in 3-D");
+    if (blob_capacity < (int64_t)sizeof(cudaIpcMemHandle_t)) FAIL(CPML_EINVAL, "blob too small (need 64 bytes)");
+    CK(cudaSetDevice(h->device));
+    cudaIpcMemHandle_t mh;
+    CK(cudaIpcGetMemHandle(&mh, h->arena));
+    memcpy(blob, &mh, sizeof(mh));
+    *nbytes = (int64_t)sizeof(mh);
+    return CPML_OK;
+}
+
+static int32_t check_side(cpml_handle *h, int32_t side)
+{
+    if (h->cfg.ndim != 3) FAIL(CPML_EINVAL, "slabs exist only in 3-D");
+    if (side != 0 && side != 1) FAIL(CPML_EINVAL, "side must be 0 (slab rank-1) or 1 (slab rank+1)");
+    if ((side == 0 && h->cfg.slab_rank == 0) || (side == 1 && h->cfg.slab_rank == h->cfg.nslabs - 1))
+        FAIL(CPML_ETOPOLOGY, "no neighbour on that side (MPI_PROC_NULL, 3D-iso :775-790)");
+    if (h->peer_on[side]) FAIL(CPML_ESTATE, "neighbour already attached");
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_p2p_attach_ipc(cpml_handle *h, int32_t side, const void *blob, int64_t nbytes)
+{
+    if (!h || !blob) return CPML_EINVAL;
+    int32_t rc = check_side(h, side); if (rc) return rc;
+    if (nbytes != (int64_t)sizeof(cudaIpcMemHandle_t)) FAIL(CPML_EINVAL, "bad blob size");
+    CK(cudaSetDevice(h->device));
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, blob, sizeof(mh));
+    void *ptr = nullptr;
+    CK(cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_arena[side] = (double *)ptr;
+    h->peer_ipc[side] = true;
+    h->peer_on[side] = true;
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_p2p_attach_local(cpml_handle *h, int32_t side, cpml_handle *neighbour)
+{
+    if (!h || !neighbour) return CPML_EINVAL;
+    int32_t rc = check_side(h, side); if (rc) return rc;
+    const cpml_config &a = h->cfg, &b = neighbour->cfg;
+    if (b.ndim != 3 || a.nx != b.nx || a.ny != b.ny || a.nz != b.nz || a.nslabs != b.nslabs ||
+        b.slab_rank != a.slab_rank + (side == 0 ? -1 : 1))
+        FAIL(CPML_ETOPOLOGY, "that handle is not the neighbouring slab of the same grid");
+    CK(cudaSetDevice(h->device));
+    if (neighbour->device != h->device) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, h->device, neighbour->device));
+        if (!can) FAIL(CPML_ECUDA, "no peer access between the two devices");
+        const cudaError_t e = cudaDeviceEnablePeerAccess(neighbour->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+        cudaGetLastError();
+    }
+    h->peer_arena[side] = neighbour->arena;
+    h->peer_ipc[side] = false;
+    h->peer_on[side] = true;
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_p2p_detach(cpml_handle *h)
+{
+    if (!h) return CPML_EINVAL;
+    cudaSetDevice(h->device);
+    for (int side = 0; side < 2; side++) {
+        if (h->peer_on[side] && h->peer_ipc[side]) {
+            cudaStreamSynchronize(h->stream);
+            cudaIpcCloseMemHandle(h->peer_arena[side]);
+        }
+        h->peer_on[side] = h->peer_ipc[side] = false;
+        h->peer_arena[side] = nullptr;
+    }
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_get_launch_info(cpml_handle *h, int32_t *info, int32_t n)
+{
+    if (!h || !info) return CPML_EINVAL;
+    int32_t rc = finalize(h); if (rc) return rc;
+    const Tile3D &t = h->tile;
+    const int32_t v[10] = {h->use_tma ? 1 : 0, t.tx, t.ty, t.stages, t.kchunk, t.nzc, t.nitems, t.grid_stress, t.grid_velocity,
+                           (h->peer_on[0] ? 1 : 0) + (h->peer_on[1] ? 2 : 0)};
+    for (int q = 0; q < n && q < 10; q++) info[q] = v[q];
     return CPML_OK;
 }
 

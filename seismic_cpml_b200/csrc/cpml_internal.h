@@ -12,6 +12,7 @@
 //     [k][j][sx], y-shell arrays [k][sy][i], z-shell arrays [sz][j][i].
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
@@ -63,6 +64,28 @@ struct Params3D {
     double *partials;         // [2][nblocks] kinetic / potential per block
     int nblocks;
     int kunit;                // every K profile == 1: the value/K division is dropped (exact)
+    // slab neighbours' halo planes, element (1,1), mapped peer memory (null: no neighbour /
+    // exchange done by the driver).  lo = slab rank-1, its plane NZ_LOCAL+1: vx, vy, sigmazz;
+    // hi = slab rank+1, its plane 0: vz, sigmaxz, sigmayz  (3D-iso :811-823, :951-963)
+    double *peer_lo[3];
+    double *peer_hi[3];
+};
+
+// TMA descriptors of one kernel's nine plane tiles (kernels_3d_tma.cu lists the order).
+struct TmaMaps {
+    CUtensorMap m[9];
+};
+
+// Work decomposition of the TMA kernels: persistent CTAs, static round-robin over
+// (x-tile, y-tile, z-chunk) items.
+struct Tile3D {
+    int tx, ty;               // thread tile = box size
+    int ntx, nty;             // tiles per plane
+    int kchunk, nzc;          // planes per item, z chunks
+    int nitems;               // ntx * nty * nzc (= energy partial slots)
+    int stages;               // shared-memory ring depth (planes)
+    int minb;                 // resident CTAs per SM the kernel variant is compiled for
+    int grid_stress, grid_velocity;
 };
 
 // One launch region of a 3-D kernel: the box [i0,i1] x [j0,j1] x [k0,k1] (1-based, k local).
@@ -126,6 +149,13 @@ void launch_stress3d(const Params3D &p, const Box3D &b, cudaStream_t s);
 void launch_velocity3d(const Params3D &p, const Box3D &b, cudaStream_t s);
 bool tile_supported(int tx, int ty);
 void launch_post3d(const Post3D &p, cudaStream_t s);
+bool tma_tile_supported(int tx, int ty);
+cudaError_t tma_occupancy(const Params3D &p, const Tile3D &t, bool stress, int *occ);
+cudaError_t launch_stress3d_tma(const Params3D &p, const TmaMaps &tm, const Tile3D &t, cudaStream_t s);
+cudaError_t launch_velocity3d_tma(const Params3D &p, const TmaMaps &tm, const Tile3D &t, cudaStream_t s);
+void launch_signal(unsigned long long *flag_lo, unsigned long long *flag_hi, unsigned long long value, cudaStream_t s);
+void launch_wait(const unsigned long long *flag_a, const unsigned long long *flag_b, unsigned long long value,
+                 unsigned int *timeout_flag, cudaStream_t s);
 void launch_stress2d(const Params2D &p, dim3 grid, dim3 block, cudaStream_t s);
 void launch_velocity2d(const Params2D &p, dim3 grid, dim3 block, cudaStream_t s);
 void launch_post2d(const Post2D &p, cudaStream_t s);

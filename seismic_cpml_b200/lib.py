@@ -67,6 +67,11 @@ SYMBOLS = {
     "cpml_synchronize": (C.c_int32, [_H]),
     "cpml_halo_plane": (C.c_int32, [_H, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "cpml_copy_plane": (C.c_int32, [_H, C.c_int32, _H, C.c_int32, C.c_int32]),
+    "cpml_p2p_export": (C.c_int32, [_H, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "cpml_p2p_attach_ipc": (C.c_int32, [_H, C.c_int32, C.c_void_p, C.c_int64]),
+    "cpml_p2p_attach_local": (C.c_int32, [_H, C.c_int32, _H]),
+    "cpml_p2p_detach": (C.c_int32, [_H]),
+    "cpml_get_launch_info": (C.c_int32, [_H, _ip, C.c_int32]),
     "cpml_get_seismograms": (C.c_int32, [_H, _dp, _dp]),
     "cpml_get_energy": (C.c_int32, [_H, _dp, _dp, _dp]),
     "cpml_get_plane": (C.c_int32, [_H, C.c_int32, C.c_int32, _dp]),
@@ -261,6 +266,31 @@ class Solver:
     def copy_plane_from(self, klocal_dst, src: "Solver", klocal_src, field):
         """One MPI_SENDRECV of the reference: plane klocal_src of `src` -> plane klocal_dst here."""
         self._ck(self._L.cpml_copy_plane(self._h, klocal_dst, src._h, klocal_src, field))
+
+    # -- direct slab-to-slab stores (replaces the MPI_SENDRECV calls of :811-823 / :951-963)
+    def p2p_export(self) -> bytes:
+        """The 64-byte CUDA IPC blob a neighbour process hands to p2p_attach_ipc."""
+        buf = C.create_string_buffer(64)
+        n = C.c_int64()
+        self._ck(self._L.cpml_p2p_export(self._h, buf, 64, C.byref(n)))
+        return buf.raw[:n.value]
+
+    def p2p_attach_ipc(self, side: int, blob: bytes):
+        buf = C.create_string_buffer(bytes(blob), len(blob))
+        self._ck(self._L.cpml_p2p_attach_ipc(self._h, side, buf, len(blob)))
+
+    def p2p_attach_local(self, side: int, neighbour: "Solver"):
+        self._ck(self._L.cpml_p2p_attach_local(self._h, side, neighbour._h))
+
+    def p2p_detach(self):
+        self._ck(self._L.cpml_p2p_detach(self._h))
+
+    def launch_info(self) -> dict:
+        v = np.zeros(10, dtype=np.int32)
+        self._ck(self._L.cpml_get_launch_info(self._h, _i(v), 10))
+        keys = ("tma", "tile_x", "tile_y", "stages", "planes_per_item", "z_chunks", "items",
+                "ctas_stress", "ctas_velocity", "peer_sides")
+        return dict(zip(keys, (int(x) for x in v)))
 
     # -- outputs
     def get_seismograms(self):

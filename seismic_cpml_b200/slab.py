@@ -1,6 +1,11 @@
 """z-slab decomposition of the 3-D solver across ranks: one process per GPU, the plane
 exchange of the reference's MPI_SENDRECV calls done with torch.distributed point-to-point
-operations (NCCL over NVLink between GPUs; gloo in the CPU tests).
+operations (NCCL over NVLink between GPUs; gloo in the CPU tests) -- or, on GPUs and by
+default, not done by the driver at all: with halo="p2p" the slabs are attached to each other
+through CUDA IPC (cpml_p2p_export / cpml_p2p_attach_ipc) and the update kernels store the
+boundary planes straight into the neighbour GPU's halo planes over NVLink, ordered by
+device-side flags; torch.distributed then only carries the 64-byte IPC blobs at start-up and
+the reductions of the results.
 
 Reference layout (seismic_CPML_3D_isotropic_MPI_OpenMP.f90):
   * rank r owns global planes r*NZ_LOCAL+1 .. (r+1)*NZ_LOCAL (:131,:397), arrays carry
@@ -54,12 +59,27 @@ class SlabDriver:
     GpuSlab below, or the numpy slab of tests/ on CPU.
     """
 
-    def __init__(self, backend, rank: int, nslabs: int, nzl: int, group=None):
+    def __init__(self, backend, rank: int, nslabs: int, nzl: int, group=None, halo: str = "sendrecv"):
         self.b, self.rank, self.nslabs, self.nzl, self.group = backend, rank, nslabs, nzl, group
         self.left = rank - 1 if rank > 0 else None          # MPI_PROC_NULL at the ends
         self.right = rank + 1 if rank < nslabs - 1 else None
         self._planes = {}
         self.bytes_sent = 0
+        if halo not in ("sendrecv", "p2p"):
+            raise ValueError("halo must be 'sendrecv' or 'p2p'")
+        self.halo = halo
+        if halo == "p2p" and nslabs > 1:
+            self._attach_peers()
+
+    def _attach_peers(self):
+        """Every rank publishes the IPC blob of its slab; each attaches its two neighbours."""
+        blobs = [None] * self.nslabs
+        dist.all_gather_object(blobs, self.b.p2p_export(), group=self.group)
+        if self.left is not None:
+            self.b.p2p_attach_ipc(0, blobs[self.left])
+        if self.right is not None:
+            self.b.p2p_attach_ipc(1, blobs[self.right])
+        dist.barrier(group=self.group)      # nobody steps before every neighbour is mapped
 
     def _plane(self, field, klocal):
         key = (field, klocal)
@@ -91,6 +111,11 @@ class SlabDriver:
 
     def step(self, it: int):
         """One pass of the loop body :804-1180 for this slab."""
+        if self.halo == "p2p":              # the kernels exchange the planes themselves
+            self.b.step_stress(it)
+            self.b.step_velocity(it)
+            self.b.step_finish(it)
+            return
         self.exchange(PHASE_V)
         self.b.step_stress(it)
         self.exchange(PHASE_S)

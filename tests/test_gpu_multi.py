@@ -1,6 +1,7 @@
-"""Multi-GPU slab decomposition over NCCL (needs >= 2 GPUs; skipped otherwise): N ranks, one
-GPU each, exchanging halo planes with torch.distributed point-to-point operations must
-reproduce the whole-grid oracle bit for bit."""
+"""Multi-GPU slab decomposition (needs >= 2 GPUs; skipped otherwise): N ranks, one GPU each,
+exchanging halo planes either by direct peer stores from inside the update kernels (CUDA IPC,
+halo="p2p") or with torch.distributed point-to-point operations over NCCL (halo="sendrecv"),
+must reproduce the whole-grid oracle bit for bit."""
 import os
 import socket
 import sys
@@ -28,7 +29,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, outdir, shape):
+def _worker(rank, world, port, outdir, shape, halo):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     import torch
@@ -49,7 +50,7 @@ def _worker(rank, world, port, outdir, shape):
     s.set_profiles(0, c["prof_x"]); s.set_profiles(1, c["prof_y"]); s.set_profiles(2, c["prof_z"])
     s.set_source_series(c["force_x"], c["force_y"])
     s.set_receivers(c["ix_rec"], c["iy_rec"])
-    drv = SlabDriver(GpuSlab(s), rank, world, s.nzl)
+    drv = SlabDriver(GpuSlab(s), rank, world, s.nzl, halo=halo)
     drv.run(1, nstep)
     owner = owner_of_plane(nz // 2, nz, world)
     sx, sy = drv.seismograms(owner)
@@ -62,15 +63,16 @@ def _worker(rank, world, port, outdir, shape):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs at least 2 GPUs")
+@pytest.mark.parametrize("halo", ["p2p", "sendrecv"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_nccl_slabs_match_oracle(world, tmp_path):
+def test_multi_gpu_slabs_match_oracle(world, halo, tmp_path):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     import refcfg
     from oracle import oracle as O
     shape = (40, 37, 48, 5, 80)
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), shape), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), shape, halo), nprocs=world, join=True)
     nx, ny, nz, npml, nstep = shape
     c = refcfg.cfg3d(nx=nx, ny=ny, nz=nz, npml=npml, nstep=nstep)
     o = O.run_3d_iso(**c, nproc=2, want_fields=True)

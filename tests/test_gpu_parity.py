@@ -189,6 +189,81 @@ def test_3d_slab_decomposition_matches_single_slab(nslabs):
             s.close()
 
 
+@pytest.mark.parametrize("nslabs", [2, 4])
+def test_3d_slabs_with_peer_stores_match_single_slab(nslabs):
+    """The slab handles attached to each other (cpml_p2p_attach_local): the update kernels
+    write the six boundary planes of :811-823 / :951-963 straight into the neighbour's halo
+    planes and device-side flags order the half steps -- no exchange call, no host
+    synchronisation inside the loop.  Result == whole grid, bit for bit."""
+    c = refcfg.cfg3d(nx=40, ny=37, nz=48, npml=5, nstep=80)
+    with solver3d(c) as whole:
+        whole.run(1, c["nstep"])
+        ref_sx, ref_sy = whole.get_seismograms()
+        ref_e = whole.get_energy()[0]
+        ref_fields = [whole.get_field(f) for f in range(9)]
+    slabs = [solver3d(c, nslabs=nslabs, slab_rank=r) for r in range(nslabs)]
+    try:
+        with pytest.raises(L.CpmlError):
+            slabs[0].p2p_attach_local(0, slabs[1])          # rank 0 has no lower neighbour
+        for r in range(nslabs - 1):
+            slabs[r].p2p_attach_local(1, slabs[r + 1])
+            slabs[r + 1].p2p_attach_local(0, slabs[r])
+        assert slabs[0].launch_info()["peer_sides"] == 2 and slabs[-1].launch_info()["peer_sides"] == 1
+        for it in range(1, c["nstep"] + 1):
+            for s in slabs:
+                s.step_stress(it)
+            for s in slabs:
+                s.step_velocity(it)
+                s.step_finish(it)
+        for s in slabs:
+            s.synchronize()
+        owner = nslabs // 2 - 1
+        sx, sy = slabs[owner].get_seismograms()
+        assert np.array_equal(sx, ref_sx) and np.array_equal(sy, ref_sy)
+        e = sum(s.get_energy()[0] for s in slabs)
+        assert refcfg.rel_l2(e, ref_e) <= TOL_ENERGY
+        for f in range(9):
+            got = np.concatenate([s.get_field(f) for s in slabs], axis=0)
+            assert np.array_equal(got, ref_fields[f]), F3[f]
+    finally:
+        for s in slabs:
+            s.close()
+
+
+@pytest.mark.parametrize("tile", [(32, 8), (64, 4), (64, 8), (104, 4), (128, 2), (128, 4)])
+@pytest.mark.parametrize("stages", [2, 5])
+def test_3d_tma_tiles_and_ring_depths(tile, stages, monkeypatch):
+    """Every TMA box shape / shared-memory ring depth gives the same bits (ragged grid: NX, NY
+    not multiples of any tile; several z chunks)."""
+    monkeypatch.setenv("CPML_TX", str(tile[0]))
+    monkeypatch.setenv("CPML_TY", str(tile[1]))
+    monkeypatch.setenv("CPML_STAGES", str(stages))
+    monkeypatch.setenv("CPML_ZCHUNKS", "3")
+    c = refcfg.cfg3d(nx=70, ny=45, nz=40, npml=6, nstep=60)
+    o = O.run_3d_iso(**c, nproc=2, want_fields=True)
+    with solver3d(c) as s:
+        info = s.launch_info()
+        assert info["tma"] == 1 and (info["tile_x"], info["tile_y"]) == tile and info["z_chunks"] == 3
+        s.run(1, c["nstep"])
+        check_traces(s.get_seismograms(), (o["sisvx"], o["sisvy"]))
+        for f, name in enumerate(F3):
+            assert np.array_equal(s.get_field(f), o[name]), name
+        assert refcfg.rel_l2(s.get_energy()[0], o["total_energy"]) <= TOL_ENERGY
+
+
+def test_3d_register_kernels_still_match(monkeypatch):
+    """CPML_KERNEL=reg: the register-marching kernels kept for A/B measurements."""
+    monkeypatch.setenv("CPML_KERNEL", "reg")
+    c = refcfg.cfg3d(nx=37, ny=45, nz=40, npml=6, nstep=60)
+    o = O.run_3d_iso(**c, nproc=2, want_fields=True)
+    with solver3d(c) as s:
+        assert s.launch_info()["tma"] == 0
+        s.run(1, c["nstep"])
+        check_traces(s.get_seismograms(), (o["sisvx"], o["sisvy"]))
+        for f, name in enumerate(F3):
+            assert np.array_equal(s.get_field(f), o[name]), name
+
+
 def test_3d_default_grid_full_size_vs_timed_oracle():
     """BASELINE config 3 (101 x 641 x 640, 41.4 M points) for 12 steps against the OpenMP
     build of the oracle (FMA-contracted, so not bit-identical: TOL applies), plus
