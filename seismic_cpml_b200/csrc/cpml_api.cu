@@ -498,7 +498,7 @@ static int32_t setup_tma(cpml_handle *h)
     t.tx = env_int("CPML_TX", c.nx <= 104 ? 104 : 64);
     t.ty = env_int("CPML_TY", c.nx <= 104 ? 4 : 8);
     if (!tma_tile_supported(t.tx, t.ty)) FAIL(CPML_EINVAL, "unsupported CPML_TX x CPML_TY tile");
-    t.stages = std::max(2, std::min(16, env_int("CPML_STAGES", 4)));
+    t.stages = std::max(1, std::min(7, env_int("CPML_STAGES", 2)));
     t.minb = std::max(1, std::min(3, env_int("CPML_MINB", 1)));
     t.ntx = (c.nx + t.tx - 1) / t.tx;
     t.nty = (c.ny + t.ty - 1) / t.ty;
@@ -526,7 +526,7 @@ static int32_t setup_tma(cpml_handle *h)
         cudaError_t e1 = tma_occupancy(p, t, true, &occ_s), e2 = tma_occupancy(p, t, false, &occ_v);
         if (e1 == cudaSuccess && e2 == cudaSuccess && occ_s >= 1 && occ_v >= 1) break;
         cudaGetLastError();
-        if (t.stages <= 2) FAIL(CPML_ECUDA, "TMA kernels do not fit on this device");
+        if (t.stages <= 1) FAIL(CPML_ECUDA, "TMA kernels do not fit on this device");
         t.stages--;
     }
     const int cap = env_int("CPML_CTAS_PER_SM", 0);
@@ -663,6 +663,8 @@ static Params3D make_p3(cpml_handle *h, int it)
     p.src_x = h->d_src_x; p.src_y = h->d_src_y;
     p.npml = c.npoints_pml; p.energy_bug_compat = c.energy_bug_compat;
     p.rho = c.rho; p.lambda = c.lambda; p.mu = c.mu;
+    p.inv_den = 1.0 / (2.0 * c.mu * (3.0 * c.lambda + 2.0 * c.mu));
+    p.inv_2mu = 1.0 / (2.0 * c.mu);
     p.partials = h->d_partials; p.nblocks = h->nblocks;
     p.kunit = 1;
     for (int ax = 0; ax < 3; ax++)

@@ -127,41 +127,125 @@ __device__ __forceinline__ void block_sum2(double &a, double &b, double *red /* 
 
 }  // namespace
 
+// Position in a ring of shared-memory stages: stage index and the mbarrier phase parity of
+// its current use.  Every load goes through the stages cyclically, so the parity flips
+// exactly when the index wraps.
+struct RingPos {
+    uint32_t s, par;
+    __device__ __forceinline__ void advance(uint32_t depth) { if (++s == depth) { s = 0; par ^= 1u; } }
+};
+
 // ------------------------------------------------------------------------------- stress
-// maps: 0 vx (halo box at (0,0))  1 vy (halo, (-2,-1))  2 vz (halo, (-2,0))
-//       3 sxx 4 syy 5 szz 6 sxy 7 sxz 8 syz (plain boxes)
+// ring N (planes n and n+1 are needed):  vx (halo box at (0,0)), vy (halo, (-2,-1))
+// ring C (plane n only):                 vz (halo, (-2,0)), sxx syy szz sxy sxz syz (plain boxes)
+// maps: 0 vx 1 vy 2 vz 3..8 sigma
+template <bool PML, bool KUNIT>
+__device__ __forceinline__ void stress_point(
+    const Params3D &p, const long long q, const int i, const int j, const int k, const int kg,
+    const bool valid, const bool do_n, const bool do_xy, const bool do_xz, const bool do_yz,
+    const bool in_x, const bool in_y, const bool in_z, const long long qx, const long long qy, const long long qz,
+    const double (&mv)[9],
+    const double vx_c, const double vx_ip, const double vx_jp, const double vx_n,
+    const double vy_c, const double vy_im, const double vy_jm, const double vy_n,
+    const double vz_c, const double vz_im, const double vz_jp, const double vz_m,
+    const double sxx, const double syy, const double szz, const double sxy, const double sxz, const double syz)
+{
+    const double odx = p.odx, ody = p.ody, odz = p.odz;
+    const double dt_l = p.dt_lambda, dt_m = p.dt_mu, dt_l2m = p.dt_lambdaplus2mu;
+    double szz_out = szz, sxz_out = sxz, syz_out = syz;
+
+    // ---- sigmaxx, sigmayy, sigmazz  (:836-863)
+    if (do_n && kg >= 2) {                                  // k2begin, :792-793
+        double value_dvx_dx = (vx_ip - vx_c) * odx;
+        double value_dvy_dy = (vy_c - vy_jm) * ody;
+        double value_dvz_dz = (vz_c - vz_m) * odz;
+        if (PML) {
+            if (in_x) value_dvx_dx = cpml_apply<KUNIT>(p.mx[0], qx, mv[0], p.cx.b_half[i], p.cx.a_half[i], KUNIT ? 1.0 : p.cx.K_half[i], value_dvx_dx);
+            if (in_y) value_dvy_dy = cpml_apply<KUNIT>(p.my[0], qy, mv[3], p.cy.b[j], p.cy.a[j], KUNIT ? 1.0 : p.cy.K[j], value_dvy_dy);
+            if (in_z) value_dvz_dz = cpml_apply<KUNIT>(p.mz[0], qz, mv[6], p.cz.b[kg], p.cz.a[kg], KUNIT ? 1.0 : p.cz.K[kg], value_dvz_dz);
+        }
+        st_stream(p.sxx + q, dt_l2m * value_dvx_dx + dt_l * (value_dvy_dy + value_dvz_dz) + sxx);
+        st_stream(p.syy + q, dt_l * (value_dvx_dx + value_dvz_dz) + dt_l2m * value_dvy_dy + syy);
+        szz_out = dt_l * (value_dvx_dx + value_dvy_dy) + dt_l2m * value_dvz_dz + szz;
+        st_stream(p.szz + q, szz_out);
+    }
+    // ---- sigmaxy  (:877-894)
+    if (do_xy) {
+        double value_dvy_dx = (vy_c - vy_im) * odx;
+        double value_dvx_dy = (vx_jp - vx_c) * ody;
+        if (PML) {
+            if (in_x) value_dvy_dx = cpml_apply<KUNIT>(p.mx[1], qx, mv[1], p.cx.b[i], p.cx.a[i], KUNIT ? 1.0 : p.cx.K[i], value_dvy_dx);
+            if (in_y) value_dvx_dy = cpml_apply<KUNIT>(p.my[1], qy, mv[4], p.cy.b_half[j], p.cy.a_half[j], KUNIT ? 1.0 : p.cy.K_half[j], value_dvx_dy);
+        }
+        st_stream(p.sxy + q, dt_m * (value_dvy_dx + value_dvx_dy) + sxy);
+    }
+    // ---- sigmaxz, sigmayz  (:908-943)
+    if (kg <= p.nz - 1) {                                   // kminus1end, :795-796
+        if (do_xz) {
+            double value_dvz_dx = (vz_c - vz_im) * odx;
+            double value_dvx_dz = (vx_n - vx_c) * odz;
+            if (PML) {
+                if (in_x) value_dvz_dx = cpml_apply<KUNIT>(p.mx[2], qx, mv[2], p.cx.b[i], p.cx.a[i], KUNIT ? 1.0 : p.cx.K[i], value_dvz_dx);
+                if (in_z) value_dvx_dz = cpml_apply<KUNIT>(p.mz[1], qz, mv[7], p.cz.b_half[kg], p.cz.a_half[kg], KUNIT ? 1.0 : p.cz.K_half[kg], value_dvx_dz);
+            }
+            sxz_out = dt_m * (value_dvz_dx + value_dvx_dz) + sxz;
+            st_stream(p.sxz + q, sxz_out);
+        }
+        if (do_yz) {
+            double value_dvz_dy = (vz_jp - vz_c) * ody;
+            double value_dvy_dz = (vy_n - vy_c) * odz;
+            if (PML) {
+                if (in_y) value_dvz_dy = cpml_apply<KUNIT>(p.my[2], qy, mv[5], p.cy.b_half[j], p.cy.a_half[j], KUNIT ? 1.0 : p.cy.K_half[j], value_dvz_dy);
+                if (in_z) value_dvy_dz = cpml_apply<KUNIT>(p.mz[2], qz, mv[8], p.cz.b_half[kg], p.cz.a_half[kg], KUNIT ? 1.0 : p.cz.K_half[kg], value_dvy_dz);
+            }
+            syz_out = dt_m * (value_dvz_dy + value_dvy_dz) + syz;
+            st_stream(p.syz + q, syz_out);
+        }
+    }
+    // ---- boundary planes go straight into the neighbour slabs' halo planes (:951-963)
+    if (valid) {
+        const long long qp = (long long)(j - 1) * p.pitch + (i - 1);
+        if (k == 1 && p.peer_lo[2]) p.peer_lo[2][qp] = szz_out;                                      // sigmazz(:,:,1) -> left
+        if (k == p.nzl && p.peer_hi[1]) { p.peer_hi[1][qp] = sxz_out; p.peer_hi[2][qp] = syz_out; }   // -> right
+    }
+}
+
 template <bool KUNIT, int TX, int TY, int MINB>
 __global__ void __launch_bounds__(TX *TY, MINB)
 k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMaps tm, const __grid_constant__ Tile3D t)
 {
     using G = TileGeom<TX, TY>;
     constexpr int W = G::W;
-    constexpr int STAGE_BYTES = 3 * G::HALO_BYTES + 6 * G::PLAIN_BYTES;
-    constexpr uint32_t TX_FULL = 3 * G::HALO_BOX_BYTES + 6 * G::PLAIN_BOX_BYTES;
-    constexpr uint32_t TX_NEXT = 2 * G::HALO_BOX_BYTES;          // vx, vy of plane ke+1
+    constexpr int NBYTES = 2 * G::HALO_BYTES;                       // ring N stage: vx, vy
+    constexpr int CBYTES = G::HALO_BYTES + 6 * G::PLAIN_BYTES;      // ring C stage: vz, 6 sigma
+    constexpr uint32_t TX_N = 2 * G::HALO_BOX_BYTES;
+    constexpr uint32_t TX_C = G::HALO_BOX_BYTES + 6 * G::PLAIN_BOX_BYTES;
+    constexpr int PD = G::PLAIN_BYTES / 8;
 
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t sbase = (smem_u32(smem_dyn) + 127u) & ~127u;
-    unsigned char *gbase = smem_dyn + (sbase - smem_u32(smem_dyn));
-    const uint32_t bar0 = sbase;                                  // S mbarriers, 8 bytes each
-    const uint32_t stage0 = sbase + kBarBytes;
-    const unsigned char *gstage0 = gbase + kBarBytes;
-    const int S = t.stages;
+    const unsigned char *gbase = smem_dyn + (sbase - smem_u32(smem_dyn));
+    const uint32_t SC = (uint32_t)t.stages, SN = SC + 1;
+    const uint32_t barN = sbase, barC = sbase + 64;                 // up to 8 mbarriers per ring
+    const uint32_t ringN = sbase + kBarBytes, ringC = ringN + SN * NBYTES;
+    const unsigned char *gN = gbase + kBarBytes, *gC = gN + (size_t)SN * NBYTES;
 
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int tid = ty * TX + tx;
     if (tid == 0) {
-        for (int s = 0; s < S; s++) mbar_init(bar0 + 8 * s, 1);
+        for (uint32_t s = 0; s < SN; s++) mbar_init(barN + 8 * s, 1);
+        for (uint32_t s = 0; s < SC; s++) mbar_init(barC + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     const int pitch = p.pitch;
     const long long pl = p.plane;
-    const double odx = p.odx, ody = p.ody, odz = p.odz;
-    const double dt_l = p.dt_lambda, dt_m = p.dt_mu, dt_l2m = p.dt_lambdaplus2mu;
+    // per-thread element offsets inside the tiles
+    const int oh = ty * W + tx;          // halo tile, box origin (0,0): centre
+    const int oc = ty * TX + tx;         // plain tile
 
-    uint32_t g = 0;     // running count of plane loads of this CTA: stage = g % S, parity = (g / S) & 1
+    RingPos rn{0, 0}, rc{0, 0};          // stage of the current plane in each ring
     for (int item = blockIdx.x; item < t.nitems; item += gridDim.x) {
         const int tix = item % t.ntx;
         const int rest = item / t.ntx;
@@ -171,32 +255,28 @@ k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMa
         const int kb = 1 + zc * t.kchunk;
         const int ke = min(p.nzl, kb + t.kchunk - 1);
         const int np = ke - kb + 1;
+        const int x0 = i0 - 1, y0 = j0 - 1;
 
-        // plane load l of this item: planes kb .. ke complete, plane ke+1 only vx, vy
-        auto issue = [&](int l) {
-            const uint32_t gl = g + (uint32_t)l;
-            const uint32_t s = gl % (uint32_t)S;
-            const uint32_t bar = bar0 + 8 * s;
-            const uint32_t dst = stage0 + s * STAGE_BYTES;
-            const int k = kb + l;
-            const int x0 = i0 - 1, y0 = j0 - 1;
-            if (l < np) {
-                mbar_expect_tx(bar, TX_FULL);
-                tma_load_3d(dst + 0 * G::HALO_BYTES, &tm.m[0], x0, y0, k, bar);
-                tma_load_3d(dst + 1 * G::HALO_BYTES, &tm.m[1], x0 - 2, y0 - 1, k, bar);
-                tma_load_3d(dst + 2 * G::HALO_BYTES, &tm.m[2], x0 - 2, y0, k, bar);
+        // ring N load l = plane kb+l (l = 0..np: the last one only feeds the z differences of
+        // plane ke); ring C load l = plane kb+l (l = 0..np-1)
+        if (tid == 0) {
+            uint32_t s = rn.s;
+            for (int l = 0; l < min((int)SN, np + 1); l++) {
+                mbar_expect_tx(barN + 8 * s, TX_N);
+                tma_load_3d(ringN + s * NBYTES, &tm.m[0], x0, y0, kb + l, barN + 8 * s);
+                tma_load_3d(ringN + s * NBYTES + G::HALO_BYTES, &tm.m[1], x0 - 2, y0 - 1, kb + l, barN + 8 * s);
+                if (++s == SN) s = 0;
+            }
+            s = rc.s;
+            for (int l = 0; l < min((int)SC, np); l++) {
+                const uint32_t dst = ringC + s * CBYTES;
+                mbar_expect_tx(barC + 8 * s, TX_C);
+                tma_load_3d(dst, &tm.m[2], x0 - 2, y0, kb + l, barC + 8 * s);
 #pragma unroll
                 for (int f = 0; f < 6; f++)
-                    tma_load_3d(dst + 3 * G::HALO_BYTES + f * G::PLAIN_BYTES, &tm.m[3 + f], x0, y0, k, bar);
-            } else {
-                mbar_expect_tx(bar, TX_NEXT);
-                tma_load_3d(dst + 0 * G::HALO_BYTES, &tm.m[0], x0, y0, k, bar);
-                tma_load_3d(dst + 1 * G::HALO_BYTES, &tm.m[1], x0 - 2, y0 - 1, k, bar);
+                    tma_load_3d(dst + G::HALO_BYTES + f * G::PLAIN_BYTES, &tm.m[3 + f], x0, y0, kb + l, barC + 8 * s);
+                if (++s == SC) s = 0;
             }
-        };
-        if (tid == 0) {
-            const int npro = min(S, np + 1);
-            for (int l = 0; l < npro; l++) issue(l);
         }
 
         const int i = i0 + tx, j = j0 + ty;
@@ -205,175 +285,225 @@ k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMa
 
         const bool in_x = valid && ((i <= p.xlo) || (i >= p.xhi));
         const bool in_y = valid && ((j <= p.ylo) || (j >= p.yhi));
-        const int sx = in_x ? shell_index(i, p.xlo, p.xhi) : 0;
-        const int sy = in_y ? shell_index(j, p.ylo, p.yhi) : 0;
-
+        const bool warp_pml = __any_sync(0xffffffffu, in_x || in_y);
         // loop bounds of the four nests (i, j part; the k part is tested per plane)
         const bool do_n = valid && (i <= p.nx - 1) && (j >= 2);     // :838-839
         const bool do_xy = valid && (i >= 2) && (j <= p.ny - 1);    // :878-879
         const bool do_xz = valid && (i >= 2);                       // :910-911
         const bool do_yz = valid && (j <= p.ny - 1);                // :927-928
 
-        double ax = 0, bxc = 0, Kx = 1, axh = 0, bxh = 0, Kxh = 1, ay = 0, by = 0, Ky = 1, ayh = 0, byh = 0, Kyh = 1;
-        if (in_x) { ax = p.cx.a[i]; bxc = p.cx.b[i]; axh = p.cx.a_half[i]; bxh = p.cx.b_half[i];
-                    if (!KUNIT) { Kx = p.cx.K[i]; Kxh = p.cx.K_half[i]; } }
-        if (in_y) { ay = p.cy.a[j]; by = p.cy.b[j]; ayh = p.cy.a_half[j]; byh = p.cy.b_half[j];
-                    if (!KUNIT) { Ky = p.cy.K[j]; Kyh = p.cy.K_half[j]; } }
-
-        // x / y shell memory variables are fetched one plane ahead of their use
-        long long qx = in_x ? ((long long)(kb - 1) * p.ny + (j - 1)) * p.sxp + sx : 0;
-        long long qy = in_y ? ((long long)(kb - 1) * p.sy + sy) * pitch + (i - 1) : 0;
+        long long qx = 0, qy = 0;
+        if (in_x) qx = ((long long)(kb - 1) * p.ny + (j - 1)) * p.sxp + shell_index(i, p.xlo, p.xhi);
+        if (in_y) qy = ((long long)(kb - 1) * p.sy + shell_index(j, p.ylo, p.yhi)) * pitch + (i - 1);
         const long long qx_step = (long long)p.ny * p.sxp, qy_step = (long long)p.sy * pitch;
-        double m_x0 = 0, m_x1 = 0, m_x2 = 0, m_y0 = 0, m_y1 = 0, m_y2 = 0;
-        if (in_x) { m_x0 = p.mx[0][qx]; m_x1 = p.mx[1][qx]; m_x2 = p.mx[2][qx]; }
-        if (in_y) { m_y0 = p.my[0][qy]; m_y1 = p.my[1][qy]; m_y2 = p.my[2][qy]; }
 
         double vz_m = valid ? p.vz[q - pl] : 0.0;                   // plane kb-1, carried along z
 
+        mbar_wait(barN + 8 * rn.s, rn.par);
         for (int n = 0; n < np; ++n, q += pl, qx += qx_step, qy += qy_step) {
             const int k = kb + n;
             const int kg = k + p.koff;                              // :837
-            const uint32_t gc = g + (uint32_t)n, gn = gc + 1;
-            const uint32_t sc = gc % (uint32_t)S, sn = gn % (uint32_t)S;
-
-            // next plane's x / y memory variables
-            double n_x0 = 0, n_x1 = 0, n_x2 = 0, n_y0 = 0, n_y1 = 0, n_y2 = 0;
-            if (n + 1 < np) {
-                if (in_x) { n_x0 = p.mx[0][qx + qx_step]; n_x1 = p.mx[1][qx + qx_step]; n_x2 = p.mx[2][qx + qx_step]; }
-                if (in_y) { n_y0 = p.my[0][qy + qy_step]; n_y1 = p.my[1][qy + qy_step]; n_y2 = p.my[2][qy + qy_step]; }
-            }
-            const bool in_z = valid && ((kg <= p.zlo) || (kg >= p.zhi));
+            // C-PML memory variables of this plane: every load is issued before the waits (and
+            // before any store of the recursion, which the compiler must assume to alias)
+            const bool z_pml = (kg <= p.zlo) || (kg >= p.zhi);      // uniform
+            const bool pml = warp_pml || z_pml;                     // warp-uniform
+            const bool in_z = valid && z_pml;
             long long qz = 0;
-            double m_z0 = 0, m_z1 = 0, m_z2 = 0, az = 0, bz = 0, Kz = 1, azh = 0, bzh = 0, Kzh = 1;
-            if (in_z) {
-                qz = ((long long)(shell_index(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1);
-                m_z0 = p.mz[0][qz]; m_z1 = p.mz[1][qz]; m_z2 = p.mz[2][qz];
-                az = p.cz.a[kg]; bz = p.cz.b[kg]; azh = p.cz.a_half[kg]; bzh = p.cz.b_half[kg];
-                if (!KUNIT) { Kz = p.cz.K[kg]; Kzh = p.cz.K_half[kg]; }
-            }
-
-            if (n == 0) mbar_wait(bar0 + 8 * sc, (gc / (uint32_t)S) & 1u);
-            mbar_wait(bar0 + 8 * sn, (gn / (uint32_t)S) & 1u);
-
-            const unsigned char *st = gstage0 + (size_t)sc * STAGE_BYTES;
-            const unsigned char *stn = gstage0 + (size_t)sn * STAGE_BYTES;
-            const double *Tvx = (const double *)(st + 0 * G::HALO_BYTES);
-            const double *Tvy = (const double *)(st + 1 * G::HALO_BYTES);
-            const double *Tvz = (const double *)(st + 2 * G::HALO_BYTES);
-            const double *Ts = (const double *)(st + 3 * G::HALO_BYTES);
-            constexpr int PD = G::PLAIN_BYTES / 8;
-            const int c = ty * TX + tx;
-
-            const double vx_c = Tvx[ty * W + tx], vx_ip = Tvx[ty * W + tx + 1], vx_jp = Tvx[(ty + 1) * W + tx];
-            const double vy_c = Tvy[(ty + 1) * W + tx + 2], vy_im = Tvy[(ty + 1) * W + tx + 1], vy_jm = Tvy[ty * W + tx + 2];
-            const double vz_c = Tvz[ty * W + tx + 2], vz_im = Tvz[ty * W + tx + 1], vz_jp = Tvz[(ty + 1) * W + tx + 2];
-            const double vx_n = ((const double *)(stn + 0 * G::HALO_BYTES))[ty * W + tx];
-            const double vy_n = ((const double *)(stn + 1 * G::HALO_BYTES))[(ty + 1) * W + tx + 2];
-            const double sxx = Ts[0 * PD + c], syy = Ts[1 * PD + c], szz = Ts[2 * PD + c];
-            const double sxy = Ts[3 * PD + c], sxz = Ts[4 * PD + c], syz = Ts[5 * PD + c];
-
-            double szz_out = szz, sxz_out = sxz, syz_out = syz;
-
-            // ---- sigmaxx, sigmayy, sigmazz  (:836-863)
-            if (do_n && kg >= 2) {                                  // k2begin, :792-793
-                double value_dvx_dx = (vx_ip - vx_c) * odx;
-                double value_dvy_dy = (vy_c - vy_jm) * ody;
-                double value_dvz_dz = (vz_c - vz_m) * odz;
-                if (in_x) value_dvx_dx = cpml_apply<KUNIT>(p.mx[0], qx, m_x0, bxh, axh, Kxh, value_dvx_dx);
-                if (in_y) value_dvy_dy = cpml_apply<KUNIT>(p.my[0], qy, m_y0, by, ay, Ky, value_dvy_dy);
-                if (in_z) value_dvz_dz = cpml_apply<KUNIT>(p.mz[0], qz, m_z0, bz, az, Kz, value_dvz_dz);
-                st_stream(p.sxx + q, dt_l2m * value_dvx_dx + dt_l * (value_dvy_dy + value_dvz_dz) + sxx);
-                st_stream(p.syy + q, dt_l * (value_dvx_dx + value_dvz_dz) + dt_l2m * value_dvy_dy + syy);
-                szz_out = dt_l * (value_dvx_dx + value_dvy_dy) + dt_l2m * value_dvz_dz + szz;
-                st_stream(p.szz + q, szz_out);
-            }
-            // ---- sigmaxy  (:877-894)
-            if (do_xy) {
-                double value_dvy_dx = (vy_c - vy_im) * odx;
-                double value_dvx_dy = (vx_jp - vx_c) * ody;
-                if (in_x) value_dvy_dx = cpml_apply<KUNIT>(p.mx[1], qx, m_x1, bxc, ax, Kx, value_dvy_dx);
-                if (in_y) value_dvx_dy = cpml_apply<KUNIT>(p.my[1], qy, m_y1, byh, ayh, Kyh, value_dvx_dy);
-                st_stream(p.sxy + q, dt_m * (value_dvy_dx + value_dvx_dy) + sxy);
-            }
-            // ---- sigmaxz, sigmayz  (:908-943)
-            if (kg <= p.nz - 1) {                                   // kminus1end, :795-796
-                if (do_xz) {
-                    double value_dvz_dx = (vz_c - vz_im) * odx;
-                    double value_dvx_dz = (vx_n - vx_c) * odz;
-                    if (in_x) value_dvz_dx = cpml_apply<KUNIT>(p.mx[2], qx, m_x2, bxc, ax, Kx, value_dvz_dx);
-                    if (in_z) value_dvx_dz = cpml_apply<KUNIT>(p.mz[1], qz, m_z1, bzh, azh, Kzh, value_dvx_dz);
-                    sxz_out = dt_m * (value_dvz_dx + value_dvx_dz) + sxz;
-                    st_stream(p.sxz + q, sxz_out);
-                }
-                if (do_yz) {
-                    double value_dvz_dy = (vz_jp - vz_c) * ody;
-                    double value_dvy_dz = (vy_n - vy_c) * odz;
-                    if (in_y) value_dvz_dy = cpml_apply<KUNIT>(p.my[2], qy, m_y2, byh, ayh, Kyh, value_dvz_dy);
-                    if (in_z) value_dvy_dz = cpml_apply<KUNIT>(p.mz[2], qz, m_z2, bzh, azh, Kzh, value_dvy_dz);
-                    syz_out = dt_m * (value_dvz_dy + value_dvy_dz) + syz;
-                    st_stream(p.syz + q, syz_out);
+            double mv[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            if (pml) {
+                if (in_x) { mv[0] = p.mx[0 + 0][qx]; mv[1] = p.mx[0 + 1][qx]; mv[2] = p.mx[0 + 2][qx]; }
+                if (in_y) { mv[3] = p.my[0 + 0][qy]; mv[4] = p.my[0 + 1][qy]; mv[5] = p.my[0 + 2][qy]; }
+                if (in_z) {
+                    qz = ((long long)(shell_index(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1);
+                    mv[6] = p.mz[0 + 0][qz]; mv[7] = p.mz[0 + 1][qz]; mv[8] = p.mz[0 + 2][qz];
                 }
             }
-            // ---- boundary planes go straight into the neighbour slabs' halo planes (:951-963)
-            if (valid) {
-                const long long qp = (long long)(j - 1) * pitch + (i - 1);
-                if (k == 1 && p.peer_lo[2]) p.peer_lo[2][qp] = szz_out;                  // sigmazz(:,:,1) -> left
-                if (k == p.nzl && p.peer_hi[1]) { p.peer_hi[1][qp] = sxz_out; p.peer_hi[2][qp] = syz_out; }   // -> right
-            }
+            RingPos rn1 = rn;
+            rn1.advance(SN);
+            mbar_wait(barN + 8 * rn1.s, rn1.par);
+            mbar_wait(barC + 8 * rc.s, rc.par);
 
+            const double *Tvx = (const double *)(gN + (size_t)rn.s * NBYTES);
+            const double *Tvy = (const double *)(gN + (size_t)rn.s * NBYTES + G::HALO_BYTES);
+            const double *Tvxn = (const double *)(gN + (size_t)rn1.s * NBYTES);
+            const double *Tvyn = (const double *)(gN + (size_t)rn1.s * NBYTES + G::HALO_BYTES);
+            const double *Tvz = (const double *)(gC + (size_t)rc.s * CBYTES);
+            const double *Ts = (const double *)(gC + (size_t)rc.s * CBYTES + G::HALO_BYTES);
+
+            const double vx_c = Tvx[oh], vx_ip = Tvx[oh + 1], vx_jp = Tvx[oh + W];
+            const double vy_c = Tvy[oh + W + 2], vy_im = Tvy[oh + W + 1], vy_jm = Tvy[oh + 2];
+            const double vz_c = Tvz[oh + 2], vz_im = Tvz[oh + 1], vz_jp = Tvz[oh + W + 2];
+            const double vx_n = Tvxn[oh], vy_n = Tvyn[oh + W + 2];
+            const double sxx = Ts[0 * PD + oc], syy = Ts[1 * PD + oc], szz = Ts[2 * PD + oc];
+            const double sxy = Ts[3 * PD + oc], sxz = Ts[4 * PD + oc], syz = Ts[5 * PD + oc];
+
+            if (pml) {
+                stress_point<true, KUNIT>(p, q, i, j, k, kg, valid, do_n, do_xy, do_xz, do_yz, in_x, in_y, in_z, qx, qy, qz, mv,
+                                          vx_c, vx_ip, vx_jp, vx_n, vy_c, vy_im, vy_jm, vy_n, vz_c, vz_im, vz_jp, vz_m,
+                                          sxx, syy, szz, sxy, sxz, syz);
+            } else {
+                stress_point<false, KUNIT>(p, q, i, j, k, kg, valid, do_n, do_xy, do_xz, do_yz, false, false, false, 0, 0, 0, mv,
+                                           vx_c, vx_ip, vx_jp, vx_n, vy_c, vy_im, vy_jm, vy_n, vz_c, vz_im, vz_jp, vz_m,
+                                           sxx, syy, szz, sxy, sxz, syz);
+            }
             vz_m = vz_c;
-            m_x0 = n_x0; m_x1 = n_x1; m_x2 = n_x2; m_y0 = n_y0; m_y1 = n_y1; m_y2 = n_y2;
 
-            __syncthreads();                                        // stage sc is free
-            if (tid == 0 && n + S <= np) issue(n + S);
+            __syncthreads();                                        // stages rn.s / rc.s are free
+            if (tid == 0) {
+                if (n + (int)SN <= np) {
+                    const uint32_t s = rn.s, bar = barN + 8 * s;
+                    const int kk = kb + n + (int)SN;
+                    mbar_expect_tx(bar, TX_N);
+                    tma_load_3d(ringN + s * NBYTES, &tm.m[0], x0, y0, kk, bar);
+                    tma_load_3d(ringN + s * NBYTES + G::HALO_BYTES, &tm.m[1], x0 - 2, y0 - 1, kk, bar);
+                }
+                if (n + (int)SC < np) {
+                    const uint32_t s = rc.s, bar = barC + 8 * s, dst = ringC + s * CBYTES;
+                    const int kk = kb + n + (int)SC;
+                    mbar_expect_tx(bar, TX_C);
+                    tma_load_3d(dst, &tm.m[2], x0 - 2, y0, kk, bar);
+#pragma unroll
+                    for (int f = 0; f < 6; f++)
+                        tma_load_3d(dst + G::HALO_BYTES + f * G::PLAIN_BYTES, &tm.m[3 + f], x0, y0, kk, bar);
+                }
+            }
+            rn = rn1;
+            rc.advance(SC);
         }
-        g += (uint32_t)(np + 1);
+        rn.advance(SN);        // plane ke+1 of ring N has been consumed as "next" only
     }
 }
 
 // ----------------------------------------------------------------------------- velocity
-// maps: 0 sxx (halo box at (-2,0))  1 syy (halo, (0,0))  2 sxy (halo, (0,-1))
-//       3 sxz (halo, (0,0))  4 syz (halo, (0,-1))  5 szz  6 vx  7 vy  8 vz (plain boxes)
+// ring N (planes n and n+1): szz (plain box)
+// ring C (plane n only):     sxx (halo box at (-2,0)), syy (halo, (0,0)), sxy (halo, (0,-1)),
+//                            sxz (halo, (0,0)), syz (halo, (0,-1)), vx vy vz (plain boxes)
+// maps: 0 sxx 1 syy 2 sxy 3 sxz 4 syz 5 szz 6 vx 7 vy 8 vz
+template <bool PML, bool KUNIT>
+__device__ __forceinline__ void velocity_point(
+    const Params3D &p, const long long q, const int i, const int j, const int k, const int kg,
+    const bool valid, const bool do_vx, const bool do_vy, const bool do_vz, const bool edge_ij, const bool ebox_ij,
+    const bool src_ij, const bool in_x, const bool in_y, const bool in_z, const long long qx, const long long qy,
+    const long long qz, const double (&mv)[9],
+    const double sxx_c, const double sxx_im, const double syy_c, const double syy_jp,
+    const double sxy_c, const double sxy_jm, const double sxy_ip, const double sxz_c, const double sxz_ip,
+    const double sxz_m, const double syz_c, const double syz_jm, const double syz_m, const double szz_c,
+    const double szz_n, double vx, double vy, double vz, double &ekin, double &epot)
+{
+    const double odx = p.odx, ody = p.ody, odz = p.odz, dt_r = p.dt_over_rho;
+    if (kg >= 2) {                                           // k2begin
+        if (do_vx) {                                         // :976-996
+            double value_dsigmaxx_dx = (sxx_c - sxx_im) * odx;
+            double value_dsigmaxy_dy = (sxy_c - sxy_jm) * ody;
+            double value_dsigmaxz_dz = (sxz_c - sxz_m) * odz;
+            if (PML) {
+                if (in_x) value_dsigmaxx_dx = cpml_apply<KUNIT>(p.mx[3], qx, mv[0], p.cx.b[i], p.cx.a[i], KUNIT ? 1.0 : p.cx.K[i], value_dsigmaxx_dx);
+                if (in_y) value_dsigmaxy_dy = cpml_apply<KUNIT>(p.my[3], qy, mv[3], p.cy.b[j], p.cy.a[j], KUNIT ? 1.0 : p.cy.K[j], value_dsigmaxy_dy);
+                if (in_z) value_dsigmaxz_dz = cpml_apply<KUNIT>(p.mz[3], qz, mv[6], p.cz.b[kg], p.cz.a[kg], KUNIT ? 1.0 : p.cz.K[kg], value_dsigmaxz_dz);
+            }
+            vx = dt_r * (value_dsigmaxx_dx + value_dsigmaxy_dy + value_dsigmaxz_dz) + vx;
+        }
+        if (do_vy) {                                         // :998-1016
+            double value_dsigmaxy_dx = (sxy_ip - sxy_c) * odx;
+            double value_dsigmayy_dy = (syy_jp - syy_c) * ody;
+            double value_dsigmayz_dz = (syz_c - syz_m) * odz;
+            if (PML) {
+                if (in_x) value_dsigmaxy_dx = cpml_apply<KUNIT>(p.mx[4], qx, mv[1], p.cx.b_half[i], p.cx.a_half[i], KUNIT ? 1.0 : p.cx.K_half[i], value_dsigmaxy_dx);
+                if (in_y) value_dsigmayy_dy = cpml_apply<KUNIT>(p.my[4], qy, mv[4], p.cy.b_half[j], p.cy.a_half[j], KUNIT ? 1.0 : p.cy.K_half[j], value_dsigmayy_dy);
+                if (in_z) value_dsigmayz_dz = cpml_apply<KUNIT>(p.mz[4], qz, mv[7], p.cz.b[kg], p.cz.a[kg], KUNIT ? 1.0 : p.cz.K[kg], value_dsigmayz_dz);
+            }
+            vy = dt_r * (value_dsigmaxy_dx + value_dsigmayy_dy + value_dsigmayz_dz) + vy;
+        }
+    }
+    if (do_vz && kg <= p.nz - 1) {                           // kminus1end, :1031-1052
+        double value_dsigmaxz_dx = (sxz_ip - sxz_c) * odx;
+        double value_dsigmayz_dy = (syz_c - syz_jm) * ody;
+        double value_dsigmazz_dz = (szz_n - szz_c) * odz;
+        if (PML) {
+            if (in_x) value_dsigmaxz_dx = cpml_apply<KUNIT>(p.mx[5], qx, mv[2], p.cx.b_half[i], p.cx.a_half[i], KUNIT ? 1.0 : p.cx.K_half[i], value_dsigmaxz_dx);
+            if (in_y) value_dsigmayz_dy = cpml_apply<KUNIT>(p.my[5], qy, mv[5], p.cy.b[j], p.cy.a[j], KUNIT ? 1.0 : p.cy.K[j], value_dsigmayz_dy);
+            if (in_z) value_dsigmazz_dz = cpml_apply<KUNIT>(p.mz[5], qz, mv[8], p.cz.b_half[kg], p.cz.a_half[kg], KUNIT ? 1.0 : p.cz.K_half[kg], value_dsigmazz_dz);
+        }
+        vz = dt_r * (value_dsigmaxz_dx + value_dsigmayz_dy + value_dsigmazz_dz) + vz;
+    }
+
+    // source, :1080-1081 (after the update of step it, before Dirichlet; quirk B10)
+    if (src_ij && k == p.ksrc) {
+        vx = vx + p.src_x[p.it - 1];
+        vy = vy + p.src_y[p.it - 1];
+    }
+    // Dirichlet on the six faces, :1087-1121
+    if (edge_ij || kg == 1 || kg == p.nz) { vx = 0.0; vy = 0.0; vz = 0.0; }
+
+    if (valid) {
+        st_stream(p.vx + q, vx);
+        st_stream(p.vy + q, vy);
+        st_stream(p.vz + q, vz);
+        // boundary planes go straight into the neighbour slabs' halo planes (:811-823)
+        const long long qp = (long long)(j - 1) * p.pitch + (i - 1);
+        if (k == 1 && p.peer_lo[0]) { p.peer_lo[0][qp] = vx; p.peer_lo[1][qp] = vy; }   // -> left
+        if (k == p.nzl && p.peer_hi[0]) p.peer_hi[0][qp] = vz;                          // -> right
+    }
+
+    // energy over the PML-free box, :1131-1177; reciprocals instead of the reference's
+    // divisions -- the energy sum is reduction-order dependent anyway (quirk B11)
+    if (ebox_ij && kg >= p.npml + 1 && kg <= p.nz - p.npml) {
+        const double lam = p.lambda, mu = p.mu;
+        const double c2lm = 2.0 * (lam + mu);
+        const double inv_den = p.inv_den, inv_2mu = p.inv_2mu;
+        ekin += (0.5 * p.rho) * (vx * vx + vy * vy + vz * vz);
+        const double epsilon_xx = (c2lm * sxx_c - lam * syy_c - lam * szz_c) * inv_den;
+        const double epsilon_yy = (c2lm * syy_c - lam * sxx_c - lam * szz_c) * inv_den;
+        const double epsilon_zz = (c2lm * szz_c - lam * sxx_c - lam * syy_c) * inv_den;
+        const double epsilon_xy = sxy_c * inv_2mu;
+        const double epsilon_xz = sxz_c * inv_2mu;
+        const double epsilon_yz = syz_c * inv_2mu;
+        // quirk B2 (:1169-1172): the reference adds epsilon_yy*sigmayy twice and never
+        // epsilon_zz*sigmazz
+        const double third = p.energy_bug_compat ? epsilon_yy * syy_c : epsilon_zz * szz_c;
+        epot += 0.5 * (epsilon_xx * sxx_c + epsilon_yy * syy_c + third +
+                       2.0 * epsilon_xy * sxy_c + 2.0 * epsilon_xz * sxz_c +
+                       2.0 * epsilon_yz * syz_c);
+    }
+}
+
 template <bool KUNIT, int TX, int TY, int MINB>
 __global__ void __launch_bounds__(TX *TY, MINB)
 k_velocity3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMaps tm, const __grid_constant__ Tile3D t)
 {
     using G = TileGeom<TX, TY>;
     constexpr int W = G::W;
-    constexpr int STAGE_BYTES = 5 * G::HALO_BYTES + 4 * G::PLAIN_BYTES;
-    constexpr uint32_t TX_FULL = 5 * G::HALO_BOX_BYTES + 4 * G::PLAIN_BOX_BYTES;
-    constexpr uint32_t TX_NEXT = G::PLAIN_BOX_BYTES;              // sigmazz of plane ke+1
+    constexpr int NBYTES = G::PLAIN_BYTES;                          // ring N stage: szz
+    constexpr int CBYTES = 5 * G::HALO_BYTES + 3 * G::PLAIN_BYTES;  // ring C stage: 5 sigma (halo), vx vy vz
+    constexpr uint32_t TX_N = G::PLAIN_BOX_BYTES;
+    constexpr uint32_t TX_C = 5 * G::HALO_BOX_BYTES + 3 * G::PLAIN_BOX_BYTES;
+    constexpr int PD = G::PLAIN_BYTES / 8, HD = G::HALO_BYTES / 8;
     constexpr int NT = TX * TY;
 
     __shared__ double red[2 * ((NT + 31) / 32)];
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t sbase = (smem_u32(smem_dyn) + 127u) & ~127u;
-    unsigned char *gbase = smem_dyn + (sbase - smem_u32(smem_dyn));
-    const uint32_t bar0 = sbase;
-    const uint32_t stage0 = sbase + kBarBytes;
-    const unsigned char *gstage0 = gbase + kBarBytes;
-    const int S = t.stages;
+    const unsigned char *gbase = smem_dyn + (sbase - smem_u32(smem_dyn));
+    const uint32_t SC = (uint32_t)t.stages, SN = SC + 1;
+    const uint32_t barN = sbase, barC = sbase + 64;
+    const uint32_t ringN = sbase + kBarBytes, ringC = ringN + SN * NBYTES;
+    const unsigned char *gN = gbase + kBarBytes, *gC = gN + (size_t)SN * NBYTES;
 
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int tid = ty * TX + tx;
     if (tid == 0) {
-        for (int s = 0; s < S; s++) mbar_init(bar0 + 8 * s, 1);
+        for (uint32_t s = 0; s < SN; s++) mbar_init(barN + 8 * s, 1);
+        for (uint32_t s = 0; s < SC; s++) mbar_init(barC + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     const int pitch = p.pitch;
     const long long pl = p.plane;
-    const double odx = p.odx, ody = p.ody, odz = p.odz, dt_r = p.dt_over_rho;
-    // energy constants (:1159-1167); reciprocals instead of the reference's divisions -- the
-    // energy sum is reduction-order dependent anyway (quirk B11)
-    const double lam = p.lambda, mu = p.mu;
-    const double c2lm = 2.0 * (lam + mu);
-    const double inv_den = 1.0 / (2.0 * mu * (3.0 * lam + 2.0 * mu));
-    const double inv_2mu = 1.0 / (2.0 * mu);
-    const double half_rho = 0.5 * p.rho;
+    const int oh = ty * W + tx;
+    const int oc = ty * TX + tx;
 
-    uint32_t g = 0;
+    RingPos rn{0, 0}, rc{0, 0};
     for (int item = blockIdx.x; item < t.nitems; item += gridDim.x) {
         const int tix = item % t.ntx;
         const int rest = item / t.ntx;
@@ -383,32 +513,32 @@ k_velocity3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ Tma
         const int kb = 1 + zc * t.kchunk;
         const int ke = min(p.nzl, kb + t.kchunk - 1);
         const int np = ke - kb + 1;
+        const int x0 = i0 - 1, y0 = j0 - 1;
 
-        auto issue = [&](int l) {
-            const uint32_t gl = g + (uint32_t)l;
-            const uint32_t s = gl % (uint32_t)S;
-            const uint32_t bar = bar0 + 8 * s;
-            const uint32_t dst = stage0 + s * STAGE_BYTES;
-            const int k = kb + l;
-            const int x0 = i0 - 1, y0 = j0 - 1;
-            if (l < np) {
-                mbar_expect_tx(bar, TX_FULL);
-                tma_load_3d(dst + 0 * G::HALO_BYTES, &tm.m[0], x0 - 2, y0, k, bar);
-                tma_load_3d(dst + 1 * G::HALO_BYTES, &tm.m[1], x0, y0, k, bar);
-                tma_load_3d(dst + 2 * G::HALO_BYTES, &tm.m[2], x0, y0 - 1, k, bar);
-                tma_load_3d(dst + 3 * G::HALO_BYTES, &tm.m[3], x0, y0, k, bar);
-                tma_load_3d(dst + 4 * G::HALO_BYTES, &tm.m[4], x0, y0 - 1, k, bar);
+        auto issue_c = [&](uint32_t s, int kk) {
+            const uint32_t bar = barC + 8 * s, dst = ringC + s * CBYTES;
+            mbar_expect_tx(bar, TX_C);
+            tma_load_3d(dst + 0 * G::HALO_BYTES, &tm.m[0], x0 - 2, y0, kk, bar);
+            tma_load_3d(dst + 1 * G::HALO_BYTES, &tm.m[1], x0, y0, kk, bar);
+            tma_load_3d(dst + 2 * G::HALO_BYTES, &tm.m[2], x0, y0 - 1, kk, bar);
+            tma_load_3d(dst + 3 * G::HALO_BYTES, &tm.m[3], x0, y0, kk, bar);
+            tma_load_3d(dst + 4 * G::HALO_BYTES, &tm.m[4], x0, y0 - 1, kk, bar);
 #pragma unroll
-                for (int f = 0; f < 4; f++)
-                    tma_load_3d(dst + 5 * G::HALO_BYTES + f * G::PLAIN_BYTES, &tm.m[5 + f], x0, y0, k, bar);
-            } else {
-                mbar_expect_tx(bar, TX_NEXT);
-                tma_load_3d(dst + 5 * G::HALO_BYTES, &tm.m[5], x0, y0, k, bar);
-            }
+            for (int f = 0; f < 3; f++)
+                tma_load_3d(dst + 5 * G::HALO_BYTES + f * G::PLAIN_BYTES, &tm.m[6 + f], x0, y0, kk, bar);
         };
         if (tid == 0) {
-            const int npro = min(S, np + 1);
-            for (int l = 0; l < npro; l++) issue(l);
+            uint32_t s = rn.s;
+            for (int l = 0; l < min((int)SN, np + 1); l++) {
+                mbar_expect_tx(barN + 8 * s, TX_N);
+                tma_load_3d(ringN + s * NBYTES, &tm.m[5], x0, y0, kb + l, barN + 8 * s);
+                if (++s == SN) s = 0;
+            }
+            s = rc.s;
+            for (int l = 0; l < min((int)SC, np); l++) {
+                issue_c(s, kb + l);
+                if (++s == SC) s = 0;
+            }
         }
 
         const int i = i0 + tx, j = j0 + ty;
@@ -417,9 +547,7 @@ k_velocity3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ Tma
 
         const bool in_x = valid && ((i <= p.xlo) || (i >= p.xhi));
         const bool in_y = valid && ((j <= p.ylo) || (j >= p.yhi));
-        const int sx = in_x ? shell_index(i, p.xlo, p.xhi) : 0;
-        const int sy = in_y ? shell_index(j, p.ylo, p.yhi) : 0;
-
+        const bool warp_pml = __any_sync(0xffffffffu, in_x || in_y);
         const bool do_vx = valid && (i >= 2) && (j >= 2);                    // :978-979
         const bool do_vy = valid && (i <= p.nx - 1) && (j <= p.ny - 1);      // :998-999
         const bool do_vz = valid && (i <= p.nx - 1) && (j >= 2);             // :1033-1034
@@ -428,137 +556,75 @@ k_velocity3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ Tma
                              (j >= p.npml + 1) && (j <= p.ny - p.npml);            // :1144-1145
         const bool src_ij = (i == p.isrc) && (j == p.jsrc);
 
-        double ax = 0, bxc = 0, Kx = 1, axh = 0, bxh = 0, Kxh = 1, ay = 0, by = 0, Ky = 1, ayh = 0, byh = 0, Kyh = 1;
-        if (in_x) { ax = p.cx.a[i]; bxc = p.cx.b[i]; axh = p.cx.a_half[i]; bxh = p.cx.b_half[i];
-                    if (!KUNIT) { Kx = p.cx.K[i]; Kxh = p.cx.K_half[i]; } }
-        if (in_y) { ay = p.cy.a[j]; by = p.cy.b[j]; ayh = p.cy.a_half[j]; byh = p.cy.b_half[j];
-                    if (!KUNIT) { Ky = p.cy.K[j]; Kyh = p.cy.K_half[j]; } }
-
-        long long qx = in_x ? ((long long)(kb - 1) * p.ny + (j - 1)) * p.sxp + sx : 0;
-        long long qy = in_y ? ((long long)(kb - 1) * p.sy + sy) * pitch + (i - 1) : 0;
+        long long qx = 0, qy = 0;
+        if (in_x) qx = ((long long)(kb - 1) * p.ny + (j - 1)) * p.sxp + shell_index(i, p.xlo, p.xhi);
+        if (in_y) qy = ((long long)(kb - 1) * p.sy + shell_index(j, p.ylo, p.yhi)) * pitch + (i - 1);
         const long long qx_step = (long long)p.ny * p.sxp, qy_step = (long long)p.sy * pitch;
-        double m_x3 = 0, m_x4 = 0, m_x5 = 0, m_y3 = 0, m_y4 = 0, m_y5 = 0;
-        if (in_x) { m_x3 = p.mx[3][qx]; m_x4 = p.mx[4][qx]; m_x5 = p.mx[5][qx]; }
-        if (in_y) { m_y3 = p.my[3][qy]; m_y4 = p.my[4][qy]; m_y5 = p.my[5][qy]; }
 
         double sxz_m = valid ? p.sxz[q - pl] : 0.0, syz_m = valid ? p.syz[q - pl] : 0.0;   // plane kb-1
         double ekin = 0.0, epot = 0.0;
 
+        mbar_wait(barN + 8 * rn.s, rn.par);
         for (int n = 0; n < np; ++n, q += pl, qx += qx_step, qy += qy_step) {
             const int k = kb + n;
             const int kg = k + p.koff;
-            const uint32_t gc = g + (uint32_t)n, gn = gc + 1;
-            const uint32_t sc = gc % (uint32_t)S, sn = gn % (uint32_t)S;
-
-            double n_x3 = 0, n_x4 = 0, n_x5 = 0, n_y3 = 0, n_y4 = 0, n_y5 = 0;
-            if (n + 1 < np) {
-                if (in_x) { n_x3 = p.mx[3][qx + qx_step]; n_x4 = p.mx[4][qx + qx_step]; n_x5 = p.mx[5][qx + qx_step]; }
-                if (in_y) { n_y3 = p.my[3][qy + qy_step]; n_y4 = p.my[4][qy + qy_step]; n_y5 = p.my[5][qy + qy_step]; }
-            }
-            const bool in_z = valid && ((kg <= p.zlo) || (kg >= p.zhi));
+            // C-PML memory variables of this plane: every load is issued before the waits (and
+            // before any store of the recursion, which the compiler must assume to alias)
+            const bool z_pml = (kg <= p.zlo) || (kg >= p.zhi);      // uniform
+            const bool pml = warp_pml || z_pml;                     // warp-uniform
+            const bool in_z = valid && z_pml;
             long long qz = 0;
-            double m_z3 = 0, m_z4 = 0, m_z5 = 0, az = 0, bz = 0, Kz = 1, azh = 0, bzh = 0, Kzh = 1;
-            if (in_z) {
-                qz = ((long long)(shell_index(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1);
-                m_z3 = p.mz[3][qz]; m_z4 = p.mz[4][qz]; m_z5 = p.mz[5][qz];
-                az = p.cz.a[kg]; bz = p.cz.b[kg]; azh = p.cz.a_half[kg]; bzh = p.cz.b_half[kg];
-                if (!KUNIT) { Kz = p.cz.K[kg]; Kzh = p.cz.K_half[kg]; }
-            }
-
-            if (n == 0) mbar_wait(bar0 + 8 * sc, (gc / (uint32_t)S) & 1u);
-            mbar_wait(bar0 + 8 * sn, (gn / (uint32_t)S) & 1u);
-
-            const unsigned char *st = gstage0 + (size_t)sc * STAGE_BYTES;
-            const unsigned char *stn = gstage0 + (size_t)sn * STAGE_BYTES;
-            const double *Txx = (const double *)(st + 0 * G::HALO_BYTES);
-            const double *Tyy = (const double *)(st + 1 * G::HALO_BYTES);
-            const double *Txy = (const double *)(st + 2 * G::HALO_BYTES);
-            const double *Txz = (const double *)(st + 3 * G::HALO_BYTES);
-            const double *Tyz = (const double *)(st + 4 * G::HALO_BYTES);
-            const double *Tp = (const double *)(st + 5 * G::HALO_BYTES);
-            constexpr int PD = G::PLAIN_BYTES / 8;
-            const int c = ty * TX + tx;
-
-            const double sxx_c = Txx[ty * W + tx + 2], sxx_im = Txx[ty * W + tx + 1];
-            const double syy_c = Tyy[ty * W + tx], syy_jp = Tyy[(ty + 1) * W + tx];
-            const double sxy_c = Txy[(ty + 1) * W + tx], sxy_jm = Txy[ty * W + tx], sxy_ip = Txy[(ty + 1) * W + tx + 1];
-            const double sxz_c = Txz[ty * W + tx], sxz_ip = Txz[ty * W + tx + 1];
-            const double syz_c = Tyz[(ty + 1) * W + tx], syz_jm = Tyz[ty * W + tx];
-            const double szz_c = Tp[0 * PD + c];
-            const double szz_n = ((const double *)(stn + 5 * G::HALO_BYTES))[c];
-            double vx = Tp[1 * PD + c], vy = Tp[2 * PD + c], vz = Tp[3 * PD + c];
-
-            if (kg >= 2) {                                           // k2begin
-                if (do_vx) {                                         // :976-996
-                    double value_dsigmaxx_dx = (sxx_c - sxx_im) * odx;
-                    double value_dsigmaxy_dy = (sxy_c - sxy_jm) * ody;
-                    double value_dsigmaxz_dz = (sxz_c - sxz_m) * odz;
-                    if (in_x) value_dsigmaxx_dx = cpml_apply<KUNIT>(p.mx[3], qx, m_x3, bxc, ax, Kx, value_dsigmaxx_dx);
-                    if (in_y) value_dsigmaxy_dy = cpml_apply<KUNIT>(p.my[3], qy, m_y3, by, ay, Ky, value_dsigmaxy_dy);
-                    if (in_z) value_dsigmaxz_dz = cpml_apply<KUNIT>(p.mz[3], qz, m_z3, bz, az, Kz, value_dsigmaxz_dz);
-                    vx = dt_r * (value_dsigmaxx_dx + value_dsigmaxy_dy + value_dsigmaxz_dz) + vx;
-                }
-                if (do_vy) {                                         // :998-1016
-                    double value_dsigmaxy_dx = (sxy_ip - sxy_c) * odx;
-                    double value_dsigmayy_dy = (syy_jp - syy_c) * ody;
-                    double value_dsigmayz_dz = (syz_c - syz_m) * odz;
-                    if (in_x) value_dsigmaxy_dx = cpml_apply<KUNIT>(p.mx[4], qx, m_x4, bxh, axh, Kxh, value_dsigmaxy_dx);
-                    if (in_y) value_dsigmayy_dy = cpml_apply<KUNIT>(p.my[4], qy, m_y4, byh, ayh, Kyh, value_dsigmayy_dy);
-                    if (in_z) value_dsigmayz_dz = cpml_apply<KUNIT>(p.mz[4], qz, m_z4, bz, az, Kz, value_dsigmayz_dz);
-                    vy = dt_r * (value_dsigmaxy_dx + value_dsigmayy_dy + value_dsigmayz_dz) + vy;
+            double mv[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            if (pml) {
+                if (in_x) { mv[0] = p.mx[3 + 0][qx]; mv[1] = p.mx[3 + 1][qx]; mv[2] = p.mx[3 + 2][qx]; }
+                if (in_y) { mv[3] = p.my[3 + 0][qy]; mv[4] = p.my[3 + 1][qy]; mv[5] = p.my[3 + 2][qy]; }
+                if (in_z) {
+                    qz = ((long long)(shell_index(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1);
+                    mv[6] = p.mz[3 + 0][qz]; mv[7] = p.mz[3 + 1][qz]; mv[8] = p.mz[3 + 2][qz];
                 }
             }
-            if (do_vz && kg <= p.nz - 1) {                           // kminus1end, :1031-1052
-                double value_dsigmaxz_dx = (sxz_ip - sxz_c) * odx;
-                double value_dsigmayz_dy = (syz_c - syz_jm) * ody;
-                double value_dsigmazz_dz = (szz_n - szz_c) * odz;
-                if (in_x) value_dsigmaxz_dx = cpml_apply<KUNIT>(p.mx[5], qx, m_x5, bxh, axh, Kxh, value_dsigmaxz_dx);
-                if (in_y) value_dsigmayz_dy = cpml_apply<KUNIT>(p.my[5], qy, m_y5, by, ay, Ky, value_dsigmayz_dy);
-                if (in_z) value_dsigmazz_dz = cpml_apply<KUNIT>(p.mz[5], qz, m_z5, bzh, azh, Kzh, value_dsigmazz_dz);
-                vz = dt_r * (value_dsigmaxz_dx + value_dsigmayz_dy + value_dsigmazz_dz) + vz;
-            }
+            RingPos rn1 = rn;
+            rn1.advance(SN);
+            mbar_wait(barN + 8 * rn1.s, rn1.par);
+            mbar_wait(barC + 8 * rc.s, rc.par);
 
-            // source, :1080-1081 (after the update of step it, before Dirichlet; quirk B10)
-            if (src_ij && k == p.ksrc) {
-                vx = vx + p.src_x[p.it - 1];
-                vy = vy + p.src_y[p.it - 1];
-            }
-            // Dirichlet on the six faces, :1087-1121
-            if (edge_ij || kg == 1 || kg == p.nz) { vx = 0.0; vy = 0.0; vz = 0.0; }
+            const double *Tc = (const double *)(gC + (size_t)rc.s * CBYTES);
+            const double *Txx = Tc, *Tyy = Tc + HD, *Txy = Tc + 2 * HD, *Txz = Tc + 3 * HD, *Tyz = Tc + 4 * HD;
+            const double *Tp = Tc + 5 * HD;
 
-            if (valid) {
-                st_stream(p.vx + q, vx);
-                st_stream(p.vy + q, vy);
-                st_stream(p.vz + q, vz);
-                // boundary planes go straight into the neighbour slabs' halo planes (:811-823)
-                const long long qp = (long long)(j - 1) * pitch + (i - 1);
-                if (k == 1 && p.peer_lo[0]) { p.peer_lo[0][qp] = vx; p.peer_lo[1][qp] = vy; }   // -> left
-                if (k == p.nzl && p.peer_hi[0]) p.peer_hi[0][qp] = vz;                          // -> right
-            }
+            const double sxx_c = Txx[oh + 2], sxx_im = Txx[oh + 1];
+            const double syy_c = Tyy[oh], syy_jp = Tyy[oh + W];
+            const double sxy_c = Txy[oh + W], sxy_jm = Txy[oh], sxy_ip = Txy[oh + W + 1];
+            const double sxz_c = Txz[oh], sxz_ip = Txz[oh + 1];
+            const double syz_c = Tyz[oh + W], syz_jm = Tyz[oh];
+            const double szz_c = ((const double *)(gN + (size_t)rn.s * NBYTES))[oc];
+            const double szz_n = ((const double *)(gN + (size_t)rn1.s * NBYTES))[oc];
+            const double vx = Tp[0 * PD + oc], vy = Tp[1 * PD + oc], vz = Tp[2 * PD + oc];
 
-            // energy over the PML-free box, :1131-1177
-            if (ebox_ij && kg >= p.npml + 1 && kg <= p.nz - p.npml) {
-                ekin += half_rho * (vx * vx + vy * vy + vz * vz);
-                const double epsilon_xx = (c2lm * sxx_c - lam * syy_c - lam * szz_c) * inv_den;
-                const double epsilon_yy = (c2lm * syy_c - lam * sxx_c - lam * szz_c) * inv_den;
-                const double epsilon_zz = (c2lm * szz_c - lam * sxx_c - lam * syy_c) * inv_den;
-                const double epsilon_xy = sxy_c * inv_2mu;
-                const double epsilon_xz = sxz_c * inv_2mu;
-                const double epsilon_yz = syz_c * inv_2mu;
-                // quirk B2 (:1169-1172): the reference adds epsilon_yy*sigmayy twice and never
-                // epsilon_zz*sigmazz
-                const double third = p.energy_bug_compat ? epsilon_yy * syy_c : epsilon_zz * szz_c;
-                epot += 0.5 * (epsilon_xx * sxx_c + epsilon_yy * syy_c + third +
-                               2.0 * epsilon_xy * sxy_c + 2.0 * epsilon_xz * sxz_c +
-                               2.0 * epsilon_yz * syz_c);
+            if (pml) {
+                velocity_point<true, KUNIT>(p, q, i, j, k, kg, valid, do_vx, do_vy, do_vz, edge_ij, ebox_ij, src_ij, in_x, in_y, in_z,
+                                            qx, qy, qz, mv, sxx_c, sxx_im, syy_c, syy_jp, sxy_c, sxy_jm, sxy_ip, sxz_c, sxz_ip, sxz_m,
+                                            syz_c, syz_jm, syz_m, szz_c, szz_n, vx, vy, vz, ekin, epot);
+            } else {
+                velocity_point<false, KUNIT>(p, q, i, j, k, kg, valid, do_vx, do_vy, do_vz, edge_ij, ebox_ij, src_ij, false, false, false,
+                                             0, 0, 0, mv, sxx_c, sxx_im, syy_c, syy_jp, sxy_c, sxy_jm, sxy_ip, sxz_c, sxz_ip, sxz_m,
+                                             syz_c, syz_jm, syz_m, szz_c, szz_n, vx, vy, vz, ekin, epot);
             }
             sxz_m = sxz_c; syz_m = syz_c;
-            m_x3 = n_x3; m_x4 = n_x4; m_x5 = n_x5; m_y3 = n_y3; m_y4 = n_y4; m_y5 = n_y5;
 
             __syncthreads();
-            if (tid == 0 && n + S <= np) issue(n + S);
+            if (tid == 0) {
+                if (n + (int)SN <= np) {
+                    const uint32_t s = rn.s, bar = barN + 8 * s;
+                    mbar_expect_tx(bar, TX_N);
+                    tma_load_3d(ringN + s * NBYTES, &tm.m[5], x0, y0, kb + n + (int)SN, bar);
+                }
+                if (n + (int)SC < np) issue_c(rc.s, kb + n + (int)SC);
+            }
+            rn = rn1;
+            rc.advance(SC);
         }
-        g += (uint32_t)(np + 1);
+        rn.advance(SN);
 
         block_sum2<NT>(ekin, epot, red);
         if (tid == 0) {
@@ -574,8 +640,10 @@ template <int TX, int TY>
 static size_t smem_need(bool stress, int stages)
 {
     using G = TileGeom<TX, TY>;
-    const size_t stage = stress ? 3 * G::HALO_BYTES + 6 * G::PLAIN_BYTES : 5 * G::HALO_BYTES + 4 * G::PLAIN_BYTES;
-    return kBarBytes + 128 + stage * (size_t)stages;
+    // ring C holds `stages` planes, ring N one more (kernels above)
+    const size_t c = stress ? G::HALO_BYTES + 6 * G::PLAIN_BYTES : 5 * G::HALO_BYTES + 3 * G::PLAIN_BYTES;
+    const size_t n = stress ? 2 * G::HALO_BYTES : G::PLAIN_BYTES;
+    return kBarBytes + 128 + c * (size_t)stages + n * (size_t)(stages + 1);
 }
 
 template <bool KUNIT, int TX, int TY, int MINB>
