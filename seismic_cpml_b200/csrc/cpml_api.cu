@@ -495,11 +495,12 @@ static int32_t setup_tma(cpml_handle *h)
     // thread tile = TMA box.  Narrow grids (the reference's NX = 101) take one 104-wide tile
     // per row; wide grids 64 x 8.  CPML_TX / CPML_TY / CPML_STAGES override (bench sweeps).
     Tile3D &t = h->tile;
-    t.tx = env_int("CPML_TX", c.nx <= 104 ? 104 : 64);
-    t.ty = env_int("CPML_TY", c.nx <= 104 ? 4 : 8);
+    t.tx = env_int("CPML_TX", c.nx <= 104 ? 104 : 128);
+    t.ty = env_int("CPML_TY", c.nx <= 104 ? 8 : 4);
     if (!tma_tile_supported(t.tx, t.ty)) FAIL(CPML_EINVAL, "unsupported CPML_TX x CPML_TY tile");
     t.stages = std::max(1, std::min(7, env_int("CPML_STAGES", 2)));
-    t.minb = std::max(1, std::min(3, env_int("CPML_MINB", 1)));
+    t.minb = std::max(1, std::min(4, env_int("CPML_MINB", 1)));
+    t.xm_bytes = h->shell[0].size() > 0 ? round_up(t.ty * h->sxp * 8, 128) : 0;
     t.ntx = (c.nx + t.tx - 1) / t.tx;
     t.nty = (c.ny + t.ty - 1) / t.ty;
 
@@ -575,7 +576,7 @@ static int32_t finalize(cpml_handle *h)
     h->sxp = std::max(4, round_up(sx.size(), 4));
     h->sy = std::max(1, sy.size());
     const int nmem = c.ndim == 3 ? 6 : 4;
-    h->mx_doubles = (size_t)h->sxp * c.ny * h->nzl;
+    h->mx_doubles = (size_t)h->sxp * c.ny * h->nzl + (size_t)h->sxp * 16;   // + slack: bulk copies of a ragged last y tile
     h->my_doubles = (size_t)h->pitch * h->sy * h->nzl;
     for (int m = 0; m < nmem; m++) {
         CK(cudaMalloc(&h->mx[m], h->mx_doubles * sizeof(double)));

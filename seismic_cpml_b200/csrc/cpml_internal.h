@@ -86,6 +86,7 @@ struct Tile3D {
     int nitems;               // ntx * nty * nzc (= energy partial slots)
     int stages;               // shared-memory ring depth (planes)
     int minb;                 // resident CTAs per SM the kernel variant is compiled for
+    int xm_bytes;             // per stage and variable: x-shell memory variables of the tile rows (0: no x shell)
     int grid_stress, grid_velocity;
 };
 

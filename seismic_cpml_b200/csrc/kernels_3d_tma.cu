@@ -86,6 +86,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
                  ::"r"(dst), "l"((unsigned long long)map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
 }
 
+// 1-D bulk copy (TMA engine, no descriptor): contiguous, 16-byte aligned, size % 16 == 0
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 __device__ __forceinline__ void st_stream(double *p, double v) { __stcs(p, v); }
 
 // memory_x = b * memory_x + a * value ; value = value / K + memory_x   (e.g. :845-851)
@@ -139,21 +146,25 @@ struct RingPos {
 // ring N (planes n and n+1 are needed):  vx (halo box at (0,0)), vy (halo, (-2,-1))
 // ring C (plane n only):                 vz (halo, (-2,0)), sxx syy szz sxy sxz syz (plain boxes)
 // maps: 0 vx 1 vy 2 vz 3..8 sigma
+//
+// One thread updates TWO x-adjacent points (16-byte shared-memory loads and global stores,
+// half the address / predicate / barrier instructions per point, two independent dependency
+// chains): with one point per thread the kernels were bound by instruction latency, not by
+// HBM (profiles/r01_v4_*).  The point update itself is written once, per point.
+struct StressVals { double sxx, syy, szz, sxy, sxz, syz; };   // in: old values, out: new values
+
 template <bool PML, bool KUNIT>
 __device__ __forceinline__ void stress_point(
-    const Params3D &p, const long long q, const int i, const int j, const int k, const int kg,
-    const bool valid, const bool do_n, const bool do_xy, const bool do_xz, const bool do_yz,
+    const Params3D &p, const int i, const int j, const int kg,
+    const bool do_n, const bool do_xy, const bool do_xz, const bool do_yz,
     const bool in_x, const bool in_y, const bool in_z, const long long qx, const long long qy, const long long qz,
     const double (&mv)[9],
     const double vx_c, const double vx_ip, const double vx_jp, const double vx_n,
     const double vy_c, const double vy_im, const double vy_jm, const double vy_n,
-    const double vz_c, const double vz_im, const double vz_jp, const double vz_m,
-    const double sxx, const double syy, const double szz, const double sxy, const double sxz, const double syz)
+    const double vz_c, const double vz_im, const double vz_jp, const double vz_m, StressVals &s)
 {
     const double odx = p.odx, ody = p.ody, odz = p.odz;
     const double dt_l = p.dt_lambda, dt_m = p.dt_mu, dt_l2m = p.dt_lambdaplus2mu;
-    double szz_out = szz, sxz_out = sxz, syz_out = syz;
-
     // ---- sigmaxx, sigmayy, sigmazz  (:836-863)
     if (do_n && kg >= 2) {                                  // k2begin, :792-793
         double value_dvx_dx = (vx_ip - vx_c) * odx;
@@ -164,10 +175,9 @@ __device__ __forceinline__ void stress_point(
             if (in_y) value_dvy_dy = cpml_apply<KUNIT>(p.my[0], qy, mv[3], p.cy.b[j], p.cy.a[j], KUNIT ? 1.0 : p.cy.K[j], value_dvy_dy);
             if (in_z) value_dvz_dz = cpml_apply<KUNIT>(p.mz[0], qz, mv[6], p.cz.b[kg], p.cz.a[kg], KUNIT ? 1.0 : p.cz.K[kg], value_dvz_dz);
         }
-        st_stream(p.sxx + q, dt_l2m * value_dvx_dx + dt_l * (value_dvy_dy + value_dvz_dz) + sxx);
-        st_stream(p.syy + q, dt_l * (value_dvx_dx + value_dvz_dz) + dt_l2m * value_dvy_dy + syy);
-        szz_out = dt_l * (value_dvx_dx + value_dvy_dy) + dt_l2m * value_dvz_dz + szz;
-        st_stream(p.szz + q, szz_out);
+        s.sxx = dt_l2m * value_dvx_dx + dt_l * (value_dvy_dy + value_dvz_dz) + s.sxx;
+        s.syy = dt_l * (value_dvx_dx + value_dvz_dz) + dt_l2m * value_dvy_dy + s.syy;
+        s.szz = dt_l * (value_dvx_dx + value_dvy_dy) + dt_l2m * value_dvz_dz + s.szz;
     }
     // ---- sigmaxy  (:877-894)
     if (do_xy) {
@@ -177,7 +187,7 @@ __device__ __forceinline__ void stress_point(
             if (in_x) value_dvy_dx = cpml_apply<KUNIT>(p.mx[1], qx, mv[1], p.cx.b[i], p.cx.a[i], KUNIT ? 1.0 : p.cx.K[i], value_dvy_dx);
             if (in_y) value_dvx_dy = cpml_apply<KUNIT>(p.my[1], qy, mv[4], p.cy.b_half[j], p.cy.a_half[j], KUNIT ? 1.0 : p.cy.K_half[j], value_dvx_dy);
         }
-        st_stream(p.sxy + q, dt_m * (value_dvy_dx + value_dvx_dy) + sxy);
+        s.sxy = dt_m * (value_dvy_dx + value_dvx_dy) + s.sxy;
     }
     // ---- sigmaxz, sigmayz  (:908-943)
     if (kg <= p.nz - 1) {                                   // kminus1end, :795-796
@@ -188,8 +198,7 @@ __device__ __forceinline__ void stress_point(
                 if (in_x) value_dvz_dx = cpml_apply<KUNIT>(p.mx[2], qx, mv[2], p.cx.b[i], p.cx.a[i], KUNIT ? 1.0 : p.cx.K[i], value_dvz_dx);
                 if (in_z) value_dvx_dz = cpml_apply<KUNIT>(p.mz[1], qz, mv[7], p.cz.b_half[kg], p.cz.a_half[kg], KUNIT ? 1.0 : p.cz.K_half[kg], value_dvx_dz);
             }
-            sxz_out = dt_m * (value_dvz_dx + value_dvx_dz) + sxz;
-            st_stream(p.sxz + q, sxz_out);
+            s.sxz = dt_m * (value_dvz_dx + value_dvx_dz) + s.sxz;
         }
         if (do_yz) {
             double value_dvz_dy = (vz_jp - vz_c) * ody;
@@ -198,20 +207,25 @@ __device__ __forceinline__ void stress_point(
                 if (in_y) value_dvz_dy = cpml_apply<KUNIT>(p.my[2], qy, mv[5], p.cy.b_half[j], p.cy.a_half[j], KUNIT ? 1.0 : p.cy.K_half[j], value_dvz_dy);
                 if (in_z) value_dvy_dz = cpml_apply<KUNIT>(p.mz[2], qz, mv[8], p.cz.b_half[kg], p.cz.a_half[kg], KUNIT ? 1.0 : p.cz.K_half[kg], value_dvy_dz);
             }
-            syz_out = dt_m * (value_dvz_dy + value_dvy_dz) + syz;
-            st_stream(p.syz + q, syz_out);
+            s.syz = dt_m * (value_dvz_dy + value_dvy_dz) + s.syz;
         }
-    }
-    // ---- boundary planes go straight into the neighbour slabs' halo planes (:951-963)
-    if (valid) {
-        const long long qp = (long long)(j - 1) * p.pitch + (i - 1);
-        if (k == 1 && p.peer_lo[2]) p.peer_lo[2][qp] = szz_out;                                      // sigmazz(:,:,1) -> left
-        if (k == p.nzl && p.peer_hi[1]) { p.peer_hi[1][qp] = sxz_out; p.peer_hi[2][qp] = syz_out; }   // -> right
     }
 }
 
+__device__ __forceinline__ double2 lds2(const double *t, int e) { return *reinterpret_cast<const double2 *>(t + e); }
+__device__ __forceinline__ void st_stream2(double *p, double a, double b) { __stcs(reinterpret_cast<double2 *>(p), make_double2(a, b)); }
+
+// Loads the nine C-PML memory variables of one point (group g0 = 0: stress kernel, 3: velocity).
+__device__ __forceinline__ void load_memvars(const Params3D &p, int g0, bool in_x, bool in_y, bool in_z,
+                                             long long qx, long long qy, long long qz, double (&mv)[9])
+{
+    if (in_x) { mv[0] = p.mx[g0 + 0][qx]; mv[1] = p.mx[g0 + 1][qx]; mv[2] = p.mx[g0 + 2][qx]; }
+    if (in_y) { mv[3] = p.my[g0 + 0][qy]; mv[4] = p.my[g0 + 1][qy]; mv[5] = p.my[g0 + 2][qy]; }
+    if (in_z) { mv[6] = p.mz[g0 + 0][qz]; mv[7] = p.mz[g0 + 1][qz]; mv[8] = p.mz[g0 + 2][qz]; }
+}
+
 template <bool KUNIT, int TX, int TY, int MINB>
-__global__ void __launch_bounds__(TX *TY, MINB)
+__global__ void __launch_bounds__(TX / 2 * TY, MINB)
 k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMaps tm, const __grid_constant__ Tile3D t)
 {
     using G = TileGeom<TX, TY>;
@@ -221,6 +235,10 @@ k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMa
     constexpr uint32_t TX_N = 2 * G::HALO_BOX_BYTES;
     constexpr uint32_t TX_C = G::HALO_BOX_BYTES + 6 * G::PLAIN_BOX_BYTES;
     constexpr int PD = G::PLAIN_BYTES / 8;
+    // the x-shell memory variables of the tile's rows ride in ring C too: rows of sxp doubles,
+    // contiguous over j, one bulk copy per variable (t.xm_bytes each, 0 without an x shell)
+    const uint32_t XMB = (uint32_t)t.xm_bytes, XM_TX = (uint32_t)(TY * p.sxp * 8);
+    const uint32_t CSTAGE = CBYTES + 3 * XMB;
 
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t sbase = (smem_u32(smem_dyn) + 127u) & ~127u;
@@ -231,7 +249,7 @@ k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMa
     const unsigned char *gN = gbase + kBarBytes, *gC = gN + (size_t)SN * NBYTES;
 
     const int tx = threadIdx.x, ty = threadIdx.y;
-    const int tid = ty * TX + tx;
+    const int tid = ty * (TX / 2) + tx;
     if (tid == 0) {
         for (uint32_t s = 0; s < SN; s++) mbar_init(barN + 8 * s, 1);
         for (uint32_t s = 0; s < SC; s++) mbar_init(barC + 8 * s, 1);
@@ -241,9 +259,8 @@ k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMa
 
     const int pitch = p.pitch;
     const long long pl = p.plane;
-    // per-thread element offsets inside the tiles
-    const int oh = ty * W + tx;          // halo tile, box origin (0,0): centre
-    const int oc = ty * TX + tx;         // plain tile
+    const int oh = ty * W + 2 * tx;      // halo tile, box origin (0,0): first point of the pair
+    const int oc = ty * TX + 2 * tx;     // plain tile
 
     RingPos rn{0, 0}, rc{0, 0};          // stage of the current plane in each ring
     for (int item = blockIdx.x; item < t.nitems; item += gridDim.x) {
@@ -257,6 +274,21 @@ k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMa
         const int np = ke - kb + 1;
         const int x0 = i0 - 1, y0 = j0 - 1;
 
+        // does the tile touch the x shell?  (uniform)
+        const bool tile_xpml = XMB != 0 && ((i0 <= p.xlo) || (i0 + TX - 1 >= p.xhi));
+        auto issue_c = [&](uint32_t s, int kk) {
+            const uint32_t bar = barC + 8 * s, dst = ringC + s * CSTAGE;
+            mbar_expect_tx(bar, TX_C + (tile_xpml ? 3 * XM_TX : 0u));
+            tma_load_3d(dst, &tm.m[2], x0 - 2, y0, kk, bar);
+#pragma unroll
+            for (int f = 0; f < 6; f++)
+                tma_load_3d(dst + G::HALO_BYTES + f * G::PLAIN_BYTES, &tm.m[3 + f], x0, y0, kk, bar);
+            if (tile_xpml) {
+                const long long row0 = ((long long)(kk - 1) * p.ny + (j0 - 1)) * p.sxp;
+#pragma unroll
+                for (int f = 0; f < 3; f++) bulk_load(dst + CBYTES + f * XMB, p.mx[f] + row0, XM_TX, bar);
+            }
+        };
         // ring N load l = plane kb+l (l = 0..np: the last one only feeds the z differences of
         // plane ke); ring C load l = plane kb+l (l = 0..np-1)
         if (tid == 0) {
@@ -269,54 +301,50 @@ k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMa
             }
             s = rc.s;
             for (int l = 0; l < min((int)SC, np); l++) {
-                const uint32_t dst = ringC + s * CBYTES;
-                mbar_expect_tx(barC + 8 * s, TX_C);
-                tma_load_3d(dst, &tm.m[2], x0 - 2, y0, kb + l, barC + 8 * s);
-#pragma unroll
-                for (int f = 0; f < 6; f++)
-                    tma_load_3d(dst + G::HALO_BYTES + f * G::PLAIN_BYTES, &tm.m[3 + f], x0, y0, kb + l, barC + 8 * s);
+                issue_c(s, kb + l);
                 if (++s == SC) s = 0;
             }
         }
 
-        const int i = i0 + tx, j = j0 + ty;
-        const bool valid = (i <= p.nx) && (j <= p.ny);
+        // the pair: points A = (i, j) and B = (i+1, j); i-1 is even, so B shares A's 16 bytes
+        const int i = i0 + 2 * tx, j = j0 + ty;
+        const bool row = (j <= p.ny);
+        const bool validA = row && (i <= p.nx), validB = row && (i + 1 <= p.nx);
         long long q = (long long)kb * pl + (long long)(j - 1) * pitch + (i - 1);
 
-        const bool in_x = valid && ((i <= p.xlo) || (i >= p.xhi));
-        const bool in_y = valid && ((j <= p.ylo) || (j >= p.yhi));
-        const bool warp_pml = __any_sync(0xffffffffu, in_x || in_y);
+        const bool in_xA = validA && ((i <= p.xlo) || (i >= p.xhi));
+        const bool in_xB = validB && ((i + 1 <= p.xlo) || (i + 1 >= p.xhi));
+        const bool in_y = validA && ((j <= p.ylo) || (j >= p.yhi));
+        const bool warp_pml = __any_sync(0xffffffffu, in_xA || in_xB || in_y);
         // loop bounds of the four nests (i, j part; the k part is tested per plane)
-        const bool do_n = valid && (i <= p.nx - 1) && (j >= 2);     // :838-839
-        const bool do_xy = valid && (i >= 2) && (j <= p.ny - 1);    // :878-879
-        const bool do_xz = valid && (i >= 2);                       // :910-911
-        const bool do_yz = valid && (j <= p.ny - 1);                // :927-928
+        const bool do_nA = validA && (i <= p.nx - 1) && (j >= 2), do_nB = validB && (i + 1 <= p.nx - 1) && (j >= 2);   // :838-839
+        const bool do_xyA = validA && (i >= 2) && (j <= p.ny - 1), do_xyB = validB && (j <= p.ny - 1);                 // :878-879
+        const bool do_xzA = validA && (i >= 2), do_xzB = validB;                                                       // :910-911
+        const bool do_yzA = validA && (j <= p.ny - 1), do_yzB = validB && (j <= p.ny - 1);                             // :927-928
 
-        long long qx = 0, qy = 0;
-        if (in_x) qx = ((long long)(kb - 1) * p.ny + (j - 1)) * p.sxp + shell_index(i, p.xlo, p.xhi);
-        if (in_y) qy = ((long long)(kb - 1) * p.sy + shell_index(j, p.ylo, p.yhi)) * pitch + (i - 1);
+        const int sxA = in_xA ? shell_index(i, p.xlo, p.xhi) : 0, sxB = in_xB ? shell_index(i + 1, p.xlo, p.xhi) : 0;
+        long long qxr = ((long long)(kb - 1) * p.ny + (j - 1)) * p.sxp;                         // x-shell row of this (j, k)
+        long long qy = in_y ? ((long long)(kb - 1) * p.sy + shell_index(j, p.ylo, p.yhi)) * pitch + (i - 1) : 0;
         const long long qx_step = (long long)p.ny * p.sxp, qy_step = (long long)p.sy * pitch;
 
-        double vz_m = valid ? p.vz[q - pl] : 0.0;                   // plane kb-1, carried along z
+        double vz_mA = 0.0, vz_mB = 0.0;                            // plane kb-1, carried along z
+        if (validA) { const double2 t2 = *reinterpret_cast<const double2 *>(p.vz + q - pl); vz_mA = t2.x; vz_mB = t2.y; }
 
         mbar_wait(barN + 8 * rn.s, rn.par);
-        for (int n = 0; n < np; ++n, q += pl, qx += qx_step, qy += qy_step) {
+        for (int n = 0; n < np; ++n, q += pl, qxr += qx_step, qy += qy_step) {
             const int k = kb + n;
             const int kg = k + p.koff;                              // :837
             // C-PML memory variables of this plane: every load is issued before the waits (and
             // before any store of the recursion, which the compiler must assume to alias)
             const bool z_pml = (kg <= p.zlo) || (kg >= p.zhi);      // uniform
             const bool pml = warp_pml || z_pml;                     // warp-uniform
-            const bool in_z = valid && z_pml;
+            const bool in_zA = validA && z_pml, in_zB = validB && z_pml;
             long long qz = 0;
-            double mv[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            double mvA[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, mvB[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
             if (pml) {
-                if (in_x) { mv[0] = p.mx[0 + 0][qx]; mv[1] = p.mx[0 + 1][qx]; mv[2] = p.mx[0 + 2][qx]; }
-                if (in_y) { mv[3] = p.my[0 + 0][qy]; mv[4] = p.my[0 + 1][qy]; mv[5] = p.my[0 + 2][qy]; }
-                if (in_z) {
-                    qz = ((long long)(shell_index(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1);
-                    mv[6] = p.mz[0 + 0][qz]; mv[7] = p.mz[0 + 1][qz]; mv[8] = p.mz[0 + 2][qz];
-                }
+                if (z_pml) qz = ((long long)(shell_index(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1);
+                load_memvars(p, 0, false, in_y, in_zA, 0, qy, qz, mvA);
+                load_memvars(p, 0, false, in_y && validB, in_zB, 0, qy + 1, qz + 1, mvB);
             }
             RingPos rn1 = rn;
             rn1.advance(SN);
@@ -327,26 +355,55 @@ k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMa
             const double *Tvy = (const double *)(gN + (size_t)rn.s * NBYTES + G::HALO_BYTES);
             const double *Tvxn = (const double *)(gN + (size_t)rn1.s * NBYTES);
             const double *Tvyn = (const double *)(gN + (size_t)rn1.s * NBYTES + G::HALO_BYTES);
-            const double *Tvz = (const double *)(gC + (size_t)rc.s * CBYTES);
-            const double *Ts = (const double *)(gC + (size_t)rc.s * CBYTES + G::HALO_BYTES);
-
-            const double vx_c = Tvx[oh], vx_ip = Tvx[oh + 1], vx_jp = Tvx[oh + W];
-            const double vy_c = Tvy[oh + W + 2], vy_im = Tvy[oh + W + 1], vy_jm = Tvy[oh + 2];
-            const double vz_c = Tvz[oh + 2], vz_im = Tvz[oh + 1], vz_jp = Tvz[oh + W + 2];
-            const double vx_n = Tvxn[oh], vy_n = Tvyn[oh + W + 2];
-            const double sxx = Ts[0 * PD + oc], syy = Ts[1 * PD + oc], szz = Ts[2 * PD + oc];
-            const double sxy = Ts[3 * PD + oc], sxz = Ts[4 * PD + oc], syz = Ts[5 * PD + oc];
-
-            if (pml) {
-                stress_point<true, KUNIT>(p, q, i, j, k, kg, valid, do_n, do_xy, do_xz, do_yz, in_x, in_y, in_z, qx, qy, qz, mv,
-                                          vx_c, vx_ip, vx_jp, vx_n, vy_c, vy_im, vy_jm, vy_n, vz_c, vz_im, vz_jp, vz_m,
-                                          sxx, syy, szz, sxy, sxz, syz);
-            } else {
-                stress_point<false, KUNIT>(p, q, i, j, k, kg, valid, do_n, do_xy, do_xz, do_yz, false, false, false, 0, 0, 0, mv,
-                                           vx_c, vx_ip, vx_jp, vx_n, vy_c, vy_im, vy_jm, vy_n, vz_c, vz_im, vz_jp, vz_m,
-                                           sxx, syy, szz, sxy, sxz, syz);
+            const double *Tvz = (const double *)(gC + (size_t)rc.s * CSTAGE);
+            const double *Ts = (const double *)(gC + (size_t)rc.s * CSTAGE + G::HALO_BYTES);
+            if (pml) {      // x-shell memory variables of this plane, staged with the tiles
+                const double *Tm = (const double *)(gC + (size_t)rc.s * CSTAGE + CBYTES);
+                const int xd = (int)(XMB / 8), r0 = ty * p.sxp;
+                if (in_xA) { mvA[0] = Tm[r0 + sxA]; mvA[1] = Tm[xd + r0 + sxA]; mvA[2] = Tm[2 * xd + r0 + sxA]; }
+                if (in_xB) { mvB[0] = Tm[r0 + sxB]; mvB[1] = Tm[xd + r0 + sxB]; mvB[2] = Tm[2 * xd + r0 + sxB]; }
             }
-            vz_m = vz_c;
+
+            const double2 vx_c = lds2(Tvx, oh), vx_jp = lds2(Tvx, oh + W), vx_n = lds2(Tvxn, oh);
+            const double vx_ipB = Tvx[oh + 2];
+            const double2 vy_c = lds2(Tvy, oh + W + 2), vy_jm = lds2(Tvy, oh + 2), vy_n = lds2(Tvyn, oh + W + 2);
+            const double vy_imA = Tvy[oh + W + 1];
+            const double2 vz_c = lds2(Tvz, oh + 2), vz_jp = lds2(Tvz, oh + W + 2);
+            const double vz_imA = Tvz[oh + 1];
+            const double2 sxx = lds2(Ts, 0 * PD + oc), syy = lds2(Ts, 1 * PD + oc), szz = lds2(Ts, 2 * PD + oc);
+            const double2 sxy = lds2(Ts, 3 * PD + oc), sxz = lds2(Ts, 4 * PD + oc), syz = lds2(Ts, 5 * PD + oc);
+
+            StressVals a{sxx.x, syy.x, szz.x, sxy.x, sxz.x, syz.x}, b{sxx.y, syy.y, szz.y, sxy.y, sxz.y, syz.y};
+            if (pml) {
+                stress_point<true, KUNIT>(p, i, j, kg, do_nA, do_xyA, do_xzA, do_yzA, in_xA, in_y, in_zA, qxr + sxA, qy, qz, mvA,
+                                          vx_c.x, vx_c.y, vx_jp.x, vx_n.x, vy_c.x, vy_imA, vy_jm.x, vy_n.x, vz_c.x, vz_imA, vz_jp.x, vz_mA, a);
+                stress_point<true, KUNIT>(p, i + 1, j, kg, do_nB, do_xyB, do_xzB, do_yzB, in_xB, in_y && validB, in_zB, qxr + sxB, qy + 1, qz + 1, mvB,
+                                          vx_c.y, vx_ipB, vx_jp.y, vx_n.y, vy_c.y, vy_c.x, vy_jm.y, vy_n.y, vz_c.y, vz_c.x, vz_jp.y, vz_mB, b);
+            } else {
+                stress_point<false, KUNIT>(p, i, j, kg, do_nA, do_xyA, do_xzA, do_yzA, false, false, false, 0, 0, 0, mvA,
+                                           vx_c.x, vx_c.y, vx_jp.x, vx_n.x, vy_c.x, vy_imA, vy_jm.x, vy_n.x, vz_c.x, vz_imA, vz_jp.x, vz_mA, a);
+                stress_point<false, KUNIT>(p, i + 1, j, kg, do_nB, do_xyB, do_xzB, do_yzB, false, false, false, 0, 0, 0, mvB,
+                                           vx_c.y, vx_ipB, vx_jp.y, vx_n.y, vy_c.y, vy_c.x, vy_jm.y, vy_n.y, vz_c.y, vz_c.x, vz_jp.y, vz_mB, b);
+            }
+            vz_mA = vz_c.x; vz_mB = vz_c.y;
+
+            // 16-byte streaming stores; where a nest does not update a point (grid edges, the pad
+            // lane of an odd NX) the value loaded from this plane is written back unchanged
+            if (validA) {
+                st_stream2(p.sxx + q, a.sxx, b.sxx);
+                st_stream2(p.syy + q, a.syy, b.syy);
+                st_stream2(p.szz + q, a.szz, b.szz);
+                st_stream2(p.sxy + q, a.sxy, b.sxy);
+                st_stream2(p.sxz + q, a.sxz, b.sxz);
+                st_stream2(p.syz + q, a.syz, b.syz);
+                // boundary planes go straight into the neighbour slabs' halo planes (:951-963)
+                const long long qp = (long long)(j - 1) * pitch + (i - 1);
+                if (k == 1 && p.peer_lo[2]) st_stream2(p.peer_lo[2] + qp, a.szz, b.szz);          // sigmazz(:,:,1) -> left
+                if (k == p.nzl && p.peer_hi[1]) {                                                 // -> right
+                    st_stream2(p.peer_hi[1] + qp, a.sxz, b.sxz);
+                    st_stream2(p.peer_hi[2] + qp, a.syz, b.syz);
+                }
+            }
 
             __syncthreads();                                        // stages rn.s / rc.s are free
             if (tid == 0) {
@@ -357,15 +414,7 @@ k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMa
                     tma_load_3d(ringN + s * NBYTES, &tm.m[0], x0, y0, kk, bar);
                     tma_load_3d(ringN + s * NBYTES + G::HALO_BYTES, &tm.m[1], x0 - 2, y0 - 1, kk, bar);
                 }
-                if (n + (int)SC < np) {
-                    const uint32_t s = rc.s, bar = barC + 8 * s, dst = ringC + s * CBYTES;
-                    const int kk = kb + n + (int)SC;
-                    mbar_expect_tx(bar, TX_C);
-                    tma_load_3d(dst, &tm.m[2], x0 - 2, y0, kk, bar);
-#pragma unroll
-                    for (int f = 0; f < 6; f++)
-                        tma_load_3d(dst + G::HALO_BYTES + f * G::PLAIN_BYTES, &tm.m[3 + f], x0, y0, kk, bar);
-                }
+                if (n + (int)SC < np) issue_c(rc.s, kb + n + (int)SC);
             }
             rn = rn1;
             rc.advance(SC);
@@ -379,18 +428,21 @@ k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMa
 // ring C (plane n only):     sxx (halo box at (-2,0)), syy (halo, (0,0)), sxy (halo, (0,-1)),
 //                            sxz (halo, (0,0)), syz (halo, (0,-1)), vx vy vz (plain boxes)
 // maps: 0 sxx 1 syy 2 sxy 3 sxz 4 syz 5 szz 6 vx 7 vy 8 vz
+struct VelVals { double vx, vy, vz; };                           // in: old values, out: new values
+
 template <bool PML, bool KUNIT>
 __device__ __forceinline__ void velocity_point(
-    const Params3D &p, const long long q, const int i, const int j, const int k, const int kg,
-    const bool valid, const bool do_vx, const bool do_vy, const bool do_vz, const bool edge_ij, const bool ebox_ij,
+    const Params3D &p, const int i, const int j, const int k, const int kg,
+    const bool do_vx, const bool do_vy, const bool do_vz, const bool edge_ij, const bool ebox_ij,
     const bool src_ij, const bool in_x, const bool in_y, const bool in_z, const long long qx, const long long qy,
     const long long qz, const double (&mv)[9],
     const double sxx_c, const double sxx_im, const double syy_c, const double syy_jp,
     const double sxy_c, const double sxy_jm, const double sxy_ip, const double sxz_c, const double sxz_ip,
     const double sxz_m, const double syz_c, const double syz_jm, const double syz_m, const double szz_c,
-    const double szz_n, double vx, double vy, double vz, double &ekin, double &epot)
+    const double szz_n, VelVals &v, double &ekin, double &epot)
 {
     const double odx = p.odx, ody = p.ody, odz = p.odz, dt_r = p.dt_over_rho;
+    double vx = v.vx, vy = v.vy, vz = v.vz;
     if (kg >= 2) {                                           // k2begin
         if (do_vx) {                                         // :976-996
             double value_dsigmaxx_dx = (sxx_c - sxx_im) * odx;
@@ -434,16 +486,7 @@ __device__ __forceinline__ void velocity_point(
     }
     // Dirichlet on the six faces, :1087-1121
     if (edge_ij || kg == 1 || kg == p.nz) { vx = 0.0; vy = 0.0; vz = 0.0; }
-
-    if (valid) {
-        st_stream(p.vx + q, vx);
-        st_stream(p.vy + q, vy);
-        st_stream(p.vz + q, vz);
-        // boundary planes go straight into the neighbour slabs' halo planes (:811-823)
-        const long long qp = (long long)(j - 1) * p.pitch + (i - 1);
-        if (k == 1 && p.peer_lo[0]) { p.peer_lo[0][qp] = vx; p.peer_lo[1][qp] = vy; }   // -> left
-        if (k == p.nzl && p.peer_hi[0]) p.peer_hi[0][qp] = vz;                          // -> right
-    }
+    v.vx = vx; v.vy = vy; v.vz = vz;
 
     // energy over the PML-free box, :1131-1177; reciprocals instead of the reference's
     // divisions -- the energy sum is reduction-order dependent anyway (quirk B11)
@@ -468,7 +511,7 @@ __device__ __forceinline__ void velocity_point(
 }
 
 template <bool KUNIT, int TX, int TY, int MINB>
-__global__ void __launch_bounds__(TX *TY, MINB)
+__global__ void __launch_bounds__(TX / 2 * TY, MINB)
 k_velocity3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMaps tm, const __grid_constant__ Tile3D t)
 {
     using G = TileGeom<TX, TY>;
@@ -478,7 +521,9 @@ k_velocity3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ Tma
     constexpr uint32_t TX_N = G::PLAIN_BOX_BYTES;
     constexpr uint32_t TX_C = 5 * G::HALO_BOX_BYTES + 3 * G::PLAIN_BOX_BYTES;
     constexpr int PD = G::PLAIN_BYTES / 8, HD = G::HALO_BYTES / 8;
-    constexpr int NT = TX * TY;
+    constexpr int NT = TX / 2 * TY;
+    const uint32_t XMB = (uint32_t)t.xm_bytes, XM_TX = (uint32_t)(TY * p.sxp * 8);    // x-shell memory variables, see k_stress3d_tma
+    const uint32_t CSTAGE = CBYTES + 3 * XMB;
 
     __shared__ double red[2 * ((NT + 31) / 32)];
     extern __shared__ unsigned char smem_dyn[];
@@ -490,7 +535,7 @@ k_velocity3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ Tma
     const unsigned char *gN = gbase + kBarBytes, *gC = gN + (size_t)SN * NBYTES;
 
     const int tx = threadIdx.x, ty = threadIdx.y;
-    const int tid = ty * TX + tx;
+    const int tid = ty * (TX / 2) + tx;
     if (tid == 0) {
         for (uint32_t s = 0; s < SN; s++) mbar_init(barN + 8 * s, 1);
         for (uint32_t s = 0; s < SC; s++) mbar_init(barC + 8 * s, 1);
@@ -500,8 +545,8 @@ k_velocity3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ Tma
 
     const int pitch = p.pitch;
     const long long pl = p.plane;
-    const int oh = ty * W + tx;
-    const int oc = ty * TX + tx;
+    const int oh = ty * W + 2 * tx;
+    const int oc = ty * TX + 2 * tx;
 
     RingPos rn{0, 0}, rc{0, 0};
     for (int item = blockIdx.x; item < t.nitems; item += gridDim.x) {
@@ -515,9 +560,15 @@ k_velocity3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ Tma
         const int np = ke - kb + 1;
         const int x0 = i0 - 1, y0 = j0 - 1;
 
+        const bool tile_xpml = XMB != 0 && ((i0 <= p.xlo) || (i0 + TX - 1 >= p.xhi));
         auto issue_c = [&](uint32_t s, int kk) {
-            const uint32_t bar = barC + 8 * s, dst = ringC + s * CBYTES;
-            mbar_expect_tx(bar, TX_C);
+            const uint32_t bar = barC + 8 * s, dst = ringC + s * CSTAGE;
+            mbar_expect_tx(bar, TX_C + (tile_xpml ? 3 * XM_TX : 0u));
+            if (tile_xpml) {
+                const long long row0 = ((long long)(kk - 1) * p.ny + (j0 - 1)) * p.sxp;
+#pragma unroll
+                for (int f = 0; f < 3; f++) bulk_load(dst + CBYTES + f * XMB, p.mx[3 + f] + row0, XM_TX, bar);
+            }
             tma_load_3d(dst + 0 * G::HALO_BYTES, &tm.m[0], x0 - 2, y0, kk, bar);
             tma_load_3d(dst + 1 * G::HALO_BYTES, &tm.m[1], x0, y0, kk, bar);
             tma_load_3d(dst + 2 * G::HALO_BYTES, &tm.m[2], x0, y0 - 1, kk, bar);
@@ -541,76 +592,111 @@ k_velocity3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ Tma
             }
         }
 
-        const int i = i0 + tx, j = j0 + ty;
-        const bool valid = (i <= p.nx) && (j <= p.ny);
+        const int i = i0 + 2 * tx, j = j0 + ty;
+        const bool row = (j <= p.ny);
+        const bool validA = row && (i <= p.nx), validB = row && (i + 1 <= p.nx);
         long long q = (long long)kb * pl + (long long)(j - 1) * pitch + (i - 1);
 
-        const bool in_x = valid && ((i <= p.xlo) || (i >= p.xhi));
-        const bool in_y = valid && ((j <= p.ylo) || (j >= p.yhi));
-        const bool warp_pml = __any_sync(0xffffffffu, in_x || in_y);
-        const bool do_vx = valid && (i >= 2) && (j >= 2);                    // :978-979
-        const bool do_vy = valid && (i <= p.nx - 1) && (j <= p.ny - 1);      // :998-999
-        const bool do_vz = valid && (i <= p.nx - 1) && (j >= 2);             // :1033-1034
-        const bool edge_ij = (i == 1) || (i == p.nx) || (j == 1) || (j == p.ny);   // :1089-1106
-        const bool ebox_ij = valid && (i >= p.npml + 1) && (i <= p.nx - p.npml) &&
-                             (j >= p.npml + 1) && (j <= p.ny - p.npml);            // :1144-1145
-        const bool src_ij = (i == p.isrc) && (j == p.jsrc);
+        const bool in_xA = validA && ((i <= p.xlo) || (i >= p.xhi));
+        const bool in_xB = validB && ((i + 1 <= p.xlo) || (i + 1 >= p.xhi));
+        const bool in_y = validA && ((j <= p.ylo) || (j >= p.yhi));
+        const bool warp_pml = __any_sync(0xffffffffu, in_xA || in_xB || in_y);
+        const bool do_vxA = validA && (i >= 2) && (j >= 2), do_vxB = validB && (j >= 2);                                         // :978-979
+        const bool do_vyA = validA && (i <= p.nx - 1) && (j <= p.ny - 1), do_vyB = validB && (i + 1 <= p.nx - 1) && (j <= p.ny - 1);   // :998-999
+        const bool do_vzA = validA && (i <= p.nx - 1) && (j >= 2), do_vzB = validB && (i + 1 <= p.nx - 1) && (j >= 2);           // :1033-1034
+        const bool edge_j = (j == 1) || (j == p.ny);
+        const bool edgeA = (i == 1) || (i == p.nx) || edge_j, edgeB = (i + 1 == p.nx) || edge_j;                                 // :1089-1106
+        const bool ebox_j = (j >= p.npml + 1) && (j <= p.ny - p.npml);
+        const bool eboxA = validA && ebox_j && (i >= p.npml + 1) && (i <= p.nx - p.npml);                                        // :1144-1145
+        const bool eboxB = validB && ebox_j && (i + 1 >= p.npml + 1) && (i + 1 <= p.nx - p.npml);
+        const bool srcA = (i == p.isrc) && (j == p.jsrc), srcB = (i + 1 == p.isrc) && (j == p.jsrc);
 
-        long long qx = 0, qy = 0;
-        if (in_x) qx = ((long long)(kb - 1) * p.ny + (j - 1)) * p.sxp + shell_index(i, p.xlo, p.xhi);
-        if (in_y) qy = ((long long)(kb - 1) * p.sy + shell_index(j, p.ylo, p.yhi)) * pitch + (i - 1);
+        const int sxA = in_xA ? shell_index(i, p.xlo, p.xhi) : 0, sxB = in_xB ? shell_index(i + 1, p.xlo, p.xhi) : 0;
+        long long qxr = ((long long)(kb - 1) * p.ny + (j - 1)) * p.sxp;
+        long long qy = in_y ? ((long long)(kb - 1) * p.sy + shell_index(j, p.ylo, p.yhi)) * pitch + (i - 1) : 0;
         const long long qx_step = (long long)p.ny * p.sxp, qy_step = (long long)p.sy * pitch;
 
-        double sxz_m = valid ? p.sxz[q - pl] : 0.0, syz_m = valid ? p.syz[q - pl] : 0.0;   // plane kb-1
+        double sxz_mA = 0.0, sxz_mB = 0.0, syz_mA = 0.0, syz_mB = 0.0;     // plane kb-1
+        if (validA) {
+            const double2 t2 = *reinterpret_cast<const double2 *>(p.sxz + q - pl), u2 = *reinterpret_cast<const double2 *>(p.syz + q - pl);
+            sxz_mA = t2.x; sxz_mB = t2.y; syz_mA = u2.x; syz_mB = u2.y;
+        }
         double ekin = 0.0, epot = 0.0;
 
         mbar_wait(barN + 8 * rn.s, rn.par);
-        for (int n = 0; n < np; ++n, q += pl, qx += qx_step, qy += qy_step) {
+        for (int n = 0; n < np; ++n, q += pl, qxr += qx_step, qy += qy_step) {
             const int k = kb + n;
             const int kg = k + p.koff;
-            // C-PML memory variables of this plane: every load is issued before the waits (and
-            // before any store of the recursion, which the compiler must assume to alias)
             const bool z_pml = (kg <= p.zlo) || (kg >= p.zhi);      // uniform
             const bool pml = warp_pml || z_pml;                     // warp-uniform
-            const bool in_z = valid && z_pml;
+            const bool in_zA = validA && z_pml, in_zB = validB && z_pml;
             long long qz = 0;
-            double mv[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            double mvA[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, mvB[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
             if (pml) {
-                if (in_x) { mv[0] = p.mx[3 + 0][qx]; mv[1] = p.mx[3 + 1][qx]; mv[2] = p.mx[3 + 2][qx]; }
-                if (in_y) { mv[3] = p.my[3 + 0][qy]; mv[4] = p.my[3 + 1][qy]; mv[5] = p.my[3 + 2][qy]; }
-                if (in_z) {
-                    qz = ((long long)(shell_index(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1);
-                    mv[6] = p.mz[3 + 0][qz]; mv[7] = p.mz[3 + 1][qz]; mv[8] = p.mz[3 + 2][qz];
-                }
+                if (z_pml) qz = ((long long)(shell_index(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1);
+                load_memvars(p, 3, false, in_y, in_zA, 0, qy, qz, mvA);
+                load_memvars(p, 3, false, in_y && validB, in_zB, 0, qy + 1, qz + 1, mvB);
             }
             RingPos rn1 = rn;
             rn1.advance(SN);
             mbar_wait(barN + 8 * rn1.s, rn1.par);
             mbar_wait(barC + 8 * rc.s, rc.par);
 
-            const double *Tc = (const double *)(gC + (size_t)rc.s * CBYTES);
+            const double *Tc = (const double *)(gC + (size_t)rc.s * CSTAGE);
+            if (pml) {      // x-shell memory variables of this plane, staged with the tiles
+                const double *Tm = (const double *)(gC + (size_t)rc.s * CSTAGE + CBYTES);
+                const int xd = (int)(XMB / 8), r0 = ty * p.sxp;
+                if (in_xA) { mvA[0] = Tm[r0 + sxA]; mvA[1] = Tm[xd + r0 + sxA]; mvA[2] = Tm[2 * xd + r0 + sxA]; }
+                if (in_xB) { mvB[0] = Tm[r0 + sxB]; mvB[1] = Tm[xd + r0 + sxB]; mvB[2] = Tm[2 * xd + r0 + sxB]; }
+            }
             const double *Txx = Tc, *Tyy = Tc + HD, *Txy = Tc + 2 * HD, *Txz = Tc + 3 * HD, *Tyz = Tc + 4 * HD;
             const double *Tp = Tc + 5 * HD;
 
-            const double sxx_c = Txx[oh + 2], sxx_im = Txx[oh + 1];
-            const double syy_c = Tyy[oh], syy_jp = Tyy[oh + W];
-            const double sxy_c = Txy[oh + W], sxy_jm = Txy[oh], sxy_ip = Txy[oh + W + 1];
-            const double sxz_c = Txz[oh], sxz_ip = Txz[oh + 1];
-            const double syz_c = Tyz[oh + W], syz_jm = Tyz[oh];
-            const double szz_c = ((const double *)(gN + (size_t)rn.s * NBYTES))[oc];
-            const double szz_n = ((const double *)(gN + (size_t)rn1.s * NBYTES))[oc];
-            const double vx = Tp[0 * PD + oc], vy = Tp[1 * PD + oc], vz = Tp[2 * PD + oc];
+            const double2 sxx_c = lds2(Txx, oh + 2);
+            const double sxx_imA = Txx[oh + 1];
+            const double2 syy_c = lds2(Tyy, oh), syy_jp = lds2(Tyy, oh + W);
+            const double2 sxy_c = lds2(Txy, oh + W), sxy_jm = lds2(Txy, oh);
+            const double sxy_ipB = Txy[oh + W + 2];
+            const double2 sxz_c = lds2(Txz, oh);
+            const double sxz_ipB = Txz[oh + 2];
+            const double2 syz_c = lds2(Tyz, oh + W), syz_jm = lds2(Tyz, oh);
+            const double2 szz_c = lds2((const double *)(gN + (size_t)rn.s * NBYTES), oc);
+            const double2 szz_n = lds2((const double *)(gN + (size_t)rn1.s * NBYTES), oc);
+            const double2 vx = lds2(Tp, 0 * PD + oc), vy = lds2(Tp, 1 * PD + oc), vz = lds2(Tp, 2 * PD + oc);
 
+            VelVals a{vx.x, vy.x, vz.x}, b{vx.y, vy.y, vz.y};
             if (pml) {
-                velocity_point<true, KUNIT>(p, q, i, j, k, kg, valid, do_vx, do_vy, do_vz, edge_ij, ebox_ij, src_ij, in_x, in_y, in_z,
-                                            qx, qy, qz, mv, sxx_c, sxx_im, syy_c, syy_jp, sxy_c, sxy_jm, sxy_ip, sxz_c, sxz_ip, sxz_m,
-                                            syz_c, syz_jm, syz_m, szz_c, szz_n, vx, vy, vz, ekin, epot);
+                velocity_point<true, KUNIT>(p, i, j, k, kg, do_vxA, do_vyA, do_vzA, edgeA, eboxA, srcA, in_xA, in_y, in_zA, qxr + sxA, qy, qz, mvA,
+                                            sxx_c.x, sxx_imA, syy_c.x, syy_jp.x, sxy_c.x, sxy_jm.x, sxy_c.y, sxz_c.x, sxz_c.y, sxz_mA,
+                                            syz_c.x, syz_jm.x, syz_mA, szz_c.x, szz_n.x, a, ekin, epot);
+                velocity_point<true, KUNIT>(p, i + 1, j, k, kg, do_vxB, do_vyB, do_vzB, edgeB, eboxB, srcB, in_xB, in_y && validB, in_zB, qxr + sxB, qy + 1, qz + 1, mvB,
+                                            sxx_c.y, sxx_c.x, syy_c.y, syy_jp.y, sxy_c.y, sxy_jm.y, sxy_ipB, sxz_c.y, sxz_ipB, sxz_mB,
+                                            syz_c.y, syz_jm.y, syz_mB, szz_c.y, szz_n.y, b, ekin, epot);
             } else {
-                velocity_point<false, KUNIT>(p, q, i, j, k, kg, valid, do_vx, do_vy, do_vz, edge_ij, ebox_ij, src_ij, false, false, false,
-                                             0, 0, 0, mv, sxx_c, sxx_im, syy_c, syy_jp, sxy_c, sxy_jm, sxy_ip, sxz_c, sxz_ip, sxz_m,
-                                             syz_c, syz_jm, syz_m, szz_c, szz_n, vx, vy, vz, ekin, epot);
+                velocity_point<false, KUNIT>(p, i, j, k, kg, do_vxA, do_vyA, do_vzA, edgeA, eboxA, srcA, false, false, false, 0, 0, 0, mvA,
+                                             sxx_c.x, sxx_imA, syy_c.x, syy_jp.x, sxy_c.x, sxy_jm.x, sxy_c.y, sxz_c.x, sxz_c.y, sxz_mA,
+                                             syz_c.x, syz_jm.x, syz_mA, szz_c.x, szz_n.x, a, ekin, epot);
+                velocity_point<false, KUNIT>(p, i + 1, j, k, kg, do_vxB, do_vyB, do_vzB, edgeB, eboxB, srcB, false, false, false, 0, 0, 0, mvB,
+                                             sxx_c.y, sxx_c.x, syy_c.y, syy_jp.y, sxy_c.y, sxy_jm.y, sxy_ipB, sxz_c.y, sxz_ipB, sxz_mB,
+                                             syz_c.y, syz_jm.y, syz_mB, szz_c.y, szz_n.y, b, ekin, epot);
             }
-            sxz_m = sxz_c; syz_m = syz_c;
+            sxz_mA = sxz_c.x; sxz_mB = sxz_c.y; syz_mA = syz_c.x; syz_mB = syz_c.y;
+
+            if (validA) {
+                // the pad lane of an odd NX keeps its zero: B is then outside every nest, not an
+                // edge point, and its loaded value is the TMA's zero fill
+                if (!validB) { b.vx = 0.0; b.vy = 0.0; b.vz = 0.0; }
+                st_stream2(p.vx + q, a.vx, b.vx);
+                st_stream2(p.vy + q, a.vy, b.vy);
+                st_stream2(p.vz + q, a.vz, b.vz);
+                // boundary planes go straight into the neighbour slabs' halo planes (:811-823)
+                const long long qp = (long long)(j - 1) * pitch + (i - 1);
+                if (k == 1 && p.peer_lo[0]) {                                                   // -> left
+                    st_stream2(p.peer_lo[0] + qp, a.vx, b.vx);
+                    st_stream2(p.peer_lo[1] + qp, a.vy, b.vy);
+                }
+                if (k == p.nzl && p.peer_hi[0]) st_stream2(p.peer_hi[0] + qp, a.vz, b.vz);      // -> right
+            }
 
             __syncthreads();
             if (tid == 0) {
@@ -637,49 +723,48 @@ k_velocity3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ Tma
 // ---- launch dispatch ---------------------------------------------------------------
 
 template <int TX, int TY>
-static size_t smem_need(bool stress, int stages)
+static size_t smem_need(bool stress, int stages, int xm_bytes)
 {
     using G = TileGeom<TX, TY>;
     // ring C holds `stages` planes, ring N one more (kernels above)
     const size_t c = stress ? G::HALO_BYTES + 6 * G::PLAIN_BYTES : 5 * G::HALO_BYTES + 3 * G::PLAIN_BYTES;
     const size_t n = stress ? 2 * G::HALO_BYTES : G::PLAIN_BYTES;
-    return kBarBytes + 128 + c * (size_t)stages + n * (size_t)(stages + 1);
+    return kBarBytes + 128 + (c + 3 * (size_t)xm_bytes) * (size_t)stages + n * (size_t)(stages + 1);
 }
 
 template <bool KUNIT, int TX, int TY, int MINB>
 static cudaError_t launch_tile(const Params3D &p, const TmaMaps &tm, const Tile3D &t, cudaStream_t s, bool stress, int *occ)
 {
-    const size_t smem = smem_need<TX, TY>(stress, t.stages);
+    const size_t smem = smem_need<TX, TY>(stress, t.stages, t.xm_bytes);
+    constexpr int NT = TX / 2 * TY;                 // one thread per pair of points
     const void *fn = stress ? (const void *)k_stress3d_tma<KUNIT, TX, TY, MINB> : (const void *)k_velocity3d_tma<KUNIT, TX, TY, MINB>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (occ) {
-        if (stress) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_stress3d_tma<KUNIT, TX, TY, MINB>, TX * TY, smem);
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_velocity3d_tma<KUNIT, TX, TY, MINB>, TX * TY, smem);
+        if (stress) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_stress3d_tma<KUNIT, TX, TY, MINB>, NT, smem);
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_velocity3d_tma<KUNIT, TX, TY, MINB>, NT, smem);
     }
-    const dim3 grid(stress ? t.grid_stress : t.grid_velocity), block(TX, TY);
+    const dim3 grid(stress ? t.grid_stress : t.grid_velocity), block(TX / 2, TY);
     if (stress) k_stress3d_tma<KUNIT, TX, TY, MINB><<<grid, block, smem, s>>>(p, tm, t);
     else        k_velocity3d_tma<KUNIT, TX, TY, MINB><<<grid, block, smem, s>>>(p, tm, t);
     return cudaGetLastError();
 }
 
-// MINB (minimum resident CTAs per SM) caps the registers: 65536 / (threads * MINB).
+// Tiles (TX x TY points, TX/2 x TY threads, a multiple of 32); MINB (minimum resident CTAs per
+// SM) caps the registers at 65536 / (threads * MINB).
 template <bool KUNIT>
 static cudaError_t dispatch_tile(const Params3D &p, const TmaMaps &tm, const Tile3D &t, cudaStream_t s, bool stress, int *occ)
 {
     switch (t.tx * 1000 + t.ty * 10 + t.minb) {
-    case 32081:  case 32082:  return launch_tile<KUNIT, 32, 8, 2>(p, tm, t, s, stress, occ);
-    case 64041:  case 64042:  return launch_tile<KUNIT, 64, 4, 2>(p, tm, t, s, stress, occ);
-    case 128021: case 128022: return launch_tile<KUNIT, 128, 2, 2>(p, tm, t, s, stress, occ);
-    case 32083:  return launch_tile<KUNIT, 32, 8, 3>(p, tm, t, s, stress, occ);
-    case 64043:  return launch_tile<KUNIT, 64, 4, 3>(p, tm, t, s, stress, occ);
-    case 128023: return launch_tile<KUNIT, 128, 2, 3>(p, tm, t, s, stress, occ);
-    case 64081:  return launch_tile<KUNIT, 64, 8, 1>(p, tm, t, s, stress, occ);
-    case 64082:  return launch_tile<KUNIT, 64, 8, 2>(p, tm, t, s, stress, occ);
-    case 104041: return launch_tile<KUNIT, 104, 4, 1>(p, tm, t, s, stress, occ);
-    case 104042: return launch_tile<KUNIT, 104, 4, 2>(p, tm, t, s, stress, occ);
-    case 128041: return launch_tile<KUNIT, 128, 4, 1>(p, tm, t, s, stress, occ);
-    case 128042: return launch_tile<KUNIT, 128, 4, 2>(p, tm, t, s, stress, occ);
+    case 64041:  case 64042:  return launch_tile<KUNIT, 64, 4, 2>(p, tm, t, s, stress, occ);      // 128 threads
+    case 64043:  case 64044:  return launch_tile<KUNIT, 64, 4, 4>(p, tm, t, s, stress, occ);
+    case 64081:  case 64082:  return launch_tile<KUNIT, 64, 8, 2>(p, tm, t, s, stress, occ);      // 256 threads
+    case 128041: case 128042: return launch_tile<KUNIT, 128, 4, 2>(p, tm, t, s, stress, occ);     // 256 threads
+    case 128043: return launch_tile<KUNIT, 128, 4, 3>(p, tm, t, s, stress, occ);
+    case 128081: return launch_tile<KUNIT, 128, 8, 1>(p, tm, t, s, stress, occ);                  // 512 threads
+    case 128082: return launch_tile<KUNIT, 128, 8, 2>(p, tm, t, s, stress, occ);
+    case 104081: return launch_tile<KUNIT, 104, 8, 1>(p, tm, t, s, stress, occ);                  // 416 threads
+    case 104082: return launch_tile<KUNIT, 104, 8, 2>(p, tm, t, s, stress, occ);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -687,7 +772,7 @@ static cudaError_t dispatch_tile(const Params3D &p, const TmaMaps &tm, const Til
 bool tma_tile_supported(int tx, int ty)
 {
     switch (tx * 100 + ty) {
-    case 3208: case 6404: case 6408: case 10404: case 12802: case 12804: return true;
+    case 6404: case 6408: case 12804: case 12808: case 10408: return true;     // TMA boxes hold at most 256 elements per dimension
     default: return false;
     }
 }
