@@ -666,6 +666,9 @@ static Params3D make_p3(cpml_handle *h, int it)
     p.rho = c.rho; p.lambda = c.lambda; p.mu = c.mu;
     p.inv_den = 1.0 / (2.0 * c.mu * (3.0 * c.lambda + 2.0 * c.mu));
     p.inv_2mu = 1.0 / (2.0 * c.mu);
+    p.inv_mu = 1.0 / c.mu;
+    p.c2lm = 2.0 * (c.lambda + c.mu);
+    p.half_rho = 0.5 * c.rho;
     p.partials = h->d_partials; p.nblocks = h->nblocks;
     p.kunit = 1;
     for (int ax = 0; ax < 3; ax++)

@@ -62,6 +62,7 @@ struct Params3D {
     int energy_bug_compat;
     double rho, lambda, mu;
     double inv_den, inv_2mu;  // 1/(2 mu (3 lambda + 2 mu)), 1/(2 mu): energy (:1159-1167)
+    double inv_mu, c2lm, half_rho;   // 1/mu, 2 (lambda + mu), rho/2
     double *partials;         // [2][nblocks] kinetic / potential per block
     int nblocks;
     int kunit;                // every K profile == 1: the value/K division is dropped (exact)

@@ -105,6 +105,19 @@ __device__ __forceinline__ double cpml_apply(double *__restrict__ mem, long long
     return KUNIT ? value + m : value / K + m;
 }
 
+// The same recursion step, branch-free across the lanes of a warp: lanes outside the shell carry
+// a = 0 and m = 0, so their m' is 0 and the derivative comes back as value + 0 (exact; only the
+// sign of a zero can differ); only shell lanes store.  This keeps the C-PML code of a warp that
+// holds a few shell lanes straight-line instead of nine divergent blocks per point.
+template <bool KUNIT>
+__device__ __forceinline__ double cpml_step(double *__restrict__ mem, long long q, bool store, double m,
+                                            double b, double a, double K, double value)
+{
+    m = b * m + a * value;
+    if (store) mem[q] = m;
+    return KUNIT ? value + m : value / K + m;
+}
+
 __device__ __forceinline__ int shell_index(int i, int lo, int hi) { return i <= lo ? i - 1 : lo + (i - hi); }
 
 template <int NT>
@@ -153,12 +166,15 @@ struct RingPos {
 // HBM (profiles/r01_v4_*).  The point update itself is written once, per point.
 struct StressVals { double sxx, syy, szz, sxy, sxz, syz; };   // in: old values, out: new values
 
-template <bool PML, bool KUNIT>
+// Coefficient table of the tile's columns in shared memory: rows a, b, K, a_half, b_half, K_half
+// (CXW doubles each).  ux / uy / uz: the warp holds x- / y-shell lanes, the plane lies in the z
+// shell (warp-uniform); in_* : this point does (stores its memory variables).
+template <bool PML, bool KUNIT, int CXW>
 __device__ __forceinline__ void stress_point(
-    const Params3D &p, const int i, const int j, const int kg,
+    const Params3D &p, const double *__restrict__ Cx, const int c, const int j, const int kg,
     const bool do_n, const bool do_xy, const bool do_xz, const bool do_yz,
-    const bool in_x, const bool in_y, const bool in_z, const long long qx, const long long qy, const long long qz,
-    const double (&mv)[9],
+    const bool ux, const bool uy, const bool uz, const bool in_x, const bool in_y, const bool in_z,
+    const long long qx, const long long qy, const long long qz, const double (&mv)[9],
     const double vx_c, const double vx_ip, const double vx_jp, const double vx_n,
     const double vy_c, const double vy_im, const double vy_jm, const double vy_n,
     const double vz_c, const double vz_im, const double vz_jp, const double vz_m, StressVals &s)
@@ -171,9 +187,9 @@ __device__ __forceinline__ void stress_point(
         double value_dvy_dy = (vy_c - vy_jm) * ody;
         double value_dvz_dz = (vz_c - vz_m) * odz;
         if (PML) {
-            if (in_x) value_dvx_dx = cpml_apply<KUNIT>(p.mx[0], qx, mv[0], p.cx.b_half[i], p.cx.a_half[i], KUNIT ? 1.0 : p.cx.K_half[i], value_dvx_dx);
-            if (in_y) value_dvy_dy = cpml_apply<KUNIT>(p.my[0], qy, mv[3], p.cy.b[j], p.cy.a[j], KUNIT ? 1.0 : p.cy.K[j], value_dvy_dy);
-            if (in_z) value_dvz_dz = cpml_apply<KUNIT>(p.mz[0], qz, mv[6], p.cz.b[kg], p.cz.a[kg], KUNIT ? 1.0 : p.cz.K[kg], value_dvz_dz);
+            if (ux) value_dvx_dx = cpml_step<KUNIT>(p.mx[0], qx, in_x, mv[0], Cx[4 * CXW + c], Cx[3 * CXW + c], KUNIT ? 1.0 : Cx[5 * CXW + c], value_dvx_dx);
+            if (uy) value_dvy_dy = cpml_step<KUNIT>(p.my[0], qy, in_y, mv[3], p.cy.b[j], p.cy.a[j], KUNIT ? 1.0 : p.cy.K[j], value_dvy_dy);
+            if (uz) value_dvz_dz = cpml_step<KUNIT>(p.mz[0], qz, in_z, mv[6], p.cz.b[kg], p.cz.a[kg], KUNIT ? 1.0 : p.cz.K[kg], value_dvz_dz);
         }
         s.sxx = dt_l2m * value_dvx_dx + dt_l * (value_dvy_dy + value_dvz_dz) + s.sxx;
         s.syy = dt_l * (value_dvx_dx + value_dvz_dz) + dt_l2m * value_dvy_dy + s.syy;
@@ -184,8 +200,8 @@ __device__ __forceinline__ void stress_point(
         double value_dvy_dx = (vy_c - vy_im) * odx;
         double value_dvx_dy = (vx_jp - vx_c) * ody;
         if (PML) {
-            if (in_x) value_dvy_dx = cpml_apply<KUNIT>(p.mx[1], qx, mv[1], p.cx.b[i], p.cx.a[i], KUNIT ? 1.0 : p.cx.K[i], value_dvy_dx);
-            if (in_y) value_dvx_dy = cpml_apply<KUNIT>(p.my[1], qy, mv[4], p.cy.b_half[j], p.cy.a_half[j], KUNIT ? 1.0 : p.cy.K_half[j], value_dvx_dy);
+            if (ux) value_dvy_dx = cpml_step<KUNIT>(p.mx[1], qx, in_x, mv[1], Cx[1 * CXW + c], Cx[0 * CXW + c], KUNIT ? 1.0 : Cx[2 * CXW + c], value_dvy_dx);
+            if (uy) value_dvx_dy = cpml_step<KUNIT>(p.my[1], qy, in_y, mv[4], p.cy.b_half[j], p.cy.a_half[j], KUNIT ? 1.0 : p.cy.K_half[j], value_dvx_dy);
         }
         s.sxy = dt_m * (value_dvy_dx + value_dvx_dy) + s.sxy;
     }
@@ -195,8 +211,8 @@ __device__ __forceinline__ void stress_point(
             double value_dvz_dx = (vz_c - vz_im) * odx;
             double value_dvx_dz = (vx_n - vx_c) * odz;
             if (PML) {
-                if (in_x) value_dvz_dx = cpml_apply<KUNIT>(p.mx[2], qx, mv[2], p.cx.b[i], p.cx.a[i], KUNIT ? 1.0 : p.cx.K[i], value_dvz_dx);
-                if (in_z) value_dvx_dz = cpml_apply<KUNIT>(p.mz[1], qz, mv[7], p.cz.b_half[kg], p.cz.a_half[kg], KUNIT ? 1.0 : p.cz.K_half[kg], value_dvx_dz);
+                if (ux) value_dvz_dx = cpml_step<KUNIT>(p.mx[2], qx, in_x, mv[2], Cx[1 * CXW + c], Cx[0 * CXW + c], KUNIT ? 1.0 : Cx[2 * CXW + c], value_dvz_dx);
+                if (uz) value_dvx_dz = cpml_step<KUNIT>(p.mz[1], qz, in_z, mv[7], p.cz.b_half[kg], p.cz.a_half[kg], KUNIT ? 1.0 : p.cz.K_half[kg], value_dvx_dz);
             }
             s.sxz = dt_m * (value_dvz_dx + value_dvx_dz) + s.sxz;
         }
@@ -204,11 +220,22 @@ __device__ __forceinline__ void stress_point(
             double value_dvz_dy = (vz_jp - vz_c) * ody;
             double value_dvy_dz = (vy_n - vy_c) * odz;
             if (PML) {
-                if (in_y) value_dvz_dy = cpml_apply<KUNIT>(p.my[2], qy, mv[5], p.cy.b_half[j], p.cy.a_half[j], KUNIT ? 1.0 : p.cy.K_half[j], value_dvz_dy);
-                if (in_z) value_dvy_dz = cpml_apply<KUNIT>(p.mz[2], qz, mv[8], p.cz.b_half[kg], p.cz.a_half[kg], KUNIT ? 1.0 : p.cz.K_half[kg], value_dvy_dz);
+                if (uy) value_dvz_dy = cpml_step<KUNIT>(p.my[2], qy, in_y, mv[5], p.cy.b_half[j], p.cy.a_half[j], KUNIT ? 1.0 : p.cy.K_half[j], value_dvz_dy);
+                if (uz) value_dvy_dz = cpml_step<KUNIT>(p.mz[2], qz, in_z, mv[8], p.cz.b_half[kg], p.cz.a_half[kg], KUNIT ? 1.0 : p.cz.K_half[kg], value_dvy_dz);
             }
             s.syz = dt_m * (value_dvz_dy + value_dvy_dz) + s.syz;
         }
+    }
+}
+
+// Fills the column coefficient table of a tile (columns beyond NX: a = b = 0, K = 1).
+template <int TX, int NT>
+__device__ __forceinline__ void fill_cx(const Params3D &p, double *Cx, int i0, int tid)
+{
+    for (int e = tid; e < 6 * TX; e += NT) {
+        const int f = e / TX, i = i0 + (e - f * TX);
+        const double *src = f == 0 ? p.cx.a : f == 1 ? p.cx.b : f == 2 ? p.cx.K : f == 3 ? p.cx.a_half : f == 4 ? p.cx.b_half : p.cx.K_half;
+        Cx[e] = (i <= p.nx) ? src[i] : ((f == 2 || f == 5) ? 1.0 : 0.0);
     }
 }
 
@@ -240,6 +267,7 @@ k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMa
     const uint32_t XMB = (uint32_t)t.xm_bytes, XM_TX = (uint32_t)(TY * p.sxp * 8);
     const uint32_t CSTAGE = CBYTES + 3 * XMB;
 
+    __shared__ double Cx[6 * TX];                                   // x coefficients of the tile's columns
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t sbase = (smem_u32(smem_dyn) + 127u) & ~127u;
     const unsigned char *gbase = smem_dyn + (sbase - smem_u32(smem_dyn));
@@ -315,7 +343,11 @@ k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMa
         const bool in_xA = validA && ((i <= p.xlo) || (i >= p.xhi));
         const bool in_xB = validB && ((i + 1 <= p.xlo) || (i + 1 >= p.xhi));
         const bool in_y = validA && ((j <= p.ylo) || (j >= p.yhi));
-        const bool warp_pml = __any_sync(0xffffffffu, in_xA || in_xB || in_y);
+        const bool ux = __any_sync(0xffffffffu, in_xA || in_xB), uy = __any_sync(0xffffffffu, in_y);   // warp-uniform
+        const bool warp_pml = ux || uy;
+        const int jc = min(j, p.ny);                                // y coefficients are read unconditionally
+        if (tile_xpml) fill_cx<TX, TX / 2 * TY>(p, Cx, i0, tid);
+        __syncthreads();
         // loop bounds of the four nests (i, j part; the k part is tested per plane)
         const bool do_nA = validA && (i <= p.nx - 1) && (j >= 2), do_nB = validB && (i + 1 <= p.nx - 1) && (j >= 2);   // :838-839
         const bool do_xyA = validA && (i >= 2) && (j <= p.ny - 1), do_xyB = validB && (j <= p.ny - 1);                 // :878-879
@@ -343,8 +375,8 @@ k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMa
             double mvA[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, mvB[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
             if (pml) {
                 if (z_pml) qz = ((long long)(shell_index(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1);
-                load_memvars(p, 0, false, in_y, in_zA, 0, qy, qz, mvA);
-                load_memvars(p, 0, false, in_y && validB, in_zB, 0, qy + 1, qz + 1, mvB);
+                load_memvars(p, 0, false, uy && in_y, in_zA, 0, qy, qz, mvA);
+                load_memvars(p, 0, false, uy && in_y && validB, in_zB, 0, qy + 1, qz + 1, mvB);
             }
             RingPos rn1 = rn;
             rn1.advance(SN);
@@ -375,15 +407,17 @@ k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMa
 
             StressVals a{sxx.x, syy.x, szz.x, sxy.x, sxz.x, syz.x}, b{sxx.y, syy.y, szz.y, sxy.y, sxz.y, syz.y};
             if (pml) {
-                stress_point<true, KUNIT>(p, i, j, kg, do_nA, do_xyA, do_xzA, do_yzA, in_xA, in_y, in_zA, qxr + sxA, qy, qz, mvA,
-                                          vx_c.x, vx_c.y, vx_jp.x, vx_n.x, vy_c.x, vy_imA, vy_jm.x, vy_n.x, vz_c.x, vz_imA, vz_jp.x, vz_mA, a);
-                stress_point<true, KUNIT>(p, i + 1, j, kg, do_nB, do_xyB, do_xzB, do_yzB, in_xB, in_y && validB, in_zB, qxr + sxB, qy + 1, qz + 1, mvB,
-                                          vx_c.y, vx_ipB, vx_jp.y, vx_n.y, vy_c.y, vy_c.x, vy_jm.y, vy_n.y, vz_c.y, vz_c.x, vz_jp.y, vz_mB, b);
+                stress_point<true, KUNIT, TX>(p, Cx, 2 * tx, jc, kg, do_nA, do_xyA, do_xzA, do_yzA, ux, uy, z_pml, in_xA, in_y, in_zA,
+                                              qxr + sxA, qy, qz, mvA,
+                                              vx_c.x, vx_c.y, vx_jp.x, vx_n.x, vy_c.x, vy_imA, vy_jm.x, vy_n.x, vz_c.x, vz_imA, vz_jp.x, vz_mA, a);
+                stress_point<true, KUNIT, TX>(p, Cx, 2 * tx + 1, jc, kg, do_nB, do_xyB, do_xzB, do_yzB, ux, uy, z_pml, in_xB, in_y && validB, in_zB,
+                                              qxr + sxB, qy + 1, qz + 1, mvB,
+                                              vx_c.y, vx_ipB, vx_jp.y, vx_n.y, vy_c.y, vy_c.x, vy_jm.y, vy_n.y, vz_c.y, vz_c.x, vz_jp.y, vz_mB, b);
             } else {
-                stress_point<false, KUNIT>(p, i, j, kg, do_nA, do_xyA, do_xzA, do_yzA, false, false, false, 0, 0, 0, mvA,
-                                           vx_c.x, vx_c.y, vx_jp.x, vx_n.x, vy_c.x, vy_imA, vy_jm.x, vy_n.x, vz_c.x, vz_imA, vz_jp.x, vz_mA, a);
-                stress_point<false, KUNIT>(p, i + 1, j, kg, do_nB, do_xyB, do_xzB, do_yzB, false, false, false, 0, 0, 0, mvB,
-                                           vx_c.y, vx_ipB, vx_jp.y, vx_n.y, vy_c.y, vy_c.x, vy_jm.y, vy_n.y, vz_c.y, vz_c.x, vz_jp.y, vz_mB, b);
+                stress_point<false, KUNIT, TX>(p, Cx, 0, jc, kg, do_nA, do_xyA, do_xzA, do_yzA, false, false, false, false, false, false, 0, 0, 0, mvA,
+                                               vx_c.x, vx_c.y, vx_jp.x, vx_n.x, vy_c.x, vy_imA, vy_jm.x, vy_n.x, vz_c.x, vz_imA, vz_jp.x, vz_mA, a);
+                stress_point<false, KUNIT, TX>(p, Cx, 0, jc, kg, do_nB, do_xyB, do_xzB, do_yzB, false, false, false, false, false, false, 0, 0, 0, mvB,
+                                               vx_c.y, vx_ipB, vx_jp.y, vx_n.y, vy_c.y, vy_c.x, vy_jm.y, vy_n.y, vz_c.y, vz_c.x, vz_jp.y, vz_mB, b);
             }
             vz_mA = vz_c.x; vz_mB = vz_c.y;
 
@@ -430,12 +464,12 @@ k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMa
 // maps: 0 sxx 1 syy 2 sxy 3 sxz 4 syz 5 szz 6 vx 7 vy 8 vz
 struct VelVals { double vx, vy, vz; };                           // in: old values, out: new values
 
-template <bool PML, bool KUNIT>
+template <bool PML, bool KUNIT, int CXW>
 __device__ __forceinline__ void velocity_point(
-    const Params3D &p, const int i, const int j, const int k, const int kg,
-    const bool do_vx, const bool do_vy, const bool do_vz, const bool edge_ij, const bool ebox_ij,
-    const bool src_ij, const bool in_x, const bool in_y, const bool in_z, const long long qx, const long long qy,
-    const long long qz, const double (&mv)[9],
+    const Params3D &p, const double *__restrict__ Cx, const int c, const int j, const int k, const int kg,
+    const bool do_vx, const bool do_vy, const bool do_vz, const bool edge_ij, const bool ebox_ij, const bool src_ij,
+    const bool ux, const bool uy, const bool uz, const bool in_x, const bool in_y, const bool in_z,
+    const long long qx, const long long qy, const long long qz, const double (&mv)[9],
     const double sxx_c, const double sxx_im, const double syy_c, const double syy_jp,
     const double sxy_c, const double sxy_jm, const double sxy_ip, const double sxz_c, const double sxz_ip,
     const double sxz_m, const double syz_c, const double syz_jm, const double syz_m, const double szz_c,
@@ -449,9 +483,9 @@ __device__ __forceinline__ void velocity_point(
             double value_dsigmaxy_dy = (sxy_c - sxy_jm) * ody;
             double value_dsigmaxz_dz = (sxz_c - sxz_m) * odz;
             if (PML) {
-                if (in_x) value_dsigmaxx_dx = cpml_apply<KUNIT>(p.mx[3], qx, mv[0], p.cx.b[i], p.cx.a[i], KUNIT ? 1.0 : p.cx.K[i], value_dsigmaxx_dx);
-                if (in_y) value_dsigmaxy_dy = cpml_apply<KUNIT>(p.my[3], qy, mv[3], p.cy.b[j], p.cy.a[j], KUNIT ? 1.0 : p.cy.K[j], value_dsigmaxy_dy);
-                if (in_z) value_dsigmaxz_dz = cpml_apply<KUNIT>(p.mz[3], qz, mv[6], p.cz.b[kg], p.cz.a[kg], KUNIT ? 1.0 : p.cz.K[kg], value_dsigmaxz_dz);
+                if (ux) value_dsigmaxx_dx = cpml_step<KUNIT>(p.mx[3], qx, in_x, mv[0], Cx[1 * CXW + c], Cx[0 * CXW + c], KUNIT ? 1.0 : Cx[2 * CXW + c], value_dsigmaxx_dx);
+                if (uy) value_dsigmaxy_dy = cpml_step<KUNIT>(p.my[3], qy, in_y, mv[3], p.cy.b[j], p.cy.a[j], KUNIT ? 1.0 : p.cy.K[j], value_dsigmaxy_dy);
+                if (uz) value_dsigmaxz_dz = cpml_step<KUNIT>(p.mz[3], qz, in_z, mv[6], p.cz.b[kg], p.cz.a[kg], KUNIT ? 1.0 : p.cz.K[kg], value_dsigmaxz_dz);
             }
             vx = dt_r * (value_dsigmaxx_dx + value_dsigmaxy_dy + value_dsigmaxz_dz) + vx;
         }
@@ -460,9 +494,9 @@ __device__ __forceinline__ void velocity_point(
             double value_dsigmayy_dy = (syy_jp - syy_c) * ody;
             double value_dsigmayz_dz = (syz_c - syz_m) * odz;
             if (PML) {
-                if (in_x) value_dsigmaxy_dx = cpml_apply<KUNIT>(p.mx[4], qx, mv[1], p.cx.b_half[i], p.cx.a_half[i], KUNIT ? 1.0 : p.cx.K_half[i], value_dsigmaxy_dx);
-                if (in_y) value_dsigmayy_dy = cpml_apply<KUNIT>(p.my[4], qy, mv[4], p.cy.b_half[j], p.cy.a_half[j], KUNIT ? 1.0 : p.cy.K_half[j], value_dsigmayy_dy);
-                if (in_z) value_dsigmayz_dz = cpml_apply<KUNIT>(p.mz[4], qz, mv[7], p.cz.b[kg], p.cz.a[kg], KUNIT ? 1.0 : p.cz.K[kg], value_dsigmayz_dz);
+                if (ux) value_dsigmaxy_dx = cpml_step<KUNIT>(p.mx[4], qx, in_x, mv[1], Cx[4 * CXW + c], Cx[3 * CXW + c], KUNIT ? 1.0 : Cx[5 * CXW + c], value_dsigmaxy_dx);
+                if (uy) value_dsigmayy_dy = cpml_step<KUNIT>(p.my[4], qy, in_y, mv[4], p.cy.b_half[j], p.cy.a_half[j], KUNIT ? 1.0 : p.cy.K_half[j], value_dsigmayy_dy);
+                if (uz) value_dsigmayz_dz = cpml_step<KUNIT>(p.mz[4], qz, in_z, mv[7], p.cz.b[kg], p.cz.a[kg], KUNIT ? 1.0 : p.cz.K[kg], value_dsigmayz_dz);
             }
             vy = dt_r * (value_dsigmaxy_dx + value_dsigmayy_dy + value_dsigmayz_dz) + vy;
         }
@@ -472,9 +506,9 @@ __device__ __forceinline__ void velocity_point(
         double value_dsigmayz_dy = (syz_c - syz_jm) * ody;
         double value_dsigmazz_dz = (szz_n - szz_c) * odz;
         if (PML) {
-            if (in_x) value_dsigmaxz_dx = cpml_apply<KUNIT>(p.mx[5], qx, mv[2], p.cx.b_half[i], p.cx.a_half[i], KUNIT ? 1.0 : p.cx.K_half[i], value_dsigmaxz_dx);
-            if (in_y) value_dsigmayz_dy = cpml_apply<KUNIT>(p.my[5], qy, mv[5], p.cy.b[j], p.cy.a[j], KUNIT ? 1.0 : p.cy.K[j], value_dsigmayz_dy);
-            if (in_z) value_dsigmazz_dz = cpml_apply<KUNIT>(p.mz[5], qz, mv[8], p.cz.b_half[kg], p.cz.a_half[kg], KUNIT ? 1.0 : p.cz.K_half[kg], value_dsigmazz_dz);
+            if (ux) value_dsigmaxz_dx = cpml_step<KUNIT>(p.mx[5], qx, in_x, mv[2], Cx[4 * CXW + c], Cx[3 * CXW + c], KUNIT ? 1.0 : Cx[5 * CXW + c], value_dsigmaxz_dx);
+            if (uy) value_dsigmayz_dy = cpml_step<KUNIT>(p.my[5], qy, in_y, mv[5], p.cy.b[j], p.cy.a[j], KUNIT ? 1.0 : p.cy.K[j], value_dsigmayz_dy);
+            if (uz) value_dsigmazz_dz = cpml_step<KUNIT>(p.mz[5], qz, in_z, mv[8], p.cz.b_half[kg], p.cz.a_half[kg], KUNIT ? 1.0 : p.cz.K_half[kg], value_dsigmazz_dz);
         }
         vz = dt_r * (value_dsigmaxz_dx + value_dsigmayz_dy + value_dsigmazz_dz) + vz;
     }
@@ -488,25 +522,25 @@ __device__ __forceinline__ void velocity_point(
     if (edge_ij || kg == 1 || kg == p.nz) { vx = 0.0; vy = 0.0; vz = 0.0; }
     v.vx = vx; v.vy = vy; v.vz = vz;
 
-    // energy over the PML-free box, :1131-1177; reciprocals instead of the reference's
-    // divisions -- the energy sum is reduction-order dependent anyway (quirk B11)
+    // energy over the PML-free box, :1131-1177.  The trace is a reduction whose order differs
+    // from the reference anyway (quirk B11), so this part uses reciprocals and fused
+    // multiply-adds (half the FP64 instructions); it agrees with the oracle to ~1e-14.
     if (ebox_ij && kg >= p.npml + 1 && kg <= p.nz - p.npml) {
-        const double lam = p.lambda, mu = p.mu;
-        const double c2lm = 2.0 * (lam + mu);
-        const double inv_den = p.inv_den, inv_2mu = p.inv_2mu;
-        ekin += (0.5 * p.rho) * (vx * vx + vy * vy + vz * vz);
-        const double epsilon_xx = (c2lm * sxx_c - lam * syy_c - lam * szz_c) * inv_den;
-        const double epsilon_yy = (c2lm * syy_c - lam * sxx_c - lam * szz_c) * inv_den;
-        const double epsilon_zz = (c2lm * szz_c - lam * sxx_c - lam * syy_c) * inv_den;
-        const double epsilon_xy = sxy_c * inv_2mu;
-        const double epsilon_xz = sxz_c * inv_2mu;
-        const double epsilon_yz = syz_c * inv_2mu;
+        const double lam = p.lambda, c2lm = p.c2lm, inv_den = p.inv_den, inv_mu = p.inv_mu;
+        ekin = __fma_rn(p.half_rho, __fma_rn(vz, vz, __fma_rn(vy, vy, vx * vx)), ekin);
+        const double epsilon_xx = __fma_rn(-lam, szz_c, __fma_rn(-lam, syy_c, c2lm * sxx_c)) * inv_den;
+        const double epsilon_yy = __fma_rn(-lam, szz_c, __fma_rn(-lam, sxx_c, c2lm * syy_c)) * inv_den;
         // quirk B2 (:1169-1172): the reference adds epsilon_yy*sigmayy twice and never
         // epsilon_zz*sigmazz
-        const double third = p.energy_bug_compat ? epsilon_yy * syy_c : epsilon_zz * szz_c;
-        epot += 0.5 * (epsilon_xx * sxx_c + epsilon_yy * syy_c + third +
-                       2.0 * epsilon_xy * sxy_c + 2.0 * epsilon_xz * sxz_c +
-                       2.0 * epsilon_yz * syz_c);
+        double third;
+        if (p.energy_bug_compat) third = epsilon_yy * syy_c;
+        else third = __fma_rn(-lam, syy_c, __fma_rn(-lam, sxx_c, c2lm * szz_c)) * inv_den * szz_c;
+        // 2 * epsilon_ij * sigma_ij = sigma_ij^2 / mu
+        double acc = __fma_rn(epsilon_xx, sxx_c, __fma_rn(epsilon_yy, syy_c, third));
+        acc = __fma_rn(sxy_c * inv_mu, sxy_c, acc);
+        acc = __fma_rn(sxz_c * inv_mu, sxz_c, acc);
+        acc = __fma_rn(syz_c * inv_mu, syz_c, acc);
+        epot = __fma_rn(0.5, acc, epot);
     }
 }
 
@@ -526,6 +560,7 @@ k_velocity3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ Tma
     const uint32_t CSTAGE = CBYTES + 3 * XMB;
 
     __shared__ double red[2 * ((NT + 31) / 32)];
+    __shared__ double Cx[6 * TX];                                   // x coefficients of the tile's columns
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t sbase = (smem_u32(smem_dyn) + 127u) & ~127u;
     const unsigned char *gbase = smem_dyn + (sbase - smem_u32(smem_dyn));
@@ -600,7 +635,11 @@ k_velocity3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ Tma
         const bool in_xA = validA && ((i <= p.xlo) || (i >= p.xhi));
         const bool in_xB = validB && ((i + 1 <= p.xlo) || (i + 1 >= p.xhi));
         const bool in_y = validA && ((j <= p.ylo) || (j >= p.yhi));
-        const bool warp_pml = __any_sync(0xffffffffu, in_xA || in_xB || in_y);
+        const bool ux = __any_sync(0xffffffffu, in_xA || in_xB), uy = __any_sync(0xffffffffu, in_y);   // warp-uniform
+        const bool warp_pml = ux || uy;
+        const int jc = min(j, p.ny);
+        if (tile_xpml) fill_cx<TX, NT>(p, Cx, i0, tid);
+        __syncthreads();
         const bool do_vxA = validA && (i >= 2) && (j >= 2), do_vxB = validB && (j >= 2);                                         // :978-979
         const bool do_vyA = validA && (i <= p.nx - 1) && (j <= p.ny - 1), do_vyB = validB && (i + 1 <= p.nx - 1) && (j <= p.ny - 1);   // :998-999
         const bool do_vzA = validA && (i <= p.nx - 1) && (j >= 2), do_vzB = validB && (i + 1 <= p.nx - 1) && (j >= 2);           // :1033-1034
@@ -634,8 +673,8 @@ k_velocity3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ Tma
             double mvA[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, mvB[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
             if (pml) {
                 if (z_pml) qz = ((long long)(shell_index(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1);
-                load_memvars(p, 3, false, in_y, in_zA, 0, qy, qz, mvA);
-                load_memvars(p, 3, false, in_y && validB, in_zB, 0, qy + 1, qz + 1, mvB);
+                load_memvars(p, 3, false, uy && in_y, in_zA, 0, qy, qz, mvA);
+                load_memvars(p, 3, false, uy && in_y && validB, in_zB, 0, qy + 1, qz + 1, mvB);
             }
             RingPos rn1 = rn;
             rn1.advance(SN);
@@ -666,19 +705,23 @@ k_velocity3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ Tma
 
             VelVals a{vx.x, vy.x, vz.x}, b{vx.y, vy.y, vz.y};
             if (pml) {
-                velocity_point<true, KUNIT>(p, i, j, k, kg, do_vxA, do_vyA, do_vzA, edgeA, eboxA, srcA, in_xA, in_y, in_zA, qxr + sxA, qy, qz, mvA,
-                                            sxx_c.x, sxx_imA, syy_c.x, syy_jp.x, sxy_c.x, sxy_jm.x, sxy_c.y, sxz_c.x, sxz_c.y, sxz_mA,
-                                            syz_c.x, syz_jm.x, syz_mA, szz_c.x, szz_n.x, a, ekin, epot);
-                velocity_point<true, KUNIT>(p, i + 1, j, k, kg, do_vxB, do_vyB, do_vzB, edgeB, eboxB, srcB, in_xB, in_y && validB, in_zB, qxr + sxB, qy + 1, qz + 1, mvB,
-                                            sxx_c.y, sxx_c.x, syy_c.y, syy_jp.y, sxy_c.y, sxy_jm.y, sxy_ipB, sxz_c.y, sxz_ipB, sxz_mB,
-                                            syz_c.y, syz_jm.y, syz_mB, szz_c.y, szz_n.y, b, ekin, epot);
+                velocity_point<true, KUNIT, TX>(p, Cx, 2 * tx, jc, k, kg, do_vxA, do_vyA, do_vzA, edgeA, eboxA, srcA, ux, uy, z_pml, in_xA, in_y, in_zA,
+                                                qxr + sxA, qy, qz, mvA,
+                                                sxx_c.x, sxx_imA, syy_c.x, syy_jp.x, sxy_c.x, sxy_jm.x, sxy_c.y, sxz_c.x, sxz_c.y, sxz_mA,
+                                                syz_c.x, syz_jm.x, syz_mA, szz_c.x, szz_n.x, a, ekin, epot);
+                velocity_point<true, KUNIT, TX>(p, Cx, 2 * tx + 1, jc, k, kg, do_vxB, do_vyB, do_vzB, edgeB, eboxB, srcB, ux, uy, z_pml, in_xB, in_y && validB, in_zB,
+                                                qxr + sxB, qy + 1, qz + 1, mvB,
+                                                sxx_c.y, sxx_c.x, syy_c.y, syy_jp.y, sxy_c.y, sxy_jm.y, sxy_ipB, sxz_c.y, sxz_ipB, sxz_mB,
+                                                syz_c.y, syz_jm.y, syz_mB, szz_c.y, szz_n.y, b, ekin, epot);
             } else {
-                velocity_point<false, KUNIT>(p, i, j, k, kg, do_vxA, do_vyA, do_vzA, edgeA, eboxA, srcA, false, false, false, 0, 0, 0, mvA,
-                                             sxx_c.x, sxx_imA, syy_c.x, syy_jp.x, sxy_c.x, sxy_jm.x, sxy_c.y, sxz_c.x, sxz_c.y, sxz_mA,
-                                             syz_c.x, syz_jm.x, syz_mA, szz_c.x, szz_n.x, a, ekin, epot);
-                velocity_point<false, KUNIT>(p, i + 1, j, k, kg, do_vxB, do_vyB, do_vzB, edgeB, eboxB, srcB, false, false, false, 0, 0, 0, mvB,
-                                             sxx_c.y, sxx_c.x, syy_c.y, syy_jp.y, sxy_c.y, sxy_jm.y, sxy_ipB, sxz_c.y, sxz_ipB, sxz_mB,
-                                             syz_c.y, syz_jm.y, syz_mB, szz_c.y, szz_n.y, b, ekin, epot);
+                velocity_point<false, KUNIT, TX>(p, Cx, 0, jc, k, kg, do_vxA, do_vyA, do_vzA, edgeA, eboxA, srcA, false, false, false, false, false, false,
+                                                 0, 0, 0, mvA,
+                                                 sxx_c.x, sxx_imA, syy_c.x, syy_jp.x, sxy_c.x, sxy_jm.x, sxy_c.y, sxz_c.x, sxz_c.y, sxz_mA,
+                                                 syz_c.x, syz_jm.x, syz_mA, szz_c.x, szz_n.x, a, ekin, epot);
+                velocity_point<false, KUNIT, TX>(p, Cx, 0, jc, k, kg, do_vxB, do_vyB, do_vzB, edgeB, eboxB, srcB, false, false, false, false, false, false,
+                                                 0, 0, 0, mvB,
+                                                 sxx_c.y, sxx_c.x, syy_c.y, syy_jp.y, sxy_c.y, sxy_jm.y, sxy_ipB, sxz_c.y, sxz_ipB, sxz_mB,
+                                                 syz_c.y, syz_jm.y, syz_mB, szz_c.y, szz_n.y, b, ekin, epot);
             }
             sxz_mA = sxz_c.x; sxz_mB = sxz_c.y; syz_mA = syz_c.x; syz_mB = syz_c.y;
 
