@@ -216,7 +216,7 @@ def run_b200(args):
         sol = P.make_solver_2d(p, s, device=local_rank)
         pts_step_rank = float(p.NX) * p.NY
     slab = GpuSlab(sol) if kind == "3d" else sol
-    drv = SlabDriver(slab, rank, world, sol.nzl) if (kind == "3d" and world > 1) else None
+    drv = SlabDriver(slab, rank, world, sol.nzl, halo=args.halo) if (kind == "3d" and world > 1) else None
     if kind != "3d":
         sol.set_stream(torch.cuda.current_stream().cuda_stream)
 
@@ -262,20 +262,23 @@ def run_b200(args):
     ms_max = float(tms.item())
     value = pts_step_rank * world * K / (ms_max * 1e-3) / 1e9
 
-    # ---- e2e: the same K steps through the public driver API with HOST buffers: upload the
-    # source series, run with the reference's display schedule (it == 5 and every IT_DISPLAY
-    # steps: max norm, seismograms, two snapshot planes come back), then pull the traces.
+    # ---- e2e: the same K steps through the public driver API with HOST buffers, structured
+    # like the reference's `do it` body: every step the host evaluates the source term
+    # (:1058-1071) and hands it over (pinned staging, H2D), runs the step, and queues the read
+    # of that step's energy and receiver sample (D2H); on the reference's display schedule
+    # (it == 5 and every IT_DISPLAY steps, :1183) the max norm, the seismograms and two snapshot
+    # planes come back; at the end the full traces.
     h2d = d2h = 0
     barrier()
     te0 = time.perf_counter()
-    fx = np.ascontiguousarray(s.force_x)
-    fy = np.ascontiguousarray(s.force_y)
-    sol.set_source_series(fx, fy)                       # H2D (pageable -> staged by the driver)
-    h2d += fx.nbytes + fy.nbytes
     a0 = W + K + 1
     for rel in range(1, K + 1):
         it = a0 + rel - 1
+        sol.set_source_step(it, s.force_x[it - 1], s.force_y[it - 1])
+        h2d += 16
         do_steps(it, it)
+        sol.fetch_step(it)
+        d2h += 32
         if rel == 5 or rel % p.IT_DISPLAY == 0:          # :1183
             vn = drv.maxnorm() if drv is not None else sol.get_maxnorm()
             d2h += 8
@@ -296,6 +299,9 @@ def run_b200(args):
     d2h += sx.nbytes + sy.nbytes + 3 * en[0].nbytes
     barrier()
     te1 = time.perf_counter()
+    last = sol.get_fetched_step(a0 + K - 1)
+    if not np.isfinite(last).all() or abs(last[0] + last[1] - en[0][a0 + K - 2]) > 1e-9 * max(1.0, abs(en[0][a0 + K - 2])):
+        raise SystemExit("per-step result read back through the pinned staging does not match the energy trace")
     te = torch.tensor([te1 - te0], dtype=torch.float64, device="cuda")
     td = torch.tensor([float(d2h)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -325,10 +331,13 @@ def run_b200(args):
                        "grid": [p.NX, p.NY, getattr(p, "NZ", 1)], "npoints_pml": p.NPOINTS_PML,
                        "deltat": p.DELTAT, "l2": "fields (>= 3 GB per rank) are far larger than the 126 MB L2; no flush needed",
                        "parallelism": f"z-slabs x{world}" if world > 1 else "single GPU",
-                       "halo": "NCCL send/recv of 6 planes per step and interface" if world > 1 else None,
+                       "halo": (None if world == 1 else
+                                "6 planes per step and interface stored straight into the neighbour GPU's halo planes "
+                                "by the update kernels over NVLink (CUDA IPC), ordered by device-side flags"
+                                if args.halo == "p2p" else "NCCL send/recv of 6 planes per step and interface"),
                        "fmad": False, "finite": finite,
                        "launch": sol.launch_info() if kind == "3d" else None},
-            "roofline": {"bound": "hbm", "kernel": "k_stress3d" if kind == "3d" else "k_stress2d",
+            "roofline": {"bound": "hbm", "kernel": ("k_stress3d_tma" if sol.launch_info()["tma"] else "k_stress3d") if kind == "3d" else "k_stress2d",
                          "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": (ach / peak) if ach else None, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": b_stress,
@@ -341,8 +350,9 @@ def run_b200(args):
                                   "frac": (b_stress + b_velocity) / (ms_max / K * 1e-3) / 1e9 / peak}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / K,
                     "d2h_bytes_per_step": float(td.item()) / K,
-                    "what": "cpml_set_source_series + K steps with the reference display schedule "
-                            "(max norm, seismograms, 2 snapshot planes at it==5 and every IT_DISPLAY) + final traces, host buffers"},
+                    "what": "per step: cpml_set_source_step (16 B pinned H2D) + the step + cpml_fetch_step (32 B D2H); "
+                            "reference display schedule (max norm, seismograms, 2 snapshot planes at it==5 and every "
+                            "IT_DISPLAY) + final traces, host buffers"},
             "gpu_launches": int(n_launch),
             "clocks": clocks,
         }
@@ -368,10 +378,12 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg4", "cfg2"])
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "sendrecv"],
+                    help="N > 1: peer stores from inside the kernels (default) or NCCL send/recv")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()
     if args.impl == "reference":

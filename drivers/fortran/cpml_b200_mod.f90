@@ -205,6 +205,29 @@ module cpml_b200
       integer(c_int32_t) :: ierr
     end function
 
+    function cpml_set_source_step(handle, it, force_x, force_y) bind(C, name='cpml_set_source_step') result(ierr)
+      import :: c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: it
+      real(c_double), value :: force_x, force_y
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_fetch_step(handle, it) bind(C, name='cpml_fetch_step') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: it
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_get_fetched_step(handle, it, out4) bind(C, name='cpml_get_fetched_step') result(ierr)
+      import :: c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: it
+      real(c_double), intent(out) :: out4(4)
+      integer(c_int32_t) :: ierr
+    end function
+
     function cpml_get_seismograms(handle, sisvx, sisvy) bind(C, name='cpml_get_seismograms') result(ierr)
       import :: c_int32_t, c_ptr, c_double
       type(c_ptr), value :: handle

@@ -126,6 +126,15 @@ int32_t cpml_set_material_2d(cpml_handle *h, const double *lambda, const double 
 int32_t cpml_set_source_series(cpml_handle *h, const double *force_x, const double *force_y,
                                int32_t n);
 
+/* Per-step forms for drivers that keep the reference's loop structure: the source term of
+ * step `it` (evaluated inside `do it`, :1058-1071) goes to the device through pinned staging,
+ * and the per-step outputs (kinetic and potential energy of this slab, :1179, and the sample
+ * of receiver 1, :1126-1127) come back the same way.  All copies are ordered on the handle's
+ * stream and do not synchronise; cpml_get_fetched_step is valid after cpml_synchronize. */
+int32_t cpml_set_source_step(cpml_handle *h, int32_t it, double force_x, double force_y);
+int32_t cpml_fetch_step(cpml_handle *h, int32_t it);
+int32_t cpml_get_fetched_step(cpml_handle *h, int32_t it, double *out4);
+
 /* ix_rec, iy_rec of :691-706 (1-based), n == NREC. */
 int32_t cpml_set_receivers(cpml_handle *h, const int32_t *ix_rec, const int32_t *iy_rec,
                            int32_t n);

@@ -15,9 +15,9 @@ for l in sys.stdin:
 '
 run() { wl=$1; shift; echo "$wl $*" >> $OUT; env "$@" timeout 300 python bench.py --workload $wl --steps 20 --warmup 3 --no-cpu-baseline 2>&1 | python -c "$fmt" >> $OUT; }
 for wl in cfg3 cfg4; do
-  for spec in "128 4 2" "64 8 2" "128 8 1" "104 8 1"; do
+  for spec in "128 7 1" "128 3 2" "128 8 1" "104 8 1"; do
     set -- $spec
-    for st in 2; do
+    for st in 2 3; do
       run $wl CPML_TX=$1 CPML_TY=$2 CPML_MINB=$3 CPML_STAGES=$st
     done
   done

@@ -80,6 +80,8 @@ struct cpml_handle {
     double *d_sisvx = nullptr, *d_sisvy = nullptr, *d_ek = nullptr, *d_ep = nullptr;
     double *d_partials = nullptr;
     unsigned long long *d_maxbits = nullptr;
+    double *pin_src = nullptr;     // pinned host staging: [2][nstep] per-step source increments
+    double *pin_out = nullptr;     // pinned host staging: [nstep][4] kinetic, potential, sisvx(it,1), sisvy(it,1)
 
     // launch geometry: 3-D kernels run once per region (interior box + PML shell boxes)
     std::vector<Box3D> regions;
@@ -225,6 +227,9 @@ static int32_t create_impl(cpml_handle *h)
     CK(cudaMalloc(&h->d_ix_rec, std::max(1, c.nrec) * sizeof(int)));
     CK(cudaMalloc(&h->d_iy_rec, std::max(1, c.nrec) * sizeof(int)));
     CK(cudaMalloc(&h->d_maxbits, sizeof(unsigned long long)));
+    CK(cudaMallocHost(&h->pin_src, 2 * nt * sizeof(double)));
+    CK(cudaMallocHost(&h->pin_out, 4 * nt * sizeof(double)));
+    memset(h->pin_out, 0, 4 * nt * sizeof(double));
 
     // ---- launch geometry of the 2-D kernels (the 3-D regions need the shells: finalize())
     if (c.ndim == 2) {
@@ -337,6 +342,7 @@ extern "C" int32_t cpml_destroy(cpml_handle *h)
     cudaFree(h->d_src_x); cudaFree(h->d_src_y); cudaFree(h->d_ix_rec); cudaFree(h->d_iy_rec);
     cudaFree(h->d_sisvx); cudaFree(h->d_sisvy); cudaFree(h->d_ek); cudaFree(h->d_ep);
     cudaFree(h->d_partials); cudaFree(h->d_maxbits);
+    cudaFreeHost(h->pin_src); cudaFreeHost(h->pin_out);
     for (auto e : h->ev) cudaEventDestroy(e);
     delete h;
     return CPML_OK;
@@ -458,6 +464,49 @@ extern "C" int32_t cpml_set_receivers(cpml_handle *h, const int32_t *ix_rec, con
 }
 
 
+// Per-step form of the source and of the loop's per-step outputs, for drivers that keep the
+// reference's structure (the source term is evaluated inside `do it`, :1058-1071, and
+// total_energy(it) / the seismogram samples are produced every step): pinned staging, copies
+// ordered on the handle's stream, no host synchronisation.
+extern "C" int32_t cpml_set_source_step(cpml_handle *h, int32_t it, double force_x, double force_y)
+{
+    if (!h) return CPML_EINVAL;
+    const cpml_config &c = h->cfg;
+    if (it < 1 || it > c.nstep) FAIL(CPML_EINVAL, "time step outside 1..NSTEP");
+    CK(cudaSetDevice(h->device));
+    double *sx = h->pin_src + (it - 1), *sy = h->pin_src + c.nstep + (it - 1);
+    *sx = c.ndim == 3 ? force_x * c.deltat / c.rho : force_x;      // :1080-1081
+    *sy = c.ndim == 3 ? force_y * c.deltat / c.rho : force_y;
+    CK(cudaMemcpyAsync(h->d_src_x + (it - 1), sx, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_src_y + (it - 1), sy, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    h->have_source = true;
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_fetch_step(cpml_handle *h, int32_t it)
+{
+    if (!h) return CPML_EINVAL;
+    const cpml_config &c = h->cfg;
+    if (it < 1 || it > c.nstep) FAIL(CPML_EINVAL, "time step outside 1..NSTEP");
+    CK(cudaSetDevice(h->device));
+    double *o = h->pin_out + 4 * (size_t)(it - 1);
+    CK(cudaMemcpyAsync(o + 0, h->d_ek + (it - 1), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(o + 1, h->d_ep + (it - 1), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (c.nrec > 0) {
+        CK(cudaMemcpyAsync(o + 2, h->d_sisvx + (it - 1), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(o + 3, h->d_sisvy + (it - 1), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_get_fetched_step(cpml_handle *h, int32_t it, double *out4)
+{
+    if (!h || !out4) return CPML_EINVAL;
+    if (it < 1 || it > h->cfg.nstep) FAIL(CPML_EINVAL, "time step outside 1..NSTEP");
+    memcpy(out4, h->pin_out + 4 * (size_t)(it - 1), 4 * sizeof(double));
+    return CPML_OK;
+}
+
 // ---- TMA path: descriptors and work decomposition -------------------------------------
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -495,11 +544,19 @@ static int32_t setup_tma(cpml_handle *h)
     // thread tile = TMA box.  Narrow grids (the reference's NX = 101) take one 104-wide tile
     // per row; wide grids 64 x 8.  CPML_TX / CPML_TY / CPML_STAGES override (bench sweeps).
     Tile3D &t = h->tile;
-    t.tx = env_int("CPML_TX", c.nx <= 104 ? 104 : 128);
-    t.ty = env_int("CPML_TY", c.nx <= 104 ? 8 : 4);
+    // default: the tile width that wastes the fewest columns (ties: the wider one), 8 rows;
+    // measured in profiles/r01_v5_tile_sweep.txt: 104 x 8 on the 101-wide default grid, 128 x 8
+    // on 1024-wide slabs, one 416- / 512-thread CTA per SM, two-plane ring
+    int best_tx = 128;
+    for (int cand : {104, 64}) {
+        const int w_best = (c.nx + best_tx - 1) / best_tx * best_tx, w = (c.nx + cand - 1) / cand * cand;
+        if (w < w_best) best_tx = cand;
+    }
+    t.tx = env_int("CPML_TX", best_tx);
+    t.ty = env_int("CPML_TY", 8);
     if (!tma_tile_supported(t.tx, t.ty)) FAIL(CPML_EINVAL, "unsupported CPML_TX x CPML_TY tile");
     t.stages = std::max(1, std::min(7, env_int("CPML_STAGES", 2)));
-    t.minb = std::max(1, std::min(4, env_int("CPML_MINB", 1)));
+    t.minb = std::max(1, std::min(4, env_int("CPML_MINB", t.tx == 64 ? 2 : 1)));
     t.xm_bytes = h->shell[0].size() > 0 ? round_up(t.ty * h->sxp * 8, 128) : 0;
     t.ntx = (c.nx + t.tx - 1) / t.tx;
     t.nty = (c.ny + t.ty - 1) / t.ty;

@@ -59,6 +59,9 @@ SYMBOLS = {
     "cpml_set_profiles": (C.c_int32, [_H, C.c_int32] + [_dp] * 6 + [C.c_int32]),
     "cpml_set_material_2d": (C.c_int32, [_H, _dp, _dp, _dp]),
     "cpml_set_source_series": (C.c_int32, [_H, _dp, _dp, C.c_int32]),
+    "cpml_set_source_step": (C.c_int32, [_H, C.c_int32, C.c_double, C.c_double]),
+    "cpml_fetch_step": (C.c_int32, [_H, C.c_int32]),
+    "cpml_get_fetched_step": (C.c_int32, [_H, C.c_int32, _dp]),
     "cpml_set_receivers": (C.c_int32, [_H, _ip, _ip, C.c_int32]),
     "cpml_run": (C.c_int32, [_H, C.c_int32, C.c_int32]),
     "cpml_step_stress": (C.c_int32, [_H, C.c_int32]),
@@ -233,6 +236,20 @@ class Solver:
         if fx.size != fy.size:
             raise CpmlError(CPML_EINVAL, "force_x and force_y differ in length")
         self._ck(self._L.cpml_set_source_series(self._h, _d(fx), _d(fy), fx.size))
+
+    def set_source_step(self, it, force_x, force_y):
+        """force_x(it), force_y(it) of :1058-1071 for one step (pinned staging, asynchronous)."""
+        self._ck(self._L.cpml_set_source_step(self._h, it, float(force_x), float(force_y)))
+
+    def fetch_step(self, it):
+        """Queue the device-to-host copy of step `it`'s energy and receiver-1 sample."""
+        self._ck(self._L.cpml_fetch_step(self._h, it))
+
+    def get_fetched_step(self, it):
+        """(kinetic, potential, sisvx(it,1), sisvy(it,1)) of a fetched step; valid after synchronize()."""
+        out = np.zeros(4)
+        self._ck(self._L.cpml_get_fetched_step(self._h, it, _d(out)))
+        return out
 
     def set_receivers(self, ix_rec, iy_rec):
         ix = np.ascontiguousarray(ix_rec, dtype=np.int32)
