@@ -27,16 +27,17 @@
 #define PI 3.141592653589793238462643 /* 3D-iso :199 */
 
 #include <time.h>
-static int g_warmup_steps = 0;
-static double g_loop_seconds = 0.0;
-static double now_seconds(void)
+/* shared with cpml_oracle_visco.c (oracle_internal.h) */
+int oracle_g_warmup_steps = 0;
+double oracle_g_loop_seconds = 0.0;
+double oracle_now_seconds(void)
 {
     struct timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
     return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
-void oracle_set_warmup_steps(int w) { g_warmup_steps = w > 0 ? w : 0; }
-double oracle_last_loop_seconds(void) { return g_loop_seconds; }
+void oracle_set_warmup_steps(int w) { oracle_g_warmup_steps = w > 0 ? w : 0; }
+double oracle_last_loop_seconds(void) { return oracle_g_loop_seconds; }
 
 int oracle_num_threads(void)
 {
@@ -74,9 +75,25 @@ void oracle_pml_profile(int n, double delta, double deltat, int npoints_pml,
                         double *a, double *b, double *K,
                         double *a_half, double *b_half, double *K_half)
 {
-    /* :402, :413 */
+    oracle_pml_profile_visco(n, delta, deltat, npoints_pml, use_pml_min, use_pml_max, cp, 1.0, rcoef,
+                             npower, k_max_pml, alpha_max_pml, origin_top_uses_n, clamp_alpha,
+                             a, b, K, a_half, b_half, K_half);
+}
+
+/* The same text with the viscoelastic program's d0 (3D-visco :547-549):
+ *   d0 = -(NPOWER+1) * cp * dsqrt(taumax) * log(Rcoef) / (2 * thickness)
+ * sqrt_taumax == 1.0 gives the isotropic formula bit for bit (x * 1.0 == x). */
+void oracle_pml_profile_visco(int n, double delta, double deltat, int npoints_pml,
+                              int use_pml_min, int use_pml_max,
+                              double cp, double sqrt_taumax, double rcoef, double npower,
+                              double k_max_pml, double alpha_max_pml,
+                              int origin_top_uses_n, int clamp_alpha,
+                              double *a, double *b, double *K,
+                              double *a_half, double *b_half, double *K_half)
+{
+    /* :402, :413 ; 3D-visco :547 */
     double thickness = npoints_pml * delta;
-    double d0 = -(npower + 1) * cp * log(rcoef) / (2.0 * thickness);
+    double d0 = -(npower + 1) * cp * sqrt_taumax * log(rcoef) / (2.0 * thickness);
     /* :455-456 (2D-4th :401 for the quirk) */
     double originleft = thickness;
     double originright = (origin_top_uses_n ? n : (n - 1)) * delta - thickness;
@@ -242,9 +259,9 @@ int oracle_run_2d(const oracle2d_config *cfg,
     const int eby0 = fourth ? NPOINTS_PML : NPOINTS_PML + 1;
     const int eby1 = fourth ? NY - NPOINTS_PML + 1 : NY - NPOINTS_PML;
 
-    double t_loop_start = now_seconds();
+    double t_loop_start = oracle_now_seconds();
     for (int it = 1; it <= NSTEP; it++) {          /* 2D-2nd :550 */
-        if (it == g_warmup_steps + 1) t_loop_start = now_seconds();
+        if (it == oracle_g_warmup_steps + 1) t_loop_start = oracle_now_seconds();
 
         /* ---- sigma_xx, sigma_yy : 2D-2nd :556-580 ; 2D-4th :557-581 */
         for (int j = 2; j <= NY; j++) {
@@ -405,7 +422,7 @@ int oracle_run_2d(const oracle2d_config *cfg,
         }
     }
 
-    g_loop_seconds = now_seconds() - t_loop_start;
+    oracle_g_loop_seconds = oracle_now_seconds() - t_loop_start;
 
     if (velocnorm_final) {                          /* 2D-2nd :719 */
         double vmax = 0.0;
@@ -517,9 +534,9 @@ int oracle_run_3d_iso(const oracle3d_config *cfg,
     const int src_rank = NPROC > 1 ? rank_cut_plane : 0;
     const int src_klocal = NPROC > 1 ? NZ_LOCAL : NZ / 2;
 
-    double t_loop_start = now_seconds();
+    double t_loop_start = oracle_now_seconds();
     for (int it = 1; it <= NSTEP; it++) {          /* :802 */
-        if (it == g_warmup_steps + 1) t_loop_start = now_seconds();
+        if (it == oracle_g_warmup_steps + 1) t_loop_start = oracle_now_seconds();
 
         /* ---- halo exchange of v : :810-823.  MPI_SENDRECV with MPI_PROC_NULL at the
          * ends leaves the end halos untouched (zero). */
@@ -775,7 +792,7 @@ int oracle_run_3d_iso(const oracle3d_config *cfg,
         }
         total_energy[it - 1] = energy_sum;
     }
-    g_loop_seconds = now_seconds() - t_loop_start;
+    oracle_g_loop_seconds = oracle_now_seconds() - t_loop_start;
 
     /* ---- results */
     if (plane_vx) memcpy(plane_vx, &F3(S[src_rank].vx, 1, 1, src_klocal), PLANE * sizeof(double)); /* :1236 */

@@ -43,6 +43,17 @@ void oracle_pml_profile(int n, double delta, double deltat, int npoints_pml,
                         double *a, double *b, double *K,
                         double *a_half, double *b_half, double *K_half);
 
+/* Same profiles with the viscoelastic program's d0 = -(NPOWER+1)*cp*dsqrt(taumax)*log(Rcoef)/(2L)
+ * (seismic_CPML_3D_viscoelastic_MPI.f90:547-549; profiles :553-801, identical text otherwise;
+ * Rcoef = 1e-4 :541, K_MAX_PML = 7 :243).  sqrt_taumax = 1 is oracle_pml_profile. */
+void oracle_pml_profile_visco(int n, double delta, double deltat, int npoints_pml,
+                              int use_pml_min, int use_pml_max,
+                              double cp, double sqrt_taumax, double rcoef, double npower,
+                              double k_max_pml, double alpha_max_pml,
+                              int origin_top_uses_n, int clamp_alpha,
+                              double *a, double *b, double *K,
+                              double *a_half, double *b_half, double *K_half);
+
 /* Source time function, first derivative of a Gaussian.
  * Follows 3D-iso :1058-1071 / 2D-2nd :644-657.  force_x/force_y have length nstep
  * (entry it-1 holds the value used at time step it). */
@@ -126,6 +137,49 @@ int oracle_run_3d_iso(const oracle3d_config *cfg,
                       double *sisvx, double *sisvy, double *total_energy,
                       double *plane_vx, double *plane_vy,
                       double *fields_final, double *vnorm_final);
+
+/* ----------------------------------------------------------- 3-D viscoelastic */
+
+/* Nearest-grid-point search of 3D-visco :839-853: like oracle_find_receivers but the
+ * abscissa of grid point i is DELTAX*i (not i-1) and the targets are given explicitly
+ * (:832-837: (xs+500, ys+500), (xs, ys+2260), (xs+500, ys+2260)). */
+void oracle_find_receivers_visco(int nx, int ny, double deltax, double deltay, int nrec,
+                                 const double *xrec, const double *yrec,
+                                 int *ix_rec, int *iy_rec, double *dist_rec);
+
+typedef struct {
+    int nx, ny, nz;       /* global grid */
+    int nproc;            /* emulated MPI z-slabs (reference default 4, :158) */
+    double deltax, deltay, deltaz, deltat;
+    double lambda, mu, rho;   /* relaxed Lame parameters and density, :167-172 */
+    int nstep;
+    int npoints_pml;
+    int isource, jsource; /* 1-based; k of source = nz/2 (:479, :1332) */
+    int nrec;
+    /* N_SLS = 2 relaxation mechanisms (:189); nu1 = dilatation (QKappa), nu2 = shear (QMu) */
+    double tau_epsilon_nu1[2], tau_sigma_nu1[2], tau_epsilon_nu2[2], tau_sigma_nu2[2];
+    int complete_halos;   /* 0 = the reference's exchange (quirk B6: half of the 4th-order z halo is
+                             never received, so the result depends on nproc); 1 = every plane the
+                             stencils read is exchanged (nproc-independent; NOT the reference) */
+} oraclev3d_config;
+
+/* Runs time steps 1..nstep of seismic_CPML_3D_viscoelastic_MPI.f90:954-1430 with the MPI ranks
+ * emulated as nproc slabs (arrays (0:NX+1,0:NY+1,-1:NZ_LOCAL+2) per slab, :301-303).  Outputs:
+ * sisvx/sisvy (nstep*nrec), energy_total/kinetic/potential (nstep, :1425-1430); optional
+ * fields_final = the 9 global fields vx..sigmayz then the 6 sigma*_R (xx,yy,zz,xy,xz,yz), each
+ * nx*ny*nz (i = 1..nx, j = 1..ny, k = 1..nz) back to back; vnorm_final = max |v| (:1435). */
+int oracle_run_3d_visco(const oraclev3d_config *cfg,
+                        const double *a_x, const double *b_x, const double *K_x,
+                        const double *a_x_half, const double *b_x_half, const double *K_x_half,
+                        const double *a_y, const double *b_y, const double *K_y,
+                        const double *a_y_half, const double *b_y_half, const double *K_y_half,
+                        const double *a_z, const double *b_z, const double *K_z,
+                        const double *a_z_half, const double *b_z_half, const double *K_z_half,
+                        const double *force_x, const double *force_y,
+                        const int *ix_rec, const int *iy_rec,
+                        double *sisvx, double *sisvy,
+                        double *energy_total, double *energy_kinetic, double *energy_potential,
+                        double *fields_final, double *vnorm_final);
 
 /* Timing of the last oracle_run_* call: wall seconds of its time loop only (set-up and
  * allocation excluded), not counting the first `w` warm-up steps. */
