@@ -40,11 +40,27 @@ class Oracle3DConfig(C.Structure):
                 ("energy_bug_compat", C.c_int)]
 
 
+class OracleV3DConfig(C.Structure):
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("nproc", C.c_int),
+                ("deltax", C.c_double), ("deltay", C.c_double), ("deltaz", C.c_double),
+                ("deltat", C.c_double),
+                ("lambda_", C.c_double), ("mu", C.c_double), ("rho", C.c_double),
+                ("nstep", C.c_int), ("npoints_pml", C.c_int),
+                ("isource", C.c_int), ("jsource", C.c_int), ("nrec", C.c_int),
+                ("tau_epsilon_nu1", C.c_double * 2), ("tau_sigma_nu1", C.c_double * 2),
+                ("tau_epsilon_nu2", C.c_double * 2), ("tau_sigma_nu2", C.c_double * 2),
+                ("complete_halos", C.c_int)]
+
+
 def build(force: bool = False) -> None:
     """Compile both oracle libraries (no-op when they are already there)."""
     names = ["liboracle_golden.so", "liboracle_timed.so"]
+    srcs = ["cpml_oracle.c", "cpml_oracle_visco.c", "cpml_oracle.h", "oracle_internal.h", "Makefile"]
     if not force and all(os.path.exists(os.path.join(_HERE, n)) for n in names):
-        return
+        # prebuilt libraries travel to the GPU box; rebuild only when a source is newer
+        newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in srcs)
+        if all(os.path.getmtime(os.path.join(_HERE, n)) >= newest for n in names):
+            return
     subprocess.run(["make", "-C", _HERE, "-B" if force else "-s", "all"], check=True,
                    stdout=subprocess.DEVNULL)
 
@@ -71,6 +87,16 @@ def lib(kind: str = "golden") -> C.CDLL:
         L.oracle_run_3d_iso.restype = C.c_int
         L.oracle_run_3d_iso.argtypes = [C.POINTER(Oracle3DConfig)] + [_dp] * 18 + [_dp] * 2 + [_ip] * 2 \
             + [_dp] * 3 + [_dp] * 2 + [_dp] * 2
+        L.oracle_pml_profile_visco.restype = None
+        L.oracle_pml_profile_visco.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
+                                               C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                               C.c_double, C.c_int, C.c_int] + [_dp] * 6
+        L.oracle_find_receivers_visco.restype = None
+        L.oracle_find_receivers_visco.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
+                                                  _dp, _dp, _ip, _ip, _dp]
+        L.oracle_run_3d_visco.restype = C.c_int
+        L.oracle_run_3d_visco.argtypes = [C.POINTER(OracleV3DConfig)] + [_dp] * 18 + [_dp] * 2 + [_ip] * 2 \
+            + [_dp] * 5 + [_dp] * 2
         L.oracle_num_threads.restype = C.c_int
         L.oracle_set_warmup_steps.argtypes = [C.c_int]
         L.oracle_last_loop_seconds.restype = C.c_double
@@ -189,6 +215,65 @@ def run_3d_iso(*, nx, ny, nz, nproc, deltax, deltay, deltaz, deltat, lam, mu, la
     if want_fields:
         out.update(dict(zip(("vx", "vy", "vz", "sigmaxx", "sigmayy", "sigmazz", "sigmaxy",
                              "sigmaxz", "sigmayz"), fields)))
+    return out
+
+
+def pml_profile_visco(n, delta, deltat, npoints_pml, use_min=True, use_max=True, *, cp, sqrt_taumax,
+                      rcoef=0.0001, npower=2.0, k_max_pml=7.0, alpha_max_pml, clamp_alpha=False,
+                      kind="golden"):
+    """3D-visco :533-801 (d0 scaled by dsqrt(taumax), Rcoef = 1e-4, K_MAX_PML = 7)."""
+    out = {k: np.zeros(n) for k in _PK}
+    lib(kind).oracle_pml_profile_visco(n, delta, deltat, npoints_pml, int(use_min), int(use_max),
+                                       cp, sqrt_taumax, rcoef, npower, k_max_pml, alpha_max_pml,
+                                       0, int(clamp_alpha), *[_d(out[k]) for k in _PK])
+    return out
+
+
+def find_receivers_visco(nx, ny, deltax, deltay, xrec, yrec, kind="golden"):
+    xr, yr = _f64(xrec), _f64(yrec)
+    nrec = xr.size
+    ix, iy = np.zeros(nrec, dtype=np.int32), np.zeros(nrec, dtype=np.int32)
+    dist = np.zeros(nrec)
+    lib(kind).oracle_find_receivers_visco(nx, ny, deltax, deltay, nrec, _d(xr), _d(yr), _i(ix), _i(iy), _d(dist))
+    return ix, iy, dist
+
+
+VISCO_FIELDS = ("vx", "vy", "vz", "sigmaxx", "sigmayy", "sigmazz", "sigmaxy", "sigmaxz", "sigmayz",
+                "sigmaxx_R", "sigmayy_R", "sigmazz_R", "sigmaxy_R", "sigmaxz_R", "sigmayz_R")
+
+
+def run_3d_visco(*, nx, ny, nz, nproc, deltax, deltay, deltaz, deltat, lam, mu, rho, nstep, npoints_pml,
+                 isource, jsource, tau_epsilon_nu1, tau_sigma_nu1, tau_epsilon_nu2, tau_sigma_nu2,
+                 prof_x, prof_y, prof_z, force_x, force_y, ix_rec, iy_rec, complete_halos=False,
+                 want_fields=False, kind="golden", **_ignored):
+    nrec = len(ix_rec)
+    A2 = C.c_double * 2
+    cfg = OracleV3DConfig(nx, ny, nz, nproc, deltax, deltay, deltaz, deltat, lam, mu, rho, nstep,
+                          npoints_pml, isource, jsource, nrec, A2(*tau_epsilon_nu1), A2(*tau_sigma_nu1),
+                          A2(*tau_epsilon_nu2), A2(*tau_sigma_nu2), int(complete_halos))
+    px = [_f64(prof_x[k]) for k in _PK]
+    py = [_f64(prof_y[k]) for k in _PK]
+    pz = [_f64(prof_z[k]) for k in _PK]
+    assert px[0].size == nx and py[0].size == ny and pz[0].size == nz
+    fx, fy = _f64(force_x), _f64(force_y)
+    assert fx.size >= nstep and fy.size >= nstep
+    ixr = np.ascontiguousarray(ix_rec, dtype=np.int32)
+    iyr = np.ascontiguousarray(iy_rec, dtype=np.int32)
+    sisvx = np.zeros((nrec, nstep))
+    sisvy = np.zeros((nrec, nstep))
+    et, ek, ep = np.zeros(nstep), np.zeros(nstep), np.zeros(nstep)
+    fields = np.zeros((15, nz, ny, nx)) if want_fields else None
+    vnorm = C.c_double(0.0)
+    rc = lib(kind).oracle_run_3d_visco(C.byref(cfg), *[_d(p) for p in px], *[_d(p) for p in py],
+                                       *[_d(p) for p in pz], _d(fx), _d(fy), _i(ixr), _i(iyr),
+                                       _d(sisvx), _d(sisvy), _d(et), _d(ek), _d(ep), _d(fields),
+                                       C.byref(vnorm))
+    if rc != 0:
+        raise RuntimeError(f"oracle_run_3d_visco failed rc={rc}")
+    out = dict(sisvx=sisvx, sisvy=sisvy, total_energy=et, energy_kinetic=ek, energy_potential=ep,
+               vnorm=vnorm.value)
+    if want_fields:
+        out.update(dict(zip(VISCO_FIELDS, fields)))
     return out
 
 

@@ -46,6 +46,12 @@ def main():
     o = O.run_3d_iso(**refcfg.cfg3d(nx=30, ny=34, nz=32, nstep=120, npml=5, k_max=3.0), nproc=2)
     np.savez_compressed(os.path.join(HERE, "cpml3d_iso_kmax3.npz"), sisvx=o["sisvx"], sisvy=o["sisvy"],
                         total_energy=o["total_energy"])
+    # 3-D viscoelastic (fourth order, N_SLS = 2, Carcione 1993 relaxation times), reduced grid,
+    # 4 emulated slabs like the reference's NPROC = 4 (quirk B6 applies at the 3 interfaces)
+    o = O.run_3d_visco(**refcfg.cfgv3d(), nproc=4)
+    np.savez_compressed(os.path.join(HERE, "cpml3d_visco_small.npz"), sisvx=o["sisvx"], sisvy=o["sisvy"],
+                        total_energy=o["total_energy"], energy_kinetic=o["energy_kinetic"],
+                        energy_potential=o["energy_potential"])
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -71,3 +71,47 @@ def rel_l2(a, b):
     den = math.sqrt(float(np.sum(b * b)))
     num = math.sqrt(float(np.sum((a - b) ** 2)))
     return num / den if den > 0 else num
+
+
+# Carcione (1993) two-mechanism relaxation times quoted in the reference as fixed alternatives to
+# the SolvOpt fit (seismic_CPML_3D_viscoelastic_MPI.f90:402-413): Qkappa ~ 20, Qmu ~ 10.
+TAU_CARCIONE_1993 = dict(tau_epsilon_nu1=(0.0334, 0.0028), tau_sigma_nu1=(0.0303, 0.0025),
+                         tau_epsilon_nu2=(0.0352, 0.0029), tau_sigma_nu2=(0.0287, 0.0024))
+
+
+def visco_taumax_taumin(tau):
+    """3D-visco :450-456."""
+    tau1 = tau["tau_sigma_nu1"][0] / tau["tau_epsilon_nu1"][0]
+    tau2 = tau["tau_sigma_nu2"][0] / tau["tau_epsilon_nu2"][0]
+    tau3 = tau["tau_sigma_nu1"][1] / tau["tau_epsilon_nu1"][1]
+    tau4 = tau["tau_sigma_nu2"][1] / tau["tau_epsilon_nu2"][1]
+    inv = [1.0 / tau1, 1.0 / tau2, 1.0 / tau3, 1.0 / tau4]
+    return max(inv), min(inv)
+
+
+def cfgv3d(nx=38, ny=46, nz=40, nstep=120, npml=6, dt=4e-4, tau=None, rec_scale=None):
+    """seismic_CPML_3D_viscoelastic_MPI.f90 (:152-244) on a reduced grid, relaxation times given."""
+    tau = dict(TAU_CARCIONE_1993 if tau is None else tau)
+    dx = 4.0
+    cp, cs, rho = 3000.0, 2000.0, 2000.0
+    f0 = 18.0
+    t0 = 1.2 / f0
+    amax = 2.0 * PI * (f0 / 2.0)
+    taumax, _ = visco_taumax_taumin(tau)
+    sq = math.sqrt(taumax)
+    kw = dict(cp=cp, sqrt_taumax=sq, alpha_max_pml=amax)
+    px = O.pml_profile_visco(nx, dx, dt, npml, clamp_alpha=True, **kw)
+    py = O.pml_profile_visco(ny, dx, dt, npml, **kw)
+    pz = O.pml_profile_visco(nz, dx, dt, npml, **kw)
+    fx, fy = O.source_series(nstep, dt, f0, t0, 1e7, 0.0)           # ANGLE_FORCE = 0 (:212)
+    isrc = min(npml + 20, nx - npml - 3)                            # :205
+    jsrc = ny // 5 + 1                                              # :206
+    xs, ys = isrc * dx, jsrc * dx                                   # :207-208
+    sc = rec_scale if rec_scale is not None else min(1.0, (nx - isrc - 2) * dx / 500.0, (ny - jsrc - 2) * dx / 2260.0)
+    xrec = [xs + 500.0 * sc, xs, xs + 500.0 * sc]                   # :832-837
+    yrec = [ys + 500.0 * sc, ys + 2260.0 * sc, ys + 2260.0 * sc]
+    ix, iy, _ = O.find_receivers_visco(nx, ny, dx, dx, xrec, yrec)
+    return dict(nx=nx, ny=ny, nz=nz, deltax=dx, deltay=dx, deltaz=dx, deltat=dt,
+                lam=rho * (cp * cp - 2.0 * cs * cs), mu=rho * cs * cs, rho=rho, nstep=nstep,
+                npoints_pml=npml, isource=isrc, jsource=jsrc, prof_x=px, prof_y=py, prof_z=pz,
+                force_x=fx, force_y=fy, ix_rec=ix, iy_rec=iy, cp_eff=cp * sq, **tau)
