@@ -23,7 +23,9 @@ module cpml_b200
   integer(c_int32_t), parameter :: CPML_AXIS_X = 0, CPML_AXIS_Y = 1, CPML_AXIS_Z = 2
   integer(c_int32_t), parameter :: CPML_F_VX = 0, CPML_F_VY = 1, CPML_F_VZ = 2, CPML_F_SIGMAXX = 3, &
                                    CPML_F_SIGMAYY = 4, CPML_F_SIGMAZZ = 5, CPML_F_SIGMAXY = 6, &
-                                   CPML_F_SIGMAXZ = 7, CPML_F_SIGMAYZ = 8
+                                   CPML_F_SIGMAXZ = 7, CPML_F_SIGMAYZ = 8, &
+                                   CPML_F_SIGMAXX_R = 9, CPML_F_SIGMAYY_R = 10, CPML_F_SIGMAZZ_R = 11, &
+                                   CPML_F_SIGMAXY_R = 12, CPML_F_SIGMAXZ_R = 13, CPML_F_SIGMAYZ_R = 14
 
 ! struct cpml_config, field for field
   type, bind(C) :: cpml_config
@@ -38,7 +40,9 @@ module cpml_b200
     integer(c_int32_t) :: slab_rank
     integer(c_int32_t) :: device
     integer(c_int32_t) :: energy_bug_compat
-    integer(c_int32_t) :: reserved_i(4)
+    integer(c_int32_t) :: rheology
+    integer(c_int32_t) :: emulate_nproc
+    integer(c_int32_t) :: reserved_i(2)
     real(c_double) :: deltax, deltay, deltaz
     real(c_double) :: deltat
     real(c_double) :: lambda, mu, lambdaplustwomu, rho
@@ -97,6 +101,15 @@ module cpml_b200
       import :: c_int32_t, c_ptr, c_double
       type(c_ptr), value :: handle
       real(c_double), intent(in) :: lambda(*), mu(*), rho(*)
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_set_attenuation(handle, n_sls, tau_epsilon_nu1, tau_sigma_nu1, tau_epsilon_nu2, tau_sigma_nu2) &
+        bind(C, name='cpml_set_attenuation') result(ierr)
+      import :: c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: n_sls
+      real(c_double), intent(in) :: tau_epsilon_nu1(*), tau_sigma_nu1(*), tau_epsilon_nu2(*), tau_sigma_nu2(*)
       integer(c_int32_t) :: ierr
     end function
 

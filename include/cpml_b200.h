@@ -8,6 +8,7 @@
  *     seismic_CPML_3D_isotropic_MPI_OpenMP.f90:802      (3-D isotropic)
  *     seismic_CPML_2D_isotropic_second_order.f90:550    (2-D, 2nd order)
  *     seismic_CPML_2D_isotropic_fourth_order.f90:551    (2-D, 4th order)
+ *     seismic_CPML_3D_viscoelastic_MPI.f90:954          (3-D viscoelastic, 4th order)
  * Everything above that line (parameters, C-PML profiles, source law, receiver
  * search, CFL check) stays in the driver and is handed over through the setters;
  * everything the loop body touches lives on the GPU behind an opaque handle; the
@@ -58,6 +59,13 @@ extern "C" {
 #define CPML_F_SIGMAXY  6
 #define CPML_F_SIGMAXZ  7
 #define CPML_F_SIGMAYZ  8
+/* viscoelastic only: the relaxed stresses sigma*_R of 3D-visco :302 (energy only) */
+#define CPML_F_SIGMAXX_R 9
+#define CPML_F_SIGMAYY_R 10
+#define CPML_F_SIGMAZZ_R 11
+#define CPML_F_SIGMAXY_R 12
+#define CPML_F_SIGMAXZ_R 13
+#define CPML_F_SIGMAYZ_R 14
 
 typedef struct cpml_handle cpml_handle;
 
@@ -66,7 +74,8 @@ typedef struct cpml_handle cpml_handle;
  * bind(C)-friendly: int32 and double only. */
 typedef struct cpml_config {
     int32_t ndim;            /* 2 or 3                                                   */
-    int32_t order;           /* spatial order: 2 or 4 (ndim==2), 2 (ndim==3)             */
+    int32_t order;           /* spatial order: 2 or 4 (ndim==2); ndim==3: 2 (isotropic) or
+                                4 (viscoelastic)                                            */
     int32_t nx, ny, nz;      /* NX, NY, NZ: GLOBAL grid; nz ignored when ndim==2         */
     int32_t nstep;           /* NSTEP: capacity of the seismogram / energy traces        */
     int32_t npoints_pml;     /* NPOINTS_PML: only used for the energy box (:1135-1145)   */
@@ -79,7 +88,16 @@ typedef struct cpml_config {
     int32_t device;          /* CUDA device ordinal, -1 = current device                 */
     int32_t energy_bug_compat; /* 1 = reference 3-D potential energy (yy counted twice,
                                 zz omitted, :1169-1172); 0 = physical formula            */
-    int32_t reserved_i[4];
+    int32_t rheology;        /* 0 = isotropic elastic; 1 = viscoelastic, N_SLS = 2 standard
+                                linear solids (seismic_CPML_3D_viscoelastic_MPI.f90): needs
+                                ndim == 3, order == 4 and cpml_set_attenuation               */
+    int32_t emulate_nproc;   /* viscoelastic only: the reference's MPI exchange delivers only
+                                half of the z halo its 4th-order stencils read (3D-visco
+                                :962-975,:1229-1242 vs :991,:1149,:1189,:1251,:1271,:1294), so
+                                its result depends on NPROC.  n > 1 reproduces the reference run
+                                with NPROC = n (default 4, :158) on ANY number of GPU slabs;
+                                0 or 1 = every tap delivered (single-rank semantics)         */
+    int32_t reserved_i[2];
     double deltax, deltay, deltaz;   /* DELTAX, DELTAY, DELTAZ                           */
     double deltat;                   /* DELTAT                                           */
     /* homogeneous medium of the 3-D program (:139-144); the 2-D programs take arrays
@@ -121,6 +139,15 @@ int32_t cpml_set_profiles(cpml_handle *h, int32_t axis,
 int32_t cpml_set_material_2d(cpml_handle *h, const double *lambda, const double *mu,
                              const double *rho);
 
+/* Viscoelastic only: the relaxation times of the n_sls = 2 standard linear solids, as returned by
+ * compute_attenuation_coeffs at 3D-visco :439-443 (nu1 = dilatation / QKappa, nu2 = shear / QMu).
+ * The library derives inv_tau_sigma, phi_nu, Mu_nu and the unrelaxed Lame parameters with the
+ * reference's own expressions (:458-477, :982-987).  lambda, mu of cpml_config are the RELAXED
+ * parameters (:171-172); lambdaplustwomu is ignored (the loop uses lambda + 2 mu, :984). */
+int32_t cpml_set_attenuation(cpml_handle *h, int32_t n_sls,
+                             const double *tau_epsilon_nu1, const double *tau_sigma_nu1,
+                             const double *tau_epsilon_nu2, const double *tau_sigma_nu2);
+
 /* force_x(it), force_y(it) of :1058-1071 for it = 1..n (n <= NSTEP).  The kernel
  * adds force*DELTAT/rho like :1080-1081. */
 int32_t cpml_set_source_series(cpml_handle *h, const double *force_x, const double *force_y,
@@ -160,7 +187,7 @@ int32_t cpml_synchronize(cpml_handle *h);
 
 /* Device address and size of one z-plane of a field in the library's internal
  * (padded) layout, klocal = 0..NZ_LOCAL+1 (0 and NZ_LOCAL+1 are the halo planes,
- * 3D-iso :273).  Identical layout on every slab of the same grid, so a plane can be
+ * 3D-iso :273); viscoelastic: klocal = -1..NZ_LOCAL+2 (two halo planes per side, 3D-visco :301).  Identical layout on every slab of the same grid, so a plane can be
  * moved slab-to-slab with ncclSend/ncclRecv, cudaMemcpyPeer or CUDA-aware MPI. */
 int32_t cpml_halo_plane(cpml_handle *h, int32_t field, int32_t klocal,
                         void **device_ptr, int64_t *nbytes);

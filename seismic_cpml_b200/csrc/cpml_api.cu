@@ -40,8 +40,17 @@ struct cpml_handle {
     double *arena = nullptr;   // ONE allocation: nfields * field_doubles + the slab flags (so that a
                                // neighbour process maps everything with a single IPC handle)
     size_t arena_doubles = 0;
-    double *field_alloc[9] = {};
-    double *f0[9] = {};        // element (1,1,0) / (1,1)
+    double *field_alloc[15] = {};
+    double *f0[15] = {};       // element (1,1,0) / (1,1)
+    size_t flags_offset = 0;   // doubles from the arena start to the slab flags
+
+    // viscoelastic (rheology == 1): six (N_SLS = 2) strain memory variables, constants of 3D-visco :458-477
+    bool visco = false;
+    double2 *e0[6] = {};       // element (1,1,0) of e1, e11, e22, e12, e13, e23
+    bool have_attenuation = false;
+    double tau[4][2] = {};     // tau_epsilon_nu1, tau_sigma_nu1, tau_epsilon_nu2, tau_sigma_nu2
+    dim3 vgrid;
+    int vkchunk = 1, vtx = 32, vty = 8;
 
     // TMA path (3-D): descriptors of the two kernels' plane tiles, work decomposition
     bool use_tma = false;
@@ -149,7 +158,16 @@ static int32_t create_impl(cpml_handle *h)
 {
     const cpml_config &c = h->cfg;
     if (c.ndim != 2 && c.ndim != 3) FAIL(CPML_EINVAL, "ndim must be 2 or 3");
-    if (c.ndim == 3 && c.order != 2) FAIL(CPML_EINVAL, "3-D isotropic solver is second order (order must be 2)");
+    if (c.rheology != 0 && c.rheology != 1) FAIL(CPML_EINVAL, "rheology must be 0 (elastic) or 1 (viscoelastic)");
+    h->visco = c.rheology == 1;
+    if (h->visco && (c.ndim != 3 || c.order != 4)) FAIL(CPML_EINVAL, "the viscoelastic solver is 3-D, fourth order (ndim = 3, order = 4)");
+    if (c.ndim == 3 && !h->visco && c.order != 2) FAIL(CPML_EINVAL, "3-D isotropic solver is second order (order must be 2)");
+    if (c.emulate_nproc < 0) FAIL(CPML_EINVAL, "emulate_nproc must be >= 0");
+    if (c.emulate_nproc > 1) {
+        if (!h->visco) FAIL(CPML_EINVAL, "emulate_nproc applies to the viscoelastic solver only (the second-order exchange is complete)");
+        if (c.nz % c.emulate_nproc != 0 || c.nz / c.emulate_nproc < std::max(2, c.npoints_pml))
+            FAIL(CPML_ETOPOLOGY, "emulate_nproc must divide NZ into slabs of at least NPOINTS_PML planes (3D-visco :525-528)");
+    }
     if (c.ndim == 2 && c.order != 2 && c.order != 4) FAIL(CPML_EINVAL, "order must be 2 or 4");
     if (c.nx < 4 || c.ny < 4 || (c.ndim == 3 && c.nz < 4)) FAIL(CPML_EINVAL, "grid too small");
     if (c.nstep < 1 || c.nrec < 0 || c.npoints_pml < 0) FAIL(CPML_EINVAL, "bad nstep / nrec / npoints_pml");
@@ -165,6 +183,7 @@ static int32_t create_impl(cpml_handle *h)
         if (c.nz % c.nslabs != 0) FAIL(CPML_ETOPOLOGY, "NZ must be a multiple of nb_procs");
         h->nzl = c.nz / c.nslabs;
         if (h->nzl < c.npoints_pml) FAIL(CPML_ETOPOLOGY, "NZ_LOCAL must be greater than NPOINTS_PML");
+        if (h->visco && h->nzl < 2) FAIL(CPML_ETOPOLOGY, "viscoelastic slabs need at least two planes");
         if (c.ksource == 0 && c.nslabs > 1 && c.nslabs % 2 != 0) FAIL(CPML_ETOPOLOGY, "nb_procs must be even");
         h->ksrc_global = c.ksource == 0 ? c.nz / 2 : c.ksource;
         if (h->ksrc_global < 1 || h->ksrc_global > c.nz) FAIL(CPML_EINVAL, "ksource outside the grid");
@@ -189,7 +208,17 @@ static int32_t create_impl(cpml_handle *h)
     h->sm_count = prop.multiProcessorCount;
 
     // ---- field layout
-    if (c.ndim == 3) {
+    int ne = 0;           // double2 arrays (viscoelastic strain memory variables)
+    if (h->visco) {
+        // (0:NX+1, 0:NY+1, -1:NZ_LOCAL+2) of 3D-visco :301, ghost ring widened to two cells
+        const int xo = 16, gy = 2;
+        h->pitch = round_up(xo + c.nx + 2, 16);
+        h->plane = (long long)h->pitch * (c.ny + 2 * gy);
+        h->origin = h->plane + (long long)gy * h->pitch + xo;      // element (1,1,0); plane k = -1 comes first
+        h->field_doubles = (size_t)h->plane * (h->nzl + 4) + 16;
+        h->nfields = 15;
+        ne = 6;
+    } else if (c.ndim == 3) {
         h->pitch = round_up(c.nx, 16);
         h->plane = (long long)h->pitch * c.ny;
         h->origin = 16;   // leading pad so that (i-1) at the first element stays inside
@@ -204,13 +233,16 @@ static int32_t create_impl(cpml_handle *h)
         h->nfields = 5;
     }
     h->field_doubles = (h->field_doubles + 15) / 16 * 16;      // every field starts on a 128-byte line
-    h->arena_doubles = (size_t)h->nfields * h->field_doubles + 16;
+    h->flags_offset = (size_t)(h->nfields + 2 * ne) * h->field_doubles;
+    h->arena_doubles = h->flags_offset + 16;
     CK(cudaMalloc(&h->arena, h->arena_doubles * sizeof(double)));
     for (int f = 0; f < h->nfields; f++) {
         h->field_alloc[f] = h->arena + (size_t)f * h->field_doubles;
         h->f0[f] = h->field_alloc[f] + h->origin;
     }
-    h->flags = (unsigned long long *)(h->arena + (size_t)h->nfields * h->field_doubles);
+    for (int m = 0; m < ne; m++)
+        h->e0[m] = (double2 *)(h->arena + (size_t)(h->nfields + 2 * m) * h->field_doubles) + h->origin;
+    h->flags = (unsigned long long *)(h->arena + h->flags_offset);
     CK(cudaMalloc(&h->d_timeout, sizeof(unsigned int)));
     CK(cudaMemset(h->d_timeout, 0, sizeof(unsigned int)));
     if (c.ndim == 2)
@@ -424,6 +456,24 @@ extern "C" int32_t cpml_set_material_2d(cpml_handle *h, const double *lambda, co
     return CPML_OK;
 }
 
+extern "C" int32_t cpml_set_attenuation(cpml_handle *h, int32_t n_sls, const double *tau_epsilon_nu1,
+                                        const double *tau_sigma_nu1, const double *tau_epsilon_nu2,
+                                        const double *tau_sigma_nu2)
+{
+    if (!h) return CPML_EINVAL;
+    if (!h->visco) FAIL(CPML_EINVAL, "cpml_set_attenuation is for the viscoelastic solver (rheology = 1)");
+    if (n_sls != 2) FAIL(CPML_EINVAL, "the viscoelastic loop is written for N_SLS = 2 (3D-visco :189, :1003-1049)");
+    if (!tau_epsilon_nu1 || !tau_sigma_nu1 || !tau_epsilon_nu2 || !tau_sigma_nu2) FAIL(CPML_EINVAL, "null relaxation times");
+    const double *src[4] = {tau_epsilon_nu1, tau_sigma_nu1, tau_epsilon_nu2, tau_sigma_nu2};
+    for (int q = 0; q < 4; q++)
+        for (int l = 0; l < 2; l++) {
+            if (!(src[q][l] > 0.0) || !std::isfinite(src[q][l])) FAIL(CPML_EINVAL, "relaxation times must be positive");
+            h->tau[q][l] = src[q][l];
+        }
+    h->have_attenuation = true;
+    return CPML_OK;
+}
+
 extern "C" int32_t cpml_set_source_series(cpml_handle *h, const double *force_x, const double *force_y, int32_t n)
 {
     if (!h) return CPML_EINVAL;
@@ -627,6 +677,7 @@ static int32_t finalize(cpml_handle *h)
     if (!h->have_source) FAIL(CPML_ESTATE, "cpml_set_source_series has not been called");
     if (c.nrec > 0 && !h->have_receivers) FAIL(CPML_ESTATE, "cpml_set_receivers has not been called");
     if (c.ndim == 2 && !h->have_material) FAIL(CPML_ESTATE, "cpml_set_material_2d has not been called");
+    if (h->visco && !h->have_attenuation) FAIL(CPML_ESTATE, "cpml_set_attenuation has not been called");
     CK(cudaSetDevice(h->device));
 
     const Shell &sx = h->shell[0], &sy = h->shell[1];
@@ -673,7 +724,19 @@ static int32_t finalize(cpml_handle *h)
         h->nz_own[ax][0] = n0;
         h->nz_own[ax][1] = n1;
     }
-    if (c.ndim == 3) {
+    if (h->visco) {
+        visco_tile(&h->vtx, &h->vty);
+        // z chunks: short enough for several waves of blocks, long enough that the three extra
+        // velocity planes fetched to fill the z windows stay small against 87 words per point
+        int kc = env_int("CPML_VKCHUNK", 16);
+        kc = std::max(1, std::min(kc, h->nzl));
+        const int nzc = (h->nzl + kc - 1) / kc;
+        h->vkchunk = (h->nzl + nzc - 1) / nzc;
+        h->vgrid = dim3((c.nx + h->vtx - 1) / h->vtx, (c.ny + h->vty - 1) / h->vty, (h->nzl + h->vkchunk - 1) / h->vkchunk);
+        h->nblocks = (int)(h->vgrid.x * h->vgrid.y * h->vgrid.z);
+        CK(cudaMalloc(&h->d_partials, 2 * (size_t)h->nblocks * sizeof(double)));
+        CK(cudaMemset(h->d_partials, 0, 2 * (size_t)h->nblocks * sizeof(double)));
+    } else if (c.ndim == 3) {
         // CPML_KERNEL=reg selects the register-marching kernels of kernels_3d.cu (A/B runs)
         const char *kv = getenv("CPML_KERNEL");
         h->use_tma = !(kv && std::string(kv) == "reg");
@@ -761,9 +824,67 @@ static Params2D make_p2(cpml_handle *h, int it)
     return p;
 }
 
+static ParamsV3D make_pv(cpml_handle *h, int it)
+{
+    const cpml_config &c = h->cfg;
+    ParamsV3D p{};
+    p.nx = c.nx; p.ny = c.ny; p.nzl = h->nzl; p.nz = c.nz; p.koff = h->koff;
+    p.pitch = h->pitch; p.plane = h->plane;
+    p.vx = h->f0[0]; p.vy = h->f0[1]; p.vz = h->f0[2];
+    p.sxx = h->f0[3]; p.syy = h->f0[4]; p.szz = h->f0[5];
+    p.sxy = h->f0[6]; p.sxz = h->f0[7]; p.syz = h->f0[8];
+    p.rxx = h->f0[9]; p.ryy = h->f0[10]; p.rzz = h->f0[11];
+    p.rxy = h->f0[12]; p.rxz = h->f0[13]; p.ryz = h->f0[14];
+    p.e1 = h->e0[0]; p.e11 = h->e0[1]; p.e22 = h->e0[2]; p.e12 = h->e0[3]; p.e13 = h->e0[4]; p.e23 = h->e0[5];
+    p.xlo = h->shell[0].lo; p.xhi = h->shell[0].hi; p.sxp = h->sxp;
+    p.ylo = h->shell[1].lo; p.yhi = h->shell[1].hi; p.sy = h->sy;
+    p.zlo = h->shell[2].lo; p.zhi = h->shell[2].hi; p.zbase = h->zbase;
+    for (int m = 0; m < 6; m++) { p.mx[m] = h->mx[m]; p.my[m] = h->my[m]; p.mz[m] = h->mz[m]; }
+    p.cx = coef_view(h, 0); p.cy = coef_view(h, 1); p.cz = coef_view(h, 2);
+    p.odx = 1.0 / c.deltax; p.ody = 1.0 / c.deltay; p.odz = 1.0 / c.deltaz;   // 3D-visco :162-164
+    p.dt = c.deltat;
+    p.dt_over_rho = c.deltat / c.rho;                                          // :337
+    // :458-477 and :982-987, same expressions and order as the reference
+    const double ONE = 1.0, TWO = 2.0, DIM = 3.0;
+    const double *te1 = h->tau[0], *ts1 = h->tau[1], *te2 = h->tau[2], *ts2 = h->tau[3];
+    for (int l = 0; l < 2; l++) {
+        p.tauinv1[l] = -(ONE / ts1[l]);
+        p.tauinv2[l] = -(ONE / ts2[l]);
+        p.phi1[l] = (ONE - te1[l] / ts1[l]) / ts1[l];
+        p.phi2[l] = (ONE - te2[l] / ts2[l]) / ts2[l];
+        p.den1[l] = 1.0 - c.deltat * 0.5 * p.tauinv1[l];
+        p.den2[l] = 1.0 - c.deltat * 0.5 * p.tauinv2[l];
+    }
+    const double Mu_nu1 = ONE - (ONE - te1[0] / ts1[0]) - (ONE - te1[1] / ts1[1]);
+    const double Mu_nu2 = ONE - (ONE - te2[0] / ts2[0]) - (ONE - te2[1] / ts2[1]);
+    const double mul_relaxed = c.mu, lambdal_relaxed = c.lambda;
+    p.lam = lambdal_relaxed; p.mu = mul_relaxed;
+    p.l2m_r = lambdal_relaxed + TWO * mul_relaxed;
+    p.lam_u = (lambdal_relaxed + 2.0 / DIM * mul_relaxed) * Mu_nu1 - 2.0 / DIM * mul_relaxed * Mu_nu2;
+    p.mu_u = mul_relaxed * Mu_nu2;
+    p.l2m_u = p.lam_u + TWO * p.mu_u;
+    p.lam23mu = lambdal_relaxed + 2.0 / DIM * mul_relaxed;
+    p.two_mu = TWO * mul_relaxed;
+    p.two_thirds_mu = TWO / DIM * mul_relaxed;
+    p.nzl_e = c.emulate_nproc > 1 ? c.nz / c.emulate_nproc : c.nz;
+    p.it = it;
+    p.isrc = c.isource; p.jsrc = c.jsource;
+    const int kl = h->ksrc_global - h->koff;
+    p.ksrc = (kl >= 1 && kl <= h->nzl) ? kl : 0;
+    p.src_x = h->d_src_x; p.src_y = h->d_src_y;
+    p.npml = c.npoints_pml;
+    p.half_rho = 0.5 * c.rho;
+    p.c2lm = 2.0 * (c.lambda + c.mu);
+    p.inv_den = 1.0 / (2.0 * c.mu * (3.0 * c.lambda + 2.0 * c.mu));
+    p.inv_2mu = 1.0 / (2.0 * c.mu);
+    p.partials = h->d_partials; p.nblocks = h->nblocks;
+    p.kchunk = h->vkchunk;
+    return p;
+}
+
 static unsigned long long *peer_flags(cpml_handle *h, int side)
 {
-    return (unsigned long long *)(h->peer_arena[side] + (size_t)h->nfields * h->field_doubles);
+    return (unsigned long long *)(h->peer_arena[side] + h->flags_offset);
 }
 
 static int32_t time_begin(cpml_handle *h, int kind)
@@ -800,6 +921,7 @@ static int32_t half_step(cpml_handle *h, int32_t it, int phase)
     rc = finalize(h); if (rc) return rc;
     CK(cudaSetDevice(h->device));
     const bool peers = h->cfg.ndim == 3 && (h->peer_on[0] || h->peer_on[1]);
+    if (peers && h->visco) FAIL(CPML_ESTATE, "the viscoelastic kernels exchange their halo planes through the driver (cpml_halo_plane)");
     if (peers) {
         if (!h->use_tma) FAIL(CPML_ESTATE, "peer stores need the TMA kernels (unset CPML_KERNEL=reg)");
         const int w = phase == 0 ? 0 : 2;
@@ -808,7 +930,11 @@ static int32_t half_step(cpml_handle *h, int32_t it, int phase)
         h->n_launches++;
     }
     rc = time_begin(h, phase); if (rc) return rc;
-    if (h->cfg.ndim == 3) {
+    if (h->visco) {
+        const ParamsV3D p = make_pv(h, it);
+        if (phase == 0) launch_vstress3d(p, h->vgrid, h->stream); else launch_vvelocity3d(p, h->vgrid, h->stream);
+        h->n_launches++;
+    } else if (h->cfg.ndim == 3) {
         const Params3D p = make_p3(h, it);
         if (h->use_tma) {
             if (phase == 0) CK(launch_stress3d_tma(p, h->maps_stress, h->tile, h->stream));
@@ -907,8 +1033,14 @@ extern "C" int32_t cpml_halo_plane(cpml_handle *h, int32_t field, int32_t klocal
 {
     if (!h) return CPML_EINVAL;
     if (h->cfg.ndim != 3) FAIL(CPML_EINVAL, "halo planes exist only in 3-D");
-    if (field < 0 || field >= 9 || klocal < 0 || klocal > h->nzl + 1 || !device_ptr || !nbytes) FAIL(CPML_EINVAL, "bad halo plane request");
-    *device_ptr = (void *)(h->f0[field] + (long long)klocal * h->plane);
+    const int hz = h->visco ? 2 : 1;
+    if (field < 0 || field >= 9 || klocal < 1 - hz || klocal > h->nzl + hz || !device_ptr || !nbytes) FAIL(CPML_EINVAL, "bad halo plane request");
+    if (h->visco) {
+        // the whole padded plane including its ghost rows: start of the row block of plane klocal
+        *device_ptr = (void *)(h->field_alloc[field] + (long long)(klocal + 1) * h->plane);
+    } else {
+        *device_ptr = (void *)(h->f0[field] + (long long)klocal * h->plane);
+    }
     *nbytes = (int64_t)h->plane * (int64_t)sizeof(double);
     return CPML_OK;
 }
@@ -918,6 +1050,19 @@ extern "C" int32_t cpml_copy_plane(cpml_handle *dst, int32_t klocal_dst, cpml_ha
     if (!dst || !src) return CPML_EINVAL;
     cpml_handle *h = dst;
     if (dst->cfg.ndim != 3 || src->cfg.ndim != 3) FAIL(CPML_EINVAL, "plane copies exist only in 3-D");
+    if (dst->visco != src->visco) FAIL(CPML_EINVAL, "slabs of different solvers");
+    if (dst->visco) {
+        if (field < 0 || field >= 9 || klocal_dst < -1 || klocal_dst > dst->nzl + 2 || klocal_src < -1 || klocal_src > src->nzl + 2 ||
+            dst->plane != src->plane)
+            FAIL(CPML_EINVAL, "bad plane copy request");
+        CK(cudaSetDevice(src->device));
+        CK(cudaStreamSynchronize(src->stream));
+        CK(cudaSetDevice(dst->device));
+        CK(cudaMemcpyPeerAsync(dst->field_alloc[field] + (long long)(klocal_dst + 1) * dst->plane, dst->device,
+                               src->field_alloc[field] + (long long)(klocal_src + 1) * src->plane, src->device,
+                               (size_t)dst->plane * sizeof(double), dst->stream));
+        return CPML_OK;
+    }
     if (dst->plane != src->plane || dst->cfg.nx != src->cfg.nx || dst->cfg.ny != src->cfg.ny) FAIL(CPML_EINVAL, "slabs of different grids");
     if (field < 0 || field >= 9 || klocal_dst < 0 || klocal_dst > dst->nzl + 1 || klocal_src < 0 || klocal_src > src->nzl + 1)
         FAIL(CPML_EINVAL, "bad plane copy request");
@@ -936,6 +1081,7 @@ extern "C" int32_t cpml_p2p_export(cpml_handle *h, void *blob, int64_t blob_capa
 {
     if (!h || !blob || !nbytes) return CPML_EINVAL;
     if (h->cfg.ndim != 3) FAIL(CPML_EINVAL, "slabs exist only in 3-D");
+    if (h->visco) FAIL(CPML_EINVAL, "peer stores are implemented for the isotropic kernels; viscoelastic slabs exchange planes through the driver");
     if (blob_capacity < (int64_t)sizeof(cudaIpcMemHandle_t)) FAIL(CPML_EINVAL, "blob too small (need 64 bytes)");
     CK(cudaSetDevice(h->device));
     cudaIpcMemHandle_t mh;
@@ -948,6 +1094,7 @@ extern "C" int32_t cpml_p2p_export(cpml_handle *h, void *blob, int64_t blob_capa
 static int32_t check_side(cpml_handle *h, int32_t side)
 {
     if (h->cfg.ndim != 3) FAIL(CPML_EINVAL, "slabs exist only in 3-D");
+    if (h->visco) FAIL(CPML_EINVAL, "peer stores are implemented for the isotropic kernels; viscoelastic slabs exchange planes through the driver");
     if (side != 0 && side != 1) FAIL(CPML_EINVAL, "side must be 0 (slab rank-1) or 1 (slab rank+1)");
     if ((side == 0 && h->cfg.slab_rank == 0) || (side == 1 && h->cfg.slab_rank == h->cfg.nslabs - 1))
         FAIL(CPML_ETOPOLOGY, "no neighbour on that side (MPI_PROC_NULL, 3D-iso :775-790)");
@@ -1013,6 +1160,11 @@ extern "C" int32_t cpml_get_launch_info(cpml_handle *h, int32_t *info, int32_t n
 {
     if (!h || !info) return CPML_EINVAL;
     int32_t rc = finalize(h); if (rc) return rc;
+    if (h->visco) {
+        const int32_t w[10] = {0, h->vtx, h->vty, 0, h->vkchunk, (int32_t)h->vgrid.z, h->nblocks, h->nblocks, h->nblocks, 0};
+        for (int q = 0; q < n && q < 10; q++) info[q] = w[q];
+        return CPML_OK;
+    }
     const Tile3D &t = h->tile;
     const int32_t v[10] = {h->use_tma ? 1 : 0, t.tx, t.ty, t.stages, t.kchunk, t.nzc, t.nitems, t.grid_stress, t.grid_velocity,
                            (h->peer_on[0] ? 1 : 0) + (h->peer_on[1] ? 2 : 0)};
@@ -1074,6 +1226,14 @@ extern "C" int32_t cpml_get_field(cpml_handle *h, int32_t field, double *out)
     if (field < 0 || field >= h->nfields) FAIL(CPML_EINVAL, "bad field id");
     CK(cudaSetDevice(h->device));
     if (c.ndim == 2) return cpml_get_plane(h, field, 0, out);
+    if (h->visco) {   // ghost rows between the planes: one 2-D copy per plane
+        for (int k = 1; k <= h->nzl; k++)
+            CK(cudaMemcpy2DAsync(out + (size_t)(k - 1) * c.nx * c.ny, (size_t)c.nx * sizeof(double),
+                                 h->f0[field] + (long long)k * h->plane, (size_t)h->pitch * sizeof(double),
+                                 (size_t)c.nx * sizeof(double), c.ny, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return CPML_OK;
+    }
     // rows of all owned planes are equally spaced (plane = pitch * ny): one 2-D copy
     CK(cudaMemcpy2DAsync(out, (size_t)c.nx * sizeof(double), h->f0[field] + h->plane, (size_t)h->pitch * sizeof(double),
                          (size_t)c.nx * sizeof(double), (size_t)c.ny * h->nzl, cudaMemcpyDeviceToHost, h->stream));
@@ -1133,7 +1293,14 @@ extern "C" int32_t cpml_algorithmic_bytes(cpml_handle *h, double *bytes_stress, 
     const double N = (double)c.nx * c.ny * h->nzl;
     const int (*nz)[2] = h->nz_own;
     double ws, wv;   // words
-    if (c.ndim == 3) {
+    if (h->visco) {
+        // stress: read vx,vy,vz; read+write 6 sigma, 6 sigma_R, 12 strain memory variables -> 3 + 2*24;
+        // velocity: read 6 sigma; read+write vx,vy,vz -> 6 + 2*3 (the energy is fused: potential part in
+        // the stress kernel, kinetic part in the velocity kernel); C-PML memory variables as isotropic
+        const double px = (double)c.ny * h->nzl, py = (double)c.nx * h->nzl, pz = (double)c.nx * c.ny;
+        ws = 51.0 * N + 2.0 * (px * (nz[0][1] + 2 * nz[0][0]) + py * (nz[1][0] + 2 * nz[1][1]) + pz * (nz[2][0] + 2 * nz[2][1]));
+        wv = 12.0 * N + 2.0 * (px * (nz[0][0] + 2 * nz[0][1]) + py * (2 * nz[1][0] + nz[1][1]) + pz * (2 * nz[2][0] + nz[2][1]));
+    } else if (c.ndim == 3) {
         // stress: read vx,vy,vz; read+write 6 sigma; memory variables per direction:
         //   x: dvx_dx (half), dvy_dx, dvz_dx (integer)   y: dvy_dy (int), dvx_dy, dvz_dy (half)
         //   z: dvz_dz (int), dvx_dz, dvy_dz (half)        -- each read + written

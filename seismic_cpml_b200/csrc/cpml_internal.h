@@ -117,6 +117,33 @@ struct Post3D {
     double *sisvx, *sisvy;
 };
 
+// ------------------------------------------------------------------ 3-D viscoelastic
+// seismic_CPML_3D_viscoelastic_MPI.f90: fourth order, N_SLS = 2.  Fields carry TWO z halo planes
+// per side (k = -1..NZ_LOCAL+2, 3D-visco :301) and a two-cell zero ghost ring in x and y (the
+// reference's (0:NX+1,0:NY+1) extents, widened so that discarded lanes stay in bounds).
+struct ParamsV3D {
+    int nx, ny, nzl, nz, koff, pitch;
+    long long plane;
+    double *vx, *vy, *vz, *sxx, *syy, *szz, *sxy, *sxz, *syz;   // element (1,1,0)
+    double *rxx, *ryy, *rzz, *rxy, *rxz, *ryz;                  // sigma*_R (:302)
+    double2 *e1, *e11, *e22, *e12, *e13, *e23;                  // (N_SLS = 2, ...) : both mechanisms of a point
+    int xlo, xhi, sxp, ylo, yhi, sy, zlo, zhi, zbase;
+    double *mx[6], *my[6], *mz[6];                              // same order as the isotropic kernels
+    AxisCoef cx, cy, cz;
+    double odx, ody, odz, dt, dt_over_rho;
+    // constants of :982-987 and :458-477, evaluated on the host in the reference's order
+    double lam, mu, l2m_r, lam23mu, two_mu, two_thirds_mu, lam_u, mu_u, l2m_u;
+    double phi1[2], phi2[2], tauinv1[2], tauinv2[2], den1[2], den2[2];   // den = 1 - dt*0.5*tauinv
+    int nzl_e;                // plane count of one EMULATED reference slab (quirk B6); nz: none
+    int it, isrc, jsrc, ksrc;
+    const double *src_x, *src_y;
+    int npml;
+    double half_rho, c2lm, inv_den, inv_2mu;
+    double *partials;         // [0, nblocks) kinetic (velocity kernel), [nblocks, 2 nblocks) potential (stress kernel)
+    int nblocks;
+    int kchunk;               // planes marched by one block
+};
+
 // ------------------------------------------------------------------ 2-D
 struct Params2D {
     int nx, ny, pitch;
@@ -159,6 +186,9 @@ cudaError_t launch_velocity3d_tma(const Params3D &p, const TmaMaps &tm, const Ti
 void launch_signal(unsigned long long *flag_lo, unsigned long long *flag_hi, unsigned long long value, cudaStream_t s);
 void launch_wait(const unsigned long long *flag_a, const unsigned long long *flag_b, unsigned long long value,
                  unsigned int *timeout_flag, cudaStream_t s);
+void launch_vstress3d(const ParamsV3D &p, dim3 grid, cudaStream_t s);
+void launch_vvelocity3d(const ParamsV3D &p, dim3 grid, cudaStream_t s);
+void visco_tile(int *tx, int *ty);
 void launch_stress2d(const Params2D &p, dim3 grid, dim3 block, cudaStream_t s);
 void launch_velocity2d(const Params2D &p, dim3 grid, dim3 block, cudaStream_t s);
 void launch_post2d(const Post2D &p, cudaStream_t s);

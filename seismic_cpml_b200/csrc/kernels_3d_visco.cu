@@ -1,0 +1,423 @@
+// 3-D viscoelastic C-PML kernels for sm_100a (fourth order in space, N_SLS = 2).
+//
+// Two fused kernels per time step replace the five loop nests, the Dirichlet pass and the
+// energy pass of seismic_CPML_3D_viscoelastic_MPI.f90:977-1430:
+//
+//   k_vstress3d    sigmaxx/yy/zz + e1,e11,e22 + sigma*_R (:977-1096), sigmaxy + e12 (:1098-1139),
+//                  sigmaxz + e13 and sigmayz + e23 (:1141-1223), and the POTENTIAL part of the
+//                  energy (:1401-1419), which only needs the stresses this kernel has just
+//                  produced -- so the six sigma*_R arrays are never read again in the step;
+//   k_vvelocity3d  vx/vy (:1244-1285), vz (:1287-1308), source (:1310-1335), Dirichlet on two
+//                  planes per face (:1337-1371), the KINETIC part of the energy (:1396-1397).
+// The step is finished by k_post3d (energy sums + seismogram sample), shared with the
+// isotropic solver.
+//
+// Mapping: one thread per (i,j) column, x across the warp, each block marches a chunk of z
+// planes.  The four-plane z windows of the fourth-order operator (vx, vy at k-1..k+2 and vz at
+// k-2..k+1 in the stress kernel; sigmaxz, sigmayz at k-2..k+1 and sigmazz at k-1..k+2 in the
+// velocity kernel) live in registers, so every plane is fetched from HBM once per kernel; the
+// radius-2 in-plane taps are re-read through L1.  The 24 (stress) / 3 (velocity) streamed
+// read-modify-write words per point use evict-first loads and stores; both relaxation mechanisms
+// of a memory variable sit next to each other (the reference's e(N_SLS,...) layout) and move as
+// one 16-byte access.  C-PML memory variables exist only inside the shells (K_MAX_PML = 7 there).
+//
+// Reference quirk B6: the MPI exchange of the reference delivers only half of the z
+// halo its stencils read; the slots never received stay zero.  With `nzl_e` = plane count of one
+// reference slab the same taps read zero here: f(k+1) of the backward z differences on the last
+// plane of a slab, f(k-1) of the forward z differences on the first plane of a slab.
+//
+// Compiled with -fmad=false, every division kept (/24, /K, /(1 - dt/2 tauinv)): velocities,
+// stresses and memory variables are bit-identical to an IEEE (non-FMA) build of the reference.
+#include "cpml_internal.h"
+
+namespace cpml {
+
+__device__ __forceinline__ double vld(const double *p) { return __ldcs(p); }
+__device__ __forceinline__ void vst(double *p, double v) { __stcs(p, v); }
+__device__ __forceinline__ double2 vld2(const double2 *p) { return __ldcs(p); }
+__device__ __forceinline__ void vst2(double2 *p, double2 v) { __stcs(p, v); }
+
+// memory_x = b * memory_x + a * value ; value / K + memory_x   (e.g. :993-999)
+__device__ __forceinline__ double vcpml(double *__restrict__ mem, long long q, double b, double a, double K, double value)
+{
+    double m = mem[q];
+    m = b * m + a * value;
+    mem[q] = m;
+    return value / K + m;
+}
+
+__device__ __forceinline__ int vshell(int i, int lo, int hi) { return i <= lo ? i - 1 : lo + (i - hi); }
+
+// (27 a - 27 b - c + d) * ONE_OVER_DELTA / 24   (:989-991)
+__device__ __forceinline__ double d4(double a, double b, double c, double d, double od)
+{
+    return (27.0 * a - 27.0 * b - c + d) * od / 24.0;
+}
+
+// Unp1 = (Un + deltat*(Sn + 0.5*tauinv*Un)) / (1 - deltat*0.5*tauinv)   (:1003-1009)
+__device__ __forceinline__ double evolve(double Un, double Sn, double tauinv, double den, double dt)
+{
+    const double tauinvUn = tauinv * Un;
+    return (Un + dt * (Sn + 0.5 * tauinvUn)) / den;
+}
+
+template <int NT>
+__device__ __forceinline__ double block_sum1(double a, double *smem /* NT/32 */)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+    const int t = threadIdx.y * blockDim.x + threadIdx.x;
+    const int w = t >> 5, l = t & 31;
+    if (l == 0) smem[w] = a;
+    __syncthreads();
+    if (w == 0) {
+        a = (l < NT / 32) ? smem[l] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+    }
+    return a;
+}
+
+template <int TX, int TY>
+__global__ void __launch_bounds__(TX *TY)
+k_vstress3d(const __grid_constant__ ParamsV3D p)
+{
+    __shared__ double red[TX * TY / 32];
+    const int i = blockIdx.x * TX + threadIdx.x + 1;
+    const int j = blockIdx.y * TY + threadIdx.y + 1;
+    double epot = 0.0;
+
+    if (i <= p.nx && j <= p.ny) {
+        const int kb = 1 + blockIdx.z * p.kchunk;
+        const int ke = min(p.nzl, kb + p.kchunk - 1);
+        const int pitch = p.pitch;
+        const long long pl = p.plane;
+        long long q = (long long)kb * pl + (long long)(j - 1) * pitch + (i - 1);
+
+        const bool in_x = (i <= p.xlo) || (i >= p.xhi);
+        const bool in_y = (j <= p.ylo) || (j >= p.yhi);
+        const int sx = in_x ? vshell(i, p.xlo, p.xhi) : 0;
+        const int sy = in_y ? vshell(j, p.ylo, p.yhi) : 0;
+
+        const bool do_n = (i <= p.nx - 1) && (j >= 2);     // :979-980
+        const bool do_xy = (i >= 2) && (j <= p.ny - 1);    // :1099-1100
+        const bool do_xz = (i >= 2);                       // :1143-1144
+        const bool do_yz = (j <= p.ny - 1);                // :1183-1184
+        const bool ebox_ij = (i >= p.npml) && (i <= p.nx - p.npml + 1) &&
+                             (j >= p.npml) && (j <= p.ny - p.npml + 1);            // :1391-1392
+
+        const double odx = p.odx, ody = p.ody, odz = p.odz, dt = p.dt;
+
+        double ax = 0, bx = 0, Kx = 1, axh = 0, bxh = 0, Kxh = 1, ay = 0, by = 0, Ky = 1, ayh = 0, byh = 0, Kyh = 1;
+        if (in_x) { ax = p.cx.a[i]; bx = p.cx.b[i]; Kx = p.cx.K[i]; axh = p.cx.a_half[i]; bxh = p.cx.b_half[i]; Kxh = p.cx.K_half[i]; }
+        if (in_y) { ay = p.cy.a[j]; by = p.cy.b[j]; Ky = p.cy.K[j]; ayh = p.cy.a_half[j]; byh = p.cy.b_half[j]; Kyh = p.cy.K_half[j]; }
+
+        // z windows
+        double vx_m = p.vx[q - pl], vx_c = p.vx[q], vx_p = p.vx[q + pl];
+        double vy_m = p.vy[q - pl], vy_c = p.vy[q], vy_p = p.vy[q + pl];
+        double vz_mm = p.vz[q - 2 * pl], vz_m = p.vz[q - pl], vz_c = p.vz[q];
+
+        for (int k = kb; k <= ke; ++k, q += pl) {
+            const int kg = k + p.koff;                      // :978
+            // ---- loads of this plane
+            const double vx_pp = p.vx[q + 2 * pl], vy_pp = p.vy[q + 2 * pl], vz_p = p.vz[q + pl];
+            const double vx_im1 = p.vx[q - 1], vx_ip1 = p.vx[q + 1], vx_ip2 = p.vx[q + 2];
+            const double vx_jm1 = p.vx[q - pitch], vx_jp1 = p.vx[q + pitch], vx_jp2 = p.vx[q + 2 * pitch];
+            const double vy_im2 = p.vy[q - 2], vy_im1 = p.vy[q - 1], vy_ip1 = p.vy[q + 1];
+            const double vy_jm2 = p.vy[q - 2 * pitch], vy_jm1 = p.vy[q - pitch], vy_jp1 = p.vy[q + pitch];
+            const double vz_im2 = p.vz[q - 2], vz_im1 = p.vz[q - 1], vz_ip1 = p.vz[q + 1];
+            const double vz_jm1 = p.vz[q - pitch], vz_jp1 = p.vz[q + pitch], vz_jp2 = p.vz[q + 2 * pitch];
+            double sxx = vld(p.sxx + q), syy = vld(p.syy + q), szz = vld(p.szz + q);
+            double sxy = vld(p.sxy + q), sxz = vld(p.sxz + q), syz = vld(p.syz + q);
+            double rxx = vld(p.rxx + q), ryy = vld(p.ryy + q), rzz = vld(p.rzz + q);
+            double rxy = vld(p.rxy + q), rxz = vld(p.rxz + q), ryz = vld(p.ryz + q);
+            double2 e1 = vld2(p.e1 + q), e11 = vld2(p.e11 + q), e22 = vld2(p.e22 + q);
+            double2 e12 = vld2(p.e12 + q), e13 = vld2(p.e13 + q), e23 = vld2(p.e23 + q);
+
+            const bool in_z = (kg <= p.zlo) || (kg >= p.zhi);
+            long long qx = 0, qy = 0, qz = 0;
+            double az = 0, bz = 0, Kz = 1, azh = 0, bzh = 0, Kzh = 1;
+            if (in_x) qx = ((long long)(k - 1) * p.ny + (j - 1)) * p.sxp + sx;
+            if (in_y) qy = ((long long)(k - 1) * p.sy + sy) * pitch + (i - 1);
+            if (in_z) {
+                qz = ((long long)(vshell(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1);
+                az = p.cz.a[kg]; bz = p.cz.b[kg]; Kz = p.cz.K[kg];
+                azh = p.cz.a_half[kg]; bzh = p.cz.b_half[kg]; Kzh = p.cz.K_half[kg];
+            }
+            // quirk B6: taps the reference's MPI exchange never delivers
+            const int kmod = kg % p.nzl_e;
+            const bool cut_up = (kmod == 0);                // last plane of a reference slab
+            const bool cut_dn = (kmod == 1);                // first plane of a reference slab
+
+            // ---- sigmaxx, sigmayy, sigmazz, e1, e11, e22, sigma*_R  (:977-1096)
+            if (do_n && kg >= 2) {                          // k2begin, :942-943
+                double duxdx = d4(vx_ip1, vx_c, vx_ip2, vx_im1, odx);
+                double duydy = d4(vy_c, vy_jm1, vy_jp1, vy_jm2, ody);
+                double duzdz = d4(vz_c, vz_m, cut_up ? 0.0 : vz_p, vz_mm, odz);
+                if (in_x) duxdx = vcpml(p.mx[0], qx, bxh, axh, Kxh, duxdx);
+                if (in_y) duydy = vcpml(p.my[0], qy, by, ay, Ky, duydy);
+                if (in_z) duzdz = vcpml(p.mz[0], qz, bz, az, Kz, duzdz);
+                const double div = duxdx + duydy + duzdz;
+
+                e1.x = evolve(e1.x, div * p.phi1[0], p.tauinv1[0], p.den1[0], dt);
+                e1.y = evolve(e1.y, div * p.phi1[1], p.tauinv1[1], p.den1[1], dt);
+                e11.x = evolve(e11.x, (duxdx - div / 3.0) * p.phi2[0], p.tauinv2[0], p.den2[0], dt);
+                e11.y = evolve(e11.y, (duxdx - div / 3.0) * p.phi2[1], p.tauinv2[1], p.den2[1], dt);
+                e22.x = evolve(e22.x, (duydy - div / 3.0) * p.phi2[0], p.tauinv2[0], p.den2[0], dt);
+                e22.y = evolve(e22.y, (duydy - div / 3.0) * p.phi2[1], p.tauinv2[1], p.den2[1], dt);
+                vst2(p.e1 + q, e1); vst2(p.e11 + q, e11); vst2(p.e22 + q, e22);
+
+                // relaxed moduli times the memory variables (:1054-1060)
+                sxx = sxx + dt * (p.lam23mu * (e1.x + e1.y) + p.two_mu * (e11.x + e11.y));
+                syy = syy + dt * (p.lam23mu * (e1.x + e1.y) + p.two_mu * (e22.x + e22.y));
+                szz = szz + dt * (p.l2m_r * (e1.x + e1.y) - p.two_thirds_mu * (e11.x + e11.y + e22.x + e22.y));
+                // unrelaxed elastic term (:1064-1077)
+                sxx = sxx + (p.l2m_u * duxdx + p.lam_u * duydy + p.lam_u * duzdz) * dt;
+                syy = syy + (p.lam_u * duxdx + p.l2m_u * duydy + p.lam_u * duzdz) * dt;
+                szz = szz + (p.lam_u * duxdx + p.lam_u * duydy + p.l2m_u * duzdz) * dt;
+                // relaxed stresses (:1079-1092)
+                rxx = rxx + (p.l2m_r * duxdx + p.lam * duydy + p.lam * duzdz) * dt;
+                ryy = ryy + (p.lam * duxdx + p.l2m_r * duydy + p.lam * duzdz) * dt;
+                rzz = rzz + (p.lam * duxdx + p.lam * duydy + p.l2m_r * duzdz) * dt;
+                vst(p.sxx + q, sxx); vst(p.syy + q, syy); vst(p.szz + q, szz);
+                vst(p.rxx + q, rxx); vst(p.ryy + q, ryy); vst(p.rzz + q, rzz);
+            }
+            // ---- sigmaxy, e12  (:1098-1139)
+            if (do_xy) {
+                double duydx = d4(vy_c, vy_im1, vy_ip1, vy_im2, odx);
+                double duxdy = d4(vx_jp1, vx_c, vx_jp2, vx_jm1, ody);
+                if (in_x) duydx = vcpml(p.mx[1], qx, bx, ax, Kx, duydx);
+                if (in_y) duxdy = vcpml(p.my[1], qy, byh, ayh, Kyh, duxdy);
+                const double g = duxdy + duydx;
+                e12.x = evolve(e12.x, g * p.phi2[0], p.tauinv2[0], p.den2[0], dt);
+                e12.y = evolve(e12.y, g * p.phi2[1], p.tauinv2[1], p.den2[1], dt);
+                vst2(p.e12 + q, e12);
+                sxy = sxy + dt * p.mu * (e12.x + e12.y);
+                sxy = sxy + p.mu_u * g * dt;
+                rxy = rxy + p.mu * g * dt;
+                vst(p.sxy + q, sxy); vst(p.rxy + q, rxy);
+            }
+            // ---- sigmaxz, e13 and sigmayz, e23  (:1141-1223)
+            if (kg <= p.nz - 1) {                           // kminus1end, :945-946
+                if (do_xz) {
+                    double duzdx = d4(vz_c, vz_im1, vz_ip1, vz_im2, odx);
+                    double duxdz = d4(vx_p, vx_c, vx_pp, cut_dn ? 0.0 : vx_m, odz);
+                    if (in_x) duzdx = vcpml(p.mx[2], qx, bx, ax, Kx, duzdx);
+                    if (in_z) duxdz = vcpml(p.mz[1], qz, bzh, azh, Kzh, duxdz);
+                    const double g = duxdz + duzdx;
+                    e13.x = evolve(e13.x, g * p.phi2[0], p.tauinv2[0], p.den2[0], dt);
+                    e13.y = evolve(e13.y, g * p.phi2[1], p.tauinv2[1], p.den2[1], dt);
+                    vst2(p.e13 + q, e13);
+                    sxz = sxz + dt * p.mu * (e13.x + e13.y);
+                    sxz = sxz + p.mu_u * g * dt;
+                    rxz = rxz + p.mu * g * dt;
+                    vst(p.sxz + q, sxz); vst(p.rxz + q, rxz);
+                }
+                if (do_yz) {
+                    double duzdy = d4(vz_jp1, vz_c, vz_jp2, vz_jm1, ody);
+                    double duydz = d4(vy_p, vy_c, vy_pp, cut_dn ? 0.0 : vy_m, odz);
+                    if (in_y) duzdy = vcpml(p.my[2], qy, byh, ayh, Kyh, duzdy);
+                    if (in_z) duydz = vcpml(p.mz[2], qz, bzh, azh, Kzh, duydz);
+                    const double g = duydz + duzdy;
+                    e23.x = evolve(e23.x, g * p.phi2[0], p.tauinv2[0], p.den2[0], dt);
+                    e23.y = evolve(e23.y, g * p.phi2[1], p.tauinv2[1], p.den2[1], dt);
+                    vst2(p.e23 + q, e23);
+                    syz = syz + dt * p.mu * (e23.x + e23.y);
+                    syz = syz + p.mu_u * g * dt;
+                    ryz = ryz + p.mu * g * dt;
+                    vst(p.syz + q, syz); vst(p.ryz + q, ryz);
+                }
+            }
+
+            // ---- potential energy over the PML-free box (:1387-1419); quirk B2: epsilon_yy *
+            // sigmayy_R is counted twice and the zz term is missing
+            if (ebox_ij && kg >= p.npml && kg <= p.nz - p.npml + 1) {
+                const double epsilon_xx = (p.c2lm * sxx - p.lam * syy - p.lam * szz) * p.inv_den;
+                const double epsilon_yy = (p.c2lm * syy - p.lam * sxx - p.lam * szz) * p.inv_den;
+                const double epsilon_xy = rxy * p.inv_2mu;
+                const double epsilon_xz = rxz * p.inv_2mu;
+                const double epsilon_yz = ryz * p.inv_2mu;
+                epot += 0.5 * (epsilon_xx * rxx + epsilon_yy * ryy + epsilon_yy * ryy +
+                               2.0 * epsilon_xy * rxy + 2.0 * epsilon_xz * rxz + 2.0 * epsilon_yz * ryz);
+            }
+
+            vx_m = vx_c; vx_c = vx_p; vx_p = vx_pp;
+            vy_m = vy_c; vy_c = vy_p; vy_p = vy_pp;
+            vz_mm = vz_m; vz_m = vz_c; vz_c = vz_p;
+        }
+    }
+
+    epot = block_sum1<TX * TY>(epot, red);
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        const int b = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        p.partials[p.nblocks + b] = epot;
+    }
+}
+
+template <int TX, int TY>
+__global__ void __launch_bounds__(TX *TY)
+k_vvelocity3d(const __grid_constant__ ParamsV3D p)
+{
+    __shared__ double red[TX * TY / 32];
+    const int i = blockIdx.x * TX + threadIdx.x + 1;
+    const int j = blockIdx.y * TY + threadIdx.y + 1;
+    double ekin = 0.0;
+
+    if (i <= p.nx && j <= p.ny) {
+        const int kb = 1 + blockIdx.z * p.kchunk;
+        const int ke = min(p.nzl, kb + p.kchunk - 1);
+        const int pitch = p.pitch;
+        const long long pl = p.plane;
+        long long q = (long long)kb * pl + (long long)(j - 1) * pitch + (i - 1);
+
+        const bool in_x = (i <= p.xlo) || (i >= p.xhi);
+        const bool in_y = (j <= p.ylo) || (j >= p.yhi);
+        const int sx = in_x ? vshell(i, p.xlo, p.xhi) : 0;
+        const int sy = in_y ? vshell(j, p.ylo, p.yhi) : 0;
+
+        const bool do_vx = (i >= 2) && (j >= 2);                    // :1246-1247
+        const bool do_vy = (i <= p.nx - 1) && (j <= p.ny - 1);      // :1266-1267
+        const bool do_vz = (i <= p.nx - 1) && (j >= 2);             // :1289-1290
+        const bool edge_ij = (i <= 1) || (i >= p.nx) || (j <= 1) || (j >= p.ny);   // :1340-1358 (two cells per face)
+        const bool ebox_ij = (i >= p.npml) && (i <= p.nx - p.npml + 1) &&
+                             (j >= p.npml) && (j <= p.ny - p.npml + 1);
+        const bool src_ij = (i == p.isrc) && (j == p.jsrc);
+
+        const double odx = p.odx, ody = p.ody, odz = p.odz, dt_r = p.dt_over_rho;
+
+        double ax = 0, bx = 0, Kx = 1, axh = 0, bxh = 0, Kxh = 1, ay = 0, by = 0, Ky = 1, ayh = 0, byh = 0, Kyh = 1;
+        if (in_x) { ax = p.cx.a[i]; bx = p.cx.b[i]; Kx = p.cx.K[i]; axh = p.cx.a_half[i]; bxh = p.cx.b_half[i]; Kxh = p.cx.K_half[i]; }
+        if (in_y) { ay = p.cy.a[j]; by = p.cy.b[j]; Ky = p.cy.K[j]; ayh = p.cy.a_half[j]; byh = p.cy.b_half[j]; Kyh = p.cy.K_half[j]; }
+
+        // z windows
+        double sxz_mm = p.sxz[q - 2 * pl], sxz_m = p.sxz[q - pl], sxz_c = p.sxz[q];
+        double syz_mm = p.syz[q - 2 * pl], syz_m = p.syz[q - pl], syz_c = p.syz[q];
+        double szz_m = p.szz[q - pl], szz_c = p.szz[q], szz_p = p.szz[q + pl];
+
+        for (int k = kb; k <= ke; ++k, q += pl) {
+            const int kg = k + p.koff;
+            // ---- loads of this plane
+            const double sxz_p = p.sxz[q + pl], syz_p = p.syz[q + pl], szz_pp = p.szz[q + 2 * pl];
+            const double sxx_im2 = p.sxx[q - 2], sxx_im1 = p.sxx[q - 1], sxx_c = p.sxx[q], sxx_ip1 = p.sxx[q + 1];
+            const double sxy_jm2 = p.sxy[q - 2 * pitch], sxy_jm1 = p.sxy[q - pitch], sxy_c = p.sxy[q], sxy_jp1 = p.sxy[q + pitch];
+            const double sxy_im1 = p.sxy[q - 1], sxy_ip1 = p.sxy[q + 1], sxy_ip2 = p.sxy[q + 2];
+            const double syy_jm1 = p.syy[q - pitch], syy_c = p.syy[q], syy_jp1 = p.syy[q + pitch], syy_jp2 = p.syy[q + 2 * pitch];
+            const double sxz_im1 = p.sxz[q - 1], sxz_ip1 = p.sxz[q + 1], sxz_ip2 = p.sxz[q + 2];
+            const double syz_jm2 = p.syz[q - 2 * pitch], syz_jm1 = p.syz[q - pitch], syz_jp1 = p.syz[q + pitch];
+            double vx = vld(p.vx + q), vy = vld(p.vy + q), vz = vld(p.vz + q);
+
+            const bool in_z = (kg <= p.zlo) || (kg >= p.zhi);
+            long long qx = 0, qy = 0, qz = 0;
+            double az = 0, bz = 0, Kz = 1, azh = 0, bzh = 0, Kzh = 1;
+            if (in_x) qx = ((long long)(k - 1) * p.ny + (j - 1)) * p.sxp + sx;
+            if (in_y) qy = ((long long)(k - 1) * p.sy + sy) * pitch + (i - 1);
+            if (in_z) {
+                qz = ((long long)(vshell(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1);
+                az = p.cz.a[kg]; bz = p.cz.b[kg]; Kz = p.cz.K[kg];
+                azh = p.cz.a_half[kg]; bzh = p.cz.b_half[kg]; Kzh = p.cz.K_half[kg];
+            }
+            const int kmod = kg % p.nzl_e;
+            const bool cut_up = (kmod == 0);
+            const bool cut_dn = (kmod == 1);
+
+            if (kg >= 2) {                                           // k2begin
+                if (do_vx) {                                         // :1244-1262
+                    double d1 = d4(sxx_c, sxx_im1, sxx_ip1, sxx_im2, odx);
+                    double d2 = d4(sxy_c, sxy_jm1, sxy_jp1, sxy_jm2, ody);
+                    double d3 = d4(sxz_c, sxz_m, cut_up ? 0.0 : sxz_p, sxz_mm, odz);
+                    if (in_x) d1 = vcpml(p.mx[3], qx, bx, ax, Kx, d1);
+                    if (in_y) d2 = vcpml(p.my[3], qy, by, ay, Ky, d2);
+                    if (in_z) d3 = vcpml(p.mz[3], qz, bz, az, Kz, d3);
+                    vx = dt_r * (d1 + d2 + d3) + vx;
+                }
+                if (do_vy) {                                         // :1266-1284
+                    double d1 = d4(sxy_ip1, sxy_c, sxy_ip2, sxy_im1, odx);
+                    double d2 = d4(syy_jp1, syy_c, syy_jp2, syy_jm1, ody);
+                    double d3 = d4(syz_c, syz_m, cut_up ? 0.0 : syz_p, syz_mm, odz);
+                    if (in_x) d1 = vcpml(p.mx[4], qx, bxh, axh, Kxh, d1);
+                    if (in_y) d2 = vcpml(p.my[4], qy, byh, ayh, Kyh, d2);
+                    if (in_z) d3 = vcpml(p.mz[4], qz, bz, az, Kz, d3);
+                    vy = dt_r * (d1 + d2 + d3) + vy;
+                }
+            }
+            if (do_vz && kg <= p.nz - 1) {                           // kminus1end, :1287-1308
+                double d1 = d4(sxz_ip1, sxz_c, sxz_ip2, sxz_im1, odx);
+                double d2 = d4(syz_c, syz_jm1, syz_jp1, syz_jm2, ody);
+                double d3 = d4(szz_p, szz_c, szz_pp, cut_dn ? 0.0 : szz_m, odz);
+                if (in_x) d1 = vcpml(p.mx[5], qx, bxh, axh, Kxh, d1);
+                if (in_y) d2 = vcpml(p.my[5], qy, by, ay, Ky, d2);
+                if (in_z) d3 = vcpml(p.mz[5], qz, bzh, azh, Kzh, d3);
+                vz = dt_r * (d1 + d2 + d3) + vz;
+            }
+
+            // source (:1332-1333), after the update of step it and before Dirichlet
+            if (src_ij && k == p.ksrc) {
+                vx = vx + p.src_x[p.it - 1];
+                vy = vy + p.src_y[p.it - 1];
+            }
+            // Dirichlet, two planes per face (:1337-1371); the ghost cells i,j = 0, N+1 and the
+            // outer halo planes are never written and stay zero
+            if (edge_ij || kg <= 1 || kg >= p.nz) { vx = 0.0; vy = 0.0; vz = 0.0; }
+
+            vst(p.vx + q, vx);
+            vst(p.vy + q, vy);
+            vst(p.vz + q, vz);
+
+            // kinetic energy over the PML-free box (:1387-1397)
+            if (ebox_ij && kg >= p.npml && kg <= p.nz - p.npml + 1)
+                ekin += p.half_rho * (vx * vx + vy * vy + vz * vz);
+
+            sxz_mm = sxz_m; sxz_m = sxz_c; sxz_c = sxz_p;
+            syz_mm = syz_m; syz_m = syz_c; syz_c = syz_p;
+            szz_m = szz_c; szz_c = szz_p; szz_p = szz_pp;
+        }
+    }
+
+    ekin = block_sum1<TX * TY>(ekin, red);
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        const int b = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        p.partials[b] = ekin;
+    }
+}
+
+// ---- launch dispatch ---------------------------------------------------------------
+
+static int g_vtx = 0, g_vty = 0;
+
+void visco_tile(int *tx, int *ty)
+{
+    if (!g_vtx) {
+        const char *sx = getenv("CPML_VTX"), *sy = getenv("CPML_VTY");
+        g_vtx = sx ? atoi(sx) : 32;
+        g_vty = sy ? atoi(sy) : 8;
+        const int key = g_vtx * 100 + g_vty;
+        if (key != 3208 && key != 3204 && key != 6404 && key != 6402 && key != 12802 && key != 1616) { g_vtx = 32; g_vty = 8; }
+    }
+    *tx = g_vtx; *ty = g_vty;
+}
+
+template <int TX, int TY>
+static void vlaunch(const ParamsV3D &p, dim3 grid, cudaStream_t s, bool stress)
+{
+    if (stress) k_vstress3d<TX, TY><<<grid, dim3(TX, TY), 0, s>>>(p);
+    else        k_vvelocity3d<TX, TY><<<grid, dim3(TX, TY), 0, s>>>(p);
+}
+
+static void vdispatch(const ParamsV3D &p, dim3 grid, cudaStream_t s, bool stress)
+{
+    int tx, ty;
+    visco_tile(&tx, &ty);
+    switch (tx * 100 + ty) {
+    case 3204:  vlaunch<32, 4>(p, grid, s, stress); break;
+    case 6404:  vlaunch<64, 4>(p, grid, s, stress); break;
+    case 6402:  vlaunch<64, 2>(p, grid, s, stress); break;
+    case 12802: vlaunch<128, 2>(p, grid, s, stress); break;
+    case 1616:  vlaunch<16, 16>(p, grid, s, stress); break;
+    default:    vlaunch<32, 8>(p, grid, s, stress); break;
+    }
+}
+
+void launch_vstress3d(const ParamsV3D &p, dim3 grid, cudaStream_t s) { vdispatch(p, grid, s, true); }
+void launch_vvelocity3d(const ParamsV3D &p, dim3 grid, cudaStream_t s) { vdispatch(p, grid, s, false); }
+
+}  // namespace cpml

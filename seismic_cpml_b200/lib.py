@@ -20,6 +20,7 @@ ERROR_NAMES = {0: "CPML_OK", 1: "CPML_EINVAL", 2: "CPML_ETOPOLOGY", 3: "CPML_ECF
                5: "CPML_ESTATE", 6: "CPML_ENOMEM"}
 AXIS_X, AXIS_Y, AXIS_Z = 0, 1, 2
 FIELDS_3D = ("vx", "vy", "vz", "sigmaxx", "sigmayy", "sigmazz", "sigmaxy", "sigmaxz", "sigmayz")
+FIELDS_3D_VISCO = FIELDS_3D + ("sigmaxx_R", "sigmayy_R", "sigmazz_R", "sigmaxy_R", "sigmaxz_R", "sigmayz_R")
 FIELDS_2D = ("vx", "vy", "sigmaxx", "sigmayy", "sigmaxy")
 PROFILE_KEYS = ("a", "b", "K", "a_half", "b_half", "K_half")
 
@@ -40,7 +41,8 @@ class CpmlConfig(C.Structure):
                 ("nstep", C.c_int32), ("npoints_pml", C.c_int32), ("nrec", C.c_int32),
                 ("isource", C.c_int32), ("jsource", C.c_int32), ("ksource", C.c_int32),
                 ("nslabs", C.c_int32), ("slab_rank", C.c_int32), ("device", C.c_int32),
-                ("energy_bug_compat", C.c_int32), ("reserved_i", C.c_int32 * 4),
+                ("energy_bug_compat", C.c_int32), ("rheology", C.c_int32),
+                ("emulate_nproc", C.c_int32), ("reserved_i", C.c_int32 * 2),
                 ("deltax", C.c_double), ("deltay", C.c_double), ("deltaz", C.c_double),
                 ("deltat", C.c_double),
                 ("lambda_", C.c_double), ("mu", C.c_double), ("lambdaplustwomu", C.c_double),
@@ -58,6 +60,7 @@ SYMBOLS = {
     "cpml_set_stream": (C.c_int32, [_H, C.c_void_p]),
     "cpml_set_profiles": (C.c_int32, [_H, C.c_int32] + [_dp] * 6 + [C.c_int32]),
     "cpml_set_material_2d": (C.c_int32, [_H, _dp, _dp, _dp]),
+    "cpml_set_attenuation": (C.c_int32, [_H, C.c_int32, _dp, _dp, _dp, _dp]),
     "cpml_set_source_series": (C.c_int32, [_H, _dp, _dp, C.c_int32]),
     "cpml_set_source_step": (C.c_int32, [_H, C.c_int32, C.c_double, C.c_double]),
     "cpml_fetch_step": (C.c_int32, [_H, C.c_int32]),
@@ -176,12 +179,13 @@ class Solver:
     def __init__(self, *, ndim, order=2, nx, ny, nz=1, nstep, npoints_pml, nrec, isource, jsource,
                  ksource=0, nslabs=1, slab_rank=0, device=-1, energy_bug_compat=True,
                  deltax, deltay, deltaz=0.0, deltat, lam=0.0, mu=0.0, lambdaplustwomu=0.0, rho=0.0,
-                 cp=0.0):
+                 cp=0.0, rheology=0, emulate_nproc=0):
         self._L = load()
         self.cfg = CpmlConfig(ndim=ndim, order=order, nx=nx, ny=ny, nz=nz, nstep=nstep,
                               npoints_pml=npoints_pml, nrec=nrec, isource=isource, jsource=jsource,
                               ksource=ksource, nslabs=nslabs, slab_rank=slab_rank, device=device,
-                              energy_bug_compat=int(energy_bug_compat),
+                              energy_bug_compat=int(energy_bug_compat), rheology=rheology,
+                              emulate_nproc=emulate_nproc,
                               deltax=deltax, deltay=deltay, deltaz=deltaz, deltat=deltat,
                               lambda_=lam, mu=mu, lambdaplustwomu=lambdaplustwomu, rho=rho, cp=cp)
         self._h = _H()
@@ -230,6 +234,13 @@ class Solver:
         if lam.size != n or mu.size != n or rho.size != n:
             raise CpmlError(CPML_EINVAL, "material arrays must hold NX*NY values")
         self._ck(self._L.cpml_set_material_2d(self._h, _d(lam), _d(mu), _d(rho)))
+
+    def set_attenuation(self, tau_epsilon_nu1, tau_sigma_nu1, tau_epsilon_nu2, tau_sigma_nu2):
+        """Relaxation times of the N_SLS = 2 mechanisms (3D-visco :439-443)."""
+        arrs = [_f64(a) for a in (tau_epsilon_nu1, tau_sigma_nu1, tau_epsilon_nu2, tau_sigma_nu2)]
+        if any(a.size != arrs[0].size for a in arrs):
+            raise CpmlError(CPML_EINVAL, "relaxation-time arrays differ in length")
+        self._ck(self._L.cpml_set_attenuation(self._h, arrs[0].size, *[_d(a) for a in arrs]))
 
     def set_source_series(self, force_x, force_y):
         fx, fy = _f64(force_x), _f64(force_y)
