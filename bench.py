@@ -9,6 +9,8 @@ One "step" = one full time step of the loop body (stress + velocity + source + D
         (N = 1: exactly the reference grid; N > 1: weak scaling, NZ = 640 N)   [default]
   cfg4  1024 x 1024 x 128 per GPU (N = 8: 1024^3), weak scaling
   cfg2  2-D fourth order 4096 x 4096 (single GPU only)
+  cfg5  seismic_CPML_3D_viscoelastic_MPI (4th order, N_SLS = 2) 1024 x 1024 x 128 per GPU, weak scaling
+  cfg5d the same program on its default grid 210 x 800 x 220 (single GPU; N > 1: 220 planes per GPU)
 Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the
 reference loop (oracle/, OpenMP, all host threads): the Fortran reference itself cannot be
 built in this image (no Fortran compiler, no MPI).
@@ -31,6 +33,11 @@ import numpy as np  # noqa: E402
 
 METRIC = "grid-point updates/s, 3-D isotropic C-PML time loop (FP64)"
 UNIT = "Gpts/s"
+
+
+def metric_name(kind):
+    return {"3d": METRIC, "3dv": "grid-point updates/s, 3-D viscoelastic C-PML time loop (FP64)",
+            "2d": "grid-point updates/s, 2-D isotropic C-PML time loop (FP64)"}[kind]
 
 
 def measured_peak():
@@ -96,6 +103,10 @@ def workload_params(name, n_gpus, nstep):
         return P.Params3DIso(NZ=640 * n_gpus, NSTEP=nstep), "3d"
     if name == "cfg4":
         return P.Params3DIso(NX=1024, NY=1024, NZ=128 * n_gpus, NSTEP=nstep), "3d"
+    if name == "cfg5":
+        return P.Params3DVisco(NX=1024, NY=1024, NZ=128 * n_gpus, NSTEP=nstep, NPROC=_visco_nproc(n_gpus, 128 * n_gpus)), "3dv"
+    if name == "cfg5d":
+        return P.Params3DVisco(NZ=220 * n_gpus, NSTEP=nstep, NPROC=_visco_nproc(n_gpus, 220 * n_gpus)), "3dv"
     if name == "cfg2":
         if n_gpus != 1:
             raise SystemExit("cfg2 (2-D) runs on one GPU")
@@ -103,9 +114,20 @@ def workload_params(name, n_gpus, nstep):
     raise SystemExit(f"unknown workload {name}")
 
 
+def _visco_nproc(n_gpus, nz):
+    """Reference NPROC to emulate: its default 4 (3D-visco :158) where the grid allows, else the GPU count."""
+    for n in (4, n_gpus, 2):
+        if n > 1 and nz % n == 0 and nz // n >= 10:
+            return n
+    return 1
+
+
 def workload_label(name, p, kind, n_gpus):
     if kind == "2d":
         return f"seismic_CPML_2D_isotropic_fourth_order {p.NX}x{p.NY}"
+    if kind == "3dv":
+        return (f"seismic_CPML_3D_viscoelastic_MPI (4th order, N_SLS=2, reference NPROC={p.NPROC} emulated): "
+                f"{p.NX}x{p.NY}x{p.NZ} ({p.NX}x{p.NY}x{p.NZ // n_gpus} per GPU, z-slabs)")
     per = f"{p.NX}x{p.NY}x{p.NZ // n_gpus} per GPU"
     tag = "default grid" if name == "cfg3" else "~1024^3 scaled grid"
     return f"seismic_CPML_3D_isotropic_MPI_OpenMP {tag}: {p.NX}x{p.NY}x{p.NZ} ({per}, z-slabs)"
@@ -135,6 +157,25 @@ def oracle_3d_gpts(p, nz_sample, steps, warmup):
     return pts / sec / 1e9, sec, O.num_threads()
 
 
+def oracle_3dv_gpts(p, nz_sample, steps, warmup):
+    """The viscoelastic CPU restatement on a z-reduced sample (NX x NY x nz_sample, 4 emulated slabs)."""
+    from oracle import oracle as O
+    from seismic_cpml_b200 import programs as P
+    q = P.Params3DVisco(NX=p.NX, NY=min(p.NY, 256), NZ=nz_sample, NSTEP=steps + warmup, NPROC=4)
+    s = P.setup_3d_visco(q)
+    O.set_ftz(True)
+    O.set_warmup_steps(warmup)
+    O.run_3d_visco(nx=q.NX, ny=q.NY, nz=q.NZ, nproc=4, deltax=q.DELTAX, deltay=q.DELTAY, deltaz=q.DELTAZ,
+                   deltat=q.DELTAT, lam=q.lam, mu=q.mu, rho=q.rho, nstep=q.NSTEP, npoints_pml=q.NPOINTS_PML,
+                   isource=q.ISOURCE, jsource=q.JSOURCE, tau_epsilon_nu1=q.tau_epsilon_nu1,
+                   tau_sigma_nu1=q.tau_sigma_nu1, tau_epsilon_nu2=q.tau_epsilon_nu2, tau_sigma_nu2=q.tau_sigma_nu2,
+                   prof_x=s.prof_x, prof_y=s.prof_y, prof_z=s.prof_z, force_x=s.force_x, force_y=s.force_y,
+                   ix_rec=s.ix_rec, iy_rec=s.iy_rec, kind="timed")
+    sec = O.last_loop_seconds()
+    O.set_warmup_steps(0)
+    return float(q.NX) * q.NY * q.NZ * steps / sec / 1e9, sec, O.num_threads()
+
+
 def oracle_2d_gpts(p, n_sample, steps, warmup):
     from oracle import oracle as O
     from seismic_cpml_b200 import programs as P
@@ -156,7 +197,13 @@ def run_reference(args):
     if rank != 0:
         return 0
     p, kind = workload_params(args.workload, args.gpus, args.steps + args.warmup)
-    if kind == "3d":
+    if kind == "3dv":
+        nz_s = 40
+        v, sec, cores = oracle_3dv_gpts(p, nz_s, args.steps, args.warmup)
+        sample = (f"{p.NX}x{min(p.NY, 256)}x{nz_s} reduced sample of the workload grid (4 emulated MPI slabs), "
+                  f"{args.steps} timed steps after {args.warmup}; full-grid memory variables and separate "
+                  "Dirichlet/energy passes as in the reference; FTZ/DAZ on")
+    elif kind == "3d":
         nz_s = 160
         v, sec, cores = oracle_3d_gpts(p, nz_s, args.steps, args.warmup)
         sample = (f"{p.NX}x{p.NY}x{nz_s} z-reduced sample of the workload grid (2 emulated MPI slabs), "
@@ -166,7 +213,7 @@ def run_reference(args):
         n_s = 2048
         v, sec, cores = oracle_2d_gpts(p, n_s, args.steps, args.warmup)
         sample = f"{n_s}x{n_s} sample grid, {args.steps} timed steps after {args.warmup}, serial like the reference"
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": metric_name(kind), "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (fields start at zero, analytic source; no RNG)",
@@ -208,16 +255,20 @@ def run_b200(args):
     K, W = args.steps, max(args.warmup, 3)
     nstep_total = W + K + K + 8          # warm-up + device-timed + e2e-timed (+ slack)
     p, kind = workload_params(args.workload, world, nstep_total)
-    s = P.setup_3d(p) if kind == "3d" else P.setup_2d(p)
+    s = P.setup_3d(p) if kind == "3d" else P.setup_3d_visco(p) if kind == "3dv" else P.setup_2d(p)
     if kind == "3d":
         sol = P.make_solver_3d(p, s, nslabs=world, slab_rank=rank, device=local_rank)
+        pts_step_rank = float(p.NX) * p.NY * (p.NZ // world)
+    elif kind == "3dv":
+        sol = P.make_solver_3d_visco(p, s, nslabs=world, slab_rank=rank, device=local_rank)
         pts_step_rank = float(p.NX) * p.NY * (p.NZ // world)
     else:
         sol = P.make_solver_2d(p, s, device=local_rank)
         pts_step_rank = float(p.NX) * p.NY
-    slab = GpuSlab(sol) if kind == "3d" else sol
-    drv = SlabDriver(slab, rank, world, sol.nzl, halo=args.halo) if (kind == "3d" and world > 1) else None
-    if kind != "3d":
+    is3d = kind in ("3d", "3dv")
+    slab = GpuSlab(sol) if is3d else sol
+    drv = SlabDriver(slab, rank, world, sol.nzl, halo=args.halo, visco=(kind == "3dv")) if (is3d and world > 1) else None
+    if not is3d:
         sol.set_stream(torch.cuda.current_stream().cuda_stream)
 
     def do_steps(a, b):
@@ -284,7 +335,7 @@ def run_b200(args):
             d2h += 8
             if vn > P.STABILITY_THRESHOLD:
                 raise SystemExit("code became unstable and blew up")
-            if kind == "3d":
+            if is3d:
                 own = owner_of_plane(p.NZ // 2, p.NZ, world)
                 if rank == own:
                     sx, sy = sol.get_seismograms()
@@ -324,7 +375,7 @@ def run_b200(args):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "metric": metric_name(kind), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic (fields start at zero, analytic source; no RNG)",
             "config": {"workload": workload_label(args.workload, p, kind, world),
@@ -334,10 +385,12 @@ def run_b200(args):
                        "halo": (None if world == 1 else
                                 "6 planes per step and interface stored straight into the neighbour GPU's halo planes "
                                 "by the update kernels over NVLink (CUDA IPC), ordered by device-side flags"
-                                if args.halo == "p2p" else "NCCL send/recv of 6 planes per step and interface"),
+                                if (args.halo == "p2p" and kind == "3d") else
+                                "NCCL send/recv of 18 planes per step and interface (complete fourth-order halo)" if kind == "3dv"
+                                else "NCCL send/recv of 6 planes per step and interface"),
                        "fmad": False, "finite": finite,
-                       "launch": sol.launch_info() if kind == "3d" else None},
-            "roofline": {"bound": "hbm", "kernel": ("k_stress3d_tma" if sol.launch_info()["tma"] else "k_stress3d") if kind == "3d" else "k_stress2d",
+                       "launch": sol.launch_info() if is3d else None},
+            "roofline": {"bound": "hbm", "kernel": ("k_stress3d_tma" if sol.launch_info()["tma"] else "k_stress3d") if kind == "3d" else "k_vstress3d" if kind == "3dv" else "k_stress2d",
                          "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": (ach / peak) if ach else None, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": b_stress,
@@ -358,7 +411,10 @@ def run_b200(args):
         }
         if args.cpu_baseline and world == 1:
             try:
-                if kind == "3d":
+                if kind == "3dv":
+                    v, sec, cores = oracle_3dv_gpts(p, 40, 4, 1)
+                    sample = f"{p.NX}x{min(p.NY, 256)}x40 reduced sample, 4 timed steps after 1, 4 emulated MPI slabs, FTZ/DAZ on"
+                elif kind == "3d":
                     v, sec, cores = oracle_3d_gpts(p, 80, 6, 2)
                     sample = f"{p.NX}x{p.NY}x80 z-reduced sample, 6 timed steps after 2, 2 emulated MPI slabs, FTZ/DAZ on"
                 else:
@@ -381,7 +437,7 @@ def main():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg4", "cfg2"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg4", "cfg2", "cfg5", "cfg5d"])
     ap.add_argument("--halo", default="p2p", choices=["p2p", "sendrecv"],
                     help="N > 1: peer stores from inside the kernels (default) or NCCL send/recv")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")

@@ -313,6 +313,27 @@ module cpml_b200
       integer(c_int32_t) :: ierr
     end function
 
+    function cpml_host_pml_profile_visco(n, delta, deltat, npoints_pml, use_pml_min, use_pml_max, cp, sqrt_taumax, &
+        rcoef, npower, k_max_pml, alpha_max_pml, origin_top_uses_n, clamp_alpha, a, b, K, a_half, b_half, K_half) &
+        bind(C, name='cpml_host_pml_profile_visco') result(ierr)
+      import :: c_int32_t, c_double
+      integer(c_int32_t), value :: n, npoints_pml, use_pml_min, use_pml_max, origin_top_uses_n, clamp_alpha
+      real(c_double), value :: delta, deltat, cp, sqrt_taumax, rcoef, npower, k_max_pml, alpha_max_pml
+      real(c_double), intent(out) :: a(*), b(*), K(*), a_half(*), b_half(*), K_half(*)
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_host_find_receivers_at(nx, ny, deltax, deltay, nrec, xrec, yrec, index_origin, ix_rec, iy_rec, dist) &
+        bind(C, name='cpml_host_find_receivers_at') result(ierr)
+      import :: c_int32_t, c_double
+      integer(c_int32_t), value :: nx, ny, nrec, index_origin
+      real(c_double), value :: deltax, deltay
+      real(c_double), intent(in) :: xrec(*), yrec(*)
+      integer(c_int32_t), intent(out) :: ix_rec(*), iy_rec(*)
+      real(c_double), intent(out) :: dist(*)
+      integer(c_int32_t) :: ierr
+    end function
+
     function cpml_host_source_series(nstep, deltat, f0, t0, factor, angle_force_deg, force_x, force_y) &
         bind(C, name='cpml_host_source_series') result(ierr)
       import :: c_int32_t, c_double

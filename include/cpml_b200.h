@@ -268,6 +268,16 @@ int32_t cpml_host_pml_profile(int32_t n, double delta, double deltat, int32_t np
                               double *a, double *b, double *K,
                               double *a_half, double *b_half, double *K_half);
 
+/* The same with the viscoelastic program's d0 = -(NPOWER+1)*cp*dsqrt(taumax)*log(Rcoef)/(2L)
+ * (3D-visco :547; Rcoef = 1e-4 :541, K_MAX_PML = 7 :243 are the driver's choices). */
+int32_t cpml_host_pml_profile_visco(int32_t n, double delta, double deltat, int32_t npoints_pml,
+                                    int32_t use_pml_min, int32_t use_pml_max,
+                                    double cp, double sqrt_taumax, double rcoef, double npower,
+                                    double k_max_pml, double alpha_max_pml,
+                                    int32_t origin_top_uses_n, int32_t clamp_alpha,
+                                    double *a, double *b, double *K,
+                                    double *a_half, double *b_half, double *K_half);
+
 /* First-derivative-of-Gaussian source of :1058-1071 for it = 1..nstep. */
 int32_t cpml_host_source_series(int32_t nstep, double deltat, double f0, double t0,
                                 double factor, double angle_force_deg,
@@ -277,6 +287,13 @@ int32_t cpml_host_source_series(int32_t nstep, double deltat, double f0, double 
 int32_t cpml_host_find_receivers(int32_t nx, int32_t ny, double deltax, double deltay,
                                  int32_t nrec, double xdeb, double ydeb, double xfin,
                                  double yfin, int32_t *ix_rec, int32_t *iy_rec, double *dist);
+
+/* Nearest-grid-point search for explicit receiver targets (3D-visco :832-853); the abscissa of
+ * grid point i is DELTAX*i when index_origin = 1 (that program), DELTAX*(i-1) when 0. */
+int32_t cpml_host_find_receivers_at(int32_t nx, int32_t ny, double deltax, double deltay,
+                                    int32_t nrec, const double *xrec, const double *yrec,
+                                    int32_t index_origin, int32_t *ix_rec, int32_t *iy_rec,
+                                    double *dist);
 
 /* Courant number of :712 (deltaz <= 0 => 2-D form of 2D-2nd :513). */
 double cpml_host_courant(double cp, double deltat, double deltax, double deltay, double deltaz);

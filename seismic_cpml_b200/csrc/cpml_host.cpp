@@ -51,11 +51,24 @@ extern "C" int32_t cpml_host_pml_profile(int32_t n, double delta, double deltat,
                                          double *a, double *b, double *K,
                                          double *a_half, double *b_half, double *K_half)
 {
+    return cpml_host_pml_profile_visco(n, delta, deltat, npoints_pml, use_pml_min, use_pml_max, cp, 1.0, rcoef, npower,
+                                       k_max_pml, alpha_max_pml, origin_top_uses_n, clamp_alpha, a, b, K, a_half, b_half, K_half);
+}
+
+// 3D-visco :533-801: the same profiles with d0 scaled by dsqrt(taumax) (:547); sqrt_taumax = 1 is
+// the isotropic formula bit for bit.
+extern "C" int32_t cpml_host_pml_profile_visco(int32_t n, double delta, double deltat, int32_t npoints_pml,
+                                               int32_t use_pml_min, int32_t use_pml_max, double cp, double sqrt_taumax,
+                                               double rcoef, double npower, double k_max_pml, double alpha_max_pml,
+                                               int32_t origin_top_uses_n, int32_t clamp_alpha,
+                                               double *a, double *b, double *K,
+                                               double *a_half, double *b_half, double *K_half)
+{
     if (n < 1 || !(delta > 0) || !(deltat > 0) || npoints_pml < 1 || !a || !b || !K || !a_half || !b_half || !K_half)
         return CPML_EINVAL;
     if (npower < 1) return CPML_EINVAL;                                   // :410
     const double thickness = npoints_pml * delta;                        // :402
-    const double d0 = -(npower + 1) * cp * std::log(rcoef) / (2.0 * thickness);   // :413
+    const double d0 = -(npower + 1) * cp * sqrt_taumax * std::log(rcoef) / (2.0 * thickness);   // :413 ; 3D-visco :547
     const double origin_min = thickness;                                  // :455
     const double origin_max = (origin_top_uses_n ? n : n - 1) * delta - thickness;   // :456 / 2D-4th :401
 
@@ -115,6 +128,28 @@ extern "C" int32_t cpml_host_find_receivers(int32_t nx, int32_t ny, double delta
             for (int32_t i = 1; i <= nx; i++) {
                 const double ex = deltax * static_cast<double>(i - 1) - xr;
                 const double ey = deltay * static_cast<double>(j - 1) - yr;
+                const double dv = std::sqrt(ex * ex + ey * ey);
+                if (dv < best) { best = dv; ix_rec[r] = i; iy_rec[r] = j; }
+            }
+        if (dist) dist[r] = best;
+    }
+    return CPML_OK;
+}
+
+// 3D-visco :832-853: explicit receiver targets; grid abscissa DELTAX*i when index_origin = 1
+// (the viscoelastic program), DELTAX*(i-1) when 0.
+extern "C" int32_t cpml_host_find_receivers_at(int32_t nx, int32_t ny, double deltax, double deltay, int32_t nrec,
+                                               const double *xrec, const double *yrec, int32_t index_origin,
+                                               int32_t *ix_rec, int32_t *iy_rec, double *dist)
+{
+    if (nx < 1 || ny < 1 || nrec < 1 || !xrec || !yrec || !ix_rec || !iy_rec) return CPML_EINVAL;
+    if (index_origin != 0 && index_origin != 1) return CPML_EINVAL;
+    for (int32_t r = 0; r < nrec; r++) {
+        double best = 1.e+30;
+        for (int32_t j = 1; j <= ny; j++)
+            for (int32_t i = 1; i <= nx; i++) {
+                const double ex = deltax * static_cast<double>(i - 1 + index_origin) - xrec[r];
+                const double ey = deltay * static_cast<double>(j - 1 + index_origin) - yrec[r];
                 const double dv = std::sqrt(ex * ex + ey * ey);
                 if (dv < best) { best = dv; ix_rec[r] = i; iy_rec[r] = j; }
             }

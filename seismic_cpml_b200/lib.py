@@ -89,6 +89,11 @@ SYMBOLS = {
     "cpml_host_pml_profile": (C.c_int32, [C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                           C.c_int32, C.c_int32] + [_dp] * 6),
+    "cpml_host_pml_profile_visco": (C.c_int32, [C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32,
+                                                C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                                C.c_double, C.c_int32, C.c_int32] + [_dp] * 6),
+    "cpml_host_find_receivers_at": (C.c_int32, [C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32,
+                                                _dp, _dp, C.c_int32, _ip, _ip, _dp]),
     "cpml_host_source_series": (C.c_int32, [C.c_int32] + [C.c_double] * 5 + [_dp, _dp]),
     "cpml_host_find_receivers": (C.c_int32, [C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32,
                                              C.c_double, C.c_double, C.c_double, C.c_double, _ip, _ip, _dp]),
@@ -147,6 +152,30 @@ def host_pml_profile(n, delta, deltat, npoints_pml, use_pml_min=True, use_pml_ma
     if rc:
         raise CpmlError(rc, "cpml_host_pml_profile")
     return out
+
+
+def host_pml_profile_visco(n, delta, deltat, npoints_pml, use_pml_min=True, use_pml_max=True, *, cp,
+                           sqrt_taumax, rcoef=0.0001, npower=2.0, k_max_pml=7.0, alpha_max_pml,
+                           clamp_alpha=False):
+    out = {k: np.zeros(n) for k in PROFILE_KEYS}
+    rc = load().cpml_host_pml_profile_visco(n, delta, deltat, npoints_pml, int(use_pml_min), int(use_pml_max),
+                                            cp, sqrt_taumax, rcoef, npower, k_max_pml, alpha_max_pml,
+                                            0, int(clamp_alpha), *[_d(out[k]) for k in PROFILE_KEYS])
+    if rc:
+        raise CpmlError(rc, "cpml_host_pml_profile_visco")
+    return out
+
+
+def host_find_receivers_at(nx, ny, deltax, deltay, xrec, yrec, index_origin=1):
+    xr, yr = _f64(xrec), _f64(yrec)
+    nrec = xr.size
+    ix, iy = np.zeros(nrec, dtype=np.int32), np.zeros(nrec, dtype=np.int32)
+    dist = np.zeros(nrec)
+    rc = load().cpml_host_find_receivers_at(nx, ny, deltax, deltay, nrec, _d(xr), _d(yr), index_origin,
+                                            _i(ix), _i(iy), _d(dist))
+    if rc:
+        raise CpmlError(rc, "cpml_host_find_receivers_at")
+    return ix, iy, dist
 
 
 def host_source_series(nstep, deltat, f0, t0, factor, angle_force_deg):

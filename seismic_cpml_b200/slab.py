@@ -32,6 +32,31 @@ PHASE_V = ((F_VX, "left"), (F_VY, "left"), (F_VZ, "right"))        # :811-823
 PHASE_S = ((F_SZZ, "left"), (F_SYZ, "right"), (F_SXZ, "right"))    # :951-963
 
 
+def exchange_plan(phase, nzl, visco=False):
+    """Messages of one exchange phase as (field, direction, first plane sent, plane count, first
+    plane received into), local k.
+
+    Isotropic (second order): one plane per field -- "left": my plane 1 -> left's NZ_LOCAL+1,
+    "right": my plane NZ_LOCAL -> right's 0.
+    Viscoelastic (fourth order, seismic_CPML_3D_viscoelastic_MPI.f90:962-975, :1229-1242): two
+    planes in the reference's direction (planes 1:2 -> NZ_LOCAL+1:NZ_LOCAL+2, or
+    NZ_LOCAL-1:NZ_LOCAL -> -1:0) PLUS the one plane the other way that the reference never sends
+    although its stencils read it.  The kernels decide per plane which taps
+    read zero (cpml_config.emulate_nproc), so GPU slabs always exchange the complete halo and the
+    result does not depend on the number of GPUs."""
+    plan = []
+    for field, direction in phase:
+        if not visco:
+            plan.append((field, "left", 1, 1, nzl + 1) if direction == "left" else (field, "right", nzl, 1, 0))
+        elif direction == "left":
+            plan.append((field, "left", 1, 2, nzl + 1))
+            plan.append((field, "right", nzl, 1, 0))
+        else:
+            plan.append((field, "right", nzl - 1, 2, -1))
+            plan.append((field, "left", 1, 1, nzl + 1))
+    return plan
+
+
 class _DevicePlane:
     """Zero-copy torch view of a device plane owned by libcpml_b200 (__cuda_array_interface__)."""
 
@@ -40,9 +65,13 @@ class _DevicePlane:
                                          "data": (ptr, False), "version": 2}
 
 
-def plane_tensor(solver, field: int, klocal: int) -> torch.Tensor:
+def plane_tensor(solver, field: int, klocal: int, nplanes: int = 1) -> torch.Tensor:
+    """View of `nplanes` consecutive planes starting at klocal (planes are contiguous in k)."""
     ptr, nbytes = solver.halo_plane(field, klocal)
-    return torch.as_tensor(_DevicePlane(ptr, nbytes), device=torch.device("cuda", torch.cuda.current_device()))
+    if nplanes > 1:
+        ptr2, _ = solver.halo_plane(field, klocal + nplanes - 1)
+        assert ptr2 - ptr == (nplanes - 1) * nbytes
+    return torch.as_tensor(_DevicePlane(ptr, nbytes * nplanes), device=torch.device("cuda", torch.cuda.current_device()))
 
 
 def owner_of_plane(kglobal: int, nz: int, nslabs: int) -> int:
@@ -59,8 +88,14 @@ class SlabDriver:
     GpuSlab below, or the numpy slab of tests/ on CPU.
     """
 
-    def __init__(self, backend, rank: int, nslabs: int, nzl: int, group=None, halo: str = "sendrecv"):
+    def __init__(self, backend, rank: int, nslabs: int, nzl: int, group=None, halo: str = "sendrecv",
+                 visco: bool = False):
         self.b, self.rank, self.nslabs, self.nzl, self.group = backend, rank, nslabs, nzl, group
+        self.visco = visco
+        self.plan_v = exchange_plan(PHASE_V, nzl, visco)
+        self.plan_s = exchange_plan(PHASE_S, nzl, visco)
+        if visco and halo == "p2p":
+            halo = "sendrecv"       # peer stores exist for the isotropic kernels only
         self.left = rank - 1 if rank > 0 else None          # MPI_PROC_NULL at the ends
         self.right = rank + 1 if rank < nslabs - 1 else None
         self._planes = {}
@@ -81,26 +116,30 @@ class SlabDriver:
             self.b.p2p_attach_ipc(1, blobs[self.right])
         dist.barrier(group=self.group)      # nobody steps before every neighbour is mapped
 
-    def _plane(self, field, klocal):
-        key = (field, klocal)
+    def _plane(self, field, klocal, nplanes=1):
+        key = (field, klocal, nplanes)
         if key not in self._planes:
-            self._planes[key] = self.b.plane(field, klocal)
+            self._planes[key] = self.b.plane(field, klocal) if nplanes == 1 else self.b.plane(field, klocal, nplanes)
         return self._planes[key]
 
-    def exchange(self, phase):
-        """One group of three MPI_SENDRECV: all sends and receives of the phase in flight at once."""
+    def exchange(self, plan):
+        """One group of MPI_SENDRECV calls: all sends and receives of the phase in flight at once."""
+        if plan is PHASE_V:
+            plan = self.plan_v
+        elif plan is PHASE_S:
+            plan = self.plan_s
         ops = []
-        for field, direction in phase:
-            if direction == "left":      # my plane 1 -> left's NZ_LOCAL+1 ; right's plane 1 -> my NZ_LOCAL+1
+        for field, direction, k_send, n, k_recv in plan:
+            if direction == "left":      # my low planes -> left's high halo ; right's low planes -> my high halo
                 if self.left is not None:
-                    ops.append(dist.P2POp(dist.isend, self._plane(field, 1), self.left, self.group))
+                    ops.append(dist.P2POp(dist.isend, self._plane(field, k_send, n), self.left, self.group))
                 if self.right is not None:
-                    ops.append(dist.P2POp(dist.irecv, self._plane(field, self.nzl + 1), self.right, self.group))
-            else:                        # my plane NZ_LOCAL -> right's 0 ; left's NZ_LOCAL -> my 0
+                    ops.append(dist.P2POp(dist.irecv, self._plane(field, k_recv, n), self.right, self.group))
+            else:                        # my high planes -> right's low halo ; left's high planes -> my low halo
                 if self.right is not None:
-                    ops.append(dist.P2POp(dist.isend, self._plane(field, self.nzl), self.right, self.group))
+                    ops.append(dist.P2POp(dist.isend, self._plane(field, k_send, n), self.right, self.group))
                 if self.left is not None:
-                    ops.append(dist.P2POp(dist.irecv, self._plane(field, 0), self.left, self.group))
+                    ops.append(dist.P2POp(dist.irecv, self._plane(field, k_recv, n), self.left, self.group))
         if not ops:
             return
         for op in ops:
@@ -167,8 +206,8 @@ class GpuSlab:
         self.s = solver
         solver.set_stream(torch.cuda.current_stream().cuda_stream)
 
-    def plane(self, field, klocal):
-        return plane_tensor(self.s, field, klocal)
+    def plane(self, field, klocal, nplanes=1):
+        return plane_tensor(self.s, field, klocal, nplanes)
 
     def __getattr__(self, name):
         return getattr(self.s, name)

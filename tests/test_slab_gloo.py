@@ -65,3 +65,69 @@ def test_slab_driver_gloo_matches_oracle(world, tmp_path):
         # 40 steps x 3 planes per interior interface direction
         n_if = (1 if r > 0 else 0) + (1 if r < world - 1 else 0)
         assert int(d["sent"]) == 40 * 3 * n_if * (c["nx"] + 2) * (c["ny"] + 2) * 8
+
+
+# ---- viscoelastic exchange plan (fourth order: two planes one way, one the other) --------------
+
+class _FakeViscoSlab:
+    """Planes tagged with (rank, field, klocal): checks WHERE the driver moves data, not the physics."""
+
+    def __init__(self, rank, nzl, npts=7):
+        import torch
+        self.rank, self.nzl = rank, nzl
+        self.f = {}
+        for field in (0, 1, 2, 5, 7, 8):
+            t = torch.full((nzl + 4, npts), -1.0, dtype=torch.float64)
+            for k in range(1, nzl + 1):
+                t[k + 1] = rank * 10000 + field * 100 + k
+            self.f[field] = t
+
+    def plane(self, field, klocal, nplanes=1):
+        return self.f[field][klocal + 1:klocal + 1 + nplanes].reshape(-1)
+
+
+def _visco_plan_worker(rank, world, port, outdir):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    import torch.distributed as dist
+    from seismic_cpml_b200.slab import PHASE_S, PHASE_V, SlabDriver
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nzl = 6
+    slab = _FakeViscoSlab(rank, nzl)
+    drv = SlabDriver(slab, rank, world, nzl, visco=True)
+    drv.exchange(PHASE_V)
+    drv.exchange(PHASE_S)
+    np.savez(os.path.join(outdir, f"v{rank}.npz"), sent=drv.bytes_sent,
+             **{f"f{k}": v.numpy() for k, v in slab.f.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_visco_exchange_plan_gloo(world, tmp_path):
+    """3D-visco :962-975 / :1229-1242 plus the planes the reference never sends (quirk B6)."""
+    mp.spawn(_visco_plan_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    nzl = 6
+    res = [np.load(tmp_path / f"v{r}.npz") for r in range(world)]
+
+    def tag(r, field, k):
+        return r * 10000 + field * 100 + k
+
+    for r, d in enumerate(res):
+        for field, two_planes_go in ((0, "left"), (1, "left"), (5, "left"), (2, "right"), (7, "right"), (8, "right")):
+            a = d[f"f{field}"][:, 0]          # index = klocal + 1
+            hi = [a[nzl + 2], a[nzl + 3]]     # planes NZ_LOCAL+1, NZ_LOCAL+2
+            lo = [a[0], a[1]]                 # planes -1, 0
+            if two_planes_go == "left":
+                want_hi = [tag(r + 1, field, 1), tag(r + 1, field, 2)] if r < world - 1 else [-1, -1]
+                want_lo = [-1, tag(r - 1, field, nzl)] if r > 0 else [-1, -1]
+            else:
+                want_hi = [tag(r + 1, field, 1), -1] if r < world - 1 else [-1, -1]
+                want_lo = [tag(r - 1, field, nzl - 1), tag(r - 1, field, nzl)] if r > 0 else [-1, -1]
+            assert hi == want_hi and lo == want_lo, (r, field, hi, want_hi, lo, want_lo)
+            assert list(a[2:nzl + 2]) == [tag(r, field, k) for k in range(1, nzl + 1)]   # owned planes untouched
+        n_if = (1 if r > 0 else 0) + (1 if r < world - 1 else 0)
+        # per interface and rank: 3 fields x (2 + 1 planes) over the two directions = 9 planes sent
+        assert int(d["sent"]) == n_if * 9 * 7 * 8
