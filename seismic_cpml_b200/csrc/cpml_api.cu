@@ -67,7 +67,7 @@ struct cpml_handle {
     // profiles
     bool have_prof[3] = {false, false, false};
     std::vector<double> hprof[3][6];
-    double *dprof[3][6] = {};  // device copies, 0-based
+    double *dprof[3][8] = {};  // device copies, 0-based; [6], [7] = RN(1/K), RN(1/K_half) for div_exact
     Shell shell[3] = {};
     int nz_own[3][2] = {};     // per axis: count of a != 0 (integer, half) -- algorithmic bytes
 
@@ -119,6 +119,14 @@ struct cpml_handle {
         h->err = (msg);            \
         return (code);             \
     } while (0)
+
+// Markstein's correctly-rounded division needs a divisor whose significand is not all ones.
+static bool all_ones_significand(double c)
+{
+    unsigned long long b;
+    memcpy(&b, &c, sizeof(b));
+    return (b & 0x000fffffffffffffULL) == 0x000fffffffffffffULL;
+}
 
 static Shell find_shell(const std::vector<double> *p, int n)
 {
@@ -193,6 +201,9 @@ static int32_t create_impl(cpml_handle *h)
         h->nzl = 1;
         h->koff = 0;
     }
+    if (c.ndim == 2 && (all_ones_significand(24.0 * c.deltax) || all_ones_significand(c.deltax) ||
+                        all_ones_significand(24.0 * c.deltay) || all_ones_significand(c.deltay)))
+        FAIL(CPML_EINVAL, "grid spacing with an all-ones significand is not supported");
     if (c.cp > 0) {   // Courant check, 3D-iso :712-717 / 2D-2nd :513-516
         const double cn = cpml_host_courant(c.cp, c.deltat, c.deltax, c.deltay, c.ndim == 3 ? c.deltaz : 0.0);
         if (cn > 1.0) FAIL(CPML_ECFL, "time step is too large, simulation will be unstable");
@@ -432,6 +443,17 @@ extern "C" int32_t cpml_set_profiles(cpml_handle *h, int32_t axis, const double 
                 if (src[q][i] == 0.0) FAIL(CPML_EINVAL, "K profile contains zero");
         if (!h->dprof[axis][q]) CK(cudaMalloc(&h->dprof[axis][q], (size_t)n * sizeof(double)));
         CK(cudaMemcpy(h->dprof[axis][q], src[q], (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    // correctly rounded reciprocals of the K profiles (div_exact, cpml_internal.h)
+    for (int q = 0; q < 2; q++) {
+        std::vector<double> r(n);
+        for (int i = 0; i < n; i++) {
+            const double K = src[q == 0 ? 2 : 5][i];
+            if (all_ones_significand(K)) FAIL(CPML_EINVAL, "K profile value with an all-ones significand is not supported");
+            r[i] = 1.0 / K;
+        }
+        if (!h->dprof[axis][6 + q]) CK(cudaMalloc(&h->dprof[axis][6 + q], (size_t)n * sizeof(double)));
+        CK(cudaMemcpy(h->dprof[axis][6 + q], r.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
     }
     h->shell[axis] = find_shell(h->hprof[axis], n);
     h->have_prof[axis] = true;
@@ -755,6 +777,7 @@ static AxisCoef coef_view(cpml_handle *h, int ax)
     AxisCoef c;
     c.a = h->dprof[ax][0] - 1; c.b = h->dprof[ax][1] - 1; c.K = h->dprof[ax][2] - 1;
     c.a_half = h->dprof[ax][3] - 1; c.b_half = h->dprof[ax][4] - 1; c.K_half = h->dprof[ax][5] - 1;
+    c.rK = h->dprof[ax][6] - 1; c.rK_half = h->dprof[ax][7] - 1;
     return c;
 }
 
@@ -817,6 +840,9 @@ static Params2D make_p2(cpml_handle *h, int it)
     for (int m = 0; m < 4; m++) { p.mx[m] = h->mx[m]; p.my[m] = h->my[m]; }
     p.cx = coef_view(h, 0); p.cy = coef_view(h, 1);
     p.deltax = c.deltax; p.deltay = c.deltay; p.deltat = c.deltat;
+    p.denx = c.order == 4 ? 24.0 * c.deltax : c.deltax;      // 2D-4th :565 / 2D-2nd :564
+    p.deny = c.order == 4 ? 24.0 * c.deltay : c.deltay;
+    p.rdenx = 1.0 / p.denx; p.rdeny = 1.0 / p.deny;
     p.it = it; p.isrc = c.isource; p.jsrc = c.jsource;
     p.force_x = h->d_src_x; p.force_y = h->d_src_y;
     p.npml = c.npoints_pml;
@@ -854,6 +880,8 @@ static ParamsV3D make_pv(cpml_handle *h, int it)
         p.phi2[l] = (ONE - te2[l] / ts2[l]) / ts2[l];
         p.den1[l] = 1.0 - c.deltat * 0.5 * p.tauinv1[l];
         p.den2[l] = 1.0 - c.deltat * 0.5 * p.tauinv2[l];
+        p.rden1[l] = 1.0 / p.den1[l];
+        p.rden2[l] = 1.0 / p.den2[l];
     }
     const double Mu_nu1 = ONE - (ONE - te1[0] / ts1[0]) - (ONE - te1[1] / ts1[1]);
     const double Mu_nu2 = ONE - (ONE - te2[0] / ts2[0]) - (ONE - te2[1] / ts2[1]);

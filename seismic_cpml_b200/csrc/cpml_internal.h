@@ -30,10 +30,38 @@ struct Shell {
     int size() const { return lo + (n - hi + 1); }
 };
 
-// 1-based device views of the six coefficient arrays of one axis.
+// 1-based device views of the six coefficient arrays of one axis, plus the correctly rounded
+// reciprocals of K and K_half (for div_exact).
 struct AxisCoef {
     const double *a, *b, *K, *a_half, *b_half, *K_half;
+    const double *rK, *rK_half;
 };
+
+#ifdef __CUDACC__
+// a / c, correctly rounded, for a divisor whose correctly rounded reciprocal y = RN(1/c) is known
+// (a constant, or a profile value with a host-computed reciprocal).  q = a*y followed by two
+// residual corrections r = fma(-c, q, a), q += r*y: after the first correction q is a faithful
+// rounding of a/c, and then Markstein's theorem (IBM J. Res. Dev. 34, 1990; Muller et al., Handbook
+// of Floating-Point Arithmetic, "division with a correctly rounded reciprocal") makes the second one
+// the correctly rounded quotient, provided nothing underflows or overflows on the way and the
+// significand of c is not all ones (checked on the host).  Outside a wide exponent window of the
+// dividend the generic IEEE division runs instead, so the result is bit-identical to a / c for
+// every input; zero dividends take the short path too.  Five dependent FP64 operations instead of
+// the ~60-instruction generic sequence (whose slow path is also taken for every zero dividend,
+// i.e. on the whole quiescent part of the grid).
+__device__ __forceinline__ double div_exact(double a, double c, double y)
+{
+    const double q0 = a * y;
+    double r = __fma_rn(-c, q0, a);
+    double q = __fma_rn(r, y, q0);
+    r = __fma_rn(-c, q, a);
+    q = __fma_rn(r, y, q);
+    const unsigned e = (unsigned)__double2hiint(a) & 0x7ff00000u;       // biased exponent field of a
+    if (e > 0x0c800000u && e < 0x73000000u) return q;                    // 2^-822 < |a| < 2^+817
+    if (a == 0.0) return q0;                                             // +-0 / c
+    return a / c;
+}
+#endif
 
 // ------------------------------------------------------------------ 3-D
 struct Params3D {
@@ -134,6 +162,7 @@ struct ParamsV3D {
     // constants of :982-987 and :458-477, evaluated on the host in the reference's order
     double lam, mu, l2m_r, lam23mu, two_mu, two_thirds_mu, lam_u, mu_u, l2m_u;
     double phi1[2], phi2[2], tauinv1[2], tauinv2[2], den1[2], den2[2];   // den = 1 - dt*0.5*tauinv
+    double rden1[2], rden2[2];                                           // RN(1/den) for div_exact
     int nzl_e;                // plane count of one EMULATED reference slab (quirk B6); nz: none
     int it, isrc, jsrc, ksrc;
     const double *src_x, *src_y;
@@ -155,6 +184,7 @@ struct Params2D {
     double *mx[4], *my[4];
     AxisCoef cx, cy;
     double deltax, deltay, deltat;
+    double denx, rdenx, deny, rdeny;         // DELTAX (2nd order) or 24*DELTAX (4th), and RN(1/.)
     int it;
     int isrc, jsrc;
     const double *force_x, *force_y;         // raw force series (2D-2nd :656-657)

@@ -17,12 +17,12 @@
 namespace cpml {
 
 __device__ __forceinline__ double cpml_apply2(double *__restrict__ mem, long long q,
-                                              double b, double a, double K, double value)
+                                              double b, double a, double K, double rK, double value)
 {
     double m = mem[q];
     m = b * m + a * value;
     mem[q] = m;
-    return value / K + m;
+    return div_exact(value, K, rK) + m;     // value / K + m, rK = RN(1/K)
 }
 
 __device__ __forceinline__ int shell_index2(int i, int lo, int hi)
@@ -30,19 +30,22 @@ __device__ __forceinline__ int shell_index2(int i, int lo, int hi)
     return i <= lo ? i - 1 : lo + (i - hi);
 }
 
+// The reference divides by DELTAX (2D-2nd :564) or by 24*DELTAX (2D-4th :565): `den` is that
+// divisor and `rden` its correctly rounded reciprocal; div_exact returns the correctly rounded
+// quotient, bit-identical to the division (cpml_internal.h).
 // forward difference u(n+1)-u(n): `s` is the element stride along the axis
 template <int ORDER>
-__device__ __forceinline__ double d_fwd(const double *f, long long q, long long s, double delta)
+__device__ __forceinline__ double d_fwd(const double *f, long long q, long long s, double den, double rden)
 {
-    if (ORDER == 2) return (f[q + s] - f[q]) / delta;
-    return (27.0 * f[q + s] - 27.0 * f[q] - f[q + 2 * s] + f[q - s]) / (24.0 * delta);
+    if (ORDER == 2) return div_exact(f[q + s] - f[q], den, rden);
+    return div_exact(27.0 * f[q + s] - 27.0 * f[q] - f[q + 2 * s] + f[q - s], den, rden);
 }
 // backward difference u(n)-u(n-1)
 template <int ORDER>
-__device__ __forceinline__ double d_bwd(const double *f, long long q, long long s, double delta)
+__device__ __forceinline__ double d_bwd(const double *f, long long q, long long s, double den, double rden)
 {
-    if (ORDER == 2) return (f[q] - f[q - s]) / delta;
-    return (27.0 * f[q] - 27.0 * f[q - s] - f[q + s] + f[q - 2 * s]) / (24.0 * delta);
+    if (ORDER == 2) return div_exact(f[q] - f[q - s], den, rden);
+    return div_exact(27.0 * f[q] - 27.0 * f[q - s] - f[q + s] + f[q - 2 * s], den, rden);
 }
 
 template <int ORDER, int TX, int TY>
@@ -64,22 +67,22 @@ k_stress2d(const __grid_constant__ Params2D p)
         const double lambda_half_x = 0.5 * (p.lambda[q + 1] + p.lambda[q]);
         const double mu_half_x = 0.5 * (p.mu[q + 1] + p.mu[q]);
         const double lambda_plus_two_mu_half_x = lambda_half_x + 2.0 * mu_half_x;
-        double value_dvx_dx = d_fwd<ORDER>(p.vx, q, 1, p.deltax);
-        double value_dvy_dy = d_bwd<ORDER>(p.vy, q, pitch, p.deltay);
-        if (in_x) value_dvx_dx = cpml_apply2(p.mx[0], qx, p.cx.b_half[i], p.cx.a_half[i], p.cx.K_half[i], value_dvx_dx);
-        if (in_y) value_dvy_dy = cpml_apply2(p.my[0], qy, p.cy.b[j], p.cy.a[j], p.cy.K[j], value_dvy_dy);
+        double value_dvx_dx = d_fwd<ORDER>(p.vx, q, 1, p.denx, p.rdenx);
+        double value_dvy_dy = d_bwd<ORDER>(p.vy, q, pitch, p.deny, p.rdeny);
+        if (in_x) value_dvx_dx = cpml_apply2(p.mx[0], qx, p.cx.b_half[i], p.cx.a_half[i], p.cx.K_half[i], p.cx.rK_half[i], value_dvx_dx);
+        if (in_y) value_dvy_dy = cpml_apply2(p.my[0], qy, p.cy.b[j], p.cy.a[j], p.cy.K[j], p.cy.rK[j], value_dvy_dy);
         p.sxx[q] = p.sxx[q] + (lambda_plus_two_mu_half_x * value_dvx_dx + lambda_half_x * value_dvy_dy) * DELTAT;
         p.syy[q] = p.syy[q] + (lambda_half_x * value_dvx_dx + lambda_plus_two_mu_half_x * value_dvy_dy) * DELTAT;
     }
     if (i >= 2 && j <= p.ny - 1) {
         const double mu_half_y = 0.5 * (p.mu[q + pitch] + p.mu[q]);
-        double value_dvy_dx = d_bwd<ORDER>(p.vy, q, 1, p.deltax);
-        double value_dvx_dy = d_fwd<ORDER>(p.vx, q, pitch, p.deltay);
-        if (in_x) value_dvy_dx = cpml_apply2(p.mx[1], qx, p.cx.b[i], p.cx.a[i], p.cx.K[i], value_dvy_dx);
+        double value_dvy_dx = d_bwd<ORDER>(p.vy, q, 1, p.denx, p.rdenx);
+        double value_dvx_dy = d_fwd<ORDER>(p.vx, q, pitch, p.deny, p.rdeny);
+        if (in_x) value_dvy_dx = cpml_apply2(p.mx[1], qx, p.cx.b[i], p.cx.a[i], p.cx.K[i], p.cx.rK[i], value_dvy_dx);
         // quirk B3: the fourth-order program divides by K_y(j) here (2D-4th :596), the
         // second-order one by K_y_half(j) (2D-2nd :595)
         if (in_y) value_dvx_dy = cpml_apply2(p.my[1], qy, p.cy.b_half[j], p.cy.a_half[j],
-                                             ORDER == 4 ? p.cy.K[j] : p.cy.K_half[j], value_dvx_dy);
+                                             ORDER == 4 ? p.cy.K[j] : p.cy.K_half[j], p.cy.rK_half[j], value_dvx_dy);
         p.sxy[q] = p.sxy[q] + mu_half_y * (value_dvy_dx + value_dvx_dy) * DELTAT;
     }
 }
@@ -129,17 +132,17 @@ k_velocity2d(const __grid_constant__ Params2D p)
         double vx = p.vx[q], vy = p.vy[q];
 
         if (i >= 2 && j >= 2) {
-            double value_dsigmaxx_dx = d_bwd<ORDER>(p.sxx, q, 1, p.deltax);
-            double value_dsigmaxy_dy = d_bwd<ORDER>(p.sxy, q, pitch, p.deltay);
-            if (in_x) value_dsigmaxx_dx = cpml_apply2(p.mx[2], qx, p.cx.b[i], p.cx.a[i], p.cx.K[i], value_dsigmaxx_dx);
-            if (in_y) value_dsigmaxy_dy = cpml_apply2(p.my[2], qy, p.cy.b[j], p.cy.a[j], p.cy.K[j], value_dsigmaxy_dy);
+            double value_dsigmaxx_dx = d_bwd<ORDER>(p.sxx, q, 1, p.denx, p.rdenx);
+            double value_dsigmaxy_dy = d_bwd<ORDER>(p.sxy, q, pitch, p.deny, p.rdeny);
+            if (in_x) value_dsigmaxx_dx = cpml_apply2(p.mx[2], qx, p.cx.b[i], p.cx.a[i], p.cx.K[i], p.cx.rK[i], value_dsigmaxx_dx);
+            if (in_y) value_dsigmaxy_dy = cpml_apply2(p.my[2], qy, p.cy.b[j], p.cy.a[j], p.cy.K[j], p.cy.rK[j], value_dsigmaxy_dy);
             vx = vx + (value_dsigmaxx_dx + value_dsigmaxy_dy) * DELTAT / rho;
         }
         if (i <= p.nx - 1 && j <= p.ny - 1) {
-            double value_dsigmaxy_dx = d_fwd<ORDER>(p.sxy, q, 1, p.deltax);
-            double value_dsigmayy_dy = d_fwd<ORDER>(p.syy, q, pitch, p.deltay);
-            if (in_x) value_dsigmaxy_dx = cpml_apply2(p.mx[3], qx, p.cx.b_half[i], p.cx.a_half[i], p.cx.K_half[i], value_dsigmaxy_dx);
-            if (in_y) value_dsigmayy_dy = cpml_apply2(p.my[3], qy, p.cy.b_half[j], p.cy.a_half[j], p.cy.K_half[j], value_dsigmayy_dy);
+            double value_dsigmaxy_dx = d_fwd<ORDER>(p.sxy, q, 1, p.denx, p.rdenx);
+            double value_dsigmayy_dy = d_fwd<ORDER>(p.syy, q, pitch, p.deny, p.rdeny);
+            if (in_x) value_dsigmaxy_dx = cpml_apply2(p.mx[3], qx, p.cx.b_half[i], p.cx.a_half[i], p.cx.K_half[i], p.cx.rK_half[i], value_dsigmaxy_dx);
+            if (in_y) value_dsigmayy_dy = cpml_apply2(p.my[3], qy, p.cy.b_half[j], p.cy.a_half[j], p.cy.K_half[j], p.cy.rK_half[j], value_dsigmayy_dy);
             vy = vy + (value_dsigmaxy_dx + value_dsigmayy_dy) * DELTAT / rho_half_x_half_y;
         }
         if (i == p.isrc && j == p.jsrc) {               // 2D-2nd :663-667
@@ -158,10 +161,12 @@ k_velocity2d(const __grid_constant__ Params2D p)
             const double l = p.lambda[q], m = p.mu[q];
             const double sxx = p.sxx[q], syy = p.syy[q], sxy = p.sxy[q];
             ekin = 0.5 * (rho * (vx * vx + vy * vy));
+            // one division for both 1/(4 mu (lambda + mu)) and 1/(2 mu): the energy is a sum whose
+            // order differs from the reference's anyway (tolerance 1e-11, not bitwise)
             const double inv4 = 1.0 / (4.0 * m * (l + m));
             const double epsilon_xx = ((l + 2.0 * m) * sxx - l * syy) * inv4;
             const double epsilon_yy = ((l + 2.0 * m) * syy - l * sxx) * inv4;
-            const double epsilon_xy = sxy / (2.0 * m);
+            const double epsilon_xy = sxy * (inv4 * (2.0 * (l + m)));
             epot = 0.5 * (epsilon_xx * sxx + epsilon_yy * syy + 2.0 * epsilon_xy * sxy);
         }
     }

@@ -26,8 +26,11 @@
 // reference slab the same taps read zero here: f(k+1) of the backward z differences on the last
 // plane of a slab, f(k-1) of the forward z differences on the first plane of a slab.
 //
-// Compiled with -fmad=false, every division kept (/24, /K, /(1 - dt/2 tauinv)): velocities,
-// stresses and memory variables are bit-identical to an IEEE (non-FMA) build of the reference.
+// Compiled with -fmad=false; every division of the reference (/24, /K, /3, /(1 - dt/2 tauinv)) is
+// a division by a constant or by a profile value, done by div_exact (cpml_internal.h): the
+// correctly rounded quotient from the divisor's reciprocal and two FMA residual corrections, five
+// FP64 operations instead of the generic ~60-instruction sequence.  Velocities, stresses and
+// memory variables stay bit-identical to an IEEE (non-FMA) build of the reference.
 #include "cpml_internal.h"
 
 namespace cpml {
@@ -37,13 +40,13 @@ __device__ __forceinline__ void vst(double *p, double v) { __stcs(p, v); }
 __device__ __forceinline__ double2 vld2(const double2 *p) { return __ldcs(p); }
 __device__ __forceinline__ void vst2(double2 *p, double2 v) { __stcs(p, v); }
 
-// memory_x = b * memory_x + a * value ; value / K + memory_x   (e.g. :993-999)
-__device__ __forceinline__ double vcpml(double *__restrict__ mem, long long q, double b, double a, double K, double value)
+// memory_x = b * memory_x + a * value ; value / K + memory_x   (e.g. :993-999); rK = RN(1/K)
+__device__ __forceinline__ double vcpml(double *__restrict__ mem, long long q, double b, double a, double K, double rK, double value)
 {
     double m = mem[q];
     m = b * m + a * value;
     mem[q] = m;
-    return value / K + m;
+    return div_exact(value, K, rK) + m;
 }
 
 __device__ __forceinline__ int vshell(int i, int lo, int hi) { return i <= lo ? i - 1 : lo + (i - hi); }
@@ -51,14 +54,14 @@ __device__ __forceinline__ int vshell(int i, int lo, int hi) { return i <= lo ? 
 // (27 a - 27 b - c + d) * ONE_OVER_DELTA / 24   (:989-991)
 __device__ __forceinline__ double d4(double a, double b, double c, double d, double od)
 {
-    return (27.0 * a - 27.0 * b - c + d) * od / 24.0;
+    return div_exact((27.0 * a - 27.0 * b - c + d) * od, 24.0, 1.0 / 24.0);
 }
 
 // Unp1 = (Un + deltat*(Sn + 0.5*tauinv*Un)) / (1 - deltat*0.5*tauinv)   (:1003-1009)
-__device__ __forceinline__ double evolve(double Un, double Sn, double tauinv, double den, double dt)
+__device__ __forceinline__ double evolve(double Un, double Sn, double tauinv, double den, double rden, double dt)
 {
     const double tauinvUn = tauinv * Un;
-    return (Un + dt * (Sn + 0.5 * tauinvUn)) / den;
+    return div_exact(Un + dt * (Sn + 0.5 * tauinvUn), den, rden);
 }
 
 template <int NT>
@@ -109,8 +112,11 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
         const double odx = p.odx, ody = p.ody, odz = p.odz, dt = p.dt;
 
         double ax = 0, bx = 0, Kx = 1, axh = 0, bxh = 0, Kxh = 1, ay = 0, by = 0, Ky = 1, ayh = 0, byh = 0, Kyh = 1;
-        if (in_x) { ax = p.cx.a[i]; bx = p.cx.b[i]; Kx = p.cx.K[i]; axh = p.cx.a_half[i]; bxh = p.cx.b_half[i]; Kxh = p.cx.K_half[i]; }
-        if (in_y) { ay = p.cy.a[j]; by = p.cy.b[j]; Ky = p.cy.K[j]; ayh = p.cy.a_half[j]; byh = p.cy.b_half[j]; Kyh = p.cy.K_half[j]; }
+        double rKx = 1, rKxh = 1, rKy = 1, rKyh = 1;
+        if (in_x) { ax = p.cx.a[i]; bx = p.cx.b[i]; Kx = p.cx.K[i]; axh = p.cx.a_half[i]; bxh = p.cx.b_half[i]; Kxh = p.cx.K_half[i];
+                    rKx = p.cx.rK[i]; rKxh = p.cx.rK_half[i]; }
+        if (in_y) { ay = p.cy.a[j]; by = p.cy.b[j]; Ky = p.cy.K[j]; ayh = p.cy.a_half[j]; byh = p.cy.b_half[j]; Kyh = p.cy.K_half[j];
+                    rKy = p.cy.rK[j]; rKyh = p.cy.rK_half[j]; }
 
         // z windows
         double vx_m = p.vx[q - pl], vx_c = p.vx[q], vx_p = p.vx[q + pl];
@@ -136,13 +142,14 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
 
             const bool in_z = (kg <= p.zlo) || (kg >= p.zhi);
             long long qx = 0, qy = 0, qz = 0;
-            double az = 0, bz = 0, Kz = 1, azh = 0, bzh = 0, Kzh = 1;
+            double az = 0, bz = 0, Kz = 1, azh = 0, bzh = 0, Kzh = 1, rKz = 1, rKzh = 1;
             if (in_x) qx = ((long long)(k - 1) * p.ny + (j - 1)) * p.sxp + sx;
             if (in_y) qy = ((long long)(k - 1) * p.sy + sy) * pitch + (i - 1);
             if (in_z) {
                 qz = ((long long)(vshell(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1);
                 az = p.cz.a[kg]; bz = p.cz.b[kg]; Kz = p.cz.K[kg];
                 azh = p.cz.a_half[kg]; bzh = p.cz.b_half[kg]; Kzh = p.cz.K_half[kg];
+                rKz = p.cz.rK[kg]; rKzh = p.cz.rK_half[kg];
             }
             // quirk B6: taps the reference's MPI exchange never delivers
             const int kmod = kg % p.nzl_e;
@@ -154,17 +161,18 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
                 double duxdx = d4(vx_ip1, vx_c, vx_ip2, vx_im1, odx);
                 double duydy = d4(vy_c, vy_jm1, vy_jp1, vy_jm2, ody);
                 double duzdz = d4(vz_c, vz_m, cut_up ? 0.0 : vz_p, vz_mm, odz);
-                if (in_x) duxdx = vcpml(p.mx[0], qx, bxh, axh, Kxh, duxdx);
-                if (in_y) duydy = vcpml(p.my[0], qy, by, ay, Ky, duydy);
-                if (in_z) duzdz = vcpml(p.mz[0], qz, bz, az, Kz, duzdz);
+                if (in_x) duxdx = vcpml(p.mx[0], qx, bxh, axh, Kxh, rKxh, duxdx);
+                if (in_y) duydy = vcpml(p.my[0], qy, by, ay, Ky, rKy, duydy);
+                if (in_z) duzdz = vcpml(p.mz[0], qz, bz, az, Kz, rKz, duzdz);
                 const double div = duxdx + duydy + duzdz;
+                const double div3 = div_exact(div, 3.0, 1.0 / 3.0);      // div/DIM
 
-                e1.x = evolve(e1.x, div * p.phi1[0], p.tauinv1[0], p.den1[0], dt);
-                e1.y = evolve(e1.y, div * p.phi1[1], p.tauinv1[1], p.den1[1], dt);
-                e11.x = evolve(e11.x, (duxdx - div / 3.0) * p.phi2[0], p.tauinv2[0], p.den2[0], dt);
-                e11.y = evolve(e11.y, (duxdx - div / 3.0) * p.phi2[1], p.tauinv2[1], p.den2[1], dt);
-                e22.x = evolve(e22.x, (duydy - div / 3.0) * p.phi2[0], p.tauinv2[0], p.den2[0], dt);
-                e22.y = evolve(e22.y, (duydy - div / 3.0) * p.phi2[1], p.tauinv2[1], p.den2[1], dt);
+                e1.x = evolve(e1.x, div * p.phi1[0], p.tauinv1[0], p.den1[0], p.rden1[0], dt);
+                e1.y = evolve(e1.y, div * p.phi1[1], p.tauinv1[1], p.den1[1], p.rden1[1], dt);
+                e11.x = evolve(e11.x, (duxdx - div3) * p.phi2[0], p.tauinv2[0], p.den2[0], p.rden2[0], dt);
+                e11.y = evolve(e11.y, (duxdx - div3) * p.phi2[1], p.tauinv2[1], p.den2[1], p.rden2[1], dt);
+                e22.x = evolve(e22.x, (duydy - div3) * p.phi2[0], p.tauinv2[0], p.den2[0], p.rden2[0], dt);
+                e22.y = evolve(e22.y, (duydy - div3) * p.phi2[1], p.tauinv2[1], p.den2[1], p.rden2[1], dt);
                 vst2(p.e1 + q, e1); vst2(p.e11 + q, e11); vst2(p.e22 + q, e22);
 
                 // relaxed moduli times the memory variables (:1054-1060)
@@ -186,11 +194,11 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
             if (do_xy) {
                 double duydx = d4(vy_c, vy_im1, vy_ip1, vy_im2, odx);
                 double duxdy = d4(vx_jp1, vx_c, vx_jp2, vx_jm1, ody);
-                if (in_x) duydx = vcpml(p.mx[1], qx, bx, ax, Kx, duydx);
-                if (in_y) duxdy = vcpml(p.my[1], qy, byh, ayh, Kyh, duxdy);
+                if (in_x) duydx = vcpml(p.mx[1], qx, bx, ax, Kx, rKx, duydx);
+                if (in_y) duxdy = vcpml(p.my[1], qy, byh, ayh, Kyh, rKyh, duxdy);
                 const double g = duxdy + duydx;
-                e12.x = evolve(e12.x, g * p.phi2[0], p.tauinv2[0], p.den2[0], dt);
-                e12.y = evolve(e12.y, g * p.phi2[1], p.tauinv2[1], p.den2[1], dt);
+                e12.x = evolve(e12.x, g * p.phi2[0], p.tauinv2[0], p.den2[0], p.rden2[0], dt);
+                e12.y = evolve(e12.y, g * p.phi2[1], p.tauinv2[1], p.den2[1], p.rden2[1], dt);
                 vst2(p.e12 + q, e12);
                 sxy = sxy + dt * p.mu * (e12.x + e12.y);
                 sxy = sxy + p.mu_u * g * dt;
@@ -202,11 +210,11 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
                 if (do_xz) {
                     double duzdx = d4(vz_c, vz_im1, vz_ip1, vz_im2, odx);
                     double duxdz = d4(vx_p, vx_c, vx_pp, cut_dn ? 0.0 : vx_m, odz);
-                    if (in_x) duzdx = vcpml(p.mx[2], qx, bx, ax, Kx, duzdx);
-                    if (in_z) duxdz = vcpml(p.mz[1], qz, bzh, azh, Kzh, duxdz);
+                    if (in_x) duzdx = vcpml(p.mx[2], qx, bx, ax, Kx, rKx, duzdx);
+                    if (in_z) duxdz = vcpml(p.mz[1], qz, bzh, azh, Kzh, rKzh, duxdz);
                     const double g = duxdz + duzdx;
-                    e13.x = evolve(e13.x, g * p.phi2[0], p.tauinv2[0], p.den2[0], dt);
-                    e13.y = evolve(e13.y, g * p.phi2[1], p.tauinv2[1], p.den2[1], dt);
+                    e13.x = evolve(e13.x, g * p.phi2[0], p.tauinv2[0], p.den2[0], p.rden2[0], dt);
+                    e13.y = evolve(e13.y, g * p.phi2[1], p.tauinv2[1], p.den2[1], p.rden2[1], dt);
                     vst2(p.e13 + q, e13);
                     sxz = sxz + dt * p.mu * (e13.x + e13.y);
                     sxz = sxz + p.mu_u * g * dt;
@@ -216,11 +224,11 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
                 if (do_yz) {
                     double duzdy = d4(vz_jp1, vz_c, vz_jp2, vz_jm1, ody);
                     double duydz = d4(vy_p, vy_c, vy_pp, cut_dn ? 0.0 : vy_m, odz);
-                    if (in_y) duzdy = vcpml(p.my[2], qy, byh, ayh, Kyh, duzdy);
-                    if (in_z) duydz = vcpml(p.mz[2], qz, bzh, azh, Kzh, duydz);
+                    if (in_y) duzdy = vcpml(p.my[2], qy, byh, ayh, Kyh, rKyh, duzdy);
+                    if (in_z) duydz = vcpml(p.mz[2], qz, bzh, azh, Kzh, rKzh, duydz);
                     const double g = duydz + duzdy;
-                    e23.x = evolve(e23.x, g * p.phi2[0], p.tauinv2[0], p.den2[0], dt);
-                    e23.y = evolve(e23.y, g * p.phi2[1], p.tauinv2[1], p.den2[1], dt);
+                    e23.x = evolve(e23.x, g * p.phi2[0], p.tauinv2[0], p.den2[0], p.rden2[0], dt);
+                    e23.y = evolve(e23.y, g * p.phi2[1], p.tauinv2[1], p.den2[1], p.rden2[1], dt);
                     vst2(p.e23 + q, e23);
                     syz = syz + dt * p.mu * (e23.x + e23.y);
                     syz = syz + p.mu_u * g * dt;
@@ -286,8 +294,11 @@ k_vvelocity3d(const __grid_constant__ ParamsV3D p)
         const double odx = p.odx, ody = p.ody, odz = p.odz, dt_r = p.dt_over_rho;
 
         double ax = 0, bx = 0, Kx = 1, axh = 0, bxh = 0, Kxh = 1, ay = 0, by = 0, Ky = 1, ayh = 0, byh = 0, Kyh = 1;
-        if (in_x) { ax = p.cx.a[i]; bx = p.cx.b[i]; Kx = p.cx.K[i]; axh = p.cx.a_half[i]; bxh = p.cx.b_half[i]; Kxh = p.cx.K_half[i]; }
-        if (in_y) { ay = p.cy.a[j]; by = p.cy.b[j]; Ky = p.cy.K[j]; ayh = p.cy.a_half[j]; byh = p.cy.b_half[j]; Kyh = p.cy.K_half[j]; }
+        double rKx = 1, rKxh = 1, rKy = 1, rKyh = 1;
+        if (in_x) { ax = p.cx.a[i]; bx = p.cx.b[i]; Kx = p.cx.K[i]; axh = p.cx.a_half[i]; bxh = p.cx.b_half[i]; Kxh = p.cx.K_half[i];
+                    rKx = p.cx.rK[i]; rKxh = p.cx.rK_half[i]; }
+        if (in_y) { ay = p.cy.a[j]; by = p.cy.b[j]; Ky = p.cy.K[j]; ayh = p.cy.a_half[j]; byh = p.cy.b_half[j]; Kyh = p.cy.K_half[j];
+                    rKy = p.cy.rK[j]; rKyh = p.cy.rK_half[j]; }
 
         // z windows
         double sxz_mm = p.sxz[q - 2 * pl], sxz_m = p.sxz[q - pl], sxz_c = p.sxz[q];
@@ -308,13 +319,14 @@ k_vvelocity3d(const __grid_constant__ ParamsV3D p)
 
             const bool in_z = (kg <= p.zlo) || (kg >= p.zhi);
             long long qx = 0, qy = 0, qz = 0;
-            double az = 0, bz = 0, Kz = 1, azh = 0, bzh = 0, Kzh = 1;
+            double az = 0, bz = 0, Kz = 1, azh = 0, bzh = 0, Kzh = 1, rKz = 1, rKzh = 1;
             if (in_x) qx = ((long long)(k - 1) * p.ny + (j - 1)) * p.sxp + sx;
             if (in_y) qy = ((long long)(k - 1) * p.sy + sy) * pitch + (i - 1);
             if (in_z) {
                 qz = ((long long)(vshell(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1);
                 az = p.cz.a[kg]; bz = p.cz.b[kg]; Kz = p.cz.K[kg];
                 azh = p.cz.a_half[kg]; bzh = p.cz.b_half[kg]; Kzh = p.cz.K_half[kg];
+                rKz = p.cz.rK[kg]; rKzh = p.cz.rK_half[kg];
             }
             const int kmod = kg % p.nzl_e;
             const bool cut_up = (kmod == 0);
@@ -325,18 +337,18 @@ k_vvelocity3d(const __grid_constant__ ParamsV3D p)
                     double d1 = d4(sxx_c, sxx_im1, sxx_ip1, sxx_im2, odx);
                     double d2 = d4(sxy_c, sxy_jm1, sxy_jp1, sxy_jm2, ody);
                     double d3 = d4(sxz_c, sxz_m, cut_up ? 0.0 : sxz_p, sxz_mm, odz);
-                    if (in_x) d1 = vcpml(p.mx[3], qx, bx, ax, Kx, d1);
-                    if (in_y) d2 = vcpml(p.my[3], qy, by, ay, Ky, d2);
-                    if (in_z) d3 = vcpml(p.mz[3], qz, bz, az, Kz, d3);
+                    if (in_x) d1 = vcpml(p.mx[3], qx, bx, ax, Kx, rKx, d1);
+                    if (in_y) d2 = vcpml(p.my[3], qy, by, ay, Ky, rKy, d2);
+                    if (in_z) d3 = vcpml(p.mz[3], qz, bz, az, Kz, rKz, d3);
                     vx = dt_r * (d1 + d2 + d3) + vx;
                 }
                 if (do_vy) {                                         // :1266-1284
                     double d1 = d4(sxy_ip1, sxy_c, sxy_ip2, sxy_im1, odx);
                     double d2 = d4(syy_jp1, syy_c, syy_jp2, syy_jm1, ody);
                     double d3 = d4(syz_c, syz_m, cut_up ? 0.0 : syz_p, syz_mm, odz);
-                    if (in_x) d1 = vcpml(p.mx[4], qx, bxh, axh, Kxh, d1);
-                    if (in_y) d2 = vcpml(p.my[4], qy, byh, ayh, Kyh, d2);
-                    if (in_z) d3 = vcpml(p.mz[4], qz, bz, az, Kz, d3);
+                    if (in_x) d1 = vcpml(p.mx[4], qx, bxh, axh, Kxh, rKxh, d1);
+                    if (in_y) d2 = vcpml(p.my[4], qy, byh, ayh, Kyh, rKyh, d2);
+                    if (in_z) d3 = vcpml(p.mz[4], qz, bz, az, Kz, rKz, d3);
                     vy = dt_r * (d1 + d2 + d3) + vy;
                 }
             }
@@ -344,9 +356,9 @@ k_vvelocity3d(const __grid_constant__ ParamsV3D p)
                 double d1 = d4(sxz_ip1, sxz_c, sxz_ip2, sxz_im1, odx);
                 double d2 = d4(syz_c, syz_jm1, syz_jp1, syz_jm2, ody);
                 double d3 = d4(szz_p, szz_c, szz_pp, cut_dn ? 0.0 : szz_m, odz);
-                if (in_x) d1 = vcpml(p.mx[5], qx, bxh, axh, Kxh, d1);
-                if (in_y) d2 = vcpml(p.my[5], qy, by, ay, Ky, d2);
-                if (in_z) d3 = vcpml(p.mz[5], qz, bzh, azh, Kzh, d3);
+                if (in_x) d1 = vcpml(p.mx[5], qx, bxh, axh, Kxh, rKxh, d1);
+                if (in_y) d2 = vcpml(p.my[5], qy, by, ay, Ky, rKy, d2);
+                if (in_z) d3 = vcpml(p.mz[5], qz, bzh, azh, Kzh, rKzh, d3);
                 vz = dt_r * (d1 + d2 + d3) + vz;
             }
 
