@@ -756,8 +756,8 @@ static int32_t finalize(cpml_handle *h)
         h->vkchunk = (h->nzl + nzc - 1) / nzc;
         h->vgrid = dim3((c.nx + h->vtx - 1) / h->vtx, (c.ny + h->vty - 1) / h->vty, (h->nzl + h->vkchunk - 1) / h->vkchunk);
         h->nblocks = (int)(h->vgrid.x * h->vgrid.y * h->vgrid.z);
-        CK(cudaMalloc(&h->d_partials, 2 * (size_t)h->nblocks * sizeof(double)));
-        CK(cudaMemset(h->d_partials, 0, 2 * (size_t)h->nblocks * sizeof(double)));
+        CK(cudaMalloc(&h->d_partials, 3 * (size_t)h->nblocks * sizeof(double)));
+        CK(cudaMemset(h->d_partials, 0, 3 * (size_t)h->nblocks * sizeof(double)));
     } else if (c.ndim == 3) {
         // CPML_KERNEL=reg selects the register-marching kernels of kernels_3d.cu (A/B runs)
         const char *kv = getenv("CPML_KERNEL");
@@ -961,7 +961,7 @@ static int32_t half_step(cpml_handle *h, int32_t it, int phase)
     if (h->visco) {
         const ParamsV3D p = make_pv(h, it);
         if (phase == 0) launch_vstress3d(p, h->vgrid, h->stream); else launch_vvelocity3d(p, h->vgrid, h->stream);
-        h->n_launches++;
+        h->n_launches += phase == 0 ? visco_stress_launches() : 1;
     } else if (h->cfg.ndim == 3) {
         const Params3D p = make_p3(h, it);
         if (h->use_tma) {
@@ -1011,6 +1011,7 @@ extern "C" int32_t cpml_step_finish(cpml_handle *h, int32_t it)
     const cpml_config &c = h->cfg;
     Post3D p{};
     p.partials = h->d_partials; p.nblocks = h->nblocks;
+    p.npot = h->visco ? 2 * h->nblocks : h->nblocks;
     p.energy_k = h->d_ek; p.energy_p = h->d_ep;
     p.it = it; p.nstep = c.nstep; p.nrec = c.nrec;
     p.ix_rec = h->d_ix_rec; p.iy_rec = h->d_iy_rec;

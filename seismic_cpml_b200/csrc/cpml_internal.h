@@ -49,6 +49,10 @@ struct AxisCoef {
 // every input; zero dividends take the short path too.  Five dependent FP64 operations instead of
 // the ~60-instruction generic sequence (whose slow path is also taken for every zero dividend,
 // i.e. on the whole quiescent part of the grid).
+// The generic division, kept out of line so that the 20-odd call sites of a kernel share one copy
+// (inlined, the fallbacks made up a third of the viscoelastic stress kernel's code).
+static __device__ __noinline__ double div_generic(double a, double c) { return a / c; }
+
 __device__ __forceinline__ double div_exact(double a, double c, double y)
 {
     const double q0 = a * y;
@@ -59,7 +63,7 @@ __device__ __forceinline__ double div_exact(double a, double c, double y)
     const unsigned e = (unsigned)__double2hiint(a) & 0x7ff00000u;       // biased exponent field of a
     if (e > 0x0c800000u && e < 0x73000000u) return q;                    // 2^-822 < |a| < 2^+817
     if (a == 0.0) return q0;                                             // +-0 / c
-    return a / c;
+    return div_generic(a, c);
 }
 #endif
 
@@ -134,7 +138,8 @@ struct Box3D {
 
 struct Post3D {
     const double *partials;
-    int nblocks;
+    int nblocks;                   // kinetic partials [0, nblocks)
+    int npot;                      // potential partials [nblocks, nblocks + npot)
     double *energy_k, *energy_p;   // traces, slot it-1 is written
     int it, nstep, nrec;
     const int *ix_rec, *iy_rec;
@@ -168,7 +173,7 @@ struct ParamsV3D {
     const double *src_x, *src_y;
     int npml;
     double half_rho, c2lm, inv_den, inv_2mu;
-    double *partials;         // [0, nblocks) kinetic (velocity kernel), [nblocks, 2 nblocks) potential (stress kernel)
+    double *partials;         // [0, nb) kinetic (velocity kernel), [nb, 2nb) and [2nb, 3nb) potential (stress launches)
     int nblocks;
     int kchunk;               // planes marched by one block
 };
@@ -219,6 +224,7 @@ void launch_wait(const unsigned long long *flag_a, const unsigned long long *fla
 void launch_vstress3d(const ParamsV3D &p, dim3 grid, cudaStream_t s);
 void launch_vvelocity3d(const ParamsV3D &p, dim3 grid, cudaStream_t s);
 void visco_tile(int *tx, int *ty);
+int visco_stress_launches();
 void launch_stress2d(const Params2D &p, dim3 grid, dim3 block, cudaStream_t s);
 void launch_velocity2d(const Params2D &p, dim3 grid, dim3 block, cudaStream_t s);
 void launch_post2d(const Post2D &p, cudaStream_t s);

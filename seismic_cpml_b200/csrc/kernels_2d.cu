@@ -82,7 +82,8 @@ k_stress2d(const __grid_constant__ Params2D p)
         // quirk B3: the fourth-order program divides by K_y(j) here (2D-4th :596), the
         // second-order one by K_y_half(j) (2D-2nd :595)
         if (in_y) value_dvx_dy = cpml_apply2(p.my[1], qy, p.cy.b_half[j], p.cy.a_half[j],
-                                             ORDER == 4 ? p.cy.K[j] : p.cy.K_half[j], p.cy.rK_half[j], value_dvx_dy);
+                                             ORDER == 4 ? p.cy.K[j] : p.cy.K_half[j],
+                                             ORDER == 4 ? p.cy.rK[j] : p.cy.rK_half[j], value_dvx_dy);
         p.sxy[q] = p.sxy[q] + mu_half_y * (value_dvy_dx + value_dvx_dy) * DELTAT;
     }
 }

@@ -366,10 +366,8 @@ __global__ void __launch_bounds__(256) k_post3d(const __grid_constant__ Post3D p
 {
     __shared__ double red[16];
     double a = 0.0, b = 0.0;
-    for (int q = threadIdx.x; q < p.nblocks; q += 256) {
-        a += p.partials[q];
-        b += p.partials[p.nblocks + q];
-    }
+    for (int q = threadIdx.x; q < p.nblocks; q += 256) a += p.partials[q];
+    for (int q = threadIdx.x; q < p.npot; q += 256) b += p.partials[p.nblocks + q];
     block_sum2<256>(a, b, red);
     if (threadIdx.x == 0) {
         p.energy_k[p.it - 1] = a;

@@ -81,14 +81,43 @@ __device__ __forceinline__ double block_sum1(double a, double *smem /* NT/32 */)
     return a;
 }
 
+// Coefficient tables of a block: rows a, b, K, 1/K, a_half, b_half, K_half, 1/K_half; columns /
+// rows beyond the grid get the identity (never used).
 template <int TX, int TY>
-__global__ void __launch_bounds__(TX *TY)
+__device__ __forceinline__ void load_coef_tables(const ParamsV3D &p, double (*cxs)[TX], double (*cys)[TY])
+{
+    const int t = threadIdx.y * TX + threadIdx.x;
+    for (int e = t; e < 8 * (TX + TY); e += TX * TY) {
+        const bool isx = e < 8 * TX;
+        const int m = isx ? e / TX : (e - 8 * TX) / TY;
+        const int c = isx ? e % TX : (e - 8 * TX) % TY;
+        const int idx = isx ? blockIdx.x * TX + c + 1 : blockIdx.y * TY + c + 1;
+        const AxisCoef &a = isx ? p.cx : p.cy;
+        const double *src = m == 0 ? a.a : m == 1 ? a.b : m == 2 ? a.K : m == 3 ? a.rK : m == 4 ? a.a_half : m == 5 ? a.b_half
+                          : m == 6 ? a.K_half : a.rK_half;
+        const double v = idx <= (isx ? p.nx : p.ny) ? src[idx] : ((m == 0 || m == 4) ? 0.0 : 1.0);
+        if (isx) cxs[m][c] = v; else cys[m][c] = v;
+    }
+    __syncthreads();
+}
+
+// PART selects what one launch updates: 0 = all six stresses (one launch per step, the default),
+// 1 = the normal stresses (sigmaxx/yy/zz, e1, e11, e22, their sigma_R), 2 = the shear stresses
+// (sigmaxy/xz/yz, e12, e13, e23, their sigma_R).  Every load is scoped to the nest that uses it,
+// which is what lets the fused kernel run in 128 registers (16 warps per SM) without spilling; the
+// split launches (CPML_VSPLIT=1) need fewer still but read the velocity planes twice and measured
+// 7 % slower on B200 (profiles/r01_v6_visco_sweep.txt).
+template <int TX, int TY, int MINB, int PART>
+__global__ void __launch_bounds__(TX *TY, MINB)
 k_vstress3d(const __grid_constant__ ParamsV3D p)
 {
+    constexpr bool NORMAL = PART != 2, SHEAR = PART != 1;
     __shared__ double red[TX * TY / 32];
+    __shared__ double cxs[8][TX], cys[8][TY];        // a, b, K, 1/K, a_half, b_half, K_half, 1/K_half
     const int i = blockIdx.x * TX + threadIdx.x + 1;
     const int j = blockIdx.y * TY + threadIdx.y + 1;
     double epot = 0.0;
+    load_coef_tables<TX, TY>(p, cxs, cys);
 
     if (i <= p.nx && j <= p.ny) {
         const int kb = 1 + blockIdx.z * p.kchunk;
@@ -110,36 +139,21 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
                              (j >= p.npml) && (j <= p.ny - p.npml + 1);            // :1391-1392
 
         const double odx = p.odx, ody = p.ody, odz = p.odz, dt = p.dt;
+        // x / y C-PML coefficients of this block's columns and rows sit in shared memory (cxs, cys):
+        // only shell points read them, at the point of use, so they cost no registers in the interior
+        const double *const cxc = &cxs[0][threadIdx.x], *const cyc = &cys[0][threadIdx.y];
 
-        double ax = 0, bx = 0, Kx = 1, axh = 0, bxh = 0, Kxh = 1, ay = 0, by = 0, Ky = 1, ayh = 0, byh = 0, Kyh = 1;
-        double rKx = 1, rKxh = 1, rKy = 1, rKyh = 1;
-        if (in_x) { ax = p.cx.a[i]; bx = p.cx.b[i]; Kx = p.cx.K[i]; axh = p.cx.a_half[i]; bxh = p.cx.b_half[i]; Kxh = p.cx.K_half[i];
-                    rKx = p.cx.rK[i]; rKxh = p.cx.rK_half[i]; }
-        if (in_y) { ay = p.cy.a[j]; by = p.cy.b[j]; Ky = p.cy.K[j]; ayh = p.cy.a_half[j]; byh = p.cy.b_half[j]; Kyh = p.cy.K_half[j];
-                    rKy = p.cy.rK[j]; rKyh = p.cy.rK_half[j]; }
-
-        // z windows
-        double vx_m = p.vx[q - pl], vx_c = p.vx[q], vx_p = p.vx[q + pl];
-        double vy_m = p.vy[q - pl], vy_c = p.vy[q], vy_p = p.vy[q + pl];
-        double vz_mm = p.vz[q - 2 * pl], vz_m = p.vz[q - pl], vz_c = p.vz[q];
+        // z windows of the fourth-order operator, carried in registers
+        double vx_m = 0, vx_c = 0, vx_p = 0, vy_m = 0, vy_c = 0, vy_p = 0, vz_mm = 0, vz_m = 0, vz_c = 0;
+        if (SHEAR) {
+            vx_m = p.vx[q - pl]; vx_c = p.vx[q]; vx_p = p.vx[q + pl];
+            vy_m = p.vy[q - pl]; vy_c = p.vy[q]; vy_p = p.vy[q + pl];
+        }
+        if (NORMAL) { vz_mm = p.vz[q - 2 * pl]; vz_m = p.vz[q - pl]; }
+        vz_c = p.vz[q];
 
         for (int k = kb; k <= ke; ++k, q += pl) {
             const int kg = k + p.koff;                      // :978
-            // ---- loads of this plane
-            const double vx_pp = p.vx[q + 2 * pl], vy_pp = p.vy[q + 2 * pl], vz_p = p.vz[q + pl];
-            const double vx_im1 = p.vx[q - 1], vx_ip1 = p.vx[q + 1], vx_ip2 = p.vx[q + 2];
-            const double vx_jm1 = p.vx[q - pitch], vx_jp1 = p.vx[q + pitch], vx_jp2 = p.vx[q + 2 * pitch];
-            const double vy_im2 = p.vy[q - 2], vy_im1 = p.vy[q - 1], vy_ip1 = p.vy[q + 1];
-            const double vy_jm2 = p.vy[q - 2 * pitch], vy_jm1 = p.vy[q - pitch], vy_jp1 = p.vy[q + pitch];
-            const double vz_im2 = p.vz[q - 2], vz_im1 = p.vz[q - 1], vz_ip1 = p.vz[q + 1];
-            const double vz_jm1 = p.vz[q - pitch], vz_jp1 = p.vz[q + pitch], vz_jp2 = p.vz[q + 2 * pitch];
-            double sxx = vld(p.sxx + q), syy = vld(p.syy + q), szz = vld(p.szz + q);
-            double sxy = vld(p.sxy + q), sxz = vld(p.sxz + q), syz = vld(p.syz + q);
-            double rxx = vld(p.rxx + q), ryy = vld(p.ryy + q), rzz = vld(p.rzz + q);
-            double rxy = vld(p.rxy + q), rxz = vld(p.rxz + q), ryz = vld(p.ryz + q);
-            double2 e1 = vld2(p.e1 + q), e11 = vld2(p.e11 + q), e22 = vld2(p.e22 + q);
-            double2 e12 = vld2(p.e12 + q), e13 = vld2(p.e13 + q), e23 = vld2(p.e23 + q);
-
             const bool in_z = (kg <= p.zlo) || (kg >= p.zhi);
             long long qx = 0, qy = 0, qz = 0;
             double az = 0, bz = 0, Kz = 1, azh = 0, bzh = 0, Kzh = 1, rKz = 1, rKzh = 1;
@@ -147,129 +161,160 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
             if (in_y) qy = ((long long)(k - 1) * p.sy + sy) * pitch + (i - 1);
             if (in_z) {
                 qz = ((long long)(vshell(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1);
-                az = p.cz.a[kg]; bz = p.cz.b[kg]; Kz = p.cz.K[kg];
-                azh = p.cz.a_half[kg]; bzh = p.cz.b_half[kg]; Kzh = p.cz.K_half[kg];
-                rKz = p.cz.rK[kg]; rKzh = p.cz.rK_half[kg];
+                if (NORMAL) { az = p.cz.a[kg]; bz = p.cz.b[kg]; Kz = p.cz.K[kg]; rKz = p.cz.rK[kg]; }
+                if (SHEAR) { azh = p.cz.a_half[kg]; bzh = p.cz.b_half[kg]; Kzh = p.cz.K_half[kg]; rKzh = p.cz.rK_half[kg]; }
             }
             // quirk B6: taps the reference's MPI exchange never delivers
             const int kmod = kg % p.nzl_e;
             const bool cut_up = (kmod == 0);                // last plane of a reference slab
             const bool cut_dn = (kmod == 1);                // first plane of a reference slab
+            const bool ebox = ebox_ij && kg >= p.npml && kg <= p.nz - p.npml + 1;      // :1387-1392
+
+            double vz_p = 0.0;
+            if (NORMAL) vz_p = p.vz[q + pl];
 
             // ---- sigmaxx, sigmayy, sigmazz, e1, e11, e22, sigma*_R  (:977-1096)
-            if (do_n && kg >= 2) {                          // k2begin, :942-943
-                double duxdx = d4(vx_ip1, vx_c, vx_ip2, vx_im1, odx);
-                double duydy = d4(vy_c, vy_jm1, vy_jp1, vy_jm2, ody);
-                double duzdz = d4(vz_c, vz_m, cut_up ? 0.0 : vz_p, vz_mm, odz);
-                if (in_x) duxdx = vcpml(p.mx[0], qx, bxh, axh, Kxh, rKxh, duxdx);
-                if (in_y) duydy = vcpml(p.my[0], qy, by, ay, Ky, rKy, duydy);
-                if (in_z) duzdz = vcpml(p.mz[0], qz, bz, az, Kz, rKz, duzdz);
-                const double div = duxdx + duydy + duzdz;
-                const double div3 = div_exact(div, 3.0, 1.0 / 3.0);      // div/DIM
+            if (NORMAL) {
+                const double vx_im1 = p.vx[q - 1], vx_0 = SHEAR ? vx_c : p.vx[q], vx_ip1 = p.vx[q + 1], vx_ip2 = p.vx[q + 2];
+                const double vy_jm2 = p.vy[q - 2 * pitch], vy_jm1 = p.vy[q - pitch], vy_0 = SHEAR ? vy_c : p.vy[q], vy_jp1 = p.vy[q + pitch];
+                double sxx = vld(p.sxx + q), syy = vld(p.syy + q), szz = vld(p.szz + q);
+                double rxx = vld(p.rxx + q), ryy = vld(p.ryy + q), rzz = vld(p.rzz + q);
+                double2 e1 = vld2(p.e1 + q), e11 = vld2(p.e11 + q), e22 = vld2(p.e22 + q);
+                if (do_n && kg >= 2) {                      // k2begin, :942-943
+                    double duxdx = d4(vx_ip1, vx_0, vx_ip2, vx_im1, odx);
+                    double duydy = d4(vy_0, vy_jm1, vy_jp1, vy_jm2, ody);
+                    double duzdz = d4(vz_c, vz_m, cut_up ? 0.0 : vz_p, vz_mm, odz);
+                    if (in_x) duxdx = vcpml(p.mx[0], qx, cxc[5 * TX], cxc[4 * TX], cxc[6 * TX], cxc[7 * TX], duxdx);
+                    if (in_y) duydy = vcpml(p.my[0], qy, cyc[1 * TY], cyc[0 * TY], cyc[2 * TY], cyc[3 * TY], duydy);
+                    if (in_z) duzdz = vcpml(p.mz[0], qz, bz, az, Kz, rKz, duzdz);
+                    const double div = duxdx + duydy + duzdz;
+                    const double div3 = div_exact(div, 3.0, 1.0 / 3.0);      // div/DIM
 
-                e1.x = evolve(e1.x, div * p.phi1[0], p.tauinv1[0], p.den1[0], p.rden1[0], dt);
-                e1.y = evolve(e1.y, div * p.phi1[1], p.tauinv1[1], p.den1[1], p.rden1[1], dt);
-                e11.x = evolve(e11.x, (duxdx - div3) * p.phi2[0], p.tauinv2[0], p.den2[0], p.rden2[0], dt);
-                e11.y = evolve(e11.y, (duxdx - div3) * p.phi2[1], p.tauinv2[1], p.den2[1], p.rden2[1], dt);
-                e22.x = evolve(e22.x, (duydy - div3) * p.phi2[0], p.tauinv2[0], p.den2[0], p.rden2[0], dt);
-                e22.y = evolve(e22.y, (duydy - div3) * p.phi2[1], p.tauinv2[1], p.den2[1], p.rden2[1], dt);
-                vst2(p.e1 + q, e1); vst2(p.e11 + q, e11); vst2(p.e22 + q, e22);
+                    e1.x = evolve(e1.x, div * p.phi1[0], p.tauinv1[0], p.den1[0], p.rden1[0], dt);
+                    e1.y = evolve(e1.y, div * p.phi1[1], p.tauinv1[1], p.den1[1], p.rden1[1], dt);
+                    e11.x = evolve(e11.x, (duxdx - div3) * p.phi2[0], p.tauinv2[0], p.den2[0], p.rden2[0], dt);
+                    e11.y = evolve(e11.y, (duxdx - div3) * p.phi2[1], p.tauinv2[1], p.den2[1], p.rden2[1], dt);
+                    e22.x = evolve(e22.x, (duydy - div3) * p.phi2[0], p.tauinv2[0], p.den2[0], p.rden2[0], dt);
+                    e22.y = evolve(e22.y, (duydy - div3) * p.phi2[1], p.tauinv2[1], p.den2[1], p.rden2[1], dt);
+                    vst2(p.e1 + q, e1); vst2(p.e11 + q, e11); vst2(p.e22 + q, e22);
 
-                // relaxed moduli times the memory variables (:1054-1060)
-                sxx = sxx + dt * (p.lam23mu * (e1.x + e1.y) + p.two_mu * (e11.x + e11.y));
-                syy = syy + dt * (p.lam23mu * (e1.x + e1.y) + p.two_mu * (e22.x + e22.y));
-                szz = szz + dt * (p.l2m_r * (e1.x + e1.y) - p.two_thirds_mu * (e11.x + e11.y + e22.x + e22.y));
-                // unrelaxed elastic term (:1064-1077)
-                sxx = sxx + (p.l2m_u * duxdx + p.lam_u * duydy + p.lam_u * duzdz) * dt;
-                syy = syy + (p.lam_u * duxdx + p.l2m_u * duydy + p.lam_u * duzdz) * dt;
-                szz = szz + (p.lam_u * duxdx + p.lam_u * duydy + p.l2m_u * duzdz) * dt;
-                // relaxed stresses (:1079-1092)
-                rxx = rxx + (p.l2m_r * duxdx + p.lam * duydy + p.lam * duzdz) * dt;
-                ryy = ryy + (p.lam * duxdx + p.l2m_r * duydy + p.lam * duzdz) * dt;
-                rzz = rzz + (p.lam * duxdx + p.lam * duydy + p.l2m_r * duzdz) * dt;
-                vst(p.sxx + q, sxx); vst(p.syy + q, syy); vst(p.szz + q, szz);
-                vst(p.rxx + q, rxx); vst(p.ryy + q, ryy); vst(p.rzz + q, rzz);
-            }
-            // ---- sigmaxy, e12  (:1098-1139)
-            if (do_xy) {
-                double duydx = d4(vy_c, vy_im1, vy_ip1, vy_im2, odx);
-                double duxdy = d4(vx_jp1, vx_c, vx_jp2, vx_jm1, ody);
-                if (in_x) duydx = vcpml(p.mx[1], qx, bx, ax, Kx, rKx, duydx);
-                if (in_y) duxdy = vcpml(p.my[1], qy, byh, ayh, Kyh, rKyh, duxdy);
-                const double g = duxdy + duydx;
-                e12.x = evolve(e12.x, g * p.phi2[0], p.tauinv2[0], p.den2[0], p.rden2[0], dt);
-                e12.y = evolve(e12.y, g * p.phi2[1], p.tauinv2[1], p.den2[1], p.rden2[1], dt);
-                vst2(p.e12 + q, e12);
-                sxy = sxy + dt * p.mu * (e12.x + e12.y);
-                sxy = sxy + p.mu_u * g * dt;
-                rxy = rxy + p.mu * g * dt;
-                vst(p.sxy + q, sxy); vst(p.rxy + q, rxy);
-            }
-            // ---- sigmaxz, e13 and sigmayz, e23  (:1141-1223)
-            if (kg <= p.nz - 1) {                           // kminus1end, :945-946
-                if (do_xz) {
-                    double duzdx = d4(vz_c, vz_im1, vz_ip1, vz_im2, odx);
-                    double duxdz = d4(vx_p, vx_c, vx_pp, cut_dn ? 0.0 : vx_m, odz);
-                    if (in_x) duzdx = vcpml(p.mx[2], qx, bx, ax, Kx, rKx, duzdx);
-                    if (in_z) duxdz = vcpml(p.mz[1], qz, bzh, azh, Kzh, rKzh, duxdz);
-                    const double g = duxdz + duzdx;
-                    e13.x = evolve(e13.x, g * p.phi2[0], p.tauinv2[0], p.den2[0], p.rden2[0], dt);
-                    e13.y = evolve(e13.y, g * p.phi2[1], p.tauinv2[1], p.den2[1], p.rden2[1], dt);
-                    vst2(p.e13 + q, e13);
-                    sxz = sxz + dt * p.mu * (e13.x + e13.y);
-                    sxz = sxz + p.mu_u * g * dt;
-                    rxz = rxz + p.mu * g * dt;
-                    vst(p.sxz + q, sxz); vst(p.rxz + q, rxz);
+                    // relaxed moduli times the memory variables (:1054-1060)
+                    sxx = sxx + dt * (p.lam23mu * (e1.x + e1.y) + p.two_mu * (e11.x + e11.y));
+                    syy = syy + dt * (p.lam23mu * (e1.x + e1.y) + p.two_mu * (e22.x + e22.y));
+                    szz = szz + dt * (p.l2m_r * (e1.x + e1.y) - p.two_thirds_mu * (e11.x + e11.y + e22.x + e22.y));
+                    // unrelaxed elastic term (:1064-1077)
+                    sxx = sxx + (p.l2m_u * duxdx + p.lam_u * duydy + p.lam_u * duzdz) * dt;
+                    syy = syy + (p.lam_u * duxdx + p.l2m_u * duydy + p.lam_u * duzdz) * dt;
+                    szz = szz + (p.lam_u * duxdx + p.lam_u * duydy + p.l2m_u * duzdz) * dt;
+                    // relaxed stresses (:1079-1092)
+                    rxx = rxx + (p.l2m_r * duxdx + p.lam * duydy + p.lam * duzdz) * dt;
+                    ryy = ryy + (p.lam * duxdx + p.l2m_r * duydy + p.lam * duzdz) * dt;
+                    rzz = rzz + (p.lam * duxdx + p.lam * duydy + p.l2m_r * duzdz) * dt;
+                    vst(p.sxx + q, sxx); vst(p.syy + q, syy); vst(p.szz + q, szz);
+                    vst(p.rxx + q, rxx); vst(p.ryy + q, ryy); vst(p.rzz + q, rzz);
                 }
-                if (do_yz) {
-                    double duzdy = d4(vz_jp1, vz_c, vz_jp2, vz_jm1, ody);
-                    double duydz = d4(vy_p, vy_c, vy_pp, cut_dn ? 0.0 : vy_m, odz);
-                    if (in_y) duzdy = vcpml(p.my[2], qy, byh, ayh, Kyh, rKyh, duzdy);
-                    if (in_z) duydz = vcpml(p.mz[2], qz, bzh, azh, Kzh, rKzh, duydz);
-                    const double g = duydz + duzdy;
-                    e23.x = evolve(e23.x, g * p.phi2[0], p.tauinv2[0], p.den2[0], p.rden2[0], dt);
-                    e23.y = evolve(e23.y, g * p.phi2[1], p.tauinv2[1], p.den2[1], p.rden2[1], dt);
-                    vst2(p.e23 + q, e23);
-                    syz = syz + dt * p.mu * (e23.x + e23.y);
-                    syz = syz + p.mu_u * g * dt;
-                    ryz = ryz + p.mu * g * dt;
-                    vst(p.syz + q, syz); vst(p.ryz + q, ryz);
+                // potential energy over the PML-free box (:1387-1419), normal-stress terms; quirk B2:
+                // epsilon_yy * sigmayy_R is counted twice and the zz term is missing
+                if (ebox) {
+                    const double epsilon_xx = (p.c2lm * sxx - p.lam * syy - p.lam * szz) * p.inv_den;
+                    const double epsilon_yy = (p.c2lm * syy - p.lam * sxx - p.lam * szz) * p.inv_den;
+                    epot += 0.5 * (epsilon_xx * rxx + epsilon_yy * ryy + epsilon_yy * ryy);
                 }
             }
 
-            // ---- potential energy over the PML-free box (:1387-1419); quirk B2: epsilon_yy *
-            // sigmayy_R is counted twice and the zz term is missing
-            if (ebox_ij && kg >= p.npml && kg <= p.nz - p.npml + 1) {
-                const double epsilon_xx = (p.c2lm * sxx - p.lam * syy - p.lam * szz) * p.inv_den;
-                const double epsilon_yy = (p.c2lm * syy - p.lam * sxx - p.lam * szz) * p.inv_den;
-                const double epsilon_xy = rxy * p.inv_2mu;
-                const double epsilon_xz = rxz * p.inv_2mu;
-                const double epsilon_yz = ryz * p.inv_2mu;
-                epot += 0.5 * (epsilon_xx * rxx + epsilon_yy * ryy + epsilon_yy * ryy +
-                               2.0 * epsilon_xy * rxy + 2.0 * epsilon_xz * rxz + 2.0 * epsilon_yz * ryz);
+            if (SHEAR) {
+                const double vx_pp = p.vx[q + 2 * pl], vy_pp = p.vy[q + 2 * pl];
+                double esh = 0.0;
+                // ---- sigmaxy, e12  (:1098-1139)
+                {
+                    const double vy_im2 = p.vy[q - 2], vy_im1 = p.vy[q - 1], vy_ip1 = p.vy[q + 1];
+                    const double vx_jm1 = p.vx[q - pitch], vx_jp1 = p.vx[q + pitch], vx_jp2 = p.vx[q + 2 * pitch];
+                    double sxy = vld(p.sxy + q), rxy = vld(p.rxy + q);
+                    double2 e12 = vld2(p.e12 + q);
+                    if (do_xy) {
+                        double duydx = d4(vy_c, vy_im1, vy_ip1, vy_im2, odx);
+                        double duxdy = d4(vx_jp1, vx_c, vx_jp2, vx_jm1, ody);
+                        if (in_x) duydx = vcpml(p.mx[1], qx, cxc[1 * TX], cxc[0 * TX], cxc[2 * TX], cxc[3 * TX], duydx);
+                        if (in_y) duxdy = vcpml(p.my[1], qy, cyc[5 * TY], cyc[4 * TY], cyc[6 * TY], cyc[7 * TY], duxdy);
+                        const double g = duxdy + duydx;
+                        e12.x = evolve(e12.x, g * p.phi2[0], p.tauinv2[0], p.den2[0], p.rden2[0], dt);
+                        e12.y = evolve(e12.y, g * p.phi2[1], p.tauinv2[1], p.den2[1], p.rden2[1], dt);
+                        vst2(p.e12 + q, e12);
+                        sxy = sxy + dt * p.mu * (e12.x + e12.y);
+                        sxy = sxy + p.mu_u * g * dt;
+                        rxy = rxy + p.mu * g * dt;
+                        vst(p.sxy + q, sxy); vst(p.rxy + q, rxy);
+                    }
+                    esh += 2.0 * (rxy * p.inv_2mu) * rxy;
+                }
+                // ---- sigmaxz, e13 and sigmayz, e23  (:1141-1223)
+                {
+                    const double vz_im2 = p.vz[q - 2], vz_im1 = p.vz[q - 1], vz_ip1 = p.vz[q + 1];
+                    double sxz = vld(p.sxz + q), rxz = vld(p.rxz + q);
+                    double2 e13 = vld2(p.e13 + q);
+                    if (do_xz && kg <= p.nz - 1) {                  // kminus1end, :945-946
+                        double duzdx = d4(vz_c, vz_im1, vz_ip1, vz_im2, odx);
+                        double duxdz = d4(vx_p, vx_c, vx_pp, cut_dn ? 0.0 : vx_m, odz);
+                        if (in_x) duzdx = vcpml(p.mx[2], qx, cxc[1 * TX], cxc[0 * TX], cxc[2 * TX], cxc[3 * TX], duzdx);
+                        if (in_z) duxdz = vcpml(p.mz[1], qz, bzh, azh, Kzh, rKzh, duxdz);
+                        const double g = duxdz + duzdx;
+                        e13.x = evolve(e13.x, g * p.phi2[0], p.tauinv2[0], p.den2[0], p.rden2[0], dt);
+                        e13.y = evolve(e13.y, g * p.phi2[1], p.tauinv2[1], p.den2[1], p.rden2[1], dt);
+                        vst2(p.e13 + q, e13);
+                        sxz = sxz + dt * p.mu * (e13.x + e13.y);
+                        sxz = sxz + p.mu_u * g * dt;
+                        rxz = rxz + p.mu * g * dt;
+                        vst(p.sxz + q, sxz); vst(p.rxz + q, rxz);
+                    }
+                    esh += 2.0 * (rxz * p.inv_2mu) * rxz;
+                }
+                {
+                    const double vz_jm1 = p.vz[q - pitch], vz_jp1 = p.vz[q + pitch], vz_jp2 = p.vz[q + 2 * pitch];
+                    double syz = vld(p.syz + q), ryz = vld(p.ryz + q);
+                    double2 e23 = vld2(p.e23 + q);
+                    if (do_yz && kg <= p.nz - 1) {
+                        double duzdy = d4(vz_jp1, vz_c, vz_jp2, vz_jm1, ody);
+                        double duydz = d4(vy_p, vy_c, vy_pp, cut_dn ? 0.0 : vy_m, odz);
+                        if (in_y) duzdy = vcpml(p.my[2], qy, cyc[5 * TY], cyc[4 * TY], cyc[6 * TY], cyc[7 * TY], duzdy);
+                        if (in_z) duydz = vcpml(p.mz[2], qz, bzh, azh, Kzh, rKzh, duydz);
+                        const double g = duydz + duzdy;
+                        e23.x = evolve(e23.x, g * p.phi2[0], p.tauinv2[0], p.den2[0], p.rden2[0], dt);
+                        e23.y = evolve(e23.y, g * p.phi2[1], p.tauinv2[1], p.den2[1], p.rden2[1], dt);
+                        vst2(p.e23 + q, e23);
+                        syz = syz + dt * p.mu * (e23.x + e23.y);
+                        syz = syz + p.mu_u * g * dt;
+                        ryz = ryz + p.mu * g * dt;
+                        vst(p.syz + q, syz); vst(p.ryz + q, ryz);
+                    }
+                    esh += 2.0 * (ryz * p.inv_2mu) * ryz;
+                }
+                // potential energy, shear terms (:1411-1419)
+                if (ebox) epot += 0.5 * esh;
+                vx_m = vx_c; vx_c = vx_p; vx_p = vx_pp;
+                vy_m = vy_c; vy_c = vy_p; vy_p = vy_pp;
             }
-
-            vx_m = vx_c; vx_c = vx_p; vx_p = vx_pp;
-            vy_m = vy_c; vy_c = vy_p; vy_p = vy_pp;
-            vz_mm = vz_m; vz_m = vz_c; vz_c = vz_p;
+            if (NORMAL) { vz_mm = vz_m; vz_m = vz_c; vz_c = vz_p; }
+            else vz_c = p.vz[q + pl];
         }
     }
 
     epot = block_sum1<TX * TY>(epot, red);
     if (threadIdx.x == 0 && threadIdx.y == 0) {
         const int b = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-        p.partials[p.nblocks + b] = epot;
+        p.partials[(PART == 2 ? 2 : 1) * p.nblocks + b] = epot;      // [nb,2nb): normal (or all), [2nb,3nb): shear
     }
 }
 
-template <int TX, int TY>
-__global__ void __launch_bounds__(TX *TY)
+template <int TX, int TY, int MINB>
+__global__ void __launch_bounds__(TX *TY, MINB)
 k_vvelocity3d(const __grid_constant__ ParamsV3D p)
 {
     __shared__ double red[TX * TY / 32];
+    __shared__ double cxs[8][TX], cys[8][TY];
     const int i = blockIdx.x * TX + threadIdx.x + 1;
     const int j = blockIdx.y * TY + threadIdx.y + 1;
     double ekin = 0.0;
+    load_coef_tables<TX, TY>(p, cxs, cys);
 
     if (i <= p.nx && j <= p.ny) {
         const int kb = 1 + blockIdx.z * p.kchunk;
@@ -293,12 +338,9 @@ k_vvelocity3d(const __grid_constant__ ParamsV3D p)
 
         const double odx = p.odx, ody = p.ody, odz = p.odz, dt_r = p.dt_over_rho;
 
-        double ax = 0, bx = 0, Kx = 1, axh = 0, bxh = 0, Kxh = 1, ay = 0, by = 0, Ky = 1, ayh = 0, byh = 0, Kyh = 1;
-        double rKx = 1, rKxh = 1, rKy = 1, rKyh = 1;
-        if (in_x) { ax = p.cx.a[i]; bx = p.cx.b[i]; Kx = p.cx.K[i]; axh = p.cx.a_half[i]; bxh = p.cx.b_half[i]; Kxh = p.cx.K_half[i];
-                    rKx = p.cx.rK[i]; rKxh = p.cx.rK_half[i]; }
-        if (in_y) { ay = p.cy.a[j]; by = p.cy.b[j]; Ky = p.cy.K[j]; ayh = p.cy.a_half[j]; byh = p.cy.b_half[j]; Kyh = p.cy.K_half[j];
-                    rKy = p.cy.rK[j]; rKyh = p.cy.rK_half[j]; }
+        // x / y C-PML coefficients of this block's columns and rows sit in shared memory (cxs, cys):
+        // only shell points read them, at the point of use, so they cost no registers in the interior
+        const double *const cxc = &cxs[0][threadIdx.x], *const cyc = &cys[0][threadIdx.y];
 
         // z windows
         double sxz_mm = p.sxz[q - 2 * pl], sxz_m = p.sxz[q - pl], sxz_c = p.sxz[q];
@@ -337,8 +379,8 @@ k_vvelocity3d(const __grid_constant__ ParamsV3D p)
                     double d1 = d4(sxx_c, sxx_im1, sxx_ip1, sxx_im2, odx);
                     double d2 = d4(sxy_c, sxy_jm1, sxy_jp1, sxy_jm2, ody);
                     double d3 = d4(sxz_c, sxz_m, cut_up ? 0.0 : sxz_p, sxz_mm, odz);
-                    if (in_x) d1 = vcpml(p.mx[3], qx, bx, ax, Kx, rKx, d1);
-                    if (in_y) d2 = vcpml(p.my[3], qy, by, ay, Ky, rKy, d2);
+                    if (in_x) d1 = vcpml(p.mx[3], qx, cxc[1 * TX], cxc[0 * TX], cxc[2 * TX], cxc[3 * TX], d1);
+                    if (in_y) d2 = vcpml(p.my[3], qy, cyc[1 * TY], cyc[0 * TY], cyc[2 * TY], cyc[3 * TY], d2);
                     if (in_z) d3 = vcpml(p.mz[3], qz, bz, az, Kz, rKz, d3);
                     vx = dt_r * (d1 + d2 + d3) + vx;
                 }
@@ -346,8 +388,8 @@ k_vvelocity3d(const __grid_constant__ ParamsV3D p)
                     double d1 = d4(sxy_ip1, sxy_c, sxy_ip2, sxy_im1, odx);
                     double d2 = d4(syy_jp1, syy_c, syy_jp2, syy_jm1, ody);
                     double d3 = d4(syz_c, syz_m, cut_up ? 0.0 : syz_p, syz_mm, odz);
-                    if (in_x) d1 = vcpml(p.mx[4], qx, bxh, axh, Kxh, rKxh, d1);
-                    if (in_y) d2 = vcpml(p.my[4], qy, byh, ayh, Kyh, rKyh, d2);
+                    if (in_x) d1 = vcpml(p.mx[4], qx, cxc[5 * TX], cxc[4 * TX], cxc[6 * TX], cxc[7 * TX], d1);
+                    if (in_y) d2 = vcpml(p.my[4], qy, cyc[5 * TY], cyc[4 * TY], cyc[6 * TY], cyc[7 * TY], d2);
                     if (in_z) d3 = vcpml(p.mz[4], qz, bz, az, Kz, rKz, d3);
                     vy = dt_r * (d1 + d2 + d3) + vy;
                 }
@@ -356,8 +398,8 @@ k_vvelocity3d(const __grid_constant__ ParamsV3D p)
                 double d1 = d4(sxz_ip1, sxz_c, sxz_ip2, sxz_im1, odx);
                 double d2 = d4(syz_c, syz_jm1, syz_jp1, syz_jm2, ody);
                 double d3 = d4(szz_p, szz_c, szz_pp, cut_dn ? 0.0 : szz_m, odz);
-                if (in_x) d1 = vcpml(p.mx[5], qx, bxh, axh, Kxh, rKxh, d1);
-                if (in_y) d2 = vcpml(p.my[5], qy, by, ay, Ky, rKy, d2);
+                if (in_x) d1 = vcpml(p.mx[5], qx, cxc[5 * TX], cxc[4 * TX], cxc[6 * TX], cxc[7 * TX], d1);
+                if (in_y) d2 = vcpml(p.my[5], qy, cyc[1 * TY], cyc[0 * TY], cyc[2 * TY], cyc[3 * TY], d2);
                 if (in_z) d3 = vcpml(p.mz[5], qz, bzh, azh, Kzh, rKzh, d3);
                 vz = dt_r * (d1 + d2 + d3) + vz;
             }
@@ -394,38 +436,53 @@ k_vvelocity3d(const __grid_constant__ ParamsV3D p)
 
 // ---- launch dispatch ---------------------------------------------------------------
 
-static int g_vtx = 0, g_vty = 0;
+static int g_vtx = 0, g_vty = 0, g_vsplit = 0, g_vminb = 0;
 
 void visco_tile(int *tx, int *ty)
 {
     if (!g_vtx) {
-        const char *sx = getenv("CPML_VTX"), *sy = getenv("CPML_VTY");
+        const char *sx = getenv("CPML_VTX"), *sy = getenv("CPML_VTY"), *sp = getenv("CPML_VSPLIT"), *sm = getenv("CPML_VMINB");
         g_vtx = sx ? atoi(sx) : 32;
         g_vty = sy ? atoi(sy) : 8;
+        g_vsplit = sp ? atoi(sp) : 0;         // 0: one stress launch per step (default), 1: normal and shear stresses in two launches
+        g_vminb = sm ? atoi(sm) : 0;          // 0: the default register cap of the tile
         const int key = g_vtx * 100 + g_vty;
-        if (key != 3208 && key != 3204 && key != 6404 && key != 6402 && key != 12802 && key != 1616) { g_vtx = 32; g_vty = 8; }
+        if (key != 3208 && key != 3204 && key != 6404 && key != 6402 && key != 1616) { g_vtx = 32; g_vty = 8; }
     }
     *tx = g_vtx; *ty = g_vty;
 }
 
-template <int TX, int TY>
-static void vlaunch(const ParamsV3D &p, dim3 grid, cudaStream_t s, bool stress)
+int visco_stress_launches() { int a, b; visco_tile(&a, &b); return g_vsplit ? 2 : 1; }
+
+// MINB = resident blocks per SM the kernels are compiled for: 65536 / (threads * MINB) registers per thread
+template <int TX, int TY, int MINB>
+static cudaError_t vlaunch(const ParamsV3D &p, dim3 grid, cudaStream_t s, bool stress)
 {
-    if (stress) k_vstress3d<TX, TY><<<grid, dim3(TX, TY), 0, s>>>(p);
-    else        k_vvelocity3d<TX, TY><<<grid, dim3(TX, TY), 0, s>>>(p);
+    if (!stress) k_vvelocity3d<TX, TY, MINB><<<grid, dim3(TX, TY), 0, s>>>(p);
+    else if (g_vsplit) {
+        k_vstress3d<TX, TY, MINB, 1><<<grid, dim3(TX, TY), 0, s>>>(p);
+        k_vstress3d<TX, TY, MINB, 2><<<grid, dim3(TX, TY), 0, s>>>(p);
+    } else k_vstress3d<TX, TY, MINB, 0><<<grid, dim3(TX, TY), 0, s>>>(p);
+    return cudaGetLastError();
 }
 
-static void vdispatch(const ParamsV3D &p, dim3 grid, cudaStream_t s, bool stress)
+template <int TX, int TY, int LO, int HI>
+static cudaError_t vlaunch_minb(const ParamsV3D &p, dim3 grid, cudaStream_t s, bool stress)
+{
+    const bool hi = g_vminb ? (g_vminb >= HI) : true;
+    return hi ? vlaunch<TX, TY, HI>(p, grid, s, stress) : vlaunch<TX, TY, LO>(p, grid, s, stress);
+}
+
+static cudaError_t vdispatch(const ParamsV3D &p, dim3 grid, cudaStream_t s, bool stress)
 {
     int tx, ty;
     visco_tile(&tx, &ty);
     switch (tx * 100 + ty) {
-    case 3204:  vlaunch<32, 4>(p, grid, s, stress); break;
-    case 6404:  vlaunch<64, 4>(p, grid, s, stress); break;
-    case 6402:  vlaunch<64, 2>(p, grid, s, stress); break;
-    case 12802: vlaunch<128, 2>(p, grid, s, stress); break;
-    case 1616:  vlaunch<16, 16>(p, grid, s, stress); break;
-    default:    vlaunch<32, 8>(p, grid, s, stress); break;
+    case 3204:  return g_vminb == 3 ? vlaunch<32, 4, 3>(p, grid, s, stress) : vlaunch_minb<32, 4, 2, 4>(p, grid, s, stress);
+    case 6404:  return vlaunch_minb<64, 4, 1, 2>(p, grid, s, stress);
+    case 6402:  return vlaunch_minb<64, 2, 2, 4>(p, grid, s, stress);
+    case 1616:  return vlaunch_minb<16, 16, 1, 2>(p, grid, s, stress);
+    default:    return vlaunch_minb<32, 8, 1, 2>(p, grid, s, stress);
     }
 }
 
