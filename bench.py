@@ -11,6 +11,7 @@ One "step" = one full time step of the loop body (stress + velocity + source + D
   cfg2  2-D fourth order 4096 x 4096 (single GPU only)
   cfg5  seismic_CPML_3D_viscoelastic_MPI (4th order, N_SLS = 2) 1024 x 1024 x 128 per GPU, weak scaling
   cfg5d the same program on its default grid 210 x 800 x 220 (single GPU; N > 1: 220 planes per GPU)
+  cfg6  seismic_CPML_2D_velocity_and_stress_fourth_order_viscoelastic as shipped, 2001 x 2001 (single GPU only)
 Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the
 reference loop (oracle/, OpenMP, all host threads): the Fortran reference itself cannot be
 built in this image (no Fortran compiler, no MPI).
@@ -37,7 +38,8 @@ UNIT = "Gpts/s"
 
 def metric_name(kind):
     return {"3d": METRIC, "3dv": "grid-point updates/s, 3-D viscoelastic C-PML time loop (FP64)",
-            "2d": "grid-point updates/s, 2-D isotropic C-PML time loop (FP64)"}[kind]
+            "2d": "grid-point updates/s, 2-D isotropic C-PML time loop (FP64)",
+            "2dv": "grid-point updates/s, 2-D viscoelastic C-PML time loop (FP64)"}[kind]
 
 
 def measured_peak():
@@ -107,6 +109,10 @@ def workload_params(name, n_gpus, nstep):
         return P.Params3DVisco(NX=1024, NY=1024, NZ=128 * n_gpus, NSTEP=nstep, NPROC=_visco_nproc(n_gpus, 128 * n_gpus)), "3dv"
     if name == "cfg5d":
         return P.Params3DVisco(NZ=220 * n_gpus, NSTEP=nstep, NPROC=_visco_nproc(n_gpus, 220 * n_gpus)), "3dv"
+    if name == "cfg6":
+        if n_gpus != 1:
+            raise SystemExit("cfg6 (2-D) runs on one GPU")
+        return P.Params2DVisco(order=4, NSTEP=nstep), "2dv"
     if name == "cfg2":
         if n_gpus != 1:
             raise SystemExit("cfg2 (2-D) runs on one GPU")
@@ -125,6 +131,8 @@ def _visco_nproc(n_gpus, nz):
 def workload_label(name, p, kind, n_gpus):
     if kind == "2d":
         return f"seismic_CPML_2D_isotropic_fourth_order {p.NX}x{p.NY}"
+    if kind == "2dv":
+        return f"seismic_CPML_2D_velocity_and_stress_fourth_order_viscoelastic (N_SLS=3) {p.NX}x{p.NY}"
     if kind == "3dv":
         return (f"seismic_CPML_3D_viscoelastic_MPI (4th order, N_SLS=2, reference NPROC={p.NPROC} emulated): "
                 f"{p.NX}x{p.NY}x{p.NZ} ({p.NX}x{p.NY}x{p.NZ // n_gpus} per GPU, z-slabs)")
@@ -137,6 +145,16 @@ def workload_label(name, p, kind, n_gpus):
 # reference arm / cpu baseline: the oracle's OpenMP build on the host cores
 # ------------------------------------------------------------------------------------
 
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm asks for the cores it may run on."""
+    from oracle import oracle as O
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    O.set_num_threads(n)
+
+
 def oracle_3d_gpts(p, nz_sample, steps, warmup):
     """Times `steps` time steps (after `warmup`) of the CPU restatement on a z-reduced sample
     of the workload: NX x NY x nz_sample, same spacing / time step / PML / source law."""
@@ -144,6 +162,7 @@ def oracle_3d_gpts(p, nz_sample, steps, warmup):
     from seismic_cpml_b200 import programs as P
     q = P.Params3DIso(NX=p.NX, NY=p.NY, NZ=nz_sample, NSTEP=steps + warmup, DELTAX=p.DELTAX, DELTAT=p.DELTAT)
     s = P.setup_3d(q)
+    _use_all_host_threads()
     O.set_ftz(True)                 # cf. reference Makefile:18 (-ftz "critical for performance")
     O.set_warmup_steps(warmup)
     O.run_3d_iso(nx=q.NX, ny=q.NY, nz=q.NZ, nproc=2, deltax=q.DELTAX, deltay=q.DELTAY, deltaz=q.DELTAZ,
@@ -163,6 +182,7 @@ def oracle_3dv_gpts(p, nz_sample, steps, warmup):
     from seismic_cpml_b200 import programs as P
     q = P.Params3DVisco(NX=p.NX, NY=min(p.NY, 256), NZ=nz_sample, NSTEP=steps + warmup, NPROC=4)
     s = P.setup_3d_visco(q)
+    _use_all_host_threads()
     O.set_ftz(True)
     O.set_warmup_steps(warmup)
     O.run_3d_visco(nx=q.NX, ny=q.NY, nz=q.NZ, nproc=4, deltax=q.DELTAX, deltay=q.DELTAY, deltaz=q.DELTAZ,
@@ -174,6 +194,24 @@ def oracle_3dv_gpts(p, nz_sample, steps, warmup):
     sec = O.last_loop_seconds()
     O.set_warmup_steps(0)
     return float(q.NX) * q.NY * q.NZ * steps / sec / 1e9, sec, O.num_threads()
+
+
+def oracle_2dv_gpts(p, n_sample, steps, warmup):
+    from oracle import oracle as O
+    from seismic_cpml_b200 import programs as P
+    q = P.Params2DVisco(order=p.order, NX=n_sample, NY=n_sample, NSTEP=steps + warmup, xsource=n_sample * 0.75, ysource=n_sample * 0.75,
+                        xdeb=n_sample, ydeb=n_sample, xfin=n_sample, yfin=n_sample)
+    s = P.setup_2d_visco(q)
+    O.set_ftz(True)
+    O.set_warmup_steps(warmup)
+    O.run_2d_visco(order=q.order, nx=q.NX, ny=q.NY, deltax=q.DELTAX, deltay=q.DELTAY, deltat=q.DELTAT, nstep=q.NSTEP,
+                   npoints_pml=q.NPOINTS_PML, isource=q.ISOURCE, jsource=q.JSOURCE, lam=s.material[0], mu=s.material[1],
+                   rho=s.material[2], tau_epsilon_nu1=q.tau_epsilon_nu1, tau_sigma_nu1=q.tau_sigma_nu1,
+                   tau_epsilon_nu2=q.tau_epsilon_nu2, tau_sigma_nu2=q.tau_sigma_nu2, prof_x=s.prof_x, prof_y=s.prof_y,
+                   force_x=s.force_x, force_y=s.force_y, ix_rec=s.ix_rec, iy_rec=s.iy_rec, kind="timed")
+    sec = O.last_loop_seconds()
+    O.set_warmup_steps(0)
+    return float(q.NX) * q.NY * steps / sec / 1e9, sec, 1      # the 2-D programs are serial
 
 
 def oracle_2d_gpts(p, n_sample, steps, warmup):
@@ -197,7 +235,11 @@ def run_reference(args):
     if rank != 0:
         return 0
     p, kind = workload_params(args.workload, args.gpus, args.steps + args.warmup)
-    if kind == "3dv":
+    if kind == "2dv":
+        n_s = 1001
+        v, sec, cores = oracle_2dv_gpts(p, n_s, args.steps, args.warmup)
+        sample = f"{n_s}x{n_s} sample grid, {args.steps} timed steps after {args.warmup}, serial like the reference"
+    elif kind == "3dv":
         nz_s = 40
         v, sec, cores = oracle_3dv_gpts(p, nz_s, args.steps, args.warmup)
         sample = (f"{p.NX}x{min(p.NY, 256)}x{nz_s} reduced sample of the workload grid (4 emulated MPI slabs), "
@@ -255,13 +297,16 @@ def run_b200(args):
     K, W = args.steps, max(args.warmup, 3)
     nstep_total = W + K + K + 8          # warm-up + device-timed + e2e-timed (+ slack)
     p, kind = workload_params(args.workload, world, nstep_total)
-    s = P.setup_3d(p) if kind == "3d" else P.setup_3d_visco(p) if kind == "3dv" else P.setup_2d(p)
+    s = P.setup_3d(p) if kind == "3d" else P.setup_3d_visco(p) if kind == "3dv" else P.setup_2d_visco(p) if kind == "2dv" else P.setup_2d(p)
     if kind == "3d":
         sol = P.make_solver_3d(p, s, nslabs=world, slab_rank=rank, device=local_rank)
         pts_step_rank = float(p.NX) * p.NY * (p.NZ // world)
     elif kind == "3dv":
         sol = P.make_solver_3d_visco(p, s, nslabs=world, slab_rank=rank, device=local_rank)
         pts_step_rank = float(p.NX) * p.NY * (p.NZ // world)
+    elif kind == "2dv":
+        sol = P.make_solver_2d_visco(p, s, device=local_rank)
+        pts_step_rank = float(p.NX) * p.NY
     else:
         sol = P.make_solver_2d(p, s, device=local_rank)
         pts_step_rank = float(p.NX) * p.NY
@@ -390,7 +435,7 @@ def run_b200(args):
                                 else "NCCL send/recv of 6 planes per step and interface"),
                        "fmad": False, "finite": finite,
                        "launch": sol.launch_info() if is3d else None},
-            "roofline": {"bound": "hbm", "kernel": ("k_stress3d_tma" if sol.launch_info()["tma"] else "k_stress3d") if kind == "3d" else "k_vstress3d" if kind == "3dv" else "k_stress2d",
+            "roofline": {"bound": "hbm", "kernel": ("k_stress3d_tma" if sol.launch_info()["tma"] else "k_stress3d") if kind == "3d" else "k_vstress3d" if kind == "3dv" else "k_vstress2d" if kind == "2dv" else "k_stress2d",
                          "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": (ach / peak) if ach else None, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": b_stress,
@@ -411,7 +456,10 @@ def run_b200(args):
         }
         if args.cpu_baseline and world == 1:
             try:
-                if kind == "3dv":
+                if kind == "2dv":
+                    v, sec, cores = oracle_2dv_gpts(p, 1001, 6, 2)
+                    sample = "1001x1001 sample grid, 6 timed steps after 2, serial like the reference"
+                elif kind == "3dv":
                     v, sec, cores = oracle_3dv_gpts(p, 40, 4, 1)
                     sample = f"{p.NX}x{min(p.NY, 256)}x40 reduced sample, 4 timed steps after 1, 4 emulated MPI slabs, FTZ/DAZ on"
                 elif kind == "3d":
@@ -437,7 +485,7 @@ def main():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg4", "cfg2", "cfg5", "cfg5d"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg4", "cfg2", "cfg5", "cfg5d", "cfg6"])
     ap.add_argument("--halo", default="p2p", choices=["p2p", "sendrecv"],
                     help="N > 1: peer stores from inside the kernels (default) or NCCL send/recv")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")

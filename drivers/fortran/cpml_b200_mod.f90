@@ -42,7 +42,8 @@ module cpml_b200
     integer(c_int32_t) :: energy_bug_compat
     integer(c_int32_t) :: rheology
     integer(c_int32_t) :: emulate_nproc
-    integer(c_int32_t) :: reserved_i(2)
+    integer(c_int32_t) :: compute_energy
+    integer(c_int32_t) :: reserved_i(1)
     real(c_double) :: deltax, deltay, deltaz
     real(c_double) :: deltat
     real(c_double) :: lambda, mu, lambdaplustwomu, rho
@@ -245,6 +246,13 @@ module cpml_b200
       import :: c_int32_t, c_ptr, c_double
       type(c_ptr), value :: handle
       real(c_double), intent(out) :: sisvx(*), sisvy(*)
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_get_pressure_seismograms(handle, sispressure) bind(C, name='cpml_get_pressure_seismograms') result(ierr)
+      import :: c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), intent(out) :: sispressure(*)
       integer(c_int32_t) :: ierr
     end function
 

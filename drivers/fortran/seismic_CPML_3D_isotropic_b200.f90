@@ -78,6 +78,7 @@ program seismic_CPML_3D_iso_b200
   cfg%nslabs = 1;  cfg%slab_rank = 0;  cfg%device = -1;  cfg%energy_bug_compat = 1
   cfg%rheology = 0
   cfg%emulate_nproc = 0
+  cfg%compute_energy = 0
   cfg%reserved_i = 0
   cfg%deltax = DELTAX;  cfg%deltay = DELTAY;  cfg%deltaz = DELTAZ;  cfg%deltat = DELTAT
   cfg%lambda = lambda;  cfg%mu = mu;  cfg%lambdaplustwomu = lambdaplustwomu;  cfg%rho = rho;  cfg%cp = cp

@@ -88,16 +88,20 @@ typedef struct cpml_config {
     int32_t device;          /* CUDA device ordinal, -1 = current device                 */
     int32_t energy_bug_compat; /* 1 = reference 3-D potential energy (yy counted twice,
                                 zz omitted, :1169-1172); 0 = physical formula            */
-    int32_t rheology;        /* 0 = isotropic elastic; 1 = viscoelastic, N_SLS = 2 standard
-                                linear solids (seismic_CPML_3D_viscoelastic_MPI.f90): needs
-                                ndim == 3, order == 4 and cpml_set_attenuation               */
+    int32_t rheology;        /* 0 = isotropic elastic; 1 = viscoelastic (needs cpml_set_attenuation):
+                                ndim == 3, order == 4: seismic_CPML_3D_viscoelastic_MPI.f90, N_SLS = 2;
+                                ndim == 2, order 2 | 4: seismic_CPML_2D_velocity_and_stress_
+                                {second,fourth}_order_viscoelastic.f90, N_SLS = 3              */
     int32_t emulate_nproc;   /* viscoelastic only: the reference's MPI exchange delivers only
                                 half of the z halo its 4th-order stencils read (3D-visco
                                 :962-975,:1229-1242 vs :991,:1149,:1189,:1251,:1271,:1294), so
                                 its result depends on NPROC.  n > 1 reproduces the reference run
                                 with NPROC = n (default 4, :158) on ANY number of GPU slabs;
                                 0 or 1 = every tap delivered (single-rank semantics)         */
-    int32_t reserved_i[2];
+    int32_t compute_energy;  /* 2-D viscoelastic only: COMPUTE_ENERGY of 2D-visco-4th :201 (.false. in the
+                                reference, the energy traces then stay zero); the other solvers always
+                                compute the energy, as their programs do                      */
+    int32_t reserved_i[1];
     double deltax, deltay, deltaz;   /* DELTAX, DELTAY, DELTAZ                           */
     double deltat;                   /* DELTAT                                           */
     /* homogeneous medium of the 3-D program (:139-144); the 2-D programs take arrays
@@ -139,11 +143,16 @@ int32_t cpml_set_profiles(cpml_handle *h, int32_t axis,
 int32_t cpml_set_material_2d(cpml_handle *h, const double *lambda, const double *mu,
                              const double *rho);
 
-/* Viscoelastic only: the relaxation times of the n_sls = 2 standard linear solids, as returned by
- * compute_attenuation_coeffs at 3D-visco :439-443 (nu1 = dilatation / QKappa, nu2 = shear / QMu).
- * The library derives inv_tau_sigma, phi_nu, Mu_nu and the unrelaxed Lame parameters with the
- * reference's own expressions (:458-477, :982-987).  lambda, mu of cpml_config are the RELAXED
- * parameters (:171-172); lambdaplustwomu is ignored (the loop uses lambda + 2 mu, :984). */
+/* Viscoelastic only: the relaxation times of the standard linear solids, as returned by
+ * compute_attenuation_coeffs.
+ * 3-D (n_sls = 2, 3D-visco :439-443; nu1 = dilatation / QKappa, nu2 = shear / QMu): the library
+ * derives inv_tau_sigma, phi_nu, Mu_nu and the unrelaxed Lame parameters with the reference's own
+ * expressions (:458-477, :982-987).  lambda, mu of cpml_config are the RELAXED parameters
+ * (:171-172); lambdaplustwomu is ignored (the loop uses lambda + 2 mu, :984).
+ * 2-D (n_sls = 3, 2D-visco-4th :366-370; nu1 from Qp, nu2 from Qs): the library derives
+ * HALF_DELTAT_over_tau_sigma, multiplication_factor_tau_sigma and DELTAT_phi (:386-399); the arrays
+ * of cpml_set_material_2d are then the UNRELAXED lambda, mu (:596-601).  tau_epsilon == tau_sigma
+ * gives the elastic branch (VISCOELASTIC_ATTENUATION = .false., :713-760) bit for bit. */
 int32_t cpml_set_attenuation(cpml_handle *h, int32_t n_sls,
                              const double *tau_epsilon_nu1, const double *tau_sigma_nu1,
                              const double *tau_epsilon_nu2, const double *tau_sigma_nu2);
@@ -226,6 +235,10 @@ int32_t cpml_get_launch_info(cpml_handle *h, int32_t *info, int32_t n);
 /* sisvx, sisvy as declared at :286: (NSTEP,NREC) column-major, zero beyond the
  * last executed step.  On a slab that does not own the receiver plane they are zero. */
 int32_t cpml_get_seismograms(cpml_handle *h, double *sisvx, double *sisvy);
+
+/* 2-D viscoelastic only: sispressure(NSTEP,NREC) of 2D-visco-4th :304, filled at :1004-1035
+ * (pressure = -(lambda + 2/3 mu)(epsilon_xx + epsilon_yy) at the receiver). */
+int32_t cpml_get_pressure_seismograms(cpml_handle *h, double *sispressure);
 
 /* Energy traces, length NSTEP.  3-D: total = this slab's share of total_energy(it)
  * (:1179 sums the shares); kinetic/potential may be NULL.  2-D: kinetic and

@@ -48,6 +48,17 @@ int oracle_num_threads(void)
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm of bench.py asks for the
+ * host's cores explicitly. */
+void oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 void oracle_set_ftz(int on)
 {
 #if defined(__x86_64__) && defined(_OPENMP)

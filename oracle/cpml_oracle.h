@@ -181,6 +181,47 @@ int oracle_run_3d_visco(const oraclev3d_config *cfg,
                         double *energy_total, double *energy_kinetic, double *energy_potential,
                         double *fields_final, double *vnorm_final);
 
+/* ----------------------------------------------------------- 2-D viscoelastic */
+
+typedef struct {
+    int order;            /* 2: seismic_CPML_2D_velocity_and_stress_second_order_viscoelastic.f90
+                             4: seismic_CPML_2D_velocity_and_stress_fourth_order_viscoelastic.f90 */
+    int nx, ny;
+    double deltax, deltay, deltat;
+    int nstep;
+    int npoints_pml;
+    int isource, jsource; /* 1-based */
+    int nrec;
+    int viscoelastic_attenuation;   /* VISCOELASTIC_ATTENUATION (:140); 0 runs the elastic branch :713-760 */
+    int compute_energy;             /* COMPUTE_ENERGY (:201), .false. in the reference */
+    /* N_SLS = 3 Zener solids (:329); nu1 from Qp, nu2 from Qs */
+    double tau_epsilon_nu1[3], tau_sigma_nu1[3], tau_epsilon_nu2[3], tau_sigma_nu2[3];
+} oraclev2d_config;
+
+/* Ricker source of the 2-D viscoelastic programs divided by the cell area (2D-visco-4th :931-947):
+ * force_source_term = factor*(1 - 2a(t-t0)^2) exp(-a(t-t0)^2) / (DELTAX*DELTAY). */
+void oracle_source_series_ricker(int nstep, double deltat, double f0, double t0, double factor,
+                                 double angle_force_deg, double deltax, double deltay,
+                                 double *force_x, double *force_y);
+
+/* Runs time steps 1..nstep of the 2-D viscoelastic programs (2D-visco-4th :705-1060; the
+ * second-order file differs only in the difference operator).  lambda/mu are the UNRELAXED
+ * parameters (:596-601), arrays of nx*ny values, i fastest.  Outputs: sisvx/sisvy/sispressure
+ * (nstep*nrec), energies (nstep; zero unless compute_energy), optional final fields vx, vy,
+ * sigma_xx, sigma_yy, sigma_xy (nx*ny each) and the nine memory variables e1(1..3), e11(1..3),
+ * e13(1..3) back to back (9*nx*ny). */
+int oracle_run_2d_visco(const oraclev2d_config *cfg,
+                        const double *lambda_unrelaxed, const double *mu_unrelaxed, const double *rho,
+                        const double *a_x, const double *b_x, const double *K_x,
+                        const double *a_x_half, const double *b_x_half, const double *K_x_half,
+                        const double *a_y, const double *b_y, const double *K_y,
+                        const double *a_y_half, const double *b_y_half, const double *K_y_half,
+                        const double *force_x, const double *force_y,
+                        const int *ix_rec, const int *iy_rec,
+                        double *sisvx, double *sisvy, double *sispressure,
+                        double *energy_kinetic, double *energy_potential,
+                        double *fields_final, double *memvar_final, double *velocnorm_final);
+
 /* Timing of the last oracle_run_* call: wall seconds of its time loop only (set-up and
  * allocation excluded), not counting the first `w` warm-up steps. */
 void oracle_set_warmup_steps(int w);
@@ -188,6 +229,8 @@ double oracle_last_loop_seconds(void);
 
 /* Number of OpenMP threads the timed build will use (1 if built without). */
 int oracle_num_threads(void);
+/* Overrides OMP_NUM_THREADS for the following oracle_run_* calls (timed build). */
+void oracle_set_num_threads(int n);
 /* Flush-to-zero / denormals-are-zero for the timed CPU baseline (cf. the
  * reference Makefile:18 remark on -ftz).  No-op in the golden build. */
 void oracle_set_ftz(int on);

@@ -52,10 +52,20 @@ class OracleV3DConfig(C.Structure):
                 ("complete_halos", C.c_int)]
 
 
+class OracleV2DConfig(C.Structure):
+    _fields_ = [("order", C.c_int), ("nx", C.c_int), ("ny", C.c_int),
+                ("deltax", C.c_double), ("deltay", C.c_double), ("deltat", C.c_double),
+                ("nstep", C.c_int), ("npoints_pml", C.c_int),
+                ("isource", C.c_int), ("jsource", C.c_int), ("nrec", C.c_int),
+                ("viscoelastic_attenuation", C.c_int), ("compute_energy", C.c_int),
+                ("tau_epsilon_nu1", C.c_double * 3), ("tau_sigma_nu1", C.c_double * 3),
+                ("tau_epsilon_nu2", C.c_double * 3), ("tau_sigma_nu2", C.c_double * 3)]
+
+
 def build(force: bool = False) -> None:
     """Compile both oracle libraries (no-op when they are already there)."""
     names = ["liboracle_golden.so", "liboracle_timed.so"]
-    srcs = ["cpml_oracle.c", "cpml_oracle_visco.c", "cpml_oracle.h", "oracle_internal.h", "Makefile"]
+    srcs = ["cpml_oracle.c", "cpml_oracle_visco.c", "cpml_oracle_visco2d.c", "cpml_oracle.h", "oracle_internal.h", "Makefile"]
     if not force and all(os.path.exists(os.path.join(_HERE, n)) for n in names):
         # prebuilt libraries travel to the GPU box; rebuild only when a source is newer
         newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in srcs)
@@ -97,6 +107,13 @@ def lib(kind: str = "golden") -> C.CDLL:
         L.oracle_run_3d_visco.restype = C.c_int
         L.oracle_run_3d_visco.argtypes = [C.POINTER(OracleV3DConfig)] + [_dp] * 18 + [_dp] * 2 + [_ip] * 2 \
             + [_dp] * 5 + [_dp] * 2
+        L.oracle_source_series_ricker.restype = None
+        L.oracle_source_series_ricker.argtypes = [C.c_int] + [C.c_double] * 7 + [_dp, _dp]
+        L.oracle_run_2d_visco.restype = C.c_int
+        L.oracle_run_2d_visco.argtypes = [C.POINTER(OracleV2DConfig)] + [_dp] * 3 + [_dp] * 12 + [_dp] * 2 \
+            + [_ip] * 2 + [_dp] * 5 + [_dp] * 3
+        L.oracle_set_num_threads.restype = None
+        L.oracle_set_num_threads.argtypes = [C.c_int]
         L.oracle_num_threads.restype = C.c_int
         L.oracle_set_warmup_steps.argtypes = [C.c_int]
         L.oracle_last_loop_seconds.restype = C.c_double
@@ -277,8 +294,55 @@ def run_3d_visco(*, nx, ny, nz, nproc, deltax, deltay, deltaz, deltat, lam, mu, 
     return out
 
 
+def source_series_ricker(nstep, deltat, f0, t0, factor, angle_force_deg, deltax, deltay, kind="golden"):
+    fx, fy = np.zeros(nstep), np.zeros(nstep)
+    lib(kind).oracle_source_series_ricker(nstep, deltat, f0, t0, factor, angle_force_deg, deltax, deltay, _d(fx), _d(fy))
+    return fx, fy
+
+
+def run_2d_visco(*, order, nx, ny, deltax, deltay, deltat, nstep, npoints_pml, isource, jsource, lam, mu, rho,
+                 tau_epsilon_nu1, tau_sigma_nu1, tau_epsilon_nu2, tau_sigma_nu2, prof_x, prof_y, force_x, force_y,
+                 ix_rec, iy_rec, viscoelastic_attenuation=True, compute_energy=False, want_fields=False,
+                 kind="golden", **_ignored):
+    """lam/mu: UNRELAXED Lame parameters, nx*ny values, i fastest."""
+    nrec = len(ix_rec)
+    A3 = C.c_double * 3
+    cfg = OracleV2DConfig(order, nx, ny, deltax, deltay, deltat, nstep, npoints_pml, isource, jsource, nrec,
+                          int(viscoelastic_attenuation), int(compute_energy), A3(*tau_epsilon_nu1),
+                          A3(*tau_sigma_nu1), A3(*tau_epsilon_nu2), A3(*tau_sigma_nu2))
+    lam, mu, rho = _f64(lam).ravel(), _f64(mu).ravel(), _f64(rho).ravel()
+    assert lam.size == nx * ny and mu.size == nx * ny and rho.size == nx * ny
+    px = [_f64(prof_x[k]) for k in _PK]
+    py = [_f64(prof_y[k]) for k in _PK]
+    fx, fy = _f64(force_x), _f64(force_y)
+    assert fx.size >= nstep and fy.size >= nstep
+    ixr = np.ascontiguousarray(ix_rec, dtype=np.int32)
+    iyr = np.ascontiguousarray(iy_rec, dtype=np.int32)
+    sisvx, sisvy, sisp = np.zeros((nrec, nstep)), np.zeros((nrec, nstep)), np.zeros((nrec, nstep))
+    ek, ep = np.zeros(nstep), np.zeros(nstep)
+    fields = np.zeros((5, ny, nx)) if want_fields else None
+    memvar = np.zeros((3, 3, ny, nx)) if want_fields else None
+    vnorm = C.c_double(0.0)
+    rc = lib(kind).oracle_run_2d_visco(C.byref(cfg), _d(lam), _d(mu), _d(rho), *[_d(p) for p in px],
+                                       *[_d(p) for p in py], _d(fx), _d(fy), _i(ixr), _i(iyr),
+                                       _d(sisvx), _d(sisvy), _d(sisp), _d(ek), _d(ep), _d(fields), _d(memvar),
+                                       C.byref(vnorm))
+    if rc != 0:
+        raise RuntimeError(f"oracle_run_2d_visco failed rc={rc}")
+    out = dict(sisvx=sisvx, sisvy=sisvy, sispressure=sisp, energy_kinetic=ek, energy_potential=ep,
+               velocnorm=vnorm.value)
+    if want_fields:
+        out.update(dict(zip(("vx", "vy", "sigmaxx", "sigmayy", "sigmaxy"), fields)))
+        out.update(e1=memvar[0], e11=memvar[1], e13=memvar[2])
+    return out
+
+
 def num_threads(kind="timed") -> int:
     return lib(kind).oracle_num_threads()
+
+
+def set_num_threads(n: int, kind="timed") -> None:
+    lib(kind).oracle_set_num_threads(int(n))
 
 
 def set_ftz(on: bool, kind="timed") -> None:

@@ -45,10 +45,12 @@ struct cpml_handle {
     size_t flags_offset = 0;   // doubles from the arena start to the slab flags
 
     // viscoelastic (rheology == 1): six (N_SLS = 2) strain memory variables, constants of 3D-visco :458-477
-    bool visco = false;
+    bool visco = false;        // 3-D viscoelastic
+    bool visco2d = false;      // 2-D viscoelastic (N_SLS = 3): fields 5..13 are e1(1..3), e11(1..3), e13(1..3)
     double2 *e0[6] = {};       // element (1,1,0) of e1, e11, e22, e12, e13, e23
     bool have_attenuation = false;
-    double tau[4][2] = {};     // tau_epsilon_nu1, tau_sigma_nu1, tau_epsilon_nu2, tau_sigma_nu2
+    double tau[4][3] = {};     // tau_epsilon_nu1, tau_sigma_nu1, tau_epsilon_nu2, tau_sigma_nu2
+    double *d_sisp = nullptr;  // 2-D viscoelastic: sispressure
     dim3 vgrid;
     int vkchunk = 1, vtx = 32, vty = 8;
 
@@ -167,8 +169,9 @@ static int32_t create_impl(cpml_handle *h)
     const cpml_config &c = h->cfg;
     if (c.ndim != 2 && c.ndim != 3) FAIL(CPML_EINVAL, "ndim must be 2 or 3");
     if (c.rheology != 0 && c.rheology != 1) FAIL(CPML_EINVAL, "rheology must be 0 (elastic) or 1 (viscoelastic)");
-    h->visco = c.rheology == 1;
-    if (h->visco && (c.ndim != 3 || c.order != 4)) FAIL(CPML_EINVAL, "the viscoelastic solver is 3-D, fourth order (ndim = 3, order = 4)");
+    h->visco = c.rheology == 1 && c.ndim == 3;
+    h->visco2d = c.rheology == 1 && c.ndim == 2;
+    if (h->visco && c.order != 4) FAIL(CPML_EINVAL, "the 3-D viscoelastic solver is fourth order (order = 4)");
     if (c.ndim == 3 && !h->visco && c.order != 2) FAIL(CPML_EINVAL, "3-D isotropic solver is second order (order must be 2)");
     if (c.emulate_nproc < 0) FAIL(CPML_EINVAL, "emulate_nproc must be >= 0");
     if (c.emulate_nproc > 1) {
@@ -241,7 +244,7 @@ static int32_t create_impl(cpml_handle *h)
         h->plane = (long long)h->pitch * (c.ny + 2 * gy);
         h->origin = (long long)gy * h->pitch + xo;
         h->field_doubles = (size_t)h->plane + 16;
-        h->nfields = 5;
+        h->nfields = h->visco2d ? 14 : 5;
     }
     h->field_doubles = (h->field_doubles + 15) / 16 * 16;      // every field starts on a 128-byte line
     h->flags_offset = (size_t)(h->nfields + 2 * ne) * h->field_doubles;
@@ -267,6 +270,7 @@ static int32_t create_impl(cpml_handle *h)
     const size_t ns = std::max<size_t>(1, nt * (size_t)c.nrec);
     CK(cudaMalloc(&h->d_sisvx, ns * sizeof(double)));
     CK(cudaMalloc(&h->d_sisvy, ns * sizeof(double)));
+    if (h->visco2d) CK(cudaMalloc(&h->d_sisp, ns * sizeof(double)));
     CK(cudaMalloc(&h->d_ix_rec, std::max(1, c.nrec) * sizeof(int)));
     CK(cudaMalloc(&h->d_iy_rec, std::max(1, c.nrec) * sizeof(int)));
     CK(cudaMalloc(&h->d_maxbits, sizeof(unsigned long long)));
@@ -383,7 +387,7 @@ extern "C" int32_t cpml_destroy(cpml_handle *h)
     for (auto &p : h->my) cudaFree(p);
     for (auto &p : h->mz) cudaFree(p);
     cudaFree(h->d_src_x); cudaFree(h->d_src_y); cudaFree(h->d_ix_rec); cudaFree(h->d_iy_rec);
-    cudaFree(h->d_sisvx); cudaFree(h->d_sisvy); cudaFree(h->d_ek); cudaFree(h->d_ep);
+    cudaFree(h->d_sisvx); cudaFree(h->d_sisvy); cudaFree(h->d_sisp); cudaFree(h->d_ek); cudaFree(h->d_ep);
     cudaFree(h->d_partials); cudaFree(h->d_maxbits);
     cudaFreeHost(h->pin_src); cudaFreeHost(h->pin_out);
     for (auto e : h->ev) cudaEventDestroy(e);
@@ -410,6 +414,8 @@ extern "C" int32_t cpml_reset(cpml_handle *h)
     const size_t ns = std::max<size_t>(1, nt * (size_t)c.nrec);
     CK(cudaMemsetAsync(h->d_sisvx, 0, ns * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->d_sisvy, 0, ns * sizeof(double), h->stream));
+    if (h->d_sisp) CK(cudaMemsetAsync(h->d_sisp, 0, ns * sizeof(double), h->stream));
+    if (h->visco2d && h->d_partials) CK(cudaMemsetAsync(h->d_partials, 0, 2 * (size_t)h->nblocks * sizeof(double), h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return CPML_OK;
 }
@@ -483,12 +489,13 @@ extern "C" int32_t cpml_set_attenuation(cpml_handle *h, int32_t n_sls, const dou
                                         const double *tau_sigma_nu2)
 {
     if (!h) return CPML_EINVAL;
-    if (!h->visco) FAIL(CPML_EINVAL, "cpml_set_attenuation is for the viscoelastic solver (rheology = 1)");
-    if (n_sls != 2) FAIL(CPML_EINVAL, "the viscoelastic loop is written for N_SLS = 2 (3D-visco :189, :1003-1049)");
+    if (!h->visco && !h->visco2d) FAIL(CPML_EINVAL, "cpml_set_attenuation is for the viscoelastic solvers (rheology = 1)");
+    if (h->visco && n_sls != 2) FAIL(CPML_EINVAL, "the 3-D viscoelastic loop is written for N_SLS = 2 (3D-visco :189, :1003-1049)");
+    if (h->visco2d && n_sls != 3) FAIL(CPML_EINVAL, "the 2-D viscoelastic programs use N_SLS = 3 (2D-visco-4th :329)");
     if (!tau_epsilon_nu1 || !tau_sigma_nu1 || !tau_epsilon_nu2 || !tau_sigma_nu2) FAIL(CPML_EINVAL, "null relaxation times");
     const double *src[4] = {tau_epsilon_nu1, tau_sigma_nu1, tau_epsilon_nu2, tau_sigma_nu2};
     for (int q = 0; q < 4; q++)
-        for (int l = 0; l < 2; l++) {
+        for (int l = 0; l < n_sls; l++) {
             if (!(src[q][l] > 0.0) || !std::isfinite(src[q][l])) FAIL(CPML_EINVAL, "relaxation times must be positive");
             h->tau[q][l] = src[q][l];
         }
@@ -699,7 +706,7 @@ static int32_t finalize(cpml_handle *h)
     if (!h->have_source) FAIL(CPML_ESTATE, "cpml_set_source_series has not been called");
     if (c.nrec > 0 && !h->have_receivers) FAIL(CPML_ESTATE, "cpml_set_receivers has not been called");
     if (c.ndim == 2 && !h->have_material) FAIL(CPML_ESTATE, "cpml_set_material_2d has not been called");
-    if (h->visco && !h->have_attenuation) FAIL(CPML_ESTATE, "cpml_set_attenuation has not been called");
+    if ((h->visco || h->visco2d) && !h->have_attenuation) FAIL(CPML_ESTATE, "cpml_set_attenuation has not been called");
     CK(cudaSetDevice(h->device));
 
     const Shell &sx = h->shell[0], &sy = h->shell[1];
@@ -843,6 +850,26 @@ static Params2D make_p2(cpml_handle *h, int it)
     p.denx = c.order == 4 ? 24.0 * c.deltax : c.deltax;      // 2D-4th :565 / 2D-2nd :564
     p.deny = c.order == 4 ? 24.0 * c.deltay : c.deltay;
     p.rdenx = 1.0 / p.denx; p.rdeny = 1.0 / p.deny;
+    if (h->visco2d) {
+        // 2D-visco-4th :210-213 (second-order file :209-210) and :386-399, in the reference's order
+        const double DELTAT = c.deltat;
+        p.c98x = c.order == 4 ? 9.0 / (8.0 * c.deltax) : 1.0 / c.deltax;
+        p.c98y = c.order == 4 ? 9.0 / (8.0 * c.deltay) : 1.0 / c.deltay;
+        p.c24x = 1.0 / (24.0 * c.deltax); p.c24y = 1.0 / (24.0 * c.deltay);
+        const double *te1 = h->tau[0], *ts1 = h->tau[1], *te2 = h->tau[2], *ts2 = h->tau[3];
+        double sum1 = 0.0, sum2 = 0.0;
+        for (int l = 0; l < 3; l++) { sum1 = sum1 + te1[l] / ts1[l]; sum2 = sum2 + te2[l] / ts2[l]; }
+        for (int l = 0; l < 3; l++) {
+            const double one_over_tau_sigma_nu1 = 1.0 / ts1[l], one_over_tau_sigma_nu2 = 1.0 / ts2[l];
+            p.half1[l] = 0.5 * DELTAT / ts1[l];
+            p.half2[l] = 0.5 * DELTAT / ts2[l];
+            p.mul1[l] = 1.0 / (1.0 + 0.5 * DELTAT * one_over_tau_sigma_nu1);
+            p.mul2[l] = 1.0 / (1.0 + 0.5 * DELTAT * one_over_tau_sigma_nu2);
+            p.dt_phi1[l] = DELTAT * (1.0 - te1[l] / ts1[l]) / ts1[l] / sum1;
+            p.dt_phi2[l] = DELTAT * (1.0 - te2[l] / ts2[l]) / ts2[l] / sum2;
+            p.e1[l] = h->f0[5 + l]; p.e11[l] = h->f0[8 + l]; p.e13[l] = h->f0[11 + l];
+        }
+    }
     p.it = it; p.isrc = c.isource; p.jsrc = c.jsource;
     p.force_x = h->d_src_x; p.force_y = h->d_src_y;
     p.npml = c.npoints_pml;
@@ -974,6 +1001,10 @@ static int32_t half_step(cpml_handle *h, int32_t it, int phase)
                 h->n_launches++;
             }
         }
+    } else if (h->visco2d) {
+        if (phase == 0) launch_vstress2d(make_p2(h, it), h->grid, h->stream);
+        else launch_vvelocity2d(make_p2(h, it), h->grid, h->stream);
+        h->n_launches++;
     } else {
         if (phase == 0) launch_stress2d(make_p2(h, it), h->grid, h->block, h->stream);
         else launch_velocity2d(make_p2(h, it), h->grid, h->block, h->stream);
@@ -1026,6 +1057,12 @@ extern "C" int32_t cpml_step_finish(cpml_handle *h, int32_t it)
         p.krec = 1;
     }
     p.sisvx = h->d_sisvx; p.sisvy = h->d_sisvy;
+    if (h->visco2d) {
+        const Params2D p2 = make_p2(h, it);
+        if (c.compute_energy) { launch_venergy2d(p2, h->grid, h->stream); h->n_launches++; }   // COMPUTE_ENERGY, :1037
+        launch_vpressure2d(p2, h->d_ix_rec, h->d_iy_rec, c.nrec, c.nstep, h->d_sisp, h->stream);
+        h->n_launches += c.nrec > 0 ? 1 : 0;
+    }
     launch_post3d(p, h->stream);
     h->n_launches++;
     CK(cudaGetLastError());
@@ -1213,6 +1250,18 @@ extern "C" int32_t cpml_get_seismograms(cpml_handle *h, double *sisvx, double *s
     return CPML_OK;
 }
 
+extern "C" int32_t cpml_get_pressure_seismograms(cpml_handle *h, double *sispressure)
+{
+    if (!h || !sispressure) return CPML_EINVAL;
+    if (!h->visco2d) FAIL(CPML_EINVAL, "pressure seismograms exist in the 2-D viscoelastic programs only");
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->cfg.nstep * (size_t)h->cfg.nrec;
+    if (n == 0) return CPML_OK;
+    CK(cudaMemcpyAsync(sispressure, h->d_sisp, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return CPML_OK;
+}
+
 extern "C" int32_t cpml_get_energy(cpml_handle *h, double *total, double *kinetic, double *potential)
 {
     if (!h) return CPML_EINVAL;
@@ -1339,6 +1388,11 @@ extern "C" int32_t cpml_algorithmic_bytes(cpml_handle *h, double *bytes_stress, 
         //   x: dsxx_dx (int), dsxy_dx, dsxz_dx (half)    y: dsxy_dy, dsyz_dy (int), dsyy_dy (half)
         //   z: dsxz_dz, dsyz_dz (int), dszz_dz (half)
         wv = 12.0 * N + 2.0 * (px * (nz[0][0] + 2 * nz[0][1]) + py * (2 * nz[1][0] + nz[1][1]) + pz * (2 * nz[2][0] + nz[2][1]));
+    } else if (h->visco2d) {
+        // stress: read vx,vy, lambda, mu; read+write 3 sigma and the 9 memory variables; velocity: read 3 sigma, rho; read+write vx,vy
+        const double px = (double)c.ny, py = (double)c.nx;
+        ws = 28.0 * N + 2.0 * (px * (nz[0][0] + nz[0][1]) + py * (nz[1][0] + nz[1][1]));
+        wv = 8.0 * N + 2.0 * (px * (nz[0][0] + nz[0][1]) + py * (nz[1][0] + nz[1][1]));
     } else {
         // stress: read vx,vy, lambda, mu; read+write 3 sigma; x: dvx_dx (half), dvy_dx (int); y: dvy_dy (int), dvx_dy (half)
         const double px = (double)c.ny, py = (double)c.nx;

@@ -190,6 +190,11 @@ struct Params2D {
     AxisCoef cx, cy;
     double deltax, deltay, deltat;
     double denx, rdenx, deny, rdeny;         // DELTAX (2nd order) or 24*DELTAX (4th), and RN(1/.)
+    // viscoelastic programs (kernels_2d_visco.cu): 9/(8 DELTA) and 1/(24 DELTA) (2D-visco-4th :210-213;
+    // second order: c98 = 1/DELTA), the N_SLS = 3 memory variables and the constants of :386-399
+    double c98x, c24x, c98y, c24y;
+    double *e1[3], *e11[3], *e13[3];
+    double half1[3], half2[3], mul1[3], mul2[3], dt_phi1[3], dt_phi2[3];
     int it;
     int isrc, jsrc;
     const double *force_x, *force_y;         // raw force series (2D-2nd :656-657)
@@ -228,6 +233,10 @@ int visco_stress_launches();
 void launch_stress2d(const Params2D &p, dim3 grid, dim3 block, cudaStream_t s);
 void launch_velocity2d(const Params2D &p, dim3 grid, dim3 block, cudaStream_t s);
 void launch_post2d(const Post2D &p, cudaStream_t s);
+void launch_vstress2d(const Params2D &p, dim3 grid, cudaStream_t s);
+void launch_vvelocity2d(const Params2D &p, dim3 grid, cudaStream_t s);
+void launch_vpressure2d(const Params2D &p, const int *ix_rec, const int *iy_rec, int nrec, int nstep, double *sispressure, cudaStream_t s);
+void launch_venergy2d(const Params2D &p, dim3 grid, cudaStream_t s);
 void launch_maxnorm(const double *vx, const double *vy, const double *vz, long long n,
                     unsigned long long *out_bits, cudaStream_t s);
 

@@ -22,6 +22,7 @@ AXIS_X, AXIS_Y, AXIS_Z = 0, 1, 2
 FIELDS_3D = ("vx", "vy", "vz", "sigmaxx", "sigmayy", "sigmazz", "sigmaxy", "sigmaxz", "sigmayz")
 FIELDS_3D_VISCO = FIELDS_3D + ("sigmaxx_R", "sigmayy_R", "sigmazz_R", "sigmaxy_R", "sigmaxz_R", "sigmayz_R")
 FIELDS_2D = ("vx", "vy", "sigmaxx", "sigmayy", "sigmaxy")
+FIELDS_2D_VISCO = FIELDS_2D + tuple(f"{e}_{l}" for e in ("e1", "e11", "e13") for l in (1, 2, 3))
 PROFILE_KEYS = ("a", "b", "K", "a_half", "b_half", "K_half")
 
 _dp = C.POINTER(C.c_double)
@@ -42,7 +43,7 @@ class CpmlConfig(C.Structure):
                 ("isource", C.c_int32), ("jsource", C.c_int32), ("ksource", C.c_int32),
                 ("nslabs", C.c_int32), ("slab_rank", C.c_int32), ("device", C.c_int32),
                 ("energy_bug_compat", C.c_int32), ("rheology", C.c_int32),
-                ("emulate_nproc", C.c_int32), ("reserved_i", C.c_int32 * 2),
+                ("emulate_nproc", C.c_int32), ("compute_energy", C.c_int32), ("reserved_i", C.c_int32 * 1),
                 ("deltax", C.c_double), ("deltay", C.c_double), ("deltaz", C.c_double),
                 ("deltat", C.c_double),
                 ("lambda_", C.c_double), ("mu", C.c_double), ("lambdaplustwomu", C.c_double),
@@ -79,6 +80,7 @@ SYMBOLS = {
     "cpml_p2p_detach": (C.c_int32, [_H]),
     "cpml_get_launch_info": (C.c_int32, [_H, _ip, C.c_int32]),
     "cpml_get_seismograms": (C.c_int32, [_H, _dp, _dp]),
+    "cpml_get_pressure_seismograms": (C.c_int32, [_H, _dp]),
     "cpml_get_energy": (C.c_int32, [_H, _dp, _dp, _dp]),
     "cpml_get_plane": (C.c_int32, [_H, C.c_int32, C.c_int32, _dp]),
     "cpml_get_field": (C.c_int32, [_H, C.c_int32, _dp]),
@@ -208,13 +210,13 @@ class Solver:
     def __init__(self, *, ndim, order=2, nx, ny, nz=1, nstep, npoints_pml, nrec, isource, jsource,
                  ksource=0, nslabs=1, slab_rank=0, device=-1, energy_bug_compat=True,
                  deltax, deltay, deltaz=0.0, deltat, lam=0.0, mu=0.0, lambdaplustwomu=0.0, rho=0.0,
-                 cp=0.0, rheology=0, emulate_nproc=0):
+                 cp=0.0, rheology=0, emulate_nproc=0, compute_energy=False):
         self._L = load()
         self.cfg = CpmlConfig(ndim=ndim, order=order, nx=nx, ny=ny, nz=nz, nstep=nstep,
                               npoints_pml=npoints_pml, nrec=nrec, isource=isource, jsource=jsource,
                               ksource=ksource, nslabs=nslabs, slab_rank=slab_rank, device=device,
                               energy_bug_compat=int(energy_bug_compat), rheology=rheology,
-                              emulate_nproc=emulate_nproc,
+                              emulate_nproc=emulate_nproc, compute_energy=int(compute_energy),
                               deltax=deltax, deltay=deltay, deltaz=deltaz, deltat=deltat,
                               lambda_=lam, mu=mu, lambdaplustwomu=lambdaplustwomu, rho=rho, cp=cp)
         self._h = _H()
@@ -357,6 +359,12 @@ class Solver:
         sx, sy = np.zeros((nrec, nstep)), np.zeros((nrec, nstep))
         self._ck(self._L.cpml_get_seismograms(self._h, _d(sx), _d(sy)))
         return sx, sy
+
+    def get_pressure_seismograms(self):
+        """sispressure shaped (NREC, NSTEP) (2-D viscoelastic programs, 2D-visco-4th :1004-1035)."""
+        sp = np.zeros((self.cfg.nrec, self.cfg.nstep))
+        self._ck(self._L.cpml_get_pressure_seismograms(self._h, _d(sp)))
+        return sp
 
     def get_energy(self):
         n = self.cfg.nstep

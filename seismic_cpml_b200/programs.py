@@ -6,6 +6,8 @@ C ABI (libcpml_b200.so).
   Program2DIso   <-> seismic_CPML_2D_isotropic_second_order.f90 (order=2)
                      seismic_CPML_2D_isotropic_fourth_order.f90 (order=4)
   Program3DVisco <-> seismic_CPML_3D_viscoelastic_MPI.f90
+  Program2DVisco <-> seismic_CPML_2D_velocity_and_stress_second_order_viscoelastic.f90 (order=2)
+                     seismic_CPML_2D_velocity_and_stress_fourth_order_viscoelastic.f90 (order=4)
 
 The reference configures itself through compile-time `parameter` constants; here they
 are dataclass fields with the Fortran names and the Fortran defaults.
@@ -241,6 +243,78 @@ class Params3DVisco:
         return (1.0 / tau1, 1.0 / tau2, 1.0 / tau3, 1.0 / tau4)
 
 
+# "Classical least-squares constants" for N_SLS = 3, Qp = 65, Qs = 55, f0 = 35 Hz that the reference
+# hard-codes in its analytical-solution program (analytical_solution_viscoelastic_2D_plane_strain_
+# Carcione_correct_with_1_over_L.f90:124-128) -- the medium of the 2-D viscoelastic programs.
+TAU_2D_VISCO = dict(tau_epsilon_nu1=(2.408158185753685e-002, 4.699608990861351e-003, 9.567997872435925e-004),
+                    tau_sigma_nu1=(2.256014638636808e-002, 4.508471279712252e-003, 8.937876403768840e-004),
+                    tau_epsilon_nu2=(2.430544480527216e-002, 4.728107829226396e-003, 9.667252695863502e-004),
+                    tau_sigma_nu2=(2.250919779429490e-002, 4.501388007338097e-003, 8.917332095369118e-004))
+
+
+@dataclass
+class Params2DVisco:
+    """Parameter block of seismic_CPML_2D_velocity_and_stress_{second,fourth}_order_viscoelastic.f90
+    (:140-230).  The relaxation times are inputs (the reference fits them with SolvOpt at :366-370)."""
+    order: int = 4
+    VISCOELASTIC_ATTENUATION: bool = True
+    NX: int = 2001
+    NY: int = 2001
+    DELTAX: float = 1.5
+    DELTAY: float | None = None
+    USE_PML_XMIN: bool = True
+    USE_PML_XMAX: bool = True
+    USE_PML_YMIN: bool = True
+    USE_PML_YMAX: bool = True
+    NPOINTS_PML: int = 10
+    cp_unrelaxed: float = 2000.0
+    cs_unrelaxed: float | None = None    # = cp_unrelaxed / 1.732 (:163)
+    density: float = 2000.0
+    DELTAT: float = 2.2e-4
+    NSTEP: int = 5200
+    f0: float = 35.0
+    t0: float | None = None
+    factor: float = 1.0
+    xsource: float = 1500.0
+    ysource: float = 1500.0
+    ISOURCE: int | None = None           # = xsource / DELTAX + 1 (:187)
+    JSOURCE: int | None = None
+    ANGLE_FORCE: float = 0.0
+    NREC: int = 1
+    xdeb: float = 2301.0
+    ydeb: float = 2301.0
+    xfin: float = 2301.0
+    yfin: float = 2301.0
+    COMPUTE_ENERGY: bool = False
+    IT_DISPLAY: int = 200
+    NPOWER: float = 2.0
+    K_MAX_PML: float = 1.0
+    ALPHA_MAX_PML: float | None = None
+    Rcoef: float = 0.001
+    N_SLS: int = 3
+    tau_epsilon_nu1: tuple = TAU_2D_VISCO["tau_epsilon_nu1"]
+    tau_sigma_nu1: tuple = TAU_2D_VISCO["tau_sigma_nu1"]
+    tau_epsilon_nu2: tuple = TAU_2D_VISCO["tau_epsilon_nu2"]
+    tau_sigma_nu2: tuple = TAU_2D_VISCO["tau_sigma_nu2"]
+
+    def __post_init__(self):
+        if self.order not in (2, 4):
+            raise ValueError("order must be 2 or 4")
+        if self.N_SLS != 3:
+            raise ValueError("the 2-D viscoelastic programs use N_SLS = 3")
+        if self.DELTAY is None: self.DELTAY = self.DELTAX
+        if self.cs_unrelaxed is None: self.cs_unrelaxed = self.cp_unrelaxed / 1.732
+        if self.t0 is None: self.t0 = 1.20 / self.f0
+        if self.ISOURCE is None: self.ISOURCE = int(self.xsource / self.DELTAX + 1)
+        if self.JSOURCE is None: self.JSOURCE = int(self.ysource / self.DELTAY + 1)
+        if self.ALPHA_MAX_PML is None: self.ALPHA_MAX_PML = 2.0 * PI * (self.f0 / 2.0)
+        if not self.VISCOELASTIC_ATTENUATION:        # dummy values of :374-380
+            self.tau_epsilon_nu1 = self.tau_sigma_nu1 = self.tau_epsilon_nu2 = self.tau_sigma_nu2 = (1.0, 1.0, 1.0)
+
+    @property
+    def cp(self): return self.cp_unrelaxed
+
+
 @dataclass
 class Setup:
     """What the reference builds before `do it = 1,NSTEP`."""
@@ -310,6 +384,50 @@ def setup_3d_visco(p: Params3DVisco) -> Setup:
     if courant > 1.0:
         raise _lib.CpmlError(_lib.CPML_ECFL, "time step is too large, simulation will be unstable")
     return Setup(prof_x, prof_y, prof_z, fx, fy, ix, iy, dist, courant)
+
+
+def host_source_series_ricker(p: "Params2DVisco"):
+    """2D-visco-4th :931-958: Ricker wavelet divided by the area of a grid cell."""
+    a = PI * PI * p.f0 * p.f0
+    rad = p.ANGLE_FORCE * (PI / 180.0)
+    fx, fy = np.zeros(p.NSTEP), np.zeros(p.NSTEP)
+    for it in range(1, p.NSTEP + 1):
+        t = float(it - 1) * p.DELTAT
+        term = p.factor * (1.0 - 2.0 * a * ((t - p.t0) * (t - p.t0))) * math.exp(-a * ((t - p.t0) * (t - p.t0)))
+        term = term / (p.DELTAX * p.DELTAY)
+        fx[it - 1] = math.sin(rad) * term
+        fy[it - 1] = math.cos(rad) * term
+    return fx, fy
+
+
+def setup_2d_visco(p: "Params2DVisco", material=None) -> Setup:
+    """2D-visco-4th :401-660."""
+    prof_x = _profile(p.NX, p.DELTAX, p, p.USE_PML_XMIN, p.USE_PML_XMAX, clamp=True)
+    prof_y = _profile(p.NY, p.DELTAY, p, p.USE_PML_YMIN, p.USE_PML_YMAX)
+    fx, fy = host_source_series_ricker(p)
+    ix, iy, dist = _lib.host_find_receivers(p.NX, p.NY, p.DELTAX, p.DELTAY, p.NREC, p.xdeb, p.ydeb, p.xfin, p.yfin)
+    courant = p.cp_unrelaxed * p.DELTAT / p.DELTAX                      # :654
+    limit = 0.606 if p.order == 4 else 1.0 / math.sqrt(2.0)               # :656 / second-order file :650
+    if p.DELTAX == p.DELTAY and courant > limit:
+        raise _lib.CpmlError(_lib.CPML_ECFL, "time step is too large, simulation will be unstable")
+    if material is None:                 # :596-602
+        n = p.NX * p.NY
+        mu = p.density * p.cs_unrelaxed * p.cs_unrelaxed
+        material = (np.full(n, p.density * p.cp_unrelaxed * p.cp_unrelaxed - 2.0 * mu), np.full(n, mu), np.full(n, p.density))
+    return Setup(prof_x, prof_y, None, fx, fy, ix, iy, dist, courant, material=material)
+
+
+def make_solver_2d_visco(p: "Params2DVisco", s: Setup, *, device=-1) -> _lib.Solver:
+    sol = _lib.Solver(ndim=2, order=p.order, rheology=1, compute_energy=p.COMPUTE_ENERGY, nx=p.NX, ny=p.NY,
+                      nstep=p.NSTEP, npoints_pml=p.NPOINTS_PML, nrec=p.NREC, isource=p.ISOURCE, jsource=p.JSOURCE,
+                      device=device, deltax=p.DELTAX, deltay=p.DELTAY, deltat=p.DELTAT, cp=0.0)
+    sol.set_profiles(_lib.AXIS_X, s.prof_x)
+    sol.set_profiles(_lib.AXIS_Y, s.prof_y)
+    sol.set_material_2d(*s.material)
+    sol.set_attenuation(p.tau_epsilon_nu1, p.tau_sigma_nu1, p.tau_epsilon_nu2, p.tau_sigma_nu2)
+    sol.set_source_series(s.force_x, s.force_y)
+    sol.set_receivers(s.ix_rec, s.iy_rec)
+    return sol
 
 
 def make_solver_3d_visco(p: Params3DVisco, s: Setup, *, nslabs=1, slab_rank=0, device=-1) -> _lib.Solver:
@@ -498,4 +616,34 @@ class Program2DIso(_ProgramBase):
             _lib.load().cpml_host_write_energy_2d(os.path.join(self.output_dir, "energy.dat").encode(),
                                                   _lib._d(ek), _lib._d(ep), self.p.NSTEP, self.p.DELTAT)
         return dict(sisvx=sx, sisvy=sy, energy_kinetic=ek, energy_potential=ep,
+                    display_log=self.display_log)
+
+
+class Program2DVisco(_ProgramBase):
+    """seismic_CPML_2D_velocity_and_stress_{second,fourth}_order_viscoelastic.f90."""
+
+    def __init__(self, params: Params2DVisco | None = None, material=None, output_dir=None, verbose=False, device=-1):
+        params = params or Params2DVisco()
+        s = setup_2d_visco(params, material)
+        super().__init__(params, s, make_solver_2d_visco(params, s, device=device), output_dir, verbose)
+
+    def _total_energy(self):
+        return self.solver.get_energy()[0]
+
+    def _snapshot_fields(self):          # :1083-1086
+        return self.solver.get_plane(0), self.solver.get_plane(1)
+
+    def results(self):
+        sx, sy = self.solver.get_seismograms()
+        sp = self.solver.get_pressure_seismograms()
+        total, ek, ep = self.solver.get_energy()
+        if self.output_dir is not None:
+            os.makedirs(self.output_dir, exist_ok=True)
+            self.write_seismograms()
+            # pressure_file_NNN.dat, :1178-1193: time - t0, pressure
+            for r in range(self.p.NREC):
+                with open(os.path.join(self.output_dir, f"pressure_file_{r + 1:03d}.dat"), "w") as f:
+                    for it in range(self.p.NSTEP):
+                        f.write(f" {np.float32(it * self.p.DELTAT - self.p.t0)}   {np.float32(sp[r, it])}\n")
+        return dict(sisvx=sx, sisvy=sy, sispressure=sp, energy_kinetic=ek, energy_potential=ep,
                     display_log=self.display_log)

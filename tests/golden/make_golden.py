@@ -52,6 +52,11 @@ def main():
     np.savez_compressed(os.path.join(HERE, "cpml3d_visco_small.npz"), sisvx=o["sisvx"], sisvy=o["sisvy"],
                         total_energy=o["total_energy"], energy_kinetic=o["energy_kinetic"],
                         energy_potential=o["energy_potential"])
+    # 2-D viscoelastic (N_SLS = 3), both orders, layered medium, reduced grid
+    for order in (2, 4):
+        o = O.run_2d_visco(**refcfg.cfgv2d(order=order, material="layered", nstep=300))
+        np.savez_compressed(os.path.join(HERE, f"cpml2d_visco_order{order}.npz"), sisvx=o["sisvx"], sisvy=o["sisvy"],
+                            sispressure=o["sispressure"])
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

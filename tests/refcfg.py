@@ -115,3 +115,41 @@ def cfgv3d(nx=38, ny=46, nz=40, nstep=120, npml=6, dt=4e-4, tau=None, rec_scale=
                 lam=rho * (cp * cp - 2.0 * cs * cs), mu=rho * cs * cs, rho=rho, nstep=nstep,
                 npoints_pml=npml, isource=isrc, jsource=jsrc, prof_x=px, prof_y=py, prof_z=pz,
                 force_x=fx, force_y=fy, ix_rec=ix, iy_rec=iy, cp_eff=cp * sq, **tau)
+
+
+# Relaxation times of the N_SLS = 3 Zener solids hard-coded in the reference's analytical-solution
+# program for Qp = 65 / Qs = 55 style media (analytical_solution_viscoelastic_2D_plane_strain_Carcione_
+# correct_with_1_over_L.f90:124-128: "classical least squares" constants, f0 = 35 Hz); used here as fixed
+# inputs that bypass the SolvOpt fit.
+TAU_2D_VISCO = dict(tau_epsilon_nu1=(2.408158185753685e-002, 4.699608990861351e-003, 9.567997872435925e-004),
+                    tau_sigma_nu1=(2.256014638636808e-002, 4.508471279712252e-003, 8.937876403768840e-004),
+                    tau_epsilon_nu2=(2.430544480527216e-002, 4.728107829226396e-003, 9.667252695863502e-004),
+                    tau_sigma_nu2=(2.250919779429490e-002, 4.501388007338097e-003, 8.917332095369118e-004))
+
+
+def cfgv2d(order=4, nx=81, ny=97, nstep=200, npml=8, tau=None, material="homogeneous", k_max=1.0, dt=2.2e-4):
+    """seismic_CPML_2D_velocity_and_stress_{second,fourth}_order_viscoelastic.f90 (:140-230) on a reduced grid."""
+    tau = dict(TAU_2D_VISCO if tau is None else tau)
+    dx = 1.5
+    cp, rho0 = 2000.0, 2000.0
+    cs = cp / 1.732
+    f0 = 35.0
+    t0 = 1.2 / f0
+    amax = 2.0 * PI * (f0 / 2.0)
+    px = O.pml_profile(nx, dx, dt, npml, cp=cp, alpha_max_pml=amax, clamp_alpha=True, k_max_pml=k_max)
+    py = O.pml_profile(ny, dx, dt, npml, cp=cp, alpha_max_pml=amax, k_max_pml=k_max)
+    fx, fy = O.source_series_ricker(nstep, dt, f0, t0, 1.0, 0.0, dx, dx)
+    isrc, jsrc = nx // 2 + 1, ny // 2 + 1
+    xs, ys = (isrc - 1) * dx, (jsrc - 1) * dx
+    ix, iy, _ = O.find_receivers(nx, ny, dx, dx, 2, xs + 20 * dx, ys + 20 * dx, xs + 10 * dx, ys - 25 * dx)
+    mu = np.full((ny, nx), rho0 * cs * cs)
+    lam = rho0 * cp * cp - 2.0 * mu
+    r = np.full((ny, nx), rho0)
+    if material == "layered":
+        jj, ii = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+        scale = np.where(jj > 2 * ny // 3, 0.7, 1.0) * (1.0 + 0.1 * ii / nx)
+        lam, mu = lam * scale, mu * scale
+        r = r * np.where(jj > 2 * ny // 3, 0.9, 1.0)
+    return dict(order=order, nx=nx, ny=ny, deltax=dx, deltay=dx, deltat=dt, nstep=nstep, npoints_pml=npml,
+                isource=isrc, jsource=jsrc, lam=lam.ravel(), mu=mu.ravel(), rho=r.ravel(), prof_x=px, prof_y=py,
+                force_x=fx, force_y=fy, ix_rec=ix, iy_rec=iy, **tau)

@@ -38,11 +38,11 @@ def test_fortran_module_binds_every_symbol_with_matching_arity():
     assert set(bound) == set(funcs), set(bound) ^ set(funcs)
     for name, n in funcs.items():
         assert bound[name] == n, (name, bound[name], n)
-    # the derived type mirrors struct cpml_config: 17 + 2 int32, then 9 + 4 doubles
+    # the derived type mirrors struct cpml_config: 18 + 1 int32, then 9 + 4 doubles
     t = f90[f90.index("type, bind(C) :: cpml_config"):f90.index("end type cpml_config")]
     ints = re.findall(r"integer\(c_int32_t\)\s*::\s*(.*)", t)
     reals = re.findall(r"real\(c_double\)\s*::\s*(.*)", t)
-    assert sum(len(x.split(",")) for x in ints) == 18      # 17 named + reserved_i(2)
+    assert sum(len(x.split(",")) for x in ints) == 19      # 18 named + reserved_i(1)
     assert sum(len(x.split(",")) for x in reals) == 10     # 9 named + reserved_d(4)
 
 
