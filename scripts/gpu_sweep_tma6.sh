@@ -1,0 +1,28 @@
+#!/bin/bash
+# isotropic TMA kernels: ring depth and tile height with the current code
+mkdir -p gpurun_out
+OUT=gpurun_out/sweep_tma6.txt; : > $OUT
+fmt='
+import sys, json
+for l in sys.stdin:
+    try:
+        d = json.loads(l); r = d["roofline"]; li = d["config"]["launch"]
+        print("  value %.2f Gpts/s  step %.3f ms  stress %.3f ms (%.0f GB/s, %.3f)  vel %.3f ms (%.0f GB/s, %.3f)  stepfrac %.3f e2e %.2f  zc %d ctas %d st %d" % (d["value"], d["ms_per_step"], r["avg_launch_ms"], r["achieved"], r["frac"], r["velocity_kernel"]["avg_launch_ms"], r["velocity_kernel"]["achieved"], r["velocity_kernel"]["frac"], r["step"]["frac"], d["e2e"]["value"], li["z_chunks"], li["ctas_stress"], li["stages"]))
+    except Exception as e:
+        print("  ?", l.strip()[:300])
+'
+run() { wl=$1; shift; echo "$wl $*" >> $OUT; env "$@" timeout 300 python bench.py --workload $wl --steps 30 --warmup 3 --no-cpu-baseline 2>&1 | python -c "$fmt" >> $OUT; }
+run cfg3 CPML_STAGES=2
+run cfg3 CPML_STAGES=3
+run cfg3 CPML_TY=4 CPML_MINB=2 CPML_STAGES=2
+run cfg3 CPML_TY=4 CPML_MINB=2 CPML_STAGES=3
+run cfg3 CPML_TY=4 CPML_MINB=2 CPML_STAGES=4
+run cfg3 CPML_TY=4 CPML_MINB=3 CPML_STAGES=2
+run cfg3 CPML_ZCHUNKS=5
+run cfg3 CPML_ZCHUNKS=10
+run cfg3 CPML_TY=4 CPML_MINB=2 CPML_STAGES=3 CPML_ZCHUNKS=5
+run cfg4 CPML_STAGES=2
+run cfg4 CPML_STAGES=3
+run cfg4 CPML_TY=4 CPML_MINB=2 CPML_STAGES=2
+run cfg4 CPML_TY=4 CPML_MINB=2 CPML_STAGES=3
+echo finished >> $OUT

@@ -806,6 +806,8 @@ static cudaError_t dispatch_tile(const Params3D &p, const TmaMaps &tm, const Til
     case 128043: return launch_tile<KUNIT, 128, 4, 3>(p, tm, t, s, stress, occ);
     case 128081: return launch_tile<KUNIT, 128, 8, 1>(p, tm, t, s, stress, occ);                  // 512 threads
     case 128082: return launch_tile<KUNIT, 128, 8, 2>(p, tm, t, s, stress, occ);
+    case 104041: case 104042: return launch_tile<KUNIT, 104, 4, 2>(p, tm, t, s, stress, occ);     // 208 threads
+    case 104043: case 104044: return launch_tile<KUNIT, 104, 4, 3>(p, tm, t, s, stress, occ);
     case 104081: return launch_tile<KUNIT, 104, 8, 1>(p, tm, t, s, stress, occ);                  // 416 threads
     case 104082: return launch_tile<KUNIT, 104, 8, 2>(p, tm, t, s, stress, occ);
     default: return cudaErrorInvalidValue;
@@ -815,7 +817,7 @@ static cudaError_t dispatch_tile(const Params3D &p, const TmaMaps &tm, const Til
 bool tma_tile_supported(int tx, int ty)
 {
     switch (tx * 100 + ty) {
-    case 6404: case 6408: case 12804: case 12808: case 10408: return true;     // TMA boxes hold at most 256 elements per dimension
+    case 6404: case 6408: case 12804: case 12808: case 10408: case 10404: return true;     // TMA boxes hold at most 256 elements per dimension
     default: return false;
     }
 }
