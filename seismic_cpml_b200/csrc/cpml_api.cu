@@ -754,6 +754,9 @@ static int32_t finalize(cpml_handle *h)
         h->nz_own[ax][1] = n1;
     }
     if (h->visco) {
+        // the viscoelastic kernels index with 32-bit element offsets
+        if (h->field_doubles >= (1ull << 31) || h->mx_doubles >= (1ull << 31) || h->my_doubles >= (1ull << 31) || h->mz_doubles >= (1ull << 31))
+            FAIL(CPML_EINVAL, "viscoelastic slab too large: a field must hold fewer than 2^31 points (use more z-slabs)");
         visco_tile(&h->vtx, &h->vty);
         // z chunks: short enough for several waves of blocks, long enough that the three extra
         // velocity planes fetched to fill the z windows stay small against 87 words per point

@@ -45,8 +45,8 @@ struct AxisCoef {
 // of Floating-Point Arithmetic, "division with a correctly rounded reciprocal") makes the second one
 // the correctly rounded quotient, provided nothing underflows or overflows on the way and the
 // significand of c is not all ones (checked on the host).  Outside a wide exponent window of the
-// dividend the generic IEEE division runs instead, so the result is bit-identical to a / c for
-// every input; zero dividends take the short path too.  Five dependent FP64 operations instead of
+// dividend the generic IEEE division runs instead, so the result equals a / c for every input
+// (for a zero dividend possibly with the other sign of zero); zero dividends stay on the short path.  Five dependent FP64 operations instead of
 // the ~60-instruction generic sequence (whose slow path is also taken for every zero dividend,
 // i.e. on the whole quiescent part of the grid).
 // The generic division, kept out of line so that the 20-odd call sites of a kernel share one copy
@@ -60,10 +60,14 @@ __device__ __forceinline__ double div_exact(double a, double c, double y)
     double q = __fma_rn(r, y, q0);
     r = __fma_rn(-c, q, a);
     q = __fma_rn(r, y, q);
-    const unsigned e = (unsigned)__double2hiint(a) & 0x7ff00000u;       // biased exponent field of a
-    if (e > 0x0c800000u && e < 0x73000000u) return q;                    // 2^-822 < |a| < 2^+817
-    if (a == 0.0) return q0;                                             // +-0 / c
-    return div_generic(a, c);
+    // one unsigned compare on the exponent field (sign shifted out): inside 2^-822 < |a| < 2^817 the
+    // five operations above are exact; outside, a zero keeps their result (+-0, equal in value to
+    // the quotient) and everything else takes the generic division
+    const unsigned u = ((unsigned)__double2hiint(a) << 1) - (0x0c9u << 21);
+    if (u >= ((0x730u - 0x0c9u) << 21)) {
+        if (a != 0.0) q = div_generic(a, c);
+    }
+    return q;
 }
 #endif
 

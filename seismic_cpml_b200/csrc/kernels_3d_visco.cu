@@ -41,7 +41,7 @@ __device__ __forceinline__ double2 vld2(const double2 *p) { return __ldcs(p); }
 __device__ __forceinline__ void vst2(double2 *p, double2 v) { __stcs(p, v); }
 
 // memory_x = b * memory_x + a * value ; value / K + memory_x   (e.g. :993-999); rK = RN(1/K)
-__device__ __forceinline__ double vcpml(double *__restrict__ mem, long long q, double b, double a, double K, double rK, double value)
+__device__ __forceinline__ double vcpml(double *__restrict__ mem, int q, double b, double a, double K, double rK, double value)
 {
     double m = mem[q];
     m = b * m + a * value;
@@ -123,8 +123,8 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
         const int kb = 1 + blockIdx.z * p.kchunk;
         const int ke = min(p.nzl, kb + p.kchunk - 1);
         const int pitch = p.pitch;
-        const long long pl = p.plane;
-        long long q = (long long)kb * pl + (long long)(j - 1) * pitch + (i - 1);
+        const int pl = (int)p.plane;           // < 2^31 elements per field (checked by cpml_create)
+        int q = kb * pl + (j - 1) * pitch + (i - 1);
 
         const bool in_x = (i <= p.xlo) || (i >= p.xhi);
         const bool in_y = (j <= p.ylo) || (j >= p.yhi);
@@ -155,12 +155,12 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
         for (int k = kb; k <= ke; ++k, q += pl) {
             const int kg = k + p.koff;                      // :978
             const bool in_z = (kg <= p.zlo) || (kg >= p.zhi);
-            long long qx = 0, qy = 0, qz = 0;
+            int qx = 0, qy = 0, qz = 0;
             double az = 0, bz = 0, Kz = 1, azh = 0, bzh = 0, Kzh = 1, rKz = 1, rKzh = 1;
-            if (in_x) qx = ((long long)(k - 1) * p.ny + (j - 1)) * p.sxp + sx;
-            if (in_y) qy = ((long long)(k - 1) * p.sy + sy) * pitch + (i - 1);
+            if (in_x) qx = ((k - 1) * p.ny + (j - 1)) * p.sxp + sx;
+            if (in_y) qy = ((k - 1) * p.sy + sy) * pitch + (i - 1);
             if (in_z) {
-                qz = ((long long)(vshell(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1);
+                qz = ((vshell(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1);
                 if (NORMAL) { az = p.cz.a[kg]; bz = p.cz.b[kg]; Kz = p.cz.K[kg]; rKz = p.cz.rK[kg]; }
                 if (SHEAR) { azh = p.cz.a_half[kg]; bzh = p.cz.b_half[kg]; Kzh = p.cz.K_half[kg]; rKzh = p.cz.rK_half[kg]; }
             }
@@ -320,8 +320,8 @@ k_vvelocity3d(const __grid_constant__ ParamsV3D p)
         const int kb = 1 + blockIdx.z * p.kchunk;
         const int ke = min(p.nzl, kb + p.kchunk - 1);
         const int pitch = p.pitch;
-        const long long pl = p.plane;
-        long long q = (long long)kb * pl + (long long)(j - 1) * pitch + (i - 1);
+        const int pl = (int)p.plane;           // < 2^31 elements per field (checked by cpml_create)
+        int q = kb * pl + (j - 1) * pitch + (i - 1);
 
         const bool in_x = (i <= p.xlo) || (i >= p.xhi);
         const bool in_y = (j <= p.ylo) || (j >= p.yhi);
@@ -360,12 +360,12 @@ k_vvelocity3d(const __grid_constant__ ParamsV3D p)
             double vx = vld(p.vx + q), vy = vld(p.vy + q), vz = vld(p.vz + q);
 
             const bool in_z = (kg <= p.zlo) || (kg >= p.zhi);
-            long long qx = 0, qy = 0, qz = 0;
+            int qx = 0, qy = 0, qz = 0;
             double az = 0, bz = 0, Kz = 1, azh = 0, bzh = 0, Kzh = 1, rKz = 1, rKzh = 1;
-            if (in_x) qx = ((long long)(k - 1) * p.ny + (j - 1)) * p.sxp + sx;
-            if (in_y) qy = ((long long)(k - 1) * p.sy + sy) * pitch + (i - 1);
+            if (in_x) qx = ((k - 1) * p.ny + (j - 1)) * p.sxp + sx;
+            if (in_y) qy = ((k - 1) * p.sy + sy) * pitch + (i - 1);
             if (in_z) {
-                qz = ((long long)(vshell(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1);
+                qz = ((vshell(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1);
                 az = p.cz.a[kg]; bz = p.cz.b[kg]; Kz = p.cz.K[kg];
                 azh = p.cz.a_half[kg]; bzh = p.cz.b_half[kg]; Kzh = p.cz.K_half[kg];
                 rKz = p.cz.rK[kg]; rKzh = p.cz.rK_half[kg];
