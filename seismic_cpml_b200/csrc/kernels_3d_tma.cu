@@ -257,6 +257,7 @@ k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMa
 {
     using G = TileGeom<TX, TY>;
     constexpr int W = G::W;
+    constexpr bool EARLY_RELEASE = (TX / 2 * TY) < 512;             // see release_and_refill below
     constexpr int NBYTES = 2 * G::HALO_BYTES;                       // ring N stage: vx, vy
     constexpr int CBYTES = G::HALO_BYTES + 6 * G::PLAIN_BYTES;      // ring C stage: vz, 6 sigma
     constexpr uint32_t TX_N = 2 * G::HALO_BOX_BYTES;
@@ -405,6 +406,26 @@ k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMa
             const double2 sxx = lds2(Ts, 0 * PD + oc), syy = lds2(Ts, 1 * PD + oc), szz = lds2(Ts, 2 * PD + oc);
             const double2 sxy = lds2(Ts, 3 * PD + oc), sxz = lds2(Ts, 4 * PD + oc), syz = lds2(Ts, 5 * PD + oc);
 
+            // Everything this plane needs from the stages rn.s / rc.s is in registers now: hand them
+            // back to the TMA unit BEFORE the arithmetic, so that the loads of the planes that reuse
+            // them are in flight during this plane's update and not only during the next one's
+            // (+2.5 % on the 104-wide tile; the 512-thread 128-wide tile has no registers to spare
+            // for it and releases after the stores, profiles/r01_v6_early_release.txt).
+            auto release_and_refill = [&]() {
+                __syncthreads();                                    // stages rn.s / rc.s are free
+                if (tid == 0) {
+                    if (n + (int)SN <= np) {
+                        const uint32_t s = rn.s, bar = barN + 8 * s;
+                        const int kk = kb + n + (int)SN;
+                        mbar_expect_tx(bar, TX_N);
+                        tma_load_3d(ringN + s * NBYTES, &tm.m[0], x0, y0, kk, bar);
+                        tma_load_3d(ringN + s * NBYTES + G::HALO_BYTES, &tm.m[1], x0 - 2, y0 - 1, kk, bar);
+                    }
+                    if (n + (int)SC < np) issue_c(rc.s, kb + n + (int)SC);
+                }
+            };
+            if (EARLY_RELEASE) release_and_refill();
+
             StressVals a{sxx.x, syy.x, szz.x, sxy.x, sxz.x, syz.x}, b{sxx.y, syy.y, szz.y, sxy.y, sxz.y, syz.y};
             if (pml) {
                 stress_point<true, KUNIT, TX>(p, Cx, 2 * tx, jc, kg, do_nA, do_xyA, do_xzA, do_yzA, ux, uy, z_pml, in_xA, in_y, in_zA,
@@ -439,17 +460,7 @@ k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMa
                 }
             }
 
-            __syncthreads();                                        // stages rn.s / rc.s are free
-            if (tid == 0) {
-                if (n + (int)SN <= np) {
-                    const uint32_t s = rn.s, bar = barN + 8 * s;
-                    const int kk = kb + n + (int)SN;
-                    mbar_expect_tx(bar, TX_N);
-                    tma_load_3d(ringN + s * NBYTES, &tm.m[0], x0, y0, kk, bar);
-                    tma_load_3d(ringN + s * NBYTES + G::HALO_BYTES, &tm.m[1], x0 - 2, y0 - 1, kk, bar);
-                }
-                if (n + (int)SC < np) issue_c(rc.s, kb + n + (int)SC);
-            }
+            if (!EARLY_RELEASE) release_and_refill();
             rn = rn1;
             rc.advance(SC);
         }
@@ -550,6 +561,7 @@ k_velocity3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ Tma
 {
     using G = TileGeom<TX, TY>;
     constexpr int W = G::W;
+    constexpr bool EARLY_RELEASE = (TX / 2 * TY) < 512;
     constexpr int NBYTES = G::PLAIN_BYTES;                          // ring N stage: szz
     constexpr int CBYTES = 5 * G::HALO_BYTES + 3 * G::PLAIN_BYTES;  // ring C stage: 5 sigma (halo), vx vy vz
     constexpr uint32_t TX_N = G::PLAIN_BOX_BYTES;
@@ -703,6 +715,20 @@ k_velocity3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ Tma
             const double2 szz_n = lds2((const double *)(gN + (size_t)rn1.s * NBYTES), oc);
             const double2 vx = lds2(Tp, 0 * PD + oc), vy = lds2(Tp, 1 * PD + oc), vz = lds2(Tp, 2 * PD + oc);
 
+            // stages rn.s / rc.s are in registers: free them before the arithmetic (see k_stress3d_tma)
+            auto release_and_refill = [&]() {
+                __syncthreads();
+                if (tid == 0) {
+                    if (n + (int)SN <= np) {
+                        const uint32_t s = rn.s, bar = barN + 8 * s;
+                        mbar_expect_tx(bar, TX_N);
+                        tma_load_3d(ringN + s * NBYTES, &tm.m[5], x0, y0, kb + n + (int)SN, bar);
+                    }
+                    if (n + (int)SC < np) issue_c(rc.s, kb + n + (int)SC);
+                }
+            };
+            if (EARLY_RELEASE) release_and_refill();
+
             VelVals a{vx.x, vy.x, vz.x}, b{vx.y, vy.y, vz.y};
             if (pml) {
                 velocity_point<true, KUNIT, TX>(p, Cx, 2 * tx, jc, k, kg, do_vxA, do_vyA, do_vzA, edgeA, eboxA, srcA, ux, uy, z_pml, in_xA, in_y, in_zA,
@@ -741,15 +767,7 @@ k_velocity3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ Tma
                 if (k == p.nzl && p.peer_hi[0]) st_stream2(p.peer_hi[0] + qp, a.vz, b.vz);      // -> right
             }
 
-            __syncthreads();
-            if (tid == 0) {
-                if (n + (int)SN <= np) {
-                    const uint32_t s = rn.s, bar = barN + 8 * s;
-                    mbar_expect_tx(bar, TX_N);
-                    tma_load_3d(ringN + s * NBYTES, &tm.m[5], x0, y0, kb + n + (int)SN, bar);
-                }
-                if (n + (int)SC < np) issue_c(rc.s, kb + n + (int)SC);
-            }
+            if (!EARLY_RELEASE) release_and_refill();
             rn = rn1;
             rc.advance(SC);
         }
