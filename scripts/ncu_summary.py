@@ -32,13 +32,18 @@ def main():
                 lines.append(f"   {k:70s} {r[idx[k]]:>18s} {units[idx[k]]}")
         stalls = []
         for h, i in idx.items():
-            if "warp_issue_stalled" in h and h.endswith("_per_warp_active.pct"):
+            if "issue_stalled_" in h and h.endswith("_per_issue_active.ratio"):
                 try:
                     stalls.append((float(r[i].replace(",", "")), h))
                 except ValueError:
                     pass
         for v, h in sorted(stalls, reverse=True)[:6]:
-            lines.append(f"   stall {h.split('warp_issue_stalled_')[1][:40]:45s} {v:8.2f} %")
+            name = h.split("issue_stalled_")[1].replace("_per_issue_active.ratio", "")
+            lines.append(f"   stall cycles per issued instruction: {name:28s} {v:8.3f}")
+        for k in ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "l1tex__throughput.avg.pct_of_peak_sustained_active",
+                  "lts__throughput.avg.pct_of_peak_sustained_elapsed"):
+            if k in idx:
+                lines.append(f"   {k:70s} {r[idx[k]]:>18s} {units[idx[k]]}")
     txt = "\n".join(lines)
     print(txt)
     if len(sys.argv) > 2:

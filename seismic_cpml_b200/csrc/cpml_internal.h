@@ -64,9 +64,9 @@ __device__ __forceinline__ double div_exact(double a, double c, double y)
     // five operations above are exact; outside, a zero keeps their result (+-0, equal in value to
     // the quotient) and everything else takes the generic division
     const unsigned u = ((unsigned)__double2hiint(a) << 1) - (0x0c9u << 21);
-    if (u >= ((0x730u - 0x0c9u) << 21)) {
-        if (a != 0.0) q = div_generic(a, c);
-    }
+    // (one predicate, no short-circuit: zero dividends -- the quiescent part of the grid -- fall
+    // straight through like ordinary ones)
+    if ((u >= ((0x730u - 0x0c9u) << 21)) & (a != 0.0)) q = div_generic(a, c);
     return q;
 }
 #endif

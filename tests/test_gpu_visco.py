@@ -136,3 +136,35 @@ def test_visco_slabs_in_one_process_match_whole_grid():
     assert np.array_equal(sx, o["sisvx"]) and np.array_equal(sy, o["sisvy"])
     for s in slabs:
         s.close()
+
+
+def test_visco_default_grid_window_equals_small_oracle():
+    """BASELINE config 5 at the reference's own size (210 x 800 x 220, NPROC = 4), 8 steps: the
+    window around the source must equal, bit for bit, the oracle run on a small grid that shares
+    the source neighbourhood -- same x-min PML, same slab interface right above the source plane.
+    Numerical domain of dependence: the fourth-order leapfrog moves information 4 cells per step,
+    so a feature the two grids do not share at distance D from the source cannot change a point at
+    distance w before step (2 D - w) / 4; the nearest one (the small grid's y-min PML, D = 35)
+    leaves w = 20 untouched for 8 steps.  Also: Dirichlet faces stay zero at full size."""
+    from seismic_cpml_b200 import programs as P
+    steps, w = 8, 20
+    p = P.Params3DVisco(NSTEP=steps)                      # defaults of 3D-visco :152-244
+    prog = P.Program3DVisco(p)
+    prog.solver.run(1, steps)
+    big = {name: prog.solver.get_field(f) for f, name in enumerate(FV) if name in ("vx", "vy", "vz", "sigmaxy", "sigmazz", "sigmayz_R")}
+    sx_big, _ = prog.solver.get_seismograms()
+    prog.solver.close()
+    assert p.ISOURCE == 30 and p.JSOURCE == 161 and p.NZ // 2 == 110
+    # small grid: source at (30, 45, 48), slab interface between planes 48 and 49 like 110 | 111
+    c = refcfg.cfgv3d(nx=80, ny=220, nz=96, npml=10, nstep=steps)
+    assert c["isource"] == 30 and c["jsource"] == 45
+    o = O.run_3d_visco(**c, nproc=2, want_fields=True)
+    for name, a in big.items():
+        wb = a[110 - 1 - w:110 + w, 161 - 1 - w:161 + w, 0:30 + w]
+        ws = o[name][48 - 1 - w:48 + w, 45 - 1 - w:45 + w, 0:30 + w]
+        assert np.abs(ws).max() > 0, name
+        assert np.array_equal(wb, ws), (name, np.abs(wb - ws).max())
+    for a in (big["vx"], big["vy"], big["vz"]):           # Dirichlet, two planes per face (:1337-1371)
+        assert not a[:, :, :1].any() and not a[:, :, -1:].any() and not a[:, :1, :].any() and not a[:, -1:, :].any()
+        assert not a[:1].any() and not a[-1:].any()
+    assert np.isfinite(sx_big).all()
