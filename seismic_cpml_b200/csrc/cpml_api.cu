@@ -82,6 +82,7 @@ struct cpml_handle {
     // 2-D material
     double *mat[3] = {};       // lambda, mu, rho allocations (same layout as fields)
     bool have_material = false;
+    bool rho_exact = true;     // no density / interpolated density with an all-ones significand
 
     // source / receivers / traces
     double *d_src_x = nullptr, *d_src_y = nullptr;
@@ -473,6 +474,15 @@ extern "C" int32_t cpml_set_material_2d(cpml_handle *h, const double *lambda, co
     if (c.ndim != 2) FAIL(CPML_EINVAL, "cpml_set_material_2d is for the 2-D solvers");
     if (!lambda || !mu || !rho) FAIL(CPML_EINVAL, "null material array");
     CK(cudaSetDevice(h->device));
+    // div_rho (kernels_2d.cu) needs divisors whose significand is not all ones: rho(i,j) and the
+    // interpolated rho_half_x_half_y of 2D-2nd :627, evaluated here exactly as the kernels do
+    h->rho_exact = true;
+    for (int j = 1; j <= c.ny && h->rho_exact; j++)
+        for (int i = 1; i <= c.nx; i++) {
+            auto R = [&](int ii, int jj) { return (ii <= c.nx && jj <= c.ny) ? rho[(size_t)(jj - 1) * c.nx + (ii - 1)] : 0.0; };
+            const double r0 = R(i, j), rh = 0.25 * (r0 + R(i + 1, j) + R(i + 1, j + 1) + R(i, j + 1));
+            if (all_ones_significand(r0) || all_ones_significand(rh) || !(r0 > 0.0)) { h->rho_exact = false; break; }
+        }
     const double *src[3] = {lambda, mu, rho};
     for (int m = 0; m < 3; m++) {
         CK(cudaMemset(h->mat[m], 0, h->field_doubles * sizeof(double)));
@@ -845,6 +855,7 @@ static Params2D make_p2(cpml_handle *h, int it)
     p.nx = c.nx; p.ny = c.ny; p.pitch = h->pitch; p.order = c.order;
     p.vx = h->f0[0]; p.vy = h->f0[1]; p.sxx = h->f0[2]; p.syy = h->f0[3]; p.sxy = h->f0[4];
     p.lambda = h->mat[0] + h->origin; p.mu = h->mat[1] + h->origin; p.rho = h->mat[2] + h->origin;
+    p.rho_exact = h->rho_exact ? 1 : 0;
     p.xlo = h->shell[0].lo; p.xhi = h->shell[0].hi; p.sxp = h->sxp;
     p.ylo = h->shell[1].lo; p.yhi = h->shell[1].hi; p.sy = h->sy;
     for (int m = 0; m < 4; m++) { p.mx[m] = h->mx[m]; p.my[m] = h->my[m]; }

@@ -188,6 +188,7 @@ struct Params2D {
     int order;                // 2 or 4
     double *vx, *vy, *sxx, *syy, *sxy;       // pointer to element (i=1, j=1)
     const double *lambda, *mu, *rho;         // same layout, zero ghost ring
+    int rho_exact;                           // 1: no density has an all-ones significand (div_rho)
     int xlo, xhi, sxp;
     int ylo, yhi, sy;
     double *mx[4], *my[4];

@@ -88,6 +88,16 @@ k_stress2d(const __grid_constant__ Params2D p)
     }
 }
 
+// a / rho for a density read from the material arrays: the correctly rounded reciprocal comes from
+// __drcp_rn (IEEE round-to-nearest), then div_exact -- the correctly rounded quotient in about half
+// the instructions of the generic division.  `exact_ok` is 0 when cpml_set_material_2d found a
+// density (or an interpolated density) with an all-ones significand, the one case Markstein's
+// theorem excludes; the generic division runs then.
+__device__ __forceinline__ double div_rho(double a, double rho, int exact_ok)
+{
+    return exact_ok ? div_exact(a, rho, __drcp_rn(rho)) : a / rho;
+}
+
 template <int NT>
 __device__ __forceinline__ void block_sum2_2d(double &a, double &b, double *smem)
 {
@@ -137,14 +147,14 @@ k_velocity2d(const __grid_constant__ Params2D p)
             double value_dsigmaxy_dy = d_bwd<ORDER>(p.sxy, q, pitch, p.deny, p.rdeny);
             if (in_x) value_dsigmaxx_dx = cpml_apply2(p.mx[2], qx, p.cx.b[i], p.cx.a[i], p.cx.K[i], p.cx.rK[i], value_dsigmaxx_dx);
             if (in_y) value_dsigmaxy_dy = cpml_apply2(p.my[2], qy, p.cy.b[j], p.cy.a[j], p.cy.K[j], p.cy.rK[j], value_dsigmaxy_dy);
-            vx = vx + (value_dsigmaxx_dx + value_dsigmaxy_dy) * DELTAT / rho;
+            vx = vx + div_rho((value_dsigmaxx_dx + value_dsigmaxy_dy) * DELTAT, rho, p.rho_exact);
         }
         if (i <= p.nx - 1 && j <= p.ny - 1) {
             double value_dsigmaxy_dx = d_fwd<ORDER>(p.sxy, q, 1, p.denx, p.rdenx);
             double value_dsigmayy_dy = d_fwd<ORDER>(p.syy, q, pitch, p.deny, p.rdeny);
             if (in_x) value_dsigmaxy_dx = cpml_apply2(p.mx[3], qx, p.cx.b_half[i], p.cx.a_half[i], p.cx.K_half[i], p.cx.rK_half[i], value_dsigmaxy_dx);
             if (in_y) value_dsigmayy_dy = cpml_apply2(p.my[3], qy, p.cy.b_half[j], p.cy.a_half[j], p.cy.K_half[j], p.cy.rK_half[j], value_dsigmayy_dy);
-            vy = vy + (value_dsigmaxy_dx + value_dsigmayy_dy) * DELTAT / rho_half_x_half_y;
+            vy = vy + div_rho((value_dsigmaxy_dx + value_dsigmayy_dy) * DELTAT, rho_half_x_half_y, p.rho_exact);
         }
         if (i == p.isrc && j == p.jsrc) {               // 2D-2nd :663-667
             vx = vx + p.force_x[p.it - 1] * DELTAT / rho;
@@ -164,7 +174,7 @@ k_velocity2d(const __grid_constant__ Params2D p)
             ekin = 0.5 * (rho * (vx * vx + vy * vy));
             // one division for both 1/(4 mu (lambda + mu)) and 1/(2 mu): the energy is a sum whose
             // order differs from the reference's anyway (tolerance 1e-11, not bitwise)
-            const double inv4 = 1.0 / (4.0 * m * (l + m));
+            const double inv4 = __drcp_rn(4.0 * m * (l + m));
             const double epsilon_xx = ((l + 2.0 * m) * sxx - l * syy) * inv4;
             const double epsilon_yy = ((l + 2.0 * m) * syy - l * sxx) * inv4;
             const double epsilon_xy = sxy * (inv4 * (2.0 * (l + m)));

@@ -13,9 +13,9 @@
 // register the new one is computed from and each memory variable is one array, read and written
 // once per step (18 words per point instead of 36 + the copy's 36).
 // These programs multiply by precomputed 9/(8 DELTAX) and 1/(24 DELTAX) (:210-213) instead of
-// dividing, so the operator has no division; /K (C-PML) goes through div_exact, /rho stays a
-// division.  Compiled with -fmad=false: fields and memory variables are bit-identical to an
-// IEEE (non-FMA) build of the reference.
+// dividing, so the operator has no division; /K (C-PML) and /rho go through div_exact.  Compiled
+// with -fmad=false: fields and memory variables are bit-identical to an IEEE (non-FMA) build of
+// the reference.
 #include "cpml_internal.h"
 
 namespace cpml {
@@ -26,6 +26,12 @@ __device__ __forceinline__ double vapply2(double *__restrict__ mem, long long q,
     m = b * m + a * value;
     mem[q] = m;
     return div_exact(value, K, rK) + m;
+}
+
+// a / rho through the correctly rounded reciprocal (see div_rho in kernels_2d.cu)
+__device__ __forceinline__ double vdiv_rho(double a, double rho, int exact_ok)
+{
+    return exact_ok ? div_exact(a, rho, __drcp_rn(rho)) : a / rho;
 }
 
 __device__ __forceinline__ int vshell2(int i, int lo, int hi) { return i <= lo ? i - 1 : lo + (i - hi); }
@@ -127,14 +133,14 @@ k_vvelocity2d(const __grid_constant__ Params2D p)
         double value_dsigma_xy_dy = vd_bwd<ORDER>(p.sxy, q, pitch, p.c98y, p.c24y);
         if (in_x) value_dsigma_xx_dx = vapply2(p.mx[2], qx, p.cx.b[i], p.cx.a[i], p.cx.K[i], p.cx.rK[i], value_dsigma_xx_dx);
         if (in_y) value_dsigma_xy_dy = vapply2(p.my[2], qy, p.cy.b[j], p.cy.a[j], p.cy.K[j], p.cy.rK[j], value_dsigma_xy_dy);
-        vx = vx + (value_dsigma_xx_dx + value_dsigma_xy_dy) * DELTAT / rho;
+        vx = vx + vdiv_rho((value_dsigma_xx_dx + value_dsigma_xy_dy) * DELTAT, rho, p.rho_exact);
     }
     if (i <= p.nx - 1 && j <= p.ny - 1) {                           // :898-925
         double value_dsigma_xy_dx = vd_fwd<ORDER>(p.sxy, q, 1, p.c98x, p.c24x);
         double value_dsigma_yy_dy = vd_fwd<ORDER>(p.syy, q, pitch, p.c98y, p.c24y);
         if (in_x) value_dsigma_xy_dx = vapply2(p.mx[3], qx, p.cx.b_half[i], p.cx.a_half[i], p.cx.K_half[i], p.cx.rK_half[i], value_dsigma_xy_dx);
         if (in_y) value_dsigma_yy_dy = vapply2(p.my[3], qy, p.cy.b_half[j], p.cy.a_half[j], p.cy.K_half[j], p.cy.rK_half[j], value_dsigma_yy_dy);
-        vy = vy + (value_dsigma_xy_dx + value_dsigma_yy_dy) * DELTAT / rho_half_x_half_y;
+        vy = vy + vdiv_rho((value_dsigma_xy_dx + value_dsigma_yy_dy) * DELTAT, rho_half_x_half_y, p.rho_exact);
     }
     if (i == p.isrc && j == p.jsrc) {                               // :971-972
         vx = vx + p.force_x[p.it - 1] * DELTAT / rho;
