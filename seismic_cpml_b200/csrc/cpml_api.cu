@@ -416,7 +416,9 @@ extern "C" int32_t cpml_reset(cpml_handle *h)
     CK(cudaMemsetAsync(h->d_sisvx, 0, ns * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->d_sisvy, 0, ns * sizeof(double), h->stream));
     if (h->d_sisp) CK(cudaMemsetAsync(h->d_sisp, 0, ns * sizeof(double), h->stream));
-    if (h->visco2d && h->d_partials) CK(cudaMemsetAsync(h->d_partials, 0, 2 * (size_t)h->nblocks * sizeof(double), h->stream));
+    // 2-D: the paired kernels write fewer partial slots than the one-point geometry allocates, and the
+    // 2-D viscoelastic kernels none unless compute_energy is set: the unused slots must read zero
+    if (c.ndim == 2 && h->d_partials) CK(cudaMemsetAsync(h->d_partials, 0, 2 * (size_t)h->nblocks * sizeof(double), h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return CPML_OK;
 }

@@ -189,9 +189,229 @@ k_velocity2d(const __grid_constant__ Params2D p)
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Paired kernels (default): one thread updates the two x-adjacent points A = (i, j), B = (i+1, j),
+// i odd, so that every row access is one aligned 16-byte load or store (the x taps of both points
+// come from three of them) and the address, predicate and loop-bound instructions are shared --
+// the one-point kernels above spend more instructions on those than on arithmetic (ncu: 268 / 566
+// instructions per point, profiles/r01_v6_ncu_cfg2.txt).  The arithmetic of a point is written
+// once (stress_point2 / velocity_point2) and is the same sequence of operations as above.
+// ---------------------------------------------------------------------------------------
+
+__device__ __forceinline__ double2 ld2(const double *f, long long q) { return *reinterpret_cast<const double2 *>(f + q); }
+__device__ __forceinline__ void st2(double *f, long long q, double a, double b) { *reinterpret_cast<double2 *>(f + q) = make_double2(a, b); }
+
+// difference of a four-tap (ORDER 4) or two-tap (ORDER 2) stencil: 27 a - 27 b - c + d over den
+template <int ORDER>
+__device__ __forceinline__ double diff2(double a, double b, double c, double d, double den, double rden)
+{
+    if (ORDER == 2) return div_exact(a - b, den, rden);
+    return div_exact(27.0 * a - 27.0 * b - c + d, den, rden);
+}
+
+template <int ORDER>
+__device__ __forceinline__ void stress_point2(const Params2D &p, int i, int j, bool in_x, bool in_y, long long qx, long long qy,
+                                              double lam_c, double lam_ip, double mu_c, double mu_ip, double mu_jp,
+                                              // vx: i+1, i, i+2, i-1 on row j; j+1, j+2, j-1 at column i
+                                              double vx_ip, double vx_c, double vx_ipp, double vx_im, double vx_jp, double vx_jpp, double vx_jm,
+                                              // vy: i-1, i+1, i-2 on row j; j-1, j+1, j-2 at column i
+                                              double vy_c, double vy_im, double vy_ip, double vy_imm, double vy_jm, double vy_jp, double vy_jmm,
+                                              double &sxx, double &syy, double &sxy)
+{
+    const double DELTAT = p.deltat;
+    if (i <= p.nx - 1 && j >= 2) {
+        const double lambda_half_x = 0.5 * (lam_ip + lam_c);
+        const double mu_half_x = 0.5 * (mu_ip + mu_c);
+        const double lambda_plus_two_mu_half_x = lambda_half_x + 2.0 * mu_half_x;
+        double value_dvx_dx = diff2<ORDER>(vx_ip, vx_c, vx_ipp, vx_im, p.denx, p.rdenx);
+        double value_dvy_dy = diff2<ORDER>(vy_c, vy_jm, vy_jp, vy_jmm, p.deny, p.rdeny);
+        if (in_x) value_dvx_dx = cpml_apply2(p.mx[0], qx, p.cx.b_half[i], p.cx.a_half[i], p.cx.K_half[i], p.cx.rK_half[i], value_dvx_dx);
+        if (in_y) value_dvy_dy = cpml_apply2(p.my[0], qy, p.cy.b[j], p.cy.a[j], p.cy.K[j], p.cy.rK[j], value_dvy_dy);
+        sxx = sxx + (lambda_plus_two_mu_half_x * value_dvx_dx + lambda_half_x * value_dvy_dy) * DELTAT;
+        syy = syy + (lambda_half_x * value_dvx_dx + lambda_plus_two_mu_half_x * value_dvy_dy) * DELTAT;
+    }
+    if (i >= 2 && j <= p.ny - 1) {
+        const double mu_half_y = 0.5 * (mu_jp + mu_c);
+        double value_dvy_dx = diff2<ORDER>(vy_c, vy_im, vy_ip, vy_imm, p.denx, p.rdenx);
+        double value_dvx_dy = diff2<ORDER>(vx_jp, vx_c, vx_jpp, vx_jm, p.deny, p.rdeny);
+        if (in_x) value_dvy_dx = cpml_apply2(p.mx[1], qx, p.cx.b[i], p.cx.a[i], p.cx.K[i], p.cx.rK[i], value_dvy_dx);
+        // quirk B3, see k_stress2d
+        if (in_y) value_dvx_dy = cpml_apply2(p.my[1], qy, p.cy.b_half[j], p.cy.a_half[j],
+                                             ORDER == 4 ? p.cy.K[j] : p.cy.K_half[j],
+                                             ORDER == 4 ? p.cy.rK[j] : p.cy.rK_half[j], value_dvx_dy);
+        sxy = sxy + mu_half_y * (value_dvy_dx + value_dvx_dy) * DELTAT;
+    }
+}
+
+template <int ORDER, int TX, int TY, int MINB>
+__global__ void __launch_bounds__(TX *TY, MINB)
+k_stress2d_pair(const __grid_constant__ Params2D p)
+{
+    const int i = 2 * (blockIdx.x * TX + threadIdx.x) + 1;            // A; B = i + 1
+    const int j = blockIdx.y * TY + threadIdx.y + 1;
+    if (i > p.nx || j > p.ny) return;
+    const bool validB = i + 1 <= p.nx;
+    const int pitch = p.pitch;
+    const long long q = (long long)(j - 1) * pitch + (i - 1);           // even: 16-byte aligned
+    const bool in_y = (j <= p.ylo) || (j >= p.yhi);
+    const bool in_xA = (i <= p.xlo) || (i >= p.xhi), in_xB = validB && ((i + 1 <= p.xlo) || (i + 1 >= p.xhi));
+    const long long qxA = in_xA ? (long long)(j - 1) * p.sxp + shell_index2(i, p.xlo, p.xhi) : 0;
+    const long long qxB = in_xB ? (long long)(j - 1) * p.sxp + shell_index2(i + 1, p.xlo, p.xhi) : 0;
+    const long long qy = in_y ? (long long)shell_index2(j, p.ylo, p.yhi) * pitch + (i - 1) : 0;
+
+    const double2 lam_c = ld2(p.lambda, q), mu_c = ld2(p.mu, q), mu_jp = ld2(p.mu, q + pitch);
+    const double lam_r = p.lambda[q + 2], mu_r = p.mu[q + 2];
+    const double2 vx_c = ld2(p.vx, q), vx_r = ld2(p.vx, q + 2), vx_jp = ld2(p.vx, q + pitch);
+    const double2 vy_c = ld2(p.vy, q), vy_l = ld2(p.vy, q - 2), vy_jm = ld2(p.vy, q - pitch);
+    double2 vx_l = make_double2(0.0, 0.0), vx_jpp = vx_l, vx_jm = vx_l, vy_jp = vx_l, vy_jmm = vx_l;
+    double vy_r = 0.0;
+    if (ORDER == 4) {
+        vx_l = ld2(p.vx, q - 2); vx_jpp = ld2(p.vx, q + 2 * pitch); vx_jm = ld2(p.vx, q - pitch);
+        vy_jp = ld2(p.vy, q + pitch); vy_jmm = ld2(p.vy, q - 2 * pitch); vy_r = p.vy[q + 2];
+    }
+    double2 sxx = ld2(p.sxx, q), syy = ld2(p.syy, q), sxy = ld2(p.sxy, q);
+
+    stress_point2<ORDER>(p, i, j, in_xA, in_y, qxA, qy, lam_c.x, lam_c.y, mu_c.x, mu_c.y, mu_jp.x,
+                         vx_c.y, vx_c.x, vx_r.x, vx_l.y, vx_jp.x, vx_jpp.x, vx_jm.x,
+                         vy_c.x, vy_l.y, vy_c.y, vy_l.x, vy_jm.x, vy_jp.x, vy_jmm.x, sxx.x, syy.x, sxy.x);
+    if (validB)
+        stress_point2<ORDER>(p, i + 1, j, in_xB, in_y, qxB, qy + 1, lam_c.y, lam_r, mu_c.y, mu_r, mu_jp.y,
+                             vx_r.x, vx_c.y, vx_r.y, vx_c.x, vx_jp.y, vx_jpp.y, vx_jm.y,
+                             vy_c.y, vy_c.x, vy_r, vy_l.y, vy_jm.y, vy_jp.y, vy_jmm.y, sxx.y, syy.y, sxy.y);
+    st2(p.sxx, q, sxx.x, sxx.y);
+    st2(p.syy, q, syy.x, syy.y);
+    st2(p.sxy, q, sxy.x, sxy.y);
+}
+
+template <int ORDER>
+__device__ __forceinline__ void velocity_point2(const Params2D &p, int i, int j, bool in_x, bool in_y, long long qx, long long qy,
+                                                double rho, double rho_half_x_half_y, double lam, double mu,
+                                                // sxx: i, i-1, i+1, i-2 ; sxy: (j, j-1, j+1, j-2) and (i+1, i, i+2, i-1) ; syy: j+1, j, j+2, j-1
+                                                double sxx_c, double sxx_im, double sxx_ip, double sxx_imm,
+                                                double sxy_c, double sxy_jm, double sxy_jp, double sxy_jmm,
+                                                double sxy_ip, double sxy_ipp, double sxy_im,
+                                                double syy_c, double syy_jp, double syy_jpp, double syy_jm,
+                                                double &vx, double &vy, double &ekin, double &epot)
+{
+    const double DELTAT = p.deltat;
+    if (i >= 2 && j >= 2) {
+        double value_dsigmaxx_dx = diff2<ORDER>(sxx_c, sxx_im, sxx_ip, sxx_imm, p.denx, p.rdenx);
+        double value_dsigmaxy_dy = diff2<ORDER>(sxy_c, sxy_jm, sxy_jp, sxy_jmm, p.deny, p.rdeny);
+        if (in_x) value_dsigmaxx_dx = cpml_apply2(p.mx[2], qx, p.cx.b[i], p.cx.a[i], p.cx.K[i], p.cx.rK[i], value_dsigmaxx_dx);
+        if (in_y) value_dsigmaxy_dy = cpml_apply2(p.my[2], qy, p.cy.b[j], p.cy.a[j], p.cy.K[j], p.cy.rK[j], value_dsigmaxy_dy);
+        vx = vx + div_rho((value_dsigmaxx_dx + value_dsigmaxy_dy) * DELTAT, rho, p.rho_exact);
+    }
+    if (i <= p.nx - 1 && j <= p.ny - 1) {
+        double value_dsigmaxy_dx = diff2<ORDER>(sxy_ip, sxy_c, sxy_ipp, sxy_im, p.denx, p.rdenx);
+        double value_dsigmayy_dy = diff2<ORDER>(syy_jp, syy_c, syy_jpp, syy_jm, p.deny, p.rdeny);
+        if (in_x) value_dsigmaxy_dx = cpml_apply2(p.mx[3], qx, p.cx.b_half[i], p.cx.a_half[i], p.cx.K_half[i], p.cx.rK_half[i], value_dsigmaxy_dx);
+        if (in_y) value_dsigmayy_dy = cpml_apply2(p.my[3], qy, p.cy.b_half[j], p.cy.a_half[j], p.cy.K_half[j], p.cy.rK_half[j], value_dsigmayy_dy);
+        vy = vy + div_rho((value_dsigmaxy_dx + value_dsigmayy_dy) * DELTAT, rho_half_x_half_y, p.rho_exact);
+    }
+    if (i == p.isrc && j == p.jsrc) {               // 2D-2nd :663-667
+        vx = vx + p.force_x[p.it - 1] * DELTAT / rho;
+        vy = vy + p.force_y[p.it - 1] * DELTAT / rho_half_x_half_y;
+    }
+    if (i == 1 || i == p.nx || j == 1 || j == p.ny) { vx = 0.0; vy = 0.0; }   // :669-680
+
+    const int e0 = ORDER == 4 ? p.npml : p.npml + 1;
+    const int ex1 = ORDER == 4 ? p.nx - p.npml + 1 : p.nx - p.npml;
+    const int ey1 = ORDER == 4 ? p.ny - p.npml + 1 : p.ny - p.npml;
+    if (i >= e0 && i <= ex1 && j >= e0 && j <= ey1) {
+        ekin += 0.5 * (rho * (vx * vx + vy * vy));
+        const double inv4 = __drcp_rn(4.0 * mu * (lam + mu));
+        const double epsilon_xx = ((lam + 2.0 * mu) * sxx_c - lam * syy_c) * inv4;
+        const double epsilon_yy = ((lam + 2.0 * mu) * syy_c - lam * sxx_c) * inv4;
+        const double epsilon_xy = sxy_c * (inv4 * (2.0 * (lam + mu)));
+        epot += 0.5 * (epsilon_xx * sxx_c + epsilon_yy * syy_c + 2.0 * epsilon_xy * sxy_c);
+    }
+}
+
+template <int ORDER, int TX, int TY, int MINB>
+__global__ void __launch_bounds__(TX *TY, MINB)
+k_velocity2d_pair(const __grid_constant__ Params2D p)
+{
+    __shared__ double red[2 * TX * TY / 32];
+    const int i = 2 * (blockIdx.x * TX + threadIdx.x) + 1;
+    const int j = blockIdx.y * TY + threadIdx.y + 1;
+    double ekin = 0.0, epot = 0.0;
+
+    if (i <= p.nx && j <= p.ny) {
+        const bool validB = i + 1 <= p.nx;
+        const int pitch = p.pitch;
+        const long long q = (long long)(j - 1) * pitch + (i - 1);
+        const bool in_y = (j <= p.ylo) || (j >= p.yhi);
+        const bool in_xA = (i <= p.xlo) || (i >= p.xhi), in_xB = validB && ((i + 1 <= p.xlo) || (i + 1 >= p.xhi));
+        const long long qxA = in_xA ? (long long)(j - 1) * p.sxp + shell_index2(i, p.xlo, p.xhi) : 0;
+        const long long qxB = in_xB ? (long long)(j - 1) * p.sxp + shell_index2(i + 1, p.xlo, p.xhi) : 0;
+        const long long qy = in_y ? (long long)shell_index2(j, p.ylo, p.yhi) * pitch + (i - 1) : 0;
+
+        const double2 rho_c = ld2(p.rho, q), rho_jp = ld2(p.rho, q + pitch);
+        const double rho_r = p.rho[q + 2], rho_jpr = p.rho[q + pitch + 2];
+        const double rhoA = rho_c.x, rhoB = rho_c.y;
+        const double rho_hA = 0.25 * (rho_c.x + rho_c.y + rho_jp.y + rho_jp.x);          // 2D-2nd :627
+        const double rho_hB = 0.25 * (rho_c.y + rho_r + rho_jpr + rho_jp.y);
+        const double2 lam = ld2(p.lambda, q), mu = ld2(p.mu, q);
+        const double2 sxx_c = ld2(p.sxx, q), sxx_l = ld2(p.sxx, q - 2);
+        const double2 sxy_c = ld2(p.sxy, q), sxy_r = ld2(p.sxy, q + 2), sxy_jm = ld2(p.sxy, q - pitch);
+        const double2 syy_c = ld2(p.syy, q), syy_jp = ld2(p.syy, q + pitch);
+        double2 z2 = make_double2(0.0, 0.0), sxy_l = z2, sxy_jp = z2, sxy_jmm = z2, syy_jpp = z2, syy_jm = z2;
+        double sxx_r = 0.0;
+        if (ORDER == 4) {
+            sxx_r = p.sxx[q + 2]; sxy_l = ld2(p.sxy, q - 2); sxy_jp = ld2(p.sxy, q + pitch); sxy_jmm = ld2(p.sxy, q - 2 * pitch);
+            syy_jpp = ld2(p.syy, q + 2 * pitch); syy_jm = ld2(p.syy, q - pitch);
+        }
+        double2 v_x = ld2(p.vx, q), v_y = ld2(p.vy, q);
+
+        velocity_point2<ORDER>(p, i, j, in_xA, in_y, qxA, qy, rhoA, rho_hA, lam.x, mu.x,
+                               sxx_c.x, sxx_l.y, sxx_c.y, sxx_l.x,
+                               sxy_c.x, sxy_jm.x, sxy_jp.x, sxy_jmm.x, sxy_c.y, sxy_r.x, sxy_l.y,
+                               syy_c.x, syy_jp.x, syy_jpp.x, syy_jm.x, v_x.x, v_y.x, ekin, epot);
+        if (validB)
+            velocity_point2<ORDER>(p, i + 1, j, in_xB, in_y, qxB, qy + 1, rhoB, rho_hB, lam.y, mu.y,
+                                   sxx_c.y, sxx_c.x, sxx_r, sxx_l.y,
+                                   sxy_c.y, sxy_jm.y, sxy_jp.y, sxy_jmm.y, sxy_r.x, sxy_r.y, sxy_c.x,
+                                   syy_c.y, syy_jp.y, syy_jpp.y, syy_jm.y, v_x.y, v_y.y, ekin, epot);
+        st2(p.vx, q, v_x.x, v_x.y);
+        st2(p.vy, q, v_y.x, v_y.y);
+    }
+    block_sum2_2d<TX * TY>(ekin, epot, red);
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        const int b = blockIdx.y * gridDim.x + blockIdx.x;
+        p.partials[b] = ekin;
+        p.partials[p.nblocks + b] = epot;
+    }
+}
+
+static int pair_mode()
+{
+    static int mode = -1;
+    if (mode < 0) { const char *e = getenv("CPML_2D_PAIR"); mode = (e && *e == '0') ? 0 : 1; }
+    return mode;
+}
+
+static int pair_minb()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("CPML_2D_MINB"); v = e ? atoi(e) : 2; }
+    return v;
+}
+
+// `grid` is the one-point geometry (32 x 8 points per block); the paired kernels cover 64 x 8.
 void launch_stress2d(const Params2D &p, dim3 grid, dim3 block, cudaStream_t s)
 {
     (void)block;
+    if (pair_mode()) {
+        const dim3 g((p.nx + 63) / 64, grid.y);
+        if (pair_minb() >= 3) {
+            if (p.order == 4) k_stress2d_pair<4, 32, 8, 3><<<g, dim3(32, 8), 0, s>>>(p);
+            else              k_stress2d_pair<2, 32, 8, 3><<<g, dim3(32, 8), 0, s>>>(p);
+        } else {
+            if (p.order == 4) k_stress2d_pair<4, 32, 8, 2><<<g, dim3(32, 8), 0, s>>>(p);
+            else              k_stress2d_pair<2, 32, 8, 2><<<g, dim3(32, 8), 0, s>>>(p);
+        }
+        return;
+    }
     if (p.order == 4) k_stress2d<4, 32, 8><<<grid, dim3(32, 8), 0, s>>>(p);
     else              k_stress2d<2, 32, 8><<<grid, dim3(32, 8), 0, s>>>(p);
 }
@@ -199,6 +419,17 @@ void launch_stress2d(const Params2D &p, dim3 grid, dim3 block, cudaStream_t s)
 void launch_velocity2d(const Params2D &p, dim3 grid, dim3 block, cudaStream_t s)
 {
     (void)block;
+    if (pair_mode()) {
+        const dim3 g((p.nx + 63) / 64, grid.y);
+        if (pair_minb() >= 3) {
+            if (p.order == 4) k_velocity2d_pair<4, 32, 8, 3><<<g, dim3(32, 8), 0, s>>>(p);
+            else              k_velocity2d_pair<2, 32, 8, 3><<<g, dim3(32, 8), 0, s>>>(p);
+        } else {
+            if (p.order == 4) k_velocity2d_pair<4, 32, 8, 2><<<g, dim3(32, 8), 0, s>>>(p);
+            else              k_velocity2d_pair<2, 32, 8, 2><<<g, dim3(32, 8), 0, s>>>(p);
+        }
+        return;
+    }
     if (p.order == 4) k_velocity2d<4, 32, 8><<<grid, dim3(32, 8), 0, s>>>(p);
     else              k_velocity2d<2, 32, 8><<<grid, dim3(32, 8), 0, s>>>(p);
 }
