@@ -367,6 +367,26 @@ module cpml_b200
       real(c_double) :: c
     end function
 
+    ! compute_attenuation_coeffs of attenuation_model_with_SolvOpt.f90 :122-169
+    function cpml_host_attenuation_fit(n_sls, qref, f0, f_min, f_max, tau_epsilon, tau_sigma, info) &
+        bind(C, name='cpml_host_attenuation_fit') result(ierr)
+      import :: c_int32_t, c_double
+      integer(c_int32_t), value :: n_sls
+      real(c_double), value :: qref, f0, f_min, f_max
+      real(c_double), intent(out) :: tau_epsilon(*), tau_sigma(*)
+      real(c_double), intent(out) :: info(4)
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_host_attenuation_fit_linear(n_sls, qref, f_min, f_max, tau_epsilon, tau_sigma) &
+        bind(C, name='cpml_host_attenuation_fit_linear') result(ierr)
+      import :: c_int32_t, c_double
+      integer(c_int32_t), value :: n_sls
+      real(c_double), value :: qref, f_min, f_max
+      real(c_double), intent(out) :: tau_epsilon(*), tau_sigma(*)
+      integer(c_int32_t) :: ierr
+    end function
+
     function cpml_host_write_seismograms(dir, sisvx, sisvy, nt, nrec, deltat) &
         bind(C, name='cpml_host_write_seismograms') result(ierr)
       import :: c_int32_t, c_double, c_char

@@ -308,6 +308,20 @@ int32_t cpml_host_find_receivers_at(int32_t nx, int32_t ny, double deltax, doubl
                                     int32_t index_origin, int32_t *ix_rec, int32_t *iy_rec,
                                     double *dist);
 
+/* Relaxation times of N_SLS standard linear solids for a constant quality factor Qref around f0:
+ * compute_attenuation_coeffs of attenuation_model_with_SolvOpt.f90 :122-169 (classical linear
+ * least squares :446-485 as first guess, then SolvOpt :489-1751 on the misfit :1798-1824 under the
+ * constraint :1883-1904).  The viscoelastic programs call it once for Qp and once for Qs with
+ * f_min = exp(log(f0) - log(12)/2), f_max = 12 f_min (2D-visco-4th :366-376).
+ * info (optional, 4 doubles): SolvOpt's options(9) (iterations, or a negative stop code), final
+ * misfit, function and gradient evaluations. */
+int32_t cpml_host_attenuation_fit(int32_t n_sls, double qref, double f0, double f_min,
+                                  double f_max, double *tau_epsilon, double *tau_sigma,
+                                  double *info);
+/* The linear first guess alone (classical_linear_least_squares :446-485). */
+int32_t cpml_host_attenuation_fit_linear(int32_t n_sls, double qref, double f_min, double f_max,
+                                         double *tau_epsilon, double *tau_sigma);
+
 /* Courant number of :712 (deltaz <= 0 => 2-D form of 2D-2nd :513). */
 double cpml_host_courant(double cp, double deltat, double deltax, double deltay, double deltaz);
 

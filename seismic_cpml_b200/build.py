@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["cpml_api.cu", "kernels_3d.cu", "kernels_3d_tma.cu", "kernels_3d_visco.cu", "kernels_2d.cu", "kernels_2d_visco.cu", "cpml_host.cpp"]
+SOURCES = ["cpml_api.cu", "kernels_3d.cu", "kernels_3d_tma.cu", "kernels_3d_visco.cu", "kernels_2d.cu", "kernels_2d_visco.cu", "cpml_host.cpp", "attenuation_fit.cpp"]
 HEADERS = [os.path.join(CSRC, "cpml_internal.h"),
            os.path.join(HERE, "..", "include", "cpml_b200.h")]
 LIB = os.path.join(HERE, "libcpml_b200.so")

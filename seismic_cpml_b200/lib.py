@@ -100,6 +100,8 @@ SYMBOLS = {
     "cpml_host_find_receivers": (C.c_int32, [C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32,
                                              C.c_double, C.c_double, C.c_double, C.c_double, _ip, _ip, _dp]),
     "cpml_host_courant": (C.c_double, [C.c_double] * 5),
+    "cpml_host_attenuation_fit": (C.c_int32, [C.c_int32] + [C.c_double] * 4 + [_dp, _dp, _dp]),
+    "cpml_host_attenuation_fit_linear": (C.c_int32, [C.c_int32] + [C.c_double] * 3 + [_dp, _dp]),
     "cpml_host_write_seismograms": (C.c_int32, [C.c_char_p, _dp, _dp, C.c_int32, C.c_int32, C.c_double]),
     "cpml_host_write_energy_3d": (C.c_int32, [C.c_char_p, _dp, C.c_int32, C.c_double]),
     "cpml_host_write_energy_2d": (C.c_int32, [C.c_char_p, _dp, _dp, C.c_int32, C.c_double]),
@@ -200,6 +202,32 @@ def host_find_receivers(nx, ny, deltax, deltay, nrec, xdeb, ydeb, xfin, yfin):
 
 def host_courant(cp, deltat, deltax, deltay, deltaz=0.0):
     return load().cpml_host_courant(cp, deltat, deltax, deltay, deltaz)
+
+
+def host_attenuation_band(f0):
+    """f_min, f_max of the fit: f_max / f_min = 12 centred (in log) on f0 (2D-visco-4th :366-368,
+    3D-visco :434-435)."""
+    import math
+    f_min = math.exp(math.log(f0) - math.log(12.0) / 2.0)
+    return f_min, 12.0 * f_min
+
+
+def host_attenuation_fit(n_sls, qref, f0, f_min=None, f_max=None, *, linear_only=False, return_info=False):
+    """compute_attenuation_coeffs(N, Qref, f0, f_min, f_max, tau_epsilon, tau_sigma) of
+    attenuation_model_with_SolvOpt.f90:122-169 -> (tau_epsilon, tau_sigma) tuples."""
+    if f_min is None or f_max is None:
+        f_min, f_max = host_attenuation_band(f0)
+    te = np.zeros(n_sls)
+    ts = np.zeros(n_sls)
+    info = np.zeros(4)
+    if linear_only:
+        rc = load().cpml_host_attenuation_fit_linear(n_sls, qref, f_min, f_max, _d(te), _d(ts))
+    else:
+        rc = load().cpml_host_attenuation_fit(n_sls, qref, f0, f_min, f_max, _d(te), _d(ts), _d(info))
+    if rc:
+        raise CpmlError(rc, "cpml_host_attenuation_fit")
+    out = (tuple(float(v) for v in te), tuple(float(v) for v in ts))
+    return out + (info,) if return_info else out
 
 
 # ---------------------------------------------------------------- handle

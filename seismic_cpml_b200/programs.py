@@ -162,11 +162,25 @@ TAU_CARCIONE_1993 = dict(tau_epsilon_nu1=(0.0334, 0.0028), tau_sigma_nu1=(0.0303
                          tau_epsilon_nu2=(0.0352, 0.0029), tau_sigma_nu2=(0.0287, 0.0024))
 
 
+def _fit_missing_tau(p, q_nu1, q_nu2, f0_att):
+    """The two compute_attenuation_coeffs calls of the viscoelastic programs (3D-visco :433-443,
+    2D-visco-4th :366-376): mode nu1 (dilatation: QKappa, or Qp in the 2-D programs) and mode nu2
+    (shear), each fitted over f_max / f_min = 12 around f0.  Only pairs left at None are fitted."""
+    for mode, q in (("nu1", q_nu1), ("nu2", q_nu2)):
+        te, ts = getattr(p, "tau_epsilon_" + mode), getattr(p, "tau_sigma_" + mode)
+        if (te is None) != (ts is None):
+            raise ValueError(f"give both tau_epsilon_{mode} and tau_sigma_{mode}, or neither")
+        if te is None:
+            te, ts = _lib.host_attenuation_fit(p.N_SLS, q, f0_att)
+            setattr(p, "tau_epsilon_" + mode, te)
+            setattr(p, "tau_sigma_" + mode, ts)
+
+
 @dataclass
 class Params3DVisco:
-    """Parameter block of seismic_CPML_3D_viscoelastic_MPI.f90:152-244.  The relaxation times are
-    inputs here (the reference derives them from QKappa_att, QMu_att, f0_attenuation with its
-    SolvOpt fit at :439-443, a set-up step outside the time loop)."""
+    """Parameter block of seismic_CPML_3D_viscoelastic_MPI.f90:152-244.  Relaxation times left at
+    None are derived from QKappa_att, QMu_att, f0_attenuation by the SolvOpt fit like the reference
+    does at :433-443 (`lib.host_attenuation_fit`); explicit tuples (e.g. TAU_CARCIONE_1993) bypass it."""
     NX: int = 210
     NY: int = 800
     NZ: int = 220
@@ -183,10 +197,13 @@ class Params3DVisco:
     t0: float | None = None              # = 1.20 / f0 (:183)
     factor: float = 1.0e7
     N_SLS: int = 2
-    tau_epsilon_nu1: tuple = TAU_CARCIONE_1993["tau_epsilon_nu1"]
-    tau_sigma_nu1: tuple = TAU_CARCIONE_1993["tau_sigma_nu1"]
-    tau_epsilon_nu2: tuple = TAU_CARCIONE_1993["tau_epsilon_nu2"]
-    tau_sigma_nu2: tuple = TAU_CARCIONE_1993["tau_sigma_nu2"]
+    QKappa_att: float = 20.0             # :191
+    QMu_att: float = 10.0
+    f0_attenuation: float = 16.0         # :192
+    tau_epsilon_nu1: tuple | None = None
+    tau_sigma_nu1: tuple | None = None
+    tau_epsilon_nu2: tuple | None = None
+    tau_sigma_nu2: tuple | None = None
     USE_PML_XMIN: bool = True
     USE_PML_XMAX: bool = True
     USE_PML_YMIN: bool = True
@@ -211,6 +228,7 @@ class Params3DVisco:
     def __post_init__(self):
         if self.N_SLS != 2:
             raise ValueError("the reference loop is written for N_SLS = 2")
+        _fit_missing_tau(self, self.QKappa_att, self.QMu_att, self.f0_attenuation)
         if self.DELTAY is None: self.DELTAY = self.DELTAX
         if self.DELTAZ is None: self.DELTAZ = self.DELTAX
         if self.t0 is None: self.t0 = 1.20 / self.f0
@@ -255,7 +273,8 @@ TAU_2D_VISCO = dict(tau_epsilon_nu1=(2.408158185753685e-002, 4.699608990861351e-
 @dataclass
 class Params2DVisco:
     """Parameter block of seismic_CPML_2D_velocity_and_stress_{second,fourth}_order_viscoelastic.f90
-    (:140-230).  The relaxation times are inputs (the reference fits them with SolvOpt at :366-370)."""
+    (:140-230).  Relaxation times left at None are fitted to Qp, Qs around f0 with SolvOpt like the
+    reference does at :366-376; the defaults reproduce TAU_2D_VISCO to the last digit."""
     order: int = 4
     VISCOELASTIC_ATTENUATION: bool = True
     NX: int = 2001
@@ -292,10 +311,12 @@ class Params2DVisco:
     ALPHA_MAX_PML: float | None = None
     Rcoef: float = 0.001
     N_SLS: int = 3
-    tau_epsilon_nu1: tuple = TAU_2D_VISCO["tau_epsilon_nu1"]
-    tau_sigma_nu1: tuple = TAU_2D_VISCO["tau_sigma_nu1"]
-    tau_epsilon_nu2: tuple = TAU_2D_VISCO["tau_epsilon_nu2"]
-    tau_sigma_nu2: tuple = TAU_2D_VISCO["tau_sigma_nu2"]
+    Qp: float = 65.0                     # :316-317
+    Qs: float = 55.0
+    tau_epsilon_nu1: tuple | None = None
+    tau_sigma_nu1: tuple | None = None
+    tau_epsilon_nu2: tuple | None = None
+    tau_sigma_nu2: tuple | None = None
 
     def __post_init__(self):
         if self.order not in (2, 4):
@@ -310,6 +331,7 @@ class Params2DVisco:
         if self.ALPHA_MAX_PML is None: self.ALPHA_MAX_PML = 2.0 * PI * (self.f0 / 2.0)
         if not self.VISCOELASTIC_ATTENUATION:        # dummy values of :374-380
             self.tau_epsilon_nu1 = self.tau_sigma_nu1 = self.tau_epsilon_nu2 = self.tau_sigma_nu2 = (1.0, 1.0, 1.0)
+        _fit_missing_tau(self, self.Qp, self.Qs, self.f0)
 
     @property
     def cp(self): return self.cp_unrelaxed

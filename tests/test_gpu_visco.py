@@ -148,7 +148,7 @@ def test_visco_default_grid_window_equals_small_oracle():
     leaves w = 20 untouched for 8 steps.  Also: Dirichlet faces stay zero at full size."""
     from seismic_cpml_b200 import programs as P
     steps, w = 8, 20
-    p = P.Params3DVisco(NSTEP=steps)                      # defaults of 3D-visco :152-244
+    p = P.Params3DVisco(NSTEP=steps, **refcfg.TAU_CARCIONE_1993)   # defaults of 3D-visco :152-244, relaxation times of :402-413
     prog = P.Program3DVisco(p)
     prog.solver.run(1, steps)
     big = {name: prog.solver.get_field(f) for f, name in enumerate(FV) if name in ("vx", "vy", "vz", "sigmaxy", "sigmazz", "sigmayz_R")}

@@ -73,6 +73,7 @@ def test_program2dvisco_mirror_and_elastic_branch():
     """The driver mirror on a reduced grid; VISCOELASTIC_ATTENUATION = False must equal the oracle's
     elastic branch (2D-visco-4th :713-760)."""
     for visco in (True, False):
+        # relaxation times: the program's own SolvOpt fit to Qp = 65, Qs = 55 (2D-visco-4th :366-376)
         p = P.Params2DVisco(order=4, NX=121, NY=101, NSTEP=200, xsource=90.0, ysource=75.0, xdeb=120.0, ydeb=100.0,
                             xfin=120.0, yfin=100.0, VISCOELASTIC_ATTENUATION=visco)
         prog = P.Program2DVisco(p)
@@ -80,9 +81,9 @@ def test_program2dvisco_mirror_and_elastic_branch():
         s = prog.s
         o = O.run_2d_visco(order=4, nx=p.NX, ny=p.NY, deltax=p.DELTAX, deltay=p.DELTAY, deltat=p.DELTAT, nstep=p.NSTEP,
                            npoints_pml=p.NPOINTS_PML, isource=p.ISOURCE, jsource=p.JSOURCE, lam=s.material[0],
-                           mu=s.material[1], rho=s.material[2], tau_epsilon_nu1=P.TAU_2D_VISCO["tau_epsilon_nu1"],
-                           tau_sigma_nu1=P.TAU_2D_VISCO["tau_sigma_nu1"], tau_epsilon_nu2=P.TAU_2D_VISCO["tau_epsilon_nu2"],
-                           tau_sigma_nu2=P.TAU_2D_VISCO["tau_sigma_nu2"], prof_x=s.prof_x, prof_y=s.prof_y,
+                           mu=s.material[1], rho=s.material[2], tau_epsilon_nu1=p.tau_epsilon_nu1,
+                           tau_sigma_nu1=p.tau_sigma_nu1, tau_epsilon_nu2=p.tau_epsilon_nu2,
+                           tau_sigma_nu2=p.tau_sigma_nu2, prof_x=s.prof_x, prof_y=s.prof_y,
                            force_x=s.force_x, force_y=s.force_y, ix_rec=s.ix_rec, iy_rec=s.iy_rec,
                            viscoelastic_attenuation=visco)
         prog.solver.close()
