@@ -660,12 +660,17 @@ class Program2DVisco(_ProgramBase):
         sp = self.solver.get_pressure_seismograms()
         total, ek, ep = self.solver.get_energy()
         if self.output_dir is not None:
+            # write_seismograms of 2D-visco-4th :1145-1193: time axis shifted by -t0 (and by +DELTAT/2 for the
+            # pressure, which is staggered in time, :1164-1168); the file names are the ones the reference's
+            # plotall_fit_is_perfect_for_viscoelastic_fourth_order.gnu reads
             os.makedirs(self.output_dir, exist_ok=True)
-            self.write_seismograms()
-            # pressure_file_NNN.dat, :1178-1193: time - t0, pressure
-            for r in range(self.p.NREC):
-                with open(os.path.join(self.output_dir, f"pressure_file_{r + 1:03d}.dat"), "w") as f:
-                    for it in range(self.p.NSTEP):
-                        f.write(f" {np.float32(it * self.p.DELTAT - self.p.t0)}   {np.float32(sp[r, it])}\n")
+            p = self.p
+            for r in range(p.NREC):
+                for name, series, shift in ((f"pressure_file_{r + 1:03d}.dat", sp[r], 0.5 * p.DELTAT),
+                                            (f"Vx_file_{r + 1:03d}.dat", sx[r], 0.0),
+                                            (f"Vy_file_half_a_grid_cell_away_from_Vx_{r + 1:03d}.dat", sy[r], 0.0)):
+                    with open(os.path.join(self.output_dir, name), "w") as f:
+                        for it in range(p.NSTEP):
+                            f.write(f" {np.float32(it * p.DELTAT - p.t0 + shift)}   {np.float32(series[it])}\n")
         return dict(sisvx=sx, sisvy=sy, sispressure=sp, energy_kinetic=ek, energy_potential=ep,
                     display_log=self.display_log)
