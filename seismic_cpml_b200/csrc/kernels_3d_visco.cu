@@ -40,6 +40,20 @@ __device__ __forceinline__ void vst(double *p, double v) { __stcs(p, v); }
 __device__ __forceinline__ double2 vld2(const double2 *p) { return __ldcs(p); }
 __device__ __forceinline__ void vst2(double2 *p, double2 v) { __stcs(p, v); }
 
+// L2 prefetch of the words a thread will stream a little later.  The stress kernel is bound by memory
+// latency, not bandwidth (13.7 long-scoreboard stall cycles per issued instruction at 16 warps per SM,
+// profiles/r01_v7_ncu_cfg5d.txt): every nest of a plane waits a full DRAM round trip for the
+// read-modify-write words it loads at its head.  A prefetch costs no register and turns those round
+// trips into L2 hits; the LSU merges the 32 addresses of a warp into the 2-4 lines they touch.
+// Measured on B200 (profiles/r01_v8_vpf_sweep.txt), 1024 x 1024 x 128 slab, stress kernel: no prefetch
+// 14.97 ms (58 % of measured HBM); everything plane k+1 streams, at the head of plane k: 11.81 ms; the
+// same two planes ahead: 14.87 ms (the prefetched lines of 296 resident blocks evict each other);
+// staggered by half a plane (default): 11.16 ms (78 %); staggered by one nest: 11.87 ms; one bulk
+// prefetch per row by lane 0 (cp.async.bulk.prefetch.L2): the same as the per-lane form.  The velocity
+// kernel (3 streamed words, all loads already hoisted to the head of the plane) is 3-4 % slower with a
+// prefetch and has none.
+__device__ __forceinline__ void pf_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // memory_x = b * memory_x + a * value ; value / K + memory_x   (e.g. :993-999); rK = RN(1/K)
 __device__ __forceinline__ double vcpml(double *__restrict__ mem, int q, double b, double a, double K, double rK, double value)
 {
@@ -170,6 +184,30 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
             const bool cut_dn = (kmod == 1);                // first plane of a reference slab
             const bool ebox = ebox_ij && kg >= p.npml && kg <= p.nz - p.npml + 1;      // :1387-1392
 
+            // L2 prefetch (see pf_l2).  pf = 1: everything plane k+1 streams, at the head of plane k.
+            // pf = 2: staggered by half a plane -- the shear words of THIS plane here (used after the
+            // normal-stress nest), the normal words of plane k+1 at the head of the shear nests.
+            if (p.pf == 1 && k + 1 <= p.nzl) {
+                const int qn = q + pl;
+                if (NORMAL) {
+                    pf_l2(p.sxx + qn); pf_l2(p.syy + qn); pf_l2(p.szz + qn);
+                    pf_l2(p.rxx + qn); pf_l2(p.ryy + qn); pf_l2(p.rzz + qn);
+                    pf_l2(p.e1 + qn); pf_l2(p.e11 + qn); pf_l2(p.e22 + qn);
+                }
+                if (SHEAR) {
+                    pf_l2(p.sxy + qn); pf_l2(p.sxz + qn); pf_l2(p.syz + qn);
+                    pf_l2(p.rxy + qn); pf_l2(p.rxz + qn); pf_l2(p.ryz + qn);
+                    pf_l2(p.e12 + qn); pf_l2(p.e13 + qn); pf_l2(p.e23 + qn);
+                    pf_l2(p.vx + qn + 2 * pl); pf_l2(p.vy + qn + 2 * pl);
+                }
+                pf_l2(p.vz + qn + pl);
+            }
+            if (p.pf == 2 && SHEAR) {
+                pf_l2(p.sxy + q); pf_l2(p.sxz + q); pf_l2(p.syz + q);
+                pf_l2(p.rxy + q); pf_l2(p.rxz + q); pf_l2(p.ryz + q);
+                pf_l2(p.e12 + q); pf_l2(p.e13 + q); pf_l2(p.e23 + q);
+                pf_l2(p.vx + q + 2 * pl); pf_l2(p.vy + q + 2 * pl);
+            }
             double vz_p = 0.0;
             if (NORMAL) vz_p = p.vz[q + pl];
 
@@ -223,6 +261,13 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
             }
 
             if (SHEAR) {
+                if (p.pf == 2 && NORMAL && k + 1 <= p.nzl) {
+                    const int qn = q + pl;
+                    pf_l2(p.sxx + qn); pf_l2(p.syy + qn); pf_l2(p.szz + qn);
+                    pf_l2(p.rxx + qn); pf_l2(p.ryy + qn); pf_l2(p.rzz + qn);
+                    pf_l2(p.e1 + qn); pf_l2(p.e11 + qn); pf_l2(p.e22 + qn);
+                    pf_l2(p.vz + qn + pl);
+                }
                 const double vx_pp = p.vx[q + 2 * pl], vy_pp = p.vy[q + 2 * pl];
                 double esh = 0.0;
                 // ---- sigmaxy, e12  (:1098-1139)
@@ -436,12 +481,15 @@ k_vvelocity3d(const __grid_constant__ ParamsV3D p)
 
 // ---- launch dispatch ---------------------------------------------------------------
 
-static int g_vtx = 0, g_vty = 0, g_vsplit = 0, g_vminb = 0;
+static int g_vtx = 0, g_vty = 0, g_vsplit = 0, g_vminb = 0, g_vpf = 0;
 
 void visco_tile(int *tx, int *ty)
 {
     if (!g_vtx) {
         const char *sx = getenv("CPML_VTX"), *sy = getenv("CPML_VTY"), *sp = getenv("CPML_VSPLIT"), *sm = getenv("CPML_VMINB");
+        const char *sf = getenv("CPML_VPF");
+        g_vpf = sf ? atoi(sf) : 2;            // L2 prefetch mode of ParamsV3D::pf (stress kernel)
+        if (g_vpf < 0 || g_vpf > 2) g_vpf = 2;
         g_vtx = sx ? atoi(sx) : 32;
         g_vty = sy ? atoi(sy) : 8;
         g_vsplit = sp ? atoi(sp) : 0;         // 0: one stress launch per step (default), 1: normal and shear stresses in two launches
@@ -473,10 +521,12 @@ static cudaError_t vlaunch_minb(const ParamsV3D &p, dim3 grid, cudaStream_t s, b
     return hi ? vlaunch<TX, TY, HI>(p, grid, s, stress) : vlaunch<TX, TY, LO>(p, grid, s, stress);
 }
 
-static cudaError_t vdispatch(const ParamsV3D &p, dim3 grid, cudaStream_t s, bool stress)
+static cudaError_t vdispatch(const ParamsV3D &p_in, dim3 grid, cudaStream_t s, bool stress)
 {
     int tx, ty;
     visco_tile(&tx, &ty);
+    ParamsV3D p = p_in;
+    p.pf = g_vpf;
     switch (tx * 100 + ty) {
     case 3204:  return g_vminb == 3 ? vlaunch<32, 4, 3>(p, grid, s, stress) : vlaunch_minb<32, 4, 2, 4>(p, grid, s, stress);
     case 6404:  return vlaunch_minb<64, 4, 1, 2>(p, grid, s, stress);
