@@ -92,8 +92,10 @@ def test_reference_configuration_on_the_gpu_fits_the_analytical_solution():
     bx, by = _analytic(p.NSTEP, m, m, 0.5)
     ex, ey = _analytic(p.NSTEP, m, m, 0.5, attenuation=False)
     print("rel L2 (reference clock)", _rel(sx, ax), _rel(sy, ay), "(leapfrog clock)", _rel(sx, bx), _rel(sy, by))
-    assert abs(np.abs(sx).max() / np.abs(ax).max() - 1.0) < 0.02
-    assert abs(np.abs(sy).max() / np.abs(ay).max() - 1.0) < 0.02
-    assert _rel(sx, ax) < 0.08 and _rel(sy, ay) < 0.08
-    assert _rel(sx, bx) < 0.05 and _rel(sy, by) < 0.05
+    # measured on B200 (and, identically to 12 digits, with the CPU oracle in 25 minutes): 4.03 % on the
+    # reference's clock, 1.91 % on the leapfrog clock after 34 S wavelengths, peak amplitudes within 0.04 %
+    assert abs(np.abs(sx).max() / np.abs(ax).max() - 1.0) < 0.005
+    assert abs(np.abs(sy).max() / np.abs(ay).max() - 1.0) < 0.005
+    assert _rel(sx, ax) < 0.05 and _rel(sy, ay) < 0.05
+    assert _rel(sx, bx) < 0.025 and _rel(sy, by) < 0.025
     assert _rel(sx, ex) > 0.5 and _rel(sy, ey) > 0.5
