@@ -50,8 +50,8 @@ __device__ __forceinline__ void vst2(double2 *p, double2 v) { __stcs(p, v); }
 // same two planes ahead: 14.87 ms (the prefetched lines of 296 resident blocks evict each other);
 // staggered by half a plane (default): 11.16 ms (78 %); staggered by one nest: 11.87 ms; one bulk
 // prefetch per row by lane 0 (cp.async.bulk.prefetch.L2): the same as the per-lane form.  The velocity
-// kernel (3 streamed words, all loads already hoisted to the head of the plane) is 3-4 % slower with a
-// prefetch and has none.
+// kernel (3 streamed words, all loads already hoisted to the head of the plane) gains at most 2 % from
+// any of four prefetch placements, less than the code costs it when switched off, and has none.
 __device__ __forceinline__ void pf_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // memory_x = b * memory_x + a * value ; value / K + memory_x   (e.g. :993-999); rK = RN(1/K)
