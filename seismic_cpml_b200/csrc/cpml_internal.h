@@ -53,21 +53,51 @@ struct AxisCoef {
 // (inlined, the fallbacks made up a third of the viscoelastic stress kernel's code).
 static __device__ __noinline__ double div_generic(double a, double c) { return a / c; }
 
-__device__ __forceinline__ double div_exact(double a, double c, double y)
+// the five operations alone (exact inside the window tested by div_slow)
+__device__ __forceinline__ double div_fast(double a, double c, double y)
 {
     const double q0 = a * y;
     double r = __fma_rn(-c, q0, a);
     double q = __fma_rn(r, y, q0);
     r = __fma_rn(-c, q, a);
-    q = __fma_rn(r, y, q);
-    // one unsigned compare on the exponent field (sign shifted out): inside 2^-822 < |a| < 2^817 the
-    // five operations above are exact; outside, a zero keeps their result (+-0, equal in value to
-    // the quotient) and everything else takes the generic division
+    return __fma_rn(r, y, q);
+}
+
+// one unsigned compare on the exponent field (sign shifted out): inside 2^-822 < |a| < 2^817 the
+// five operations above are exact; outside, a zero keeps their result (+-0, equal in value to
+// the quotient) and everything else takes the generic division
+// (one predicate, no short-circuit: zero dividends -- the quiescent part of the grid -- fall
+// straight through like ordinary ones)
+__device__ __forceinline__ bool div_slow(double a)
+{
     const unsigned u = ((unsigned)__double2hiint(a) << 1) - (0x0c9u << 21);
-    // (one predicate, no short-circuit: zero dividends -- the quiescent part of the grid -- fall
-    // straight through like ordinary ones)
-    if ((u >= ((0x730u - 0x0c9u) << 21)) & (a != 0.0)) q = div_generic(a, c);
+    return (u >= ((0x730u - 0x0c9u) << 21)) & (a != 0.0);
+}
+
+__device__ __forceinline__ double div_exact(double a, double c, double y)
+{
+    double q = div_fast(a, c, y);
+    if (div_slow(a)) q = div_generic(a, c);
     return q;
+}
+
+// Two / three independent quotients behind ONE range test (in place): the generic division returns the
+// same correctly rounded value for an in-range dividend, so when any of the group leaves the window all of
+// them are redone.  Saves the branch / reconvergence instructions of the other tests (a third of the
+// non-arithmetic instructions of a fourth-order difference).
+__device__ __forceinline__ void div_exact2(double &a0, double &a1, double c0, double y0, double c1, double y1)
+{
+    const double q0 = div_fast(a0, c0, y0), q1 = div_fast(a1, c1, y1);
+    if (div_slow(a0) | div_slow(a1)) { a0 = div_generic(a0, c0); a1 = div_generic(a1, c1); }
+    else { a0 = q0; a1 = q1; }
+}
+__device__ __forceinline__ void div_exact3(double &a0, double &a1, double &a2, double c0, double y0, double c1, double y1,
+                                           double c2, double y2)
+{
+    const double q0 = div_fast(a0, c0, y0), q1 = div_fast(a1, c1, y1), q2 = div_fast(a2, c2, y2);
+    if (div_slow(a0) | div_slow(a1) | div_slow(a2)) {
+        a0 = div_generic(a0, c0); a1 = div_generic(a1, c1); a2 = div_generic(a2, c2);
+    } else { a0 = q0; a1 = q1; a2 = q2; }
 }
 #endif
 

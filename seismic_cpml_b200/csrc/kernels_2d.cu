@@ -202,11 +202,12 @@ __device__ __forceinline__ double2 ld2(const double *f, long long q) { return *r
 __device__ __forceinline__ void st2(double *f, long long q, double a, double b) { *reinterpret_cast<double2 *>(f + q) = make_double2(a, b); }
 
 // difference of a four-tap (ORDER 4) or two-tap (ORDER 2) stencil: 27 a - 27 b - c + d over den
+// (the numerator; the two differences of a nest are divided behind one shared range test, div_exact2)
 template <int ORDER>
-__device__ __forceinline__ double diff2(double a, double b, double c, double d, double den, double rden)
+__device__ __forceinline__ double diffn(double a, double b, double c, double d)
 {
-    if (ORDER == 2) return div_exact(a - b, den, rden);
-    return div_exact(27.0 * a - 27.0 * b - c + d, den, rden);
+    if (ORDER == 2) return a - b;
+    return 27.0 * a - 27.0 * b - c + d;
 }
 
 template <int ORDER>
@@ -223,8 +224,9 @@ __device__ __forceinline__ void stress_point2(const Params2D &p, int i, int j, b
         const double lambda_half_x = 0.5 * (lam_ip + lam_c);
         const double mu_half_x = 0.5 * (mu_ip + mu_c);
         const double lambda_plus_two_mu_half_x = lambda_half_x + 2.0 * mu_half_x;
-        double value_dvx_dx = diff2<ORDER>(vx_ip, vx_c, vx_ipp, vx_im, p.denx, p.rdenx);
-        double value_dvy_dy = diff2<ORDER>(vy_c, vy_jm, vy_jp, vy_jmm, p.deny, p.rdeny);
+        double value_dvx_dx = diffn<ORDER>(vx_ip, vx_c, vx_ipp, vx_im);
+        double value_dvy_dy = diffn<ORDER>(vy_c, vy_jm, vy_jp, vy_jmm);
+        div_exact2(value_dvx_dx, value_dvy_dy, p.denx, p.rdenx, p.deny, p.rdeny);
         if (in_x) value_dvx_dx = cpml_apply2(p.mx[0], qx, p.cx.b_half[i], p.cx.a_half[i], p.cx.K_half[i], p.cx.rK_half[i], value_dvx_dx);
         if (in_y) value_dvy_dy = cpml_apply2(p.my[0], qy, p.cy.b[j], p.cy.a[j], p.cy.K[j], p.cy.rK[j], value_dvy_dy);
         sxx = sxx + (lambda_plus_two_mu_half_x * value_dvx_dx + lambda_half_x * value_dvy_dy) * DELTAT;
@@ -232,8 +234,9 @@ __device__ __forceinline__ void stress_point2(const Params2D &p, int i, int j, b
     }
     if (i >= 2 && j <= p.ny - 1) {
         const double mu_half_y = 0.5 * (mu_jp + mu_c);
-        double value_dvy_dx = diff2<ORDER>(vy_c, vy_im, vy_ip, vy_imm, p.denx, p.rdenx);
-        double value_dvx_dy = diff2<ORDER>(vx_jp, vx_c, vx_jpp, vx_jm, p.deny, p.rdeny);
+        double value_dvy_dx = diffn<ORDER>(vy_c, vy_im, vy_ip, vy_imm);
+        double value_dvx_dy = diffn<ORDER>(vx_jp, vx_c, vx_jpp, vx_jm);
+        div_exact2(value_dvy_dx, value_dvx_dy, p.denx, p.rdenx, p.deny, p.rdeny);
         if (in_x) value_dvy_dx = cpml_apply2(p.mx[1], qx, p.cx.b[i], p.cx.a[i], p.cx.K[i], p.cx.rK[i], value_dvy_dx);
         // quirk B3, see k_stress2d
         if (in_y) value_dvx_dy = cpml_apply2(p.my[1], qy, p.cy.b_half[j], p.cy.a_half[j],
@@ -295,15 +298,17 @@ __device__ __forceinline__ void velocity_point2(const Params2D &p, int i, int j,
 {
     const double DELTAT = p.deltat;
     if (i >= 2 && j >= 2) {
-        double value_dsigmaxx_dx = diff2<ORDER>(sxx_c, sxx_im, sxx_ip, sxx_imm, p.denx, p.rdenx);
-        double value_dsigmaxy_dy = diff2<ORDER>(sxy_c, sxy_jm, sxy_jp, sxy_jmm, p.deny, p.rdeny);
+        double value_dsigmaxx_dx = diffn<ORDER>(sxx_c, sxx_im, sxx_ip, sxx_imm);
+        double value_dsigmaxy_dy = diffn<ORDER>(sxy_c, sxy_jm, sxy_jp, sxy_jmm);
+        div_exact2(value_dsigmaxx_dx, value_dsigmaxy_dy, p.denx, p.rdenx, p.deny, p.rdeny);
         if (in_x) value_dsigmaxx_dx = cpml_apply2(p.mx[2], qx, p.cx.b[i], p.cx.a[i], p.cx.K[i], p.cx.rK[i], value_dsigmaxx_dx);
         if (in_y) value_dsigmaxy_dy = cpml_apply2(p.my[2], qy, p.cy.b[j], p.cy.a[j], p.cy.K[j], p.cy.rK[j], value_dsigmaxy_dy);
         vx = vx + div_rho((value_dsigmaxx_dx + value_dsigmaxy_dy) * DELTAT, rho, p.rho_exact);
     }
     if (i <= p.nx - 1 && j <= p.ny - 1) {
-        double value_dsigmaxy_dx = diff2<ORDER>(sxy_ip, sxy_c, sxy_ipp, sxy_im, p.denx, p.rdenx);
-        double value_dsigmayy_dy = diff2<ORDER>(syy_jp, syy_c, syy_jpp, syy_jm, p.deny, p.rdeny);
+        double value_dsigmaxy_dx = diffn<ORDER>(sxy_ip, sxy_c, sxy_ipp, sxy_im);
+        double value_dsigmayy_dy = diffn<ORDER>(syy_jp, syy_c, syy_jpp, syy_jm);
+        div_exact2(value_dsigmaxy_dx, value_dsigmayy_dy, p.denx, p.rdenx, p.deny, p.rdeny);
         if (in_x) value_dsigmaxy_dx = cpml_apply2(p.mx[3], qx, p.cx.b_half[i], p.cx.a_half[i], p.cx.K_half[i], p.cx.rK_half[i], value_dsigmaxy_dx);
         if (in_y) value_dsigmayy_dy = cpml_apply2(p.my[3], qy, p.cy.b_half[j], p.cy.a_half[j], p.cy.K_half[j], p.cy.rK_half[j], value_dsigmayy_dy);
         vy = vy + div_rho((value_dsigmaxy_dx + value_dsigmayy_dy) * DELTAT, rho_half_x_half_y, p.rho_exact);

@@ -65,17 +65,24 @@ __device__ __forceinline__ double vcpml(double *__restrict__ mem, int q, double 
 
 __device__ __forceinline__ int vshell(int i, int lo, int hi) { return i <= lo ? i - 1 : lo + (i - hi); }
 
-// (27 a - 27 b - c + d) * ONE_OVER_DELTA / 24   (:989-991)
-__device__ __forceinline__ double d4(double a, double b, double c, double d, double od)
+// (27 a - 27 b - c + d) * ONE_OVER_DELTA / 24   (:989-991): the numerator; the three (or two) differences of
+// a nest are then divided behind one shared range test (div_exact3 / div_exact2, cpml_internal.h)
+__device__ __forceinline__ double d4n(double a, double b, double c, double d, double od)
 {
-    return div_exact((27.0 * a - 27.0 * b - c + d) * od, 24.0, 1.0 / 24.0);
+    return (27.0 * a - 27.0 * b - c + d) * od;
 }
+#define DIV24_3(x, y, z) div_exact3(x, y, z, 24.0, 1.0 / 24.0, 24.0, 1.0 / 24.0, 24.0, 1.0 / 24.0)
+#define DIV24_2(x, y) div_exact2(x, y, 24.0, 1.0 / 24.0, 24.0, 1.0 / 24.0)
 
-// Unp1 = (Un + deltat*(Sn + 0.5*tauinv*Un)) / (1 - deltat*0.5*tauinv)   (:1003-1009)
-__device__ __forceinline__ double evolve(double Un, double Sn, double tauinv, double den, double rden, double dt)
+// Unp1 = (Un + deltat*(Sn + 0.5*tauinv*Un)) / (1 - deltat*0.5*tauinv)   (:1003-1009), both mechanisms of
+// one memory variable behind one range test
+__device__ __forceinline__ double2 evolve2(double2 U, double S0, double S1, const double (&tauinv)[2], const double (&den)[2],
+                                           const double (&rden)[2], double dt)
 {
-    const double tauinvUn = tauinv * Un;
-    return div_exact(Un + dt * (Sn + 0.5 * tauinvUn), den, rden);
+    const double t0 = tauinv[0] * U.x, t1 = tauinv[1] * U.y;
+    double n0 = U.x + dt * (S0 + 0.5 * t0), n1 = U.y + dt * (S1 + 0.5 * t1);
+    div_exact2(n0, n1, den[0], rden[0], den[1], rden[1]);
+    return make_double2(n0, n1);
 }
 
 template <int NT>
@@ -219,21 +226,19 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
                 double rxx = vld(p.rxx + q), ryy = vld(p.ryy + q), rzz = vld(p.rzz + q);
                 double2 e1 = vld2(p.e1 + q), e11 = vld2(p.e11 + q), e22 = vld2(p.e22 + q);
                 if (do_n && kg >= 2) {                      // k2begin, :942-943
-                    double duxdx = d4(vx_ip1, vx_0, vx_ip2, vx_im1, odx);
-                    double duydy = d4(vy_0, vy_jm1, vy_jp1, vy_jm2, ody);
-                    double duzdz = d4(vz_c, vz_m, cut_up ? 0.0 : vz_p, vz_mm, odz);
+                    double duxdx = d4n(vx_ip1, vx_0, vx_ip2, vx_im1, odx);
+                    double duydy = d4n(vy_0, vy_jm1, vy_jp1, vy_jm2, ody);
+                    double duzdz = d4n(vz_c, vz_m, cut_up ? 0.0 : vz_p, vz_mm, odz);
+                    DIV24_3(duxdx, duydy, duzdz);
                     if (in_x) duxdx = vcpml(p.mx[0], qx, cxc[5 * TX], cxc[4 * TX], cxc[6 * TX], cxc[7 * TX], duxdx);
                     if (in_y) duydy = vcpml(p.my[0], qy, cyc[1 * TY], cyc[0 * TY], cyc[2 * TY], cyc[3 * TY], duydy);
                     if (in_z) duzdz = vcpml(p.mz[0], qz, bz, az, Kz, rKz, duzdz);
                     const double div = duxdx + duydy + duzdz;
                     const double div3 = div_exact(div, 3.0, 1.0 / 3.0);      // div/DIM
 
-                    e1.x = evolve(e1.x, div * p.phi1[0], p.tauinv1[0], p.den1[0], p.rden1[0], dt);
-                    e1.y = evolve(e1.y, div * p.phi1[1], p.tauinv1[1], p.den1[1], p.rden1[1], dt);
-                    e11.x = evolve(e11.x, (duxdx - div3) * p.phi2[0], p.tauinv2[0], p.den2[0], p.rden2[0], dt);
-                    e11.y = evolve(e11.y, (duxdx - div3) * p.phi2[1], p.tauinv2[1], p.den2[1], p.rden2[1], dt);
-                    e22.x = evolve(e22.x, (duydy - div3) * p.phi2[0], p.tauinv2[0], p.den2[0], p.rden2[0], dt);
-                    e22.y = evolve(e22.y, (duydy - div3) * p.phi2[1], p.tauinv2[1], p.den2[1], p.rden2[1], dt);
+                    e1 = evolve2(e1, div * p.phi1[0], div * p.phi1[1], p.tauinv1, p.den1, p.rden1, dt);
+                    e11 = evolve2(e11, (duxdx - div3) * p.phi2[0], (duxdx - div3) * p.phi2[1], p.tauinv2, p.den2, p.rden2, dt);
+                    e22 = evolve2(e22, (duydy - div3) * p.phi2[0], (duydy - div3) * p.phi2[1], p.tauinv2, p.den2, p.rden2, dt);
                     vst2(p.e1 + q, e1); vst2(p.e11 + q, e11); vst2(p.e22 + q, e22);
 
                     // relaxed moduli times the memory variables (:1054-1060)
@@ -277,13 +282,13 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
                     double sxy = vld(p.sxy + q), rxy = vld(p.rxy + q);
                     double2 e12 = vld2(p.e12 + q);
                     if (do_xy) {
-                        double duydx = d4(vy_c, vy_im1, vy_ip1, vy_im2, odx);
-                        double duxdy = d4(vx_jp1, vx_c, vx_jp2, vx_jm1, ody);
+                        double duydx = d4n(vy_c, vy_im1, vy_ip1, vy_im2, odx);
+                        double duxdy = d4n(vx_jp1, vx_c, vx_jp2, vx_jm1, ody);
+                        DIV24_2(duydx, duxdy);
                         if (in_x) duydx = vcpml(p.mx[1], qx, cxc[1 * TX], cxc[0 * TX], cxc[2 * TX], cxc[3 * TX], duydx);
                         if (in_y) duxdy = vcpml(p.my[1], qy, cyc[5 * TY], cyc[4 * TY], cyc[6 * TY], cyc[7 * TY], duxdy);
                         const double g = duxdy + duydx;
-                        e12.x = evolve(e12.x, g * p.phi2[0], p.tauinv2[0], p.den2[0], p.rden2[0], dt);
-                        e12.y = evolve(e12.y, g * p.phi2[1], p.tauinv2[1], p.den2[1], p.rden2[1], dt);
+                        e12 = evolve2(e12, g * p.phi2[0], g * p.phi2[1], p.tauinv2, p.den2, p.rden2, dt);
                         vst2(p.e12 + q, e12);
                         sxy = sxy + dt * p.mu * (e12.x + e12.y);
                         sxy = sxy + p.mu_u * g * dt;
@@ -298,13 +303,13 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
                     double sxz = vld(p.sxz + q), rxz = vld(p.rxz + q);
                     double2 e13 = vld2(p.e13 + q);
                     if (do_xz && kg <= p.nz - 1) {                  // kminus1end, :945-946
-                        double duzdx = d4(vz_c, vz_im1, vz_ip1, vz_im2, odx);
-                        double duxdz = d4(vx_p, vx_c, vx_pp, cut_dn ? 0.0 : vx_m, odz);
+                        double duzdx = d4n(vz_c, vz_im1, vz_ip1, vz_im2, odx);
+                        double duxdz = d4n(vx_p, vx_c, vx_pp, cut_dn ? 0.0 : vx_m, odz);
+                        DIV24_2(duzdx, duxdz);
                         if (in_x) duzdx = vcpml(p.mx[2], qx, cxc[1 * TX], cxc[0 * TX], cxc[2 * TX], cxc[3 * TX], duzdx);
                         if (in_z) duxdz = vcpml(p.mz[1], qz, bzh, azh, Kzh, rKzh, duxdz);
                         const double g = duxdz + duzdx;
-                        e13.x = evolve(e13.x, g * p.phi2[0], p.tauinv2[0], p.den2[0], p.rden2[0], dt);
-                        e13.y = evolve(e13.y, g * p.phi2[1], p.tauinv2[1], p.den2[1], p.rden2[1], dt);
+                        e13 = evolve2(e13, g * p.phi2[0], g * p.phi2[1], p.tauinv2, p.den2, p.rden2, dt);
                         vst2(p.e13 + q, e13);
                         sxz = sxz + dt * p.mu * (e13.x + e13.y);
                         sxz = sxz + p.mu_u * g * dt;
@@ -318,13 +323,13 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
                     double syz = vld(p.syz + q), ryz = vld(p.ryz + q);
                     double2 e23 = vld2(p.e23 + q);
                     if (do_yz && kg <= p.nz - 1) {
-                        double duzdy = d4(vz_jp1, vz_c, vz_jp2, vz_jm1, ody);
-                        double duydz = d4(vy_p, vy_c, vy_pp, cut_dn ? 0.0 : vy_m, odz);
+                        double duzdy = d4n(vz_jp1, vz_c, vz_jp2, vz_jm1, ody);
+                        double duydz = d4n(vy_p, vy_c, vy_pp, cut_dn ? 0.0 : vy_m, odz);
+                        DIV24_2(duzdy, duydz);
                         if (in_y) duzdy = vcpml(p.my[2], qy, cyc[5 * TY], cyc[4 * TY], cyc[6 * TY], cyc[7 * TY], duzdy);
                         if (in_z) duydz = vcpml(p.mz[2], qz, bzh, azh, Kzh, rKzh, duydz);
                         const double g = duydz + duzdy;
-                        e23.x = evolve(e23.x, g * p.phi2[0], p.tauinv2[0], p.den2[0], p.rden2[0], dt);
-                        e23.y = evolve(e23.y, g * p.phi2[1], p.tauinv2[1], p.den2[1], p.rden2[1], dt);
+                        e23 = evolve2(e23, g * p.phi2[0], g * p.phi2[1], p.tauinv2, p.den2, p.rden2, dt);
                         vst2(p.e23 + q, e23);
                         syz = syz + dt * p.mu * (e23.x + e23.y);
                         syz = syz + p.mu_u * g * dt;
@@ -421,18 +426,20 @@ k_vvelocity3d(const __grid_constant__ ParamsV3D p)
 
             if (kg >= 2) {                                           // k2begin
                 if (do_vx) {                                         // :1244-1262
-                    double d1 = d4(sxx_c, sxx_im1, sxx_ip1, sxx_im2, odx);
-                    double d2 = d4(sxy_c, sxy_jm1, sxy_jp1, sxy_jm2, ody);
-                    double d3 = d4(sxz_c, sxz_m, cut_up ? 0.0 : sxz_p, sxz_mm, odz);
+                    double d1 = d4n(sxx_c, sxx_im1, sxx_ip1, sxx_im2, odx);
+                    double d2 = d4n(sxy_c, sxy_jm1, sxy_jp1, sxy_jm2, ody);
+                    double d3 = d4n(sxz_c, sxz_m, cut_up ? 0.0 : sxz_p, sxz_mm, odz);
+                    DIV24_3(d1, d2, d3);
                     if (in_x) d1 = vcpml(p.mx[3], qx, cxc[1 * TX], cxc[0 * TX], cxc[2 * TX], cxc[3 * TX], d1);
                     if (in_y) d2 = vcpml(p.my[3], qy, cyc[1 * TY], cyc[0 * TY], cyc[2 * TY], cyc[3 * TY], d2);
                     if (in_z) d3 = vcpml(p.mz[3], qz, bz, az, Kz, rKz, d3);
                     vx = dt_r * (d1 + d2 + d3) + vx;
                 }
                 if (do_vy) {                                         // :1266-1284
-                    double d1 = d4(sxy_ip1, sxy_c, sxy_ip2, sxy_im1, odx);
-                    double d2 = d4(syy_jp1, syy_c, syy_jp2, syy_jm1, ody);
-                    double d3 = d4(syz_c, syz_m, cut_up ? 0.0 : syz_p, syz_mm, odz);
+                    double d1 = d4n(sxy_ip1, sxy_c, sxy_ip2, sxy_im1, odx);
+                    double d2 = d4n(syy_jp1, syy_c, syy_jp2, syy_jm1, ody);
+                    double d3 = d4n(syz_c, syz_m, cut_up ? 0.0 : syz_p, syz_mm, odz);
+                    DIV24_3(d1, d2, d3);
                     if (in_x) d1 = vcpml(p.mx[4], qx, cxc[5 * TX], cxc[4 * TX], cxc[6 * TX], cxc[7 * TX], d1);
                     if (in_y) d2 = vcpml(p.my[4], qy, cyc[5 * TY], cyc[4 * TY], cyc[6 * TY], cyc[7 * TY], d2);
                     if (in_z) d3 = vcpml(p.mz[4], qz, bz, az, Kz, rKz, d3);
@@ -440,9 +447,10 @@ k_vvelocity3d(const __grid_constant__ ParamsV3D p)
                 }
             }
             if (do_vz && kg <= p.nz - 1) {                           // kminus1end, :1287-1308
-                double d1 = d4(sxz_ip1, sxz_c, sxz_ip2, sxz_im1, odx);
-                double d2 = d4(syz_c, syz_jm1, syz_jp1, syz_jm2, ody);
-                double d3 = d4(szz_p, szz_c, szz_pp, cut_dn ? 0.0 : szz_m, odz);
+                double d1 = d4n(sxz_ip1, sxz_c, sxz_ip2, sxz_im1, odx);
+                double d2 = d4n(syz_c, syz_jm1, syz_jp1, syz_jm2, ody);
+                double d3 = d4n(szz_p, szz_c, szz_pp, cut_dn ? 0.0 : szz_m, odz);
+                DIV24_3(d1, d2, d3);
                 if (in_x) d1 = vcpml(p.mx[5], qx, cxc[5 * TX], cxc[4 * TX], cxc[6 * TX], cxc[7 * TX], d1);
                 if (in_y) d2 = vcpml(p.my[5], qy, cyc[1 * TY], cyc[0 * TY], cyc[2 * TY], cyc[3 * TY], d2);
                 if (in_z) d3 = vcpml(p.mz[5], qz, bzh, azh, Kzh, rKzh, d3);
