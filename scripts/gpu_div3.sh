@@ -1,7 +1,7 @@
 #!/bin/bash
 # viscoelastic kernels after grouping the range tests of the divisions (div_exact2 / div_exact3)
 mkdir -p gpurun_out
-OUT=gpurun_out/sweep_div3.txt; : > $OUT
+OUT=gpurun_out/sweep_div5.txt; : > $OUT
 fmt='
 import sys, json
 for l in sys.stdin:
@@ -12,6 +12,6 @@ for l in sys.stdin:
         print("  ?", l.strip()[:300])
 '
 run() { wl=$1; shift; echo "$wl $*" >> $OUT; env "$@" timeout 300 python bench.py --workload $wl --steps 30 --warmup 3 --no-cpu-baseline 2>&1 | python -c "$fmt" >> $OUT; }
-( timeout 600 python -m pytest tests/test_gpu_visco.py -x -q ) > gpurun_out/test_div3.log 2>&1; echo "pytest rc=$?" >> gpurun_out/test_div3.log
+( timeout 600 python -m pytest tests/test_gpu_visco.py -x -q ) > gpurun_out/test_div5.log 2>&1; echo "pytest rc=$?" >> gpurun_out/test_div5.log
 for wl in cfg5d cfg5; do run $wl CPML_VPF=2; done
 echo finished >> $OUT

@@ -81,6 +81,38 @@ __device__ __forceinline__ double div_exact(double a, double c, double y)
     return q;
 }
 
+// Divisors with a SMALL ODD PART (24 = 3 * 8, 3): one correction is enough, provably.  With c = d * 2^k,
+// d odd, the quotient a / c is never closer to a rounding midpoint than 1 / (2 d) ulp: in units of half an
+// ulp, a / c minus the odd integer of a midpoint is a non-zero integer over d (non-zero because a midpoint
+// times c would need more than 53 bits).  q0 = RN(a y) is within 1.5 ulp of a / c, so r = a - c q0 is a small
+// multiple of a common unit and exact in the FMA, and q0 + r y differs from a / c by |r / c| 2^-53 < 2^-52 ulp --
+// far inside the 1 / (2 d) ulp margin, so RN(q0 + r y) is the correctly rounded quotient.
+__device__ __forceinline__ double div_fast_small(double a, double c, double y)
+{
+    const double q0 = a * y;
+    const double r = __fma_rn(-c, q0, a);
+    return __fma_rn(r, y, q0);
+}
+__device__ __forceinline__ double div_small(double a, double c, double y)
+{
+    double q = div_fast_small(a, c, y);
+    if (div_slow(a)) q = div_generic(a, c);
+    return q;
+}
+__device__ __forceinline__ void div_small2(double &a0, double &a1, double c, double y)
+{
+    const double q0 = div_fast_small(a0, c, y), q1 = div_fast_small(a1, c, y);
+    if (div_slow(a0) | div_slow(a1)) { a0 = div_generic(a0, c); a1 = div_generic(a1, c); }
+    else { a0 = q0; a1 = q1; }
+}
+__device__ __forceinline__ void div_small3(double &a0, double &a1, double &a2, double c, double y)
+{
+    const double q0 = div_fast_small(a0, c, y), q1 = div_fast_small(a1, c, y), q2 = div_fast_small(a2, c, y);
+    if (div_slow(a0) | div_slow(a1) | div_slow(a2)) {
+        a0 = div_generic(a0, c); a1 = div_generic(a1, c); a2 = div_generic(a2, c);
+    } else { a0 = q0; a1 = q1; a2 = q2; }
+}
+
 // Two / three independent quotients behind ONE range test (in place): the generic division returns the
 // same correctly rounded value for an in-range dividend, so when any of the group leaves the window all of
 // them are redone.  Saves the branch / reconvergence instructions of the other tests (a third of the

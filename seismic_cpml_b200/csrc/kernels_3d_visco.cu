@@ -66,13 +66,14 @@ __device__ __forceinline__ double vcpml(double *__restrict__ mem, int q, double 
 __device__ __forceinline__ int vshell(int i, int lo, int hi) { return i <= lo ? i - 1 : lo + (i - hi); }
 
 // (27 a - 27 b - c + d) * ONE_OVER_DELTA / 24   (:989-991): the numerator; the three (or two) differences of
-// a nest are then divided behind one shared range test (div_exact3 / div_exact2, cpml_internal.h)
+// a nest are then divided by 24 behind one shared range test, with the single correction that is enough
+// for a divisor with a small odd part (div_small3 / div_small2, cpml_internal.h)
 __device__ __forceinline__ double d4n(double a, double b, double c, double d, double od)
 {
     return (27.0 * a - 27.0 * b - c + d) * od;
 }
-#define DIV24_3(x, y, z) div_exact3(x, y, z, 24.0, 1.0 / 24.0, 24.0, 1.0 / 24.0, 24.0, 1.0 / 24.0)
-#define DIV24_2(x, y) div_exact2(x, y, 24.0, 1.0 / 24.0, 24.0, 1.0 / 24.0)
+#define DIV24_3(x, y, z) div_small3(x, y, z, 24.0, 1.0 / 24.0)
+#define DIV24_2(x, y) div_small2(x, y, 24.0, 1.0 / 24.0)
 
 // Unp1 = (Un + deltat*(Sn + 0.5*tauinv*Un)) / (1 - deltat*0.5*tauinv)   (:1003-1009), both mechanisms of
 // one memory variable behind one range test
@@ -234,7 +235,7 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
                     if (in_y) duydy = vcpml(p.my[0], qy, cyc[1 * TY], cyc[0 * TY], cyc[2 * TY], cyc[3 * TY], duydy);
                     if (in_z) duzdz = vcpml(p.mz[0], qz, bz, az, Kz, rKz, duzdz);
                     const double div = duxdx + duydy + duzdz;
-                    const double div3 = div_exact(div, 3.0, 1.0 / 3.0);      // div/DIM
+                    const double div3 = div_small(div, 3.0, 1.0 / 3.0);      // div/DIM
 
                     e1 = evolve2(e1, div * p.phi1[0], div * p.phi1[1], p.tauinv1, p.den1, p.rden1, dt);
                     e11 = evolve2(e11, (duxdx - div3) * p.phi2[0], (duxdx - div3) * p.phi2[1], p.tauinv2, p.den2, p.rden2, dt);
