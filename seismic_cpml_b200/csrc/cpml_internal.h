@@ -242,8 +242,9 @@ struct ParamsV3D {
     double *partials;         // [0, nb) kinetic (velocity kernel), [nb, 2nb) and [2nb, 3nb) potential (stress launches)
     int nblocks;
     int kchunk;               // planes marched by one block
-    int pf;                   // stress kernel, L2 prefetch of the streamed words: 0 off, 1 one plane ahead,
-                              // 2 staggered by half a plane (set by the dispatcher, CPML_VPF)
+    int pf;                   // L2 prefetch (set by the dispatcher, CPML_VPF).  Bits 0-1, stress kernel, streamed words:
+                              // 0 off, 1 one plane ahead, 2 staggered by half a plane; bit 2, both kernels: the C-PML
+                              // memory variables of the next plane
 };
 
 // ------------------------------------------------------------------ 2-D

@@ -177,6 +177,7 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
         for (int k = kb; k <= ke; ++k, q += pl) {
             const int kg = k + p.koff;                      // :978
             const bool in_z = (kg <= p.zlo) || (kg >= p.zhi);
+            const bool in_pml = in_x | in_y | in_z;          // one branch per nest for the interior points
             int qx = 0, qy = 0, qz = 0;
             double az = 0, bz = 0, Kz = 1, azh = 0, bzh = 0, Kzh = 1, rKz = 1, rKzh = 1;
             if (in_x) qx = ((k - 1) * p.ny + (j - 1)) * p.sxp + sx;
@@ -191,11 +192,36 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
             const bool cut_up = (kmod == 0);                // last plane of a reference slab
             const bool cut_dn = (kmod == 1);                // first plane of a reference slab
             const bool ebox = ebox_ij && kg >= p.npml && kg <= p.nz - p.npml + 1;      // :1387-1392
+            // C-PML memory variables of the NEXT plane (and of the first plane of the chunk) into L2: each
+            // recursion is a dependent load -> update -> store, up to three in a row per nest, and the shell
+            // points (23 % of the default grid) took 21 % / 31 % of the stall samples of the two kernels with
+            // 5 % / 10 % of their instructions (profiles/r01_v8_ncu_cfg5d.txt, source page)
+            if ((p.pf & 4) && (in_pml | (kg + 1 <= p.zlo) | (kg + 1 >= p.zhi))) {
+                for (int d = (k == kb ? 0 : 1); d <= 1; ++d) {
+                    if (k + d > p.nzl) break;
+                    if (in_x) {
+                        const int qn = ((k + d - 1) * p.ny + (j - 1)) * p.sxp + sx;
+                        if (NORMAL) pf_l2(p.mx[0] + qn);
+                        if (SHEAR) { pf_l2(p.mx[1] + qn); pf_l2(p.mx[2] + qn); }
+                    }
+                    if (in_y) {
+                        const int qn = ((k + d - 1) * p.sy + sy) * pitch + (i - 1);
+                        if (NORMAL) pf_l2(p.my[0] + qn);
+                        if (SHEAR) { pf_l2(p.my[1] + qn); pf_l2(p.my[2] + qn); }
+                    }
+                    const int kgn = kg + d;
+                    if ((kgn <= p.zlo) || (kgn >= p.zhi)) {
+                        const int qn = ((vshell(kgn, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1);
+                        if (NORMAL) pf_l2(p.mz[0] + qn);
+                        if (SHEAR) { pf_l2(p.mz[1] + qn); pf_l2(p.mz[2] + qn); }
+                    }
+                }
+            }
 
             // L2 prefetch (see pf_l2).  pf = 1: everything plane k+1 streams, at the head of plane k.
             // pf = 2: staggered by half a plane -- the shear words of THIS plane here (used after the
             // normal-stress nest), the normal words of plane k+1 at the head of the shear nests.
-            if (p.pf == 1 && k + 1 <= p.nzl) {
+            if ((p.pf & 3) == 1 && k + 1 <= p.nzl) {
                 const int qn = q + pl;
                 if (NORMAL) {
                     pf_l2(p.sxx + qn); pf_l2(p.syy + qn); pf_l2(p.szz + qn);
@@ -210,7 +236,7 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
                 }
                 pf_l2(p.vz + qn + pl);
             }
-            if (p.pf == 2 && SHEAR) {
+            if ((p.pf & 3) == 2 && SHEAR) {
                 pf_l2(p.sxy + q); pf_l2(p.sxz + q); pf_l2(p.syz + q);
                 pf_l2(p.rxy + q); pf_l2(p.rxz + q); pf_l2(p.ryz + q);
                 pf_l2(p.e12 + q); pf_l2(p.e13 + q); pf_l2(p.e23 + q);
@@ -231,9 +257,11 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
                     double duydy = d4n(vy_0, vy_jm1, vy_jp1, vy_jm2, ody);
                     double duzdz = d4n(vz_c, vz_m, cut_up ? 0.0 : vz_p, vz_mm, odz);
                     DIV24_3(duxdx, duydy, duzdz);
-                    if (in_x) duxdx = vcpml(p.mx[0], qx, cxc[5 * TX], cxc[4 * TX], cxc[6 * TX], cxc[7 * TX], duxdx);
-                    if (in_y) duydy = vcpml(p.my[0], qy, cyc[1 * TY], cyc[0 * TY], cyc[2 * TY], cyc[3 * TY], duydy);
-                    if (in_z) duzdz = vcpml(p.mz[0], qz, bz, az, Kz, rKz, duzdz);
+                    if (in_pml) {
+                        if (in_x) duxdx = vcpml(p.mx[0], qx, cxc[5 * TX], cxc[4 * TX], cxc[6 * TX], cxc[7 * TX], duxdx);
+                        if (in_y) duydy = vcpml(p.my[0], qy, cyc[1 * TY], cyc[0 * TY], cyc[2 * TY], cyc[3 * TY], duydy);
+                        if (in_z) duzdz = vcpml(p.mz[0], qz, bz, az, Kz, rKz, duzdz);
+                    }
                     const double div = duxdx + duydy + duzdz;
                     const double div3 = div_small(div, 3.0, 1.0 / 3.0);      // div/DIM
 
@@ -267,7 +295,7 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
             }
 
             if (SHEAR) {
-                if (p.pf == 2 && NORMAL && k + 1 <= p.nzl) {
+                if ((p.pf & 3) == 2 && NORMAL && k + 1 <= p.nzl) {
                     const int qn = q + pl;
                     pf_l2(p.sxx + qn); pf_l2(p.syy + qn); pf_l2(p.szz + qn);
                     pf_l2(p.rxx + qn); pf_l2(p.ryy + qn); pf_l2(p.rzz + qn);
@@ -286,8 +314,10 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
                         double duydx = d4n(vy_c, vy_im1, vy_ip1, vy_im2, odx);
                         double duxdy = d4n(vx_jp1, vx_c, vx_jp2, vx_jm1, ody);
                         DIV24_2(duydx, duxdy);
-                        if (in_x) duydx = vcpml(p.mx[1], qx, cxc[1 * TX], cxc[0 * TX], cxc[2 * TX], cxc[3 * TX], duydx);
-                        if (in_y) duxdy = vcpml(p.my[1], qy, cyc[5 * TY], cyc[4 * TY], cyc[6 * TY], cyc[7 * TY], duxdy);
+                        if (in_pml) {
+                            if (in_x) duydx = vcpml(p.mx[1], qx, cxc[1 * TX], cxc[0 * TX], cxc[2 * TX], cxc[3 * TX], duydx);
+                            if (in_y) duxdy = vcpml(p.my[1], qy, cyc[5 * TY], cyc[4 * TY], cyc[6 * TY], cyc[7 * TY], duxdy);
+                        }
                         const double g = duxdy + duydx;
                         e12 = evolve2(e12, g * p.phi2[0], g * p.phi2[1], p.tauinv2, p.den2, p.rden2, dt);
                         vst2(p.e12 + q, e12);
@@ -307,8 +337,10 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
                         double duzdx = d4n(vz_c, vz_im1, vz_ip1, vz_im2, odx);
                         double duxdz = d4n(vx_p, vx_c, vx_pp, cut_dn ? 0.0 : vx_m, odz);
                         DIV24_2(duzdx, duxdz);
-                        if (in_x) duzdx = vcpml(p.mx[2], qx, cxc[1 * TX], cxc[0 * TX], cxc[2 * TX], cxc[3 * TX], duzdx);
-                        if (in_z) duxdz = vcpml(p.mz[1], qz, bzh, azh, Kzh, rKzh, duxdz);
+                        if (in_pml) {
+                            if (in_x) duzdx = vcpml(p.mx[2], qx, cxc[1 * TX], cxc[0 * TX], cxc[2 * TX], cxc[3 * TX], duzdx);
+                            if (in_z) duxdz = vcpml(p.mz[1], qz, bzh, azh, Kzh, rKzh, duxdz);
+                        }
                         const double g = duxdz + duzdx;
                         e13 = evolve2(e13, g * p.phi2[0], g * p.phi2[1], p.tauinv2, p.den2, p.rden2, dt);
                         vst2(p.e13 + q, e13);
@@ -327,8 +359,10 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
                         double duzdy = d4n(vz_jp1, vz_c, vz_jp2, vz_jm1, ody);
                         double duydz = d4n(vy_p, vy_c, vy_pp, cut_dn ? 0.0 : vy_m, odz);
                         DIV24_2(duzdy, duydz);
-                        if (in_y) duzdy = vcpml(p.my[2], qy, cyc[5 * TY], cyc[4 * TY], cyc[6 * TY], cyc[7 * TY], duzdy);
-                        if (in_z) duydz = vcpml(p.mz[2], qz, bzh, azh, Kzh, rKzh, duydz);
+                        if (in_pml) {
+                            if (in_y) duzdy = vcpml(p.my[2], qy, cyc[5 * TY], cyc[4 * TY], cyc[6 * TY], cyc[7 * TY], duzdy);
+                            if (in_z) duydz = vcpml(p.mz[2], qz, bzh, azh, Kzh, rKzh, duydz);
+                        }
                         const double g = duydz + duzdy;
                         e23 = evolve2(e23, g * p.phi2[0], g * p.phi2[1], p.tauinv2, p.den2, p.rden2, dt);
                         vst2(p.e23 + q, e23);
@@ -411,6 +445,7 @@ k_vvelocity3d(const __grid_constant__ ParamsV3D p)
             double vx = vld(p.vx + q), vy = vld(p.vy + q), vz = vld(p.vz + q);
 
             const bool in_z = (kg <= p.zlo) || (kg >= p.zhi);
+            const bool in_pml = in_x | in_y | in_z;          // one branch per nest for the interior points
             int qx = 0, qy = 0, qz = 0;
             double az = 0, bz = 0, Kz = 1, azh = 0, bzh = 0, Kzh = 1, rKz = 1, rKzh = 1;
             if (in_x) qx = ((k - 1) * p.ny + (j - 1)) * p.sxp + sx;
@@ -424,6 +459,24 @@ k_vvelocity3d(const __grid_constant__ ParamsV3D p)
             const int kmod = kg % p.nzl_e;
             const bool cut_up = (kmod == 0);
             const bool cut_dn = (kmod == 1);
+            if ((p.pf & 4) && (in_pml | (kg + 1 <= p.zlo) | (kg + 1 >= p.zhi))) {      // memory variables of the next plane into L2, see k_vstress3d
+                for (int d = (k == kb ? 0 : 1); d <= 1; ++d) {
+                    if (k + d > p.nzl) break;
+                    if (in_x) {
+                        const int qn = ((k + d - 1) * p.ny + (j - 1)) * p.sxp + sx;
+                        pf_l2(p.mx[3] + qn); pf_l2(p.mx[4] + qn); pf_l2(p.mx[5] + qn);
+                    }
+                    if (in_y) {
+                        const int qn = ((k + d - 1) * p.sy + sy) * pitch + (i - 1);
+                        pf_l2(p.my[3] + qn); pf_l2(p.my[4] + qn); pf_l2(p.my[5] + qn);
+                    }
+                    const int kgn = kg + d;
+                    if ((kgn <= p.zlo) || (kgn >= p.zhi)) {
+                        const int qn = ((vshell(kgn, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1);
+                        pf_l2(p.mz[3] + qn); pf_l2(p.mz[4] + qn); pf_l2(p.mz[5] + qn);
+                    }
+                }
+            }
 
             if (kg >= 2) {                                           // k2begin
                 if (do_vx) {                                         // :1244-1262
@@ -431,9 +484,11 @@ k_vvelocity3d(const __grid_constant__ ParamsV3D p)
                     double d2 = d4n(sxy_c, sxy_jm1, sxy_jp1, sxy_jm2, ody);
                     double d3 = d4n(sxz_c, sxz_m, cut_up ? 0.0 : sxz_p, sxz_mm, odz);
                     DIV24_3(d1, d2, d3);
-                    if (in_x) d1 = vcpml(p.mx[3], qx, cxc[1 * TX], cxc[0 * TX], cxc[2 * TX], cxc[3 * TX], d1);
-                    if (in_y) d2 = vcpml(p.my[3], qy, cyc[1 * TY], cyc[0 * TY], cyc[2 * TY], cyc[3 * TY], d2);
-                    if (in_z) d3 = vcpml(p.mz[3], qz, bz, az, Kz, rKz, d3);
+                    if (in_pml) {
+                        if (in_x) d1 = vcpml(p.mx[3], qx, cxc[1 * TX], cxc[0 * TX], cxc[2 * TX], cxc[3 * TX], d1);
+                        if (in_y) d2 = vcpml(p.my[3], qy, cyc[1 * TY], cyc[0 * TY], cyc[2 * TY], cyc[3 * TY], d2);
+                        if (in_z) d3 = vcpml(p.mz[3], qz, bz, az, Kz, rKz, d3);
+                    }
                     vx = dt_r * (d1 + d2 + d3) + vx;
                 }
                 if (do_vy) {                                         // :1266-1284
@@ -441,9 +496,11 @@ k_vvelocity3d(const __grid_constant__ ParamsV3D p)
                     double d2 = d4n(syy_jp1, syy_c, syy_jp2, syy_jm1, ody);
                     double d3 = d4n(syz_c, syz_m, cut_up ? 0.0 : syz_p, syz_mm, odz);
                     DIV24_3(d1, d2, d3);
-                    if (in_x) d1 = vcpml(p.mx[4], qx, cxc[5 * TX], cxc[4 * TX], cxc[6 * TX], cxc[7 * TX], d1);
-                    if (in_y) d2 = vcpml(p.my[4], qy, cyc[5 * TY], cyc[4 * TY], cyc[6 * TY], cyc[7 * TY], d2);
-                    if (in_z) d3 = vcpml(p.mz[4], qz, bz, az, Kz, rKz, d3);
+                    if (in_pml) {
+                        if (in_x) d1 = vcpml(p.mx[4], qx, cxc[5 * TX], cxc[4 * TX], cxc[6 * TX], cxc[7 * TX], d1);
+                        if (in_y) d2 = vcpml(p.my[4], qy, cyc[5 * TY], cyc[4 * TY], cyc[6 * TY], cyc[7 * TY], d2);
+                        if (in_z) d3 = vcpml(p.mz[4], qz, bz, az, Kz, rKz, d3);
+                    }
                     vy = dt_r * (d1 + d2 + d3) + vy;
                 }
             }
@@ -452,9 +509,11 @@ k_vvelocity3d(const __grid_constant__ ParamsV3D p)
                 double d2 = d4n(syz_c, syz_jm1, syz_jp1, syz_jm2, ody);
                 double d3 = d4n(szz_p, szz_c, szz_pp, cut_dn ? 0.0 : szz_m, odz);
                 DIV24_3(d1, d2, d3);
-                if (in_x) d1 = vcpml(p.mx[5], qx, cxc[5 * TX], cxc[4 * TX], cxc[6 * TX], cxc[7 * TX], d1);
-                if (in_y) d2 = vcpml(p.my[5], qy, cyc[1 * TY], cyc[0 * TY], cyc[2 * TY], cyc[3 * TY], d2);
-                if (in_z) d3 = vcpml(p.mz[5], qz, bzh, azh, Kzh, rKzh, d3);
+                if (in_pml) {
+                    if (in_x) d1 = vcpml(p.mx[5], qx, cxc[5 * TX], cxc[4 * TX], cxc[6 * TX], cxc[7 * TX], d1);
+                    if (in_y) d2 = vcpml(p.my[5], qy, cyc[1 * TY], cyc[0 * TY], cyc[2 * TY], cyc[3 * TY], d2);
+                    if (in_z) d3 = vcpml(p.mz[5], qz, bzh, azh, Kzh, rKzh, d3);
+                }
                 vz = dt_r * (d1 + d2 + d3) + vz;
             }
 
@@ -497,8 +556,8 @@ void visco_tile(int *tx, int *ty)
     if (!g_vtx) {
         const char *sx = getenv("CPML_VTX"), *sy = getenv("CPML_VTY"), *sp = getenv("CPML_VSPLIT"), *sm = getenv("CPML_VMINB");
         const char *sf = getenv("CPML_VPF");
-        g_vpf = sf ? atoi(sf) : 2;            // L2 prefetch mode of ParamsV3D::pf (stress kernel)
-        if (g_vpf < 0 || g_vpf > 2) g_vpf = 2;
+        g_vpf = sf ? atoi(sf) : 6;            // L2 prefetch mode of ParamsV3D::pf
+        if (g_vpf < 0 || g_vpf > 6 || (g_vpf & 3) == 3) g_vpf = 6;
         g_vtx = sx ? atoi(sx) : 32;
         g_vty = sy ? atoi(sy) : 8;
         g_vsplit = sp ? atoi(sp) : 0;         // 0: one stress launch per step (default), 1: normal and shear stresses in two launches
