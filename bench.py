@@ -145,6 +145,9 @@ def workload_label(name, p, kind, n_gpus):
 # reference arm / cpu baseline: the oracle's OpenMP build on the host cores
 # ------------------------------------------------------------------------------------
 
+_CPU_THREADS = None      # None: every core this process may run on; an int: that many (the 1-thread figure)
+
+
 def _use_all_host_threads():
     """torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm asks for the cores it may run on."""
     from oracle import oracle as O
@@ -152,7 +155,17 @@ def _use_all_host_threads():
         n = len(os.sched_getaffinity(0))
     except AttributeError:
         n = os.cpu_count() or 1
-    O.set_num_threads(n)
+    O.set_num_threads(n if _CPU_THREADS is None else _CPU_THREADS)
+
+
+def _one_thread(fn, *a):
+    """The same measurement with one OpenMP thread (report both)."""
+    global _CPU_THREADS
+    _CPU_THREADS = 1
+    try:
+        return fn(*a)
+    finally:
+        _CPU_THREADS = None
 
 
 def oracle_3d_gpts(p, nz_sample, steps, warmup):
@@ -456,19 +469,26 @@ def run_b200(args):
         }
         if args.cpu_baseline and world == 1:
             try:
+                one = None
                 if kind == "2dv":
-                    v, sec, cores = oracle_2dv_gpts(p, 1001, 6, 2)
-                    sample = "1001x1001 sample grid, 6 timed steps after 2, serial like the reference"
+                    v, sec, cores = oracle_2dv_gpts(p, 1001, 40, 2)
+                    sample = "1001x1001 sample grid, 40 timed steps after 2, serial like the reference"
                 elif kind == "3dv":
-                    v, sec, cores = oracle_3dv_gpts(p, 40, 4, 1)
-                    sample = f"{p.NX}x{min(p.NY, 256)}x40 reduced sample, 4 timed steps after 1, 4 emulated MPI slabs, FTZ/DAZ on"
+                    v, sec, cores = oracle_3dv_gpts(p, 80, 12, 2)
+                    sample = f"{p.NX}x{min(p.NY, 256)}x80 reduced sample, 12 timed steps after 2, 4 emulated MPI slabs, FTZ/DAZ on"
+                    one = _one_thread(oracle_3dv_gpts, p, 40, 3, 1)
                 elif kind == "3d":
-                    v, sec, cores = oracle_3d_gpts(p, 80, 6, 2)
-                    sample = f"{p.NX}x{p.NY}x80 z-reduced sample, 6 timed steps after 2, 2 emulated MPI slabs, FTZ/DAZ on"
+                    nz_s = min(160, p.NZ)
+                    v, sec, cores = oracle_3d_gpts(p, nz_s, 24, 2)
+                    sample = f"{p.NX}x{p.NY}x{nz_s} z-reduced sample, 24 timed steps after 2, 2 emulated MPI slabs, FTZ/DAZ on"
+                    one = _one_thread(oracle_3d_gpts, p, 40, 4, 1)
                 else:
-                    v, sec, cores = oracle_2d_gpts(p, 1024, 6, 2)
-                    sample = "1024x1024 sample grid, 6 timed steps after 2, serial like the reference"
-                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+                    v, sec, cores = oracle_2d_gpts(p, 1024, 40, 2)
+                    sample = "1024x1024 sample grid, 40 timed steps after 2, serial like the reference"
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                        "seconds": sec}
+                if one is not None:
+                    line["cpu_baseline"]["one_thread"] = {"value": one[0], "cores": one[2], "seconds": one[1]}
             except Exception as exc:   # the oracle is only the yardstick; never fail the GPU number on it
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
         print(json.dumps(line), flush=True)
