@@ -7,6 +7,11 @@
 //   xseismic_cpml --program 3d_iso      == seismic_CPML_3D_isotropic_MPI_OpenMP.f90
 //   xseismic_cpml --program 2d_second   == seismic_CPML_2D_isotropic_second_order.f90
 //   xseismic_cpml --program 2d_fourth   == seismic_CPML_2D_isotropic_fourth_order.f90
+//   xseismic_cpml --program 3d_visco    == seismic_CPML_3D_viscoelastic_MPI.f90
+//   xseismic_cpml --program 2d_visco_second | 2d_visco_fourth
+//                                       == seismic_CPML_2D_velocity_and_stress_{second,fourth}_order_viscoelastic.f90
+// (the viscoelastic programs also take NPROC= QKappa_att= QMu_att= f0_attenuation= / Qp= Qs= xsource=
+//  ysource= COMPUTE_ENERGY= ; their relaxation times come from the SolvOpt fit like in the reference)
 // Parameters are the Fortran `parameter` names given as NAME=value on the command line
 // (the reference edits them in the source and recompiles): NX= NY= NZ= NSTEP= DELTAX=
 // DELTAT= NPOINTS_PML= ISOURCE= JSOURCE= NREC= IT_DISPLAY= f0= factor= ANGLE_FORCE= cp= rho=
@@ -50,6 +55,206 @@ struct Profile {
     explicit Profile(int n) : a(n), b(n), K(n), a_half(n), b_half(n), K_half(n) {}
 };
 
+void set_profiles(cpml_handle *h, int axis, const Profile &p, int n)
+{
+    CHECK(h, cpml_set_profiles(h, axis, p.a.data(), p.b.data(), p.K.data(), p.a_half.data(), p.b_half.data(), p.K_half.data(), n));
+}
+
+// compute_attenuation_coeffs for the two modes (3D-visco :433-443, 2D-visco-4th :366-376)
+void fit_attenuation(int n_sls, double q1, double q2, double f0_att, std::vector<double> (&tau)[4])
+{
+    const double f_min = std::exp(std::log(f0_att) - std::log(12.0) / 2.0), f_max = 12.0 * f_min;
+    for (auto &t : tau) t.assign(n_sls, 0.0);
+    double info[4];
+    if (cpml_host_attenuation_fit(n_sls, q1, f0_att, f_min, f_max, tau[0].data(), tau[1].data(), info) != CPML_OK ||
+        cpml_host_attenuation_fit(n_sls, q2, f0_att, f_min, f_max, tau[2].data(), tau[3].data(), info) != CPML_OK) {
+        fprintf(stderr, "attenuation fit failed\n");
+        exit(1);
+    }
+    const char *names[4] = {"tau_epsilon_nu1", "tau_sigma_nu1", "tau_epsilon_nu2", "tau_sigma_nu2"};
+    for (int k = 0; k < 4; k++) {
+        printf(" %s =", names[k]);
+        for (double v : tau[k]) printf(" %.16g", v);
+        printf("\n");
+    }
+    printf("\n");
+}
+
+// ---- the viscoelastic programs ------------------------------------------------------------------
+int run_visco(const Args &A)
+{
+    const bool is3d = A.program == "3d_visco";
+    const int order = is3d ? 4 : (A.program == "2d_visco_fourth" ? 4 : 2);
+    // parameter block: 3D-visco :152-244 ; 2D-visco-4th :140-230
+    const int NX = A.geti("NX", is3d ? 210 : 2001), NY = A.geti("NY", is3d ? 800 : 2001), NZ = is3d ? A.geti("NZ", 220) : 1;
+    const int NPROC = A.geti("NPROC", 4);
+    const double DELTAX = A.get("DELTAX", is3d ? 4.0 : 1.5), DELTAY = A.get("DELTAY", DELTAX), DELTAZ = A.get("DELTAZ", DELTAX);
+    const double cp = A.get("cp", is3d ? 3000.0 : 2000.0), cs = A.get("cs", is3d ? 2000.0 : cp / 1.732), rho = A.get("rho", 2000.0);
+    const int NSTEP = A.geti("NSTEP", is3d ? 100000 : 5200);
+    const double DELTAT = A.get("DELTAT", is3d ? 4.e-4 : 2.2e-4);
+    const double f0 = A.get("f0", is3d ? 18.0 : 35.0), t0 = A.get("t0", 1.20 / f0), factor = A.get("factor", is3d ? 1.e7 : 1.0);
+    const int NPOINTS_PML = A.geti("NPOINTS_PML", 10);
+    const double xs2d = A.get("xsource", 1500.0), ys2d = A.get("ysource", 1500.0);
+    const int ISOURCE = A.geti("ISOURCE", is3d ? NPOINTS_PML + 20 : (int)(xs2d / DELTAX + 1));
+    const int JSOURCE = A.geti("JSOURCE", is3d ? NY / 5 + 1 : (int)(ys2d / DELTAY + 1));
+    const double ANGLE_FORCE = A.get("ANGLE_FORCE", 0.0);
+    const int NREC = A.geti("NREC", is3d ? 3 : 1);
+    const int IT_DISPLAY = A.geti("IT_DISPLAY", is3d ? 10000 : 200);
+    const double NPOWER = 2.0, K_MAX_PML = A.get("K_MAX_PML", is3d ? 7.0 : 1.0), ALPHA_MAX_PML = 2.0 * PI * (f0 / 2.0);
+    const double Rcoef = is3d ? 0.0001 : 0.001;
+    const int N_SLS = is3d ? 2 : 3;
+    const int COMPUTE_ENERGY = is3d ? 1 : A.geti("COMPUTE_ENERGY", 0);
+
+    printf("\n %s viscoelastic finite-difference code in velocity and stress formulation with C-PML\n\n", is3d ? "3D" : "2D");
+    printf(" NX = %d\n NY = %d\n", NX, NY);
+    if (is3d) printf(" NZ = %d\n", NZ);
+    printf("\n Total number of grid points = %lld\n\n", (long long)NX * NY * NZ);
+
+    std::vector<double> tau[4];
+    if (is3d) fit_attenuation(N_SLS, A.get("QKappa_att", 20.0), A.get("QMu_att", 10.0), A.get("f0_attenuation", 16.0), tau);
+    else      fit_attenuation(N_SLS, A.get("Qp", 65.0), A.get("Qs", 55.0), f0, tau);
+
+    Profile px(NX), py(NY), pz(is3d ? NZ : 1);
+    double courant;
+    double cp_cfl = 0.0;
+    if (is3d) {
+        double taumax = 0.0;                                               // :450-456
+        for (int l = 0; l < N_SLS; l++) {
+            taumax = std::max(taumax, 1.0 / (tau[1][l] / tau[0][l]));
+            taumax = std::max(taumax, 1.0 / (tau[3][l] / tau[2][l]));
+        }
+        const double sq = std::sqrt(taumax);
+        auto prof = [&](int n, double d, int clamp, Profile &p) {
+            cpml_host_pml_profile_visco(n, d, DELTAT, NPOINTS_PML, 1, 1, cp, sq, Rcoef, NPOWER, K_MAX_PML, ALPHA_MAX_PML, 0, clamp,
+                                        p.a.data(), p.b.data(), p.K.data(), p.a_half.data(), p.b_half.data(), p.K_half.data());
+        };
+        prof(NX, DELTAX, 1, px); prof(NY, DELTAY, 0, py); prof(NZ, DELTAZ, 0, pz);
+        cp_cfl = cp * sq;
+        courant = cpml_host_courant(cp_cfl, DELTAT, DELTAX, DELTAY, DELTAZ);                            // :856
+        if (courant > 1.0) { fprintf(stderr, "time step is too large, simulation will be unstable\n"); return 1; }
+    } else {
+        auto prof = [&](int n, double d, int clamp, Profile &p) {
+            cpml_host_pml_profile(n, d, DELTAT, NPOINTS_PML, 1, 1, cp, Rcoef, NPOWER, K_MAX_PML, ALPHA_MAX_PML, 0, clamp,
+                                  p.a.data(), p.b.data(), p.K.data(), p.a_half.data(), p.b_half.data(), p.K_half.data());
+        };
+        prof(NX, DELTAX, 1, px); prof(NY, DELTAY, 0, py);
+        courant = cp * DELTAT / DELTAX;                                                                 // :654
+        if (DELTAX == DELTAY && courant > (order == 4 ? 0.606 : 1.0 / std::sqrt(2.0))) {
+            fprintf(stderr, "time step is too large, simulation will be unstable\n"); return 1;
+        }
+    }
+    printf(" Courant number is %.15g\n\n", courant);
+
+    // source time function: first derivative of a Gaussian (3-D, :1310-1335) / Ricker over the cell area (2-D, :931-958)
+    std::vector<double> force_x(NSTEP), force_y(NSTEP);
+    if (is3d) cpml_host_source_series(NSTEP, DELTAT, f0, t0, factor, ANGLE_FORCE, force_x.data(), force_y.data());
+    else {
+        const double a = PI * PI * f0 * f0, rad = ANGLE_FORCE * (PI / 180.0);
+        for (int it = 1; it <= NSTEP; it++) {
+            const double t = (double)(it - 1) * DELTAT;
+            double term = factor * (1.0 - 2.0 * a * ((t - t0) * (t - t0))) * std::exp(-a * ((t - t0) * (t - t0)));
+            term = term / (DELTAX * DELTAY);
+            force_x[it - 1] = std::sin(rad) * term;
+            force_y[it - 1] = std::cos(rad) * term;
+        }
+    }
+    // receivers: explicit targets (3-D, :825-853) / a line (2-D, :187-199)
+    std::vector<int32_t> ix_rec(NREC), iy_rec(NREC);
+    std::vector<double> dist(NREC);
+    if (is3d) {
+        const double xs = ISOURCE * DELTAX, ys = JSOURCE * DELTAY;                                      // :207-208
+        std::vector<double> xr = {xs + 500.0, xs, xs + 500.0}, yr = {ys + 500.0, ys + 2260.0, ys + 2260.0};
+        xr.resize(NREC, xs); yr.resize(NREC, ys);
+        for (int r = 0; r < NREC; r++) {
+            char kx[16], ky[16];
+            snprintf(kx, sizeof kx, "xrec%d", r + 1); snprintf(ky, sizeof ky, "yrec%d", r + 1);
+            xr[r] = A.get(kx, xr[r]); yr[r] = A.get(ky, yr[r]);
+        }
+        cpml_host_find_receivers_at(NX, NY, DELTAX, DELTAY, NREC, xr.data(), yr.data(), 1, ix_rec.data(), iy_rec.data(), dist.data());
+    } else {
+        cpml_host_find_receivers(NX, NY, DELTAX, DELTAY, NREC, A.get("xdeb", 2301.0), A.get("ydeb", 2301.0),
+                                 A.get("xfin", 2301.0), A.get("yfin", 2301.0), ix_rec.data(), iy_rec.data(), dist.data());
+    }
+    for (int r = 0; r < NREC; r++)
+        printf(" receiver %d closest grid point found at distance %g in i,j = %d %d\n", r + 1, dist[r], ix_rec[r], iy_rec[r]);
+    printf("\n");
+
+    cpml_config cfg{};
+    cfg.ndim = is3d ? 3 : 2; cfg.order = order; cfg.rheology = 1;
+    cfg.nx = NX; cfg.ny = NY; cfg.nz = NZ; cfg.nstep = NSTEP; cfg.npoints_pml = NPOINTS_PML; cfg.nrec = NREC;
+    cfg.isource = ISOURCE; cfg.jsource = JSOURCE; cfg.ksource = 0; cfg.nslabs = 1; cfg.slab_rank = 0; cfg.device = -1;
+    cfg.energy_bug_compat = 1;
+    cfg.deltax = DELTAX; cfg.deltay = DELTAY; cfg.deltaz = DELTAZ; cfg.deltat = DELTAT;
+    if (is3d) {
+        cfg.emulate_nproc = NPROC;
+        cfg.lambda = rho * (cp * cp - 2.0 * cs * cs); cfg.mu = rho * cs * cs; cfg.rho = rho; cfg.cp = cp_cfl;
+    } else {
+        cfg.compute_energy = COMPUTE_ENERGY;
+    }
+    cpml_handle *h = nullptr;
+    CHECK(nullptr, cpml_create(&cfg, &h));
+    set_profiles(h, CPML_AXIS_X, px, NX);
+    set_profiles(h, CPML_AXIS_Y, py, NY);
+    if (is3d) set_profiles(h, CPML_AXIS_Z, pz, NZ);
+    else {
+        const size_t n = (size_t)NX * NY;                       // homogeneous unrelaxed medium, :596-602
+        const double mu = rho * cs * cs;
+        std::vector<double> lam(n, rho * cp * cp - 2.0 * mu), muv(n, mu), rh(n, rho);
+        CHECK(h, cpml_set_material_2d(h, lam.data(), muv.data(), rh.data()));
+    }
+    CHECK(h, cpml_set_attenuation(h, N_SLS, tau[0].data(), tau[1].data(), tau[2].data(), tau[3].data()));
+    CHECK(h, cpml_set_source_series(h, force_x.data(), force_y.data(), NSTEP));
+    CHECK(h, cpml_set_receivers(h, ix_rec.data(), iy_rec.data(), NREC));
+
+    std::vector<double> sisvx((size_t)NSTEP * NREC), sisvy((size_t)NSTEP * NREC), sisp((size_t)NSTEP * NREC);
+    std::vector<double> e_tot(NSTEP), e_kin(NSTEP), e_pot(NSTEP), plane((size_t)NX * NY);
+    const auto t_start = std::chrono::steady_clock::now();
+    auto write_all = [&]() {
+        CHECK(h, cpml_get_seismograms(h, sisvx.data(), sisvy.data()));
+        if (!is3d) CHECK(h, cpml_get_pressure_seismograms(h, sisp.data()));
+        cpml_host_write_seismograms_visco(A.out.c_str(), sisvx.data(), sisvy.data(), is3d ? nullptr : sisp.data(), NSTEP, NREC, DELTAT, t0);
+    };
+    int it_begin = 1;
+    while (it_begin <= NSTEP) {
+        int it_end = std::min(NSTEP, (it_begin / IT_DISPLAY + 1) * IT_DISPLAY);
+        if (it_begin <= 5 && it_end > 5) it_end = 5;
+        CHECK(h, cpml_run(h, it_begin, it_end));
+        const int it = it_end;
+        if (it % IT_DISPLAY == 0 || it == 5) {
+            double vnorm = 0.0;
+            CHECK(h, cpml_get_maxnorm(h, &vnorm));
+            const double tcpu = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+            printf(" Time step # %d out of %d\n Time: %g seconds\n Max norm velocity vector V (m/s) = %.15g\n", it, NSTEP,
+                   (double)(float)((it - 1) * DELTAT), vnorm);
+            if (COMPUTE_ENERGY) {
+                CHECK(h, cpml_get_energy(h, e_tot.data(), e_kin.data(), e_pot.data()));
+                printf(" Total energy = %.15g\n", e_tot[it - 1]);
+            }
+            printf(" Elapsed time in seconds = %g\n Mean elapsed time per time step in seconds = %g\n\n", tcpu, tcpu / it);
+            if (vnorm > STABILITY_THRESHOLD || !std::isfinite(vnorm)) { fprintf(stderr, "code became unstable and blew up\n"); return 1; }
+            write_all();
+            if (A.images)
+                for (int f = 0; f < 2; f++) {
+                    CHECK(h, cpml_get_plane(h, f, is3d ? NZ / 2 : 0, plane.data()));
+                    cpml_host_create_color_image(A.out.c_str(), plane.data(), NX, NY, it, ISOURCE, JSOURCE, ix_rec.data(),
+                                                 iy_rec.data(), NREC, NPOINTS_PML, 1, 1, 1, 1, f + 1);
+                }
+        }
+        it_begin = it_end + 1;
+    }
+    write_all();
+    if (COMPUTE_ENERGY) {
+        CHECK(h, cpml_get_energy(h, e_tot.data(), e_kin.data(), e_pot.data()));
+        const std::string epath = A.out + "/energy.dat";
+        cpml_host_write_energy_2d(epath.c_str(), e_kin.data(), e_pot.data(), NSTEP, DELTAT);   // time, kinetic, potential, total
+    }
+    const double tcpu = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+    printf(" Total elapsed time = %g s, %.3f Gpts/s\n", tcpu, (double)NX * NY * NZ * NSTEP / tcpu / 1e9);
+    cpml_destroy(h);
+    printf("\n End of the simulation\n\n");
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char **argv)
@@ -63,6 +268,7 @@ int main(int argc, char **argv)
         else if (s.find('=') != std::string::npos) A.kv[s.substr(0, s.find('='))] = atof(s.c_str() + s.find('=') + 1);
         else { fprintf(stderr, "unknown argument %s\n", s.c_str()); return 2; }
     }
+    if (A.program == "3d_visco" || A.program == "2d_visco_second" || A.program == "2d_visco_fourth") return run_visco(A);
     const bool is3d = A.program == "3d_iso";
     const bool fourth = A.program == "2d_fourth";
     if (!is3d && !fourth && A.program != "2d_second") { fprintf(stderr, "unknown program %s\n", A.program.c_str()); return 2; }

@@ -397,6 +397,17 @@ module cpml_b200
       integer(c_int32_t) :: ierr
     end function
 
+    function cpml_host_write_seismograms_visco(dir, sisvx, sisvy, sispressure, nt, nrec, deltat, t0) &
+        bind(C, name='cpml_host_write_seismograms_visco') result(ierr)
+      import :: c_int32_t, c_double, c_char, c_ptr
+      character(kind=c_char), intent(in) :: dir(*)
+      real(c_double), intent(in) :: sisvx(*), sisvy(*)
+      type(c_ptr), value :: sispressure        ! c_loc(sispressure) in the 2-D programs, c_null_ptr in 3-D
+      integer(c_int32_t), value :: nt, nrec
+      real(c_double), value :: deltat, t0
+      integer(c_int32_t) :: ierr
+    end function
+
     function cpml_host_write_energy_3d(path, total, nt, deltat) bind(C, name='cpml_host_write_energy_3d') result(ierr)
       import :: c_int32_t, c_double, c_char
       character(kind=c_char), intent(in) :: path(*)

@@ -331,6 +331,13 @@ double cpml_host_courant(double cp, double deltat, double deltax, double deltay,
  * specific; these write gnuplot-parsable text with the same columns. */
 int32_t cpml_host_write_seismograms(const char *dir, const double *sisvx, const double *sisvy,
                                     int32_t nt, int32_t nrec, double deltat);
+/* The viscoelastic programs' write_seismograms: time axis minus t0 (3D-visco :1596-1616); with
+ * sispressure != NULL the 2-D form (2D-visco-4th :1145-1193): Vx_file_NNN.dat,
+ * Vy_file_half_a_grid_cell_away_from_Vx_NNN.dat and pressure_file_NNN.dat (time + DELTAT/2), the
+ * files plotall_fit_is_perfect_for_viscoelastic_fourth_order.gnu reads. */
+int32_t cpml_host_write_seismograms_visco(const char *dir, const double *sisvx, const double *sisvy,
+                                          const double *sispressure, int32_t nt, int32_t nrec,
+                                          double deltat, double t0);
 int32_t cpml_host_write_energy_3d(const char *path, const double *total, int32_t nt,
                                   double deltat);
 int32_t cpml_host_write_energy_2d(const char *path, const double *kinetic,

@@ -188,6 +188,35 @@ extern "C" int32_t cpml_host_write_seismograms(const char *dir, const double *si
     return CPML_OK;
 }
 
+// write_seismograms of the viscoelastic programs: the time axis is shifted by -t0 (3D-visco :1603,1613;
+// 2D-visco-4th :1178,1188); the 2-D programs also record the pressure, which their scheme holds half a
+// time step later (:1164-1168), and name the Vy file after its staggered position (:1184)
+extern "C" int32_t cpml_host_write_seismograms_visco(const char *dir, const double *sisvx, const double *sisvy,
+                                                     const double *sispressure, int32_t nt, int32_t nrec,
+                                                     double deltat, double t0)
+{
+    if (!sisvx || !sisvy || nt < 1 || nrec < 0) return CPML_EINVAL;
+    const bool two_d = sispressure != nullptr;
+    for (int comp = 0; comp < (two_d ? 3 : 2); comp++) {
+        const double *sis = comp == 0 ? sisvx : comp == 1 ? sisvy : sispressure;
+        const char *fmt = comp == 0 ? "Vx_file_%03d.dat"
+                        : comp == 1 ? (two_d ? "Vy_file_half_a_grid_cell_away_from_Vx_%03d.dat" : "Vy_file_%03d.dat")
+                                    : "pressure_file_%03d.dat";
+        const double shift = comp == 2 ? deltat / 2.0 : 0.0;
+        for (int32_t r = 1; r <= nrec; r++) {
+            char name[96];
+            snprintf(name, sizeof name, fmt, r);
+            FILE *f = fopen(join(dir, name).c_str(), "w");
+            if (!f) return CPML_EINVAL;
+            for (int32_t it = 1; it <= nt; it++)
+                fprintf(f, "  %.8E   %.8E\n", (double)(float)((double)(it - 1) * deltat - t0 + shift),
+                        (double)(float)sis[(size_t)(r - 1) * nt + (it - 1)]);
+            fclose(f);
+        }
+    }
+    return CPML_OK;
+}
+
 extern "C" int32_t cpml_host_write_energy_3d(const char *path, const double *total, int32_t nt, double deltat)
 {
     if (!path || !total) return CPML_EINVAL;

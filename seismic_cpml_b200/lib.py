@@ -103,6 +103,7 @@ SYMBOLS = {
     "cpml_host_attenuation_fit": (C.c_int32, [C.c_int32] + [C.c_double] * 4 + [_dp, _dp, _dp]),
     "cpml_host_attenuation_fit_linear": (C.c_int32, [C.c_int32] + [C.c_double] * 3 + [_dp, _dp]),
     "cpml_host_write_seismograms": (C.c_int32, [C.c_char_p, _dp, _dp, C.c_int32, C.c_int32, C.c_double]),
+    "cpml_host_write_seismograms_visco": (C.c_int32, [C.c_char_p, _dp, _dp, _dp, C.c_int32, C.c_int32, C.c_double, C.c_double]),
     "cpml_host_write_energy_3d": (C.c_int32, [C.c_char_p, _dp, C.c_int32, C.c_double]),
     "cpml_host_write_energy_2d": (C.c_int32, [C.c_char_p, _dp, _dp, C.c_int32, C.c_double]),
     "cpml_host_create_color_image": (C.c_int32, [C.c_char_p, _dp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -606,7 +606,8 @@ class Program3DVisco(_ProgramBase):
         total, ek, ep = self.solver.get_energy()
         if self.output_dir is not None:
             os.makedirs(self.output_dir, exist_ok=True)
-            self.write_seismograms()
+            _lib.load().cpml_host_write_seismograms_visco(self.output_dir.encode(), _lib._d(sx), _lib._d(sy), None,
+                                                          self.p.NSTEP, self.p.NREC, self.p.DELTAT, self.p.t0)   # :1596-1616
             with open(os.path.join(self.output_dir, "energy.dat"), "w") as f:      # :1478-1483, four columns
                 for it in range(self.p.NSTEP):
                     f.write(f" {np.float32(it * self.p.DELTAT)} {np.float32(ek[it])} {np.float32(ep[it])} {np.float32(total[it])}\n")
@@ -660,17 +661,10 @@ class Program2DVisco(_ProgramBase):
         sp = self.solver.get_pressure_seismograms()
         total, ek, ep = self.solver.get_energy()
         if self.output_dir is not None:
-            # write_seismograms of 2D-visco-4th :1145-1193: time axis shifted by -t0 (and by +DELTAT/2 for the
-            # pressure, which is staggered in time, :1164-1168); the file names are the ones the reference's
+            # write_seismograms of 2D-visco-4th :1145-1193: the files the reference's
             # plotall_fit_is_perfect_for_viscoelastic_fourth_order.gnu reads
             os.makedirs(self.output_dir, exist_ok=True)
-            p = self.p
-            for r in range(p.NREC):
-                for name, series, shift in ((f"pressure_file_{r + 1:03d}.dat", sp[r], 0.5 * p.DELTAT),
-                                            (f"Vx_file_{r + 1:03d}.dat", sx[r], 0.0),
-                                            (f"Vy_file_half_a_grid_cell_away_from_Vx_{r + 1:03d}.dat", sy[r], 0.0)):
-                    with open(os.path.join(self.output_dir, name), "w") as f:
-                        for it in range(p.NSTEP):
-                            f.write(f" {np.float32(it * p.DELTAT - p.t0 + shift)}   {np.float32(series[it])}\n")
+            _lib.load().cpml_host_write_seismograms_visco(self.output_dir.encode(), _lib._d(sx), _lib._d(sy), _lib._d(sp),
+                                                          self.p.NSTEP, self.p.NREC, self.p.DELTAT, self.p.t0)
         return dict(sisvx=sx, sisvy=sy, sispressure=sp, energy_kinetic=ek, energy_potential=ep,
                     display_log=self.display_log)

@@ -109,3 +109,67 @@ def test_cpp_driver_3d_small_grid(driver_exe, tmp_path):
     e = np.loadtxt(tmp_path / "energy.dat")
     assert d.shape == (120, 2) and e.shape == (120, 2) and np.abs(d[:, 1]).max() > 0 and np.all(np.isfinite(e))
     assert os.path.exists(tmp_path / "image000100_Vy.pnm")
+
+
+def test_cpp_driver_viscoelastic_setup_uses_the_solvopt_fit(driver_exe, tmp_path):
+    """The viscoelastic programs of the C++ driver: set-up phase on the host (relaxation times from the
+    SolvOpt fit, printed like the reference does at 3D-visco :445-455), then the same loud failure without
+    a GPU."""
+    r = subprocess.run([driver_exe, "--program", "2d_visco_fourth", "NSTEP=4", "--out", str(tmp_path), "--no-images"],
+                       capture_output=True, text=True)
+    # the reference's own constants (analytical program :124-128)
+    assert "tau_epsilon_nu1 = 0.02408158185753685 0.004699608990861351 0.0009567997872435925" in r.stdout
+    assert "tau_sigma_nu2 = 0.0225091977942949 0.004501388007338097 0.0008917332095369118" in r.stdout
+    assert "in i,j = 1535 1535" in r.stdout and "Courant number is 0.293333333333333" in r.stdout
+    r3 = subprocess.run([driver_exe, "--program", "3d_visco", "NX=40", "NY=50", "NZ=40", "NSTEP=4", "--out", str(tmp_path),
+                         "--no-images"], capture_output=True, text=True)
+    assert "tau_epsilon_nu1 = 0.03433147438440785 0.003631112527072353" in r3.stdout
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        assert r.returncode != 0 and "no CPU fallback" in r.stderr
+        assert r3.returncode != 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("program,order", [("2d_visco_second", 2), ("2d_visco_fourth", 4)])
+def test_cpp_driver_2d_viscoelastic_output_files_match_oracle(driver_exe, tmp_path, program, order):
+    from seismic_cpml_b200 import programs as P
+    kw = dict(NX=121, NY=101, NSTEP=200, xsource=90.0, ysource=75.0, xdeb=120.0, ydeb=100.0, xfin=120.0, yfin=100.0)
+    args = [f"{k}={v}" for k, v in kw.items()]
+    r = subprocess.run([driver_exe, "--program", program, *args, "IT_DISPLAY=100", "--out", str(tmp_path)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "End of the simulation" in r.stdout
+    p = P.Params2DVisco(order=order, **kw)
+    s = P.setup_2d_visco(p)
+    o = O.run_2d_visco(order=order, nx=p.NX, ny=p.NY, deltax=p.DELTAX, deltay=p.DELTAY, deltat=p.DELTAT, nstep=p.NSTEP,
+                       npoints_pml=p.NPOINTS_PML, isource=p.ISOURCE, jsource=p.JSOURCE, lam=s.material[0], mu=s.material[1],
+                       rho=s.material[2], tau_epsilon_nu1=p.tau_epsilon_nu1, tau_sigma_nu1=p.tau_sigma_nu1,
+                       tau_epsilon_nu2=p.tau_epsilon_nu2, tau_sigma_nu2=p.tau_sigma_nu2, prof_x=s.prof_x, prof_y=s.prof_y,
+                       force_x=s.force_x, force_y=s.force_y, ix_rec=s.ix_rec, iy_rec=s.iy_rec)
+    for name, key, shift in (("Vx_file_001.dat", "sisvx", 0.0), ("Vy_file_half_a_grid_cell_away_from_Vx_001.dat", "sisvy", 0.0),
+                             ("pressure_file_001.dat", "sispressure", 0.5 * p.DELTAT)):
+        d = np.loadtxt(tmp_path / name)
+        assert d.shape == (p.NSTEP, 2)
+        assert np.abs(o[key][0]).max() > 0
+        assert np.array_equal(d[:, 1].astype(np.float32), o[key][0].astype(np.float32)), name
+        # time axis of write_seismograms (2D-visco-4th :1168,1178): (it-1) DELTAT - t0 (+ DELTAT/2 for the pressure)
+        assert np.allclose(d[:, 0], np.arange(p.NSTEP) * p.DELTAT - p.t0 + shift, rtol=0, atol=1e-7)
+    assert os.path.exists(tmp_path / "image000100_Vx.pnm")
+
+
+@pytest.mark.gpu
+def test_cpp_driver_3d_viscoelastic_small_grid(driver_exe, tmp_path):
+    r = subprocess.run([driver_exe, "--program", "3d_visco", "NX=60", "NY=80", "NZ=48", "NSTEP=60", "NPROC=2", "IT_DISPLAY=50",
+                        "xrec1=200", "yrec1=200", "xrec2=160", "yrec2=240", "xrec3=200", "yrec3=240", "--out", str(tmp_path)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    d = np.loadtxt(tmp_path / "Vy_file_001.dat")
+    e = np.loadtxt(tmp_path / "energy.dat")
+    assert d.shape == (60, 2) and e.shape == (60, 4) and np.abs(d[:, 1]).max() > 0 and np.all(np.isfinite(e))
+    assert d[0, 0] == pytest.approx(-1.2 / 18.0, rel=1e-6)          # time axis minus t0 (3D-visco :1603)
+    assert "Total energy =" in r.stdout
