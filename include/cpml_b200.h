@@ -226,8 +226,9 @@ int32_t cpml_p2p_attach_local(cpml_handle *h, int32_t side, cpml_handle *neighbo
 int32_t cpml_p2p_detach(cpml_handle *h);
 
 /* Launch geometry chosen for the 3-D kernels (diagnostics for bench.py / profiles):
- * info[0..9] = uses_tma, tile_x, tile_y, stages, planes per work item, z chunks, work items,
- * CTAs of the stress kernel, CTAs of the velocity kernel, attached sides bit mask. */
+ * info[0..9] = uses_tma, tile_x, tile_y, stages, planes per work item, z chunks, work items (velocity
+ * kernel), CTAs of the stress kernel, CTAs of the velocity kernel, attached sides bit mask;
+ * info[10..13] = tile_y, planes per work item, z chunks, work items of the stress kernel. */
 int32_t cpml_get_launch_info(cpml_handle *h, int32_t *info, int32_t n);
 
 /* ---- outputs (device -> driver) ------------------------------------------- */

@@ -57,7 +57,7 @@ struct cpml_handle {
     // TMA path (3-D): descriptors of the two kernels' plane tiles, work decomposition
     bool use_tma = false;
     TmaMaps maps_stress{}, maps_velocity{};
-    Tile3D tile{};
+    Tile3D tile{}, tile_stress{};        // velocity kernel (also: energy partial slots) / stress kernel
 
     // slab neighbours reached by direct peer stores (cpml_p2p_*): side 0 = rank-1, 1 = rank+1
     bool peer_on[2] = {false, false};
@@ -623,21 +623,17 @@ static int32_t encode_plane_map(cpml_handle *h, EncodeTiledFn enc, CUtensorMap *
     return CPML_OK;
 }
 
-static int32_t setup_tma(cpml_handle *h)
+// One kernel's tile, TMA descriptors and work decomposition.  The two kernels get their own: on the
+// 101-wide default grid the stress kernel is fastest on 104 x 7 tiles (384 threads = 12 warps, three per SM
+// sub-partition: 168 registers instead of 128, no spills; 1.02 ms against 1.12 ms), the velocity kernel on
+// 104 x 8 (1.04 ms against 1.10 ms) -- profiles/r01_v8_tile_104x7.txt.
+static int32_t build_tile(cpml_handle *h, EncodeTiledFn enc, bool stress, Tile3D &t, TmaMaps &maps)
 {
     const cpml_config &c = h->cfg;
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-    if (!fn || qres != cudaDriverEntryPointSuccess) FAIL(CPML_ECUDA, "driver does not export cuTensorMapEncodeTiled");
-    const EncodeTiledFn enc = (EncodeTiledFn)fn;
-
-    // thread tile = TMA box.  Narrow grids (the reference's NX = 101) take one 104-wide tile
-    // per row; wide grids 64 x 8.  CPML_TX / CPML_TY / CPML_STAGES override (bench sweeps).
-    Tile3D &t = h->tile;
-    // default: the tile width that wastes the fewest columns (ties: the wider one), 8 rows;
-    // measured in profiles/r01_v5_tile_sweep.txt: 104 x 8 on the 101-wide default grid, 128 x 8
-    // on 1024-wide slabs, one 416- / 512-thread CTA per SM, two-plane ring
+    // thread tile = TMA box.  Narrow grids (the reference's NX = 101) take one 104-wide tile per row, wide
+    // grids 128 x 8: the width that wastes the fewest columns (ties: the wider one), measured in
+    // profiles/r01_v5_tile_sweep.txt; one CTA per SM, two-plane ring.  CPML_TX / CPML_TY / CPML_STAGES /
+    // CPML_ZCHUNKS override both kernels, CPML_TY_STRESS / CPML_ZCHUNKS_STRESS the stress kernel alone.
     int best_tx = 128;
     for (int cand : {104, 64}) {
         const int w_best = (c.nx + best_tx - 1) / best_tx * best_tx, w = (c.nx + cand - 1) / cand * cand;
@@ -645,21 +641,24 @@ static int32_t setup_tma(cpml_handle *h)
     }
     t.tx = env_int("CPML_TX", best_tx);
     t.ty = env_int("CPML_TY", 8);
+    if (stress) t.ty = env_int("CPML_TY_STRESS", (t.tx == 104 && t.ty == 8) ? 7 : t.ty);
     if (!tma_tile_supported(t.tx, t.ty)) FAIL(CPML_EINVAL, "unsupported CPML_TX x CPML_TY tile");
     t.stages = std::max(1, std::min(7, env_int("CPML_STAGES", 2)));
     t.minb = std::max(1, std::min(4, env_int("CPML_MINB", t.tx == 64 ? 2 : 1)));
+    if (t.ty == 7) t.minb = 1;
     t.xm_bytes = h->shell[0].size() > 0 ? round_up(t.ty * h->sxp * 8, 128) : 0;
     t.ntx = (c.nx + t.tx - 1) / t.tx;
     t.nty = (c.ny + t.ty - 1) / t.ty;
 
-    // descriptors: 0 vx 1 vy 2 vz 3 sxx 4 syy 5 szz 6 sxy 7 sxz 8 syz
+    // descriptors: stress 0 vx 1 vy 2 vz 3 sxx 4 syy 5 szz 6 sxy 7 sxz 8 syz (three halo boxes);
+    // velocity 0 sxx 1 syy 2 sxy 3 sxz 4 syz 5 szz 6 vx 7 vy 8 vz (five halo boxes)
     const int hx = t.tx + 2, hy = t.ty + 1;
     const int stress_field[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};
     const int velocity_field[9] = {3, 4, 6, 7, 8, 5, 0, 1, 2};
+    const int nhalo = stress ? 3 : 5;
     for (int m = 0; m < 9; m++) {
-        int32_t rc = encode_plane_map(h, enc, &h->maps_stress.m[m], stress_field[m], m < 3 ? hx : t.tx, m < 3 ? hy : t.ty);
-        if (rc) return rc;
-        rc = encode_plane_map(h, enc, &h->maps_velocity.m[m], velocity_field[m], m < 5 ? hx : t.tx, m < 5 ? hy : t.ty);
+        const int32_t rc = encode_plane_map(h, enc, &maps.m[m], stress ? stress_field[m] : velocity_field[m],
+                                            m < nhalo ? hx : t.tx, m < nhalo ? hy : t.ty);
         if (rc) return rc;
     }
 
@@ -670,40 +669,61 @@ static int32_t setup_tma(cpml_handle *h)
         for (int q : {2, 5})
             for (double K : h->hprof[ax][q])
                 if (K != 1.0) p.kunit = 0;
-    int occ_s = 0, occ_v = 0;
+    int occ = 0;
     while (true) {
-        cudaError_t e1 = tma_occupancy(p, t, true, &occ_s), e2 = tma_occupancy(p, t, false, &occ_v);
-        if (e1 == cudaSuccess && e2 == cudaSuccess && occ_s >= 1 && occ_v >= 1) break;
+        const cudaError_t e = tma_occupancy(p, t, stress, &occ);
+        if (e == cudaSuccess && occ >= 1) break;
         cudaGetLastError();
         if (t.stages <= 1) FAIL(CPML_ECUDA, "TMA kernels do not fit on this device");
         t.stages--;
     }
     const int cap = env_int("CPML_CTAS_PER_SM", 0);
-    if (cap > 0) { occ_s = std::min(occ_s, cap); occ_v = std::min(occ_v, cap); }
+    if (cap > 0) occ = std::min(occ, cap);
 
-    // z chunks: minimise rounds x (planes per item + pipeline fill) over the persistent grid
+    // z chunks: minimise rounds x (planes per item + pipeline fill) over the persistent grid; among the
+    // decompositions within 5 % of the best take the finest one (measured: 18 chunks against 9 on the default
+    // grid +1.3 %, 16 against 8 with 104 x 7 tiles +3 %, 2 against 1 on 1024 x 1024 x 128 slabs +4 %)
     const int tiles = t.ntx * t.nty;
-    const int resident = h->sm_count * std::min(occ_s, occ_v);
-    int best = 1;
-    double best_cost = 1e300;
+    const int resident = h->sm_count * occ;
     const int cmax = std::max(1, h->nzl / 8);
-    for (int nc = 1; nc <= cmax; nc++) {
+    auto cost_of = [&](int nc, int *ncr_out) {
         const int kc = (h->nzl + nc - 1) / nc;
         const int ncr = (h->nzl + kc - 1) / kc;
         const long long items = (long long)tiles * ncr;
         const double rounds = (double)((items + resident - 1) / resident);
-        const double cost = rounds * (kc + 3.0);
-        if (cost < best_cost - 1e-9) { best_cost = cost; best = ncr; }
+        *ncr_out = ncr;
+        return rounds * (kc + 3.0);
+    };
+    double best_cost = 1e300;
+    for (int nc = 1; nc <= cmax; nc++) { int ncr; best_cost = std::min(best_cost, cost_of(nc, &ncr)); }
+    int best = 1;
+    for (int nc = 1; nc <= cmax; nc++) {
+        int ncr;
+        if (cost_of(nc, &ncr) <= 1.05 * best_cost) best = std::max(best, ncr);
     }
     int nzc = env_int("CPML_ZCHUNKS", 0);
+    if (stress) nzc = env_int("CPML_ZCHUNKS_STRESS", nzc);
     if (nzc <= 0) nzc = best;
     nzc = std::max(1, std::min(nzc, h->nzl));
     t.kchunk = (h->nzl + nzc - 1) / nzc;
     t.nzc = (h->nzl + t.kchunk - 1) / t.kchunk;
     t.nitems = tiles * t.nzc;
-    t.grid_stress = std::min(t.nitems, h->sm_count * occ_s);
-    t.grid_velocity = std::min(t.nitems, h->sm_count * occ_v);
-    h->nblocks = t.nitems;
+    t.grid_stress = t.grid_velocity = std::min(t.nitems, h->sm_count * occ);
+    return CPML_OK;
+}
+
+static int32_t setup_tma(cpml_handle *h)
+{
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) FAIL(CPML_ECUDA, "driver does not export cuTensorMapEncodeTiled");
+    const EncodeTiledFn enc = (EncodeTiledFn)fn;
+    int32_t rc = build_tile(h, enc, true, h->tile_stress, h->maps_stress);
+    if (rc) return rc;
+    rc = build_tile(h, enc, false, h->tile, h->maps_velocity);
+    if (rc) return rc;
+    h->nblocks = h->tile.nitems;        // energy partial slots: one per item of the velocity kernel
     return CPML_OK;
 }
 
@@ -1008,7 +1028,7 @@ static int32_t half_step(cpml_handle *h, int32_t it, int phase)
     } else if (h->cfg.ndim == 3) {
         const Params3D p = make_p3(h, it);
         if (h->use_tma) {
-            if (phase == 0) CK(launch_stress3d_tma(p, h->maps_stress, h->tile, h->stream));
+            if (phase == 0) CK(launch_stress3d_tma(p, h->maps_stress, h->tile_stress, h->stream));
             else CK(launch_velocity3d_tma(p, h->maps_velocity, h->tile, h->stream));
             h->n_launches++;
         } else {
@@ -1247,10 +1267,10 @@ extern "C" int32_t cpml_get_launch_info(cpml_handle *h, int32_t *info, int32_t n
         for (int q = 0; q < n && q < 10; q++) info[q] = w[q];
         return CPML_OK;
     }
-    const Tile3D &t = h->tile;
-    const int32_t v[10] = {h->use_tma ? 1 : 0, t.tx, t.ty, t.stages, t.kchunk, t.nzc, t.nitems, t.grid_stress, t.grid_velocity,
-                           (h->peer_on[0] ? 1 : 0) + (h->peer_on[1] ? 2 : 0)};
-    for (int q = 0; q < n && q < 10; q++) info[q] = v[q];
+    const Tile3D &t = h->tile, &ts = h->tile_stress;
+    const int32_t v[14] = {h->use_tma ? 1 : 0, t.tx, t.ty, t.stages, t.kchunk, t.nzc, t.nitems, ts.grid_stress, t.grid_velocity,
+                           (h->peer_on[0] ? 1 : 0) + (h->peer_on[1] ? 2 : 0), ts.ty, ts.kchunk, ts.nzc, ts.nitems};
+    for (int q = 0; q < n && q < 14; q++) info[q] = v[q];
     return CPML_OK;
 }
 

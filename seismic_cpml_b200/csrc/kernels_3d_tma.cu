@@ -147,6 +147,12 @@ __device__ __forceinline__ void block_sum2(double &a, double &b, double *red /* 
 
 }  // namespace
 
+// Threads of a CTA: one per pair of points, rounded up to whole warps.  Tiles whose pair count is not
+// a multiple of 32 (104 x 7: 364 pairs on 384 threads = 12 warps, three per SM sub-partition, which lifts
+// the register cap from 128 to 168) are launched one-dimensional with idle threads at the end.
+__host__ __device__ constexpr int tile_pairs(int tx, int ty) { return tx / 2 * ty; }
+__host__ __device__ constexpr int tile_threads(int tx, int ty) { return (tile_pairs(tx, ty) + 31) / 32 * 32; }
+
 // Position in a ring of shared-memory stages: stage index and the mbarrier phase parity of
 // its current use.  Every load goes through the stages cyclically, so the parity flips
 // exactly when the index wraps.
@@ -252,12 +258,12 @@ __device__ __forceinline__ void load_memvars(const Params3D &p, int g0, bool in_
 }
 
 template <bool KUNIT, int TX, int TY, int MINB>
-__global__ void __launch_bounds__(TX / 2 * TY, MINB)
+__global__ void __launch_bounds__(tile_threads(TX, TY), MINB)
 k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMaps tm, const __grid_constant__ Tile3D t)
 {
     using G = TileGeom<TX, TY>;
     constexpr int W = G::W;
-    constexpr bool EARLY_RELEASE = (TX / 2 * TY) < 512;             // see release_and_refill below
+    constexpr bool EARLY_RELEASE = tile_threads(TX, TY) < 512;             // see release_and_refill below
     constexpr int NBYTES = 2 * G::HALO_BYTES;                       // ring N stage: vx, vy
     constexpr int CBYTES = G::HALO_BYTES + 6 * G::PLAIN_BYTES;      // ring C stage: vz, 6 sigma
     constexpr uint32_t TX_N = 2 * G::HALO_BOX_BYTES;
@@ -277,8 +283,12 @@ k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMa
     const uint32_t ringN = sbase + kBarBytes, ringC = ringN + SN * NBYTES;
     const unsigned char *gN = gbase + kBarBytes, *gC = gN + (size_t)SN * NBYTES;
 
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int tid = ty * (TX / 2) + tx;
+    constexpr bool PADDED = tile_pairs(TX, TY) % 32 != 0;           // one-dimensional launch with idle threads
+    const int tid = PADDED ? (int)threadIdx.x : (int)(threadIdx.y * (TX / 2) + threadIdx.x);
+    const int tx = PADDED ? tid % (TX / 2) : (int)threadIdx.x;
+    const int ty_raw = PADDED ? tid / (TX / 2) : (int)threadIdx.y;
+    const bool lane_ok = !PADDED || ty_raw < TY;
+    const int ty = PADDED ? min(ty_raw, TY - 1) : ty_raw;           // idle threads read row TY-1 and store nothing
     if (tid == 0) {
         for (uint32_t s = 0; s < SN; s++) mbar_init(barN + 8 * s, 1);
         for (uint32_t s = 0; s < SC; s++) mbar_init(barC + 8 * s, 1);
@@ -337,7 +347,7 @@ k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMa
 
         // the pair: points A = (i, j) and B = (i+1, j); i-1 is even, so B shares A's 16 bytes
         const int i = i0 + 2 * tx, j = j0 + ty;
-        const bool row = (j <= p.ny);
+        const bool row = lane_ok && (j <= p.ny);
         const bool validA = row && (i <= p.nx), validB = row && (i + 1 <= p.nx);
         long long q = (long long)kb * pl + (long long)(j - 1) * pitch + (i - 1);
 
@@ -347,7 +357,7 @@ k_stress3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMa
         const bool ux = __any_sync(0xffffffffu, in_xA || in_xB), uy = __any_sync(0xffffffffu, in_y);   // warp-uniform
         const bool warp_pml = ux || uy;
         const int jc = min(j, p.ny);                                // y coefficients are read unconditionally
-        if (tile_xpml) fill_cx<TX, TX / 2 * TY>(p, Cx, i0, tid);
+        if (tile_xpml) fill_cx<TX, tile_threads(TX, TY)>(p, Cx, i0, tid);
         __syncthreads();
         // loop bounds of the four nests (i, j part; the k part is tested per plane)
         const bool do_nA = validA && (i <= p.nx - 1) && (j >= 2), do_nB = validB && (i + 1 <= p.nx - 1) && (j >= 2);   // :838-839
@@ -556,18 +566,18 @@ __device__ __forceinline__ void velocity_point(
 }
 
 template <bool KUNIT, int TX, int TY, int MINB>
-__global__ void __launch_bounds__(TX / 2 * TY, MINB)
+__global__ void __launch_bounds__(tile_threads(TX, TY), MINB)
 k_velocity3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ TmaMaps tm, const __grid_constant__ Tile3D t)
 {
     using G = TileGeom<TX, TY>;
     constexpr int W = G::W;
-    constexpr bool EARLY_RELEASE = (TX / 2 * TY) < 512;
+    constexpr bool EARLY_RELEASE = tile_threads(TX, TY) < 512;
     constexpr int NBYTES = G::PLAIN_BYTES;                          // ring N stage: szz
     constexpr int CBYTES = 5 * G::HALO_BYTES + 3 * G::PLAIN_BYTES;  // ring C stage: 5 sigma (halo), vx vy vz
     constexpr uint32_t TX_N = G::PLAIN_BOX_BYTES;
     constexpr uint32_t TX_C = 5 * G::HALO_BOX_BYTES + 3 * G::PLAIN_BOX_BYTES;
     constexpr int PD = G::PLAIN_BYTES / 8, HD = G::HALO_BYTES / 8;
-    constexpr int NT = TX / 2 * TY;
+    constexpr int NT = tile_threads(TX, TY);
     const uint32_t XMB = (uint32_t)t.xm_bytes, XM_TX = (uint32_t)(TY * p.sxp * 8);    // x-shell memory variables, see k_stress3d_tma
     const uint32_t CSTAGE = CBYTES + 3 * XMB;
 
@@ -581,8 +591,12 @@ k_velocity3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ Tma
     const uint32_t ringN = sbase + kBarBytes, ringC = ringN + SN * NBYTES;
     const unsigned char *gN = gbase + kBarBytes, *gC = gN + (size_t)SN * NBYTES;
 
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int tid = ty * (TX / 2) + tx;
+    constexpr bool PADDED = tile_pairs(TX, TY) % 32 != 0;           // one-dimensional launch with idle threads
+    const int tid = PADDED ? (int)threadIdx.x : (int)(threadIdx.y * (TX / 2) + threadIdx.x);
+    const int tx = PADDED ? tid % (TX / 2) : (int)threadIdx.x;
+    const int ty_raw = PADDED ? tid / (TX / 2) : (int)threadIdx.y;
+    const bool lane_ok = !PADDED || ty_raw < TY;
+    const int ty = PADDED ? min(ty_raw, TY - 1) : ty_raw;           // idle threads read row TY-1 and store nothing
     if (tid == 0) {
         for (uint32_t s = 0; s < SN; s++) mbar_init(barN + 8 * s, 1);
         for (uint32_t s = 0; s < SC; s++) mbar_init(barC + 8 * s, 1);
@@ -640,7 +654,7 @@ k_velocity3d_tma(const __grid_constant__ Params3D p, const __grid_constant__ Tma
         }
 
         const int i = i0 + 2 * tx, j = j0 + ty;
-        const bool row = (j <= p.ny);
+        const bool row = lane_ok && (j <= p.ny);
         const bool validA = row && (i <= p.nx), validB = row && (i + 1 <= p.nx);
         long long q = (long long)kb * pl + (long long)(j - 1) * pitch + (i - 1);
 
@@ -797,7 +811,7 @@ template <bool KUNIT, int TX, int TY, int MINB>
 static cudaError_t launch_tile(const Params3D &p, const TmaMaps &tm, const Tile3D &t, cudaStream_t s, bool stress, int *occ)
 {
     const size_t smem = smem_need<TX, TY>(stress, t.stages, t.xm_bytes);
-    constexpr int NT = TX / 2 * TY;                 // one thread per pair of points
+    constexpr int NT = tile_threads(TX, TY);        // one thread per pair of points, whole warps
     const void *fn = stress ? (const void *)k_stress3d_tma<KUNIT, TX, TY, MINB> : (const void *)k_velocity3d_tma<KUNIT, TX, TY, MINB>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -805,7 +819,8 @@ static cudaError_t launch_tile(const Params3D &p, const TmaMaps &tm, const Tile3
         if (stress) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_stress3d_tma<KUNIT, TX, TY, MINB>, NT, smem);
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_velocity3d_tma<KUNIT, TX, TY, MINB>, NT, smem);
     }
-    const dim3 grid(stress ? t.grid_stress : t.grid_velocity), block(TX / 2, TY);
+    const dim3 grid(stress ? t.grid_stress : t.grid_velocity);
+    const dim3 block = tile_pairs(TX, TY) % 32 != 0 ? dim3(NT) : dim3(TX / 2, TY);
     if (stress) k_stress3d_tma<KUNIT, TX, TY, MINB><<<grid, block, smem, s>>>(p, tm, t);
     else        k_velocity3d_tma<KUNIT, TX, TY, MINB><<<grid, block, smem, s>>>(p, tm, t);
     return cudaGetLastError();
@@ -826,6 +841,7 @@ static cudaError_t dispatch_tile(const Params3D &p, const TmaMaps &tm, const Til
     case 128082: return launch_tile<KUNIT, 128, 8, 2>(p, tm, t, s, stress, occ);
     case 104041: case 104042: return launch_tile<KUNIT, 104, 4, 2>(p, tm, t, s, stress, occ);     // 208 threads
     case 104043: case 104044: return launch_tile<KUNIT, 104, 4, 3>(p, tm, t, s, stress, occ);
+    case 104071: return launch_tile<KUNIT, 104, 7, 1>(p, tm, t, s, stress, occ);                  // 364 pairs on 384 threads
     case 104081: return launch_tile<KUNIT, 104, 8, 1>(p, tm, t, s, stress, occ);                  // 416 threads
     case 104082: return launch_tile<KUNIT, 104, 8, 2>(p, tm, t, s, stress, occ);
     default: return cudaErrorInvalidValue;
@@ -835,7 +851,7 @@ static cudaError_t dispatch_tile(const Params3D &p, const TmaMaps &tm, const Til
 bool tma_tile_supported(int tx, int ty)
 {
     switch (tx * 100 + ty) {
-    case 6404: case 6408: case 12804: case 12808: case 10408: case 10404: return true;     // TMA boxes hold at most 256 elements per dimension
+    case 6404: case 6408: case 12804: case 12808: case 10408: case 10404: case 10407: return true;     // TMA boxes hold at most 256 elements per dimension
     default: return false;
     }
 }

@@ -374,10 +374,11 @@ class Solver:
         self._ck(self._L.cpml_p2p_detach(self._h))
 
     def launch_info(self) -> dict:
-        v = np.zeros(10, dtype=np.int32)
-        self._ck(self._L.cpml_get_launch_info(self._h, _i(v), 10))
+        v = np.zeros(14, dtype=np.int32)
+        self._ck(self._L.cpml_get_launch_info(self._h, _i(v), 14))
         keys = ("tma", "tile_x", "tile_y", "stages", "planes_per_item", "z_chunks", "items",
-                "ctas_stress", "ctas_velocity", "peer_sides")
+                "ctas_stress", "ctas_velocity", "peer_sides", "stress_tile_y", "stress_planes_per_item",
+                "stress_z_chunks", "stress_items")
         return dict(zip(keys, (int(x) for x in v)))
 
     # -- outputs
