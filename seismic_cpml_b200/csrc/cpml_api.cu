@@ -645,7 +645,7 @@ static int32_t build_tile(cpml_handle *h, EncodeTiledFn enc, bool stress, Tile3D
     if (!tma_tile_supported(t.tx, t.ty)) FAIL(CPML_EINVAL, "unsupported CPML_TX x CPML_TY tile");
     t.stages = std::max(1, std::min(7, env_int("CPML_STAGES", 2)));
     t.minb = std::max(1, std::min(4, env_int("CPML_MINB", t.tx == 64 ? 2 : 1)));
-    if (t.ty == 7) t.minb = 1;
+    if (t.ty == 7 || t.ty == 6) t.minb = 1;
     t.xm_bytes = h->shell[0].size() > 0 ? round_up(t.ty * h->sxp * 8, 128) : 0;
     t.ntx = (c.nx + t.tx - 1) / t.tx;
     t.nty = (c.ny + t.ty - 1) / t.ty;

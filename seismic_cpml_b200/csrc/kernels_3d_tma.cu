@@ -837,6 +837,7 @@ static cudaError_t dispatch_tile(const Params3D &p, const TmaMaps &tm, const Til
     case 64081:  case 64082:  return launch_tile<KUNIT, 64, 8, 2>(p, tm, t, s, stress, occ);      // 256 threads
     case 128041: case 128042: return launch_tile<KUNIT, 128, 4, 2>(p, tm, t, s, stress, occ);     // 256 threads
     case 128043: return launch_tile<KUNIT, 128, 4, 3>(p, tm, t, s, stress, occ);
+    case 128061: return launch_tile<KUNIT, 128, 6, 1>(p, tm, t, s, stress, occ);                  // 384 threads: 168-register cap
     case 128081: return launch_tile<KUNIT, 128, 8, 1>(p, tm, t, s, stress, occ);                  // 512 threads
     case 128082: return launch_tile<KUNIT, 128, 8, 2>(p, tm, t, s, stress, occ);
     case 104041: case 104042: return launch_tile<KUNIT, 104, 4, 2>(p, tm, t, s, stress, occ);     // 208 threads
@@ -851,7 +852,7 @@ static cudaError_t dispatch_tile(const Params3D &p, const TmaMaps &tm, const Til
 bool tma_tile_supported(int tx, int ty)
 {
     switch (tx * 100 + ty) {
-    case 6404: case 6408: case 12804: case 12808: case 10408: case 10404: case 10407: return true;     // TMA boxes hold at most 256 elements per dimension
+    case 6404: case 6408: case 12804: case 12808: case 10408: case 10404: case 10407: case 12806: return true;     // TMA boxes hold at most 256 elements per dimension
     default: return false;
     }
 }

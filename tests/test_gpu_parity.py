@@ -230,7 +230,7 @@ def test_3d_slabs_with_peer_stores_match_single_slab(nslabs):
             s.close()
 
 
-@pytest.mark.parametrize("tile", [(64, 4), (64, 8), (104, 7), (104, 8), (128, 4), (128, 8)])
+@pytest.mark.parametrize("tile", [(64, 4), (64, 8), (104, 7), (104, 8), (128, 4), (128, 6), (128, 8)])
 @pytest.mark.parametrize("stages", [1, 3])
 def test_3d_tma_tiles_and_ring_depths(tile, stages, monkeypatch):
     """Every TMA box shape / shared-memory ring depth gives the same bits (ragged grid: NX, NY
