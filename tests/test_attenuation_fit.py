@@ -103,3 +103,16 @@ def test_program_parameter_blocks_fit_their_relaxation_times_like_the_reference(
         P.Params3DVisco(tau_epsilon_nu1=(0.03, 0.003))
     # VISCOELASTIC_ATTENUATION = .false.: the dummy values of 2D-visco-4th :374-380, no fit
     assert P.Params2DVisco(VISCOELASTIC_ATTENUATION=False).tau_sigma_nu2 == (1.0, 1.0, 1.0)
+
+
+def test_single_correction_division_tool(tmp_path):
+    """tools/div_small_check.c: the one-correction division by 24 and 3 of the viscoelastic kernels equals a / c
+    (a short run here; the full 11.2e9-case run is quoted in DESIGN.md)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "div_small_check")
+    subprocess.run(["gcc", "-O2", "-fopenmp", "-ffp-contract=off", "-o", exe, os.path.join(root, "tools", "div_small_check.c"), "-lm"],
+                   check=True)
+    r = subprocess.run([exe, "2"], capture_output=True, text=True)
+    assert r.returncode == 0 and " bad 0" in r.stdout, r.stdout
