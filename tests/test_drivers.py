@@ -173,3 +173,21 @@ def test_cpp_driver_3d_viscoelastic_small_grid(driver_exe, tmp_path):
     assert d.shape == (60, 2) and e.shape == (60, 4) and np.abs(d[:, 1]).max() > 0 and np.all(np.isfinite(e))
     assert d[0, 0] == pytest.approx(-1.2 / 18.0, rel=1e-6)          # time axis minus t0 (3D-visco :1603)
     assert "Total energy =" in r.stdout
+
+
+def test_fortran_viscoelastic_driver_keeps_the_reference_parameter_surface():
+    src = open(os.path.join(DRV, "fortran", "seismic_CPML_2D_viscoelastic_b200.f90")).read()
+    for name in ("NX = 2001", "NY = 2001", "DELTAX = 1.5d0", "DELTAT = 2.2d-4", "NSTEP = 5200", "NPOINTS_PML = 10",
+                 "cp_unrelaxed = 2000.d0", "f0 = 35.d0", "factor = 1.d0", "xsource = 1500.d0", "ANGLE_FORCE = 0.d0",
+                 "NREC = 1", "xdeb = 2301.d0", "IT_DISPLAY = 200", "N_SLS = 3", "Qp = 65.d0", "Qs = 55.d0",
+                 "COMPUTE_ENERGY = .false."):
+        assert name in src, name
+    for call in ("cpml_host_attenuation_fit", "cpml_create", "cpml_set_profiles", "cpml_set_material_2d",
+                 "cpml_set_attenuation", "cpml_set_source_series", "cpml_set_receivers", "cpml_run",
+                 "cpml_get_seismograms", "cpml_get_pressure_seismograms", "cpml_host_write_seismograms_visco",
+                 "cpml_get_maxnorm", "cpml_destroy"):
+        assert call in src, call
+    # every library function it calls is bound by the module with the arity used here
+    f90 = open(os.path.join(DRV, "fortran", "cpml_b200_mod.f90")).read()
+    for call in re.findall(r"\b(cpml_[a-z0-9_]+)\(", src):
+        assert ("function " + call + "(") in f90 or ("subroutine " + call + "(") in f90, call
