@@ -174,7 +174,9 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
         if (NORMAL) { vz_mm = p.vz[q - 2 * pl]; vz_m = p.vz[q - pl]; }
         vz_c = p.vz[q];
 
-        for (int k = kb; k <= ke; ++k, q += pl) {
+        int kmod = (kb + p.koff) % p.nzl_e;                  // position inside the emulated reference slab (quirk B6),
+                                                              // advanced with the plane instead of a modulo per plane
+        for (int k = kb; k <= ke; ++k, q += pl, kmod = (kmod + 1 == p.nzl_e) ? 0 : kmod + 1) {
             const int kg = k + p.koff;                      // :978
             const bool in_z = (kg <= p.zlo) || (kg >= p.zhi);
             const bool in_pml = in_x | in_y | in_z;          // one branch per nest for the interior points
@@ -188,7 +190,6 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
                 if (SHEAR) { azh = p.cz.a_half[kg]; bzh = p.cz.b_half[kg]; Kzh = p.cz.K_half[kg]; rKzh = p.cz.rK_half[kg]; }
             }
             // quirk B6: taps the reference's MPI exchange never delivers
-            const int kmod = kg % p.nzl_e;
             const bool cut_up = (kmod == 0);                // last plane of a reference slab
             const bool cut_dn = (kmod == 1);                // first plane of a reference slab
             const bool ebox = ebox_ij && kg >= p.npml && kg <= p.nz - p.npml + 1;      // :1387-1392
@@ -432,7 +433,8 @@ k_vvelocity3d(const __grid_constant__ ParamsV3D p)
         double syz_mm = p.syz[q - 2 * pl], syz_m = p.syz[q - pl], syz_c = p.syz[q];
         double szz_m = p.szz[q - pl], szz_c = p.szz[q], szz_p = p.szz[q + pl];
 
-        for (int k = kb; k <= ke; ++k, q += pl) {
+        int kmod = (kb + p.koff) % p.nzl_e;                  // see k_vstress3d
+        for (int k = kb; k <= ke; ++k, q += pl, kmod = (kmod + 1 == p.nzl_e) ? 0 : kmod + 1) {
             const int kg = k + p.koff;
             // ---- loads of this plane
             const double sxz_p = p.sxz[q + pl], syz_p = p.syz[q + pl], szz_pp = p.szz[q + 2 * pl];
@@ -456,7 +458,6 @@ k_vvelocity3d(const __grid_constant__ ParamsV3D p)
                 azh = p.cz.a_half[kg]; bzh = p.cz.b_half[kg]; Kzh = p.cz.K_half[kg];
                 rKz = p.cz.rK[kg]; rKzh = p.cz.rK_half[kg];
             }
-            const int kmod = kg % p.nzl_e;
             const bool cut_up = (kmod == 0);
             const bool cut_dn = (kmod == 1);
             if ((p.pf & 4) && (in_pml | (kg + 1 <= p.zlo) | (kg + 1 >= p.zhi))) {      // memory variables of the next plane into L2, see k_vstress3d
