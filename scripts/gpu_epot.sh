@@ -1,0 +1,24 @@
+#!/bin/bash
+# isotropic TMA kernels: potential energy summed by the stress kernel instead of the velocity kernel; A/B on one box
+mkdir -p gpurun_out
+OUT=gpurun_out/sweep_epot.txt; : > $OUT
+fmt='
+import sys, json
+for l in sys.stdin:
+    try:
+        d = json.loads(l); r = d["roofline"]
+        print("  value %.2f Gpts/s  step %.3f ms  stress %.3f ms (%.3f)  vel %.3f ms (%.3f)  stepfrac %.3f e2e %.2f" % (d["value"], d["ms_per_step"], r["avg_launch_ms"], r["frac"], r["velocity_kernel"]["avg_launch_ms"], r["velocity_kernel"]["frac"], r["step"]["frac"], d["e2e"]["value"]))
+    except Exception as e:
+        print("  ?", l.strip()[:300])
+'
+run() { wl=$1; shift; echo "$wl $*" >> $OUT; env "$@" timeout 300 python bench.py --workload $wl --steps $STEPS --warmup 5 --no-cpu-baseline 2>&1 | python -c "$fmt" >> $OUT; }
+( timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "3d" ) > gpurun_out/test_epot.log 2>&1; echo "pytest rc=$?" >> gpurun_out/test_epot.log
+cp seismic_cpml_b200/libcpml_b200.so /tmp/new.so
+STEPS=100
+cp ab/libcpml_b200_head.so seismic_cpml_b200/libcpml_b200.so; run cfg3 LIB=head
+cp /tmp/new.so seismic_cpml_b200/libcpml_b200.so; run cfg3 LIB=new
+STEPS=40
+run cfg4 LIB=new
+cp ab/libcpml_b200_head.so seismic_cpml_b200/libcpml_b200.so; run cfg4 LIB=head
+cp /tmp/new.so seismic_cpml_b200/libcpml_b200.so
+echo finished >> $OUT
