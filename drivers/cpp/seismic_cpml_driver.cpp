@@ -213,6 +213,10 @@ int run_visco(const Args &A)
         CHECK(h, cpml_get_seismograms(h, sisvx.data(), sisvy.data()));
         if (!is3d) CHECK(h, cpml_get_pressure_seismograms(h, sisp.data()));
         cpml_host_write_seismograms_visco(A.out.c_str(), sisvx.data(), sisvy.data(), is3d ? nullptr : sisp.data(), NSTEP, NREC, DELTAT, t0);
+        if (is3d) {     // Vz_file_NNN.dat: an extension, the reference records Vx and Vy only
+            CHECK(h, cpml_get_seismograms_vz(h, sisp.data()));
+            cpml_host_write_seismograms_vz(A.out.c_str(), sisp.data(), NSTEP, NREC, DELTAT, t0);
+        }
     };
     int it_begin = 1;
     while (it_begin <= NSTEP) {
@@ -379,6 +383,10 @@ int main(int argc, char **argv)
     // ---- final output (:1247-1257 ; 2D-2nd :737-746)
     CHECK(h, cpml_get_seismograms(h, sisvx.data(), sisvy.data()));
     cpml_host_write_seismograms(A.out.c_str(), sisvx.data(), sisvy.data(), NSTEP, NREC, DELTAT);
+    if (is3d) {         // Vz_file_NNN.dat: an extension, the reference records Vx and Vy only
+        CHECK(h, cpml_get_seismograms_vz(h, sisvx.data()));
+        cpml_host_write_seismograms_vz(A.out.c_str(), sisvx.data(), NSTEP, NREC, DELTAT, 0.0);
+    }
     CHECK(h, cpml_get_energy(h, e_tot.data(), e_kin.data(), e_pot.data()));
     const std::string epath = A.out + "/energy.dat";
     if (is3d) cpml_host_write_energy_3d(epath.c_str(), e_tot.data(), NSTEP, DELTAT);

@@ -249,6 +249,13 @@ module cpml_b200
       integer(c_int32_t) :: ierr
     end function
 
+    function cpml_get_seismograms_vz(handle, sisvz) bind(C, name='cpml_get_seismograms_vz') result(ierr)
+      import :: c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), intent(out) :: sisvz(*)
+      integer(c_int32_t) :: ierr
+    end function
+
     function cpml_get_pressure_seismograms(handle, sispressure) bind(C, name='cpml_get_pressure_seismograms') result(ierr)
       import :: c_int32_t, c_ptr, c_double
       type(c_ptr), value :: handle
@@ -403,6 +410,16 @@ module cpml_b200
       character(kind=c_char), intent(in) :: dir(*)
       real(c_double), intent(in) :: sisvx(*), sisvy(*)
       type(c_ptr), value :: sispressure        ! c_loc(sispressure) in the 2-D programs, c_null_ptr in 3-D
+      integer(c_int32_t), value :: nt, nrec
+      real(c_double), value :: deltat, t0
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_host_write_seismograms_vz(dir, sisvz, nt, nrec, deltat, t0) &
+        bind(C, name='cpml_host_write_seismograms_vz') result(ierr)
+      import :: c_int32_t, c_double, c_char
+      character(kind=c_char), intent(in) :: dir(*)
+      real(c_double), intent(in) :: sisvz(*)
       integer(c_int32_t), value :: nt, nrec
       real(c_double), value :: deltat, t0
       integer(c_int32_t) :: ierr

@@ -124,6 +124,9 @@ program seismic_CPML_3D_iso_b200
 ! --- final output
   call cpml_check(cpml_get_seismograms(h, sisvx, sisvy), h, 'seismograms')
   ierr = cpml_host_write_seismograms(here, sisvx, sisvy, NSTEP, NREC, DELTAT)
+! Vz_file_NNN.dat: an extension -- the reference records Vx and Vy only although its plotgnu reads Vz files
+  call cpml_check(cpml_get_seismograms_vz(h, sisvx), h, 'seismograms vz')
+  ierr = cpml_host_write_seismograms_vz(here, sisvx, NSTEP, NREC, DELTAT, 0.d0)
   call cpml_check(cpml_get_energy(h, total_energy, energy_kinetic, energy_potential), h, 'energy')
   ierr = cpml_host_write_energy_3d('energy.dat' // c_null_char, total_energy, NSTEP, DELTAT)
   ierr = cpml_destroy(h)

@@ -237,6 +237,11 @@ int32_t cpml_get_launch_info(cpml_handle *h, int32_t *info, int32_t n);
  * last executed step.  On a slab that does not own the receiver plane they are zero. */
 int32_t cpml_get_seismograms(cpml_handle *h, double *sisvx, double *sisvy);
 
+/* EXTENSION (not in the reference): the 3-D programs record Vx and Vy only although
+ * their plot script reads Vz_file_NNN.dat; sisvz(it, irec) = vz(ix_rec, iy_rec, NZ/2), same layout as
+ * cpml_get_seismograms.  3-D only. */
+int32_t cpml_get_seismograms_vz(cpml_handle *h, double *sisvz);
+
 /* 2-D viscoelastic only: sispressure(NSTEP,NREC) of 2D-visco-4th :304, filled at :1004-1035
  * (pressure = -(lambda + 2/3 mu)(epsilon_xx + epsilon_yy) at the receiver). */
 int32_t cpml_get_pressure_seismograms(cpml_handle *h, double *sispressure);
@@ -339,6 +344,9 @@ int32_t cpml_host_write_seismograms(const char *dir, const double *sisvx, const 
 int32_t cpml_host_write_seismograms_visco(const char *dir, const double *sisvx, const double *sisvy,
                                           const double *sispressure, int32_t nt, int32_t nrec,
                                           double deltat, double t0);
+/* Vz_file_NNN.dat for cpml_get_seismograms_vz (time axis minus t0; t0 = 0 for the isotropic program). */
+int32_t cpml_host_write_seismograms_vz(const char *dir, const double *sisvz, int32_t nt, int32_t nrec,
+                                       double deltat, double t0);
 int32_t cpml_host_write_energy_3d(const char *path, const double *total, int32_t nt,
                                   double deltat);
 int32_t cpml_host_write_energy_2d(const char *path, const double *kinetic,

@@ -51,6 +51,7 @@ struct cpml_handle {
     bool have_attenuation = false;
     double tau[4][3] = {};     // tau_epsilon_nu1, tau_sigma_nu1, tau_epsilon_nu2, tau_sigma_nu2
     double *d_sisp = nullptr;  // 2-D viscoelastic: sispressure
+    double *d_sisvz = nullptr; // 3-D: Vz seismograms (extension, quirk B7)
     dim3 vgrid;
     int vkchunk = 1, vtx = 32, vty = 8;
 
@@ -272,6 +273,7 @@ static int32_t create_impl(cpml_handle *h)
     CK(cudaMalloc(&h->d_sisvx, ns * sizeof(double)));
     CK(cudaMalloc(&h->d_sisvy, ns * sizeof(double)));
     if (h->visco2d) CK(cudaMalloc(&h->d_sisp, ns * sizeof(double)));
+    if (c.ndim == 3) CK(cudaMalloc(&h->d_sisvz, ns * sizeof(double)));
     CK(cudaMalloc(&h->d_ix_rec, std::max(1, c.nrec) * sizeof(int)));
     CK(cudaMalloc(&h->d_iy_rec, std::max(1, c.nrec) * sizeof(int)));
     CK(cudaMalloc(&h->d_maxbits, sizeof(unsigned long long)));
@@ -388,7 +390,7 @@ extern "C" int32_t cpml_destroy(cpml_handle *h)
     for (auto &p : h->my) cudaFree(p);
     for (auto &p : h->mz) cudaFree(p);
     cudaFree(h->d_src_x); cudaFree(h->d_src_y); cudaFree(h->d_ix_rec); cudaFree(h->d_iy_rec);
-    cudaFree(h->d_sisvx); cudaFree(h->d_sisvy); cudaFree(h->d_sisp); cudaFree(h->d_ek); cudaFree(h->d_ep);
+    cudaFree(h->d_sisvx); cudaFree(h->d_sisvy); cudaFree(h->d_sisp); cudaFree(h->d_sisvz); cudaFree(h->d_ek); cudaFree(h->d_ep);
     cudaFree(h->d_partials); cudaFree(h->d_maxbits);
     cudaFreeHost(h->pin_src); cudaFreeHost(h->pin_out);
     for (auto e : h->ev) cudaEventDestroy(e);
@@ -416,6 +418,7 @@ extern "C" int32_t cpml_reset(cpml_handle *h)
     CK(cudaMemsetAsync(h->d_sisvx, 0, ns * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->d_sisvy, 0, ns * sizeof(double), h->stream));
     if (h->d_sisp) CK(cudaMemsetAsync(h->d_sisp, 0, ns * sizeof(double), h->stream));
+    if (h->d_sisvz) CK(cudaMemsetAsync(h->d_sisvz, 0, ns * sizeof(double), h->stream));
     // 2-D: the paired kernels write fewer partial slots than the one-point geometry allocates, and the
     // 2-D viscoelastic kernels none unless compute_energy is set: the unused slots must read zero
     if (c.ndim == 2 && h->d_partials) CK(cudaMemsetAsync(h->d_partials, 0, 2 * (size_t)h->nblocks * sizeof(double), h->stream));
@@ -1093,6 +1096,7 @@ extern "C" int32_t cpml_step_finish(cpml_handle *h, int32_t it)
         p.krec = 1;
     }
     p.sisvx = h->d_sisvx; p.sisvy = h->d_sisvy;
+    p.vz = c.ndim == 3 ? h->f0[2] : nullptr; p.sisvz = h->d_sisvz;
     if (h->visco2d) {
         const Params2D p2 = make_p2(h, it);
         if (c.compute_energy) { launch_venergy2d(p2, h->grid, h->stream); h->n_launches++; }   // COMPUTE_ENERGY, :1037
@@ -1282,6 +1286,18 @@ extern "C" int32_t cpml_get_seismograms(cpml_handle *h, double *sisvx, double *s
     if (n == 0) return CPML_OK;
     CK(cudaMemcpyAsync(sisvx, h->d_sisvx, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(sisvy, h->d_sisvy, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_get_seismograms_vz(cpml_handle *h, double *sisvz)
+{
+    if (!h || !sisvz) return CPML_EINVAL;
+    if (h->cfg.ndim != 3) FAIL(CPML_EINVAL, "Vz seismograms exist in the 3-D programs only");
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->cfg.nstep * (size_t)h->cfg.nrec;
+    if (n == 0) return CPML_OK;
+    CK(cudaMemcpyAsync(sisvz, h->d_sisvz, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return CPML_OK;
 }

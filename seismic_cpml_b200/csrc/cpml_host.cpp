@@ -188,6 +188,25 @@ extern "C" int32_t cpml_host_write_seismograms(const char *dir, const double *si
     return CPML_OK;
 }
 
+// Vz_file_NNN.dat: not written by the reference (quirk B7: its plotgnu reads them, its programs record Vx and
+// Vy only); same format as the other two, time axis minus t0 (0 for the isotropic program)
+extern "C" int32_t cpml_host_write_seismograms_vz(const char *dir, const double *sisvz, int32_t nt, int32_t nrec,
+                                                  double deltat, double t0)
+{
+    if (!sisvz || nt < 1 || nrec < 0) return CPML_EINVAL;
+    for (int32_t r = 1; r <= nrec; r++) {
+        char name[64];
+        snprintf(name, sizeof name, "Vz_file_%03d.dat", r);
+        FILE *f = fopen(join(dir, name).c_str(), "w");
+        if (!f) return CPML_EINVAL;
+        for (int32_t it = 1; it <= nt; it++)
+            fprintf(f, "  %.8E   %.8E\n", (double)(float)((double)(it - 1) * deltat - t0),
+                    (double)(float)sisvz[(size_t)(r - 1) * nt + (it - 1)]);
+        fclose(f);
+    }
+    return CPML_OK;
+}
+
 // write_seismograms of the viscoelastic programs: the time axis is shifted by -t0 (3D-visco :1603,1613;
 // 2D-visco-4th :1178,1188); the 2-D programs also record the pressure, which their scheme holds half a
 // time step later (:1164-1168), and name the Vy file after its staggered position (:1184)

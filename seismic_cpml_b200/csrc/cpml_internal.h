@@ -210,10 +210,11 @@ struct Post3D {
     int it, nstep, nrec;
     const int *ix_rec, *iy_rec;
     const double *vx, *vy;         // element (1,1,0)
+    const double *vz;              // 3-D only (null in 2-D): the Vz extension, quirk B7
     int pitch;
     long long plane;
     int krec;                      // local k of the receiver plane, 0: not here
-    double *sisvx, *sisvy;
+    double *sisvx, *sisvy, *sisvz;
 };
 
 // ------------------------------------------------------------------ 3-D viscoelastic

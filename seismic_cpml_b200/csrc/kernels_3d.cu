@@ -378,6 +378,9 @@ __global__ void __launch_bounds__(256) k_post3d(const __grid_constant__ Post3D p
             const long long q = (long long)p.krec * p.plane + (long long)(p.iy_rec[r] - 1) * p.pitch + (p.ix_rec[r] - 1);
             p.sisvx[(long long)r * p.nstep + (p.it - 1)] = p.vx[q];
             p.sisvy[(long long)r * p.nstep + (p.it - 1)] = p.vy[q];
+            // not in the reference (it records Vx and Vy only although its plot script reads Vz files, quirk
+            // B7): vz at the same array indices, vz(ix_rec, iy_rec, NZ/2)
+            if (p.vz) p.sisvz[(long long)r * p.nstep + (p.it - 1)] = p.vz[q];
         }
     }
 }

@@ -81,6 +81,7 @@ SYMBOLS = {
     "cpml_get_launch_info": (C.c_int32, [_H, _ip, C.c_int32]),
     "cpml_get_seismograms": (C.c_int32, [_H, _dp, _dp]),
     "cpml_get_pressure_seismograms": (C.c_int32, [_H, _dp]),
+    "cpml_get_seismograms_vz": (C.c_int32, [_H, _dp]),
     "cpml_get_energy": (C.c_int32, [_H, _dp, _dp, _dp]),
     "cpml_get_plane": (C.c_int32, [_H, C.c_int32, C.c_int32, _dp]),
     "cpml_get_field": (C.c_int32, [_H, C.c_int32, _dp]),
@@ -104,6 +105,7 @@ SYMBOLS = {
     "cpml_host_attenuation_fit_linear": (C.c_int32, [C.c_int32] + [C.c_double] * 3 + [_dp, _dp]),
     "cpml_host_write_seismograms": (C.c_int32, [C.c_char_p, _dp, _dp, C.c_int32, C.c_int32, C.c_double]),
     "cpml_host_write_seismograms_visco": (C.c_int32, [C.c_char_p, _dp, _dp, _dp, C.c_int32, C.c_int32, C.c_double, C.c_double]),
+    "cpml_host_write_seismograms_vz": (C.c_int32, [C.c_char_p, _dp, C.c_int32, C.c_int32, C.c_double, C.c_double]),
     "cpml_host_write_energy_3d": (C.c_int32, [C.c_char_p, _dp, C.c_int32, C.c_double]),
     "cpml_host_write_energy_2d": (C.c_int32, [C.c_char_p, _dp, _dp, C.c_int32, C.c_double]),
     "cpml_host_create_color_image": (C.c_int32, [C.c_char_p, _dp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
@@ -389,6 +391,13 @@ class Solver:
         sx, sy = np.zeros((nrec, nstep)), np.zeros((nrec, nstep))
         self._ck(self._L.cpml_get_seismograms(self._h, _d(sx), _d(sy)))
         return sx, sy
+
+    def get_seismograms_vz(self):
+        """sisvz (NREC, NSTEP): vz(ix_rec, iy_rec, NZ/2) -- an extension, the reference records Vx and Vy only
+        (quirk B7).  3-D only."""
+        sz = np.zeros((self.cfg.nrec, self.cfg.nstep))
+        self._ck(self._L.cpml_get_seismograms_vz(self._h, _d(sz)))
+        return sz
 
     def get_pressure_seismograms(self):
         """sispressure shaped (NREC, NSTEP) (2-D viscoelastic programs, 2D-visco-4th :1004-1035)."""

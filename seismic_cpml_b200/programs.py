@@ -576,13 +576,16 @@ class Program3DIso(_ProgramBase):
 
     def results(self):
         sx, sy = self.solver.get_seismograms()
+        sz = self.solver.get_seismograms_vz()          # extension: the reference records Vx and Vy only (quirk B7)
         total = self._total_energy()
         if self.output_dir is not None:  # :1247-1257
             os.makedirs(self.output_dir, exist_ok=True)
             self.write_seismograms()
+            _lib.load().cpml_host_write_seismograms_vz(self.output_dir.encode(), _lib._d(sz), self.p.NSTEP, self.p.NREC,
+                                                       self.p.DELTAT, 0.0)
             _lib.load().cpml_host_write_energy_3d(os.path.join(self.output_dir, "energy.dat").encode(),
                                                   _lib._d(total), self.p.NSTEP, self.p.DELTAT)
-        return dict(sisvx=sx, sisvy=sy, total_energy=total, display_log=self.display_log)
+        return dict(sisvx=sx, sisvy=sy, sisvz=sz, total_energy=total, display_log=self.display_log)
 
 
 class Program3DVisco(_ProgramBase):
@@ -603,15 +606,18 @@ class Program3DVisco(_ProgramBase):
 
     def results(self):
         sx, sy = self.solver.get_seismograms()
+        sz = self.solver.get_seismograms_vz()          # extension, quirk B7
         total, ek, ep = self.solver.get_energy()
         if self.output_dir is not None:
             os.makedirs(self.output_dir, exist_ok=True)
             _lib.load().cpml_host_write_seismograms_visco(self.output_dir.encode(), _lib._d(sx), _lib._d(sy), None,
                                                           self.p.NSTEP, self.p.NREC, self.p.DELTAT, self.p.t0)   # :1596-1616
+            _lib.load().cpml_host_write_seismograms_vz(self.output_dir.encode(), _lib._d(sz), self.p.NSTEP, self.p.NREC,
+                                                       self.p.DELTAT, self.p.t0)
             with open(os.path.join(self.output_dir, "energy.dat"), "w") as f:      # :1478-1483, four columns
                 for it in range(self.p.NSTEP):
                     f.write(f" {np.float32(it * self.p.DELTAT)} {np.float32(ek[it])} {np.float32(ep[it])} {np.float32(total[it])}\n")
-        return dict(sisvx=sx, sisvy=sy, total_energy=total, energy_kinetic=ek, energy_potential=ep,
+        return dict(sisvx=sx, sisvy=sy, sisvz=sz, total_energy=total, energy_kinetic=ek, energy_potential=ep,
                     display_log=self.display_log)
 
 

@@ -109,6 +109,8 @@ def test_cpp_driver_3d_small_grid(driver_exe, tmp_path):
     e = np.loadtxt(tmp_path / "energy.dat")
     assert d.shape == (120, 2) and e.shape == (120, 2) and np.abs(d[:, 1]).max() > 0 and np.all(np.isfinite(e))
     assert os.path.exists(tmp_path / "image000100_Vy.pnm")
+    vz = np.loadtxt(tmp_path / "Vz_file_001.dat")               # extension (quirk B7)
+    assert vz.shape == (120, 2) and np.all(np.isfinite(vz))
 
 
 def test_cpp_driver_viscoelastic_setup_uses_the_solvopt_fit(driver_exe, tmp_path):
@@ -172,6 +174,7 @@ def test_cpp_driver_3d_viscoelastic_small_grid(driver_exe, tmp_path):
     e = np.loadtxt(tmp_path / "energy.dat")
     assert d.shape == (60, 2) and e.shape == (60, 4) and np.abs(d[:, 1]).max() > 0 and np.all(np.isfinite(e))
     assert d[0, 0] == pytest.approx(-1.2 / 18.0, rel=1e-6)          # time axis minus t0 (3D-visco :1603)
+    assert np.loadtxt(tmp_path / "Vz_file_003.dat").shape == (60, 2)
     assert "Total energy =" in r.stdout
 
 

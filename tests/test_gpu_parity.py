@@ -359,3 +359,27 @@ def test_2d_4096_fourth_order_properties():
     assert np.array_equal(a, b)
     # far from the source nothing has moved yet
     assert not big_vx[: n // 2, : n // 2].any()
+
+
+def test_3d_vz_seismograms_extension():
+    """Vz seismograms (cpml_get_seismograms_vz): an extension -- the reference records Vx and Vy only although
+    its plot script reads Vz files (quirk B7).  sisvz(it, irec) must be vz(ix_rec, iy_rec, NZ/2) after step it:
+    checked against the oracle's final vz field for several run lengths, and against the solver's own plane."""
+    c0 = refcfg.cfg3d(nx=37, ny=45, nz=40, nstep=120, npml=6)
+    k = c0["nz"] // 2
+    with solver3d(c0) as s:
+        s.run(1, c0["nstep"])
+        sz = s.get_seismograms_vz()
+        sx, _ = s.get_seismograms()
+        plane = s.get_plane(2, k)
+    assert sz.shape == sx.shape and np.abs(sz).max() > 0
+    for r, (ix, iy) in enumerate(zip(c0["ix_rec"], c0["iy_rec"])):
+        assert sz[r, -1] == plane[iy - 1, ix - 1]
+    for n in (30, 75, 120):
+        c = refcfg.cfg3d(nx=37, ny=45, nz=40, nstep=n, npml=6)
+        o = O.run_3d_iso(**c, nproc=2, want_fields=True)
+        for r, (ix, iy) in enumerate(zip(c["ix_rec"], c["iy_rec"])):
+            assert sz[r, n - 1] == o["vz"][k - 1, iy - 1, ix - 1], (n, r)
+    with solver2d(refcfg.cfg2d(2, nx=60, ny=70, nstep=10, npml=6)) as s2:
+        with pytest.raises(L.CpmlError):
+            s2.get_seismograms_vz()

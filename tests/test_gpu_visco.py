@@ -168,3 +168,18 @@ def test_visco_default_grid_window_equals_small_oracle():
         assert not a[:, :, :1].any() and not a[:, :, -1:].any() and not a[:, :1, :].any() and not a[:, -1:, :].any()
         assert not a[:1].any() and not a[-1:].any()
     assert np.isfinite(sx_big).all()
+
+
+def test_visco_vz_seismograms_extension():
+    """cpml_get_seismograms_vz for the viscoelastic program (extension, quirk B7): the last sample equals the
+    solver's own vz plane NZ/2 at the receivers, and the oracle's final vz field."""
+    c = refcfg.cfgv3d()
+    k = c["nz"] // 2
+    with solver_visco(c, emulate_nproc=4) as s:
+        s.run(1, c["nstep"])
+        sz = s.get_seismograms_vz()
+        plane = s.get_plane(2, k)
+    o = O.run_3d_visco(**c, nproc=4, want_fields=True)
+    assert np.abs(sz).max() > 0
+    for r, (ix, iy) in enumerate(zip(c["ix_rec"], c["iy_rec"])):
+        assert sz[r, -1] == plane[iy - 1, ix - 1] == o["vz"][k - 1, iy - 1, ix - 1]
