@@ -236,6 +236,7 @@ int run_visco(const Args &A)
             }
             printf(" Elapsed time in seconds = %g\n Mean elapsed time per time step in seconds = %g\n\n", tcpu, tcpu / it);
             if (vnorm > STABILITY_THRESHOLD || !std::isfinite(vnorm)) { fprintf(stderr, "code became unstable and blew up\n"); return 1; }
+            if (is3d) cpml_host_write_timestamp(A.out.c_str(), it, DELTAT, vnorm, e_tot[it - 1], tcpu);   // 3D-visco :1469-1479
             write_all();
             if (A.images)
                 for (int f = 0; f < 2; f++) {
@@ -368,6 +369,7 @@ int main(int argc, char **argv)
                    " Total energy = %.15g\n Elapsed time in seconds = %g\n Mean elapsed time per time step in seconds = %g\n\n",
                    it, NSTEP, (double)(float)((it - 1) * DELTAT), vnorm, e_tot[it - 1], tcpu, tcpu / it);
             if (vnorm > STABILITY_THRESHOLD || !std::isfinite(vnorm)) { fprintf(stderr, "code became unstable and blew up\n"); return 1; }
+            if (is3d) cpml_host_write_timestamp(A.out.c_str(), it, DELTAT, vnorm, e_tot[it - 1], tcpu);   // :1219-1229
             CHECK(h, cpml_get_seismograms(h, sisvx.data(), sisvy.data()));
             cpml_host_write_seismograms(A.out.c_str(), sisvx.data(), sisvy.data(), NSTEP, NREC, DELTAT);
             if (A.images)

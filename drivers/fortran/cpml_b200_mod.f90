@@ -425,6 +425,15 @@ module cpml_b200
       integer(c_int32_t) :: ierr
     end function
 
+    function cpml_host_write_timestamp(dir, it, deltat, vsolidnorm, total_energy, tcpu) &
+        bind(C, name='cpml_host_write_timestamp') result(ierr)
+      import :: c_int32_t, c_double, c_char
+      character(kind=c_char), intent(in) :: dir(*)
+      integer(c_int32_t), value :: it
+      real(c_double), value :: deltat, vsolidnorm, total_energy, tcpu
+      integer(c_int32_t) :: ierr
+    end function
+
     function cpml_host_write_energy_3d(path, total, nt, deltat) bind(C, name='cpml_host_write_energy_3d') result(ierr)
       import :: c_int32_t, c_double, c_char
       character(kind=c_char), intent(in) :: path(*)

@@ -344,6 +344,9 @@ int32_t cpml_host_write_seismograms(const char *dir, const double *sisvx, const 
 int32_t cpml_host_write_seismograms_visco(const char *dir, const double *sisvx, const double *sisvy,
                                           const double *sispressure, int32_t nt, int32_t nrec,
                                           double deltat, double t0);
+/* timestampNNNNNN, the progress file of the 3-D programs (3D-iso :1219-1229, 3D-visco :1469-1479). */
+int32_t cpml_host_write_timestamp(const char *dir, int32_t it, double deltat, double vsolidnorm,
+                                  double total_energy, double tcpu);
 /* Vz_file_NNN.dat for cpml_get_seismograms_vz (time axis minus t0; t0 = 0 for the isotropic program). */
 int32_t cpml_host_write_seismograms_vz(const char *dir, const double *sisvz, int32_t nt, int32_t nrec,
                                        double deltat, double t0);

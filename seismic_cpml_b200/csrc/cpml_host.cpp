@@ -188,6 +188,28 @@ extern "C" int32_t cpml_host_write_seismograms(const char *dir, const double *si
     return CPML_OK;
 }
 
+// timestampNNNNNN of the 3-D programs: progress of the simulation (3D-iso :1219-1229, 3D-visco :1469-1479)
+extern "C" int32_t cpml_host_write_timestamp(const char *dir, int32_t it, double deltat, double vsolidnorm,
+                                             double total_energy, double tcpu)
+{
+    if (it < 1) return CPML_EINVAL;
+    char name[32];
+    snprintf(name, sizeof name, "timestamp%06d", it);
+    FILE *f = fopen(join(dir, name).c_str(), "w");
+    if (!f) return CPML_EINVAL;
+    const int int_tcpu = (int)tcpu, ihours = int_tcpu / 3600, iminutes = (int_tcpu - 3600 * ihours) / 60;
+    const int iseconds = int_tcpu - 3600 * ihours - 60 * iminutes;
+    fprintf(f, " Time step # %d\n", it);
+    fprintf(f, " Time:   %.8E  seconds\n", (double)(float)((it - 1) * deltat));
+    fprintf(f, " Max norm velocity vector V (m/s) =   %.16E\n", vsolidnorm);
+    fprintf(f, " Total energy =   %.16E\n", total_energy);
+    fprintf(f, " Elapsed time in seconds =   %.16E\n", tcpu);
+    fprintf(f, " Elapsed time in hh:mm:ss = %4d h %02d m %02d s\n", ihours, iminutes, iseconds);
+    fprintf(f, " Mean elapsed time per time step in seconds =   %.16E\n", tcpu / (double)it);
+    fclose(f);
+    return CPML_OK;
+}
+
 // Vz_file_NNN.dat: not written by the reference (quirk B7: its plotgnu reads them, its programs record Vx and
 // Vy only); same format as the other two, time axis minus t0 (0 for the isotropic program)
 extern "C" int32_t cpml_host_write_seismograms_vz(const char *dir, const double *sisvz, int32_t nt, int32_t nrec,

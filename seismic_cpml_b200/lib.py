@@ -106,6 +106,7 @@ SYMBOLS = {
     "cpml_host_write_seismograms": (C.c_int32, [C.c_char_p, _dp, _dp, C.c_int32, C.c_int32, C.c_double]),
     "cpml_host_write_seismograms_visco": (C.c_int32, [C.c_char_p, _dp, _dp, _dp, C.c_int32, C.c_int32, C.c_double, C.c_double]),
     "cpml_host_write_seismograms_vz": (C.c_int32, [C.c_char_p, _dp, C.c_int32, C.c_int32, C.c_double, C.c_double]),
+    "cpml_host_write_timestamp": (C.c_int32, [C.c_char_p, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double]),
     "cpml_host_write_energy_3d": (C.c_int32, [C.c_char_p, _dp, C.c_int32, C.c_double]),
     "cpml_host_write_energy_2d": (C.c_int32, [C.c_char_p, _dp, _dp, C.c_int32, C.c_double]),
     "cpml_host_create_color_image": (C.c_int32, [C.c_char_p, _dp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -504,6 +504,7 @@ class _ProgramBase:
         self.output_dir = output_dir
         self.verbose = verbose
         self.display_log = []            # (it, time, max norm, total energy)
+        self._t_start = None
 
     def _display_steps(self):
         p = self.p
@@ -517,6 +518,8 @@ class _ProgramBase:
         p = self.p
         last = p.NSTEP if nstep is None else min(nstep, p.NSTEP)
         it0 = 1
+        import time
+        self._t_start = time.time()
         for stop in self._display_steps():
             if stop > last:
                 break
@@ -542,9 +545,13 @@ class _ProgramBase:
             raise UnstableError("code became unstable and blew up")
         if self.output_dir is not None:
             os.makedirs(self.output_dir, exist_ok=True)
+            L = _lib.load()
+            if hasattr(p, "NZ"):         # timestampNNNNNN: the 3-D programs only (3D-iso :1219-1229)
+                import time
+                L.cpml_host_write_timestamp(self.output_dir.encode(), it, p.DELTAT, vnorm, float(total),
+                                            time.time() - (self._t_start or time.time()))
             self.write_seismograms()
             vx, vy = self._snapshot_fields()
-            L = _lib.load()
             for img, num in ((vx, 1), (vy, 2)):
                 img = np.ascontiguousarray(img)
                 L.cpml_host_create_color_image(self.output_dir.encode(), _lib._d(img), p.NX, p.NY, it,
