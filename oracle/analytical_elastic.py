@@ -104,3 +104,47 @@ def receiver_velocities_2d(times, mx, my, *, delta, cp, cs, rho, f0, t0, factor,
         vx[s:s + 512] = 2.0 * deltafreq * (e @ phi_x).real
         vy[s:s + 512] = 2.0 * deltafreq * (e @ phi_y).real
     return vx, vy
+
+
+def velocity_3d_visco(times, offset, i, j, *, lam_relaxed, mu_relaxed, rho, f0, t0, amplitude,
+                      tau_epsilon_nu1, tau_sigma_nu1, tau_epsilon_nu2, tau_sigma_nu2, freqmax=None):
+    """The same Green's function (Aki & Richards 4.23) in the frequency domain with the complex moduli of the
+    3-D viscoelastic program (correspondence principle): from its memory-variable equations
+    (seismic_CPML_3D_viscoelastic_MPI.f90:458-477, 1003-1077)
+        K(w)  = K_relaxed  * (1 - L + sum_l (1 + i w tau_eps1_l) / (1 + i w tau_sig1_l)),  K_relaxed = lambda + 2/3 mu,
+        mu(w) = mu_relaxed * (1 - L + sum_l (1 + i w tau_eps2_l) / (1 + i w tau_sig2_l)),
+    i.e. the classical form WITHOUT the 1/L factor, relaxed moduli as reference.  Force amplitude * g'(t) along
+    axis j, velocity component i, time dependence exp(+i w t)."""
+    times = np.asarray(times, dtype=np.float64)
+    offset = np.asarray(offset, dtype=np.float64)
+    r = float(np.sqrt(np.sum(offset * offset)))
+    gam = offset / r
+    dij = 1.0 if i == j else 0.0
+    a = PI * PI * f0 * f0
+    if freqmax is None:
+        freqmax = 8.0 * f0
+    period = 8.0 * max(float(times.max()), 4.0 * t0)
+    nfreq = int(np.ceil(freqmax * period))
+    deltafreq = freqmax / nfreq
+    w = 2.0 * PI * deltafreq * np.arange(1, nfreq)
+    L = len(tau_sigma_nu1)
+    m1 = 1.0 - L + sum((1.0 + 1j * w * e) / (1.0 + 1j * w * s) for e, s in zip(tau_epsilon_nu1, tau_sigma_nu1))
+    m2 = 1.0 - L + sum((1.0 + 1j * w * e) / (1.0 + 1j * w * s) for e, s in zip(tau_epsilon_nu2, tau_sigma_nu2))
+    kappa = (lam_relaxed + 2.0 / 3.0 * mu_relaxed) * m1
+    mu = mu_relaxed * m2
+    alpha = np.sqrt((kappa + 4.0 / 3.0 * mu) / rho)
+    beta = np.sqrt(mu / rho)
+
+    def prim(tau):          # antiderivative of tau exp(-i w tau)
+        return np.exp(-1j * w * tau) * (1j * w * tau + 1.0) / (w * w)
+
+    near = prim(r / beta) - prim(r / alpha)
+    green = ((3.0 * gam[i] * gam[j] - dij) / r ** 3 * near
+             + gam[i] * gam[j] * np.exp(-1j * w * r / alpha) / (alpha ** 2 * r)
+             - (gam[i] * gam[j] - dij) * np.exp(-1j * w * r / beta) / (beta ** 2 * r)) / (4.0 * PI * rho)
+    # velocity spectrum for the force amplitude * g'(t): (i w)^2 * amplitude * G(w) * green
+    spec = -(w ** 2) * amplitude * np.sqrt(PI / a) * np.exp(-w ** 2 / (4.0 * a)) * np.exp(-1j * w * t0) * green
+    v = np.empty(times.size)
+    for s0 in range(0, times.size, 512):
+        v[s0:s0 + 512] = 2.0 * deltafreq * (np.exp(1j * np.outer(times[s0:s0 + 512], w)) @ spec).real
+    return v

@@ -161,6 +161,9 @@ typedef struct {
     int complete_halos;   /* 0 = the reference's exchange (quirk B6: half of the 4th-order z halo is
                              never received, so the result depends on nproc); 1 = every plane the
                              stencils read is exchanged (nproc-independent; NOT the reference) */
+    int sigmazz_isotropic; /* 0 = the reference's memory-variable term of sigmazz (:1058-1060: (lambda+2mu) sum e1
+                              - 2/3 mu sum(e11+e22), quirk B14); 1 = the isotropic form sigmaxx / sigmayy use,
+                              (lambda+2/3 mu) sum e1 - 2 mu sum(e11+e22) (NOT the reference; analytical check only) */
 } oraclev3d_config;
 
 /* Runs time steps 1..nstep of seismic_CPML_3D_viscoelastic_MPI.f90:954-1430 with the MPI ranks

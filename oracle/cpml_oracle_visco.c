@@ -228,6 +228,11 @@ int oracle_run_3d_visco(const oraclev3d_config *cfg,
                             (E(s->e1, 1, i, j, k) + E(s->e1, 2, i, j, k)) + TWO * mul_relaxed * (E(s->e11, 1, i, j, k) + E(s->e11, 2, i, j, k)));
                         F(s->sigmayy, i, j, k) = F(s->sigmayy, i, j, k) + deltat * ((lambdal_relaxed + 2.0 / DIM * mul_relaxed) *
                             (E(s->e1, 1, i, j, k) + E(s->e1, 2, i, j, k)) + TWO * mul_relaxed * (E(s->e22, 1, i, j, k) + E(s->e22, 2, i, j, k)));
+                        if (cfg->sigmazz_isotropic)   /* NOT the reference (quirk B14): the isotropic form, for the analytical check */
+                            F(s->sigmazz, i, j, k) = F(s->sigmazz, i, j, k) + deltat * ((lambdal_relaxed + 2.0 / DIM * mul_relaxed) *
+                                (E(s->e1, 1, i, j, k) + E(s->e1, 2, i, j, k)) - TWO * mul_relaxed * (E(s->e11, 1, i, j, k) + E(s->e11, 2, i, j, k)
+                                + E(s->e22, 1, i, j, k) + E(s->e22, 2, i, j, k)));
+                        else
                         F(s->sigmazz, i, j, k) = F(s->sigmazz, i, j, k) + deltat * ((lambdal_relaxed + 2.0 * mul_relaxed) *
                             (E(s->e1, 1, i, j, k) + E(s->e1, 2, i, j, k)) - TWO / DIM * mul_relaxed * (E(s->e11, 1, i, j, k) + E(s->e11, 2, i, j, k)
                             + E(s->e22, 1, i, j, k) + E(s->e22, 2, i, j, k)));

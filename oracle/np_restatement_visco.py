@@ -31,7 +31,10 @@ def _p1(a, n):
 def run_3d_visco_np(*, nx, ny, nz, deltax, deltay, deltaz, deltat, lam, mu, rho, nstep, npoints_pml,
                     isource, jsource, tau_epsilon_nu1, tau_sigma_nu1, tau_epsilon_nu2, tau_sigma_nu2,
                     prof_x, prof_y, prof_z, force_x, force_y, ix_rec, iy_rec, emulate_nproc=1,
-                    **_ignored):
+                    sigmazz_isotropic=False, **_ignored):
+    """sigmazz_isotropic=True replaces the reference's memory-variable term of sigmazz (:1058-1060, quirk B14)
+    by the isotropic form its sigmaxx / sigmayy use -- NOT the reference, only for the analytical check in
+    tests/test_analytical_visco3d.py."""
     NX, NY, NZ, DT = nx, ny, nz, deltat
     sh = (NX + 2, NY + 2, NZ + 4)
     vx, vy, vz, sxx, syy, szz, sxy, sxz, syz = (np.zeros(sh) for _ in range(9))
@@ -139,8 +142,12 @@ def run_3d_visco_np(*, nx, ny, nz, deltax, deltay, deltaz, deltat, lam, mu, rho,
         q = s()
         sxx[q] = sxx[q] + DT * ((lam + 2.0 / 3.0 * mu) * (e1[0][q] + e1[1][q]) + 2.0 * mu * (e11[0][q] + e11[1][q]))
         syy[q] = syy[q] + DT * ((lam + 2.0 / 3.0 * mu) * (e1[0][q] + e1[1][q]) + 2.0 * mu * (e22[0][q] + e22[1][q]))
-        szz[q] = szz[q] + DT * ((lam + 2.0 * mu) * (e1[0][q] + e1[1][q])
-                                - 2.0 / 3.0 * mu * (e11[0][q] + e11[1][q] + e22[0][q] + e22[1][q]))
+        if sigmazz_isotropic:
+            szz[q] = szz[q] + DT * ((lam + 2.0 / 3.0 * mu) * (e1[0][q] + e1[1][q])
+                                    - 2.0 * mu * (e11[0][q] + e11[1][q] + e22[0][q] + e22[1][q]))
+        else:
+            szz[q] = szz[q] + DT * ((lam + 2.0 * mu) * (e1[0][q] + e1[1][q])
+                                    - 2.0 / 3.0 * mu * (e11[0][q] + e11[1][q] + e22[0][q] + e22[1][q]))
         sxx[q] = sxx[q] + (l2m_u * duxdx + lam_u * duydy + lam_u * duzdz) * DT
         syy[q] = syy[q] + (lam_u * duxdx + l2m_u * duydy + lam_u * duzdz) * DT
         szz[q] = szz[q] + (lam_u * duxdx + lam_u * duydy + l2m_u * duzdz) * DT

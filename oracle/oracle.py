@@ -49,7 +49,7 @@ class OracleV3DConfig(C.Structure):
                 ("isource", C.c_int), ("jsource", C.c_int), ("nrec", C.c_int),
                 ("tau_epsilon_nu1", C.c_double * 2), ("tau_sigma_nu1", C.c_double * 2),
                 ("tau_epsilon_nu2", C.c_double * 2), ("tau_sigma_nu2", C.c_double * 2),
-                ("complete_halos", C.c_int)]
+                ("complete_halos", C.c_int), ("sigmazz_isotropic", C.c_int)]
 
 
 class OracleV2DConfig(C.Structure):
@@ -261,13 +261,13 @@ VISCO_FIELDS = ("vx", "vy", "vz", "sigmaxx", "sigmayy", "sigmazz", "sigmaxy", "s
 
 def run_3d_visco(*, nx, ny, nz, nproc, deltax, deltay, deltaz, deltat, lam, mu, rho, nstep, npoints_pml,
                  isource, jsource, tau_epsilon_nu1, tau_sigma_nu1, tau_epsilon_nu2, tau_sigma_nu2,
-                 prof_x, prof_y, prof_z, force_x, force_y, ix_rec, iy_rec, complete_halos=False,
+                 prof_x, prof_y, prof_z, force_x, force_y, ix_rec, iy_rec, complete_halos=False, sigmazz_isotropic=False,
                  want_fields=False, kind="golden", **_ignored):
     nrec = len(ix_rec)
     A2 = C.c_double * 2
     cfg = OracleV3DConfig(nx, ny, nz, nproc, deltax, deltay, deltaz, deltat, lam, mu, rho, nstep,
                           npoints_pml, isource, jsource, nrec, A2(*tau_epsilon_nu1), A2(*tau_sigma_nu1),
-                          A2(*tau_epsilon_nu2), A2(*tau_sigma_nu2), int(complete_halos))
+                          A2(*tau_epsilon_nu2), A2(*tau_sigma_nu2), int(complete_halos), int(sigmazz_isotropic))
     px = [_f64(prof_x[k]) for k in _PK]
     py = [_f64(prof_y[k]) for k in _PK]
     pz = [_f64(prof_z[k]) for k in _PK]
