@@ -196,3 +196,43 @@ def test_fortran_viscoelastic_driver_keeps_the_reference_parameter_surface():
     f90 = open(os.path.join(DRV, "fortran", "cpml_b200_mod.f90")).read()
     for call in re.findall(r"\b(cpml_[a-z0-9_]+)\(", src):
         assert ("function " + call + "(") in f90 or ("subroutine " + call + "(") in f90, call
+
+
+def _split_args(s):
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        depth += ch == "("
+        depth -= ch == ")"
+        if ch == "," and depth == 0:
+            out.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    out.append(cur)
+    return [a for a in out if a.strip()]
+
+
+def test_every_fortran_driver_calls_the_module_with_matching_arity():
+    """The Fortran drivers cannot be compiled here; at least every call into the library must name a function
+    the module binds and pass the number of arguments the binding declares."""
+    mod = re.sub(r"&\s*\n\s*", " ", open(os.path.join(DRV, "fortran", "cpml_b200_mod.f90")).read())
+    arity = {m.group(1): len([a for a in m.group(2).split(",") if a.strip()])
+             for m in re.finditer(r"(?:function|subroutine)\s+(cpml_[a-z0-9_]+)\s*\(([^)]*)\)", mod)}
+    drivers = sorted(f for f in os.listdir(os.path.join(DRV, "fortran")) if f.startswith("seismic_") and f.endswith(".f90"))
+    assert len(drivers) >= 3
+    for fn in drivers:
+        src = open(os.path.join(DRV, "fortran", fn)).read()
+        src = "\n".join(line for line in src.split("\n") if not line.lstrip().startswith("!"))
+        src = re.sub(r"&\s*\n\s*", " ", src)
+        calls = 0
+        for m in re.finditer(r"\b(cpml_[a-z0-9_]+)\(", src):
+            name, k, depth = m.group(1), m.end(), 1
+            while depth > 0:
+                depth += src[k] == "("
+                depth -= src[k] == ")"
+                k += 1
+            assert name in arity, (fn, name)
+            assert arity[name] == len(_split_args(src[m.end():k - 1])), (fn, name)
+            calls += 1
+        assert calls >= 15, fn
+        assert src.count("program ") >= 2 and "use cpml_b200" in src and "implicit none" in src, fn
