@@ -43,7 +43,7 @@ module cpml_b200
     integer(c_int32_t) :: rheology
     integer(c_int32_t) :: emulate_nproc
     integer(c_int32_t) :: compute_energy
-    integer(c_int32_t) :: reserved_i(1)
+    integer(c_int32_t) :: sigmazz_isotropic   ! 3-D viscoelastic: 0 = the reference's sigmazz memory term (quirk B14) ; 1 = isotropic
     real(c_double) :: deltax, deltay, deltaz
     real(c_double) :: deltat
     real(c_double) :: lambda, mu, lambdaplustwomu, rho

@@ -82,7 +82,7 @@ program seismic_CPML_2D_iso_b200
   cfg%rheology = 0
   cfg%emulate_nproc = 0
   cfg%compute_energy = 0
-  cfg%reserved_i = 0
+  cfg%sigmazz_isotropic = 0
   cfg%deltax = DELTAX;  cfg%deltay = DELTAY;  cfg%deltaz = 0.d0;  cfg%deltat = DELTAT
   cfg%lambda = 0.d0;  cfg%mu = 0.d0;  cfg%lambdaplustwomu = 0.d0;  cfg%rho = 0.d0;  cfg%cp = cp
   cfg%reserved_d = 0.d0

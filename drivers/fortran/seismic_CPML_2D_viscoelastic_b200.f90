@@ -115,7 +115,7 @@ program seismic_CPML_2D_visco_b200
   cfg%rheology = 1
   cfg%emulate_nproc = 0
   cfg%compute_energy = b2i(COMPUTE_ENERGY)
-  cfg%reserved_i = 0
+  cfg%sigmazz_isotropic = 0
   cfg%deltax = DELTAX;  cfg%deltay = DELTAY;  cfg%deltaz = 0.d0;  cfg%deltat = DELTAT
   cfg%lambda = 0.d0;  cfg%mu = 0.d0;  cfg%lambdaplustwomu = 0.d0;  cfg%rho = 0.d0;  cfg%cp = 0.d0
   cfg%reserved_d = 0.d0

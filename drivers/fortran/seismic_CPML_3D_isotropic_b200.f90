@@ -79,7 +79,7 @@ program seismic_CPML_3D_iso_b200
   cfg%rheology = 0
   cfg%emulate_nproc = 0
   cfg%compute_energy = 0
-  cfg%reserved_i = 0
+  cfg%sigmazz_isotropic = 0
   cfg%deltax = DELTAX;  cfg%deltay = DELTAY;  cfg%deltaz = DELTAZ;  cfg%deltat = DELTAT
   cfg%lambda = lambda;  cfg%mu = mu;  cfg%lambdaplustwomu = lambdaplustwomu;  cfg%rho = rho;  cfg%cp = cp
   cfg%reserved_d = 0.d0

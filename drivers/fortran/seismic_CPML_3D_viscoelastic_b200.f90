@@ -107,7 +107,7 @@ program seismic_visco_CPML_3D_b200
   cfg%rheology = 1
   cfg%emulate_nproc = NPROC
   cfg%compute_energy = 0
-  cfg%reserved_i = 0
+  cfg%sigmazz_isotropic = 0
   cfg%deltax = DELTAX;  cfg%deltay = DELTAY;  cfg%deltaz = DELTAZ;  cfg%deltat = DELTAT
   cfg%lambda = lambda;  cfg%mu = mu;  cfg%lambdaplustwomu = 0.d0;  cfg%rho = rho;  cfg%cp = cp*sqrt_taumax
   cfg%reserved_d = 0.d0

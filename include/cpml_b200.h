@@ -101,7 +101,12 @@ typedef struct cpml_config {
     int32_t compute_energy;  /* 2-D viscoelastic only: COMPUTE_ENERGY of 2D-visco-4th :201 (.false. in the
                                 reference, the energy traces then stay zero); the other solvers always
                                 compute the energy, as their programs do                      */
-    int32_t reserved_i[1];
+    int32_t sigmazz_isotropic; /* 3-D viscoelastic only.  0 = the reference: the memory-variable term of sigmazz is
+                                (lambda+2mu) sum e1 - 2/3 mu sum(e11+e22) (3D-visco :1058-1060), which is not the
+                                isotropic form its sigmaxx / sigmayy use (6 % misfit to the
+                                analytical viscoelastic solution, tests/test_analytical_visco3d.py).  1 = the
+                                isotropic form (lambda+2/3 mu) sum e1 - 2 mu sum(e11+e22): NOT the reference,
+                                for users who want the physics (1.6 % misfit)                              */
     double deltax, deltay, deltaz;   /* DELTAX, DELTAY, DELTAZ                           */
     double deltat;                   /* DELTAT                                           */
     /* homogeneous medium of the 3-D program (:139-144); the 2-D programs take arrays

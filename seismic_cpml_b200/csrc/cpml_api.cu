@@ -960,6 +960,8 @@ static ParamsV3D make_pv(cpml_handle *h, int it)
     p.lam23mu = lambdal_relaxed + 2.0 / DIM * mul_relaxed;
     p.two_mu = TWO * mul_relaxed;
     p.two_thirds_mu = TWO / DIM * mul_relaxed;
+    p.szz_e1 = c.sigmazz_isotropic ? p.lam23mu : p.l2m_r;
+    p.szz_dev = c.sigmazz_isotropic ? p.two_mu : p.two_thirds_mu;
     p.nzl_e = c.emulate_nproc > 1 ? c.nz / c.emulate_nproc : c.nz;
     p.it = it;
     p.isrc = c.isource; p.jsrc = c.jsource;

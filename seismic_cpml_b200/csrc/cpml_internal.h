@@ -233,6 +233,8 @@ struct ParamsV3D {
     double odx, ody, odz, dt, dt_over_rho;
     // constants of :982-987 and :458-477, evaluated on the host in the reference's order
     double lam, mu, l2m_r, lam23mu, two_mu, two_thirds_mu, lam_u, mu_u, l2m_u;
+    double szz_e1, szz_dev;   // coefficients of the sigmazz memory-variable term: (l2m_r, two_thirds_mu) as in the
+                              // reference (:1058-1060, quirk B14) or (lam23mu, two_mu) with cfg.sigmazz_isotropic
     double phi1[2], phi2[2], tauinv1[2], tauinv2[2], den1[2], den2[2];   // den = 1 - dt*0.5*tauinv
     double rden1[2], rden2[2];                                           // RN(1/den) for div_exact
     int nzl_e;                // plane count of one EMULATED reference slab (quirk B6); nz: none

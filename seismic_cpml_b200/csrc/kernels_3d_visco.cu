@@ -274,7 +274,7 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
                     // relaxed moduli times the memory variables (:1054-1060)
                     sxx = sxx + dt * (p.lam23mu * (e1.x + e1.y) + p.two_mu * (e11.x + e11.y));
                     syy = syy + dt * (p.lam23mu * (e1.x + e1.y) + p.two_mu * (e22.x + e22.y));
-                    szz = szz + dt * (p.l2m_r * (e1.x + e1.y) - p.two_thirds_mu * (e11.x + e11.y + e22.x + e22.y));
+                    szz = szz + dt * (p.szz_e1 * (e1.x + e1.y) - p.szz_dev * (e11.x + e11.y + e22.x + e22.y));   // quirk B14
                     // unrelaxed elastic term (:1064-1077)
                     sxx = sxx + (p.l2m_u * duxdx + p.lam_u * duydy + p.lam_u * duzdz) * dt;
                     syy = syy + (p.lam_u * duxdx + p.l2m_u * duydy + p.lam_u * duzdz) * dt;

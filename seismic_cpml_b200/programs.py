@@ -224,6 +224,7 @@ class Params3DVisco:
     ALPHA_MAX_PML: float | None = None
     Rcoef: float = 0.0001                # :541
     energy_bug_compat: bool = True
+    sigmazz_isotropic: bool = False      # True: the isotropic memory-variable term in sigmazz, NOT the reference (quirk B14)
 
     def __post_init__(self):
         if self.N_SLS != 2:
@@ -456,7 +457,8 @@ def make_solver_3d_visco(p: Params3DVisco, s: Setup, *, nslabs=1, slab_rank=0, d
     sol = _lib.Solver(ndim=3, order=4, rheology=1, emulate_nproc=p.NPROC, nx=p.NX, ny=p.NY, nz=p.NZ,
                       nstep=p.NSTEP, npoints_pml=p.NPOINTS_PML, nrec=p.NREC, isource=p.ISOURCE,
                       jsource=p.JSOURCE, ksource=p.KSOURCE, nslabs=nslabs, slab_rank=slab_rank, device=device,
-                      energy_bug_compat=p.energy_bug_compat, deltax=p.DELTAX, deltay=p.DELTAY,
+                      energy_bug_compat=p.energy_bug_compat, sigmazz_isotropic=p.sigmazz_isotropic,
+                      deltax=p.DELTAX, deltay=p.DELTAY,
                       deltaz=p.DELTAZ, deltat=p.DELTAT, lam=p.lam, mu=p.mu, rho=p.rho,
                       cp=p.cp * math.sqrt(p.taumax))
     sol.set_profiles(_lib.AXIS_X, s.prof_x)

@@ -24,8 +24,8 @@ TOL_ENERGY = 1e-11
 FV = L.FIELDS_3D_VISCO
 
 
-def solver_visco(c, emulate_nproc=0, nslabs=1, slab_rank=0, device=-1):
-    s = L.Solver(ndim=3, order=4, rheology=1, emulate_nproc=emulate_nproc, nx=c["nx"], ny=c["ny"], nz=c["nz"],
+def solver_visco(c, emulate_nproc=0, nslabs=1, slab_rank=0, device=-1, **kw):
+    s = L.Solver(ndim=3, order=4, rheology=1, emulate_nproc=emulate_nproc, nx=c["nx"], ny=c["ny"], nz=c["nz"], **kw,
                  nstep=c["nstep"], npoints_pml=c["npoints_pml"], nrec=len(c["ix_rec"]), isource=c["isource"],
                  jsource=c["jsource"], nslabs=nslabs, slab_rank=slab_rank, device=device, deltax=c["deltax"],
                  deltay=c["deltay"], deltaz=c["deltaz"], deltat=c["deltat"], lam=c["lam"], mu=c["mu"],
@@ -183,3 +183,18 @@ def test_visco_vz_seismograms_extension():
     assert np.abs(sz).max() > 0
     for r, (ix, iy) in enumerate(zip(c["ix_rec"], c["iy_rec"])):
         assert sz[r, -1] == plane[iy - 1, ix - 1] == o["vz"][k - 1, iy - 1, ix - 1]
+
+
+def test_visco_sigmazz_isotropic_option_matches_the_oracle_variant():
+    """cfg.sigmazz_isotropic = 1 (NOT the reference: the isotropic memory-variable term in sigmazz, quirk B14):
+    bit-identical to the oracle run with the same flag, and different from the reference run."""
+    c = refcfg.cfgv3d()
+    with solver_visco(c, emulate_nproc=4, sigmazz_isotropic=True) as s:
+        s.run(1, c["nstep"])
+        sx, sy = s.get_seismograms()
+        szz = s.get_field(5)
+    o = O.run_3d_visco(**c, nproc=4, sigmazz_isotropic=True, want_fields=True)
+    r = O.run_3d_visco(**c, nproc=4)
+    assert np.array_equal(sx, o["sisvx"]) and np.array_equal(sy, o["sisvy"])
+    assert np.array_equal(szz, o["sigmazz"])
+    assert not np.array_equal(sx, r["sisvx"])
