@@ -69,3 +69,37 @@ def test_numpy_restatement_follows_the_c_oracle_with_the_isotropic_term_too():
     assert np.array_equal(a["sisvx"], b["sisvx"]) and np.array_equal(a["sisvy"], b["sisvy"])
     r = O.run_3d_visco(**c, nproc=1)
     assert not np.array_equal(a["sisvx"], r["sisvx"])
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_3d_viscoelastic_gpu_against_the_analytical_solution():
+    """The same two comparisons through the C ABI on the GPU (cfg.sigmazz_isotropic = 1 / 0, one slab)."""
+    from seismic_cpml_b200 import lib as L
+    c = _cfg()
+    tau = {k: c[k] for k in ("tau_epsilon_nu1", "tau_sigma_nu1", "tau_epsilon_nu2", "tau_sigma_nu2")}
+    t = (np.arange(NSTEP) + 0.5) * c["deltat"]
+    kw = dict(lam_relaxed=c["lam"], mu_relaxed=c["mu"], rho=c["rho"], f0=F0, t0=1.2 / F0, amplitude=1e7 * DX ** 3, **tau)
+    ax = E.velocity_3d_visco(t, ((MX - 0.5) * DX, (MY - 0.5) * DX, 0.0), 0, 1, **kw)
+    ay = E.velocity_3d_visco(t, (MX * DX, MY * DX, 0.0), 1, 1, **kw)
+    misfit = {}
+    for iso in (True, False):
+        s = L.Solver(ndim=3, order=4, rheology=1, emulate_nproc=0, sigmazz_isotropic=iso, nx=c["nx"], ny=c["ny"], nz=c["nz"],
+                     nstep=c["nstep"], npoints_pml=c["npoints_pml"], nrec=1, isource=c["isource"], jsource=c["jsource"],
+                     deltax=c["deltax"], deltay=c["deltay"], deltaz=c["deltaz"], deltat=c["deltat"], lam=c["lam"],
+                     mu=c["mu"], rho=c["rho"], cp=c["cp_eff"])
+        with s:
+            s.set_profiles(L.AXIS_X, c["prof_x"])
+            s.set_profiles(L.AXIS_Y, c["prof_y"])
+            s.set_profiles(L.AXIS_Z, c["prof_z"])
+            s.set_attenuation(c["tau_epsilon_nu1"], c["tau_sigma_nu1"], c["tau_epsilon_nu2"], c["tau_sigma_nu2"])
+            s.set_source_series(c["force_x"], c["force_y"])
+            s.set_receivers(c["ix_rec"], c["iy_rec"])
+            s.run(1, NSTEP)
+            sx, sy = s.get_seismograms()
+        misfit[iso] = (_rel(sx[0], ax), _rel(sy[0], ay))
+    print("3-D viscoelastic, GPU vs analytical: isotropic sigmazz term", misfit[True], "reference term", misfit[False])
+    assert max(misfit[True]) < 0.025
+    assert 0.04 < misfit[False][0] < 0.09 and misfit[False][1] < 0.04
