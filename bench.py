@@ -99,6 +99,39 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# The workloads as plain numbers (BASELINE.json configs), shared by both arms: the CPU arm builds its inputs from
+# these with oracle/workloads.py and never touches the product package.
+WORKLOADS = {
+    "cfg3": dict(kind="3d", nx=101, ny=641, nz_per_gpu=640, deltat=1.6e-3, npml=10),
+    "cfg4": dict(kind="3d", nx=1024, ny=1024, nz_per_gpu=128, deltat=1.6e-3, npml=10),
+    "cfg5": dict(kind="3dv", nx=1024, ny=1024, nz_per_gpu=128, deltat=4e-4, npml=10),
+    "cfg5d": dict(kind="3dv", nx=210, ny=800, nz_per_gpu=220, deltat=4e-4, npml=10),
+    "cfg2": dict(kind="2d", nx=4096, ny=4096, nz_per_gpu=1, deltat=1e-3, npml=10, order=4),
+    "cfg6": dict(kind="2dv", nx=2001, ny=2001, nz_per_gpu=1, deltat=2.2e-4, npml=10, order=4),
+}
+
+
+def common_config(name, n_gpus):
+    """The `config` object of the JSON line: identical in both arms (the driver compares them)."""
+    w = WORKLOADS[name]
+    kind = w["kind"]
+    nz = w["nz_per_gpu"] * n_gpus if kind in ("3d", "3dv") else 1
+    if kind == "2d":
+        label = f"seismic_CPML_2D_isotropic_fourth_order {w['nx']}x{w['ny']}"
+    elif kind == "2dv":
+        label = f"seismic_CPML_2D_velocity_and_stress_fourth_order_viscoelastic (N_SLS=3) {w['nx']}x{w['ny']}"
+    elif kind == "3dv":
+        label = (f"seismic_CPML_3D_viscoelastic_MPI (4th order, N_SLS=2, reference NPROC={_visco_nproc(n_gpus, nz)} emulated): "
+                 f"{w['nx']}x{w['ny']}x{nz} ({w['nx']}x{w['ny']}x{w['nz_per_gpu']} per GPU, z-slabs)")
+    else:
+        tag = "default grid" if name == "cfg3" else "~1024^3 scaled grid"
+        label = (f"seismic_CPML_3D_isotropic_MPI_OpenMP {tag}: {w['nx']}x{w['ny']}x{nz} "
+                 f"({w['nx']}x{w['ny']}x{w['nz_per_gpu']} per GPU, z-slabs)")
+    return {"workload": label, "grid": [w["nx"], w["ny"], nz], "npoints_pml": w["npml"], "deltat": w["deltat"],
+            "parallelism": f"z-slabs x{n_gpus}" if n_gpus > 1 else "single GPU / whole grid",
+            "l2": "the state streamed every step (0.5-10 GB per rank) is far larger than the 126 MB L2; no flush needed"}
+
+
 def workload_params(name, n_gpus, nstep):
     from seismic_cpml_b200 import programs as P
     if name == "cfg3":
@@ -128,19 +161,6 @@ def _visco_nproc(n_gpus, nz):
     return 1
 
 
-def workload_label(name, p, kind, n_gpus):
-    if kind == "2d":
-        return f"seismic_CPML_2D_isotropic_fourth_order {p.NX}x{p.NY}"
-    if kind == "2dv":
-        return f"seismic_CPML_2D_velocity_and_stress_fourth_order_viscoelastic (N_SLS=3) {p.NX}x{p.NY}"
-    if kind == "3dv":
-        return (f"seismic_CPML_3D_viscoelastic_MPI (4th order, N_SLS=2, reference NPROC={p.NPROC} emulated): "
-                f"{p.NX}x{p.NY}x{p.NZ} ({p.NX}x{p.NY}x{p.NZ // n_gpus} per GPU, z-slabs)")
-    per = f"{p.NX}x{p.NY}x{p.NZ // n_gpus} per GPU"
-    tag = "default grid" if name == "cfg3" else "~1024^3 scaled grid"
-    return f"seismic_CPML_3D_isotropic_MPI_OpenMP {tag}: {p.NX}x{p.NY}x{p.NZ} ({per}, z-slabs)"
-
-
 # ------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle's OpenMP build on the host cores
 # ------------------------------------------------------------------------------------
@@ -158,125 +178,101 @@ def _use_all_host_threads():
     O.set_num_threads(n if _CPU_THREADS is None else _CPU_THREADS)
 
 
-def _one_thread(fn, *a):
-    """The same measurement with one OpenMP thread (report both)."""
-    global _CPU_THREADS
-    _CPU_THREADS = 1
+def _mem_available_bytes():
     try:
-        return fn(*a)
-    finally:
-        _CPU_THREADS = None
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) * 1024
+    except Exception:
+        pass
+    return 16 << 30
 
 
-def oracle_3d_gpts(p, nz_sample, steps, warmup):
-    """Times `steps` time steps (after `warmup`) of the CPU restatement on a z-reduced sample
-    of the workload: NX x NY x nz_sample, same spacing / time step / PML / source law."""
+def _timed(run, kw, steps, warmup, **extra):
     from oracle import oracle as O
-    from seismic_cpml_b200 import programs as P
-    q = P.Params3DIso(NX=p.NX, NY=p.NY, NZ=nz_sample, NSTEP=steps + warmup, DELTAX=p.DELTAX, DELTAT=p.DELTAT)
-    s = P.setup_3d(q)
     _use_all_host_threads()
     O.set_ftz(True)                 # cf. reference Makefile:18 (-ftz "critical for performance")
     O.set_warmup_steps(warmup)
-    O.run_3d_iso(nx=q.NX, ny=q.NY, nz=q.NZ, nproc=2, deltax=q.DELTAX, deltay=q.DELTAY, deltaz=q.DELTAZ,
-                 deltat=q.DELTAT, lam=q.lam, mu=q.mu, lambdaplustwomu=q.lambdaplustwomu, rho=q.rho,
-                 nstep=q.NSTEP, npoints_pml=q.NPOINTS_PML, isource=q.ISOURCE, jsource=q.JSOURCE,
-                 prof_x=s.prof_x, prof_y=s.prof_y, prof_z=s.prof_z, force_x=s.force_x, force_y=s.force_y,
-                 ix_rec=s.ix_rec, iy_rec=s.iy_rec, kind="timed")
+    run(**kw, kind="timed", **extra)
     sec = O.last_loop_seconds()
     O.set_warmup_steps(0)
-    pts = float(q.NX) * q.NY * q.NZ * steps
-    return pts / sec / 1e9, sec, O.num_threads()
+    return sec, O.num_threads()
 
 
-def oracle_3dv_gpts(p, nz_sample, steps, warmup):
-    """The viscoelastic CPU restatement on a z-reduced sample (NX x NY x nz_sample, 4 emulated slabs)."""
+def cpu_arm(name, n_gpus, steps, warmup, exact=True):
+    """Times `steps` time steps (after `warmup`) of the CPU restatement of the reference loop on the workload's
+    own grid (exact=True and the host has the memory for the reference's full-grid arrays), else on a bounded
+    sample of it.  Inputs come from oracle/workloads.py.  Returns (Gpts/s, seconds, threads, sample text)."""
     from oracle import oracle as O
-    from seismic_cpml_b200 import programs as P
-    q = P.Params3DVisco(NX=p.NX, NY=min(p.NY, 256), NZ=nz_sample, NSTEP=steps + warmup, NPROC=4)
-    s = P.setup_3d_visco(q)
-    _use_all_host_threads()
-    O.set_ftz(True)
-    O.set_warmup_steps(warmup)
-    O.run_3d_visco(nx=q.NX, ny=q.NY, nz=q.NZ, nproc=4, deltax=q.DELTAX, deltay=q.DELTAY, deltaz=q.DELTAZ,
-                   deltat=q.DELTAT, lam=q.lam, mu=q.mu, rho=q.rho, nstep=q.NSTEP, npoints_pml=q.NPOINTS_PML,
-                   isource=q.ISOURCE, jsource=q.JSOURCE, tau_epsilon_nu1=q.tau_epsilon_nu1,
-                   tau_sigma_nu1=q.tau_sigma_nu1, tau_epsilon_nu2=q.tau_epsilon_nu2, tau_sigma_nu2=q.tau_sigma_nu2,
-                   prof_x=s.prof_x, prof_y=s.prof_y, prof_z=s.prof_z, force_x=s.force_x, force_y=s.force_y,
-                   ix_rec=s.ix_rec, iy_rec=s.iy_rec, kind="timed")
-    sec = O.last_loop_seconds()
-    O.set_warmup_steps(0)
-    return float(q.NX) * q.NY * q.NZ * steps / sec / 1e9, sec, O.num_threads()
-
-
-def oracle_2dv_gpts(p, n_sample, steps, warmup):
-    from oracle import oracle as O
-    from seismic_cpml_b200 import programs as P
-    q = P.Params2DVisco(order=p.order, NX=n_sample, NY=n_sample, NSTEP=steps + warmup, xsource=n_sample * 0.75, ysource=n_sample * 0.75,
-                        xdeb=n_sample, ydeb=n_sample, xfin=n_sample, yfin=n_sample)
-    s = P.setup_2d_visco(q)
-    O.set_ftz(True)
-    O.set_warmup_steps(warmup)
-    O.run_2d_visco(order=q.order, nx=q.NX, ny=q.NY, deltax=q.DELTAX, deltay=q.DELTAY, deltat=q.DELTAT, nstep=q.NSTEP,
-                   npoints_pml=q.NPOINTS_PML, isource=q.ISOURCE, jsource=q.JSOURCE, lam=s.material[0], mu=s.material[1],
-                   rho=s.material[2], tau_epsilon_nu1=q.tau_epsilon_nu1, tau_sigma_nu1=q.tau_sigma_nu1,
-                   tau_epsilon_nu2=q.tau_epsilon_nu2, tau_sigma_nu2=q.tau_sigma_nu2, prof_x=s.prof_x, prof_y=s.prof_y,
-                   force_x=s.force_x, force_y=s.force_y, ix_rec=s.ix_rec, iy_rec=s.iy_rec, kind="timed")
-    sec = O.last_loop_seconds()
-    O.set_warmup_steps(0)
-    return float(q.NX) * q.NY * steps / sec / 1e9, sec, 1      # the 2-D programs are serial
-
-
-def oracle_2d_gpts(p, n_sample, steps, warmup):
-    from oracle import oracle as O
-    from seismic_cpml_b200 import programs as P
-    q = P.Params2DIso(order=p.order, NX=n_sample, NY=n_sample, NSTEP=steps + warmup)
-    s = P.setup_2d(q)
-    O.set_ftz(True)
-    O.set_warmup_steps(warmup)
-    O.run_2d(order=q.order, nx=q.NX, ny=q.NY, deltax=q.DELTAX, deltay=q.DELTAY, deltat=q.DELTAT, nstep=q.NSTEP,
-             npoints_pml=q.NPOINTS_PML, isource=q.ISOURCE, jsource=q.JSOURCE, lam=s.material[0], mu=s.material[1],
-             rho=s.material[2], prof_x=s.prof_x, prof_y=s.prof_y, force_x=s.force_x, force_y=s.force_y,
-             ix_rec=s.ix_rec, iy_rec=s.iy_rec, kind="timed")
-    sec = O.last_loop_seconds()
-    O.set_warmup_steps(0)
-    return float(q.NX) * q.NY * steps / sec / 1e9, sec, 1      # the 2-D programs are serial
+    from oracle import workloads as WL
+    w = WORKLOADS[name]
+    kind, nx, ny = w["kind"], w["nx"], w["ny"]
+    nstep = steps + warmup
+    avail = _mem_available_bytes()
+    if kind == "3d":
+        nz = w["nz_per_gpu"] * n_gpus
+        need = lambda nz_: 8.0 * nx * ny * (nz_ + 4) * 27 * 1.15     # 9 fields + 18 full-grid memory variables (:275)
+        nz_s = nz
+        if not exact:
+            nz_s = min(nz, 160)
+        while need(nz_s) > 0.6 * avail and nz_s > 40:
+            nz_s = max(40, nz_s // 2 // 2 * 2)
+        kw = WL.iso3d(nx, ny, nz_s, nstep, dt=w["deltat"], npml=w["npml"])
+        sec, cores = _timed(O.run_3d_iso, kw, steps, warmup, nproc=2)
+        pts = float(nx) * ny * nz_s * steps
+        what = (f"the workload grid itself, {nx}x{ny}x{nz_s}" if nz_s == nz else
+                f"{nx}x{ny}x{nz_s} z-reduced sample of the workload grid")
+        sample = (f"{what} (2 emulated MPI slabs), {steps} timed steps after {warmup}; full-grid memory variables and "
+                  "separate Dirichlet/energy passes as in the reference; FTZ/DAZ on; inputs from oracle/workloads.py")
+    elif kind == "3dv":
+        nz = w["nz_per_gpu"] * n_gpus
+        need = lambda ny_, nz_: 8.0 * (nx + 2) * (ny_ + 2) * (nz_ + 16) * 45 * 1.15   # 45 full arrays (SURVEY a17)
+        ny_s, nz_s = ny, nz
+        if not exact:
+            ny_s, nz_s = min(ny, 256), min(nz, 80)
+        while need(ny_s, nz_s) > 0.6 * avail and (nz_s > 40 or ny_s > 128):
+            if nz_s > 40: nz_s = max(40, nz_s // 2 // 4 * 4)
+            else: ny_s = max(128, ny_s // 2)
+        nproc = _visco_nproc(n_gpus, nz) if nz_s == nz else 4
+        kw = WL.visco3d(nx, ny_s, nz_s, nstep, dt=w["deltat"], npml=w["npml"])
+        sec, cores = _timed(O.run_3d_visco, kw, steps, warmup, nproc=nproc)
+        pts = float(nx) * ny_s * nz_s * steps
+        what = (f"the workload grid itself, {nx}x{ny_s}x{nz_s}" if (ny_s, nz_s) == (ny, nz) else
+                f"{nx}x{ny_s}x{nz_s} reduced sample of the workload grid")
+        sample = (f"{what} ({nproc} emulated MPI slabs), {steps} timed steps after {warmup}; full-grid memory variables "
+                  "and separate Dirichlet/energy passes as in the reference; FTZ/DAZ on; inputs from oracle/workloads.py")
+    elif kind == "2dv":
+        n_s = nx if exact else 1001
+        kw = WL.visco2d(w["order"], n_s, n_s, nstep, dt=w["deltat"], npml=w["npml"])
+        sec, cores = _timed(O.run_2d_visco, kw, steps, warmup)
+        cores = 1                                               # the 2-D programs are serial
+        pts = float(n_s) * n_s * steps
+        sample = f"{n_s}x{n_s} grid, {steps} timed steps after {warmup}, serial like the reference; inputs from oracle/workloads.py"
+    else:
+        n_s = nx if exact else 1024
+        kw = WL.iso2d(w["order"], n_s, n_s, nstep, npml=w["npml"])
+        sec, cores = _timed(O.run_2d, kw, steps, warmup)
+        cores = 1
+        pts = float(n_s) * n_s * steps
+        sample = f"{n_s}x{n_s} grid, {steps} timed steps after {warmup}, serial like the reference; inputs from oracle/workloads.py"
+    return pts / sec / 1e9, sec, cores, sample
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    p, kind = workload_params(args.workload, args.gpus, args.steps + args.warmup)
-    if kind == "2dv":
-        n_s = 1001
-        v, sec, cores = oracle_2dv_gpts(p, n_s, args.steps, args.warmup)
-        sample = f"{n_s}x{n_s} sample grid, {args.steps} timed steps after {args.warmup}, serial like the reference"
-    elif kind == "3dv":
-        nz_s = 40
-        v, sec, cores = oracle_3dv_gpts(p, nz_s, args.steps, args.warmup)
-        sample = (f"{p.NX}x{min(p.NY, 256)}x{nz_s} reduced sample of the workload grid (4 emulated MPI slabs), "
-                  f"{args.steps} timed steps after {args.warmup}; full-grid memory variables and separate "
-                  "Dirichlet/energy passes as in the reference; FTZ/DAZ on")
-    elif kind == "3d":
-        nz_s = 160
-        v, sec, cores = oracle_3d_gpts(p, nz_s, args.steps, args.warmup)
-        sample = (f"{p.NX}x{p.NY}x{nz_s} z-reduced sample of the workload grid (2 emulated MPI slabs), "
-                  f"{args.steps} timed steps after {args.warmup}; full-grid memory variables and separate "
-                  "Dirichlet/energy passes as in the reference; FTZ/DAZ on")
-    else:
-        n_s = 2048
-        v, sec, cores = oracle_2d_gpts(p, n_s, args.steps, args.warmup)
-        sample = f"{n_s}x{n_s} sample grid, {args.steps} timed steps after {args.warmup}, serial like the reference"
+    kind = WORKLOADS[args.workload]["kind"]
+    v, sec, cores, sample = cpu_arm(args.workload, args.gpus, args.steps, args.warmup, exact=True)
     line = {"impl": "reference", "metric": metric_name(kind), "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (fields start at zero, analytic source; no RNG)",
-            "config": {"workload": workload_label(args.workload, p, kind, args.gpus)},
+            "config": common_config(args.workload, args.gpus),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                             "note": "C/OpenMP restatement of the reference loops (oracle/cpml_oracle.c, "
+                             "note": "C/OpenMP restatement of the reference loops (oracle/cpml_oracle*.c, "
                                      "gcc -O3 -march=x86-64-v3 -fopenmp); the Fortran reference cannot be "
-                                     "compiled in this image"},
+                                     "compiled in this image (no Fortran compiler, no MPI)"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
     return 0
@@ -419,46 +415,49 @@ def run_b200(args):
     e2e_value = pts_step_rank * world * K / float(te.item()) / 1e9
     finite = bool(np.isfinite(en[0]).all() and np.isfinite(sx).all())
 
-    # ---- roofline of the dominant kernel (stress: 15 of the 27 words per point)
+    # ---- roofline: the step (both update kernels) is the headline, the two kernels are sub-records
     b_stress, b_velocity = sol.algorithmic_bytes()
     peak, peak_src = measured_peak()
-    ach = b_stress / (ms_stress / K * 1e-3) / 1e9 if ms_stress > 0 else None
+    step_ms = ms_max / K
+    ach_s = b_stress / (ms_stress / K * 1e-3) / 1e9 if ms_stress > 0 else None
     ach_v = b_velocity / (ms_velocity / K * 1e-3) / 1e9 if ms_velocity > 0 else None
-    traffic = None
+    ach_step = (b_stress + b_velocity) / (step_ms * 1e-3) / 1e9
+    traffic = {}
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get(args.workload, {}).get("stress_dram_bytes_per_launch")
+            traffic = json.load(f).get(args.workload, {})
     except Exception:
         pass
+    names = {"3d": ("k_stress3d_ws", "k_velocity3d_ws"), "3dv": ("k_vstress3d", "k_vvelocity3d"),
+             "2dv": ("k_vstress2d", "k_vvelocity2d"), "2d": ("k_stress2d_pair", "k_velocity2d_pair")}[kind]
+    if kind == "3d":
+        names = sol.kernel_names()
+    t_s, t_v = traffic.get("stress_dram_bytes_per_launch"), traffic.get("velocity_dram_bytes_per_launch")
 
     if rank == 0:
+        cfg = common_config(args.workload, world)
         line = {
             "metric": metric_name(kind), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic (fields start at zero, analytic source; no RNG)",
-            "config": {"workload": workload_label(args.workload, p, kind, world),
-                       "grid": [p.NX, p.NY, getattr(p, "NZ", 1)], "npoints_pml": p.NPOINTS_PML,
-                       "deltat": p.DELTAT, "l2": "fields (>= 3 GB per rank) are far larger than the 126 MB L2; no flush needed",
-                       "parallelism": f"z-slabs x{world}" if world > 1 else "single GPU",
-                       "halo": (None if world == 1 else
-                                "6 planes per step and interface stored straight into the neighbour GPU's halo planes "
-                                "by the update kernels over NVLink (CUDA IPC), ordered by device-side flags"
-                                if (args.halo == "p2p" and kind == "3d") else
-                                "NCCL send/recv of 18 planes per step and interface (complete fourth-order halo)" if kind == "3dv"
-                                else "NCCL send/recv of 6 planes per step and interface"),
-                       "fmad": False, "finite": finite,
-                       "launch": sol.launch_info() if is3d else None},
-            "roofline": {"bound": "hbm", "kernel": ("k_stress3d_tma" if sol.launch_info()["tma"] else "k_stress3d") if kind == "3d" else "k_vstress3d" if kind == "3dv" else "k_vstress2d" if kind == "2dv" else "k_stress2d",
-                         "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": (ach / peak) if ach else None, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": b_stress,
-                         "avg_launch_ms": ms_stress / K,
-                         "velocity_kernel": {"achieved": ach_v, "frac": (ach_v / peak) if ach_v else None,
-                                             "algorithmic_bytes_per_launch": b_velocity,
-                                             "avg_launch_ms": ms_velocity / K},
-                         "step": {"algorithmic_bytes": b_stress + b_velocity,
-                                  "achieved": (b_stress + b_velocity) / (ms_max / K * 1e-3) / 1e9,
-                                  "frac": (b_stress + b_velocity) / (ms_max / K * 1e-3) / 1e9 / peak}},
+            "config": cfg,
+            "run": {"halo": (None if world == 1 else
+                             "boundary planes stored straight into the neighbour GPU's halo planes by the update kernels "
+                             "over NVLink (CUDA IPC), ordered by device-side flags" if args.halo == "p2p" else
+                             "NCCL send/recv of the halo planes between the kernels"),
+                    "fmad": False, "finite": finite, "launch": sol.launch_info() if is3d else None},
+            "roofline": {"bound": "hbm", "kernel": f"time step = {names[0]} + {names[1]}",
+                         "achieved": ach_step, "peak": peak, "unit": "GB/s", "frac": ach_step / peak,
+                         "traffic": (t_s + t_v) if (t_s and t_v) else None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_step": b_stress + b_velocity, "step_ms": step_ms,
+                         "slowest_kernel": names[1] if (ach_v or 0) < (ach_s or 0) else names[0],
+                         "kernels": {
+                             names[0]: {"achieved": ach_s, "frac": (ach_s / peak) if ach_s else None,
+                                        "algorithmic_bytes_per_launch": b_stress, "avg_launch_ms": ms_stress / K,
+                                        "traffic": t_s},
+                             names[1]: {"achieved": ach_v, "frac": (ach_v / peak) if ach_v else None,
+                                        "algorithmic_bytes_per_launch": b_velocity, "avg_launch_ms": ms_velocity / K,
+                                        "traffic": t_v}}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / K,
                     "d2h_bytes_per_step": float(td.item()) / K,
                     "what": "per step: cpml_set_source_step (16 B pinned H2D) + the step + cpml_fetch_step (32 B D2H); "
@@ -469,26 +468,10 @@ def run_b200(args):
         }
         if args.cpu_baseline and world == 1:
             try:
-                one = None
-                if kind == "2dv":
-                    v, sec, cores = oracle_2dv_gpts(p, 1001, 40, 2)
-                    sample = "1001x1001 sample grid, 40 timed steps after 2, serial like the reference"
-                elif kind == "3dv":
-                    v, sec, cores = oracle_3dv_gpts(p, 80, 12, 2)
-                    sample = f"{p.NX}x{min(p.NY, 256)}x80 reduced sample, 12 timed steps after 2, 4 emulated MPI slabs, FTZ/DAZ on"
-                    one = _one_thread(oracle_3dv_gpts, p, 40, 3, 1)
-                elif kind == "3d":
-                    nz_s = min(160, p.NZ)
-                    v, sec, cores = oracle_3d_gpts(p, nz_s, 24, 2)
-                    sample = f"{p.NX}x{p.NY}x{nz_s} z-reduced sample, 24 timed steps after 2, 2 emulated MPI slabs, FTZ/DAZ on"
-                    one = _one_thread(oracle_3d_gpts, p, 40, 4, 1)
-                else:
-                    v, sec, cores = oracle_2d_gpts(p, 1024, 40, 2)
-                    sample = "1024x1024 sample grid, 40 timed steps after 2, serial like the reference"
+                big = kind in ("3d", "3dv")
+                v, sec, cores, sample = cpu_arm(args.workload, 1, 24 if big else 40, 2, exact=False)
                 line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                                         "seconds": sec}
-                if one is not None:
-                    line["cpu_baseline"]["one_thread"] = {"value": one[0], "cores": one[2], "seconds": one[1]}
             except Exception as exc:   # the oracle is only the yardstick; never fail the GPU number on it
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
         print(json.dumps(line), flush=True)

@@ -66,6 +66,8 @@ struct cpml_handle {
     bool peer_ipc[2] = {false, false};
     unsigned long long *flags = nullptr;     // [0] v from lo, [1] v from hi, [2] sigma from lo, [3] sigma from hi
     unsigned int *d_timeout = nullptr;
+    unsigned long long epoch = 0;            // run number (cpml_reset increments it): flag values are epoch << 32 | it, so a
+                                             // neighbour's signal survives this slab's reset and stale values never satisfy a wait
 
     // profiles
     bool have_prof[3] = {false, false, false};
@@ -103,8 +105,11 @@ struct cpml_handle {
 
     // kernel timing
     bool timing = false;
-    std::vector<cudaEvent_t> ev;   // triples: start, after stress / start, after velocity
-    std::vector<int> ev_kind;
+    // fixed pool of event pairs created by cpml_enable_kernel_timing (nothing is created inside a
+    // timed loop); slot q of the ring: ev[2q] before / ev[2q+1] after launch number ev_used+q
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> ev_kind;      // per slot: 0 stress, 1 velocity, -1 free
+    size_t ev_head = 0, ev_count = 0;
     double ms_stress = 0, ms_velocity = 0;
     long long n_launches = 0;
 };
@@ -178,6 +183,7 @@ static int32_t create_impl(cpml_handle *h)
     if (c.emulate_nproc < 0) FAIL(CPML_EINVAL, "emulate_nproc must be >= 0");
     if (c.emulate_nproc > 1) {
         if (!h->visco) FAIL(CPML_EINVAL, "emulate_nproc applies to the viscoelastic solver only (the second-order exchange is complete)");
+        if (c.emulate_nproc % 2 != 0) FAIL(CPML_ETOPOLOGY, "nb_procs must be even (3D-visco :522-523)");
         if (c.nz % c.emulate_nproc != 0 || c.nz / c.emulate_nproc < std::max(2, c.npoints_pml))
             FAIL(CPML_ETOPOLOGY, "emulate_nproc must divide NZ into slabs of at least NPOINTS_PML planes (3D-visco :525-528)");
     }
@@ -259,6 +265,7 @@ static int32_t create_impl(cpml_handle *h)
     for (int m = 0; m < ne; m++)
         h->e0[m] = (double2 *)(h->arena + (size_t)(h->nfields + 2 * m) * h->field_doubles) + h->origin;
     h->flags = (unsigned long long *)(h->arena + h->flags_offset);
+    CK(cudaMemset(h->flags, 0, 16 * sizeof(double)));          // zeroed once: cpml_reset leaves the flag words alone
     CK(cudaMalloc(&h->d_timeout, sizeof(unsigned int)));
     CK(cudaMemset(h->d_timeout, 0, sizeof(unsigned int)));
     if (c.ndim == 2)
@@ -267,6 +274,8 @@ static int32_t create_impl(cpml_handle *h)
     const size_t nt = (size_t)c.nstep;
     CK(cudaMalloc(&h->d_src_x, nt * sizeof(double)));
     CK(cudaMalloc(&h->d_src_y, nt * sizeof(double)));
+    CK(cudaMemset(h->d_src_x, 0, nt * sizeof(double)));      // steps beyond a short series inject nothing
+    CK(cudaMemset(h->d_src_y, 0, nt * sizeof(double)));
     CK(cudaMalloc(&h->d_ek, nt * sizeof(double)));
     CK(cudaMalloc(&h->d_ep, nt * sizeof(double)));
     const size_t ns = std::max<size_t>(1, nt * (size_t)c.nrec);
@@ -403,7 +412,11 @@ extern "C" int32_t cpml_reset(cpml_handle *h)
     if (!h) return CPML_EINVAL;
     const cpml_config &c = h->cfg;
     CK(cudaSetDevice(h->device));
-    CK(cudaMemsetAsync(h->arena, 0, h->arena_doubles * sizeof(double), h->stream));   // fields and slab flags
+    // the fields -- not the slab flags behind them: a neighbour that has already reset and stepped may have
+    // published there (slab drivers put a barrier between the last step of a run, the resets and the first step)
+    CK(cudaMemsetAsync(h->arena, 0, h->flags_offset * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->d_timeout, 0, sizeof(unsigned int), h->stream));
+    h->epoch++;
     if (h->finalized) {
         for (int m = 0; m < 6; m++) {
             if (h->mx[m]) CK(cudaMemsetAsync(h->mx[m], 0, h->mx_doubles * sizeof(double), h->stream));
@@ -514,6 +527,16 @@ extern "C" int32_t cpml_set_attenuation(cpml_handle *h, int32_t n_sls, const dou
             if (!(src[q][l] > 0.0) || !std::isfinite(src[q][l])) FAIL(CPML_EINVAL, "relaxation times must be positive");
             h->tau[q][l] = src[q][l];
         }
+    if (h->visco) {
+        // div_exact divides by den = 1 - DELTAT/2 * tauinv (make_pv): Markstein's argument excludes divisors with
+        // an all-ones significand, like K, rho and the grid spacings
+        for (int q : {1, 3})
+            for (int l = 0; l < n_sls; l++) {
+                const double tauinv = -(1.0 / h->tau[q][l]);
+                if (all_ones_significand(1.0 - h->cfg.deltat * 0.5 * tauinv))
+                    FAIL(CPML_EINVAL, "1 - DELTAT/2 * tauinv has an all-ones significand: not supported");
+            }
+    }
     h->have_attenuation = true;
     return CPML_OK;
 }
@@ -983,20 +1006,37 @@ static unsigned long long *peer_flags(cpml_handle *h, int side)
     return (unsigned long long *)(h->peer_arena[side] + h->flags_offset);
 }
 
+static const size_t kEventSlots = 4096;      // launches in flight before the oldest pair is harvested
+
+// Adds the elapsed time of the oldest recorded pair to its kernel's total and frees the slot.
+static int32_t harvest_oldest(cpml_handle *h)
+{
+    const size_t q = h->ev_head;
+    float ms = 0.f;
+    CK(cudaEventSynchronize(h->ev[2 * q + 1]));
+    CK(cudaEventElapsedTime(&ms, h->ev[2 * q], h->ev[2 * q + 1]));
+    (h->ev_kind[q] == 0 ? h->ms_stress : h->ms_velocity) += ms;
+    h->ev_kind[q] = -1;
+    h->ev_head = (h->ev_head + 1) % kEventSlots;
+    h->ev_count--;
+    return CPML_OK;
+}
+
 static int32_t time_begin(cpml_handle *h, int kind)
 {
     if (!h->timing) return CPML_OK;
-    cudaEvent_t a, b;
-    CK(cudaEventCreate(&a));
-    CK(cudaEventCreate(&b));
-    h->ev.push_back(a); h->ev.push_back(b); h->ev_kind.push_back(kind);
-    CK(cudaEventRecord(a, h->stream));
+    if (h->ev_count == kEventSlots) { const int32_t rc = harvest_oldest(h); if (rc) return rc; }
+    const size_t q = (h->ev_head + h->ev_count) % kEventSlots;
+    h->ev_kind[q] = kind;
+    h->ev_count++;
+    CK(cudaEventRecord(h->ev[2 * q], h->stream));
     return CPML_OK;
 }
 static int32_t time_end(cpml_handle *h)
 {
     if (!h->timing) return CPML_OK;
-    CK(cudaEventRecord(h->ev.back(), h->stream));
+    const size_t q = (h->ev_head + h->ev_count - 1) % kEventSlots;
+    CK(cudaEventRecord(h->ev[2 * q + 1], h->stream));
     return CPML_OK;
 }
 
@@ -1021,9 +1061,12 @@ static int32_t half_step(cpml_handle *h, int32_t it, int phase)
     if (peers) {
         if (!h->use_tma) FAIL(CPML_ESTATE, "peer stores need the TMA kernels (unset CPML_KERNEL=reg)");
         const int w = phase == 0 ? 0 : 2;
-        launch_wait(h->peer_on[0] ? h->flags + w : nullptr, h->peer_on[1] ? h->flags + w + 1 : nullptr,
-                    (unsigned long long)(phase == 0 ? it - 1 : it), h->d_timeout, h->stream);
-        h->n_launches++;
+        // the stress update of step 1 reads the zero halo planes of the reset: nothing to wait for
+        if (!(phase == 0 && it == 1)) {
+            launch_wait(h->peer_on[0] ? h->flags + w : nullptr, h->peer_on[1] ? h->flags + w + 1 : nullptr,
+                        (h->epoch << 32) | (unsigned long long)(phase == 0 ? it - 1 : it), h->d_timeout, h->stream);
+            h->n_launches++;
+        }
     }
     rc = time_begin(h, phase); if (rc) return rc;
     if (h->visco) {
@@ -1055,7 +1098,7 @@ static int32_t half_step(cpml_handle *h, int32_t it, int phase)
     if (peers) {
         const int w = phase == 0 ? 2 : 0;
         launch_signal(h->peer_on[0] ? peer_flags(h, 0) + w + 1 : nullptr, h->peer_on[1] ? peer_flags(h, 1) + w : nullptr,
-                      (unsigned long long)it, h->stream);
+                      (h->epoch << 32) | (unsigned long long)it, h->stream);
         h->n_launches++;
     }
     CK(cudaGetLastError());
@@ -1111,10 +1154,10 @@ extern "C" int32_t cpml_step_finish(cpml_handle *h, int32_t it)
     return CPML_OK;
 }
 
-extern "C" int32_t cpml_synchronize(cpml_handle *h)
+// Waits for the handle's stream; with peer stores also checks that no wait kernel gave up on a neighbour
+// (results computed from stale halo planes must not be handed out without an error).
+static int32_t sync_checked(cpml_handle *h)
 {
-    if (!h) return CPML_EINVAL;
-    CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     if (h->peer_on[0] || h->peer_on[1]) {
         unsigned int timed_out = 0;
@@ -1122,6 +1165,13 @@ extern "C" int32_t cpml_synchronize(cpml_handle *h)
         if (timed_out) FAIL(CPML_ESTATE, "a neighbour slab never published its boundary planes (wait kernel timed out)");
     }
     return CPML_OK;
+}
+
+extern "C" int32_t cpml_synchronize(cpml_handle *h)
+{
+    if (!h) return CPML_EINVAL;
+    CK(cudaSetDevice(h->device));
+    return sync_checked(h);
 }
 
 extern "C" int32_t cpml_run(cpml_handle *h, int32_t it_begin, int32_t it_end)
@@ -1288,7 +1338,7 @@ extern "C" int32_t cpml_get_seismograms(cpml_handle *h, double *sisvx, double *s
     if (n == 0) return CPML_OK;
     CK(cudaMemcpyAsync(sisvx, h->d_sisvx, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(sisvy, h->d_sisvy, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    { const int32_t rc_sync = sync_checked(h); if (rc_sync) return rc_sync; }
     return CPML_OK;
 }
 
@@ -1300,7 +1350,7 @@ extern "C" int32_t cpml_get_seismograms_vz(cpml_handle *h, double *sisvz)
     const size_t n = (size_t)h->cfg.nstep * (size_t)h->cfg.nrec;
     if (n == 0) return CPML_OK;
     CK(cudaMemcpyAsync(sisvz, h->d_sisvz, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    { const int32_t rc_sync = sync_checked(h); if (rc_sync) return rc_sync; }
     return CPML_OK;
 }
 
@@ -1312,7 +1362,7 @@ extern "C" int32_t cpml_get_pressure_seismograms(cpml_handle *h, double *sispres
     const size_t n = (size_t)h->cfg.nstep * (size_t)h->cfg.nrec;
     if (n == 0) return CPML_OK;
     CK(cudaMemcpyAsync(sispressure, h->d_sisp, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    { const int32_t rc_sync = sync_checked(h); if (rc_sync) return rc_sync; }
     return CPML_OK;
 }
 
@@ -1324,7 +1374,7 @@ extern "C" int32_t cpml_get_energy(cpml_handle *h, double *total, double *kineti
     std::vector<double> ek(n), ep(n);
     CK(cudaMemcpyAsync(ek.data(), h->d_ek, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(ep.data(), h->d_ep, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    { const int32_t rc_sync = sync_checked(h); if (rc_sync) return rc_sync; }
     for (size_t q = 0; q < n; q++) {
         if (total) total[q] = ek[q] + ep[q];       // :1179 sums kinetic + potential
         if (kinetic) kinetic[q] = ek[q];
@@ -1347,7 +1397,7 @@ extern "C" int32_t cpml_get_plane(cpml_handle *h, int32_t field, int32_t kglobal
     }
     CK(cudaMemcpy2DAsync(out, (size_t)c.nx * sizeof(double), h->f0[field] + off, (size_t)h->pitch * sizeof(double),
                          (size_t)c.nx * sizeof(double), c.ny, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    { const int32_t rc_sync = sync_checked(h); if (rc_sync) return rc_sync; }
     return CPML_OK;
 }
 
@@ -1363,13 +1413,13 @@ extern "C" int32_t cpml_get_field(cpml_handle *h, int32_t field, double *out)
             CK(cudaMemcpy2DAsync(out + (size_t)(k - 1) * c.nx * c.ny, (size_t)c.nx * sizeof(double),
                                  h->f0[field] + (long long)k * h->plane, (size_t)h->pitch * sizeof(double),
                                  (size_t)c.nx * sizeof(double), c.ny, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
+        { const int32_t rc_sync = sync_checked(h); if (rc_sync) return rc_sync; }
         return CPML_OK;
     }
     // rows of all owned planes are equally spaced (plane = pitch * ny): one 2-D copy
     CK(cudaMemcpy2DAsync(out, (size_t)c.nx * sizeof(double), h->f0[field] + h->plane, (size_t)h->pitch * sizeof(double),
                          (size_t)c.nx * sizeof(double), (size_t)c.ny * h->nzl, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    { const int32_t rc_sync = sync_checked(h); if (rc_sync) return rc_sync; }
     return CPML_OK;
 }
 
@@ -1386,7 +1436,7 @@ extern "C" int32_t cpml_get_maxnorm(cpml_handle *h, double *out)
     h->n_launches++;
     unsigned long long bits = 0;
     CK(cudaMemcpyAsync(&bits, h->d_maxbits, sizeof(bits), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    { const int32_t rc_sync = sync_checked(h); if (rc_sync) return rc_sync; }
     memcpy(out, &bits, sizeof(double));
     return CPML_OK;
 }
@@ -1394,6 +1444,12 @@ extern "C" int32_t cpml_get_maxnorm(cpml_handle *h, double *out)
 extern "C" int32_t cpml_enable_kernel_timing(cpml_handle *h, int32_t on)
 {
     if (!h) return CPML_EINVAL;
+    if (on && h->ev.empty()) {      // the event pool is created here, outside any timed loop
+        CK(cudaSetDevice(h->device));
+        h->ev.resize(2 * kEventSlots);
+        h->ev_kind.assign(kEventSlots, -1);
+        for (auto &e : h->ev) CK(cudaEventCreate(&e));
+    }
     h->timing = on != 0;
     return CPML_OK;
 }
@@ -1403,13 +1459,7 @@ extern "C" int32_t cpml_get_kernel_times(cpml_handle *h, double *ms_stress, doub
     if (!h) return CPML_EINVAL;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
-    for (size_t q = 0; q < h->ev_kind.size(); q++) {
-        float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, h->ev[2 * q], h->ev[2 * q + 1]));
-        (h->ev_kind[q] == 0 ? h->ms_stress : h->ms_velocity) += ms;
-    }
-    for (auto e : h->ev) cudaEventDestroy(e);
-    h->ev.clear(); h->ev_kind.clear();
+    while (h->ev_count > 0) { const int32_t rc = harvest_oldest(h); if (rc) return rc; }
     if (ms_stress) *ms_stress = h->ms_stress;
     if (ms_velocity) *ms_velocity = h->ms_velocity;
     if (n_launches) *n_launches = h->n_launches;

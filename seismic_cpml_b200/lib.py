@@ -385,6 +385,13 @@ class Solver:
                 "stress_z_chunks", "stress_items")
         return dict(zip(keys, (int(x) for x in v)))
 
+    def kernel_names(self):
+        """Names of the two update kernels of a 3-D isotropic handle (launch_info()["tma"]: 0 register-marching,
+        1 TMA-staged, 2 TMA-staged with a producer warp)."""
+        k = self.launch_info()["tma"]
+        return {0: ("k_stress3d", "k_velocity3d"), 1: ("k_stress3d_tma", "k_velocity3d_tma"),
+                2: ("k_stress3d_ws", "k_velocity3d_ws")}[k]
+
     # -- outputs
     def get_seismograms(self):
         """(sisvx, sisvy), each shaped (NREC, NSTEP): row r is the trace of receiver r+1

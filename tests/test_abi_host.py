@@ -96,6 +96,8 @@ def _bad(**over):
     (dict(deltat=3e-3), L.CPML_ECFL),                     # Courant > 1 (:717)
     (dict(isource=40), L.CPML_EINVAL),
     (dict(ndim=2, nslabs=2), L.CPML_ETOPOLOGY),
+    (dict(order=4, rheology=1, nz=30, emulate_nproc=3), L.CPML_ETOPOLOGY),   # 'nb_procs must be even' (3D-visco :522-523)
+    (dict(order=4, rheology=1, emulate_nproc=5), L.CPML_ETOPOLOGY),
 ])
 def test_create_validation(over, code):
     with pytest.raises(L.CpmlError) as e:

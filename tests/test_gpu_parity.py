@@ -383,3 +383,100 @@ def test_3d_vz_seismograms_extension():
     with solver2d(refcfg.cfg2d(2, nx=60, ny=70, nstep=10, npml=6)) as s2:
         with pytest.raises(L.CpmlError):
             s2.get_seismograms_vz()
+
+
+# ------------------------------------------------------------------ sizes the bench numbers are quoted on
+
+def _iso3d_workload(nx, ny, nz, nstep, **kw):
+    """The 3-D isotropic program's own parameter block (:124-218) on an nx x ny x nz grid, oracle-side set-up."""
+    from oracle import workloads as WL
+    return WL.iso3d(nx, ny, nz, nstep, **kw)
+
+
+@pytest.mark.parametrize("tx", [64, 104, 128])
+def test_3d_interior_x_tiles(tx, monkeypatch):
+    """NX = 300: several x tiles per row for every tile width -- tiles that touch the low x shell, interior
+    tiles (no x shell: the staged x-shell rows are skipped) and tiles that touch the high shell; bitwise."""
+    monkeypatch.setenv("CPML_TX", str(tx))
+    c = refcfg.cfg3d(nx=300, ny=40, nz=32, npml=6, nstep=70)
+    o = O.run_3d_iso(**c, nproc=2, want_fields=True)
+    with solver3d(c) as s:
+        info = s.launch_info()
+        assert info["tile_x"] == tx and (300 + tx - 1) // tx >= 3
+        s.run(1, c["nstep"])
+        check_traces(s.get_seismograms(), (o["sisvx"], o["sisvy"]))
+        for f, name in enumerate(F3):
+            assert np.array_equal(s.get_field(f), o[name]), name
+        assert refcfg.rel_l2(s.get_energy()[0], o["total_energy"]) <= TOL_ENERGY
+
+
+def test_3d_cfg4_slab_window_vs_oracle():
+    """BASELINE config 4's per-GPU grid (1024 x 1024 x 128, default tiles: several x tiles per row, 512-thread
+    CTAs), 30 steps: a window around the source -- it includes the x-max C-PML shell, 21 cells from the source --
+    must equal, bit for bit, the oracle run on an 80 x 126 x 84 grid that shares that window (finite numerical
+    propagation speed: one cell per step, so nothing outside the window has reached it and the small grid's
+    other shells are still at rest)."""
+    nx, ny, nz, steps = 1024, 1024, 128, 30
+    big = _iso3d_workload(nx, ny, nz, steps)
+    mx, my, mz = 80, 126, 84
+    small = _iso3d_workload(mx, my, mz, steps)
+    isb, jsb, ksb = big["isource"], big["jsource"], nz // 2
+    iss, jss, kss = small["isource"], small["jsource"], mz // 2
+    assert nx - isb == mx - iss == 21                       # same distance to the x-max edge
+    assert min(iss - 1, jss - 1, my - jss, kss - 1, mz - kss) >= steps + 10 + 1
+    o = O.run_3d_iso(**small, nproc=2, want_fields=True)
+    with solver3d(big) as s:
+        info = s.launch_info()
+        assert (nx + info["tile_x"] - 1) // info["tile_x"] >= 2
+        s.run(1, steps)
+        x0, y0 = isb - iss, jsb - jss                       # big index = small index + offset
+        for f in (0, 1, 2, 3, 5, 6, 7, 8):
+            name = F3[f]
+            for dk in (-25, -7, -1, 0, 1, 6, 20):
+                got = s.get_plane(f, ksb + dk)[y0:y0 + my, x0:x0 + mx]
+                ref = o[name][kss + dk - 1]
+                assert np.array_equal(got, ref), (name, dk, np.abs(got - ref).max())
+            assert np.abs(o[name][kss - 1]).max() > 0
+        # the wave has not left the window: planes far from the source are still at rest
+        assert not s.get_plane(0, 5).any() and not s.get_plane(2, nz - 4).any()
+        pv = s.get_plane(0, ksb)
+        assert not pv[: y0 - 2].any() and not pv[:, : x0 - 2].any()
+        assert refcfg.rel_l2(s.get_energy()[0], o["total_energy"]) <= TOL_ENERGY
+
+
+@pytest.mark.slow
+def test_3d_default_xy_geometry_full_run_seismograms():
+    """The shipped x-y geometry (101 x 641, source (80,428), receivers (70,231) and (80,31)) with NZ = 64, ALL 2500
+    time steps: seismograms at the real receivers through first arrival, PML contact and decay, and the energy
+    trace, against the OpenMP build of the oracle (FMA-contracted: TOL applies) -- north_star's <= 1e-5."""
+    c = _iso3d_workload(101, 641, 64, 2500)
+    assert (list(c["ix_rec"]), list(c["iy_rec"])) == ([70, 80], [231, 31])
+    o = O.run_3d_iso(**c, nproc=2, kind="timed")
+    with solver3d(c) as s:
+        s.run(1, c["nstep"])
+        sx, sy = s.get_seismograms()
+        e = s.get_energy()[0]
+    for g, r in ((sx, o["sisvx"]), (sy, o["sisvy"])):
+        for rec in range(2):
+            assert np.abs(r[rec]).max() > 1e-3
+            assert refcfg.rel_l2(g[rec], r[rec]) <= TOL, (rec, refcfg.rel_l2(g[rec], r[rec]))
+    assert refcfg.rel_l2(e, o["total_energy"]) <= TOL
+    assert e[-1] < 1e-3 * e.max()                           # the shells did absorb the wavefield
+
+
+@pytest.mark.slow
+def test_3d_default_grid_450_steps_vs_timed_oracle():
+    """BASELINE config 3 at full size (101 x 641 x 640) for 450 steps: past the first arrival at the nearest
+    receiver (197 cells from the source), with the wavefront inside the x shells; seismograms, the energy
+    trace and the receiver plane against the OpenMP build of the oracle (TOL)."""
+    c = _iso3d_workload(101, 641, 640, 450)
+    o = O.run_3d_iso(**c, nproc=2, want_planes=True, kind="timed")
+    with solver3d(c) as s:
+        s.run(1, c["nstep"])
+        sx, sy = s.get_seismograms()
+        e = s.get_energy()[0]
+        pvx, pvy = s.get_plane(0, 320), s.get_plane(1, 320)
+    assert np.abs(o["sisvx"][0]).max() > 1e-6               # receiver 1 has seen the wave
+    assert refcfg.rel_l2(sx[0], o["sisvx"][0]) <= TOL and refcfg.rel_l2(sy[0], o["sisvy"][0]) <= TOL
+    assert refcfg.rel_l2(e, o["total_energy"]) <= TOL
+    assert refcfg.rel_l2(pvx, o["plane_vx"]) <= TOL and refcfg.rel_l2(pvy, o["plane_vy"]) <= TOL
