@@ -56,7 +56,9 @@ struct cpml_handle {
     int vkchunk = 1, vtx = 32, vty = 8;
 
     // TMA path (3-D): descriptors of the two kernels' plane tiles, work decomposition
-    bool use_tma = false;
+    bool use_tma = false;          // TMA-staged kernels (either family)
+    bool use_ws = false;           // ... with a producer warp and in-kernel slab ordering (kernels_3d_ws.cu, the default)
+    unsigned int *d_bcount = nullptr;   // [2] boundary-item counters of the in-kernel slab ordering
     TmaMaps maps_stress{}, maps_velocity{};
     Tile3D tile{}, tile_stress{};        // velocity kernel (also: energy partial slots) / stress kernel
 
@@ -268,6 +270,8 @@ static int32_t create_impl(cpml_handle *h)
     CK(cudaMemset(h->flags, 0, 16 * sizeof(double)));          // zeroed once: cpml_reset leaves the flag words alone
     CK(cudaMalloc(&h->d_timeout, sizeof(unsigned int)));
     CK(cudaMemset(h->d_timeout, 0, sizeof(unsigned int)));
+    CK(cudaMalloc(&h->d_bcount, 2 * sizeof(unsigned int)));
+    CK(cudaMemset(h->d_bcount, 0, 2 * sizeof(unsigned int)));
     if (c.ndim == 2)
         for (int m = 0; m < 3; m++) CK(cudaMalloc(&h->mat[m], h->field_doubles * sizeof(double)));
 
@@ -393,6 +397,7 @@ extern "C" int32_t cpml_destroy(cpml_handle *h)
     cpml_p2p_detach(h);
     cudaFree(h->arena);
     cudaFree(h->d_timeout);
+    cudaFree(h->d_bcount);
     for (auto &p : h->mat) cudaFree(p);
     for (auto &ax : h->dprof) for (auto &p : ax) cudaFree(p);
     for (auto &p : h->mx) cudaFree(p);
@@ -416,6 +421,7 @@ extern "C" int32_t cpml_reset(cpml_handle *h)
     // published there (slab drivers put a barrier between the last step of a run, the resets and the first step)
     CK(cudaMemsetAsync(h->arena, 0, h->flags_offset * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->d_timeout, 0, sizeof(unsigned int), h->stream));
+    CK(cudaMemsetAsync(h->d_bcount, 0, 2 * sizeof(unsigned int), h->stream));
     h->epoch++;
     if (h->finalized) {
         for (int m = 0; m < 6; m++) {
@@ -666,10 +672,18 @@ static int32_t build_tile(cpml_handle *h, EncodeTiledFn enc, bool stress, Tile3D
         if (w < w_best) best_tx = cand;
     }
     t.tx = env_int("CPML_TX", best_tx);
-    t.ty = env_int("CPML_TY", 8);
-    if (stress) t.ty = env_int("CPML_TY_STRESS", (t.tx == 104 && t.ty == 8) ? 7 : t.ty);
-    if (!tma_tile_supported(t.tx, t.ty)) FAIL(CPML_EINVAL, "unsupported CPML_TX x CPML_TY tile");
-    t.stages = std::max(1, std::min(7, env_int("CPML_STAGES", 2)));
+    if (h->use_ws) {
+        // with the producer warp a CTA is tile/2 + 32 threads: 104 x 8 -> 14 warps, 128 x 7 -> 15 warps (at most four per
+        // SM sub-partition: 128 registers); both kernels use the same tile unless CPML_TY_STRESS says otherwise
+        t.ty = env_int("CPML_TY", t.tx == 128 ? 7 : 8);
+        if (stress) t.ty = env_int("CPML_TY_STRESS", t.ty);
+        if (!ws_tile_supported(t.tx, t.ty)) FAIL(CPML_EINVAL, "unsupported CPML_TX x CPML_TY tile for the producer-warp kernels");
+    } else {
+        t.ty = env_int("CPML_TY", 8);
+        if (stress) t.ty = env_int("CPML_TY_STRESS", (t.tx == 104 && t.ty == 8) ? 7 : t.ty);
+        if (!tma_tile_supported(t.tx, t.ty)) FAIL(CPML_EINVAL, "unsupported CPML_TX x CPML_TY tile");
+    }
+    t.stages = std::max(1, std::min(h->use_ws ? 4 : 7, env_int("CPML_STAGES", 2)));
     t.minb = std::max(1, std::min(4, env_int("CPML_MINB", t.tx == 64 ? 2 : 1)));
     if (t.ty == 7 || t.ty == 6) t.minb = 1;
     t.xm_bytes = h->shell[0].size() > 0 ? round_up(t.ty * h->sxp * 8, 128) : 0;
@@ -697,7 +711,7 @@ static int32_t build_tile(cpml_handle *h, EncodeTiledFn enc, bool stress, Tile3D
                 if (K != 1.0) p.kunit = 0;
     int occ = 0;
     while (true) {
-        const cudaError_t e = tma_occupancy(p, t, stress, &occ);
+        const cudaError_t e = h->use_ws ? ws_occupancy(p, t, stress, &occ) : tma_occupancy(p, t, stress, &occ);
         if (e == cudaSuccess && occ >= 1) break;
         cudaGetLastError();
         if (t.stages <= 1) FAIL(CPML_ECUDA, "TMA kernels do not fit on this device");
@@ -827,9 +841,15 @@ static int32_t finalize(cpml_handle *h)
         CK(cudaMalloc(&h->d_partials, 3 * (size_t)h->nblocks * sizeof(double)));
         CK(cudaMemset(h->d_partials, 0, 3 * (size_t)h->nblocks * sizeof(double)));
     } else if (c.ndim == 3) {
-        // CPML_KERNEL=reg selects the register-marching kernels of kernels_3d.cu (A/B runs)
+        // CPML_KERNEL=reg selects the register-marching kernels of kernels_3d.cu, CPML_KERNEL=tma the TMA-staged
+        // kernels without a producer warp (kernels_3d_tma.cu); both are kept for A/B runs
         const char *kv = getenv("CPML_KERNEL");
-        h->use_tma = !(kv && std::string(kv) == "reg");
+        const std::string kvs = kv ? kv : "";
+        h->use_tma = kvs != "reg";
+        h->use_ws = h->use_tma && kvs != "tma";
+        if (h->use_ws && (h->field_doubles >= (1ull << 32) || h->mx_doubles >= (1ull << 32) || h->my_doubles >= (1ull << 32) ||
+                          h->mz_doubles >= (1ull << 32)))
+            h->use_ws = false;      // the producer-warp kernels index with 32-bit element offsets (fields of < 2^32 points)
         if (h->use_tma) { const int32_t rc = setup_tma(h); if (rc) return rc; }
         else build_regions(h);
         CK(cudaMalloc(&h->d_partials, 2 * (size_t)std::max(1, h->nblocks) * sizeof(double)));
@@ -1058,7 +1078,24 @@ static int32_t half_step(cpml_handle *h, int32_t it, int phase)
     CK(cudaSetDevice(h->device));
     const bool peers = h->cfg.ndim == 3 && (h->peer_on[0] || h->peer_on[1]);
     if (peers && h->visco) FAIL(CPML_ESTATE, "the viscoelastic kernels exchange their halo planes through the driver (cpml_halo_plane)");
-    if (peers) {
+    SlabSync ss{};
+    if (peers && h->use_ws) {
+        // the kernels order the slabs themselves: boundary items poll flag words [w], [w+1] of this slab and the
+        // last boundary item of a side publishes into the neighbour's words (same words as k_wait / k_signal)
+        const int w = phase == 0 ? 0 : 2, wp = phase == 0 ? 2 : 0;
+        const bool nothing_to_wait_for = phase == 0 && it == 1;      // step 1 reads the zero halo planes of the reset
+        if (!nothing_to_wait_for) {
+            ss.wait_lo = h->peer_on[0] ? h->flags + w : nullptr;
+            ss.wait_hi = h->peer_on[1] ? h->flags + w + 1 : nullptr;
+        }
+        ss.wait_value = (h->epoch << 32) | (unsigned long long)(phase == 0 ? it - 1 : it);
+        ss.pub_lo = h->peer_on[0] ? peer_flags(h, 0) + wp + 1 : nullptr;
+        ss.pub_hi = h->peer_on[1] ? peer_flags(h, 1) + wp : nullptr;
+        ss.pub_value = (h->epoch << 32) | (unsigned long long)it;
+        ss.count = h->d_bcount;
+        ss.n_boundary = (phase == 0 ? h->tile_stress : h->tile).ntx * (phase == 0 ? h->tile_stress : h->tile).nty;
+        ss.timeout = h->d_timeout;
+    } else if (peers) {
         if (!h->use_tma) FAIL(CPML_ESTATE, "peer stores need the TMA kernels (unset CPML_KERNEL=reg)");
         const int w = phase == 0 ? 0 : 2;
         // the stress update of step 1 reads the zero halo planes of the reset: nothing to wait for
@@ -1075,7 +1112,11 @@ static int32_t half_step(cpml_handle *h, int32_t it, int phase)
         h->n_launches += phase == 0 ? visco_stress_launches() : 1;
     } else if (h->cfg.ndim == 3) {
         const Params3D p = make_p3(h, it);
-        if (h->use_tma) {
+        if (h->use_ws) {
+            if (phase == 0) CK(launch_stress3d_ws(p, h->maps_stress, h->tile_stress, ss, h->stream));
+            else CK(launch_velocity3d_ws(p, h->maps_velocity, h->tile, ss, h->stream));
+            h->n_launches++;
+        } else if (h->use_tma) {
             if (phase == 0) CK(launch_stress3d_tma(p, h->maps_stress, h->tile_stress, h->stream));
             else CK(launch_velocity3d_tma(p, h->maps_velocity, h->tile, h->stream));
             h->n_launches++;
@@ -1095,7 +1136,7 @@ static int32_t half_step(cpml_handle *h, int32_t it, int phase)
         h->n_launches++;
     }
     rc = time_end(h); if (rc) return rc;
-    if (peers) {
+    if (peers && !h->use_ws) {
         const int w = phase == 0 ? 2 : 0;
         launch_signal(h->peer_on[0] ? peer_flags(h, 0) + w + 1 : nullptr, h->peer_on[1] ? peer_flags(h, 1) + w : nullptr,
                       (h->epoch << 32) | (unsigned long long)it, h->stream);
@@ -1324,7 +1365,7 @@ extern "C" int32_t cpml_get_launch_info(cpml_handle *h, int32_t *info, int32_t n
         return CPML_OK;
     }
     const Tile3D &t = h->tile, &ts = h->tile_stress;
-    const int32_t v[14] = {h->use_tma ? 1 : 0, t.tx, t.ty, t.stages, t.kchunk, t.nzc, t.nitems, ts.grid_stress, t.grid_velocity,
+    const int32_t v[14] = {h->use_ws ? 2 : h->use_tma ? 1 : 0, t.tx, t.ty, t.stages, t.kchunk, t.nzc, t.nitems, ts.grid_stress, t.grid_velocity,
                            (h->peer_on[0] ? 1 : 0) + (h->peer_on[1] ? 2 : 0), ts.ty, ts.kchunk, ts.nzc, ts.nitems};
     for (int q = 0; q < n && q < 14; q++) info[q] = v[q];
     return CPML_OK;

@@ -189,6 +189,19 @@ struct Tile3D {
     int grid_stress, grid_velocity;
 };
 
+// Slab-to-slab ordering done INSIDE the update kernels (kernels_3d_ws.cu): the work items that read a halo plane
+// poll this slab's flag words, the CTA that finishes the last boundary item of a side publishes to that neighbour.
+// All pointers null: single slab, or the exchange is done by the driver.
+struct SlabSync {
+    const unsigned long long *wait_lo, *wait_hi;   // this slab's flag words written by slab rank-1 / rank+1
+    unsigned long long wait_value;                 // epoch << 32 | time step the planes must belong to
+    unsigned long long *pub_lo, *pub_hi;           // the neighbours' flag words this slab writes (mapped peer memory)
+    unsigned long long pub_value;
+    unsigned int *count;                           // [2] boundary items completed on the lo / hi side (self-resetting)
+    int n_boundary;                                // work items per boundary chunk (= tiles per plane)
+    unsigned int *timeout;                         // set when a poll gives up
+};
+
 // One launch region of a 3-D kernel: the box [i0,i1] x [j0,j1] x [k0,k1] (1-based, k local).
 // The thread grid starts at ia <= i0 (ia-1 a multiple of 4, so warp rows stay 32-byte
 // sector aligned); lanes with i < i0 idle.
@@ -296,6 +309,10 @@ bool tma_tile_supported(int tx, int ty);
 cudaError_t tma_occupancy(const Params3D &p, const Tile3D &t, bool stress, int *occ);
 cudaError_t launch_stress3d_tma(const Params3D &p, const TmaMaps &tm, const Tile3D &t, cudaStream_t s);
 cudaError_t launch_velocity3d_tma(const Params3D &p, const TmaMaps &tm, const Tile3D &t, cudaStream_t s);
+bool ws_tile_supported(int tx, int ty);
+cudaError_t ws_occupancy(const Params3D &p, const Tile3D &t, bool stress, int *occ);
+cudaError_t launch_stress3d_ws(const Params3D &p, const TmaMaps &tm, const Tile3D &t, const SlabSync &ss, cudaStream_t s);
+cudaError_t launch_velocity3d_ws(const Params3D &p, const TmaMaps &tm, const Tile3D &t, const SlabSync &ss, cudaStream_t s);
 void launch_signal(unsigned long long *flag_lo, unsigned long long *flag_hi, unsigned long long value, cudaStream_t s);
 void launch_wait(const unsigned long long *flag_a, const unsigned long long *flag_b, unsigned long long value,
                  unsigned int *timeout_flag, cudaStream_t s);

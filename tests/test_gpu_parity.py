@@ -230,20 +230,28 @@ def test_3d_slabs_with_peer_stores_match_single_slab(nslabs):
             s.close()
 
 
-@pytest.mark.parametrize("tile", [(64, 4), (64, 8), (104, 7), (104, 8), (128, 4), (128, 6), (128, 8)])
+TMA_TILES = [("tma", t) for t in [(64, 4), (64, 8), (104, 7), (104, 8), (128, 4), (128, 6), (128, 8)]] + \
+            [("ws", t) for t in [(64, 4), (64, 8), (104, 7), (104, 8), (128, 6), (128, 7)]]
+
+
+@pytest.mark.parametrize("kernel,tile", TMA_TILES)
 @pytest.mark.parametrize("stages", [1, 3])
-def test_3d_tma_tiles_and_ring_depths(tile, stages, monkeypatch):
-    """Every TMA box shape / shared-memory ring depth gives the same bits (ragged grid: NX, NY
-    not multiples of any tile; several z chunks)."""
+def test_3d_tma_tiles_and_ring_depths(kernel, tile, stages, monkeypatch):
+    """Every TMA box shape / shared-memory ring depth of both TMA-staged kernel families (CPML_KERNEL=tma: thread 0
+    issues the loads; ws, the default: a producer warp does) gives the same bits (ragged grid: NX, NY not multiples
+    of any tile; several z chunks, so the boundary-chunks-first item order of the ws kernels is exercised)."""
+    monkeypatch.setenv("CPML_KERNEL", kernel)
     monkeypatch.setenv("CPML_TX", str(tile[0]))
     monkeypatch.setenv("CPML_TY", str(tile[1]))
+    monkeypatch.setenv("CPML_TY_STRESS", str(tile[1]))
     monkeypatch.setenv("CPML_STAGES", str(stages))
     monkeypatch.setenv("CPML_ZCHUNKS", "3")
     c = refcfg.cfg3d(nx=70, ny=45, nz=40, npml=6, nstep=60)
     o = O.run_3d_iso(**c, nproc=2, want_fields=True)
     with solver3d(c) as s:
         info = s.launch_info()
-        assert info["tma"] == 1 and (info["tile_x"], info["tile_y"]) == tile and info["z_chunks"] == 3
+        assert info["tma"] == (2 if kernel == "ws" else 1)
+        assert (info["tile_x"], info["tile_y"]) == tile and info["z_chunks"] == 3
         s.run(1, c["nstep"])
         check_traces(s.get_seismograms(), (o["sisvx"], o["sisvy"]))
         for f, name in enumerate(F3):
@@ -257,7 +265,7 @@ def test_3d_register_kernels_still_match(monkeypatch):
     c = refcfg.cfg3d(nx=37, ny=45, nz=40, npml=6, nstep=60)
     o = O.run_3d_iso(**c, nproc=2, want_fields=True)
     with solver3d(c) as s:
-        assert s.launch_info()["tma"] == 0
+        assert s.launch_info()["tma"] == 0 and s.kernel_names() == ("k_stress3d", "k_velocity3d")
         s.run(1, c["nstep"])
         check_traces(s.get_seismograms(), (o["sisvx"], o["sisvy"]))
         for f, name in enumerate(F3):
