@@ -279,6 +279,38 @@ int32_t cpml_enable_kernel_timing(cpml_handle *h, int32_t on);
  * DESIGN.md states the formula.  Also split per kernel. */
 int32_t cpml_algorithmic_bytes(cpml_handle *h, double *bytes_stress, double *bytes_velocity);
 
+/* ---- the whole z-slab decomposition behind one handle (single host thread, no MPI) --- */
+/* Replaces what the reference's Fortran program does around its MPI calls: rank set-up (3D-iso :337-346),
+ * neighbours (:770-796), the plane exchange (:811-823, :951-963; 3D-visco :962-975, :1229-1242), the energy
+ * reduction (:1179) and the seismograms of rank_cut_plane (:1124-1129).  cpml_multi_create makes `ngpus` slab
+ * handles (cfg->nslabs / slab_rank / device are ignored) on devices[0..ngpus-1] (NULL: devices 0..ngpus-1; a
+ * device may appear more than once), attaches neighbouring slabs to each other (cpml_p2p_attach_local) and gives
+ * every device its own stream.  The setters forward to every slab; cpml_multi_step launches one pass of the loop
+ * body on every slab and returns without waiting; cpml_multi_run loops and synchronises.  Getters return what the
+ * reference's rank_cut_plane holds: the summed energy, the cut plane's seismograms, any plane by GLOBAL k. */
+typedef struct cpml_multi cpml_multi;
+int32_t cpml_multi_create(const cpml_config *cfg, int32_t ngpus, const int32_t *devices, cpml_multi **out);
+int32_t cpml_multi_destroy(cpml_multi *m);
+const char *cpml_multi_last_error(const cpml_multi *m);
+int32_t cpml_multi_ngpus(const cpml_multi *m);
+int32_t cpml_multi_slab(cpml_multi *m, int32_t rank, cpml_handle **out);     /* borrowed: timing, launch info, ... */
+int32_t cpml_multi_reset(cpml_multi *m);
+int32_t cpml_multi_set_profiles(cpml_multi *m, int32_t axis, const double *a, const double *b, const double *K,
+                                const double *a_half, const double *b_half, const double *K_half, int32_t n);
+int32_t cpml_multi_set_attenuation(cpml_multi *m, int32_t n_sls, const double *tau_epsilon_nu1, const double *tau_sigma_nu1,
+                                   const double *tau_epsilon_nu2, const double *tau_sigma_nu2);
+int32_t cpml_multi_set_source_series(cpml_multi *m, const double *force_x, const double *force_y, int32_t n);
+int32_t cpml_multi_set_receivers(cpml_multi *m, const int32_t *ix_rec, const int32_t *iy_rec, int32_t n);
+int32_t cpml_multi_step(cpml_multi *m, int32_t it);
+int32_t cpml_multi_run(cpml_multi *m, int32_t it_begin, int32_t it_end);
+int32_t cpml_multi_synchronize(cpml_multi *m);
+int32_t cpml_multi_get_seismograms(cpml_multi *m, double *sisvx, double *sisvy);
+int32_t cpml_multi_get_seismograms_vz(cpml_multi *m, double *sisvz);
+int32_t cpml_multi_get_energy(cpml_multi *m, double *total, double *kinetic, double *potential);
+int32_t cpml_multi_get_plane(cpml_multi *m, int32_t field, int32_t kglobal, double *out);
+int32_t cpml_multi_get_field(cpml_multi *m, int32_t field, double *out);      /* (NX,NY,NZ), slabs concatenated */
+int32_t cpml_multi_get_maxnorm(cpml_multi *m, double *out);
+
 /* ---- host-side helpers that mirror the reference's set-up phase ------------- */
 /* (pure host code, no device needed; the drivers in drivers/ use them)          */
 

@@ -243,7 +243,15 @@ static int32_t create_impl(cpml_handle *h)
         h->nfields = 15;
         ne = 6;
     } else if (c.ndim == 3) {
-        h->pitch = round_up(c.nx, 16);
+        // Row pitch: NX rounded up to 4 doubles (one 32-byte sector), NOT to a 128-byte line.  The TMA kernels do not
+        // care where a row starts, and with NX = 101 a 112-double pitch left 11 pad doubles per row that the 128-byte
+        // L2 promotion of the tensor loads fetched anyway and that turned the last sector of every stored row into a
+        // partial write (ncu: 1.09x the algorithmic DRAM bytes, profiles/r02_a_ncu_cfg3_ws.txt); with 104 the planes
+        // are dense -- the kernels also write the (zero) pad pairs -- and nothing but whole sectors moves.
+        // CPML_PITCH_ALIGN=16 restores the old layout for A/B runs.
+        int align = env_int("CPML_PITCH_ALIGN", 4);
+        if (align != 2 && align != 4 && align != 8 && align != 16) align = 4;
+        h->pitch = round_up(c.nx, align);
         h->plane = (long long)h->pitch * c.ny;
         h->origin = 16;   // leading pad so that (i-1) at the first element stays inside
         h->field_doubles = (size_t)h->plane * (h->nzl + 2) + 32 + (size_t)h->pitch;
@@ -645,8 +653,12 @@ static int32_t encode_plane_map(cpml_handle *h, EncodeTiledFn enc, CUtensorMap *
     const cuuint64_t strides[2] = {(cuuint64_t)h->pitch * sizeof(double), (cuuint64_t)h->plane * sizeof(double)};
     const cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
+    // L2 promotion of the tensor loads: 128 B by default; CPML_L2PROMO = 0 none, 1 64 B, 2 128 B, 3 256 B (A/B runs)
+    static const CUtensorMapL2promotion promo[4] = {CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
+                                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B};
+    const int pm = std::max(0, std::min(3, env_int("CPML_L2PROMO", 2)));
     const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)h->f0[field], dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo[pm],
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         h->err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
@@ -671,6 +683,9 @@ static int32_t build_tile(cpml_handle *h, EncodeTiledFn enc, bool stress, Tile3D
         const int w_best = (c.nx + best_tx - 1) / best_tx * best_tx, w = (c.nx + cand - 1) / cand * cand;
         if (w < w_best) best_tx = cand;
     }
+    // producer-warp kernels: 104 x 8 (14 warps, halo rows 9/8) beats 128 x 7 (15 warps, 8/7) unless it wastes more than
+    // 4 % more columns -- 1024-wide slabs: 23.7 against 23.3 Gpts/s (profiles/r02_a_bench.txt)
+    if (h->use_ws && best_tx == 128 && (c.nx + 103) / 104 * 104 <= 1.04 * ((c.nx + 127) / 128 * 128)) best_tx = 104;
     t.tx = env_int("CPML_TX", best_tx);
     if (h->use_ws) {
         // with the producer warp a CTA is tile/2 + 32 threads: 104 x 8 -> 14 warps, 128 x 7 -> 15 warps (at most four per
@@ -1018,6 +1033,12 @@ static ParamsV3D make_pv(cpml_handle *h, int it)
     p.inv_2mu = 1.0 / (2.0 * c.mu);
     p.partials = h->d_partials; p.nblocks = h->nblocks;
     p.kchunk = h->vkchunk;
+    // neighbour slabs' fields (element (1,1,0)) for the in-kernel halo stores: vx vy sigmazz / vz sigmaxz sigmayz
+    const int pf[6] = {0, 1, 5, 2, 7, 8};
+    for (int q = 0; q < 6; q++) {
+        p.peer_lo[q] = h->peer_on[0] ? h->peer_arena[0] + (size_t)pf[q] * h->field_doubles + h->origin : nullptr;
+        p.peer_hi[q] = h->peer_on[1] ? h->peer_arena[1] + (size_t)pf[q] * h->field_doubles + h->origin : nullptr;
+    }
     return p;
 }
 
@@ -1077,9 +1098,8 @@ static int32_t half_step(cpml_handle *h, int32_t it, int phase)
     rc = finalize(h); if (rc) return rc;
     CK(cudaSetDevice(h->device));
     const bool peers = h->cfg.ndim == 3 && (h->peer_on[0] || h->peer_on[1]);
-    if (peers && h->visco) FAIL(CPML_ESTATE, "the viscoelastic kernels exchange their halo planes through the driver (cpml_halo_plane)");
     SlabSync ss{};
-    if (peers && h->use_ws) {
+    if (peers && h->use_ws && !h->visco) {
         // the kernels order the slabs themselves: boundary items poll flag words [w], [w+1] of this slab and the
         // last boundary item of a side publishes into the neighbour's words (same words as k_wait / k_signal)
         const int w = phase == 0 ? 0 : 2, wp = phase == 0 ? 2 : 0;
@@ -1096,7 +1116,7 @@ static int32_t half_step(cpml_handle *h, int32_t it, int phase)
         ss.n_boundary = (phase == 0 ? h->tile_stress : h->tile).ntx * (phase == 0 ? h->tile_stress : h->tile).nty;
         ss.timeout = h->d_timeout;
     } else if (peers) {
-        if (!h->use_tma) FAIL(CPML_ESTATE, "peer stores need the TMA kernels (unset CPML_KERNEL=reg)");
+        if (!h->use_tma && !h->visco) FAIL(CPML_ESTATE, "peer stores need the TMA kernels (unset CPML_KERNEL=reg)");
         const int w = phase == 0 ? 0 : 2;
         // the stress update of step 1 reads the zero halo planes of the reset: nothing to wait for
         if (!(phase == 0 && it == 1)) {
@@ -1136,7 +1156,7 @@ static int32_t half_step(cpml_handle *h, int32_t it, int phase)
         h->n_launches++;
     }
     rc = time_end(h); if (rc) return rc;
-    if (peers && !h->use_ws) {
+    if (peers && (!h->use_ws || h->visco)) {
         const int w = phase == 0 ? 2 : 0;
         launch_signal(h->peer_on[0] ? peer_flags(h, 0) + w + 1 : nullptr, h->peer_on[1] ? peer_flags(h, 1) + w : nullptr,
                       (h->epoch << 32) | (unsigned long long)it, h->stream);
@@ -1280,7 +1300,6 @@ extern "C" int32_t cpml_p2p_export(cpml_handle *h, void *blob, int64_t blob_capa
 {
     if (!h || !blob || !nbytes) return CPML_EINVAL;
     if (h->cfg.ndim != 3) FAIL(CPML_EINVAL, "slabs exist only in 3-D");
-    if (h->visco) FAIL(CPML_EINVAL, "peer stores are implemented for the isotropic kernels; viscoelastic slabs exchange planes through the driver");
     if (blob_capacity < (int64_t)sizeof(cudaIpcMemHandle_t)) FAIL(CPML_EINVAL, "blob too small (need 64 bytes)");
     CK(cudaSetDevice(h->device));
     cudaIpcMemHandle_t mh;
@@ -1293,7 +1312,6 @@ extern "C" int32_t cpml_p2p_export(cpml_handle *h, void *blob, int64_t blob_capa
 static int32_t check_side(cpml_handle *h, int32_t side)
 {
     if (h->cfg.ndim != 3) FAIL(CPML_EINVAL, "slabs exist only in 3-D");
-    if (h->visco) FAIL(CPML_EINVAL, "peer stores are implemented for the isotropic kernels; viscoelastic slabs exchange planes through the driver");
     if (side != 0 && side != 1) FAIL(CPML_EINVAL, "side must be 0 (slab rank-1) or 1 (slab rank+1)");
     if ((side == 0 && h->cfg.slab_rank == 0) || (side == 1 && h->cfg.slab_rank == h->cfg.nslabs - 1))
         FAIL(CPML_ETOPOLOGY, "no neighbour on that side (MPI_PROC_NULL, 3D-iso :775-790)");
@@ -1360,7 +1378,8 @@ extern "C" int32_t cpml_get_launch_info(cpml_handle *h, int32_t *info, int32_t n
     if (!h || !info) return CPML_EINVAL;
     int32_t rc = finalize(h); if (rc) return rc;
     if (h->visco) {
-        const int32_t w[10] = {0, h->vtx, h->vty, 0, h->vkchunk, (int32_t)h->vgrid.z, h->nblocks, h->nblocks, h->nblocks, 0};
+        const int32_t w[10] = {0, h->vtx, h->vty, 0, h->vkchunk, (int32_t)h->vgrid.z, h->nblocks, h->nblocks, h->nblocks,
+                               (h->peer_on[0] ? 1 : 0) + (h->peer_on[1] ? 2 : 0)};
         for (int q = 0; q < n && q < 10; q++) info[q] = w[q];
         return CPML_OK;
     }

@@ -258,6 +258,9 @@ struct ParamsV3D {
     double *partials;         // [0, nb) kinetic (velocity kernel), [nb, 2nb) and [2nb, 3nb) potential (stress launches)
     int nblocks;
     int kchunk;               // planes marched by one block
+    // slab neighbours' fields, element (1,1,0), mapped peer memory (null: no neighbour / exchange done by the driver):
+    // [0] vx [1] vy [2] sigmazz go "left" (3D-visco :963-969, :1230-1232), [3] vz [4] sigmaxz [5] sigmayz "right"
+    double *peer_lo[6], *peer_hi[6];
     int pf;                   // L2 prefetch (set by the dispatcher, CPML_VPF).  Bits 0-1, stress kernel, streamed words:
                               // 0 off, 1 one plane ahead, 2 staggered by half a plane; bit 2, both kernels: the C-PML
                               // memory variables of the next plane

@@ -54,6 +54,25 @@ __device__ __forceinline__ void vst2(double2 *p, double2 v) { __stcs(p, v); }
 // any of four prefetch placements, less than the code costs it when switched off, and has none.
 __device__ __forceinline__ void pf_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// Fourth-order halo exchange by direct stores into the neighbour slabs (replaces the MPI_SENDRECV calls of :962-975
+// and :1229-1242).  A field that travels "left" in the reference (vx, vy, sigmazz: planes 1:2 -> the lower slab's
+// NZ_LOCAL+1:NZ_LOCAL+2) ALSO sends its plane NZ_LOCAL to the upper slab's plane 0, and a field that travels "right"
+// (vz, sigmaxz, sigmayz: planes NZ_LOCAL-1:NZ_LOCAL -> the upper slab's -1:0) ALSO sends its plane 1 to the lower
+// slab's NZ_LOCAL+1: the reference never sends those two planes although its stencils read them (quirk B6); GPU slabs
+// always exchange the complete halo and the kernels decide per plane which taps read zero (nzl_e).
+// rel = offset of the point inside its plane, pl = plane pitch.
+template <bool LEFT>
+__device__ __forceinline__ void peer_put(double *lo, double *hi, int k, int nzl, int rel, int pl, double v)
+{
+    if (LEFT) {
+        if (lo && k <= 2) __stcs(lo + (nzl + k) * pl + rel, v);
+        if (hi && k == nzl) __stcs(hi + rel, v);
+    } else {
+        if (hi && k >= nzl - 1) __stcs(hi + (k - nzl) * pl + rel, v);
+        if (lo && k == 1) __stcs(lo + (nzl + 1) * pl + rel, v);
+    }
+}
+
 // memory_x = b * memory_x + a * value ; value / K + memory_x   (e.g. :993-999); rK = RN(1/K)
 __device__ __forceinline__ double vcpml(double *__restrict__ mem, int q, double b, double a, double K, double rK, double value)
 {
@@ -193,6 +212,7 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
             const bool cut_up = (kmod == 0);                // last plane of a reference slab
             const bool cut_dn = (kmod == 1);                // first plane of a reference slab
             const bool ebox = ebox_ij && kg >= p.npml && kg <= p.nz - p.npml + 1;      // :1387-1392
+            const bool bnd = (k <= 2) | (k >= p.nzl - 1);   // planes a neighbour slab needs (uniform)
             // C-PML memory variables of the NEXT plane (and of the first plane of the chunk) into L2: each
             // recursion is a dependent load -> update -> store, up to three in a row per nest, and the shell
             // points (23 % of the default grid) took 21 % / 31 % of the stall samples of the two kernels with
@@ -286,6 +306,7 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
                     vst(p.sxx + q, sxx); vst(p.syy + q, syy); vst(p.szz + q, szz);
                     vst(p.rxx + q, rxx); vst(p.ryy + q, ryy); vst(p.rzz + q, rzz);
                 }
+                if (bnd) peer_put<true>(p.peer_lo[2], p.peer_hi[2], k, p.nzl, q - k * pl, pl, szz);
                 // potential energy over the PML-free box (:1387-1419), normal-stress terms; quirk B2:
                 // epsilon_yy * sigmayy_R is counted twice and the zz term is missing
                 if (ebox) {
@@ -350,6 +371,7 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
                         rxz = rxz + p.mu * g * dt;
                         vst(p.sxz + q, sxz); vst(p.rxz + q, rxz);
                     }
+                    if (bnd) peer_put<false>(p.peer_lo[4], p.peer_hi[4], k, p.nzl, q - k * pl, pl, sxz);
                     esh += 2.0 * (rxz * p.inv_2mu) * rxz;
                 }
                 {
@@ -372,6 +394,7 @@ k_vstress3d(const __grid_constant__ ParamsV3D p)
                         ryz = ryz + p.mu * g * dt;
                         vst(p.syz + q, syz); vst(p.ryz + q, ryz);
                     }
+                    if (bnd) peer_put<false>(p.peer_lo[5], p.peer_hi[5], k, p.nzl, q - k * pl, pl, syz);
                     esh += 2.0 * (ryz * p.inv_2mu) * ryz;
                 }
                 // potential energy, shear terms (:1411-1419)
@@ -530,6 +553,12 @@ k_vvelocity3d(const __grid_constant__ ParamsV3D p)
             vst(p.vx + q, vx);
             vst(p.vy + q, vy);
             vst(p.vz + q, vz);
+            if ((k <= 2) | (k >= p.nzl - 1)) {              // planes a neighbour slab needs (:962-975)
+                const int rel = q - k * pl;
+                peer_put<true>(p.peer_lo[0], p.peer_hi[0], k, p.nzl, rel, pl, vx);
+                peer_put<true>(p.peer_lo[1], p.peer_hi[1], k, p.nzl, rel, pl, vy);
+                peer_put<false>(p.peer_lo[3], p.peer_hi[3], k, p.nzl, rel, pl, vz);
+            }
 
             // kinetic energy over the PML-free box (:1387-1397)
             if (ebox_ij && kg >= p.npml && kg <= p.nz - p.npml + 1)

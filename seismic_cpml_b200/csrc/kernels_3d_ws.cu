@@ -220,6 +220,7 @@ k_stress3d_ws(const __grid_constant__ Params3D p, const __grid_constant__ TmaMap
         const int i = i0 + 2 * tx, j = j0 + ty;
         const bool row = lane_ok && (j <= p.ny);
         const bool validA = row && (i <= p.nx), validB = row && (i + 1 <= p.nx);
+        const bool storeA = row && (i + 1 <= pitch);                // validA or a pad pair of the row
         unsigned q = (unsigned)kb * pl + (unsigned)((j - 1) * pitch + (i - 1));
 
         const bool in_xA = validA && ((i <= p.xlo) || (i >= p.xhi));
@@ -312,13 +313,17 @@ k_stress3d_ws(const __grid_constant__ Params3D p, const __grid_constant__ TmaMap
 
             // 16-byte streaming stores; where a nest does not update a point (grid edges, the pad
             // lane of an odd NX) the value loaded from this plane is written back unchanged
-            if (validA) {
+            // (pad pairs between NX and the row pitch are stored too -- their values are the TMA's zero fill, no nest
+            // touches them -- so that every row, hence every 32-byte sector of the plane, is written whole)
+            if (storeA) {
                 st_stream2(p.sxx + q, a.sxx, b.sxx);
                 st_stream2(p.syy + q, a.syy, b.syy);
                 st_stream2(p.szz + q, a.szz, b.szz);
                 st_stream2(p.sxy + q, a.sxy, b.sxy);
                 st_stream2(p.sxz + q, a.sxz, b.sxz);
                 st_stream2(p.syz + q, a.syz, b.syz);
+            }
+            if (validA) {
                 // boundary planes go straight into the neighbour slabs' halo planes (:951-963)
                 const unsigned qp = (unsigned)((j - 1) * pitch + (i - 1));
                 if (k == 1 && p.peer_lo[2]) st_stream2(p.peer_lo[2] + qp, a.szz, b.szz);          // sigmazz(:,:,1) -> left
@@ -462,6 +467,7 @@ k_velocity3d_ws(const __grid_constant__ Params3D p, const __grid_constant__ TmaM
         const int i = i0 + 2 * tx, j = j0 + ty;
         const bool row = lane_ok && (j <= p.ny);
         const bool validA = row && (i <= p.nx), validB = row && (i + 1 <= p.nx);
+        const bool storeA = row && (i + 1 <= pitch);                // validA or a pad pair of the row
         unsigned q = (unsigned)kb * pl + (unsigned)((j - 1) * pitch + (i - 1));
 
         const bool in_xA = validA && ((i <= p.xlo) || (i >= p.xhi));
@@ -567,13 +573,16 @@ k_velocity3d_ws(const __grid_constant__ Params3D p, const __grid_constant__ TmaM
             }
             sxz_mA = sxz_c.x; sxz_mB = sxz_c.y; syz_mA = syz_c.x; syz_mB = syz_c.y;
 
-            if (validA) {
-                // the pad lane of an odd NX keeps its zero: B is then outside every nest, not an
-                // edge point, and its loaded value is the TMA's zero fill
-                if (!validB) { b.vx = 0.0; b.vy = 0.0; b.vz = 0.0; }
+            // pad lanes (beyond NX, inside the row pitch) hold and keep zero: they are outside every nest and their
+            // loaded values are the TMA's zero fill; they are stored so that whole rows / sectors are written
+            if (!validA) { a.vx = 0.0; a.vy = 0.0; a.vz = 0.0; }
+            if (!validB) { b.vx = 0.0; b.vy = 0.0; b.vz = 0.0; }
+            if (storeA) {
                 st_stream2(p.vx + q, a.vx, b.vx);
                 st_stream2(p.vy + q, a.vy, b.vy);
                 st_stream2(p.vz + q, a.vz, b.vz);
+            }
+            if (validA) {
                 // boundary planes go straight into the neighbour slabs' halo planes (:811-823)
                 const unsigned qp = (unsigned)((j - 1) * pitch + (i - 1));
                 if (k == 1 && p.peer_lo[0]) {                                                   // -> left

@@ -89,6 +89,25 @@ SYMBOLS = {
     "cpml_get_kernel_times": (C.c_int32, [_H, _dp, _dp, C.POINTER(C.c_int64), C.c_int32]),
     "cpml_enable_kernel_timing": (C.c_int32, [_H, C.c_int32]),
     "cpml_algorithmic_bytes": (C.c_int32, [_H, _dp, _dp]),
+    "cpml_multi_create": (C.c_int32, [C.POINTER(CpmlConfig), C.c_int32, _ip, C.POINTER(_H)]),
+    "cpml_multi_destroy": (C.c_int32, [_H]),
+    "cpml_multi_last_error": (C.c_char_p, [_H]),
+    "cpml_multi_ngpus": (C.c_int32, [_H]),
+    "cpml_multi_slab": (C.c_int32, [_H, C.c_int32, C.POINTER(_H)]),
+    "cpml_multi_reset": (C.c_int32, [_H]),
+    "cpml_multi_set_profiles": (C.c_int32, [_H, C.c_int32] + [_dp] * 6 + [C.c_int32]),
+    "cpml_multi_set_attenuation": (C.c_int32, [_H, C.c_int32, _dp, _dp, _dp, _dp]),
+    "cpml_multi_set_source_series": (C.c_int32, [_H, _dp, _dp, C.c_int32]),
+    "cpml_multi_set_receivers": (C.c_int32, [_H, _ip, _ip, C.c_int32]),
+    "cpml_multi_step": (C.c_int32, [_H, C.c_int32]),
+    "cpml_multi_run": (C.c_int32, [_H, C.c_int32, C.c_int32]),
+    "cpml_multi_synchronize": (C.c_int32, [_H]),
+    "cpml_multi_get_seismograms": (C.c_int32, [_H, _dp, _dp]),
+    "cpml_multi_get_seismograms_vz": (C.c_int32, [_H, _dp]),
+    "cpml_multi_get_energy": (C.c_int32, [_H, _dp, _dp, _dp]),
+    "cpml_multi_get_plane": (C.c_int32, [_H, C.c_int32, C.c_int32, _dp]),
+    "cpml_multi_get_field": (C.c_int32, [_H, C.c_int32, _dp]),
+    "cpml_multi_get_maxnorm": (C.c_int32, [_H, _dp]),
     "cpml_host_pml_profile": (C.c_int32, [C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                           C.c_int32, C.c_int32] + [_dp] * 6),
@@ -448,3 +467,124 @@ class Solver:
         a, b = C.c_double(), C.c_double()
         self._ck(self._L.cpml_algorithmic_bytes(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+
+class MultiSolver:
+    """One cpml_multi handle: the whole 3-D grid decomposed into z-slabs over `ngpus` devices of this node, driven
+    from this one process (the reference's MPI layout without MPI; include/cpml_b200.h "cpml_multi_*")."""
+
+    def __init__(self, ngpus, devices=None, **cfg):
+        self._L = load()
+        nz = cfg["nz"]
+        cfg.setdefault("ndim", 3)
+        cfg.setdefault("order", 2)
+        cfg.setdefault("energy_bug_compat", True)
+        keys = dict(lam="lambda_")
+        c = CpmlConfig()
+        for k, v in cfg.items():
+            setattr(c, keys.get(k, k), int(v) if isinstance(v, bool) else v)
+        c.nslabs, c.slab_rank, c.device = 1, 0, -1
+        self.cfg = c
+        self.ngpus = ngpus
+        self._m = _H()
+        dev = None
+        if devices is not None:
+            dev = np.ascontiguousarray(devices, dtype=np.int32)
+        rc = self._L.cpml_multi_create(C.byref(c), ngpus, _i(dev) if dev is not None else None, C.byref(self._m))
+        if rc:
+            msg = self._L.cpml_multi_last_error(None)
+            self._m = _H()
+            raise CpmlError(rc, msg.decode() if msg else "cpml_multi_create")
+        self.nzl = nz // ngpus
+
+    def _ck(self, rc):
+        if rc:
+            msg = self._L.cpml_multi_last_error(self._m)
+            raise CpmlError(rc, msg.decode() if msg else "")
+
+    def close(self):
+        if getattr(self, "_m", None):
+            self._L.cpml_multi_destroy(self._m)
+            self._m = _H()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def slab_launch_info(self, rank):
+        h = _H()
+        self._ck(self._L.cpml_multi_slab(self._m, rank, C.byref(h)))
+        v = np.zeros(14, dtype=np.int32)
+        rc = self._L.cpml_get_launch_info(h, _i(v), 14)
+        if rc:
+            raise CpmlError(rc, "cpml_get_launch_info")
+        return {"tma": int(v[0]), "peer_sides": int(v[9])}
+
+    def set_profiles(self, axis, prof):
+        arrs = [_f64(prof[k]) for k in PROFILE_KEYS]
+        self._ck(self._L.cpml_multi_set_profiles(self._m, axis, *[_d(a) for a in arrs], arrs[0].size))
+
+    def set_attenuation(self, tau_epsilon_nu1, tau_sigma_nu1, tau_epsilon_nu2, tau_sigma_nu2):
+        arrs = [_f64(a) for a in (tau_epsilon_nu1, tau_sigma_nu1, tau_epsilon_nu2, tau_sigma_nu2)]
+        self._ck(self._L.cpml_multi_set_attenuation(self._m, arrs[0].size, *[_d(a) for a in arrs]))
+
+    def set_source_series(self, force_x, force_y):
+        fx, fy = _f64(force_x), _f64(force_y)
+        self._ck(self._L.cpml_multi_set_source_series(self._m, _d(fx), _d(fy), fx.size))
+
+    def set_receivers(self, ix_rec, iy_rec):
+        ix = np.ascontiguousarray(ix_rec, dtype=np.int32)
+        iy = np.ascontiguousarray(iy_rec, dtype=np.int32)
+        self._ck(self._L.cpml_multi_set_receivers(self._m, _i(ix), _i(iy), ix.size))
+
+    def reset(self):
+        self._ck(self._L.cpml_multi_reset(self._m))
+
+    def step(self, it):
+        self._ck(self._L.cpml_multi_step(self._m, it))
+
+    def run(self, it_begin, it_end):
+        self._ck(self._L.cpml_multi_run(self._m, it_begin, it_end))
+
+    def synchronize(self):
+        self._ck(self._L.cpml_multi_synchronize(self._m))
+
+    def get_seismograms(self):
+        nrec, nstep = self.cfg.nrec, self.cfg.nstep
+        sx, sy = np.zeros((nrec, nstep)), np.zeros((nrec, nstep))
+        self._ck(self._L.cpml_multi_get_seismograms(self._m, _d(sx), _d(sy)))
+        return sx, sy
+
+    def get_seismograms_vz(self):
+        sz = np.zeros((self.cfg.nrec, self.cfg.nstep))
+        self._ck(self._L.cpml_multi_get_seismograms_vz(self._m, _d(sz)))
+        return sz
+
+    def get_energy(self):
+        n = self.cfg.nstep
+        tot, ek, ep = np.zeros(n), np.zeros(n), np.zeros(n)
+        self._ck(self._L.cpml_multi_get_energy(self._m, _d(tot), _d(ek), _d(ep)))
+        return tot, ek, ep
+
+    def get_plane(self, field, kglobal):
+        out = np.zeros((self.cfg.ny, self.cfg.nx))
+        self._ck(self._L.cpml_multi_get_plane(self._m, field, kglobal, _d(out)))
+        return out
+
+    def get_field(self, field):
+        out = np.zeros((self.cfg.nz, self.cfg.ny, self.cfg.nx))
+        self._ck(self._L.cpml_multi_get_field(self._m, field, _d(out)))
+        return out
+
+    def get_maxnorm(self):
+        v = C.c_double()
+        self._ck(self._L.cpml_multi_get_maxnorm(self._m, C.byref(v)))
+        return v.value

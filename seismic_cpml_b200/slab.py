@@ -94,8 +94,6 @@ class SlabDriver:
         self.visco = visco
         self.plan_v = exchange_plan(PHASE_V, nzl, visco)
         self.plan_s = exchange_plan(PHASE_S, nzl, visco)
-        if visco and halo == "p2p":
-            halo = "sendrecv"       # peer stores exist for the isotropic kernels only
         self.left = rank - 1 if rank > 0 else None          # MPI_PROC_NULL at the ends
         self.right = rank + 1 if rank < nslabs - 1 else None
         self._planes = {}

@@ -85,9 +85,9 @@ def test_multi_gpu_slabs_match_oracle(world, halo, tmp_path):
         assert np.array_equal(d["vz"], o["vz"][r * nzl:(r + 1) * nzl])
 
 
-# ---- viscoelastic slabs: NCCL send/recv of the complete fourth-order halo ----------------------
+# ---- viscoelastic slabs: the complete fourth-order halo by in-kernel peer stores or NCCL send/recv ------------
 
-def _visco_worker(rank, world, port, outdir, shape, emulate):
+def _visco_worker(rank, world, port, outdir, shape, emulate, halo="p2p"):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     import torch
@@ -102,7 +102,7 @@ def _visco_worker(rank, world, port, outdir, shape, emulate):
     nx, ny, nz, npml, nstep = shape
     c = refcfg.cfgv3d(nx=nx, ny=ny, nz=nz, npml=npml, nstep=nstep)
     s = TV.solver_visco(c, emulate_nproc=emulate, nslabs=world, slab_rank=rank, device=rank)
-    drv = SlabDriver(GpuSlab(s), rank, world, s.nzl, visco=True)
+    drv = SlabDriver(GpuSlab(s), rank, world, s.nzl, visco=True, halo=halo)
     drv.run(1, nstep)
     owner = owner_of_plane(nz // 2, nz, world)
     sx, sy = drv.seismograms(owner)
@@ -114,9 +114,10 @@ def _visco_worker(rank, world, port, outdir, shape, emulate):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs at least 2 GPUs")
+@pytest.mark.parametrize("halo", ["p2p", "sendrecv"])
 @pytest.mark.parametrize("emulate", [1, 4])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_multi_gpu_visco_slabs_match_oracle(world, emulate, tmp_path):
+def test_multi_gpu_visco_slabs_match_oracle(world, emulate, halo, tmp_path):
     """The result must depend on emulate_nproc (the reference's NPROC) only, never on the number of GPUs."""
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
@@ -124,7 +125,7 @@ def test_multi_gpu_visco_slabs_match_oracle(world, emulate, tmp_path):
     import refcfg
     from oracle import oracle as O
     shape = (40, 37, 48, 5, 80)
-    mp.spawn(_visco_worker, args=(world, _free_port(), str(tmp_path), shape, emulate), nprocs=world, join=True)
+    mp.spawn(_visco_worker, args=(world, _free_port(), str(tmp_path), shape, emulate, halo), nprocs=world, join=True)
     nx, ny, nz, npml, nstep = shape
     c = refcfg.cfgv3d(nx=nx, ny=ny, nz=nz, npml=npml, nstep=nstep)
     o = O.run_3d_visco(**c, nproc=emulate, want_fields=True)
@@ -135,3 +136,80 @@ def test_multi_gpu_visco_slabs_match_oracle(world, emulate, tmp_path):
         assert refcfg.rel_l2(d["e"], o["total_energy"]) <= 1e-11
         assert np.array_equal(d["vz"], o["vz"][r * nzl:(r + 1) * nzl])
         assert np.array_equal(d["sxy_r"], o["sigmaxy_R"][r * nzl:(r + 1) * nzl])
+
+
+# ---- cpml_multi_*: the whole decomposition behind one handle, one host thread, no MPI / torch.distributed --------
+
+def _multi_iso(c, ngpus, devices):
+    from seismic_cpml_b200 import lib as L
+    m = L.MultiSolver(ngpus, devices=devices, ndim=3, order=2, nx=c["nx"], ny=c["ny"], nz=c["nz"], nstep=c["nstep"],
+                      npoints_pml=c["npoints_pml"], nrec=len(c["ix_rec"]), isource=c["isource"], jsource=c["jsource"],
+                      deltax=c["deltax"], deltay=c["deltay"], deltaz=c["deltaz"], deltat=c["deltat"], lam=c["lam"],
+                      mu=c["mu"], lambdaplustwomu=c["lambdaplustwomu"], rho=c["rho"], cp=3300.0)
+    m.set_profiles(0, c["prof_x"]); m.set_profiles(1, c["prof_y"]); m.set_profiles(2, c["prof_z"])
+    m.set_source_series(c["force_x"], c["force_y"])
+    m.set_receivers(c["ix_rec"], c["iy_rec"])
+    return m
+
+
+def _multi_visco(c, ngpus, devices, emulate):
+    from seismic_cpml_b200 import lib as L
+    m = L.MultiSolver(ngpus, devices=devices, ndim=3, order=4, rheology=1, emulate_nproc=emulate, nx=c["nx"], ny=c["ny"],
+                      nz=c["nz"], nstep=c["nstep"], npoints_pml=c["npoints_pml"], nrec=len(c["ix_rec"]),
+                      isource=c["isource"], jsource=c["jsource"], deltax=c["deltax"], deltay=c["deltay"],
+                      deltaz=c["deltaz"], deltat=c["deltat"], lam=c["lam"], mu=c["mu"], rho=c["rho"], cp=c["cp_eff"])
+    m.set_profiles(0, c["prof_x"]); m.set_profiles(1, c["prof_y"]); m.set_profiles(2, c["prof_z"])
+    m.set_attenuation(c["tau_epsilon_nu1"], c["tau_sigma_nu1"], c["tau_epsilon_nu2"], c["tau_sigma_nu2"])
+    m.set_source_series(c["force_x"], c["force_y"])
+    m.set_receivers(c["ix_rec"], c["iy_rec"])
+    return m
+
+
+def _devices(ngpus, spread):
+    """spread: one slab per GPU (needs ngpus devices); else every slab on device 0 (runs on a one-GPU box: the
+    slabs then share a stream, the peer stores and the in-kernel ordering work exactly as across devices)."""
+    if spread and _ngpu() < ngpus:
+        pytest.skip(f"needs {ngpus} GPUs")
+    return list(range(ngpus)) if spread else [0] * ngpus
+
+
+@pytest.mark.parametrize("ngpus,spread", [(2, False), (4, False), (2, True), (4, True), (8, True)])
+def test_multi_handle_isotropic_matches_oracle(ngpus, spread):
+    import refcfg
+    from oracle import oracle as O
+    c = refcfg.cfg3d(nx=40, ny=37, nz=48, npml=5, nstep=80)
+    o = O.run_3d_iso(**c, nproc=2, want_fields=True, want_planes=True)
+    with _multi_iso(c, ngpus, _devices(ngpus, spread)) as m:
+        assert m.slab_launch_info(0) == {"tma": 2, "peer_sides": 2}
+        assert m.slab_launch_info(ngpus - 1)["peer_sides"] == 1
+        m.run(1, 50)
+        m.run(51, c["nstep"])
+        sx, sy = m.get_seismograms()
+        assert np.array_equal(sx, o["sisvx"]) and np.array_equal(sy, o["sisvy"])
+        assert refcfg.rel_l2(m.get_energy()[0], o["total_energy"]) <= 1e-11
+        assert m.get_maxnorm() == pytest.approx(o["vnorm"], rel=1e-15)
+        for f, name in ((0, "vx"), (2, "vz"), (5, "sigmazz"), (7, "sigmaxz")):
+            assert np.array_equal(m.get_field(f), o[name]), name
+        assert np.array_equal(m.get_plane(0, c["nz"] // 2), o["plane_vx"])
+        sx1 = sx.copy()
+        m.reset()                                   # a second run after cpml_multi_reset: the flag epochs move on
+        assert m.get_maxnorm() == 0.0
+        m.run(1, c["nstep"])
+        assert np.array_equal(m.get_seismograms()[0], sx1)
+
+
+@pytest.mark.parametrize("emulate", [1, 4])
+@pytest.mark.parametrize("ngpus,spread", [(2, False), (4, False), (2, True), (8, True)])
+def test_multi_handle_viscoelastic_matches_oracle(ngpus, spread, emulate):
+    import refcfg
+    from oracle import oracle as O
+    c = refcfg.cfgv3d(nx=40, ny=37, nz=48, npml=5, nstep=80)
+    o = O.run_3d_visco(**{k: v for k, v in c.items() if k != "cp_eff"}, nproc=emulate, want_fields=True)
+    with _multi_visco(c, ngpus, _devices(ngpus, spread), emulate) as m:
+        assert m.slab_launch_info(0)["peer_sides"] == 2
+        m.run(1, c["nstep"])
+        sx, sy = m.get_seismograms()
+        assert np.array_equal(sx, o["sisvx"]) and np.array_equal(sy, o["sisvy"])
+        assert refcfg.rel_l2(m.get_energy()[0], o["total_energy"]) <= 1e-11
+        for f, name in ((2, "vz"), (12, "sigmaxy_R"), (7, "sigmaxz")):
+            assert np.array_equal(m.get_field(f), o[name]), name
