@@ -465,6 +465,146 @@ module cpml_b200
       integer(c_int32_t) :: ierr
     end function
 
+    ! ---- the whole z-slab decomposition behind one handle (one host thread, no MPI): cpml_multi_* ----
+    function cpml_multi_create(cfg, ngpus, devices, multi) bind(C, name='cpml_multi_create') result(ierr)
+      import :: c_int32_t, c_ptr, cpml_config
+      type(cpml_config), intent(in) :: cfg
+      integer(c_int32_t), value :: ngpus
+      type(c_ptr), value :: devices          ! c_null_ptr: devices 0..ngpus-1, else c_loc of an integer(c_int32_t) array
+      type(c_ptr), intent(out) :: multi
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_multi_destroy(multi) bind(C, name='cpml_multi_destroy') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: multi
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_multi_last_error(multi) bind(C, name='cpml_multi_last_error') result(msg)
+      import :: c_ptr
+      type(c_ptr), value :: multi
+      type(c_ptr) :: msg
+    end function
+
+    function cpml_multi_ngpus(multi) bind(C, name='cpml_multi_ngpus') result(n)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: multi
+      integer(c_int32_t) :: n
+    end function
+
+    function cpml_multi_slab(multi, rank, handle) bind(C, name='cpml_multi_slab') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: multi
+      integer(c_int32_t), value :: rank
+      type(c_ptr), intent(out) :: handle
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_multi_reset(multi) bind(C, name='cpml_multi_reset') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: multi
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_multi_set_profiles(multi, axis, a, b, K, a_half, b_half, K_half, n) &
+        bind(C, name='cpml_multi_set_profiles') result(ierr)
+      import :: c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: multi
+      integer(c_int32_t), value :: axis, n
+      real(c_double), intent(in) :: a(*), b(*), K(*), a_half(*), b_half(*), K_half(*)
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_multi_set_attenuation(multi, n_sls, tau_epsilon_nu1, tau_sigma_nu1, tau_epsilon_nu2, tau_sigma_nu2) &
+        bind(C, name='cpml_multi_set_attenuation') result(ierr)
+      import :: c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: multi
+      integer(c_int32_t), value :: n_sls
+      real(c_double), intent(in) :: tau_epsilon_nu1(*), tau_sigma_nu1(*), tau_epsilon_nu2(*), tau_sigma_nu2(*)
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_multi_set_source_series(multi, force_x, force_y, n) bind(C, name='cpml_multi_set_source_series') result(ierr)
+      import :: c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: multi
+      real(c_double), intent(in) :: force_x(*), force_y(*)
+      integer(c_int32_t), value :: n
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_multi_set_receivers(multi, ix_rec, iy_rec, n) bind(C, name='cpml_multi_set_receivers') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: multi
+      integer(c_int32_t), intent(in) :: ix_rec(*), iy_rec(*)
+      integer(c_int32_t), value :: n
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_multi_step(multi, it) bind(C, name='cpml_multi_step') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: multi
+      integer(c_int32_t), value :: it
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_multi_run(multi, it_begin, it_end) bind(C, name='cpml_multi_run') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: multi
+      integer(c_int32_t), value :: it_begin, it_end
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_multi_synchronize(multi) bind(C, name='cpml_multi_synchronize') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: multi
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_multi_get_seismograms(multi, sisvx, sisvy) bind(C, name='cpml_multi_get_seismograms') result(ierr)
+      import :: c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: multi
+      real(c_double), intent(out) :: sisvx(*), sisvy(*)
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_multi_get_seismograms_vz(multi, sisvz) bind(C, name='cpml_multi_get_seismograms_vz') result(ierr)
+      import :: c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: multi
+      real(c_double), intent(out) :: sisvz(*)
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_multi_get_energy(multi, total, kinetic, potential) bind(C, name='cpml_multi_get_energy') result(ierr)
+      import :: c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: multi
+      real(c_double), intent(out) :: total(*), kinetic(*), potential(*)
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_multi_get_plane(multi, field, kglobal, plane) bind(C, name='cpml_multi_get_plane') result(ierr)
+      import :: c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: multi
+      integer(c_int32_t), value :: field, kglobal
+      real(c_double), intent(out) :: plane(*)
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_multi_get_field(multi, field, values) bind(C, name='cpml_multi_get_field') result(ierr)
+      import :: c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: multi
+      integer(c_int32_t), value :: field
+      real(c_double), intent(out) :: values(*)
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_multi_get_maxnorm(multi, vmax) bind(C, name='cpml_multi_get_maxnorm') result(ierr)
+      import :: c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: multi
+      real(c_double), intent(out) :: vmax
+      integer(c_int32_t) :: ierr
+    end function
+
   end interface
 
 contains
