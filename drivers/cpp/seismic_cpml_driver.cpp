@@ -15,7 +15,8 @@
 // Parameters are the Fortran `parameter` names given as NAME=value on the command line
 // (the reference edits them in the source and recompiles): NX= NY= NZ= NSTEP= DELTAX=
 // DELTAT= NPOINTS_PML= ISOURCE= JSOURCE= NREC= IT_DISPLAY= f0= factor= ANGLE_FORCE= cp= rho=
-// xdeb= ydeb= xfin= yfin= K_MAX_PML= ; --out DIR selects the output directory,
+// xdeb= ydeb= xfin= yfin= K_MAX_PML= ; NGPU= decomposes the 3-D programs into that many z-slabs, one GPU each, the
+// way the reference uses NPROC MPI ranks (SAME_DEVICE=1: all slabs on device 0); --out DIR selects the output directory,
 // --no-images skips the PNM snapshots.
 //
 // Build: see drivers/Makefile (g++ -O2 -std=c++17 -Iinclude ... -lcpml_b200)
@@ -43,21 +44,61 @@ struct Args {
     int geti(const char *k, int dflt) const { return (int)std::lround(get(k, dflt)); }
 };
 
-[[noreturn]] void die(cpml_handle *h, const char *where)
-{
-    fprintf(stderr, " libcpml_b200 error in %s: %s\n", where, cpml_last_error(h));
-    exit(1);
-}
-#define CHECK(h, call) do { if ((call) != CPML_OK) die(h, #call); } while (0)
 
 struct Profile {
     std::vector<double> a, b, K, a_half, b_half, K_half;
     explicit Profile(int n) : a(n), b(n), K(n), a_half(n), b_half(n), K_half(n) {}
 };
 
-void set_profiles(cpml_handle *h, int axis, const Profile &p, int n)
+// One simulation: a single handle (2-D programs; 3-D with NGPU=1) or, for the 3-D programs with NGPU >= 2, the
+// whole z-slab decomposition behind a cpml_multi handle -- what the reference does with NPROC MPI ranks
+// (3D-iso :337-346, :770-796), here from this one process.  NGPU= selects the number of slabs, one GPU each;
+// SAME_DEVICE=1 puts every slab on device 0 (for boxes with a single GPU).
+struct Sim {
+    cpml_handle *h = nullptr;
+    cpml_multi *m = nullptr;
+    [[noreturn]] void die(const char *where) const
+    {
+        fprintf(stderr, " libcpml_b200 error in %s: %s\n", where, m ? cpml_multi_last_error(m) : cpml_last_error(h));
+        exit(1);
+    }
+    void ck(int32_t rc, const char *where) const { if (rc != CPML_OK) die(where); }
+    void create(const cpml_config &cfg, int ngpu, bool same_device)
+    {
+        if (cfg.ndim == 3 && ngpu >= 2) {
+            std::vector<int32_t> dev(ngpu, 0);
+            if (cpml_multi_create(&cfg, ngpu, same_device ? dev.data() : nullptr, &m) != CPML_OK) {
+                fprintf(stderr, " libcpml_b200 error in cpml_multi_create: %s\n", cpml_multi_last_error(nullptr));
+                exit(1);
+            }
+            printf(" z-slab decomposition over %d GPU slabs (NZ_LOCAL = %d)\n\n", ngpu, cfg.nz / ngpu);
+        } else if (cpml_create(&cfg, &h) != CPML_OK) {
+            fprintf(stderr, " libcpml_b200 error in cpml_create: %s\n", cpml_last_error(nullptr));
+            exit(1);
+        }
+    }
+    void set_profiles(int axis, const double *a, const double *b, const double *K, const double *ah, const double *bh, const double *Kh, int n)
+    { ck(m ? cpml_multi_set_profiles(m, axis, a, b, K, ah, bh, Kh, n) : cpml_set_profiles(h, axis, a, b, K, ah, bh, Kh, n), "set_profiles"); }
+    void set_material_2d(const double *lam, const double *mu, const double *rho) { ck(cpml_set_material_2d(h, lam, mu, rho), "set_material_2d"); }
+    void set_attenuation(int n, const double *a, const double *b, const double *c, const double *d)
+    { ck(m ? cpml_multi_set_attenuation(m, n, a, b, c, d) : cpml_set_attenuation(h, n, a, b, c, d), "set_attenuation"); }
+    void set_source_series(const double *fx, const double *fy, int n)
+    { ck(m ? cpml_multi_set_source_series(m, fx, fy, n) : cpml_set_source_series(h, fx, fy, n), "set_source_series"); }
+    void set_receivers(const int32_t *ix, const int32_t *iy, int n)
+    { ck(m ? cpml_multi_set_receivers(m, ix, iy, n) : cpml_set_receivers(h, ix, iy, n), "set_receivers"); }
+    void run(int a, int b) { ck(m ? cpml_multi_run(m, a, b) : cpml_run(h, a, b), "run"); }
+    void get_maxnorm(double *v) { ck(m ? cpml_multi_get_maxnorm(m, v) : cpml_get_maxnorm(h, v), "get_maxnorm"); }
+    void get_energy(double *t, double *k, double *p) { ck(m ? cpml_multi_get_energy(m, t, k, p) : cpml_get_energy(h, t, k, p), "get_energy"); }
+    void get_seismograms(double *sx, double *sy) { ck(m ? cpml_multi_get_seismograms(m, sx, sy) : cpml_get_seismograms(h, sx, sy), "get_seismograms"); }
+    void get_seismograms_vz(double *sz) { ck(m ? cpml_multi_get_seismograms_vz(m, sz) : cpml_get_seismograms_vz(h, sz), "get_seismograms_vz"); }
+    void get_pressure_seismograms(double *sp) { ck(cpml_get_pressure_seismograms(h, sp), "get_pressure_seismograms"); }
+    void get_plane(int f, int k, double *out) { ck(m ? cpml_multi_get_plane(m, f, k, out) : cpml_get_plane(h, f, k, out), "get_plane"); }
+    void destroy() { if (m) cpml_multi_destroy(m); else cpml_destroy(h); m = nullptr; h = nullptr; }
+};
+
+void set_profiles(Sim &S, int axis, const Profile &p, int n)
 {
-    CHECK(h, cpml_set_profiles(h, axis, p.a.data(), p.b.data(), p.K.data(), p.a_half.data(), p.b_half.data(), p.K_half.data(), n));
+    S.set_profiles(axis, p.a.data(), p.b.data(), p.K.data(), p.a_half.data(), p.b_half.data(), p.K_half.data(), n);
 }
 
 // compute_attenuation_coeffs for the two modes (3D-visco :433-443, 2D-visco-4th :366-376)
@@ -191,30 +232,30 @@ int run_visco(const Args &A)
     } else {
         cfg.compute_energy = COMPUTE_ENERGY;
     }
-    cpml_handle *h = nullptr;
-    CHECK(nullptr, cpml_create(&cfg, &h));
-    set_profiles(h, CPML_AXIS_X, px, NX);
-    set_profiles(h, CPML_AXIS_Y, py, NY);
-    if (is3d) set_profiles(h, CPML_AXIS_Z, pz, NZ);
+    Sim S;
+    S.create(cfg, A.geti("NGPU", 1), A.geti("SAME_DEVICE", 0) != 0);
+    set_profiles(S, CPML_AXIS_X, px, NX);
+    set_profiles(S, CPML_AXIS_Y, py, NY);
+    if (is3d) set_profiles(S, CPML_AXIS_Z, pz, NZ);
     else {
         const size_t n = (size_t)NX * NY;                       // homogeneous unrelaxed medium, :596-602
         const double mu = rho * cs * cs;
         std::vector<double> lam(n, rho * cp * cp - 2.0 * mu), muv(n, mu), rh(n, rho);
-        CHECK(h, cpml_set_material_2d(h, lam.data(), muv.data(), rh.data()));
+        S.set_material_2d(lam.data(), muv.data(), rh.data());
     }
-    CHECK(h, cpml_set_attenuation(h, N_SLS, tau[0].data(), tau[1].data(), tau[2].data(), tau[3].data()));
-    CHECK(h, cpml_set_source_series(h, force_x.data(), force_y.data(), NSTEP));
-    CHECK(h, cpml_set_receivers(h, ix_rec.data(), iy_rec.data(), NREC));
+    S.set_attenuation(N_SLS, tau[0].data(), tau[1].data(), tau[2].data(), tau[3].data());
+    S.set_source_series(force_x.data(), force_y.data(), NSTEP);
+    S.set_receivers(ix_rec.data(), iy_rec.data(), NREC);
 
     std::vector<double> sisvx((size_t)NSTEP * NREC), sisvy((size_t)NSTEP * NREC), sisp((size_t)NSTEP * NREC);
     std::vector<double> e_tot(NSTEP), e_kin(NSTEP), e_pot(NSTEP), plane((size_t)NX * NY);
     const auto t_start = std::chrono::steady_clock::now();
     auto write_all = [&]() {
-        CHECK(h, cpml_get_seismograms(h, sisvx.data(), sisvy.data()));
-        if (!is3d) CHECK(h, cpml_get_pressure_seismograms(h, sisp.data()));
+        S.get_seismograms(sisvx.data(), sisvy.data());
+        if (!is3d) S.get_pressure_seismograms(sisp.data());
         cpml_host_write_seismograms_visco(A.out.c_str(), sisvx.data(), sisvy.data(), is3d ? nullptr : sisp.data(), NSTEP, NREC, DELTAT, t0);
         if (is3d) {     // Vz_file_NNN.dat: an extension, the reference records Vx and Vy only
-            CHECK(h, cpml_get_seismograms_vz(h, sisp.data()));
+            S.get_seismograms_vz(sisp.data());
             cpml_host_write_seismograms_vz(A.out.c_str(), sisp.data(), NSTEP, NREC, DELTAT, t0);
         }
     };
@@ -222,16 +263,16 @@ int run_visco(const Args &A)
     while (it_begin <= NSTEP) {
         int it_end = std::min(NSTEP, (it_begin / IT_DISPLAY + 1) * IT_DISPLAY);
         if (it_begin <= 5 && it_end > 5) it_end = 5;
-        CHECK(h, cpml_run(h, it_begin, it_end));
+        S.run(it_begin, it_end);
         const int it = it_end;
         if (it % IT_DISPLAY == 0 || it == 5) {
             double vnorm = 0.0;
-            CHECK(h, cpml_get_maxnorm(h, &vnorm));
+            S.get_maxnorm(&vnorm);
             const double tcpu = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
             printf(" Time step # %d out of %d\n Time: %g seconds\n Max norm velocity vector V (m/s) = %.15g\n", it, NSTEP,
                    (double)(float)((it - 1) * DELTAT), vnorm);
             if (COMPUTE_ENERGY) {
-                CHECK(h, cpml_get_energy(h, e_tot.data(), e_kin.data(), e_pot.data()));
+                S.get_energy(e_tot.data(), e_kin.data(), e_pot.data());
                 printf(" Total energy = %.15g\n", e_tot[it - 1]);
             }
             printf(" Elapsed time in seconds = %g\n Mean elapsed time per time step in seconds = %g\n\n", tcpu, tcpu / it);
@@ -240,7 +281,7 @@ int run_visco(const Args &A)
             write_all();
             if (A.images)
                 for (int f = 0; f < 2; f++) {
-                    CHECK(h, cpml_get_plane(h, f, is3d ? NZ / 2 : 0, plane.data()));
+                    S.get_plane(f, is3d ? NZ / 2 : 0, plane.data());
                     cpml_host_create_color_image(A.out.c_str(), plane.data(), NX, NY, it, ISOURCE, JSOURCE, ix_rec.data(),
                                                  iy_rec.data(), NREC, NPOINTS_PML, 1, 1, 1, 1, f + 1);
                 }
@@ -249,13 +290,14 @@ int run_visco(const Args &A)
     }
     write_all();
     if (COMPUTE_ENERGY) {
-        CHECK(h, cpml_get_energy(h, e_tot.data(), e_kin.data(), e_pot.data()));
+        S.get_energy(e_tot.data(), e_kin.data(), e_pot.data());
         const std::string epath = A.out + "/energy.dat";
         cpml_host_write_energy_2d(epath.c_str(), e_kin.data(), e_pot.data(), NSTEP, DELTAT);   // time, kinetic, potential, total
     }
+    cpml_host_write_gnuplot_scripts(A.out.c_str(), is3d ? 0 : 1);          // plot_energy, plotgnu (3D-iso :1260-1313)
     const double tcpu = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     printf(" Total elapsed time = %g s, %.3f Gpts/s\n", tcpu, (double)NX * NY * NZ * NSTEP / tcpu / 1e9);
-    cpml_destroy(h);
+    S.destroy();
     printf("\n End of the simulation\n\n");
     return 0;
 }
@@ -335,19 +377,19 @@ int main(int argc, char **argv)
     cfg.deltax = DELTAX; cfg.deltay = DELTAY; cfg.deltaz = DELTAZ; cfg.deltat = DELTAT;
     cfg.lambda = rho * (cp * cp - 2.0 * cs * cs); cfg.mu = rho * cs * cs; cfg.lambdaplustwomu = rho * cp * cp;
     cfg.rho = rho; cfg.cp = cp;
-    cpml_handle *h = nullptr;
-    CHECK(nullptr, cpml_create(&cfg, &h));
-    CHECK(h, cpml_set_profiles(h, CPML_AXIS_X, px.a.data(), px.b.data(), px.K.data(), px.a_half.data(), px.b_half.data(), px.K_half.data(), NX));
-    CHECK(h, cpml_set_profiles(h, CPML_AXIS_Y, py.a.data(), py.b.data(), py.K.data(), py.a_half.data(), py.b_half.data(), py.K_half.data(), NY));
+    Sim S;
+    S.create(cfg, A.geti("NGPU", 1), A.geti("SAME_DEVICE", 0) != 0);
+    S.set_profiles(CPML_AXIS_X, px.a.data(), px.b.data(), px.K.data(), px.a_half.data(), px.b_half.data(), px.K_half.data(), NX);
+    S.set_profiles(CPML_AXIS_Y, py.a.data(), py.b.data(), py.K.data(), py.a_half.data(), py.b_half.data(), py.K_half.data(), NY);
     if (is3d)
-        CHECK(h, cpml_set_profiles(h, CPML_AXIS_Z, pz.a.data(), pz.b.data(), pz.K.data(), pz.a_half.data(), pz.b_half.data(), pz.K_half.data(), NZ));
+        S.set_profiles(CPML_AXIS_Z, pz.a.data(), pz.b.data(), pz.K.data(), pz.a_half.data(), pz.b_half.data(), pz.K_half.data(), NZ);
     else {
         const size_t n = (size_t)NX * NY;     // homogeneous medium of 2D-2nd :468-474
         std::vector<double> lam(n, cfg.lambda), mu(n, cfg.mu), rh(n, rho);
-        CHECK(h, cpml_set_material_2d(h, lam.data(), mu.data(), rh.data()));
+        S.set_material_2d(lam.data(), mu.data(), rh.data());
     }
-    CHECK(h, cpml_set_source_series(h, force_x.data(), force_y.data(), NSTEP));
-    CHECK(h, cpml_set_receivers(h, ix_rec.data(), iy_rec.data(), NREC));
+    S.set_source_series(force_x.data(), force_y.data(), NSTEP);
+    S.set_receivers(ix_rec.data(), iy_rec.data(), NREC);
 
     std::vector<double> sisvx((size_t)NSTEP * NREC), sisvy((size_t)NSTEP * NREC);
     std::vector<double> e_tot(NSTEP), e_kin(NSTEP), e_pot(NSTEP), plane((size_t)NX * NY);
@@ -358,23 +400,23 @@ int main(int argc, char **argv)
     while (it_begin <= NSTEP) {
         int it_end = std::min(NSTEP, (it_begin / IT_DISPLAY + 1) * IT_DISPLAY);
         if (it_begin <= 5 && it_end > 5) it_end = 5;
-        CHECK(h, cpml_run(h, it_begin, it_end));
+        S.run(it_begin, it_end);
         const int it = it_end;
         if (it % IT_DISPLAY == 0 || it == 5) {
             double vnorm = 0.0;
-            CHECK(h, cpml_get_maxnorm(h, &vnorm));
-            CHECK(h, cpml_get_energy(h, e_tot.data(), e_kin.data(), e_pot.data()));
+            S.get_maxnorm(&vnorm);
+            S.get_energy(e_tot.data(), e_kin.data(), e_pot.data());
             const double tcpu = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
             printf(" Time step # %d out of %d\n Time: %g seconds\n Max norm velocity vector V (m/s) = %.15g\n"
                    " Total energy = %.15g\n Elapsed time in seconds = %g\n Mean elapsed time per time step in seconds = %g\n\n",
                    it, NSTEP, (double)(float)((it - 1) * DELTAT), vnorm, e_tot[it - 1], tcpu, tcpu / it);
             if (vnorm > STABILITY_THRESHOLD || !std::isfinite(vnorm)) { fprintf(stderr, "code became unstable and blew up\n"); return 1; }
             if (is3d) cpml_host_write_timestamp(A.out.c_str(), it, DELTAT, vnorm, e_tot[it - 1], tcpu);   // :1219-1229
-            CHECK(h, cpml_get_seismograms(h, sisvx.data(), sisvy.data()));
+            S.get_seismograms(sisvx.data(), sisvy.data());
             cpml_host_write_seismograms(A.out.c_str(), sisvx.data(), sisvy.data(), NSTEP, NREC, DELTAT);
             if (A.images)
                 for (int f = 0; f < 2; f++) {
-                    CHECK(h, cpml_get_plane(h, f, is3d ? NZ / 2 : 0, plane.data()));
+                    S.get_plane(f, is3d ? NZ / 2 : 0, plane.data());
                     cpml_host_create_color_image(A.out.c_str(), plane.data(), NX, NY, it, ISOURCE, JSOURCE, ix_rec.data(),
                                                  iy_rec.data(), NREC, NPOINTS_PML, use_pml, use_pml, use_pml, use_pml, f + 1);
                 }
@@ -383,19 +425,20 @@ int main(int argc, char **argv)
     }
 
     // ---- final output (:1247-1257 ; 2D-2nd :737-746)
-    CHECK(h, cpml_get_seismograms(h, sisvx.data(), sisvy.data()));
+    S.get_seismograms(sisvx.data(), sisvy.data());
     cpml_host_write_seismograms(A.out.c_str(), sisvx.data(), sisvy.data(), NSTEP, NREC, DELTAT);
     if (is3d) {         // Vz_file_NNN.dat: an extension, the reference records Vx and Vy only
-        CHECK(h, cpml_get_seismograms_vz(h, sisvx.data()));
+        S.get_seismograms_vz(sisvx.data());
         cpml_host_write_seismograms_vz(A.out.c_str(), sisvx.data(), NSTEP, NREC, DELTAT, 0.0);
     }
-    CHECK(h, cpml_get_energy(h, e_tot.data(), e_kin.data(), e_pot.data()));
+    S.get_energy(e_tot.data(), e_kin.data(), e_pot.data());
     const std::string epath = A.out + "/energy.dat";
     if (is3d) cpml_host_write_energy_3d(epath.c_str(), e_tot.data(), NSTEP, DELTAT);
     else      cpml_host_write_energy_2d(epath.c_str(), e_kin.data(), e_pot.data(), NSTEP, DELTAT);
+    cpml_host_write_gnuplot_scripts(A.out.c_str(), is3d ? 0 : 1);          // plot_energy, plotgnu (3D-iso :1260-1313)
     const double tcpu = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     printf(" Total elapsed time = %g s, %.3f Gpts/s\n", tcpu, (double)NX * NY * NZ * NSTEP / tcpu / 1e9);
-    cpml_destroy(h);
+    S.destroy();
     printf("\n End of the simulation\n\n");
     return 0;
 }

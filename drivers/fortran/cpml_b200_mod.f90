@@ -605,6 +605,21 @@ module cpml_b200
       integer(c_int32_t) :: ierr
     end function
 
+    function cpml_host_format_real(value, kind, text, capacity) bind(C, name='cpml_host_format_real') result(ierr)
+      import :: c_int32_t, c_double, c_char
+      real(c_double), value :: value
+      integer(c_int32_t), value :: kind, capacity
+      character(kind=c_char), intent(out) :: text(*)
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_host_write_gnuplot_scripts(dir, program) bind(C, name='cpml_host_write_gnuplot_scripts') result(ierr)
+      import :: c_int32_t, c_char
+      character(kind=c_char), intent(in) :: dir(*)
+      integer(c_int32_t), value :: program
+      integer(c_int32_t) :: ierr
+    end function
+
   end interface
 
 contains

@@ -125,6 +125,7 @@ program seismic_CPML_2D_iso_b200
   ierr = cpml_host_write_seismograms(here, sisvx, sisvy, NSTEP, NREC, DELTAT)
   call cpml_check(cpml_get_energy(h, total_energy, total_energy_kinetic, total_energy_potential), h, 'energy')
   ierr = cpml_host_write_energy_2d('energy.dat' // c_null_char, total_energy_kinetic, total_energy_potential, NSTEP, DELTAT)
+  ierr = cpml_host_write_gnuplot_scripts('.' // c_null_char, 1)   ! plot_energy, plotgnu
   ierr = cpml_destroy(h)
 
   print *

@@ -162,6 +162,7 @@ program seismic_CPML_2D_visco_b200
   if (COMPUTE_ENERGY) then
     call cpml_check(cpml_get_energy(h, total_energy, energy_kinetic, energy_potential), h, 'energy')
     ierr = cpml_host_write_energy_2d('energy.dat' // c_null_char, energy_kinetic, energy_potential, NSTEP, DELTAT)
+    ierr = cpml_host_write_gnuplot_scripts('.' // c_null_char, 1)   ! plot_energy, plotgnu
   endif
   ierr = cpml_destroy(h)
 

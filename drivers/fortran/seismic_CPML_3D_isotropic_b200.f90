@@ -129,6 +129,7 @@ program seismic_CPML_3D_iso_b200
   ierr = cpml_host_write_seismograms_vz(here, sisvx, NSTEP, NREC, DELTAT, 0.d0)
   call cpml_check(cpml_get_energy(h, total_energy, energy_kinetic, energy_potential), h, 'energy')
   ierr = cpml_host_write_energy_3d('energy.dat' // c_null_char, total_energy, NSTEP, DELTAT)
+  ierr = cpml_host_write_gnuplot_scripts('.' // c_null_char, 0)   ! plot_energy, plotgnu
   ierr = cpml_destroy(h)
 
   print *

@@ -160,6 +160,7 @@ program seismic_visco_CPML_3D_b200
   ierr = cpml_host_write_seismograms_visco(here, sisvx, sisvy, c_null_ptr, NSTEP, NREC, DELTAT, t0)
   call cpml_check(cpml_get_energy(h, total_energy, energy_kinetic, energy_potential), h, 'energy')
   ierr = cpml_host_write_energy_2d('energy.dat' // c_null_char, energy_kinetic, energy_potential, NSTEP, DELTAT)
+  ierr = cpml_host_write_gnuplot_scripts('.' // c_null_char, 0)   ! plot_energy, plotgnu
   ierr = cpml_destroy(h)
 
   print *

@@ -399,6 +399,15 @@ int32_t cpml_host_create_color_image(const char *dir, const double *image_data_2
                                      int32_t use_pml_xmax, int32_t use_pml_ymin,
                                      int32_t use_pml_ymax, int32_t field_number);
 
+/* Output fidelity.  The writers above produce, byte for byte, what the gfortran build of the reference writes with
+ * its list-directed `write(unit,*)` statements (REAL(4) as 1PG16.9E2, REAL(8) as 1PG25.17E3, 9 / 17 significant digits
+ * in F and E editing alike, one leading blank per record, one blank between items; libgfortran io/write.c).
+ * cpml_host_format_real returns that text for one item (kind 4: the value is demoted like sngl(); kind 8).
+ * cpml_host_write_gnuplot_scripts writes plot_energy, plotgnu (and plot_comparison for the 2-D programs) exactly as
+ * the programs do (3D-iso :1260-1313, 2D-2nd :748-806): program 0 = 3-D, 1 = 2-D. */
+int32_t cpml_host_format_real(double value, int32_t kind, char *out, int32_t capacity);
+int32_t cpml_host_write_gnuplot_scripts(const char *dir, int32_t program);
+
 #ifdef __cplusplus
 }
 #endif

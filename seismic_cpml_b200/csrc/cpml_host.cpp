@@ -5,6 +5,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -165,6 +167,70 @@ extern "C" double cpml_host_courant(double cp, double deltat, double deltax, dou
     return cp * deltat * std::sqrt(s);
 }
 
+// ---- gfortran list-directed output -------------------------------------------------
+// The reference writes its seismogram, energy and timestamp files with `write(unit,*)` (3D-iso :1219-1229,
+// :1254-1256, :1349): the text is whatever the compiler's list-directed formatting produces.  The reference Makefile
+// builds with gfortran, whose run-time library (libgfortran/io/write.c, write_real / set_fnode_default) formats a
+// default REAL(4) as 1PG16.9E2 and a REAL(8) as 1PG25.17E3 "with the same number of significant digits whether F or
+// E editing is used" (9 and 17), a default INTEGER right-justified in 11 columns, starts every record with one blank
+// and puts one blank before every item that follows another one (except a character item after a character item).
+// Restated here so that the files are byte-for-byte what the gfortran build of the reference would write for the
+// same numbers (tests/test_output_format.py checks hand-derived strings).
+namespace {
+
+// 1PGw.dEe of a list-directed item: d significant digits; F editing, followed by e+2 blanks, when the value rounded to
+// d digits lies in [0.1, 10^d), E editing otherwise.
+std::string gf_real(double v, int w, int d, int e)
+{
+    const int n = e + 2;
+    char buf[96];
+    std::string body;
+    bool f_edit = true;
+    if (std::isnan(v)) { body = "NaN"; f_edit = false; }
+    else if (std::isinf(v)) { body = v < 0 ? "-Infinity" : "Infinity"; f_edit = false; }
+    else if (v == 0.0) {
+        snprintf(buf, sizeof buf, "%.*f", d - 1, v);
+        body = buf;
+    } else {
+        snprintf(buf, sizeof buf, "%.*E", d - 1, v);              // correctly rounded to d significant digits
+        const char *E = strchr(buf, 'E');
+        const int ex = atoi(E + 1);
+        if (ex >= -1 && ex < d) {
+            snprintf(buf, sizeof buf, "%#.*f", d - (ex + 1), v);   // '#': gfortran keeps the point of "123456792."
+            body = buf;
+        } else {
+            f_edit = false;
+            body.assign(buf, (size_t)(E - buf));
+            char ebuf[16];
+            snprintf(ebuf, sizeof ebuf, "E%c%0*d", ex < 0 ? '-' : '+', e, std::abs(ex));
+            body += ebuf;
+        }
+    }
+    const int field = f_edit ? w - n : w;
+    std::string out;
+    if ((int)body.size() < field) out.assign((size_t)(field - (int)body.size()), ' ');
+    out += body;
+    if (f_edit) out.append((size_t)n, ' ');
+    return out;
+}
+
+std::string gf_r4(double v) { return gf_real((double)(float)v, 16, 9, 2); }     // sngl(...)
+std::string gf_r8(double v) { return gf_real(v, 25, 17, 3); }
+std::string gf_i4(int v) { char b[16]; snprintf(b, sizeof b, "%11d", v); return b; }
+
+}  // namespace
+
+// The text gfortran writes for a list-directed REAL(4) (kind = 4, the value is first demoted like sngl()) or REAL(8)
+// (kind = 8) item, without the record's leading blank / the item separator.  Exported for the tests and the drivers.
+extern "C" int32_t cpml_host_format_real(double value, int32_t kind, char *out, int32_t capacity)
+{
+    if (!out || (kind != 4 && kind != 8)) return CPML_EINVAL;
+    const std::string s = kind == 4 ? gf_r4(value) : gf_r8(value);
+    if ((int)s.size() + 1 > capacity) return CPML_EINVAL;
+    memcpy(out, s.c_str(), s.size() + 1);
+    return CPML_OK;
+}
+
 // ---- writers ---------------------------------------------------------------------
 
 extern "C" int32_t cpml_host_write_seismograms(const char *dir, const double *sisvx, const double *sisvy,
@@ -180,8 +246,8 @@ extern "C" int32_t cpml_host_write_seismograms(const char *dir, const double *si
             if (!f) return CPML_EINVAL;
             // time and amplitude, both demoted to single precision like sngl(...) :1349
             for (int32_t it = 1; it <= nt; it++)
-                fprintf(f, "  %.8E   %.8E\n", (double)(float)((double)(it - 1) * deltat),
-                        (double)(float)sis[(size_t)(r - 1) * nt + (it - 1)]);
+                fprintf(f, " %s   %s\n", gf_r4((double)(it - 1) * deltat).c_str(),
+                        gf_r4(sis[(size_t)(r - 1) * nt + (it - 1)]).c_str());
             fclose(f);
         }
     }
@@ -199,13 +265,13 @@ extern "C" int32_t cpml_host_write_timestamp(const char *dir, int32_t it, double
     if (!f) return CPML_EINVAL;
     const int int_tcpu = (int)tcpu, ihours = int_tcpu / 3600, iminutes = (int_tcpu - 3600 * ihours) / 60;
     const int iseconds = int_tcpu - 3600 * ihours - 60 * iminutes;
-    fprintf(f, " Time step # %d\n", it);
-    fprintf(f, " Time:   %.8E  seconds\n", (double)(float)((it - 1) * deltat));
-    fprintf(f, " Max norm velocity vector V (m/s) =   %.16E\n", vsolidnorm);
-    fprintf(f, " Total energy =   %.16E\n", total_energy);
-    fprintf(f, " Elapsed time in seconds =   %.16E\n", tcpu);
+    fprintf(f, " Time step #  %s\n", gf_i4(it).c_str());                                   // write(IOUT,*) 'Time step # ',it
+    fprintf(f, " Time:  %s  seconds\n", gf_r4((it - 1) * deltat).c_str());                 // 'Time: ',sngl(...),' seconds'
+    fprintf(f, " Max norm velocity vector V (m/s) =  %s\n", gf_r8(vsolidnorm).c_str());
+    fprintf(f, " Total energy =  %s\n", gf_r8(total_energy).c_str());
+    fprintf(f, " Elapsed time in seconds =  %s\n", gf_r8(tcpu).c_str());
     fprintf(f, " Elapsed time in hh:mm:ss = %4d h %02d m %02d s\n", ihours, iminutes, iseconds);
-    fprintf(f, " Mean elapsed time per time step in seconds =   %.16E\n", tcpu / (double)it);
+    fprintf(f, " Mean elapsed time per time step in seconds =  %s\n", gf_r8(tcpu / (double)it).c_str());
     fclose(f);
     return CPML_OK;
 }
@@ -222,8 +288,8 @@ extern "C" int32_t cpml_host_write_seismograms_vz(const char *dir, const double 
         FILE *f = fopen(join(dir, name).c_str(), "w");
         if (!f) return CPML_EINVAL;
         for (int32_t it = 1; it <= nt; it++)
-            fprintf(f, "  %.8E   %.8E\n", (double)(float)((double)(it - 1) * deltat - t0),
-                    (double)(float)sisvz[(size_t)(r - 1) * nt + (it - 1)]);
+            fprintf(f, " %s   %s\n", gf_r4((double)(it - 1) * deltat - t0).c_str(),
+                    gf_r4(sisvz[(size_t)(r - 1) * nt + (it - 1)]).c_str());
         fclose(f);
     }
     return CPML_OK;
@@ -250,8 +316,8 @@ extern "C" int32_t cpml_host_write_seismograms_visco(const char *dir, const doub
             FILE *f = fopen(join(dir, name).c_str(), "w");
             if (!f) return CPML_EINVAL;
             for (int32_t it = 1; it <= nt; it++)
-                fprintf(f, "  %.8E   %.8E\n", (double)(float)((double)(it - 1) * deltat - t0 + shift),
-                        (double)(float)sis[(size_t)(r - 1) * nt + (it - 1)]);
+                fprintf(f, " %s   %s\n", gf_r4((double)(it - 1) * deltat - t0 + shift).c_str(),
+                        gf_r4(sis[(size_t)(r - 1) * nt + (it - 1)]).c_str());
             fclose(f);
         }
     }
@@ -264,7 +330,7 @@ extern "C" int32_t cpml_host_write_energy_3d(const char *path, const double *tot
     FILE *f = fopen(path, "w");
     if (!f) return CPML_EINVAL;
     for (int32_t it = 1; it <= nt; it++)                                  // :1254-1256
-        fprintf(f, "  %.8E   %.16E\n", (double)(float)((double)(it - 1) * deltat), total[it - 1]);
+        fprintf(f, " %s %s\n", gf_r4((double)(it - 1) * deltat).c_str(), gf_r8(total[it - 1]).c_str());
     fclose(f);
     return CPML_OK;
 }
@@ -276,9 +342,8 @@ extern "C" int32_t cpml_host_write_energy_2d(const char *path, const double *kin
     FILE *f = fopen(path, "w");
     if (!f) return CPML_EINVAL;
     for (int32_t it = 1; it <= nt; it++)                                  // 2D-2nd :742-745
-        fprintf(f, "  %.8E   %.8E   %.8E   %.8E\n", (double)(float)((double)(it - 1) * deltat),
-                (double)(float)kinetic[it - 1], (double)(float)potential[it - 1],
-                (double)(float)(kinetic[it - 1] + potential[it - 1]));
+        fprintf(f, " %s %s %s %s\n", gf_r4((double)(it - 1) * deltat).c_str(), gf_r4(kinetic[it - 1]).c_str(),
+                gf_r4(potential[it - 1]).c_str(), gf_r4(kinetic[it - 1] + potential[it - 1]).c_str());
     fclose(f);
     return CPML_OK;
 }
@@ -330,6 +395,71 @@ extern "C" int32_t cpml_host_create_color_image(const char *dir, const double *i
             fprintf(f, "%3d %3d %3d\n", R, G, B);                          // :1498
         }
     }
+    fclose(f);
+    return CPML_OK;
+}
+
+
+// plot_energy / plotgnu (/ plot_comparison) -- the Gnuplot scripts the programs leave next to their output files
+// (3D-iso :1260-1313, 2D-2nd :748-806; the fourth-order and viscoelastic programs write the same text).  Each line
+// is a list-directed character record (one leading blank), `write(20,*)` alone an empty record.  The receiver list is
+// the reference's own hard-coded one (001 and 002), whatever NREC is.  program: 0 = 3-D (plotgnu also names the Vz
+// files, which the 3-D reference never writes -- quirk B7 -- and this library does), 1 = 2-D.
+extern "C" int32_t cpml_host_write_gnuplot_scripts(const char *dir, int32_t program)
+{
+    if (!dir || (program != 0 && program != 1)) return CPML_EINVAL;
+    auto put = [](FILE *f, const char *line) { if (line[0]) fprintf(f, " %s\n", line); else fprintf(f, "\n"); };
+    const bool d3 = program == 0;
+    FILE *f = fopen(join(dir, "plot_energy").c_str(), "w");
+    if (!f) return CPML_EINVAL;
+    put(f, "# set term x11");
+    put(f, "set term postscript landscape monochrome dashed \"Helvetica\" 22");
+    put(f, "");
+    put(f, "set xlabel \"Time (s)\"");
+    put(f, "set ylabel \"Total energy\"");
+    put(f, "");
+    put(f, d3 ? "set output \"CPML3D_total_energy_semilog.eps\"" : "set output \"cpml_total_energy_semilog.eps\"");
+    put(f, "set logscale y");
+    put(f, d3 ? "plot \"energy.dat\" t 'Total energy' w l lc 1"
+              : "plot \"energy.dat\" us 1:2 t 'Ec' w l lc 1, \"energy.dat\" us 1:3  t 'Ep' w l lc 3, \"energy.dat\" us 1:4 t 'Total energy' w l lc 4");
+    put(f, "pause -1 \"Hit any key...\"");
+    put(f, "");
+    fclose(f);
+    if (!d3) {
+        f = fopen(join(dir, "plot_comparison").c_str(), "w");
+        if (!f) return CPML_EINVAL;
+        put(f, "# set term x11");
+        put(f, "set term postscript landscape monochrome dashed \"Helvetica\" 22");
+        put(f, "");
+        put(f, "set xlabel \"Time (s)\"");
+        put(f, "set ylabel \"Total energy\"");
+        put(f, "");
+        put(f, "set output \"compare_total_energy_semilog.eps\"");
+        put(f, "set logscale y");
+        put(f, "plot \"energy.dat\" us 1:4 t 'Total energy CPML' w l lc 1,  \"../collino/energy.dat\" us 1:4 t 'Total energy Collino' w l lc 2");
+        put(f, "pause -1 \"Hit any key...\"");
+        put(f, "");
+        fclose(f);
+    }
+    f = fopen(join(dir, "plotgnu").c_str(), "w");
+    if (!f) return CPML_EINVAL;
+    put(f, "set term x11");
+    put(f, "# set term postscript landscape monochrome dashed \"Helvetica\" 22");
+    put(f, "");
+    put(f, "set xlabel \"Time (s)\"");
+    put(f, "set ylabel \"Amplitude (m / s)\"");
+    put(f, "");
+    for (int r = 1; r <= 2; r++)
+        for (const char *c : {"Vx", "Vy", "Vz"}) {
+            if (!d3 && c[1] == 'z') continue;
+            char line[128];
+            snprintf(line, sizeof line, "set output \"v_sigma_%s_receiver_%03d.eps\"", c, r);
+            put(f, line);
+            snprintf(line, sizeof line, "plot \"%s_file_%03d.dat\" t '%s C-PML' w l lc 1", c, r, c);
+            put(f, line);
+            put(f, "pause -1 \"Hit any key...\"");
+            put(f, "");
+        }
     fclose(f);
     return CPML_OK;
 }

@@ -128,6 +128,8 @@ SYMBOLS = {
     "cpml_host_write_timestamp": (C.c_int32, [C.c_char_p, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double]),
     "cpml_host_write_energy_3d": (C.c_int32, [C.c_char_p, _dp, C.c_int32, C.c_double]),
     "cpml_host_write_energy_2d": (C.c_int32, [C.c_char_p, _dp, _dp, C.c_int32, C.c_double]),
+    "cpml_host_format_real": (C.c_int32, [C.c_double, C.c_int32, C.c_char_p, C.c_int32]),
+    "cpml_host_write_gnuplot_scripts": (C.c_int32, [C.c_char_p, C.c_int32]),
     "cpml_host_create_color_image": (C.c_int32, [C.c_char_p, _dp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                  C.c_int32, _ip, _ip, C.c_int32, C.c_int32, C.c_int32,
                                                  C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
@@ -251,6 +253,15 @@ def host_attenuation_fit(n_sls, qref, f0, f_min=None, f_max=None, *, linear_only
         raise CpmlError(rc, "cpml_host_attenuation_fit")
     out = (tuple(float(v) for v in te), tuple(float(v) for v in ts))
     return out + (info,) if return_info else out
+
+
+def host_format_real(value, kind=4) -> str:
+    """gfortran's list-directed text of a REAL(kind) item (cpml_host_format_real)."""
+    buf = C.create_string_buffer(64)
+    rc = load().cpml_host_format_real(float(value), kind, buf, 64)
+    if rc:
+        raise CpmlError(rc, "cpml_host_format_real")
+    return buf.value.decode()
 
 
 # ---------------------------------------------------------------- handle

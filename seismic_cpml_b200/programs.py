@@ -592,6 +592,7 @@ class Program3DIso(_ProgramBase):
             self.write_seismograms()
             _lib.load().cpml_host_write_seismograms_vz(self.output_dir.encode(), _lib._d(sz), self.p.NSTEP, self.p.NREC,
                                                        self.p.DELTAT, 0.0)
+            _lib.load().cpml_host_write_gnuplot_scripts(self.output_dir.encode(), 0)       # :1260-1313
             _lib.load().cpml_host_write_energy_3d(os.path.join(self.output_dir, "energy.dat").encode(),
                                                   _lib._d(total), self.p.NSTEP, self.p.DELTAT)
         return dict(sisvx=sx, sisvy=sy, sisvz=sz, total_energy=total, display_log=self.display_log)
@@ -651,6 +652,7 @@ class Program2DIso(_ProgramBase):
         if self.output_dir is not None:  # 2D-2nd :737-746
             os.makedirs(self.output_dir, exist_ok=True)
             self.write_seismograms()
+            _lib.load().cpml_host_write_gnuplot_scripts(self.output_dir.encode(), 1)       # 2D-2nd :748-806
             _lib.load().cpml_host_write_energy_2d(os.path.join(self.output_dir, "energy.dat").encode(),
                                                   _lib._d(ek), _lib._d(ep), self.p.NSTEP, self.p.DELTAT)
         return dict(sisvx=sx, sisvy=sy, energy_kinetic=ek, energy_potential=ep,

@@ -166,6 +166,45 @@ def test_cpp_driver_2d_viscoelastic_output_files_match_oracle(driver_exe, tmp_pa
     assert os.path.exists(tmp_path / "image000100_Vx.pnm")
 
 
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("program", ["3d_iso", "3d_visco"])
+@pytest.mark.parametrize("ngpu,same", [(2, 1), (4, 1), (2, 0), (8, 0)])
+def test_cpp_driver_ngpu_equals_single_gpu(driver_exe, tmp_path, program, ngpu, same):
+    """NGPU= (the compiled driver's stand-in for the reference's NPROC MPI ranks: cpml_multi_*, one host thread, no
+    MPI, no Python): the seismogram and energy FILES of an NGPU run equal those of the one-GPU run byte for byte
+    (energy: to summation order).  same=1 puts every slab on device 0, so this also runs on a one-GPU box."""
+    if not same and _ngpu() < ngpu:
+        pytest.skip(f"needs {ngpu} GPUs")
+    common = ["NX=48", "NY=60", "NZ=48", "NSTEP=100", "NPOINTS_PML=5", "IT_DISPLAY=50", "--no-images"]
+    if program == "3d_iso":
+        common += ["ydeb=300", "yfin=100"]
+    else:
+        common += ["NPROC=4", "xrec1=200", "yrec1=200", "xrec2=160", "yrec2=240", "xrec3=200", "yrec3=240"]
+    outs = []
+    for extra, sub in (([], "one"), ([f"NGPU={ngpu}", f"SAME_DEVICE={same}"], "multi")):
+        d = tmp_path / sub
+        d.mkdir()
+        r = subprocess.run([driver_exe, "--program", program] + common + extra + ["--out", str(d)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr + r.stdout[-500:]
+        outs.append(d)
+        if extra:
+            assert f"z-slab decomposition over {ngpu} GPU slabs" in r.stdout
+    for name in ("Vx_file_001.dat", "Vy_file_002.dat", "Vz_file_001.dat"):
+        a, b = open(outs[0] / name).read(), open(outs[1] / name).read()
+        assert a == b and len(a) > 1000, name
+        assert np.abs(np.loadtxt(outs[0] / name)[:, 1]).max() > 0
+    e0, e1 = np.loadtxt(outs[0] / "energy.dat"), np.loadtxt(outs[1] / "energy.dat")
+    assert np.allclose(e0, e1, rtol=1e-11, atol=0)
+
+
 @pytest.mark.gpu
 def test_cpp_driver_3d_viscoelastic_small_grid(driver_exe, tmp_path):
     r = subprocess.run([driver_exe, "--program", "3d_visco", "NX=60", "NY=80", "NZ=48", "NSTEP=60", "NPROC=2", "IT_DISPLAY=50",
