@@ -432,6 +432,8 @@ def run_b200(args):
              "2dv": ("k_vstress2d", "k_vvelocity2d"), "2d": ("k_stress2d_pair", "k_velocity2d_pair")}[kind]
     if kind == "3d":
         names = sol.kernel_names()
+    elif kind == "3dv" and sol.launch_info()["tma"] == 2:
+        names = ("k_vstress3d", "k_vvelocity3d_ws")
     t_s, t_v = traffic.get("stress_dram_bytes_per_launch"), traffic.get("velocity_dram_bytes_per_launch")
 
     if rank == 0:

@@ -54,6 +54,9 @@ struct cpml_handle {
     double *d_sisvz = nullptr; // 3-D: Vz seismograms (extension, quirk B7)
     dim3 vgrid;
     int vkchunk = 1, vtx = 32, vty = 8;
+    bool v_ws = false;         // TMA-staged velocity kernel with a producer warp (kernels_3d_visco_ws.cu, the default)
+    Tile3D vtile{};
+    TmaMaps vmaps{};
 
     // TMA path (3-D): descriptors of the two kernels' plane tiles, work decomposition
     bool use_tma = false;          // TMA-staged kernels (either family)
@@ -782,6 +785,73 @@ static int32_t setup_tma(cpml_handle *h)
     return CPML_OK;
 }
 
+// Tile, tensor maps and work decomposition of the TMA-staged viscoelastic velocity kernel.  The tensors are the padded
+// arrays (x offset 16, two ghost rows, planes -1 .. NZ_LOCAL+2), so every edge tap reads the zeros the reference reads.
+static int32_t setup_visco_ws(cpml_handle *h)
+{
+    const cpml_config &c = h->cfg;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) FAIL(CPML_ECUDA, "driver does not export cuTensorMapEncodeTiled");
+    const EncodeTiledFn enc = (EncodeTiledFn)fn;
+    Tile3D &t = h->vtile;
+    int best_tx = 104;
+    for (int cand : {108, 64}) {      // the width that wastes the fewest columns
+        const int w_best = (c.nx + best_tx - 1) / best_tx * best_tx, w = (c.nx + cand - 1) / cand * cand;
+        if (w < w_best) best_tx = cand;
+    }
+    t.tx = env_int("CPML_VWS_TX", best_tx);
+    t.ty = 8;
+    if (!vws_tile_supported(t.tx, t.ty)) FAIL(CPML_EINVAL, "unsupported CPML_VWS_TX tile");
+    t.stages = std::max(1, std::min(3, env_int("CPML_VWS_STAGES", 2)));
+    t.minb = 1;
+    t.xm_bytes = h->shell[0].size() > 0 ? round_up(t.ty * h->sxp * 8, 128) : 0;
+    t.ntx = (c.nx + t.tx - 1) / t.tx;
+    t.nty = (c.ny + t.ty - 1) / t.ty;
+    // maps: 0 sxx 1 sxy 2 syy 3 sxz 4 syz 5 szz 6 vx 7 vy 8 vz
+    const int field[9] = {3, 6, 4, 7, 8, 5, 0, 1, 2};
+    int box[9][2];
+    vws_boxes(t.tx, t.ty, box);
+    for (int m = 0; m < 9; m++) {
+        const cuuint64_t dims[3] = {(cuuint64_t)h->pitch, (cuuint64_t)(c.ny + 4), (cuuint64_t)(h->nzl + 4)};
+        const cuuint64_t strides[2] = {(cuuint64_t)h->pitch * sizeof(double), (cuuint64_t)h->plane * sizeof(double)};
+        const cuuint32_t bx[3] = {(cuuint32_t)box[m][0], (cuuint32_t)box[m][1], 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        const CUresult r = enc(&h->vmaps.m[m], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)h->field_alloc[field[m]], dims, strides, bx, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) FAIL(CPML_ECUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    }
+    int occ = 0;
+    while (true) {
+        const cudaError_t e = vws_occupancy(t, &occ);
+        if (e == cudaSuccess && occ >= 1) break;
+        cudaGetLastError();
+        if (t.stages <= 1) FAIL(CPML_ECUDA, "the TMA-staged viscoelastic velocity kernel does not fit on this device");
+        t.stages--;
+    }
+    // z chunks: rounds x (planes per item + pipeline fill and window preload) over the persistent grid, finest within 5 %
+    const int tiles = t.ntx * t.nty, resident = h->sm_count * occ, cmax = std::max(1, h->nzl / 8);
+    auto cost_of = [&](int nc, int *ncr_out) {
+        const int kc = (h->nzl + nc - 1) / nc, ncr = (h->nzl + kc - 1) / kc;
+        *ncr_out = ncr;
+        return (double)(((long long)tiles * ncr + resident - 1) / resident) * (kc + 4.0);
+    };
+    double best_cost = 1e300;
+    for (int nc = 1; nc <= cmax; nc++) { int ncr; best_cost = std::min(best_cost, cost_of(nc, &ncr)); }
+    int best = 1;
+    for (int nc = 1; nc <= cmax; nc++) { int ncr; if (cost_of(nc, &ncr) <= 1.05 * best_cost) best = std::max(best, ncr); }
+    int nzc = env_int("CPML_VWS_ZCHUNKS", 0);
+    if (nzc <= 0) nzc = best;
+    nzc = std::max(1, std::min(nzc, h->nzl));
+    t.kchunk = (h->nzl + nzc - 1) / nzc;
+    t.nzc = (h->nzl + t.kchunk - 1) / t.kchunk;
+    t.nitems = tiles * t.nzc;
+    t.grid_stress = t.grid_velocity = std::min(t.nitems, h->sm_count * occ);
+    return CPML_OK;
+}
+
 // Allocates the shell-only memory variables once every input is known.
 static int32_t finalize(cpml_handle *h)
 {
@@ -853,6 +923,13 @@ static int32_t finalize(cpml_handle *h)
         h->vkchunk = (h->nzl + nzc - 1) / nzc;
         h->vgrid = dim3((c.nx + h->vtx - 1) / h->vtx, (c.ny + h->vty - 1) / h->vty, (h->nzl + h->vkchunk - 1) / h->vkchunk);
         h->nblocks = (int)(h->vgrid.x * h->vgrid.y * h->vgrid.z);
+        // CPML_VKERNEL=reg keeps the register-marching velocity kernel (A/B runs)
+        const char *vk = getenv("CPML_VKERNEL");
+        h->v_ws = !(vk && std::string(vk) == "reg");
+        if (h->v_ws) { const int32_t rc = setup_visco_ws(h); if (rc) return rc; }
+        // energy partial slots: [0, nblocks) kinetic (velocity kernel: one per block or per work item), then two
+        // regions of nblocks for the potential parts of the stress launches; slots a kernel never writes stay zero
+        if (h->v_ws) h->nblocks = std::max(h->nblocks, h->vtile.nitems);
         CK(cudaMalloc(&h->d_partials, 3 * (size_t)h->nblocks * sizeof(double)));
         CK(cudaMemset(h->d_partials, 0, 3 * (size_t)h->nblocks * sizeof(double)));
     } else if (c.ndim == 3) {
@@ -1128,7 +1205,9 @@ static int32_t half_step(cpml_handle *h, int32_t it, int phase)
     rc = time_begin(h, phase); if (rc) return rc;
     if (h->visco) {
         const ParamsV3D p = make_pv(h, it);
-        if (phase == 0) launch_vstress3d(p, h->vgrid, h->stream); else launch_vvelocity3d(p, h->vgrid, h->stream);
+        if (phase == 0) launch_vstress3d(p, h->vgrid, h->stream);
+        else if (h->v_ws) CK(launch_vvelocity3d_ws(p, h->vmaps, h->vtile, h->stream));
+        else launch_vvelocity3d(p, h->vgrid, h->stream);
         h->n_launches += phase == 0 ? visco_stress_launches() : 1;
     } else if (h->cfg.ndim == 3) {
         const Params3D p = make_p3(h, it);
@@ -1378,7 +1457,7 @@ extern "C" int32_t cpml_get_launch_info(cpml_handle *h, int32_t *info, int32_t n
     if (!h || !info) return CPML_EINVAL;
     int32_t rc = finalize(h); if (rc) return rc;
     if (h->visco) {
-        const int32_t w[10] = {0, h->vtx, h->vty, 0, h->vkchunk, (int32_t)h->vgrid.z, h->nblocks, h->nblocks, h->nblocks,
+        const int32_t w[10] = {h->v_ws ? 2 : 0, h->vtx, h->vty, 0, h->vkchunk, (int32_t)h->vgrid.z, h->nblocks, h->nblocks, h->nblocks,
                                (h->peer_on[0] ? 1 : 0) + (h->peer_on[1] ? 2 : 0)};
         for (int q = 0; q < n && q < 10; q++) info[q] = w[q];
         return CPML_OK;

@@ -319,6 +319,10 @@ cudaError_t launch_velocity3d_ws(const Params3D &p, const TmaMaps &tm, const Til
 void launch_signal(unsigned long long *flag_lo, unsigned long long *flag_hi, unsigned long long value, cudaStream_t s);
 void launch_wait(const unsigned long long *flag_a, const unsigned long long *flag_b, unsigned long long value,
                  unsigned int *timeout_flag, cudaStream_t s);
+bool vws_tile_supported(int tx, int ty);
+void vws_boxes(int tx, int ty, int (*box)[2]);
+cudaError_t vws_occupancy(const Tile3D &t, int *occ);
+cudaError_t launch_vvelocity3d_ws(const ParamsV3D &p, const TmaMaps &tm, const Tile3D &t, cudaStream_t s);
 void launch_vstress3d(const ParamsV3D &p, dim3 grid, cudaStream_t s);
 void launch_vvelocity3d(const ParamsV3D &p, dim3 grid, cudaStream_t s);
 void visco_tile(int *tx, int *ty);

@@ -56,15 +56,34 @@ def check_against(s, o, c):
     assert s.get_maxnorm() == pytest.approx(o["vnorm"], rel=1e-15)
 
 
+@pytest.mark.parametrize("vkernel", ["ws", "reg"])
 @pytest.mark.parametrize("shape", [(38, 46, 40, 6), (64, 33, 48, 5), (97, 40, 32, 8)])
 @pytest.mark.parametrize("nproc", [1, 4])
-def test_visco_matches_oracle(shape, nproc):
+def test_visco_matches_oracle(shape, nproc, vkernel, monkeypatch):
     """All 15 fields, seismograms and the three energy traces after 120 steps on ragged grids, for
-    the single-rank semantics and for the reference's default NPROC = 4."""
+    the single-rank semantics and for the reference's default NPROC = 4; with the TMA-staged velocity kernel
+    (ws, the default) and the register-marching one (CPML_VKERNEL=reg)."""
+    monkeypatch.setenv("CPML_VKERNEL", vkernel)
     nx, ny, nz, npml = shape
     c = refcfg.cfgv3d(nx=nx, ny=ny, nz=nz, npml=npml, nstep=120)
     o = O.run_3d_visco(**c, nproc=nproc, want_fields=True)
     with solver_visco(c, emulate_nproc=nproc) as s:
+        assert s.launch_info()["tma"] == (2 if vkernel == "ws" else 0)
+        s.run(1, c["nstep"])
+        check_against(s, o, c)
+
+
+@pytest.mark.parametrize("tx", [64, 104, 108])
+@pytest.mark.parametrize("stages", [1, 2, 3])
+def test_visco_ws_velocity_tiles(tx, stages, monkeypatch):
+    """Every tile width / ring depth of the TMA-staged velocity kernel: two x tiles per row (the second one ragged),
+    three z chunks, K_MAX_PML = 7 shells on all six faces; bitwise."""
+    monkeypatch.setenv("CPML_VWS_TX", str(tx))
+    monkeypatch.setenv("CPML_VWS_STAGES", str(stages))
+    monkeypatch.setenv("CPML_VWS_ZCHUNKS", "3")
+    c = refcfg.cfgv3d(nx=120, ny=37, nz=36, npml=5, nstep=70)
+    o = O.run_3d_visco(**c, nproc=2, want_fields=True)
+    with solver_visco(c, emulate_nproc=2) as s:
         s.run(1, c["nstep"])
         check_against(s, o, c)
 
