@@ -374,6 +374,7 @@ def run_b200(args):
     # (it == 5 and every IT_DISPLAY steps, :1183) the max norm, the seismograms and two snapshot
     # planes come back; at the end the full traces.
     h2d = d2h = 0
+    snap_pending, snap_sum = False, 0.0
     barrier()
     te0 = time.perf_counter()
     a0 = W + K + 1
@@ -389,16 +390,25 @@ def run_b200(args):
             d2h += 8
             if vn > P.STABILITY_THRESHOLD:
                 raise SystemExit("code became unstable and blew up")
-            if is3d:
-                own = owner_of_plane(p.NZ // 2, p.NZ, world)
-                if rank == own:
-                    sx, sy = sol.get_seismograms()
-                    pv = sol.get_plane(0, p.NZ // 2), sol.get_plane(1, p.NZ // 2)
-                    d2h += sx.nbytes + sy.nbytes + pv[0].nbytes + pv[1].nbytes
-            else:
+            # the two snapshot planes of the display (vx, vy of the cut plane / the 2-D fields): asynchronous pulls
+            # (device-side copy + D2H into pinned memory on a side stream); the planes of the PREVIOUS display are
+            # collected first -- the image of step it is written while the loop is already beyond it
+            own = owner_of_plane(p.NZ // 2, p.NZ, world) if is3d else 0
+            if rank == own:
                 sx, sy = sol.get_seismograms()
-                pv = sol.get_plane(0), sol.get_plane(1)
-                d2h += sx.nbytes + sy.nbytes + pv[0].nbytes + pv[1].nbytes
+                d2h += sx.nbytes + sy.nbytes
+                kcut = p.NZ // 2 if is3d else 0
+                for slot in (0, 1):
+                    if snap_pending:
+                        pv = sol.snapshot_end(slot, copy=False)
+                        snap_sum += float(pv[pv.shape[0] // 2, pv.shape[1] // 2])
+                    sol.snapshot_begin(slot, slot, kcut)
+                    d2h += 8 * p.NX * p.NY
+                snap_pending = True
+    if snap_pending:
+        for slot in (0, 1):
+            pv = sol.snapshot_end(slot, copy=False)
+            snap_sum += float(pv[pv.shape[0] // 2, pv.shape[1] // 2])
     sx, sy = sol.get_seismograms()
     en = sol.get_energy()
     d2h += sx.nbytes + sy.nbytes + 3 * en[0].nbytes
@@ -463,8 +473,8 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / K,
                     "d2h_bytes_per_step": float(td.item()) / K,
                     "what": "per step: cpml_set_source_step (16 B pinned H2D) + the step + cpml_fetch_step (32 B D2H); "
-                            "reference display schedule (max norm, seismograms, 2 snapshot planes at it==5 and every "
-                            "IT_DISPLAY) + final traces, host buffers"},
+                            "reference display schedule (max norm, seismograms, 2 snapshot planes through "
+                            "cpml_snapshot_begin/_end at it==5 and every IT_DISPLAY) + final traces, host buffers"},
             "gpu_launches": int(n_launch),
             "clocks": clocks,
         }

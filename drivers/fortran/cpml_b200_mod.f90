@@ -465,6 +465,22 @@ module cpml_b200
       integer(c_int32_t) :: ierr
     end function
 
+    function cpml_snapshot_begin(handle, slot, field, kglobal) bind(C, name='cpml_snapshot_begin') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: slot, field, kglobal
+      integer(c_int32_t) :: ierr
+    end function
+
+    function cpml_snapshot_end(handle, slot, plane, pinned) bind(C, name='cpml_snapshot_end') result(ierr)
+      import :: c_int32_t, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: slot
+      type(c_ptr), value :: plane          ! c_loc of a real(c_double) (NX,NY) array, or c_null_ptr
+      type(c_ptr), value :: pinned         ! c_loc of a type(c_ptr) that receives the pinned buffer, or c_null_ptr
+      integer(c_int32_t) :: ierr
+    end function
+
     ! ---- the whole z-slab decomposition behind one handle (one host thread, no MPI): cpml_multi_* ----
     function cpml_multi_create(cfg, ngpus, devices, multi) bind(C, name='cpml_multi_create') result(ierr)
       import :: c_int32_t, c_ptr, cpml_config

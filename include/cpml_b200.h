@@ -261,6 +261,13 @@ int32_t cpml_get_energy(cpml_handle *h, double *total, double *kinetic, double *
  * Returns CPML_EINVAL if this slab does not hold that plane. */
 int32_t cpml_get_plane(cpml_handle *h, int32_t field, int32_t kglobal, double *out);
 
+/* The same plane without stalling the time loop: _begin copies it device-side (so later steps cannot change it) and
+ * starts the transfer into pinned host memory on a side stream, then returns; _end waits for that transfer and
+ * copies the dense (NX,NY) plane to `out` (may be NULL) and/or hands out the pinned buffer itself (`pinned`, may be
+ * NULL; valid until the next _begin on that slot).  Two slots (0, 1): the reference displays Vx and Vy. */
+int32_t cpml_snapshot_begin(cpml_handle *h, int32_t slot, int32_t field, int32_t kglobal);
+int32_t cpml_snapshot_end(cpml_handle *h, int32_t slot, double *out, const double **pinned);
+
 /* Whole field of this slab, (NX,NY,NZ_LOCAL) (3-D) or (NX,NY) (2-D), dense. */
 int32_t cpml_get_field(cpml_handle *h, int32_t field, double *out);
 

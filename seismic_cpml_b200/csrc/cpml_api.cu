@@ -103,6 +103,12 @@ struct cpml_handle {
     double *pin_src = nullptr;     // pinned host staging: [2][nstep] per-step source increments
     double *pin_out = nullptr;     // pinned host staging: [nstep][4] kinetic, potential, sisvx(it,1), sisvy(it,1)
 
+    // asynchronous snapshot planes (cpml_snapshot_begin / _end): device-side copy, then D2H into pinned memory on a side stream
+    cudaStream_t snap_stream = nullptr;
+    cudaEvent_t snap_ready[2] = {nullptr, nullptr}, snap_done[2] = {nullptr, nullptr};
+    double *snap_dev[2] = {nullptr, nullptr}, *snap_pin[2] = {nullptr, nullptr};
+    bool snap_pending[2] = {false, false};
+
     // launch geometry: 3-D kernels run once per region (interior box + PML shell boxes)
     std::vector<Box3D> regions;
     dim3 grid, block;          // 2-D kernels
@@ -418,6 +424,13 @@ extern "C" int32_t cpml_destroy(cpml_handle *h)
     cudaFree(h->d_sisvx); cudaFree(h->d_sisvy); cudaFree(h->d_sisp); cudaFree(h->d_sisvz); cudaFree(h->d_ek); cudaFree(h->d_ep);
     cudaFree(h->d_partials); cudaFree(h->d_maxbits);
     cudaFreeHost(h->pin_src); cudaFreeHost(h->pin_out);
+    for (int q = 0; q < 2; q++) {
+        if (h->snap_done[q]) cudaEventSynchronize(h->snap_done[q]);
+        cudaFree(h->snap_dev[q]); cudaFreeHost(h->snap_pin[q]);
+        if (h->snap_ready[q]) cudaEventDestroy(h->snap_ready[q]);
+        if (h->snap_done[q]) cudaEventDestroy(h->snap_done[q]);
+    }
+    if (h->snap_stream) cudaStreamDestroy(h->snap_stream);
     for (auto e : h->ev) cudaEventDestroy(e);
     delete h;
     return CPML_OK;
@@ -761,7 +774,10 @@ static int32_t build_tile(cpml_handle *h, EncodeTiledFn enc, bool stress, Tile3D
     }
     int nzc = env_int("CPML_ZCHUNKS", 0);
     if (stress) nzc = env_int("CPML_ZCHUNKS_STRESS", nzc);
-    if (nzc <= 0) nzc = best;
+    // producer-warp stress kernel: twice as many chunks again (default grid: 40 chunks of 16 planes 0.967 ms against
+    // 0.995 ms with 20; 64 or 80 chunks no better -- profiles/r02_c_bench.txt); its item-boundary cost is small because
+    // the producer starts the next item's loads while the consumers finish the current one
+    if (nzc <= 0) nzc = (stress && h->use_ws) ? std::min(cmax, 2 * best) : best;
     nzc = std::max(1, std::min(nzc, h->nzl));
     t.kchunk = (h->nzl + nzc - 1) / nzc;
     t.nzc = (h->nzl + t.kchunk - 1) / t.kchunk;
@@ -1540,6 +1556,61 @@ extern "C" int32_t cpml_get_plane(cpml_handle *h, int32_t field, int32_t kglobal
     return CPML_OK;
 }
 
+// ---- asynchronous snapshot planes ------------------------------------------------------
+// The display phase of the reference hands vx(:,:,NZ_LOCAL) and vy(:,:,NZ_LOCAL) to create_color_image every IT_DISPLAY
+// steps (3D-iso :1236-1239; the 2-D programs their whole 134 MB fields at 4096 x 4096).  cpml_get_plane copies
+// synchronously into the caller's pageable buffer and stalls the time loop for the whole transfer;
+// cpml_snapshot_begin instead copies the plane device-side (a dense NX x NY image, so later time steps cannot touch it)
+// and starts the device-to-host transfer into PINNED memory on a side stream: the loop goes on, and
+// cpml_snapshot_end collects the plane whenever the driver wants it (typically at the next display step).
+
+extern "C" int32_t cpml_snapshot_begin(cpml_handle *h, int32_t slot, int32_t field, int32_t kglobal)
+{
+    if (!h) return CPML_EINVAL;
+    const cpml_config &c = h->cfg;
+    if (slot < 0 || slot > 1) FAIL(CPML_EINVAL, "snapshot slot must be 0 or 1");
+    if (field < 0 || field >= h->nfields) FAIL(CPML_EINVAL, "bad field id");
+    if (h->snap_pending[slot]) FAIL(CPML_ESTATE, "snapshot slot still holds a plane that was not collected (cpml_snapshot_end)");
+    CK(cudaSetDevice(h->device));
+    long long off = 0;
+    if (c.ndim == 3) {
+        const int kl = kglobal - h->koff;
+        if (kl < 1 || kl > h->nzl) FAIL(CPML_EINVAL, "this slab does not hold that plane");
+        off = (long long)kl * h->plane;
+    }
+    const size_t bytes = (size_t)c.nx * c.ny * sizeof(double);
+    if (!h->snap_stream) CK(cudaStreamCreateWithFlags(&h->snap_stream, cudaStreamNonBlocking));
+    if (!h->snap_dev[slot]) {
+        CK(cudaMalloc(&h->snap_dev[slot], bytes));
+        CK(cudaMallocHost(&h->snap_pin[slot], bytes));
+        CK(cudaEventCreateWithFlags(&h->snap_ready[slot], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->snap_done[slot], cudaEventDisableTiming));
+        CK(cudaEventRecord(h->snap_done[slot], h->snap_stream));
+    }
+    CK(cudaStreamWaitEvent(h->stream, h->snap_done[slot], 0));          // the previous transfer out of snap_dev is over
+    CK(cudaMemcpy2DAsync(h->snap_dev[slot], (size_t)c.nx * sizeof(double), h->f0[field] + off, (size_t)h->pitch * sizeof(double),
+                         (size_t)c.nx * sizeof(double), c.ny, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaEventRecord(h->snap_ready[slot], h->stream));
+    CK(cudaStreamWaitEvent(h->snap_stream, h->snap_ready[slot], 0));
+    CK(cudaMemcpyAsync(h->snap_pin[slot], h->snap_dev[slot], bytes, cudaMemcpyDeviceToHost, h->snap_stream));
+    CK(cudaEventRecord(h->snap_done[slot], h->snap_stream));
+    h->snap_pending[slot] = true;
+    return CPML_OK;
+}
+
+extern "C" int32_t cpml_snapshot_end(cpml_handle *h, int32_t slot, double *out, const double **pinned)
+{
+    if (!h) return CPML_EINVAL;
+    if (slot < 0 || slot > 1) FAIL(CPML_EINVAL, "snapshot slot must be 0 or 1");
+    if (!h->snap_pending[slot]) FAIL(CPML_ESTATE, "no snapshot was started in this slot (cpml_snapshot_begin)");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventSynchronize(h->snap_done[slot]));
+    if (out) memcpy(out, h->snap_pin[slot], (size_t)h->cfg.nx * h->cfg.ny * sizeof(double));
+    if (pinned) *pinned = h->snap_pin[slot];        // valid until the next cpml_snapshot_begin on this slot
+    h->snap_pending[slot] = false;
+    return CPML_OK;
+}
+
 extern "C" int32_t cpml_get_field(cpml_handle *h, int32_t field, double *out)
 {
     if (!h || !out) return CPML_EINVAL;
@@ -1640,8 +1711,9 @@ extern "C" int32_t cpml_algorithmic_bytes(cpml_handle *h, double *bytes_stress, 
         // stress: read vx,vy, lambda, mu; read+write 3 sigma; x: dvx_dx (half), dvy_dx (int); y: dvy_dy (int), dvx_dy (half)
         const double px = (double)c.ny, py = (double)c.nx;
         ws = 10.0 * N + 2.0 * (px * (nz[0][0] + nz[0][1]) + py * (nz[1][0] + nz[1][1]));
-        // velocity: read 3 sigma, rho, (lambda, mu for the energy); read+write vx,vy
-        wv = 10.0 * N + 2.0 * (px * (nz[0][0] + nz[0][1]) + py * (nz[1][0] + nz[1][1]));
+        // velocity: read 3 sigma, rho; read+write vx,vy (the potential energy is summed in the stress kernel, which
+        // already holds lambda and mu: 18 words per point-update)
+        wv = 8.0 * N + 2.0 * (px * (nz[0][0] + nz[0][1]) + py * (nz[1][0] + nz[1][1]));
     }
     if (bytes_stress) *bytes_stress = 8.0 * ws;
     if (bytes_velocity) *bytes_velocity = 8.0 * wv;

@@ -246,55 +246,81 @@ __device__ __forceinline__ void stress_point2(const Params2D &p, int i, int j, b
     }
 }
 
+// Potential energy of one point from the stresses of this step (2D-2nd :706-711); lives in the STRESS kernel, which
+// has lambda, mu and the new stresses in registers, so that the velocity kernel does not stream lambda and mu a
+// second time (18 instead of 20 words per point-update).
+template <int ORDER>
+__device__ __forceinline__ double epot_point2(const Params2D &p, int i, int j, double lam, double mu, double sxx, double syy, double sxy)
+{
+    const int e0 = ORDER == 4 ? p.npml : p.npml + 1;                       // 2D-2nd :695-704, 2D-4th :696-705
+    const int ex1 = ORDER == 4 ? p.nx - p.npml + 1 : p.nx - p.npml;
+    const int ey1 = ORDER == 4 ? p.ny - p.npml + 1 : p.ny - p.npml;
+    if (!(i >= e0 && i <= ex1 && j >= e0 && j <= ey1)) return 0.0;
+    // one division for both 1/(4 mu (lambda + mu)) and 1/(2 mu): the energy is a sum whose order differs from the
+    // reference's anyway (tolerance 1e-11, not bitwise)
+    const double inv4 = __drcp_rn(4.0 * mu * (lam + mu));
+    const double epsilon_xx = ((lam + 2.0 * mu) * sxx - lam * syy) * inv4;
+    const double epsilon_yy = ((lam + 2.0 * mu) * syy - lam * sxx) * inv4;
+    const double epsilon_xy = sxy * (inv4 * (2.0 * (lam + mu)));
+    return 0.5 * (epsilon_xx * sxx + epsilon_yy * syy + 2.0 * epsilon_xy * sxy);
+}
+
 template <int ORDER, int TX, int TY, int MINB>
 __global__ void __launch_bounds__(TX *TY, MINB)
 k_stress2d_pair(const __grid_constant__ Params2D p)
 {
+    __shared__ double red[2 * TX * TY / 32];
     const int i = 2 * (blockIdx.x * TX + threadIdx.x) + 1;            // A; B = i + 1
     const int j = blockIdx.y * TY + threadIdx.y + 1;
-    if (i > p.nx || j > p.ny) return;
-    const bool validB = i + 1 <= p.nx;
-    const int pitch = p.pitch;
-    const long long q = (long long)(j - 1) * pitch + (i - 1);           // even: 16-byte aligned
-    const bool in_y = (j <= p.ylo) || (j >= p.yhi);
-    const bool in_xA = (i <= p.xlo) || (i >= p.xhi), in_xB = validB && ((i + 1 <= p.xlo) || (i + 1 >= p.xhi));
-    const long long qxA = in_xA ? (long long)(j - 1) * p.sxp + shell_index2(i, p.xlo, p.xhi) : 0;
-    const long long qxB = in_xB ? (long long)(j - 1) * p.sxp + shell_index2(i + 1, p.xlo, p.xhi) : 0;
-    const long long qy = in_y ? (long long)shell_index2(j, p.ylo, p.yhi) * pitch + (i - 1) : 0;
+    double epot = 0.0, unused = 0.0;
+    if (i <= p.nx && j <= p.ny) {
+        const bool validB = i + 1 <= p.nx;
+        const int pitch = p.pitch;
+        const long long q = (long long)(j - 1) * pitch + (i - 1);           // even: 16-byte aligned
+        const bool in_y = (j <= p.ylo) || (j >= p.yhi);
+        const bool in_xA = (i <= p.xlo) || (i >= p.xhi), in_xB = validB && ((i + 1 <= p.xlo) || (i + 1 >= p.xhi));
+        const long long qxA = in_xA ? (long long)(j - 1) * p.sxp + shell_index2(i, p.xlo, p.xhi) : 0;
+        const long long qxB = in_xB ? (long long)(j - 1) * p.sxp + shell_index2(i + 1, p.xlo, p.xhi) : 0;
+        const long long qy = in_y ? (long long)shell_index2(j, p.ylo, p.yhi) * pitch + (i - 1) : 0;
 
-    const double2 lam_c = ld2(p.lambda, q), mu_c = ld2(p.mu, q), mu_jp = ld2(p.mu, q + pitch);
-    const double lam_r = p.lambda[q + 2], mu_r = p.mu[q + 2];
-    const double2 vx_c = ld2(p.vx, q), vx_r = ld2(p.vx, q + 2), vx_jp = ld2(p.vx, q + pitch);
-    const double2 vy_c = ld2(p.vy, q), vy_l = ld2(p.vy, q - 2), vy_jm = ld2(p.vy, q - pitch);
-    double2 vx_l = make_double2(0.0, 0.0), vx_jpp = vx_l, vx_jm = vx_l, vy_jp = vx_l, vy_jmm = vx_l;
-    double vy_r = 0.0;
-    if (ORDER == 4) {
-        vx_l = ld2(p.vx, q - 2); vx_jpp = ld2(p.vx, q + 2 * pitch); vx_jm = ld2(p.vx, q - pitch);
-        vy_jp = ld2(p.vy, q + pitch); vy_jmm = ld2(p.vy, q - 2 * pitch); vy_r = p.vy[q + 2];
+        const double2 lam_c = ld2(p.lambda, q), mu_c = ld2(p.mu, q), mu_jp = ld2(p.mu, q + pitch);
+        const double lam_r = p.lambda[q + 2], mu_r = p.mu[q + 2];
+        const double2 vx_c = ld2(p.vx, q), vx_r = ld2(p.vx, q + 2), vx_jp = ld2(p.vx, q + pitch);
+        const double2 vy_c = ld2(p.vy, q), vy_l = ld2(p.vy, q - 2), vy_jm = ld2(p.vy, q - pitch);
+        double2 vx_l = make_double2(0.0, 0.0), vx_jpp = vx_l, vx_jm = vx_l, vy_jp = vx_l, vy_jmm = vx_l;
+        double vy_r = 0.0;
+        if (ORDER == 4) {
+            vx_l = ld2(p.vx, q - 2); vx_jpp = ld2(p.vx, q + 2 * pitch); vx_jm = ld2(p.vx, q - pitch);
+            vy_jp = ld2(p.vy, q + pitch); vy_jmm = ld2(p.vy, q - 2 * pitch); vy_r = p.vy[q + 2];
+        }
+        double2 sxx = ld2(p.sxx, q), syy = ld2(p.syy, q), sxy = ld2(p.sxy, q);
+
+        stress_point2<ORDER>(p, i, j, in_xA, in_y, qxA, qy, lam_c.x, lam_c.y, mu_c.x, mu_c.y, mu_jp.x,
+                             vx_c.y, vx_c.x, vx_r.x, vx_l.y, vx_jp.x, vx_jpp.x, vx_jm.x,
+                             vy_c.x, vy_l.y, vy_c.y, vy_l.x, vy_jm.x, vy_jp.x, vy_jmm.x, sxx.x, syy.x, sxy.x);
+        if (validB)
+            stress_point2<ORDER>(p, i + 1, j, in_xB, in_y, qxB, qy + 1, lam_c.y, lam_r, mu_c.y, mu_r, mu_jp.y,
+                                 vx_r.x, vx_c.y, vx_r.y, vx_c.x, vx_jp.y, vx_jpp.y, vx_jm.y,
+                                 vy_c.y, vy_c.x, vy_r, vy_l.y, vy_jm.y, vy_jp.y, vy_jmm.y, sxx.y, syy.y, sxy.y);
+        st2(p.sxx, q, sxx.x, sxx.y);
+        st2(p.syy, q, syy.x, syy.y);
+        st2(p.sxy, q, sxy.x, sxy.y);
+        epot = epot_point2<ORDER>(p, i, j, lam_c.x, mu_c.x, sxx.x, syy.x, sxy.x);
+        if (validB) epot += epot_point2<ORDER>(p, i + 1, j, lam_c.y, mu_c.y, sxx.y, syy.y, sxy.y);
     }
-    double2 sxx = ld2(p.sxx, q), syy = ld2(p.syy, q), sxy = ld2(p.sxy, q);
-
-    stress_point2<ORDER>(p, i, j, in_xA, in_y, qxA, qy, lam_c.x, lam_c.y, mu_c.x, mu_c.y, mu_jp.x,
-                         vx_c.y, vx_c.x, vx_r.x, vx_l.y, vx_jp.x, vx_jpp.x, vx_jm.x,
-                         vy_c.x, vy_l.y, vy_c.y, vy_l.x, vy_jm.x, vy_jp.x, vy_jmm.x, sxx.x, syy.x, sxy.x);
-    if (validB)
-        stress_point2<ORDER>(p, i + 1, j, in_xB, in_y, qxB, qy + 1, lam_c.y, lam_r, mu_c.y, mu_r, mu_jp.y,
-                             vx_r.x, vx_c.y, vx_r.y, vx_c.x, vx_jp.y, vx_jpp.y, vx_jm.y,
-                             vy_c.y, vy_c.x, vy_r, vy_l.y, vy_jm.y, vy_jp.y, vy_jmm.y, sxx.y, syy.y, sxy.y);
-    st2(p.sxx, q, sxx.x, sxx.y);
-    st2(p.syy, q, syy.x, syy.y);
-    st2(p.sxy, q, sxy.x, sxy.y);
+    block_sum2_2d<TX * TY>(epot, unused, red);
+    if (threadIdx.x == 0 && threadIdx.y == 0) p.partials[p.nblocks + blockIdx.y * gridDim.x + blockIdx.x] = epot;
 }
 
 template <int ORDER>
 __device__ __forceinline__ void velocity_point2(const Params2D &p, int i, int j, bool in_x, bool in_y, long long qx, long long qy,
-                                                double rho, double rho_half_x_half_y, double lam, double mu,
+                                                double rho, double rho_half_x_half_y,
                                                 // sxx: i, i-1, i+1, i-2 ; sxy: (j, j-1, j+1, j-2) and (i+1, i, i+2, i-1) ; syy: j+1, j, j+2, j-1
                                                 double sxx_c, double sxx_im, double sxx_ip, double sxx_imm,
                                                 double sxy_c, double sxy_jm, double sxy_jp, double sxy_jmm,
                                                 double sxy_ip, double sxy_ipp, double sxy_im,
                                                 double syy_c, double syy_jp, double syy_jpp, double syy_jm,
-                                                double &vx, double &vy, double &ekin, double &epot)
+                                                double &vx, double &vy, double &ekin)
 {
     const double DELTAT = p.deltat;
     if (i >= 2 && j >= 2) {
@@ -322,14 +348,7 @@ __device__ __forceinline__ void velocity_point2(const Params2D &p, int i, int j,
     const int e0 = ORDER == 4 ? p.npml : p.npml + 1;
     const int ex1 = ORDER == 4 ? p.nx - p.npml + 1 : p.nx - p.npml;
     const int ey1 = ORDER == 4 ? p.ny - p.npml + 1 : p.ny - p.npml;
-    if (i >= e0 && i <= ex1 && j >= e0 && j <= ey1) {
-        ekin += 0.5 * (rho * (vx * vx + vy * vy));
-        const double inv4 = __drcp_rn(4.0 * mu * (lam + mu));
-        const double epsilon_xx = ((lam + 2.0 * mu) * sxx_c - lam * syy_c) * inv4;
-        const double epsilon_yy = ((lam + 2.0 * mu) * syy_c - lam * sxx_c) * inv4;
-        const double epsilon_xy = sxy_c * (inv4 * (2.0 * (lam + mu)));
-        epot += 0.5 * (epsilon_xx * sxx_c + epsilon_yy * syy_c + 2.0 * epsilon_xy * sxy_c);
-    }
+    if (i >= e0 && i <= ex1 && j >= e0 && j <= ey1) ekin += 0.5 * (rho * (vx * vx + vy * vy));     // potential part: k_stress2d_pair
 }
 
 template <int ORDER, int TX, int TY, int MINB>
@@ -356,7 +375,6 @@ k_velocity2d_pair(const __grid_constant__ Params2D p)
         const double rhoA = rho_c.x, rhoB = rho_c.y;
         const double rho_hA = 0.25 * (rho_c.x + rho_c.y + rho_jp.y + rho_jp.x);          // 2D-2nd :627
         const double rho_hB = 0.25 * (rho_c.y + rho_r + rho_jpr + rho_jp.y);
-        const double2 lam = ld2(p.lambda, q), mu = ld2(p.mu, q);
         const double2 sxx_c = ld2(p.sxx, q), sxx_l = ld2(p.sxx, q - 2);
         const double2 sxy_c = ld2(p.sxy, q), sxy_r = ld2(p.sxy, q + 2), sxy_jm = ld2(p.sxy, q - pitch);
         const double2 syy_c = ld2(p.syy, q), syy_jp = ld2(p.syy, q + pitch);
@@ -368,24 +386,20 @@ k_velocity2d_pair(const __grid_constant__ Params2D p)
         }
         double2 v_x = ld2(p.vx, q), v_y = ld2(p.vy, q);
 
-        velocity_point2<ORDER>(p, i, j, in_xA, in_y, qxA, qy, rhoA, rho_hA, lam.x, mu.x,
+        velocity_point2<ORDER>(p, i, j, in_xA, in_y, qxA, qy, rhoA, rho_hA,
                                sxx_c.x, sxx_l.y, sxx_c.y, sxx_l.x,
                                sxy_c.x, sxy_jm.x, sxy_jp.x, sxy_jmm.x, sxy_c.y, sxy_r.x, sxy_l.y,
-                               syy_c.x, syy_jp.x, syy_jpp.x, syy_jm.x, v_x.x, v_y.x, ekin, epot);
+                               syy_c.x, syy_jp.x, syy_jpp.x, syy_jm.x, v_x.x, v_y.x, ekin);
         if (validB)
-            velocity_point2<ORDER>(p, i + 1, j, in_xB, in_y, qxB, qy + 1, rhoB, rho_hB, lam.y, mu.y,
+            velocity_point2<ORDER>(p, i + 1, j, in_xB, in_y, qxB, qy + 1, rhoB, rho_hB,
                                    sxx_c.y, sxx_c.x, sxx_r, sxx_l.y,
                                    sxy_c.y, sxy_jm.y, sxy_jp.y, sxy_jmm.y, sxy_r.x, sxy_r.y, sxy_c.x,
-                                   syy_c.y, syy_jp.y, syy_jpp.y, syy_jm.y, v_x.y, v_y.y, ekin, epot);
+                                   syy_c.y, syy_jp.y, syy_jpp.y, syy_jm.y, v_x.y, v_y.y, ekin);
         st2(p.vx, q, v_x.x, v_x.y);
         st2(p.vy, q, v_y.x, v_y.y);
     }
     block_sum2_2d<TX * TY>(ekin, epot, red);
-    if (threadIdx.x == 0 && threadIdx.y == 0) {
-        const int b = blockIdx.y * gridDim.x + blockIdx.x;
-        p.partials[b] = ekin;
-        p.partials[p.nblocks + b] = epot;
-    }
+    if (threadIdx.x == 0 && threadIdx.y == 0) p.partials[blockIdx.y * gridDim.x + blockIdx.x] = ekin;
 }
 
 static int pair_mode()

@@ -84,6 +84,8 @@ SYMBOLS = {
     "cpml_get_seismograms_vz": (C.c_int32, [_H, _dp]),
     "cpml_get_energy": (C.c_int32, [_H, _dp, _dp, _dp]),
     "cpml_get_plane": (C.c_int32, [_H, C.c_int32, C.c_int32, _dp]),
+    "cpml_snapshot_begin": (C.c_int32, [_H, C.c_int32, C.c_int32, C.c_int32]),
+    "cpml_snapshot_end": (C.c_int32, [_H, C.c_int32, _dp, C.POINTER(_dp)]),
     "cpml_get_field": (C.c_int32, [_H, C.c_int32, _dp]),
     "cpml_get_maxnorm": (C.c_int32, [_H, _dp]),
     "cpml_get_kernel_times": (C.c_int32, [_H, _dp, _dp, C.POINTER(C.c_int64), C.c_int32]),
@@ -454,6 +456,23 @@ class Solver:
         out = np.zeros((self.cfg.ny, self.cfg.nx))
         self._ck(self._L.cpml_get_plane(self._h, field, kglobal, _d(out)))
         return out
+
+    def snapshot_begin(self, slot, field, kglobal=0):
+        """Start the asynchronous pull of one (NX,NY) plane (device-side copy + D2H into pinned memory on a side
+        stream); the time loop is not stalled.  Collect with snapshot_end(slot)."""
+        self._ck(self._L.cpml_snapshot_begin(self._h, slot, field, kglobal))
+
+    def snapshot_end(self, slot, copy=True):
+        """The plane started by snapshot_begin(slot): a copy (default) or a zero-copy view of the library's pinned
+        buffer (valid until the next snapshot_begin on that slot)."""
+        ny, nx = self.cfg.ny, self.cfg.nx
+        if copy:
+            out = np.zeros((ny, nx))
+            self._ck(self._L.cpml_snapshot_end(self._h, slot, _d(out), None))
+            return out
+        ptr = _dp()
+        self._ck(self._L.cpml_snapshot_end(self._h, slot, None, C.byref(ptr)))
+        return np.ctypeslib.as_array(ptr, shape=(ny, nx))
 
     def get_field(self, field):
         shape = (self.nzl, self.cfg.ny, self.cfg.nx) if self.cfg.ndim == 3 else (self.cfg.ny, self.cfg.nx)

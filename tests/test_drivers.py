@@ -110,7 +110,7 @@ def test_cpp_driver_3d_small_grid(driver_exe, tmp_path):
     assert d.shape == (120, 2) and e.shape == (120, 2) and np.abs(d[:, 1]).max() > 0 and np.all(np.isfinite(e))
     assert os.path.exists(tmp_path / "image000100_Vy.pnm")
     stamp = open(tmp_path / "timestamp000100").read()            # 3D-iso :1219-1229
-    assert "Time step # 100" in stamp and "Total energy =" in stamp and "Elapsed time in hh:mm:ss" in stamp
+    assert " Time step #          100\n" in stamp and "Total energy =" in stamp and "Elapsed time in hh:mm:ss" in stamp
     vz = np.loadtxt(tmp_path / "Vz_file_001.dat")               # extension (quirk B7)
     assert vz.shape == (120, 2) and np.all(np.isfinite(vz))
 

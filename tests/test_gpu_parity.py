@@ -488,3 +488,34 @@ def test_3d_default_grid_450_steps_vs_timed_oracle():
     assert refcfg.rel_l2(sx[0], o["sisvx"][0]) <= TOL and refcfg.rel_l2(sy[0], o["sisvy"][0]) <= TOL
     assert refcfg.rel_l2(e, o["total_energy"]) <= TOL
     assert refcfg.rel_l2(pvx, o["plane_vx"]) <= TOL and refcfg.rel_l2(pvy, o["plane_vy"]) <= TOL
+
+
+def test_asynchronous_snapshot_planes():
+    """cpml_snapshot_begin / _end: the plane is the one of the step at which the pull was STARTED, however far the loop
+    has moved on when it is collected (device-side copy first); slots are independent; misuse is refused."""
+    c = refcfg.cfg3d(nx=37, ny=45, nz=40, nstep=90, npml=6)
+    k = c["nz"] // 2
+    with solver3d(c) as s:
+        s.run(1, 50)
+        ref_vx, ref_vy = s.get_plane(0, k), s.get_plane(1, k)
+        s.snapshot_begin(0, 0, k)
+        s.snapshot_begin(1, 1, k)
+        with pytest.raises(L.CpmlError):
+            s.snapshot_begin(0, 0, k)                  # slot 0 has not been collected yet
+        for it in range(51, 91):                       # the loop goes on while the planes travel
+            s.step_stress(it); s.step_velocity(it); s.step_finish(it)
+        a = s.snapshot_end(0)
+        b = s.snapshot_end(1, copy=False).copy()
+        assert np.array_equal(a, ref_vx) and np.array_equal(b, ref_vy) and np.abs(a).max() > 0
+        assert not np.array_equal(s.get_plane(0, k), ref_vx)
+        with pytest.raises(L.CpmlError):
+            s.snapshot_end(0)
+        s.snapshot_begin(0, 2, k)                      # the slot is free again
+        assert np.array_equal(s.snapshot_end(0), s.get_plane(2, k))
+    c2 = refcfg.cfg2d(4, nx=70, ny=90, nstep=40, npml=8, ydeb=500.0, yfin=200.0)
+    with solver2d(c2) as s2:
+        s2.run(1, 30)
+        ref = s2.get_plane(1)
+        s2.snapshot_begin(0, 1)
+        s2.run(31, 40)
+        assert np.array_equal(s2.snapshot_end(0), ref)
