@@ -197,10 +197,12 @@ def test_cpp_driver_ngpu_equals_single_gpu(driver_exe, tmp_path, program, ngpu, 
         outs.append(d)
         if extra:
             assert f"z-slab decomposition over {ngpu} GPU slabs" in r.stdout
-    for name in ("Vx_file_001.dat", "Vy_file_002.dat", "Vz_file_001.dat"):
+    peak = 0.0
+    for name in ("Vx_file_001.dat", "Vy_file_001.dat", "Vy_file_002.dat", "Vz_file_001.dat"):
         a, b = open(outs[0] / name).read(), open(outs[1] / name).read()
         assert a == b and len(a) > 1000, name
-        assert np.abs(np.loadtxt(outs[0] / name)[:, 1]).max() > 0
+        peak = max(peak, np.abs(np.loadtxt(outs[0] / name)[:, 1]).max())
+    assert peak > 0                    # (the viscoelastic source acts along y: Vx stays zero at receivers on its axis)
     e0, e1 = np.loadtxt(outs[0] / "energy.dat"), np.loadtxt(outs[1] / "energy.dat")
     assert np.allclose(e0, e1, rtol=1e-11, atol=0)
 
