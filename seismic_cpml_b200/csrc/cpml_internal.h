@@ -32,10 +32,12 @@ struct Shell {
 
 // 1-based device views of the six coefficient arrays of one axis, plus the correctly rounded
 // reciprocals of K and K_half (for div_exact).
-struct AxisCoef {
-    const double *a, *b, *K, *a_half, *b_half, *K_half;
-    const double *rK, *rK_half;
+template <typename T>
+struct AxisCoefT {
+    const T *a, *b, *K, *a_half, *b_half, *K_half;
+    const T *rK, *rK_half;
 };
+using AxisCoef = AxisCoefT<double>;
 
 #ifdef __CUDACC__
 // a / c, correctly rounded, for a divisor whose correctly rounded reciprocal y = RN(1/c) is known
@@ -134,24 +136,28 @@ __device__ __forceinline__ void div_exact3(double &a0, double &a1, double &a2, d
 #endif
 
 // ------------------------------------------------------------------ 3-D
-struct Params3D {
+// T = double: the reference's precision.  T = float: the single-precision build the reference endorses ("significantly
+// faster", 3D-iso :114-116): fields, memory variables, profiles and update constants in single precision; the energy
+// is still accumulated in double.
+template <typename T>
+struct Params3DT {
     int nx, ny, nzl;          // local slab extent
     int nz;                   // global NZ
     int koff;                 // offset_k = rank * NZ_LOCAL (3D-iso :397)
     int pitch;                // row pitch in doubles
     long long plane;          // plane pitch in doubles (= pitch * ny)
     // fields: pointer to element (i=1, j=1, k=0)
-    double *vx, *vy, *vz, *sxx, *syy, *szz, *sxy, *sxz, *syz;
+    T *vx, *vy, *vz, *sxx, *syy, *szz, *sxy, *sxz, *syz;
     // shells
     int xlo, xhi, sxp;        // sxp: padded x-shell row length
     int ylo, yhi, sy;         // sy: number of y-shell rows
     int zlo, zhi;             // global z shell
     int zbase;                // global shell index of this slab's first stored z-shell plane
     // memory variables, see kernels_3d.cu for the order inside each group
-    double *mx[6], *my[6], *mz[6];
-    AxisCoef cx, cy, cz;      // cz is indexed by GLOBAL k
-    double odx, ody, odz;     // ONE_OVER_DELTAX.. (:134-136)
-    double dt_lambda, dt_mu, dt_lambdaplus2mu, dt_over_rho;   // :296-300
+    T *mx[6], *my[6], *mz[6];
+    AxisCoefT<T> cx, cy, cz;  // cz is indexed by GLOBAL k
+    T odx, ody, odz;          // ONE_OVER_DELTAX.. (:134-136)
+    T dt_lambda, dt_mu, dt_lambdaplus2mu, dt_over_rho;   // :296-300
     // velocity kernel extras
     int it;                   // time step (1-based)
     int isrc, jsrc, ksrc;     // source point, ksrc local (0: not on this slab)
@@ -167,9 +173,11 @@ struct Params3D {
     // slab neighbours' halo planes, element (1,1), mapped peer memory (null: no neighbour /
     // exchange done by the driver).  lo = slab rank-1, its plane NZ_LOCAL+1: vx, vy, sigmazz;
     // hi = slab rank+1, its plane 0: vz, sigmaxz, sigmayz  (3D-iso :811-823, :951-963)
-    double *peer_lo[3];
-    double *peer_hi[3];
+    T *peer_lo[3];
+    T *peer_hi[3];
 };
+using Params3D = Params3DT<double>;
+using Params3DF = Params3DT<float>;
 
 // TMA descriptors of one kernel's nine plane tiles (kernels_3d_tma.cu lists the order).
 struct TmaMaps {

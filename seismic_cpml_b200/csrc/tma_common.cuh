@@ -18,15 +18,21 @@ constexpr int kBarBytes = 128;   // room for up to 16 mbarriers ahead of the sta
 
 __host__ __device__ constexpr int round128(int v) { return (v + 127) / 128 * 128; }
 
-template <int TX, int TY>
-struct TileGeom {
-    static constexpr int W = TX + 2;                       // halo box row length
+// HX: cells a halo box starts before the tile when the operator reaches back -- 16 bytes (the x start of a tiled load
+// must be 16-byte aligned): 2 doubles or 4 floats; the box is TX + HX wide either way.
+template <typename T, int TX, int TY>
+struct TileGeomT {
+    static constexpr int ES = (int)sizeof(T);
+    static constexpr int HX = 16 / ES;
+    static constexpr int W = TX + HX;                      // halo box row length
     static constexpr int HROWS = TY + 1;                   // halo box rows
-    static constexpr int HALO_BOX_BYTES = W * HROWS * 8;
-    static constexpr int PLAIN_BOX_BYTES = TX * TY * 8;
+    static constexpr int HALO_BOX_BYTES = W * HROWS * ES;
+    static constexpr int PLAIN_BOX_BYTES = TX * TY * ES;
     static constexpr int HALO_BYTES = round128(HALO_BOX_BYTES);
     static constexpr int PLAIN_BYTES = round128(PLAIN_BOX_BYTES);
 };
+template <int TX, int TY>
+using TileGeom = TileGeomT<double, TX, TY>;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -65,12 +71,13 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void st_stream(double *p, double v) { __stcs(p, v); }
+template <typename T>
+__device__ __forceinline__ void st_stream(T *p, T v) { __stcs(p, v); }
 
 // memory_x = b * memory_x + a * value ; value = value / K + memory_x   (e.g. :845-851)
-template <bool KUNIT>
-__device__ __forceinline__ double cpml_apply(double *__restrict__ mem, long long q, double m,
-                                             double b, double a, double K, double value)
+template <bool KUNIT, typename T>
+__device__ __forceinline__ T cpml_apply(T *__restrict__ mem, long long q, T m,
+                                        T b, T a, T K, T value)
 {
     m = b * m + a * value;
     mem[q] = m;
@@ -81,9 +88,9 @@ __device__ __forceinline__ double cpml_apply(double *__restrict__ mem, long long
 // a = 0 and m = 0, so their m' is 0 and the derivative comes back as value + 0 (exact; only the
 // sign of a zero can differ); only shell lanes store.  This keeps the C-PML code of a warp that
 // holds a few shell lanes straight-line instead of nine divergent blocks per point.
-template <bool KUNIT>
-__device__ __forceinline__ double cpml_step(double *__restrict__ mem, long long q, bool store, double m,
-                                            double b, double a, double K, double value)
+template <bool KUNIT, typename T>
+__device__ __forceinline__ T cpml_step(T *__restrict__ mem, long long q, bool store, T m,
+                                       T b, T a, T K, T value)
 {
     m = b * m + a * value;
     if (store) mem[q] = m;
@@ -142,32 +149,34 @@ struct RingPos {
 // half the address / predicate / barrier instructions per point, two independent dependency
 // chains): with one point per thread the kernels were bound by instruction latency, not by
 // HBM (profiles/r01_v4_*).  The point update itself is written once, per point.
-struct StressVals { double sxx, syy, szz, sxy, sxz, syz; };   // in: old values, out: new values
+template <typename T>
+struct StressValsT { T sxx, syy, szz, sxy, sxz, syz; };   // in: old values, out: new values
+using StressVals = StressValsT<double>;
 
 // Coefficient table of the tile's columns in shared memory: rows a, b, K, a_half, b_half, K_half
 // (CXW doubles each).  ux / uy / uz: the warp holds x- / y-shell lanes, the plane lies in the z
 // shell (warp-uniform); in_* : this point does (stores its memory variables).
-template <bool PML, bool KUNIT, int CXW>
+template <bool PML, bool KUNIT, int CXW, typename T>
 __device__ __forceinline__ void stress_point(
-    const Params3D &p, const double *__restrict__ Cx, const int c, const int j, const int kg,
+    const Params3DT<T> &p, const T *__restrict__ Cx, const int c, const int j, const int kg,
     const bool do_n, const bool do_xy, const bool do_xz, const bool do_yz,
     const bool ux, const bool uy, const bool uz, const bool in_x, const bool in_y, const bool in_z,
-    const long long qx, const long long qy, const long long qz, const double (&mv)[9],
-    const double vx_c, const double vx_ip, const double vx_jp, const double vx_n,
-    const double vy_c, const double vy_im, const double vy_jm, const double vy_n,
-    const double vz_c, const double vz_im, const double vz_jp, const double vz_m, StressVals &s)
+    const long long qx, const long long qy, const long long qz, const T (&mv)[9],
+    const T vx_c, const T vx_ip, const T vx_jp, const T vx_n,
+    const T vy_c, const T vy_im, const T vy_jm, const T vy_n,
+    const T vz_c, const T vz_im, const T vz_jp, const T vz_m, StressValsT<T> &s)
 {
-    const double odx = p.odx, ody = p.ody, odz = p.odz;
-    const double dt_l = p.dt_lambda, dt_m = p.dt_mu, dt_l2m = p.dt_lambdaplus2mu;
+    const T odx = p.odx, ody = p.ody, odz = p.odz;
+    const T dt_l = p.dt_lambda, dt_m = p.dt_mu, dt_l2m = p.dt_lambdaplus2mu;
     // ---- sigmaxx, sigmayy, sigmazz  (:836-863)
     if (do_n && kg >= 2) {                                  // k2begin, :792-793
-        double value_dvx_dx = (vx_ip - vx_c) * odx;
-        double value_dvy_dy = (vy_c - vy_jm) * ody;
-        double value_dvz_dz = (vz_c - vz_m) * odz;
+        T value_dvx_dx = (vx_ip - vx_c) * odx;
+        T value_dvy_dy = (vy_c - vy_jm) * ody;
+        T value_dvz_dz = (vz_c - vz_m) * odz;
         if (PML) {
-            if (ux) value_dvx_dx = cpml_step<KUNIT>(p.mx[0], qx, in_x, mv[0], Cx[4 * CXW + c], Cx[3 * CXW + c], KUNIT ? 1.0 : Cx[5 * CXW + c], value_dvx_dx);
-            if (uy) value_dvy_dy = cpml_step<KUNIT>(p.my[0], qy, in_y, mv[3], p.cy.b[j], p.cy.a[j], KUNIT ? 1.0 : p.cy.K[j], value_dvy_dy);
-            if (uz) value_dvz_dz = cpml_step<KUNIT>(p.mz[0], qz, in_z, mv[6], p.cz.b[kg], p.cz.a[kg], KUNIT ? 1.0 : p.cz.K[kg], value_dvz_dz);
+            if (ux) value_dvx_dx = cpml_step<KUNIT>(p.mx[0], qx, in_x, mv[0], Cx[4 * CXW + c], Cx[3 * CXW + c], KUNIT ? T(1) : Cx[5 * CXW + c], value_dvx_dx);
+            if (uy) value_dvy_dy = cpml_step<KUNIT>(p.my[0], qy, in_y, mv[3], p.cy.b[j], p.cy.a[j], KUNIT ? T(1) : p.cy.K[j], value_dvy_dy);
+            if (uz) value_dvz_dz = cpml_step<KUNIT>(p.mz[0], qz, in_z, mv[6], p.cz.b[kg], p.cz.a[kg], KUNIT ? T(1) : p.cz.K[kg], value_dvz_dz);
         }
         s.sxx = dt_l2m * value_dvx_dx + dt_l * (value_dvy_dy + value_dvz_dz) + s.sxx;
         s.syy = dt_l * (value_dvx_dx + value_dvz_dz) + dt_l2m * value_dvy_dy + s.syy;
@@ -175,31 +184,31 @@ __device__ __forceinline__ void stress_point(
     }
     // ---- sigmaxy  (:877-894)
     if (do_xy) {
-        double value_dvy_dx = (vy_c - vy_im) * odx;
-        double value_dvx_dy = (vx_jp - vx_c) * ody;
+        T value_dvy_dx = (vy_c - vy_im) * odx;
+        T value_dvx_dy = (vx_jp - vx_c) * ody;
         if (PML) {
-            if (ux) value_dvy_dx = cpml_step<KUNIT>(p.mx[1], qx, in_x, mv[1], Cx[1 * CXW + c], Cx[0 * CXW + c], KUNIT ? 1.0 : Cx[2 * CXW + c], value_dvy_dx);
-            if (uy) value_dvx_dy = cpml_step<KUNIT>(p.my[1], qy, in_y, mv[4], p.cy.b_half[j], p.cy.a_half[j], KUNIT ? 1.0 : p.cy.K_half[j], value_dvx_dy);
+            if (ux) value_dvy_dx = cpml_step<KUNIT>(p.mx[1], qx, in_x, mv[1], Cx[1 * CXW + c], Cx[0 * CXW + c], KUNIT ? T(1) : Cx[2 * CXW + c], value_dvy_dx);
+            if (uy) value_dvx_dy = cpml_step<KUNIT>(p.my[1], qy, in_y, mv[4], p.cy.b_half[j], p.cy.a_half[j], KUNIT ? T(1) : p.cy.K_half[j], value_dvx_dy);
         }
         s.sxy = dt_m * (value_dvy_dx + value_dvx_dy) + s.sxy;
     }
     // ---- sigmaxz, sigmayz  (:908-943)
     if (kg <= p.nz - 1) {                                   // kminus1end, :795-796
         if (do_xz) {
-            double value_dvz_dx = (vz_c - vz_im) * odx;
-            double value_dvx_dz = (vx_n - vx_c) * odz;
+            T value_dvz_dx = (vz_c - vz_im) * odx;
+            T value_dvx_dz = (vx_n - vx_c) * odz;
             if (PML) {
-                if (ux) value_dvz_dx = cpml_step<KUNIT>(p.mx[2], qx, in_x, mv[2], Cx[1 * CXW + c], Cx[0 * CXW + c], KUNIT ? 1.0 : Cx[2 * CXW + c], value_dvz_dx);
-                if (uz) value_dvx_dz = cpml_step<KUNIT>(p.mz[1], qz, in_z, mv[7], p.cz.b_half[kg], p.cz.a_half[kg], KUNIT ? 1.0 : p.cz.K_half[kg], value_dvx_dz);
+                if (ux) value_dvz_dx = cpml_step<KUNIT>(p.mx[2], qx, in_x, mv[2], Cx[1 * CXW + c], Cx[0 * CXW + c], KUNIT ? T(1) : Cx[2 * CXW + c], value_dvz_dx);
+                if (uz) value_dvx_dz = cpml_step<KUNIT>(p.mz[1], qz, in_z, mv[7], p.cz.b_half[kg], p.cz.a_half[kg], KUNIT ? T(1) : p.cz.K_half[kg], value_dvx_dz);
             }
             s.sxz = dt_m * (value_dvz_dx + value_dvx_dz) + s.sxz;
         }
         if (do_yz) {
-            double value_dvz_dy = (vz_jp - vz_c) * ody;
-            double value_dvy_dz = (vy_n - vy_c) * odz;
+            T value_dvz_dy = (vz_jp - vz_c) * ody;
+            T value_dvy_dz = (vy_n - vy_c) * odz;
             if (PML) {
-                if (uy) value_dvz_dy = cpml_step<KUNIT>(p.my[2], qy, in_y, mv[5], p.cy.b_half[j], p.cy.a_half[j], KUNIT ? 1.0 : p.cy.K_half[j], value_dvz_dy);
-                if (uz) value_dvy_dz = cpml_step<KUNIT>(p.mz[2], qz, in_z, mv[8], p.cz.b_half[kg], p.cz.a_half[kg], KUNIT ? 1.0 : p.cz.K_half[kg], value_dvy_dz);
+                if (uy) value_dvz_dy = cpml_step<KUNIT>(p.my[2], qy, in_y, mv[5], p.cy.b_half[j], p.cy.a_half[j], KUNIT ? T(1) : p.cy.K_half[j], value_dvz_dy);
+                if (uz) value_dvy_dz = cpml_step<KUNIT>(p.mz[2], qz, in_z, mv[8], p.cz.b_half[kg], p.cz.a_half[kg], KUNIT ? T(1) : p.cz.K_half[kg], value_dvy_dz);
             }
             s.syz = dt_m * (value_dvz_dy + value_dvy_dz) + s.syz;
         }
@@ -207,22 +216,27 @@ __device__ __forceinline__ void stress_point(
 }
 
 // Fills the column coefficient table of a tile (columns beyond NX: a = b = 0, K = 1).
-template <int TX, int NT>
-__device__ __forceinline__ void fill_cx(const Params3D &p, double *Cx, int i0, int tid)
+template <int TX, int NT, typename T>
+__device__ __forceinline__ void fill_cx(const Params3DT<T> &p, T *Cx, int i0, int tid)
 {
     for (int e = tid; e < 6 * TX; e += NT) {
         const int f = e / TX, i = i0 + (e - f * TX);
-        const double *src = f == 0 ? p.cx.a : f == 1 ? p.cx.b : f == 2 ? p.cx.K : f == 3 ? p.cx.a_half : f == 4 ? p.cx.b_half : p.cx.K_half;
-        Cx[e] = (i <= p.nx) ? src[i] : ((f == 2 || f == 5) ? 1.0 : 0.0);
+        const T *src = f == 0 ? p.cx.a : f == 1 ? p.cx.b : f == 2 ? p.cx.K : f == 3 ? p.cx.a_half : f == 4 ? p.cx.b_half : p.cx.K_half;
+        Cx[e] = (i <= p.nx) ? src[i] : ((f == 2 || f == 5) ? T(1) : T(0));
     }
 }
 
 __device__ __forceinline__ double2 lds2(const double *t, int e) { return *reinterpret_cast<const double2 *>(t + e); }
+__device__ __forceinline__ float2 lds2(const float *t, int e) { return *reinterpret_cast<const float2 *>(t + e); }
 __device__ __forceinline__ void st_stream2(double *p, double a, double b) { __stcs(reinterpret_cast<double2 *>(p), make_double2(a, b)); }
+__device__ __forceinline__ void st_stream2(float *p, float a, float b) { __stcs(reinterpret_cast<float2 *>(p), make_float2(a, b)); }
+__device__ __forceinline__ double2 ldg2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ float2 ldg2(const float *p) { return *reinterpret_cast<const float2 *>(p); }
 
 // Loads the nine C-PML memory variables of one point (group g0 = 0: stress kernel, 3: velocity).
-__device__ __forceinline__ void load_memvars(const Params3D &p, int g0, bool in_x, bool in_y, bool in_z,
-                                             long long qx, long long qy, long long qz, double (&mv)[9])
+template <typename T>
+__device__ __forceinline__ void load_memvars(const Params3DT<T> &p, int g0, bool in_x, bool in_y, bool in_z,
+                                             long long qx, long long qy, long long qz, T (&mv)[9])
 {
     if (in_x) { mv[0] = p.mx[g0 + 0][qx]; mv[1] = p.mx[g0 + 1][qx]; mv[2] = p.mx[g0 + 2][qx]; }
     if (in_y) { mv[3] = p.my[g0 + 0][qy]; mv[4] = p.my[g0 + 1][qy]; mv[5] = p.my[g0 + 2][qy]; }
@@ -234,61 +248,63 @@ __device__ __forceinline__ void load_memvars(const Params3D &p, int g0, bool in_
 // ring C (plane n only):     sxx (halo box at (-2,0)), syy (halo, (0,0)), sxy (halo, (0,-1)),
 //                            sxz (halo, (0,0)), syz (halo, (0,-1)), vx vy vz (plain boxes)
 // maps: 0 sxx 1 syy 2 sxy 3 sxz 4 syz 5 szz 6 vx 7 vy 8 vz
-struct VelVals { double vx, vy, vz; };                           // in: old values, out: new values
+template <typename T>
+struct VelValsT { T vx, vy, vz; };                           // in: old values, out: new values
+using VelVals = VelValsT<double>;
 
-template <bool PML, bool KUNIT, int CXW>
+template <bool PML, bool KUNIT, int CXW, typename T>
 __device__ __forceinline__ void velocity_point(
-    const Params3D &p, const double *__restrict__ Cx, const int c, const int j, const int k, const int kg,
+    const Params3DT<T> &p, const T *__restrict__ Cx, const int c, const int j, const int k, const int kg,
     const bool do_vx, const bool do_vy, const bool do_vz, const bool edge_ij, const bool ebox_ij, const bool src_ij,
     const bool ux, const bool uy, const bool uz, const bool in_x, const bool in_y, const bool in_z,
-    const long long qx, const long long qy, const long long qz, const double (&mv)[9],
-    const double sxx_c, const double sxx_im, const double syy_c, const double syy_jp,
-    const double sxy_c, const double sxy_jm, const double sxy_ip, const double sxz_c, const double sxz_ip,
-    const double sxz_m, const double syz_c, const double syz_jm, const double syz_m, const double szz_c,
-    const double szz_n, VelVals &v, double &ekin, double &epot)
+    const long long qx, const long long qy, const long long qz, const T (&mv)[9],
+    const T sxx_c, const T sxx_im, const T syy_c, const T syy_jp,
+    const T sxy_c, const T sxy_jm, const T sxy_ip, const T sxz_c, const T sxz_ip,
+    const T sxz_m, const T syz_c, const T syz_jm, const T syz_m, const T szz_c,
+    const T szz_n, VelValsT<T> &v, double &ekin, double &epot)
 {
-    const double odx = p.odx, ody = p.ody, odz = p.odz, dt_r = p.dt_over_rho;
-    double vx = v.vx, vy = v.vy, vz = v.vz;
+    const T odx = p.odx, ody = p.ody, odz = p.odz, dt_r = p.dt_over_rho;
+    T vx = v.vx, vy = v.vy, vz = v.vz;
     if (kg >= 2) {                                           // k2begin
         if (do_vx) {                                         // :976-996
-            double value_dsigmaxx_dx = (sxx_c - sxx_im) * odx;
-            double value_dsigmaxy_dy = (sxy_c - sxy_jm) * ody;
-            double value_dsigmaxz_dz = (sxz_c - sxz_m) * odz;
+            T value_dsigmaxx_dx = (sxx_c - sxx_im) * odx;
+            T value_dsigmaxy_dy = (sxy_c - sxy_jm) * ody;
+            T value_dsigmaxz_dz = (sxz_c - sxz_m) * odz;
             if (PML) {
-                if (ux) value_dsigmaxx_dx = cpml_step<KUNIT>(p.mx[3], qx, in_x, mv[0], Cx[1 * CXW + c], Cx[0 * CXW + c], KUNIT ? 1.0 : Cx[2 * CXW + c], value_dsigmaxx_dx);
-                if (uy) value_dsigmaxy_dy = cpml_step<KUNIT>(p.my[3], qy, in_y, mv[3], p.cy.b[j], p.cy.a[j], KUNIT ? 1.0 : p.cy.K[j], value_dsigmaxy_dy);
-                if (uz) value_dsigmaxz_dz = cpml_step<KUNIT>(p.mz[3], qz, in_z, mv[6], p.cz.b[kg], p.cz.a[kg], KUNIT ? 1.0 : p.cz.K[kg], value_dsigmaxz_dz);
+                if (ux) value_dsigmaxx_dx = cpml_step<KUNIT>(p.mx[3], qx, in_x, mv[0], Cx[1 * CXW + c], Cx[0 * CXW + c], KUNIT ? T(1) : Cx[2 * CXW + c], value_dsigmaxx_dx);
+                if (uy) value_dsigmaxy_dy = cpml_step<KUNIT>(p.my[3], qy, in_y, mv[3], p.cy.b[j], p.cy.a[j], KUNIT ? T(1) : p.cy.K[j], value_dsigmaxy_dy);
+                if (uz) value_dsigmaxz_dz = cpml_step<KUNIT>(p.mz[3], qz, in_z, mv[6], p.cz.b[kg], p.cz.a[kg], KUNIT ? T(1) : p.cz.K[kg], value_dsigmaxz_dz);
             }
             vx = dt_r * (value_dsigmaxx_dx + value_dsigmaxy_dy + value_dsigmaxz_dz) + vx;
         }
         if (do_vy) {                                         // :998-1016
-            double value_dsigmaxy_dx = (sxy_ip - sxy_c) * odx;
-            double value_dsigmayy_dy = (syy_jp - syy_c) * ody;
-            double value_dsigmayz_dz = (syz_c - syz_m) * odz;
+            T value_dsigmaxy_dx = (sxy_ip - sxy_c) * odx;
+            T value_dsigmayy_dy = (syy_jp - syy_c) * ody;
+            T value_dsigmayz_dz = (syz_c - syz_m) * odz;
             if (PML) {
-                if (ux) value_dsigmaxy_dx = cpml_step<KUNIT>(p.mx[4], qx, in_x, mv[1], Cx[4 * CXW + c], Cx[3 * CXW + c], KUNIT ? 1.0 : Cx[5 * CXW + c], value_dsigmaxy_dx);
-                if (uy) value_dsigmayy_dy = cpml_step<KUNIT>(p.my[4], qy, in_y, mv[4], p.cy.b_half[j], p.cy.a_half[j], KUNIT ? 1.0 : p.cy.K_half[j], value_dsigmayy_dy);
-                if (uz) value_dsigmayz_dz = cpml_step<KUNIT>(p.mz[4], qz, in_z, mv[7], p.cz.b[kg], p.cz.a[kg], KUNIT ? 1.0 : p.cz.K[kg], value_dsigmayz_dz);
+                if (ux) value_dsigmaxy_dx = cpml_step<KUNIT>(p.mx[4], qx, in_x, mv[1], Cx[4 * CXW + c], Cx[3 * CXW + c], KUNIT ? T(1) : Cx[5 * CXW + c], value_dsigmaxy_dx);
+                if (uy) value_dsigmayy_dy = cpml_step<KUNIT>(p.my[4], qy, in_y, mv[4], p.cy.b_half[j], p.cy.a_half[j], KUNIT ? T(1) : p.cy.K_half[j], value_dsigmayy_dy);
+                if (uz) value_dsigmayz_dz = cpml_step<KUNIT>(p.mz[4], qz, in_z, mv[7], p.cz.b[kg], p.cz.a[kg], KUNIT ? T(1) : p.cz.K[kg], value_dsigmayz_dz);
             }
             vy = dt_r * (value_dsigmaxy_dx + value_dsigmayy_dy + value_dsigmayz_dz) + vy;
         }
     }
     if (do_vz && kg <= p.nz - 1) {                           // kminus1end, :1031-1052
-        double value_dsigmaxz_dx = (sxz_ip - sxz_c) * odx;
-        double value_dsigmayz_dy = (syz_c - syz_jm) * ody;
-        double value_dsigmazz_dz = (szz_n - szz_c) * odz;
+        T value_dsigmaxz_dx = (sxz_ip - sxz_c) * odx;
+        T value_dsigmayz_dy = (syz_c - syz_jm) * ody;
+        T value_dsigmazz_dz = (szz_n - szz_c) * odz;
         if (PML) {
-            if (ux) value_dsigmaxz_dx = cpml_step<KUNIT>(p.mx[5], qx, in_x, mv[2], Cx[4 * CXW + c], Cx[3 * CXW + c], KUNIT ? 1.0 : Cx[5 * CXW + c], value_dsigmaxz_dx);
-            if (uy) value_dsigmayz_dy = cpml_step<KUNIT>(p.my[5], qy, in_y, mv[5], p.cy.b[j], p.cy.a[j], KUNIT ? 1.0 : p.cy.K[j], value_dsigmayz_dy);
-            if (uz) value_dsigmazz_dz = cpml_step<KUNIT>(p.mz[5], qz, in_z, mv[8], p.cz.b_half[kg], p.cz.a_half[kg], KUNIT ? 1.0 : p.cz.K_half[kg], value_dsigmazz_dz);
+            if (ux) value_dsigmaxz_dx = cpml_step<KUNIT>(p.mx[5], qx, in_x, mv[2], Cx[4 * CXW + c], Cx[3 * CXW + c], KUNIT ? T(1) : Cx[5 * CXW + c], value_dsigmaxz_dx);
+            if (uy) value_dsigmayz_dy = cpml_step<KUNIT>(p.my[5], qy, in_y, mv[5], p.cy.b[j], p.cy.a[j], KUNIT ? T(1) : p.cy.K[j], value_dsigmayz_dy);
+            if (uz) value_dsigmazz_dz = cpml_step<KUNIT>(p.mz[5], qz, in_z, mv[8], p.cz.b_half[kg], p.cz.a_half[kg], KUNIT ? T(1) : p.cz.K_half[kg], value_dsigmazz_dz);
         }
         vz = dt_r * (value_dsigmaxz_dx + value_dsigmayz_dy + value_dsigmazz_dz) + vz;
     }
 
     // source, :1080-1081 (after the update of step it, before Dirichlet; quirk B10)
     if (src_ij && k == p.ksrc) {
-        vx = vx + p.src_x[p.it - 1];
-        vy = vy + p.src_y[p.it - 1];
+        vx = vx + (T)p.src_x[p.it - 1];
+        vy = vy + (T)p.src_y[p.it - 1];
     }
     // Dirichlet on the six faces, :1087-1121
     if (edge_ij || kg == 1 || kg == p.nz) { vx = 0.0; vy = 0.0; vz = 0.0; }
@@ -299,19 +315,22 @@ __device__ __forceinline__ void velocity_point(
     // multiply-adds (half the FP64 instructions); it agrees with the oracle to ~1e-14.
     if (ebox_ij && kg >= p.npml + 1 && kg <= p.nz - p.npml) {
         const double lam = p.lambda, c2lm = p.c2lm, inv_den = p.inv_den, inv_mu = p.inv_mu;
-        ekin = __fma_rn(p.half_rho, __fma_rn(vz, vz, __fma_rn(vy, vy, vx * vx)), ekin);
-        const double epsilon_xx = __fma_rn(-lam, szz_c, __fma_rn(-lam, syy_c, c2lm * sxx_c)) * inv_den;
-        const double epsilon_yy = __fma_rn(-lam, szz_c, __fma_rn(-lam, sxx_c, c2lm * syy_c)) * inv_den;
+        // (accumulated in double in the single-precision build too: the conversions are no-ops for T = double)
+        const double dvx = vx, dvy = vy, dvz = vz;
+        const double esxx = sxx_c, esyy = syy_c, eszz = szz_c, esxy = sxy_c, esxz = sxz_c, esyz = syz_c;
+        ekin = __fma_rn(p.half_rho, __fma_rn(dvz, dvz, __fma_rn(dvy, dvy, dvx * dvx)), ekin);
+        const double epsilon_xx = __fma_rn(-lam, eszz, __fma_rn(-lam, esyy, c2lm * esxx)) * inv_den;
+        const double epsilon_yy = __fma_rn(-lam, eszz, __fma_rn(-lam, esxx, c2lm * esyy)) * inv_den;
         // quirk B2 (:1169-1172): the reference adds epsilon_yy*sigmayy twice and never
         // epsilon_zz*sigmazz
         double third;
-        if (p.energy_bug_compat) third = epsilon_yy * syy_c;
-        else third = __fma_rn(-lam, syy_c, __fma_rn(-lam, sxx_c, c2lm * szz_c)) * inv_den * szz_c;
+        if (p.energy_bug_compat) third = epsilon_yy * esyy;
+        else third = __fma_rn(-lam, esyy, __fma_rn(-lam, esxx, c2lm * eszz)) * inv_den * eszz;
         // 2 * epsilon_ij * sigma_ij = sigma_ij^2 / mu
-        double acc = __fma_rn(epsilon_xx, sxx_c, __fma_rn(epsilon_yy, syy_c, third));
-        acc = __fma_rn(sxy_c * inv_mu, sxy_c, acc);
-        acc = __fma_rn(sxz_c * inv_mu, sxz_c, acc);
-        acc = __fma_rn(syz_c * inv_mu, syz_c, acc);
+        double acc = __fma_rn(epsilon_xx, esxx, __fma_rn(epsilon_yy, esyy, third));
+        acc = __fma_rn(esxy * inv_mu, esxy, acc);
+        acc = __fma_rn(esxz * inv_mu, esxz, acc);
+        acc = __fma_rn(esyz * inv_mu, esyz, acc);
         epot = __fma_rn(0.5, acc, epot);
     }
 }

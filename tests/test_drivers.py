@@ -187,7 +187,7 @@ def test_cpp_driver_ngpu_equals_single_gpu(driver_exe, tmp_path, program, ngpu, 
     if program == "3d_iso":
         common += ["ydeb=300", "yfin=100"]
     else:
-        common += ["NPROC=4", "xrec1=200", "yrec1=200", "xrec2=160", "yrec2=240", "xrec3=200", "yrec3=240"]
+        common += ["NPROC=4", "xrec1=120", "yrec1=100", "xrec2=100", "yrec2=120", "xrec3=120", "yrec3=120", "NSTEP=260"]
     outs = []
     for extra, sub in (([], "one"), ([f"NGPU={ngpu}", f"SAME_DEVICE={same}"], "multi")):
         d = tmp_path / sub
