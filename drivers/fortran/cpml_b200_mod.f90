@@ -44,6 +44,7 @@ module cpml_b200
     integer(c_int32_t) :: emulate_nproc
     integer(c_int32_t) :: compute_energy
     integer(c_int32_t) :: sigmazz_isotropic   ! 3-D viscoelastic: 0 = the reference's sigmazz memory term (quirk B14) ; 1 = isotropic
+    integer(c_int32_t) :: precision           ! 0 = double precision (the reference as shipped) ; 1 = single precision (3D-iso :114-116)
     real(c_double) :: deltax, deltay, deltaz
     real(c_double) :: deltat
     real(c_double) :: lambda, mu, lambdaplustwomu, rho

@@ -107,6 +107,12 @@ typedef struct cpml_config {
                                 analytical viscoelastic solution, tests/test_analytical_visco3d.py).  1 = the
                                 isotropic form (lambda+2/3 mu) sum e1 - 2 mu sum(e11+e22): NOT the reference,
                                 for users who want the physics (1.6 % misfit)                              */
+    int32_t precision;       /* 0 = double precision, the reference as shipped.  1 = single precision, the build the
+                                reference endorses as "significantly faster" (3D-iso :114-116: declare everything
+                                `real`): wavefields, memory variables, profiles and update constants in FP32 (the
+                                energy is still summed in double); 3-D isotropic solver on one GPU only.  Getters keep
+                                returning double arrays.  Not bit-comparable with the double-precision run: see
+                                DESIGN.md for the measured differences                                          */
     double deltax, deltay, deltaz;   /* DELTAX, DELTAY, DELTAZ                           */
     double deltat;                   /* DELTAT                                           */
     /* homogeneous medium of the 3-D program (:139-144); the 2-D programs take arrays

@@ -158,19 +158,23 @@ def run_2d_np(*, order, nx, ny, deltax, deltay, deltat, nstep, npoints_pml, isou
 
 def run_3d_iso_np(*, nx, ny, nz, deltax, deltay, deltaz, deltat, lam, mu, lambdaplustwomu, rho,
                   nstep, npoints_pml, isource, jsource, prof_x, prof_y, prof_z,
-                  force_x, force_y, ix_rec, iy_rec, energy_bug_compat=True):
+                  force_x, force_y, ix_rec, iy_rec, energy_bug_compat=True, dtype=np.float64):
+    """dtype=np.float32: the single-precision build the reference endorses (3D-iso :114-116) -- wavefields, memory
+    variables, profiles and update constants in IEEE single (numpy rounds every operation, no FMA); the update constants
+    are rounded once from their double values and the energy is summed in double, like the CUDA kernels do."""
+    T = dtype
     NX, NY, NZ, P = nx, ny, nz, npoints_pml
     sh = (NX + 2, NY + 2, NZ + 2)
-    vx, vy, vz, sxx, syy, szz, sxy, sxz, syz = (np.zeros(sh) for _ in range(9))
-    mem = {n: np.zeros(sh) for n in (
+    vx, vy, vz, sxx, syy, szz, sxy, sxz, syz = (np.zeros(sh, dtype=T) for _ in range(9))
+    mem = {n: np.zeros(sh, dtype=T) for n in (
         "dvx_dx", "dvx_dy", "dvx_dz", "dvy_dx", "dvy_dy", "dvy_dz", "dvz_dx", "dvz_dy", "dvz_dz",
         "dsxx_dx", "dsyy_dy", "dszz_dz", "dsxy_dx", "dsxy_dy", "dsxz_dx", "dsxz_dz",
         "dsyz_dy", "dsyz_dz")}
-    X = {k: _p1(prof_x[k], NX)[:, None, None] for k in prof_x}
-    Y = {k: _p1(prof_y[k], NY)[None, :, None] for k in prof_y}
-    Z = {k: _p1(prof_z[k], NZ)[None, None, :] for k in prof_z}
-    odx, ody, odz = 1.0 / deltax, 1.0 / deltay, 1.0 / deltaz
-    DT_l, DT_m, DT_l2m, DT_r = deltat * lam, deltat * mu, deltat * lambdaplustwomu, deltat / rho
+    X = {k: _p1(prof_x[k], NX).astype(T)[:, None, None] for k in prof_x}
+    Y = {k: _p1(prof_y[k], NY).astype(T)[None, :, None] for k in prof_y}
+    Z = {k: _p1(prof_z[k], NZ).astype(T)[None, None, :] for k in prof_z}
+    odx, ody, odz = T(1.0 / deltax), T(1.0 / deltay), T(1.0 / deltaz)
+    DT_l, DT_m, DT_l2m, DT_r = T(deltat * lam), T(deltat * mu), T(deltat * lambdaplustwomu), T(deltat / rho)
     nrec = len(ix_rec)
     sisvx, sisvy = np.zeros((nrec, nstep)), np.zeros((nrec, nstep))
     energy = np.zeros(nstep)
@@ -275,8 +279,8 @@ def run_3d_iso_np(*, nx, ny, nz, deltax, deltay, deltaz, deltat, lam, mu, lambda
         vz[s()] = DT_r * (d1 + d2 + d3) + vz[s()]
 
         # source at (ISOURCE, JSOURCE, NZ/2)
-        vx[isource, jsource, ks] = vx[isource, jsource, ks] + force_x[it - 1] * deltat / rho
-        vy[isource, jsource, ks] = vy[isource, jsource, ks] + force_y[it - 1] * deltat / rho
+        vx[isource, jsource, ks] = vx[isource, jsource, ks] + T(force_x[it - 1] * deltat / rho)
+        vy[isource, jsource, ks] = vy[isource, jsource, ks] + T(force_y[it - 1] * deltat / rho)
 
         # Dirichlet on the six faces
         for f in (vx, vy, vz):
@@ -291,15 +295,17 @@ def run_3d_iso_np(*, nx, ny, nz, deltax, deltay, deltaz, deltat, lam, mu, lambda
             sisvx[r, it - 1] = vx[ix_rec[r], iy_rec[r], ks]
             sisvy[r, it - 1] = vy[ix_rec[r], iy_rec[r], ks]
 
-        kin = np.sum(0.5 * rho * (vx[EB] ** 2 + vy[EB] ** 2 + vz[EB] ** 2))
+        evx, evy, evz = (f[EB].astype(np.float64) for f in (vx, vy, vz))
+        esxx, esyy, eszz, esxy, esxz, esyz = (f[EB].astype(np.float64) for f in (sxx, syy, szz, sxy, sxz, syz))
+        kin = np.sum(0.5 * rho * (evx ** 2 + evy ** 2 + evz ** 2))
         den = 2.0 * mu * (3.0 * lam + 2.0 * mu)
-        exx = (2.0 * (lam + mu) * sxx[EB] - lam * syy[EB] - lam * szz[EB]) / den
-        eyy = (2.0 * (lam + mu) * syy[EB] - lam * sxx[EB] - lam * szz[EB]) / den
-        ezz = (2.0 * (lam + mu) * szz[EB] - lam * sxx[EB] - lam * syy[EB]) / den
-        exy, exz, eyz = sxy[EB] / (2.0 * mu), sxz[EB] / (2.0 * mu), syz[EB] / (2.0 * mu)
-        third = eyy * syy[EB] if energy_bug_compat else ezz * szz[EB]
-        pot = np.sum(0.5 * (exx * sxx[EB] + eyy * syy[EB] + third + 2.0 * exy * sxy[EB]
-                            + 2.0 * exz * sxz[EB] + 2.0 * eyz * syz[EB]))
+        exx = (2.0 * (lam + mu) * esxx - lam * esyy - lam * eszz) / den
+        eyy = (2.0 * (lam + mu) * esyy - lam * esxx - lam * eszz) / den
+        ezz = (2.0 * (lam + mu) * eszz - lam * esxx - lam * esyy) / den
+        exy, exz, eyz = esxy / (2.0 * mu), esxz / (2.0 * mu), esyz / (2.0 * mu)
+        third = eyy * esyy if energy_bug_compat else ezz * eszz
+        pot = np.sum(0.5 * (exx * esxx + eyy * esyy + third + 2.0 * exy * esxy
+                            + 2.0 * exz * esxz + 2.0 * eyz * esyz))
         energy[it - 1] = kin + pot
 
     inner = (slice(1, NX + 1), slice(1, NY + 1), slice(1, NZ + 1))

@@ -5,12 +5,12 @@
 N=$1; steps=${2:-60}
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/topo$N.txt 2>&1
-( time timeout 1500 python -m pytest tests/test_gpu_multi.py tests/test_drivers.py -m gpu -q -rs ) > gpurun_out/test_multi$N.log 2>&1
+( time timeout 1500 python -m pytest tests/test_gpu_multi.py tests/test_drivers.py -m gpu -q -rs $PYTEST_EXTRA ) > gpurun_out/test_multi$N.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/test_multi$N.log
 tail -8 gpurun_out/test_multi$N.log
 : > gpurun_out/bench_n$N.jsonl
 port=29510
-for wl in cfg3 cfg4 cfg5 cfg5d "cfg3 --halo sendrecv" "cfg5 --halo sendrecv"; do
+for wl in ${WORKLOADS:-cfg3 cfg4 cfg5 cfg5d "cfg3 --halo sendrecv" "cfg5 --halo sendrecv"}; do
   port=$((port+1))
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port \
      bench.py --gpus $N --steps $steps --warmup 5 --workload $wl 2>> gpurun_out/bench_n$N.err | tail -1 >> gpurun_out/bench_n$N.jsonl

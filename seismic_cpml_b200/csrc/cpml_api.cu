@@ -60,6 +60,9 @@ struct cpml_handle {
 
     // TMA path (3-D): descriptors of the two kernels' plane tiles, work decomposition
     bool use_tma = false;          // TMA-staged kernels (either family)
+    bool f32 = false;              // cfg.precision == 1: single-precision wavefields (3-D isotropic, one GPU)
+    float *dprof_f[3][6] = {};     // single-precision copies of the profiles
+    double *d_scratch = nullptr;   // one padded plane in double: single-precision planes are converted here for the getters
     bool use_ws = false;           // ... with a producer warp and in-kernel slab ordering (kernels_3d_ws.cu, the default)
     unsigned int *d_bcount = nullptr;   // [2] boundary-item counters of the in-kernel slab ordering
     TmaMaps maps_stress{}, maps_velocity{};
@@ -191,6 +194,10 @@ static int32_t create_impl(cpml_handle *h)
     h->visco2d = c.rheology == 1 && c.ndim == 2;
     if (h->visco && c.order != 4) FAIL(CPML_EINVAL, "the 3-D viscoelastic solver is fourth order (order = 4)");
     if (c.ndim == 3 && !h->visco && c.order != 2) FAIL(CPML_EINVAL, "3-D isotropic solver is second order (order must be 2)");
+    if (c.precision != 0 && c.precision != 1) FAIL(CPML_EINVAL, "precision must be 0 (double) or 1 (single)");
+    h->f32 = c.precision == 1;
+    if (h->f32 && (c.ndim != 3 || c.rheology != 0)) FAIL(CPML_EINVAL, "single precision is implemented for the 3-D isotropic solver");
+    if (h->f32 && c.nslabs != 1) FAIL(CPML_ETOPOLOGY, "single precision runs on one GPU (nslabs = 1)");
     if (c.emulate_nproc < 0) FAIL(CPML_EINVAL, "emulate_nproc must be >= 0");
     if (c.emulate_nproc > 1) {
         if (!h->visco) FAIL(CPML_EINVAL, "emulate_nproc applies to the viscoelastic solver only (the second-order exchange is complete)");
@@ -415,6 +422,8 @@ extern "C" int32_t cpml_destroy(cpml_handle *h)
     cudaFree(h->arena);
     cudaFree(h->d_timeout);
     cudaFree(h->d_bcount);
+    cudaFree(h->d_scratch);
+    for (auto &ax : h->dprof_f) for (auto &p : ax) cudaFree(p);
     for (auto &p : h->mat) cudaFree(p);
     for (auto &ax : h->dprof) for (auto &p : ax) cudaFree(p);
     for (auto &p : h->mx) cudaFree(p);
@@ -510,6 +519,12 @@ extern "C" int32_t cpml_set_profiles(cpml_handle *h, int32_t axis, const double 
         if (!h->dprof[axis][6 + q]) CK(cudaMalloc(&h->dprof[axis][6 + q], (size_t)n * sizeof(double)));
         CK(cudaMemcpy(h->dprof[axis][6 + q], r.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
     }
+    if (h->f32)
+        for (int q = 0; q < 6; q++) {
+            std::vector<float> pf(src[q], src[q] + n);
+            if (!h->dprof_f[axis][q]) CK(cudaMalloc(&h->dprof_f[axis][q], (size_t)n * sizeof(float)));
+            CK(cudaMemcpy(h->dprof_f[axis][q], pf.data(), (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+        }
     h->shell[axis] = find_shell(h->hprof[axis], n);
     h->have_prof[axis] = true;
     return CPML_OK;
@@ -665,15 +680,17 @@ static int32_t encode_plane_map(cpml_handle *h, EncodeTiledFn enc, CUtensorMap *
     const cpml_config &c = h->cfg;
     // tensor = the field as (x, y, plane) with the grid's own extents: whatever a box covers
     // beyond NX / NY (or before index 1) is zero-filled by the TMA unit, never read
+    const size_t es = h->f32 ? sizeof(float) : sizeof(double);
+    void *base = h->f32 ? (void *)((float *)h->field_alloc[field] + h->origin) : (void *)h->f0[field];
     const cuuint64_t dims[3] = {(cuuint64_t)c.nx, (cuuint64_t)c.ny, (cuuint64_t)(h->nzl + 2)};
-    const cuuint64_t strides[2] = {(cuuint64_t)h->pitch * sizeof(double), (cuuint64_t)h->plane * sizeof(double)};
+    const cuuint64_t strides[2] = {(cuuint64_t)h->pitch * es, (cuuint64_t)h->plane * es};
     const cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     // L2 promotion of the tensor loads: 128 B by default; CPML_L2PROMO = 0 none, 1 64 B, 2 128 B, 3 256 B (A/B runs)
     static const CUtensorMapL2promotion promo[4] = {CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
                                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B};
     const int pm = std::max(0, std::min(3, env_int("CPML_L2PROMO", 2)));
-    const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)h->f0[field], dims, strides, box, estr,
+    const CUresult r = enc(out, h->f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo[pm],
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -708,7 +725,7 @@ static int32_t build_tile(cpml_handle *h, EncodeTiledFn enc, bool stress, Tile3D
         // SM sub-partition: 128 registers); both kernels use the same tile unless CPML_TY_STRESS says otherwise
         t.ty = env_int("CPML_TY", t.tx == 128 ? 7 : 8);
         if (stress) t.ty = env_int("CPML_TY_STRESS", t.ty);
-        if (!ws_tile_supported(t.tx, t.ty)) FAIL(CPML_EINVAL, "unsupported CPML_TX x CPML_TY tile for the producer-warp kernels");
+        if (!ws_tile_supported(t.tx, t.ty, h->f32)) FAIL(CPML_EINVAL, "unsupported CPML_TX x CPML_TY tile for the producer-warp kernels");
     } else {
         t.ty = env_int("CPML_TY", 8);
         if (stress) t.ty = env_int("CPML_TY_STRESS", (t.tx == 104 && t.ty == 8) ? 7 : t.ty);
@@ -717,13 +734,13 @@ static int32_t build_tile(cpml_handle *h, EncodeTiledFn enc, bool stress, Tile3D
     t.stages = std::max(1, std::min(h->use_ws ? 4 : 7, env_int("CPML_STAGES", 2)));
     t.minb = std::max(1, std::min(4, env_int("CPML_MINB", t.tx == 64 ? 2 : 1)));
     if (t.ty == 7 || t.ty == 6) t.minb = 1;
-    t.xm_bytes = h->shell[0].size() > 0 ? round_up(t.ty * h->sxp * 8, 128) : 0;
+    t.xm_bytes = h->shell[0].size() > 0 ? round_up(t.ty * h->sxp * (h->f32 ? 4 : 8), 128) : 0;
     t.ntx = (c.nx + t.tx - 1) / t.tx;
     t.nty = (c.ny + t.ty - 1) / t.ty;
 
     // descriptors: stress 0 vx 1 vy 2 vz 3 sxx 4 syy 5 szz 6 sxy 7 sxz 8 syz (three halo boxes);
     // velocity 0 sxx 1 syy 2 sxy 3 sxz 4 syz 5 szz 6 vx 7 vy 8 vz (five halo boxes)
-    const int hx = t.tx + 2, hy = t.ty + 1;
+    const int hx = t.tx + (h->f32 ? 4 : 2), hy = t.ty + 1;      // halo boxes start 16 bytes before the tile
     const int stress_field[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};
     const int velocity_field[9] = {3, 4, 6, 7, 8, 5, 0, 1, 2};
     const int nhalo = stress ? 3 : 5;
@@ -742,7 +759,7 @@ static int32_t build_tile(cpml_handle *h, EncodeTiledFn enc, bool stress, Tile3D
                 if (K != 1.0) p.kunit = 0;
     int occ = 0;
     while (true) {
-        const cudaError_t e = h->use_ws ? ws_occupancy(p, t, stress, &occ) : tma_occupancy(p, t, stress, &occ);
+        const cudaError_t e = h->use_ws ? ws_occupancy(p, t, stress, &occ, h->f32) : tma_occupancy(p, t, stress, &occ);
         if (e == cudaSuccess && occ >= 1) break;
         cudaGetLastError();
         if (t.stages <= 1) FAIL(CPML_ECUDA, "TMA kernels do not fit on this device");
@@ -958,6 +975,8 @@ static int32_t finalize(cpml_handle *h)
         if (h->use_ws && (h->field_doubles >= (1ull << 32) || h->mx_doubles >= (1ull << 32) || h->my_doubles >= (1ull << 32) ||
                           h->mz_doubles >= (1ull << 32)))
             h->use_ws = false;      // the producer-warp kernels index with 32-bit element offsets (fields of < 2^32 points)
+        if (h->f32 && !h->use_ws) FAIL(CPML_EINVAL, "single precision needs the producer-warp kernels (unset CPML_KERNEL)");
+        if (h->f32) CK(cudaMalloc(&h->d_scratch, (size_t)h->plane * sizeof(double)));
         if (h->use_tma) { const int32_t rc = setup_tma(h); if (rc) return rc; }
         else build_regions(h);
         CK(cudaMalloc(&h->d_partials, 2 * (size_t)std::max(1, h->nblocks) * sizeof(double)));
@@ -1021,6 +1040,35 @@ static Params3D make_p3(cpml_handle *h, int it)
         p.peer_lo[q] = h->peer_on[0] ? h->peer_arena[0] + (size_t)lo_f[q] * h->field_doubles + h->origin + (long long)(h->nzl + 1) * h->plane : nullptr;
         p.peer_hi[q] = h->peer_on[1] ? h->peer_arena[1] + (size_t)hi_f[q] * h->field_doubles + h->origin : nullptr;
     }
+    return p;
+}
+
+// The same block for the single-precision kernels: update constants rounded ONCE from their double values, fields
+// and memory variables viewed as float arrays (same element counts and offsets), profiles from the float copies.
+static Params3DF make_p3f(cpml_handle *h, int it)
+{
+    const Params3D d = make_p3(h, it);
+    Params3DF p{};
+    p.nx = d.nx; p.ny = d.ny; p.nzl = d.nzl; p.nz = d.nz; p.koff = d.koff; p.pitch = d.pitch; p.plane = d.plane;
+    float **fld[9] = {&p.vx, &p.vy, &p.vz, &p.sxx, &p.syy, &p.szz, &p.sxy, &p.sxz, &p.syz};
+    for (int f = 0; f < 9; f++) *fld[f] = (float *)h->field_alloc[f] + h->origin;
+    p.xlo = d.xlo; p.xhi = d.xhi; p.sxp = d.sxp; p.ylo = d.ylo; p.yhi = d.yhi; p.sy = d.sy;
+    p.zlo = d.zlo; p.zhi = d.zhi; p.zbase = d.zbase;
+    for (int m = 0; m < 6; m++) { p.mx[m] = (float *)h->mx[m]; p.my[m] = (float *)h->my[m]; p.mz[m] = (float *)h->mz[m]; }
+    AxisCoefT<float> *ax[3] = {&p.cx, &p.cy, &p.cz};
+    for (int a = 0; a < 3; a++) {
+        ax[a]->a = h->dprof_f[a][0] - 1; ax[a]->b = h->dprof_f[a][1] - 1; ax[a]->K = h->dprof_f[a][2] - 1;
+        ax[a]->a_half = h->dprof_f[a][3] - 1; ax[a]->b_half = h->dprof_f[a][4] - 1; ax[a]->K_half = h->dprof_f[a][5] - 1;
+        ax[a]->rK = nullptr; ax[a]->rK_half = nullptr;
+    }
+    p.odx = (float)d.odx; p.ody = (float)d.ody; p.odz = (float)d.odz;
+    p.dt_lambda = (float)d.dt_lambda; p.dt_mu = (float)d.dt_mu; p.dt_lambdaplus2mu = (float)d.dt_lambdaplus2mu;
+    p.dt_over_rho = (float)d.dt_over_rho;
+    p.it = d.it; p.isrc = d.isrc; p.jsrc = d.jsrc; p.ksrc = d.ksrc; p.src_x = d.src_x; p.src_y = d.src_y;
+    p.npml = d.npml; p.energy_bug_compat = d.energy_bug_compat;
+    p.rho = d.rho; p.lambda = d.lambda; p.mu = d.mu; p.inv_den = d.inv_den; p.inv_2mu = d.inv_2mu;
+    p.inv_mu = d.inv_mu; p.c2lm = d.c2lm; p.half_rho = d.half_rho;
+    p.partials = d.partials; p.nblocks = d.nblocks; p.kunit = d.kunit;
     return p;
 }
 
@@ -1227,7 +1275,12 @@ static int32_t half_step(cpml_handle *h, int32_t it, int phase)
         h->n_launches += phase == 0 ? visco_stress_launches() : 1;
     } else if (h->cfg.ndim == 3) {
         const Params3D p = make_p3(h, it);
-        if (h->use_ws) {
+        if (h->f32) {
+            const Params3DF pf = make_p3f(h, it);
+            if (phase == 0) CK(launch_stress3d_ws(pf, h->maps_stress, h->tile_stress, ss, h->stream));
+            else CK(launch_velocity3d_ws(pf, h->maps_velocity, h->tile, ss, h->stream));
+            h->n_launches++;
+        } else if (h->use_ws) {
             if (phase == 0) CK(launch_stress3d_ws(p, h->maps_stress, h->tile_stress, ss, h->stream));
             else CK(launch_velocity3d_ws(p, h->maps_velocity, h->tile, ss, h->stream));
             h->n_launches++;
@@ -1298,6 +1351,12 @@ extern "C" int32_t cpml_step_finish(cpml_handle *h, int32_t it)
     }
     p.sisvx = h->d_sisvx; p.sisvy = h->d_sisvy;
     p.vz = c.ndim == 3 ? h->f0[2] : nullptr; p.sisvz = h->d_sisvz;
+    if (h->f32) {       // the float views start at the same ELEMENT offset of each field slot
+        p.f32 = 1;
+        p.vx = (const double *)((float *)h->field_alloc[0] + h->origin);
+        p.vy = (const double *)((float *)h->field_alloc[1] + h->origin);
+        p.vz = (const double *)((float *)h->field_alloc[2] + h->origin);
+    }
     if (h->visco2d) {
         const Params2D p2 = make_p2(h, it);
         if (c.compute_energy) { launch_venergy2d(p2, h->grid, h->stream); h->n_launches++; }   // COMPUTE_ENERGY, :1037
@@ -1347,6 +1406,7 @@ extern "C" int32_t cpml_halo_plane(cpml_handle *h, int32_t field, int32_t klocal
 {
     if (!h) return CPML_EINVAL;
     if (h->cfg.ndim != 3) FAIL(CPML_EINVAL, "halo planes exist only in 3-D");
+    if (h->f32) FAIL(CPML_EINVAL, "single precision runs on one GPU: no halo planes");
     const int hz = h->visco ? 2 : 1;
     if (field < 0 || field >= 9 || klocal < 1 - hz || klocal > h->nzl + hz || !device_ptr || !nbytes) FAIL(CPML_EINVAL, "bad halo plane request");
     if (h->visco) {
@@ -1538,6 +1598,15 @@ extern "C" int32_t cpml_get_energy(cpml_handle *h, double *total, double *kineti
     return CPML_OK;
 }
 
+// Device pointer to plane `off` (element offset from element (1,1,0)) of a field as DOUBLE values: the field itself, or --
+// single precision -- the scratch plane the values were just converted into (on the handle's stream).
+static const double *plane_as_double(cpml_handle *h, int field, long long off)
+{
+    if (!h->f32) return h->f0[field] + off;
+    launch_f2d((const float *)h->field_alloc[field] + h->origin + off, h->d_scratch, (long long)h->pitch * h->cfg.ny, h->stream);
+    return h->d_scratch;
+}
+
 extern "C" int32_t cpml_get_plane(cpml_handle *h, int32_t field, int32_t kglobal, double *out)
 {
     if (!h || !out) return CPML_EINVAL;
@@ -1550,7 +1619,7 @@ extern "C" int32_t cpml_get_plane(cpml_handle *h, int32_t field, int32_t kglobal
         if (kl < 1 || kl > h->nzl) FAIL(CPML_EINVAL, "this slab does not hold that plane");
         off = (long long)kl * h->plane;
     }
-    CK(cudaMemcpy2DAsync(out, (size_t)c.nx * sizeof(double), h->f0[field] + off, (size_t)h->pitch * sizeof(double),
+    CK(cudaMemcpy2DAsync(out, (size_t)c.nx * sizeof(double), plane_as_double(h, field, off), (size_t)h->pitch * sizeof(double),
                          (size_t)c.nx * sizeof(double), c.ny, cudaMemcpyDeviceToHost, h->stream));
     { const int32_t rc_sync = sync_checked(h); if (rc_sync) return rc_sync; }
     return CPML_OK;
@@ -1588,7 +1657,7 @@ extern "C" int32_t cpml_snapshot_begin(cpml_handle *h, int32_t slot, int32_t fie
         CK(cudaEventRecord(h->snap_done[slot], h->snap_stream));
     }
     CK(cudaStreamWaitEvent(h->stream, h->snap_done[slot], 0));          // the previous transfer out of snap_dev is over
-    CK(cudaMemcpy2DAsync(h->snap_dev[slot], (size_t)c.nx * sizeof(double), h->f0[field] + off, (size_t)h->pitch * sizeof(double),
+    CK(cudaMemcpy2DAsync(h->snap_dev[slot], (size_t)c.nx * sizeof(double), plane_as_double(h, field, off), (size_t)h->pitch * sizeof(double),
                          (size_t)c.nx * sizeof(double), c.ny, cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaEventRecord(h->snap_ready[slot], h->stream));
     CK(cudaStreamWaitEvent(h->snap_stream, h->snap_ready[slot], 0));
@@ -1626,6 +1695,14 @@ extern "C" int32_t cpml_get_field(cpml_handle *h, int32_t field, double *out)
         { const int32_t rc_sync = sync_checked(h); if (rc_sync) return rc_sync; }
         return CPML_OK;
     }
+    if (h->f32) {     // plane by plane through the conversion scratch
+        for (int k = 1; k <= h->nzl; k++)
+            CK(cudaMemcpy2DAsync(out + (size_t)(k - 1) * c.nx * c.ny, (size_t)c.nx * sizeof(double),
+                                 plane_as_double(h, field, (long long)k * h->plane), (size_t)h->pitch * sizeof(double),
+                                 (size_t)c.nx * sizeof(double), c.ny, cudaMemcpyDeviceToHost, h->stream));
+        { const int32_t rc_sync = sync_checked(h); if (rc_sync) return rc_sync; }
+        return CPML_OK;
+    }
     // rows of all owned planes are equally spaced (plane = pitch * ny): one 2-D copy
     CK(cudaMemcpy2DAsync(out, (size_t)c.nx * sizeof(double), h->f0[field] + h->plane, (size_t)h->pitch * sizeof(double),
                          (size_t)c.nx * sizeof(double), (size_t)c.ny * h->nzl, cudaMemcpyDeviceToHost, h->stream));
@@ -1639,7 +1716,10 @@ extern "C" int32_t cpml_get_maxnorm(cpml_handle *h, double *out)
     const cpml_config &c = h->cfg;
     CK(cudaSetDevice(h->device));
     CK(cudaMemsetAsync(h->d_maxbits, 0, sizeof(unsigned long long), h->stream));
-    if (c.ndim == 3)
+    if (h->f32)
+        launch_maxnorm_f((const float *)h->field_alloc[0] + h->origin + h->plane, (const float *)h->field_alloc[1] + h->origin + h->plane,
+                         (const float *)h->field_alloc[2] + h->origin + h->plane, h->plane * h->nzl, h->d_maxbits, h->stream);
+    else if (c.ndim == 3)
         launch_maxnorm(h->f0[0] + h->plane, h->f0[1] + h->plane, h->f0[2] + h->plane, h->plane * h->nzl, h->d_maxbits, h->stream);
     else
         launch_maxnorm(h->field_alloc[0], h->field_alloc[1], nullptr, (long long)h->field_doubles, h->d_maxbits, h->stream);
@@ -1715,7 +1795,8 @@ extern "C" int32_t cpml_algorithmic_bytes(cpml_handle *h, double *bytes_stress, 
         // already holds lambda and mu: 18 words per point-update)
         wv = 8.0 * N + 2.0 * (px * (nz[0][0] + nz[0][1]) + py * (nz[1][0] + nz[1][1]));
     }
-    if (bytes_stress) *bytes_stress = 8.0 * ws;
-    if (bytes_velocity) *bytes_velocity = 8.0 * wv;
+    const double es = h->f32 ? 4.0 : 8.0;       // bytes per word
+    if (bytes_stress) *bytes_stress = es * ws;
+    if (bytes_velocity) *bytes_velocity = es * wv;
     return CPML_OK;
 }

@@ -235,6 +235,7 @@ struct Post3D {
     int pitch;
     long long plane;
     int krec;                      // local k of the receiver plane, 0: not here
+    int f32;                       // 1: vx, vy, vz point to single-precision fields
     double *sisvx, *sisvy, *sisvz;
 };
 
@@ -320,10 +321,14 @@ bool tma_tile_supported(int tx, int ty);
 cudaError_t tma_occupancy(const Params3D &p, const Tile3D &t, bool stress, int *occ);
 cudaError_t launch_stress3d_tma(const Params3D &p, const TmaMaps &tm, const Tile3D &t, cudaStream_t s);
 cudaError_t launch_velocity3d_tma(const Params3D &p, const TmaMaps &tm, const Tile3D &t, cudaStream_t s);
-bool ws_tile_supported(int tx, int ty);
-cudaError_t ws_occupancy(const Params3D &p, const Tile3D &t, bool stress, int *occ);
+bool ws_tile_supported(int tx, int ty, bool f32);
+cudaError_t ws_occupancy(const Params3D &p, const Tile3D &t, bool stress, int *occ, bool f32);
 cudaError_t launch_stress3d_ws(const Params3D &p, const TmaMaps &tm, const Tile3D &t, const SlabSync &ss, cudaStream_t s);
 cudaError_t launch_velocity3d_ws(const Params3D &p, const TmaMaps &tm, const Tile3D &t, const SlabSync &ss, cudaStream_t s);
+cudaError_t launch_stress3d_ws(const Params3DF &p, const TmaMaps &tm, const Tile3D &t, const SlabSync &ss, cudaStream_t s);
+cudaError_t launch_velocity3d_ws(const Params3DF &p, const TmaMaps &tm, const Tile3D &t, const SlabSync &ss, cudaStream_t s);
+void launch_f2d(const float *src, double *dst, long long n, cudaStream_t s);
+void launch_maxnorm_f(const float *vx, const float *vy, const float *vz, long long n, unsigned long long *out_bits, cudaStream_t s);
 void launch_signal(unsigned long long *flag_lo, unsigned long long *flag_hi, unsigned long long value, cudaStream_t s);
 void launch_wait(const unsigned long long *flag_a, const unsigned long long *flag_b, unsigned long long value,
                  unsigned int *timeout_flag, cudaStream_t s);

@@ -376,11 +376,14 @@ __global__ void __launch_bounds__(256) k_post3d(const __grid_constant__ Post3D p
     if (p.krec > 0) {
         for (int r = threadIdx.x; r < p.nrec; r += 256) {
             const long long q = (long long)p.krec * p.plane + (long long)(p.iy_rec[r] - 1) * p.pitch + (p.ix_rec[r] - 1);
-            p.sisvx[(long long)r * p.nstep + (p.it - 1)] = p.vx[q];
-            p.sisvy[(long long)r * p.nstep + (p.it - 1)] = p.vy[q];
+            // (single-precision fields: the traces are still double, like sisvx(NSTEP,NREC) of a build that only
+            // demotes the wavefields)
+            auto at = [&](const double *f) { return p.f32 ? (double)reinterpret_cast<const float *>(f)[q] : f[q]; };
+            p.sisvx[(long long)r * p.nstep + (p.it - 1)] = at(p.vx);
+            p.sisvy[(long long)r * p.nstep + (p.it - 1)] = at(p.vy);
             // not in the reference (it records Vx and Vy only although its plot script reads Vz files, quirk
             // B7): vz at the same array indices, vz(ix_rec, iy_rec, NZ/2)
-            if (p.vz) p.sisvz[(long long)r * p.nstep + (p.it - 1)] = p.vz[q];
+            if (p.vz) p.sisvz[(long long)r * p.nstep + (p.it - 1)] = at(p.vz);
         }
     }
 }
@@ -403,6 +406,31 @@ __global__ void __launch_bounds__(256) k_maxnorm(const double *vx, const double 
         m = t > m ? t : m;
     }
     if ((threadIdx.x & 31) == 0) atomicMax(out_bits, (unsigned long long)__double_as_longlong(m));
+}
+
+// single-precision fields: the same maximum, evaluated in double
+__global__ void __launch_bounds__(256) k_maxnorm_f(const float *vx, const float *vy, const float *vz,
+                                                    long long n, unsigned long long *out_bits)
+{
+    double m = 0.0;
+    for (long long q = (long long)blockIdx.x * 256 + threadIdx.x; q < n; q += (long long)gridDim.x * 256) {
+        const double a = vx[q], b = vy[q], c = vz ? vz[q] : 0.0;
+        const double v = sqrt(a * a + b * b + c * c);
+        m = v > m ? v : m;
+        if (v != v) m = __longlong_as_double(0x7ff0000000000000LL);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double t = __shfl_down_sync(0xffffffffu, m, o);
+        m = t > m ? t : m;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, (unsigned long long)__double_as_longlong(m));
+}
+
+// single-precision plane -> double (the getters hand out double arrays in every precision)
+__global__ void __launch_bounds__(256) k_f2d(const float *src, double *dst, long long n)
+{
+    for (long long q = (long long)blockIdx.x * 256 + threadIdx.x; q < n; q += (long long)gridDim.x * 256) dst[q] = (double)src[q];
 }
 
 // ---- launch dispatch ---------------------------------------------------------------
@@ -455,6 +483,20 @@ void launch_maxnorm(const double *vx, const double *vy, const double *vz, long l
     long long nb = (n + 255) / 256;
     if (nb > 148 * 16) nb = 148 * 16;
     k_maxnorm<<<(int)nb, 256, 0, s>>>(vx, vy, vz, n, out_bits);
+}
+
+void launch_maxnorm_f(const float *vx, const float *vy, const float *vz, long long n, unsigned long long *out_bits, cudaStream_t s)
+{
+    long long nb = (n + 255) / 256;
+    if (nb > 148 * 16) nb = 148 * 16;
+    k_maxnorm_f<<<(int)nb, 256, 0, s>>>(vx, vy, vz, n, out_bits);
+}
+
+void launch_f2d(const float *src, double *dst, long long n, cudaStream_t s)
+{
+    long long nb = (n + 255) / 256;
+    if (nb > 148 * 16) nb = 148 * 16;
+    k_f2d<<<(int)nb, 256, 0, s>>>(src, dst, n);
 }
 
 }  // namespace cpml

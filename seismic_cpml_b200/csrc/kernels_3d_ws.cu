@@ -110,23 +110,23 @@ __device__ __forceinline__ Item decode_item(int item, const Tile3D &t)
 // ring C (plane n only):                 vz (halo, (-2,0)), sxx syy szz sxy sxz syz (plain boxes),
 //                                        x-shell memory variables of the tile rows (three bulk copies)
 // maps: 0 vx 1 vy 2 vz 3..8 sigma
-template <bool KUNIT, int TX, int TY>
+template <typename T, bool KUNIT, int TX, int TY>
 __global__ void __launch_bounds__(tile_threads(TX, TY) + 32, 1)
-k_stress3d_ws(const __grid_constant__ Params3D p, const __grid_constant__ TmaMaps tm, const __grid_constant__ Tile3D t,
+k_stress3d_ws(const __grid_constant__ Params3DT<T> p, const __grid_constant__ TmaMaps tm, const __grid_constant__ Tile3D t,
               const __grid_constant__ SlabSync ss)
 {
-    using G = TileGeom<TX, TY>;
-    constexpr int W = G::W;
+    using G = TileGeomT<T, TX, TY>;
+    constexpr int W = G::W, HX = G::HX, ES = G::ES;
     constexpr int NC = tile_threads(TX, TY), NALL = NC + 32;
     constexpr int NBYTES = 2 * G::HALO_BYTES;                       // ring N stage: vx, vy
     constexpr int CBYTES = G::HALO_BYTES + 6 * G::PLAIN_BYTES;      // ring C stage: vz, 6 sigma
     constexpr uint32_t TX_N = 2 * G::HALO_BOX_BYTES;
     constexpr uint32_t TX_C = G::HALO_BOX_BYTES + 6 * G::PLAIN_BOX_BYTES;
-    constexpr int PD = G::PLAIN_BYTES / 8;
-    const uint32_t XMB = (uint32_t)t.xm_bytes, XM_TX = (uint32_t)(TY * p.sxp * 8);
+    constexpr int PD = G::PLAIN_BYTES / ES;
+    const uint32_t XMB = (uint32_t)t.xm_bytes, XM_TX = (uint32_t)(TY * p.sxp * ES);
     const uint32_t CSTAGE = CBYTES + 3 * XMB;
 
-    __shared__ double Cx[6 * TX];                                   // x coefficients of the tile's columns
+    __shared__ T Cx[6 * TX];                                   // x coefficients of the tile's columns
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t sbase = (smem_u32(smem_dyn) + 127u) & ~127u;
     const unsigned char *gbase = smem_dyn + (sbase - smem_u32(smem_dyn));
@@ -158,12 +158,12 @@ k_stress3d_ws(const __grid_constant__ Params3D p, const __grid_constant__ TmaMap
                 const uint32_t bar = barN + 8 * s;
                 mbar_expect_tx(bar, TX_N);
                 tma_load_3d(ringN + s * NBYTES, &tm.m[0], x0, y0, kk, bar);
-                tma_load_3d(ringN + s * NBYTES + G::HALO_BYTES, &tm.m[1], x0 - 2, y0 - 1, kk, bar);
+                tma_load_3d(ringN + s * NBYTES + G::HALO_BYTES, &tm.m[1], x0 - HX, y0 - 1, kk, bar);
             };
             auto issue_c = [&](uint32_t s, int kk) {
                 const uint32_t bar = barC + 8 * s, dst = ringC + s * CSTAGE;
                 mbar_expect_tx(bar, TX_C + (tile_xpml ? 3 * XM_TX : 0u));
-                tma_load_3d(dst, &tm.m[2], x0 - 2, y0, kk, bar);
+                tma_load_3d(dst, &tm.m[2], x0 - HX, y0, kk, bar);
 #pragma unroll
                 for (int f = 0; f < 6; f++)
                     tma_load_3d(dst + G::HALO_BYTES + f * G::PLAIN_BYTES, &tm.m[3 + f], x0, y0, kk, bar);
@@ -241,8 +241,8 @@ k_stress3d_ws(const __grid_constant__ Params3D p, const __grid_constant__ TmaMap
         unsigned qy = in_y ? (unsigned)(((kb - 1) * p.sy + shell_index(j, p.ylo, p.yhi)) * pitch + (i - 1)) : 0u;
         const unsigned qx_step = (unsigned)(p.ny * p.sxp), qy_step = (unsigned)(p.sy * pitch);
 
-        double vz_mA = 0.0, vz_mB = 0.0;                            // plane kb-1, carried along z
-        if (validA) { const double2 t2 = *reinterpret_cast<const double2 *>(p.vz + q - pl); vz_mA = t2.x; vz_mB = t2.y; }
+        T vz_mA = 0, vz_mB = 0;                                     // plane kb-1, carried along z
+        if (validA) { const auto t2 = ldg2(p.vz + q - pl); vz_mA = t2.x; vz_mB = t2.y; }
 
         mbar_wait(barN + 8 * rn.s, rn.par);
         for (int n = 0; n < np; ++n, q += pl, qxr += qx_step, qy += qy_step) {
@@ -252,7 +252,7 @@ k_stress3d_ws(const __grid_constant__ Params3D p, const __grid_constant__ TmaMap
             const bool gen = uy || z_pml;                           // warp-uniform: y / z shell memory variables needed
             const bool in_zA = validA && z_pml, in_zB = validB && z_pml;
             unsigned qz = 0;
-            double mvA[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, mvB[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            T mvA[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, mvB[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
             if (gen) {      // issued before the waits (and before any store of the recursion, which may alias)
                 if (z_pml) qz = (unsigned)(((shell_index(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1));
                 load_memvars(p, 0, false, uy && in_y, in_zA, 0, qy, qz, mvA);
@@ -263,32 +263,33 @@ k_stress3d_ws(const __grid_constant__ Params3D p, const __grid_constant__ TmaMap
             mbar_wait(barN + 8 * rn1.s, rn1.par);
             mbar_wait(barC + 8 * rc.s, rc.par);
 
-            const double *Tvx = (const double *)(gN + (size_t)rn.s * NBYTES);
-            const double *Tvy = (const double *)(gN + (size_t)rn.s * NBYTES + G::HALO_BYTES);
-            const double *Tvxn = (const double *)(gN + (size_t)rn1.s * NBYTES);
-            const double *Tvyn = (const double *)(gN + (size_t)rn1.s * NBYTES + G::HALO_BYTES);
-            const double *Tvz = (const double *)(gC + (size_t)rc.s * CSTAGE);
-            const double *Ts = (const double *)(gC + (size_t)rc.s * CSTAGE + G::HALO_BYTES);
+            const T *Tvx = (const T *)(gN + (size_t)rn.s * NBYTES);
+            const T *Tvy = (const T *)(gN + (size_t)rn.s * NBYTES + G::HALO_BYTES);
+            const T *Tvxn = (const T *)(gN + (size_t)rn1.s * NBYTES);
+            const T *Tvyn = (const T *)(gN + (size_t)rn1.s * NBYTES + G::HALO_BYTES);
+            const T *Tvz = (const T *)(gC + (size_t)rc.s * CSTAGE);
+            const T *Ts = (const T *)(gC + (size_t)rc.s * CSTAGE + G::HALO_BYTES);
             if (ux) {       // x-shell memory variables of this plane, staged with the tiles
-                const double *Tm = (const double *)(gC + (size_t)rc.s * CSTAGE + CBYTES);
-                const int xd = (int)(XMB / 8), r0 = ty * p.sxp;
+                const T *Tm = (const T *)(gC + (size_t)rc.s * CSTAGE + CBYTES);
+                const int xd = (int)(XMB / ES), r0 = ty * p.sxp;
                 if (in_xA) { mvA[0] = Tm[r0 + sxA]; mvA[1] = Tm[xd + r0 + sxA]; mvA[2] = Tm[2 * xd + r0 + sxA]; }
                 if (in_xB) { mvB[0] = Tm[r0 + sxB]; mvB[1] = Tm[xd + r0 + sxB]; mvB[2] = Tm[2 * xd + r0 + sxB]; }
             }
 
-            const double2 vx_c = lds2(Tvx, oh), vx_jp = lds2(Tvx, oh + W), vx_n = lds2(Tvxn, oh);
-            const double vx_ipB = Tvx[oh + 2];
-            const double2 vy_c = lds2(Tvy, oh + W + 2), vy_jm = lds2(Tvy, oh + 2), vy_n = lds2(Tvyn, oh + W + 2);
-            const double vy_imA = Tvy[oh + W + 1];
-            const double2 vz_c = lds2(Tvz, oh + 2), vz_jp = lds2(Tvz, oh + W + 2);
-            const double vz_imA = Tvz[oh + 1];
-            const double2 sxx = lds2(Ts, 0 * PD + oc), syy = lds2(Ts, 1 * PD + oc), szz = lds2(Ts, 2 * PD + oc);
-            const double2 sxy = lds2(Ts, 3 * PD + oc), sxz = lds2(Ts, 4 * PD + oc), syz = lds2(Ts, 5 * PD + oc);
+            // (boxes that start HX cells before the tile hold point A at offset +HX)
+            const auto vx_c = lds2(Tvx, oh), vx_jp = lds2(Tvx, oh + W), vx_n = lds2(Tvxn, oh);
+            const T vx_ipB = Tvx[oh + 2];
+            const auto vy_c = lds2(Tvy, oh + W + HX), vy_jm = lds2(Tvy, oh + HX), vy_n = lds2(Tvyn, oh + W + HX);
+            const T vy_imA = Tvy[oh + W + HX - 1];
+            const auto vz_c = lds2(Tvz, oh + HX), vz_jp = lds2(Tvz, oh + W + HX);
+            const T vz_imA = Tvz[oh + HX - 1];
+            const auto sxx = lds2(Ts, 0 * PD + oc), syy = lds2(Ts, 1 * PD + oc), szz = lds2(Ts, 2 * PD + oc);
+            const auto sxy = lds2(Ts, 3 * PD + oc), sxz = lds2(Ts, 4 * PD + oc), syz = lds2(Ts, 5 * PD + oc);
 
             // everything this plane needs from stages rn.s / rc.s is in registers: hand them back to the producer
             bar_arrive(kRelBar0 + (int)rc.s, NALL);
 
-            StressVals a{sxx.x, syy.x, szz.x, sxy.x, sxz.x, syz.x}, b{sxx.y, syy.y, szz.y, sxy.y, sxz.y, syz.y};
+            StressValsT<T> a{sxx.x, syy.x, szz.x, sxy.x, sxz.x, syz.x}, b{sxx.y, syy.y, szz.y, sxy.y, sxz.y, syz.y};
             if (gen) {
                 stress_point<true, KUNIT, TX>(p, Cx, 2 * tx, jc, kg, do_nA, do_xyA, do_xzA, do_yzA, ux, uy, z_pml, in_xA, in_y, in_zA,
                                               qxr + sxA, qy, qz, mvA,
@@ -354,24 +355,24 @@ k_stress3d_ws(const __grid_constant__ Params3D p, const __grid_constant__ TmaMap
 // ring C (plane n only):     sxx (halo box at (-2,0)), syy (halo, (0,0)), sxy (halo, (0,-1)),
 //                            sxz (halo, (0,0)), syz (halo, (0,-1)), vx vy vz (plain boxes), x-shell memory variables
 // maps: 0 sxx 1 syy 2 sxy 3 sxz 4 syz 5 szz 6 vx 7 vy 8 vz
-template <bool KUNIT, int TX, int TY>
+template <typename T, bool KUNIT, int TX, int TY>
 __global__ void __launch_bounds__(tile_threads(TX, TY) + 32, 1)
-k_velocity3d_ws(const __grid_constant__ Params3D p, const __grid_constant__ TmaMaps tm, const __grid_constant__ Tile3D t,
+k_velocity3d_ws(const __grid_constant__ Params3DT<T> p, const __grid_constant__ TmaMaps tm, const __grid_constant__ Tile3D t,
                 const __grid_constant__ SlabSync ss)
 {
-    using G = TileGeom<TX, TY>;
-    constexpr int W = G::W;
+    using G = TileGeomT<T, TX, TY>;
+    constexpr int W = G::W, HX = G::HX, ES = G::ES;
     constexpr int NC = tile_threads(TX, TY), NALL = NC + 32;
     constexpr int NBYTES = G::PLAIN_BYTES;                          // ring N stage: szz
     constexpr int CBYTES = 5 * G::HALO_BYTES + 3 * G::PLAIN_BYTES;  // ring C stage: 5 sigma (halo), vx vy vz
     constexpr uint32_t TX_N = G::PLAIN_BOX_BYTES;
     constexpr uint32_t TX_C = 5 * G::HALO_BOX_BYTES + 3 * G::PLAIN_BOX_BYTES;
-    constexpr int PD = G::PLAIN_BYTES / 8, HD = G::HALO_BYTES / 8;
-    const uint32_t XMB = (uint32_t)t.xm_bytes, XM_TX = (uint32_t)(TY * p.sxp * 8);
+    constexpr int PD = G::PLAIN_BYTES / ES, HD = G::HALO_BYTES / ES;
+    const uint32_t XMB = (uint32_t)t.xm_bytes, XM_TX = (uint32_t)(TY * p.sxp * ES);
     const uint32_t CSTAGE = CBYTES + 3 * XMB;
 
     __shared__ double red[2 * (NC / 32)];
-    __shared__ double Cx[6 * TX];                                   // x coefficients of the tile's columns
+    __shared__ T Cx[6 * TX];                                   // x coefficients of the tile's columns
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t sbase = (smem_u32(smem_dyn) + 127u) & ~127u;
     const unsigned char *gbase = smem_dyn + (sbase - smem_u32(smem_dyn));
@@ -412,7 +413,7 @@ k_velocity3d_ws(const __grid_constant__ Params3D p, const __grid_constant__ TmaM
 #pragma unroll
                     for (int f = 0; f < 3; f++) bulk_load(dst + CBYTES + f * XMB, p.mx[3 + f] + row0, XM_TX, bar);
                 }
-                tma_load_3d(dst + 0 * G::HALO_BYTES, &tm.m[0], x0 - 2, y0, kk, bar);
+                tma_load_3d(dst + 0 * G::HALO_BYTES, &tm.m[0], x0 - HX, y0, kk, bar);
                 tma_load_3d(dst + 1 * G::HALO_BYTES, &tm.m[1], x0, y0, kk, bar);
                 tma_load_3d(dst + 2 * G::HALO_BYTES, &tm.m[2], x0, y0 - 1, kk, bar);
                 tma_load_3d(dst + 3 * G::HALO_BYTES, &tm.m[3], x0, y0, kk, bar);
@@ -492,9 +493,9 @@ k_velocity3d_ws(const __grid_constant__ Params3D p, const __grid_constant__ TmaM
         unsigned qy = in_y ? (unsigned)(((kb - 1) * p.sy + shell_index(j, p.ylo, p.yhi)) * pitch + (i - 1)) : 0u;
         const unsigned qx_step = (unsigned)(p.ny * p.sxp), qy_step = (unsigned)(p.sy * pitch);
 
-        double sxz_mA = 0.0, sxz_mB = 0.0, syz_mA = 0.0, syz_mB = 0.0;     // plane kb-1
+        T sxz_mA = 0, sxz_mB = 0, syz_mA = 0, syz_mB = 0;                  // plane kb-1
         if (validA) {
-            const double2 t2 = *reinterpret_cast<const double2 *>(p.sxz + q - pl), u2 = *reinterpret_cast<const double2 *>(p.syz + q - pl);
+            const auto t2 = ldg2(p.sxz + q - pl), u2 = ldg2(p.syz + q - pl);
             sxz_mA = t2.x; sxz_mB = t2.y; syz_mA = u2.x; syz_mB = u2.y;
         }
         double ekin = 0.0, epot = 0.0;
@@ -507,7 +508,7 @@ k_velocity3d_ws(const __grid_constant__ Params3D p, const __grid_constant__ TmaM
             const bool gen = uy || z_pml;                           // warp-uniform
             const bool in_zA = validA && z_pml, in_zB = validB && z_pml;
             unsigned qz = 0;
-            double mvA[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, mvB[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            T mvA[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, mvB[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
             if (gen) {
                 if (z_pml) qz = (unsigned)(((shell_index(kg, p.zlo, p.zhi) - p.zbase) * p.ny + (j - 1)) * pitch + (i - 1));
                 load_memvars(p, 3, false, uy && in_y, in_zA, 0, qy, qz, mvA);
@@ -518,31 +519,31 @@ k_velocity3d_ws(const __grid_constant__ Params3D p, const __grid_constant__ TmaM
             mbar_wait(barN + 8 * rn1.s, rn1.par);
             mbar_wait(barC + 8 * rc.s, rc.par);
 
-            const double *Tc = (const double *)(gC + (size_t)rc.s * CSTAGE);
+            const T *Tc = (const T *)(gC + (size_t)rc.s * CSTAGE);
             if (ux) {
-                const double *Tm = (const double *)(gC + (size_t)rc.s * CSTAGE + CBYTES);
-                const int xd = (int)(XMB / 8), r0 = ty * p.sxp;
+                const T *Tm = (const T *)(gC + (size_t)rc.s * CSTAGE + CBYTES);
+                const int xd = (int)(XMB / ES), r0 = ty * p.sxp;
                 if (in_xA) { mvA[0] = Tm[r0 + sxA]; mvA[1] = Tm[xd + r0 + sxA]; mvA[2] = Tm[2 * xd + r0 + sxA]; }
                 if (in_xB) { mvB[0] = Tm[r0 + sxB]; mvB[1] = Tm[xd + r0 + sxB]; mvB[2] = Tm[2 * xd + r0 + sxB]; }
             }
-            const double *Txx = Tc, *Tyy = Tc + HD, *Txy = Tc + 2 * HD, *Txz = Tc + 3 * HD, *Tyz = Tc + 4 * HD;
-            const double *Tp = Tc + 5 * HD;
+            const T *Txx = Tc, *Tyy = Tc + HD, *Txy = Tc + 2 * HD, *Txz = Tc + 3 * HD, *Tyz = Tc + 4 * HD;
+            const T *Tp = Tc + 5 * HD;
 
-            const double2 sxx_c = lds2(Txx, oh + 2);
-            const double sxx_imA = Txx[oh + 1];
-            const double2 syy_c = lds2(Tyy, oh), syy_jp = lds2(Tyy, oh + W);
-            const double2 sxy_c = lds2(Txy, oh + W), sxy_jm = lds2(Txy, oh);
-            const double sxy_ipB = Txy[oh + W + 2];
-            const double2 sxz_c = lds2(Txz, oh);
-            const double sxz_ipB = Txz[oh + 2];
-            const double2 syz_c = lds2(Tyz, oh + W), syz_jm = lds2(Tyz, oh);
-            const double2 szz_c = lds2((const double *)(gN + (size_t)rn.s * NBYTES), oc);
-            const double2 szz_n = lds2((const double *)(gN + (size_t)rn1.s * NBYTES), oc);
-            const double2 vx = lds2(Tp, 0 * PD + oc), vy = lds2(Tp, 1 * PD + oc), vz = lds2(Tp, 2 * PD + oc);
+            const auto sxx_c = lds2(Txx, oh + HX);                  // box starts HX cells before the tile
+            const T sxx_imA = Txx[oh + HX - 1];
+            const auto syy_c = lds2(Tyy, oh), syy_jp = lds2(Tyy, oh + W);
+            const auto sxy_c = lds2(Txy, oh + W), sxy_jm = lds2(Txy, oh);
+            const T sxy_ipB = Txy[oh + W + 2];
+            const auto sxz_c = lds2(Txz, oh);
+            const T sxz_ipB = Txz[oh + 2];
+            const auto syz_c = lds2(Tyz, oh + W), syz_jm = lds2(Tyz, oh);
+            const auto szz_c = lds2((const T *)(gN + (size_t)rn.s * NBYTES), oc);
+            const auto szz_n = lds2((const T *)(gN + (size_t)rn1.s * NBYTES), oc);
+            const auto vx = lds2(Tp, 0 * PD + oc), vy = lds2(Tp, 1 * PD + oc), vz = lds2(Tp, 2 * PD + oc);
 
             bar_arrive(kRelBar0 + (int)rc.s, NALL);                 // stages rn.s / rc.s are in registers
 
-            VelVals a{vx.x, vy.x, vz.x}, b{vx.y, vy.y, vz.y};
+            VelValsT<T> a{vx.x, vy.x, vz.x}, b{vx.y, vy.y, vz.y};
             if (gen) {
                 velocity_point<true, KUNIT, TX>(p, Cx, 2 * tx, jc, k, kg, do_vxA, do_vyA, do_vzA, edgeA, eboxA, srcA, ux, uy, z_pml, in_xA, in_y, in_zA,
                                                 qxr + sxA, qy, qz, mvA,
@@ -575,8 +576,8 @@ k_velocity3d_ws(const __grid_constant__ Params3D p, const __grid_constant__ TmaM
 
             // pad lanes (beyond NX, inside the row pitch) hold and keep zero: they are outside every nest and their
             // loaded values are the TMA's zero fill; they are stored so that whole rows / sectors are written
-            if (!validA) { a.vx = 0.0; a.vy = 0.0; a.vz = 0.0; }
-            if (!validB) { b.vx = 0.0; b.vy = 0.0; b.vz = 0.0; }
+            if (!validA) { a.vx = 0; a.vy = 0; a.vz = 0; }
+            if (!validB) { b.vx = 0; b.vy = 0; b.vz = 0; }
             if (storeA) {
                 st_stream2(p.vx + q, a.vx, b.vx);
                 st_stream2(p.vy + q, a.vy, b.vy);
@@ -608,64 +609,80 @@ k_velocity3d_ws(const __grid_constant__ Params3D p, const __grid_constant__ TmaM
 
 // ---- launch dispatch ---------------------------------------------------------------
 
-template <int TX, int TY>
+template <typename T, int TX, int TY>
 static size_t ws_smem_need(bool stress, int stages, int xm_bytes)
 {
-    using G = TileGeom<TX, TY>;
+    using G = TileGeomT<T, TX, TY>;
     const size_t c = stress ? G::HALO_BYTES + 6 * G::PLAIN_BYTES : 5 * G::HALO_BYTES + 3 * G::PLAIN_BYTES;
     const size_t n = stress ? 2 * G::HALO_BYTES : G::PLAIN_BYTES;
     return kBarBytes + 128 + (c + 3 * (size_t)xm_bytes) * (size_t)stages + n * (size_t)(stages + 1);
 }
 
-template <bool KUNIT, int TX, int TY>
-static cudaError_t ws_launch_tile(const Params3D &p, const TmaMaps &tm, const Tile3D &t, const SlabSync &ss, cudaStream_t s,
+template <typename T, bool KUNIT, int TX, int TY>
+static cudaError_t ws_launch_tile(const Params3DT<T> &p, const TmaMaps &tm, const Tile3D &t, const SlabSync &ss, cudaStream_t s,
                                   bool stress, int *occ)
 {
-    const size_t smem = ws_smem_need<TX, TY>(stress, t.stages, t.xm_bytes);
+    const size_t smem = ws_smem_need<T, TX, TY>(stress, t.stages, t.xm_bytes);
     constexpr int NT = tile_threads(TX, TY) + 32;     // consumer warps + the producer warp
-    const void *fn = stress ? (const void *)k_stress3d_ws<KUNIT, TX, TY> : (const void *)k_velocity3d_ws<KUNIT, TX, TY>;
+    const void *fn = stress ? (const void *)k_stress3d_ws<T, KUNIT, TX, TY> : (const void *)k_velocity3d_ws<T, KUNIT, TX, TY>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (occ) {
-        if (stress) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_stress3d_ws<KUNIT, TX, TY>, NT, smem);
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_velocity3d_ws<KUNIT, TX, TY>, NT, smem);
+        if (stress) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_stress3d_ws<T, KUNIT, TX, TY>, NT, smem);
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_velocity3d_ws<T, KUNIT, TX, TY>, NT, smem);
     }
     const dim3 grid(stress ? t.grid_stress : t.grid_velocity);
-    if (stress) k_stress3d_ws<KUNIT, TX, TY><<<grid, NT, smem, s>>>(p, tm, t, ss);
-    else        k_velocity3d_ws<KUNIT, TX, TY><<<grid, NT, smem, s>>>(p, tm, t, ss);
+    if (stress) k_stress3d_ws<T, KUNIT, TX, TY><<<grid, NT, smem, s>>>(p, tm, t, ss);
+    else        k_velocity3d_ws<T, KUNIT, TX, TY><<<grid, NT, smem, s>>>(p, tm, t, ss);
     return cudaGetLastError();
 }
 
 // Tiles (TX x TY points, one consumer thread per pair of x-adjacent points + 32 producer threads).  With the
 // producer warp a 128 x 8 tile would be 17 warps (five on one SM sub-partition: 96 registers), so wide grids
-// take 128 x 7 (15 warps) or 104 x 8 (14 warps).
+// take 128 x 7 (15 warps) or 104 x 8 (14 warps).  The single-precision build has 64 x 8, 104 x 8 and 128 x 7.
 template <bool KUNIT>
 static cudaError_t ws_dispatch(const Params3D &p, const TmaMaps &tm, const Tile3D &t, const SlabSync &ss, cudaStream_t s,
                                bool stress, int *occ)
 {
     switch (t.tx * 100 + t.ty) {
-    case 6404:  return ws_launch_tile<KUNIT, 64, 4>(p, tm, t, ss, s, stress, occ);      // 128 + 32 threads (tests)
-    case 6408:  return ws_launch_tile<KUNIT, 64, 8>(p, tm, t, ss, s, stress, occ);      // 256 + 32
-    case 10407: return ws_launch_tile<KUNIT, 104, 7>(p, tm, t, ss, s, stress, occ);     // 384 + 32
-    case 10408: return ws_launch_tile<KUNIT, 104, 8>(p, tm, t, ss, s, stress, occ);     // 416 + 32
-    case 12806: return ws_launch_tile<KUNIT, 128, 6>(p, tm, t, ss, s, stress, occ);     // 384 + 32
-    case 12807: return ws_launch_tile<KUNIT, 128, 7>(p, tm, t, ss, s, stress, occ);     // 448 + 32
+    case 6404:  return ws_launch_tile<double, KUNIT, 64, 4>(p, tm, t, ss, s, stress, occ);      // 128 + 32 threads (tests)
+    case 6408:  return ws_launch_tile<double, KUNIT, 64, 8>(p, tm, t, ss, s, stress, occ);      // 256 + 32
+    case 10407: return ws_launch_tile<double, KUNIT, 104, 7>(p, tm, t, ss, s, stress, occ);     // 384 + 32
+    case 10408: return ws_launch_tile<double, KUNIT, 104, 8>(p, tm, t, ss, s, stress, occ);     // 416 + 32
+    case 12806: return ws_launch_tile<double, KUNIT, 128, 6>(p, tm, t, ss, s, stress, occ);     // 384 + 32
+    case 12807: return ws_launch_tile<double, KUNIT, 128, 7>(p, tm, t, ss, s, stress, occ);     // 448 + 32
+    default: return cudaErrorInvalidValue;
+    }
+}
+template <bool KUNIT>
+static cudaError_t ws_dispatch(const Params3DF &p, const TmaMaps &tm, const Tile3D &t, const SlabSync &ss, cudaStream_t s,
+                               bool stress, int *occ)
+{
+    switch (t.tx * 100 + t.ty) {
+    case 6408:  return ws_launch_tile<float, KUNIT, 64, 8>(p, tm, t, ss, s, stress, occ);
+    case 10408: return ws_launch_tile<float, KUNIT, 104, 8>(p, tm, t, ss, s, stress, occ);
+    case 12807: return ws_launch_tile<float, KUNIT, 128, 7>(p, tm, t, ss, s, stress, occ);
     default: return cudaErrorInvalidValue;
     }
 }
 
-bool ws_tile_supported(int tx, int ty)
+bool ws_tile_supported(int tx, int ty, bool f32)
 {
     switch (tx * 100 + ty) {
-    case 6404: case 6408: case 10407: case 10408: case 12806: case 12807: return true;
+    case 6408: case 10408: case 12807: return true;
+    case 6404: case 10407: case 12806: return !f32;
     default: return false;
     }
 }
 
-cudaError_t ws_occupancy(const Params3D &p, const Tile3D &t, bool stress, int *occ)
+cudaError_t ws_occupancy(const Params3D &p, const Tile3D &t, bool stress, int *occ, bool f32)
 {
     TmaMaps dummy{};
     SlabSync none{};
+    if (f32) {
+        Params3DF pf{};
+        return p.kunit ? ws_dispatch<true>(pf, dummy, t, none, nullptr, stress, occ) : ws_dispatch<false>(pf, dummy, t, none, nullptr, stress, occ);
+    }
     return p.kunit ? ws_dispatch<true>(p, dummy, t, none, nullptr, stress, occ) : ws_dispatch<false>(p, dummy, t, none, nullptr, stress, occ);
 }
 
@@ -674,6 +691,14 @@ cudaError_t launch_stress3d_ws(const Params3D &p, const TmaMaps &tm, const Tile3
     return p.kunit ? ws_dispatch<true>(p, tm, t, ss, s, true, nullptr) : ws_dispatch<false>(p, tm, t, ss, s, true, nullptr);
 }
 cudaError_t launch_velocity3d_ws(const Params3D &p, const TmaMaps &tm, const Tile3D &t, const SlabSync &ss, cudaStream_t s)
+{
+    return p.kunit ? ws_dispatch<true>(p, tm, t, ss, s, false, nullptr) : ws_dispatch<false>(p, tm, t, ss, s, false, nullptr);
+}
+cudaError_t launch_stress3d_ws(const Params3DF &p, const TmaMaps &tm, const Tile3D &t, const SlabSync &ss, cudaStream_t s)
+{
+    return p.kunit ? ws_dispatch<true>(p, tm, t, ss, s, true, nullptr) : ws_dispatch<false>(p, tm, t, ss, s, true, nullptr);
+}
+cudaError_t launch_velocity3d_ws(const Params3DF &p, const TmaMaps &tm, const Tile3D &t, const SlabSync &ss, cudaStream_t s)
 {
     return p.kunit ? ws_dispatch<true>(p, tm, t, ss, s, false, nullptr) : ws_dispatch<false>(p, tm, t, ss, s, false, nullptr);
 }

@@ -44,6 +44,7 @@ class CpmlConfig(C.Structure):
                 ("nslabs", C.c_int32), ("slab_rank", C.c_int32), ("device", C.c_int32),
                 ("energy_bug_compat", C.c_int32), ("rheology", C.c_int32),
                 ("emulate_nproc", C.c_int32), ("compute_energy", C.c_int32), ("sigmazz_isotropic", C.c_int32),
+                ("precision", C.c_int32),
                 ("deltax", C.c_double), ("deltay", C.c_double), ("deltaz", C.c_double),
                 ("deltat", C.c_double),
                 ("lambda_", C.c_double), ("mu", C.c_double), ("lambdaplustwomu", C.c_double),
@@ -274,13 +275,13 @@ class Solver:
     def __init__(self, *, ndim, order=2, nx, ny, nz=1, nstep, npoints_pml, nrec, isource, jsource,
                  ksource=0, nslabs=1, slab_rank=0, device=-1, energy_bug_compat=True, sigmazz_isotropic=False,
                  deltax, deltay, deltaz=0.0, deltat, lam=0.0, mu=0.0, lambdaplustwomu=0.0, rho=0.0,
-                 cp=0.0, rheology=0, emulate_nproc=0, compute_energy=False):
+                 cp=0.0, rheology=0, emulate_nproc=0, compute_energy=False, precision=0):
         self._L = load()
         self.cfg = CpmlConfig(ndim=ndim, order=order, nx=nx, ny=ny, nz=nz, nstep=nstep,
                               npoints_pml=npoints_pml, nrec=nrec, isource=isource, jsource=jsource,
                               ksource=ksource, nslabs=nslabs, slab_rank=slab_rank, device=device,
                               energy_bug_compat=int(energy_bug_compat), sigmazz_isotropic=int(sigmazz_isotropic),
-                              rheology=rheology,
+                              rheology=rheology, precision=precision,
                               emulate_nproc=emulate_nproc, compute_energy=int(compute_energy),
                               deltax=deltax, deltay=deltay, deltaz=deltaz, deltat=deltat,
                               lambda_=lam, mu=mu, lambdaplustwomu=lambdaplustwomu, rho=rho, cp=cp)

@@ -181,6 +181,9 @@ def test_cpp_driver_ngpu_equals_single_gpu(driver_exe, tmp_path, program, ngpu, 
     """NGPU= (the compiled driver's stand-in for the reference's NPROC MPI ranks: cpml_multi_*, one host thread, no
     MPI, no Python): the seismogram and energy FILES of an NGPU run equal those of the one-GPU run byte for byte
     (energy: to summation order).  same=1 puts every slab on device 0, so this also runs on a one-GPU box."""
+    only = [int(x) for x in os.environ.get("CPML_TEST_WORLDS", "").split(",") if x.strip()]
+    if only and (ngpu not in only or same):
+        pytest.skip("CPML_TEST_WORLDS")
     if not same and _ngpu() < ngpu:
         pytest.skip(f"needs {ngpu} GPUs")
     common = ["NX=48", "NY=60", "NZ=48", "NSTEP=100", "NPOINTS_PML=5", "IT_DISPLAY=50", "--no-images"]
