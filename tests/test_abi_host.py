@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_config_struct_matches_header_layout():
-    # 19 int32 (15 named + 4 reserved) + pad to 8 + 13 doubles
+    # 20 int32 (the last one, precision, fills what used to be padding) + 13 doubles
     assert C.sizeof(L.CpmlConfig) == 80 + 13 * 8
     assert L.CpmlConfig.deltax.offset == 80
 
