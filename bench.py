@@ -7,6 +7,8 @@ One "step" = one full time step of the loop body (stress + velocity + source + D
 + seismogram sample + energy) over the rank's z-slab.  Workloads (BASELINE.json configs):
   cfg3  seismic_CPML_3D_isotropic_MPI_OpenMP default grid 101 x 641 x 640 per GPU
         (N = 1: exactly the reference grid; N > 1: weak scaling, NZ = 640 N)   [default]
+  cfg3f the same grid in SINGLE precision (cpml_config.precision = 1, the build the reference endorses, 3D-iso :114-116;
+        one GPU; its CPU arm is the double-precision restatement)
   cfg4  1024 x 1024 x 128 per GPU (N = 8: 1024^3), weak scaling
   cfg2  2-D fourth order 4096 x 4096 (single GPU only)
   cfg5  seismic_CPML_3D_viscoelastic_MPI (4th order, N_SLS = 2) 1024 x 1024 x 128 per GPU, weak scaling
@@ -103,6 +105,7 @@ class ClockSampler:
 # these with oracle/workloads.py and never touches the product package.
 WORKLOADS = {
     "cfg3": dict(kind="3d", nx=101, ny=641, nz_per_gpu=640, deltat=1.6e-3, npml=10),
+    "cfg3f": dict(kind="3d", nx=101, ny=641, nz_per_gpu=640, deltat=1.6e-3, npml=10, precision=1),
     "cfg4": dict(kind="3d", nx=1024, ny=1024, nz_per_gpu=128, deltat=1.6e-3, npml=10),
     "cfg5": dict(kind="3dv", nx=1024, ny=1024, nz_per_gpu=128, deltat=4e-4, npml=10),
     "cfg5d": dict(kind="3dv", nx=210, ny=800, nz_per_gpu=220, deltat=4e-4, npml=10),
@@ -124,7 +127,8 @@ def common_config(name, n_gpus):
         label = (f"seismic_CPML_3D_viscoelastic_MPI (4th order, N_SLS=2, reference NPROC={_visco_nproc(n_gpus, nz)} emulated): "
                  f"{w['nx']}x{w['ny']}x{nz} ({w['nx']}x{w['ny']}x{w['nz_per_gpu']} per GPU, z-slabs)")
     else:
-        tag = "default grid" if name == "cfg3" else "~1024^3 scaled grid"
+        tag = ("default grid" if name == "cfg3" else "default grid, SINGLE PRECISION (3D-iso :114-116)" if name == "cfg3f"
+               else "~1024^3 scaled grid")
         label = (f"seismic_CPML_3D_isotropic_MPI_OpenMP {tag}: {w['nx']}x{w['ny']}x{nz} "
                  f"({w['nx']}x{w['ny']}x{w['nz_per_gpu']} per GPU, z-slabs)")
     return {"workload": label, "grid": [w["nx"], w["ny"], nz], "npoints_pml": w["npml"], "deltat": w["deltat"],
@@ -134,7 +138,7 @@ def common_config(name, n_gpus):
 
 def workload_params(name, n_gpus, nstep):
     from seismic_cpml_b200 import programs as P
-    if name == "cfg3":
+    if name in ("cfg3", "cfg3f"):
         return P.Params3DIso(NZ=640 * n_gpus, NSTEP=nstep), "3d"
     if name == "cfg4":
         return P.Params3DIso(NX=1024, NY=1024, NZ=128 * n_gpus, NSTEP=nstep), "3d"
@@ -307,8 +311,11 @@ def run_b200(args):
     nstep_total = W + K + K + 8          # warm-up + device-timed + e2e-timed (+ slack)
     p, kind = workload_params(args.workload, world, nstep_total)
     s = P.setup_3d(p) if kind == "3d" else P.setup_3d_visco(p) if kind == "3dv" else P.setup_2d_visco(p) if kind == "2dv" else P.setup_2d(p)
+    f32 = WORKLOADS[args.workload].get("precision", 0) == 1
+    if f32 and world != 1:
+        raise SystemExit("cfg3f (single precision) runs on one GPU")
     if kind == "3d":
-        sol = P.make_solver_3d(p, s, nslabs=world, slab_rank=rank, device=local_rank)
+        sol = P.make_solver_3d(p, s, nslabs=world, slab_rank=rank, device=local_rank, precision=1 if f32 else 0)
         pts_step_rank = float(p.NX) * p.NY * (p.NZ // world)
     elif kind == "3dv":
         sol = P.make_solver_3d_visco(p, s, nslabs=world, slab_rank=rank, device=local_rank)
@@ -455,9 +462,10 @@ def run_b200(args):
     if rank == 0:
         cfg = common_config(args.workload, world)
         line = {
-            "metric": metric_name(kind), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "metric": metric_name(kind).replace("FP64", "FP32") if f32 else metric_name(kind), "value": value, "unit": UNIT,
+            "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic (fields start at zero, analytic source; no RNG)",
+            "dtype": "f32" if f32 else "f64", "data": "synthetic (fields start at zero, analytic source; no RNG)",
             "config": cfg,
             "run": {"halo": (None if world == 1 else
                              "boundary planes stored straight into the neighbour GPU's halo planes by the update kernels "
@@ -506,7 +514,7 @@ def main():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg4", "cfg2", "cfg5", "cfg5d", "cfg6"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg3f", "cfg4", "cfg2", "cfg5", "cfg5d", "cfg6"])
     ap.add_argument("--halo", default="p2p", choices=["p2p", "sendrecv"],
                     help="N > 1: peer stores from inside the kernels (default) or NCCL send/recv")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")

@@ -470,8 +470,9 @@ def make_solver_3d_visco(p: Params3DVisco, s: Setup, *, nslabs=1, slab_rank=0, d
     return sol
 
 
-def make_solver_3d(p: Params3DIso, s: Setup, *, nslabs=1, slab_rank=0, device=-1) -> _lib.Solver:
-    sol = _lib.Solver(ndim=3, order=2, nx=p.NX, ny=p.NY, nz=p.NZ, nstep=p.NSTEP,
+def make_solver_3d(p: Params3DIso, s: Setup, *, nslabs=1, slab_rank=0, device=-1, precision=0) -> _lib.Solver:
+    """precision=1: the single-precision build the reference endorses (3D-iso :114-116), one GPU only."""
+    sol = _lib.Solver(ndim=3, order=2, nx=p.NX, ny=p.NY, nz=p.NZ, nstep=p.NSTEP, precision=precision,
                       npoints_pml=p.NPOINTS_PML, nrec=p.NREC, isource=p.ISOURCE, jsource=p.JSOURCE,
                       ksource=p.KSOURCE, nslabs=nslabs, slab_rank=slab_rank, device=device,
                       energy_bug_compat=p.energy_bug_compat, deltax=p.DELTAX, deltay=p.DELTAY,
