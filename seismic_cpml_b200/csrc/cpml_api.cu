@@ -731,7 +731,9 @@ static int32_t build_tile(cpml_handle *h, EncodeTiledFn enc, bool stress, Tile3D
         if (stress) t.ty = env_int("CPML_TY_STRESS", (t.tx == 104 && t.ty == 8) ? 7 : t.ty);
         if (!tma_tile_supported(t.tx, t.ty)) FAIL(CPML_EINVAL, "unsupported CPML_TX x CPML_TY tile");
     }
-    t.stages = std::max(1, std::min(h->use_ws ? 4 : 7, env_int("CPML_STAGES", 2)));
+    // ring depth: two planes in double precision (three evict each other's lines from L2 before they are consumed:
+    // 20.1 against 22.1 Gpts/s); the single-precision stages are half the size and three are 1.4 % faster
+    t.stages = std::max(1, std::min(h->use_ws ? 4 : 7, env_int("CPML_STAGES", h->f32 ? 3 : 2)));
     t.minb = std::max(1, std::min(4, env_int("CPML_MINB", t.tx == 64 ? 2 : 1)));
     if (t.ty == 7 || t.ty == 6) t.minb = 1;
     t.xm_bytes = h->shell[0].size() > 0 ? round_up(t.ty * h->sxp * (h->f32 ? 4 : 8), 128) : 0;
