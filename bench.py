@@ -457,6 +457,8 @@ def run_b200(args):
         names = sol.kernel_names()
     elif kind == "3dv" and sol.launch_info()["tma"] == 2:
         names = ("k_vstress3d", "k_vvelocity3d_ws")
+    elif kind == "2d" and os.environ.get("CPML_2D_KERNEL", "ws") != "pair":
+        names = ("k_stress2d_ws", "k_velocity2d_ws")
     t_s, t_v = traffic.get("stress_dram_bytes_per_launch"), traffic.get("velocity_dram_bytes_per_launch")
 
     if rank == 0:

@@ -13,8 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJDIR = os.path.join(CSRC, "_build")
 SOURCES = ["cpml_api.cu", "cpml_multi.cu", "kernels_3d.cu", "kernels_3d_tma.cu", "kernels_3d_ws.cu", "kernels_3d_visco.cu", "kernels_3d_visco_ws.cu",
-           "kernels_2d.cu", "kernels_2d_visco.cu", "cpml_host.cpp", "attenuation_fit.cpp"]
-HEADERS = [os.path.join(CSRC, "cpml_internal.h"), os.path.join(CSRC, "tma_common.cuh"), os.path.join(CSRC, "visco_common.cuh"),
+           "kernels_2d.cu", "kernels_2d_ws.cu", "kernels_2d_visco.cu", "cpml_host.cpp", "attenuation_fit.cpp"]
+HEADERS = [os.path.join(CSRC, "cpml_internal.h"), os.path.join(CSRC, "tma_common.cuh"), os.path.join(CSRC, "visco_common.cuh"), os.path.join(CSRC, "kernels_2d_point.cuh"),
            os.path.join(HERE, "..", "include", "cpml_b200.h")]
 LIB = os.path.join(HERE, "libcpml_b200.so")
 

@@ -54,6 +54,9 @@ struct cpml_handle {
     double *d_sisvz = nullptr; // 3-D: Vz seismograms (extension, quirk B7)
     dim3 vgrid;
     int vkchunk = 1, vtx = 32, vty = 8;
+    bool ws2 = false;          // 2-D isotropic: TMA-staged y-marching kernels (kernels_2d_ws.cu, the default)
+    Tile2D tile2{};
+    TmaMaps maps2_stress{}, maps2_velocity{};
     bool v_ws = false;         // TMA-staged velocity kernel with a producer warp (kernels_3d_visco_ws.cu, the default)
     Tile3D vtile{};
     TmaMaps vmaps{};
@@ -887,6 +890,64 @@ static int32_t setup_visco_ws(cpml_handle *h)
     return CPML_OK;
 }
 
+// Tensor maps and work decomposition of the TMA-staged 2-D kernels.  The tensors are the padded arrays (x offset 16, two
+// ghost rows), so every edge tap reads the zeros of the reference's (0:NX+1,0:NY+1) arrays from memory.
+static int32_t setup_2d_ws(cpml_handle *h)
+{
+    const cpml_config &c = h->cfg;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) FAIL(CPML_ECUDA, "driver does not export cuTensorMapEncodeTiled");
+    const EncodeTiledFn enc = (EncodeTiledFn)fn;
+    Tile2D &t = h->tile2;
+    int bs[7][2], bv[6][2];
+    ws2_geometry(&t.tx, &t.rb, bs, bv);
+    auto encode = [&](CUtensorMap *out, double *base, const int (&box)[2]) -> int32_t {
+        const cuuint64_t dims[2] = {(cuuint64_t)h->pitch, (cuuint64_t)(c.ny + 4)};
+        const cuuint64_t strides[1] = {(cuuint64_t)h->pitch * sizeof(double)};
+        const cuuint32_t bx[2] = {(cuuint32_t)box[0], (cuuint32_t)box[1]};
+        const cuuint32_t estr[2] = {1u, 1u};
+        const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)base, dims, strides, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) FAIL(CPML_ECUDA, "cuTensorMapEncodeTiled (2-D) failed with CUresult " + std::to_string((int)r));
+        return CPML_OK;
+    };
+    // stress: vx vy lambda mu sxx syy sxy ; velocity: sxx sxy rho syy vx vy
+    double *sb[7] = {h->field_alloc[0], h->field_alloc[1], h->mat[0], h->mat[1], h->field_alloc[2], h->field_alloc[3], h->field_alloc[4]};
+    double *vb[6] = {h->field_alloc[2], h->field_alloc[4], h->mat[2], h->field_alloc[3], h->field_alloc[0], h->field_alloc[1]};
+    for (int m = 0; m < 7; m++) { const int32_t rc = encode(&h->maps2_stress.m[m], sb[m], bs[m]); if (rc) return rc; }
+    for (int m = 0; m < 6; m++) { const int32_t rc = encode(&h->maps2_velocity.m[m], vb[m], bv[m]); if (rc) return rc; }
+    int occ_s = 0, occ_v = 0;
+    if (ws2_occupancy(c.order, true, &occ_s) != cudaSuccess || ws2_occupancy(c.order, false, &occ_v) != cudaSuccess || occ_s < 1 || occ_v < 1) {
+        cudaGetLastError();
+        FAIL(CPML_ECUDA, "the TMA-staged 2-D kernels do not fit on this device");
+    }
+    t.ntx = (c.nx + t.tx - 1) / t.tx;
+    // y chunks: rounds over the resident CTAs x (blocks per chunk + pipeline fill), finest within 3 % of the best
+    const int resident = h->sm_count * std::min(occ_s, occ_v);
+    const int cmax = std::max(1, c.ny / (16 * t.rb));
+    auto cost_of = [&](int nc) {
+        const int rows = ((c.ny + nc - 1) / nc + t.rb - 1) / t.rb * t.rb;
+        const int ncr = (c.ny + rows - 1) / rows;
+        return (double)(((long long)t.ntx * ncr + resident - 1) / resident) * (rows / t.rb + 4.0);
+    };
+    double best_cost = 1e300;
+    for (int nc = 1; nc <= cmax; nc++) best_cost = std::min(best_cost, cost_of(nc));
+    int best = 1;
+    for (int nc = 1; nc <= cmax; nc++) if (cost_of(nc) <= 1.03 * best_cost) best = nc;
+    int nc = env_int("CPML_2D_CHUNKS", 0);
+    if (nc <= 0) nc = best;
+    nc = std::max(1, std::min(nc, cmax));
+    t.rows = ((c.ny + nc - 1) / nc + t.rb - 1) / t.rb * t.rb;
+    t.nchunks = (c.ny + t.rows - 1) / t.rows;
+    t.nitems = t.ntx * t.nchunks;
+    if (t.nitems > h->nblocks) FAIL(CPML_EINVAL, "internal: more 2-D work items than energy partial slots");
+    t.grid_stress = std::min(t.nitems, h->sm_count * occ_s);
+    t.grid_velocity = std::min(t.nitems, h->sm_count * occ_v);
+    return CPML_OK;
+}
+
 // Allocates the shell-only memory variables once every input is known.
 static int32_t finalize(cpml_handle *h)
 {
@@ -983,6 +1044,17 @@ static int32_t finalize(cpml_handle *h)
         else build_regions(h);
         CK(cudaMalloc(&h->d_partials, 2 * (size_t)std::max(1, h->nblocks) * sizeof(double)));
         CK(cudaMemset(h->d_partials, 0, 2 * (size_t)std::max(1, h->nblocks) * sizeof(double)));
+    }
+    if (c.ndim == 2 && !h->visco2d) {
+        // CPML_2D_KERNEL=pair keeps the one-launch-per-point kernels of kernels_2d.cu (A/B runs)
+        const char *k2 = getenv("CPML_2D_KERNEL");
+        h->ws2 = !(k2 && std::string(k2) == "pair");
+        if (h->ws2) {
+            const int32_t rc = setup_2d_ws(h); if (rc) return rc;
+            // energy partials: one slot per work item (the one-point geometry of create has 65536 slots at 4096 x 4096,
+            // which the one-block finisher k_post3d spent 43 us per step summing: 6 % of the step)
+            h->nblocks = h->tile2.nitems;
+        }
     }
     h->finalized = true;
     return CPML_OK;
@@ -1299,6 +1371,10 @@ static int32_t half_step(cpml_handle *h, int32_t it, int phase)
     } else if (h->visco2d) {
         if (phase == 0) launch_vstress2d(make_p2(h, it), h->grid, h->stream);
         else launch_vvelocity2d(make_p2(h, it), h->grid, h->stream);
+        h->n_launches++;
+    } else if (h->ws2) {
+        if (phase == 0) CK(launch_stress2d_ws(make_p2(h, it), h->maps2_stress, h->tile2, h->stream));
+        else CK(launch_velocity2d_ws(make_p2(h, it), h->maps2_velocity, h->tile2, h->stream));
         h->n_launches++;
     } else {
         if (phase == 0) launch_stress2d(make_p2(h, it), h->grid, h->block, h->stream);

@@ -210,6 +210,14 @@ struct SlabSync {
     unsigned int *timeout;                         // set when a poll gives up
 };
 
+// Work decomposition of the TMA-staged 2-D kernels (kernels_2d_ws.cu): strips of tx columns, marched along y in blocks
+// of rb rows; a work item is (strip, y chunk of `rows` rows).
+struct Tile2D {
+    int tx, rb;
+    int ntx, rows, nchunks, nitems;
+    int grid_stress, grid_velocity;
+};
+
 // One launch region of a 3-D kernel: the box [i0,i1] x [j0,j1] x [k0,k1] (1-based, k local).
 // The thread grid starts at ia <= i0 (ia-1 a multiple of 4, so warp rows stay 32-byte
 // sector aligned); lanes with i < i0 idle.
@@ -340,6 +348,10 @@ void launch_vstress3d(const ParamsV3D &p, dim3 grid, cudaStream_t s);
 void launch_vvelocity3d(const ParamsV3D &p, dim3 grid, cudaStream_t s);
 void visco_tile(int *tx, int *ty);
 int visco_stress_launches();
+void ws2_geometry(int *tx, int *rb, int (*box_stress)[2], int (*box_velocity)[2]);
+cudaError_t ws2_occupancy(int order, bool stress, int *occ);
+cudaError_t launch_stress2d_ws(const Params2D &p, const TmaMaps &tm, const Tile2D &t, cudaStream_t s);
+cudaError_t launch_velocity2d_ws(const Params2D &p, const TmaMaps &tm, const Tile2D &t, cudaStream_t s);
 void launch_stress2d(const Params2D &p, dim3 grid, dim3 block, cudaStream_t s);
 void launch_velocity2d(const Params2D &p, dim3 grid, dim3 block, cudaStream_t s);
 void launch_post2d(const Post2D &p, cudaStream_t s);

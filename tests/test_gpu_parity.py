@@ -298,8 +298,11 @@ def test_3d_default_grid_full_size_vs_timed_oracle():
 
 # ------------------------------------------------------------------ 2-D
 
+@pytest.mark.parametrize("kernel", ["ws", "pair"])
 @pytest.mark.parametrize("order", [2, 4])
-def test_2d_layered_matches_oracle_and_golden(order):
+def test_2d_layered_matches_oracle_and_golden(order, kernel, monkeypatch):
+    """Both 2-D kernel families: the TMA-staged y-marching kernels (ws, the default) and the pair kernels."""
+    monkeypatch.setenv("CPML_2D_KERNEL", kernel)
     c = refcfg.cfg2d(order, nx=83, ny=131, nstep=600, npml=8, material="layered", ydeb=600.0, yfin=200.0)
     g = np.load(os.path.join(GOLD, f"cpml2d_layered_order{order}.npz"))
     o = O.run_2d(**c, want_fields=True)
@@ -330,6 +333,26 @@ def test_2d_shipped_configuration_full_run(order):
     e = res["energy_kinetic"] + res["energy_potential"]
     assert e[-1] < 1e-6 * e.max()
     prog.solver.close()
+
+
+@pytest.mark.parametrize("order", [2, 4])
+@pytest.mark.parametrize("chunks,minb", [(1, 3), (3, 3), (5, 2)])
+def test_2d_ws_strips_and_chunks(order, chunks, minb, monkeypatch):
+    """The y-marching kernels on a grid with three x strips (the last one ragged), NY not a multiple of the row block,
+    heterogeneous medium, K_MAX_PML = 2 shells, for 1 / 3 / 5 y chunks (the chunk seams fall inside the wavefield):
+    fields bitwise, energies to summation order."""
+    monkeypatch.setenv("CPML_2D_CHUNKS", str(chunks))
+    monkeypatch.setenv("CPML_2D_WS_MINB", str(minb))
+    c = refcfg.cfg2d(order, nx=150, ny=203, nstep=500, npml=8, material="layered", ydeb=900.0, yfin=300.0, k_max=2.0)
+    o = O.run_2d(**c, want_fields=True)
+    with solver2d(c) as s:
+        s.run(1, c["nstep"])
+        check_traces(s.get_seismograms(), (o["sisvx"], o["sisvy"]))
+        for f, name in enumerate(F2):
+            assert np.array_equal(s.get_field(f), o[name]), name
+        _, ek, ep = s.get_energy()
+        assert refcfg.rel_l2(ek, o["energy_kinetic"]) <= TOL_ENERGY and refcfg.rel_l2(ep, o["energy_potential"]) <= TOL_ENERGY
+    assert np.abs(o["sisvx"]).max() > 1e-3
 
 
 def test_2d_kmax_quirk_b3_fourth_order():
