@@ -926,7 +926,7 @@ static int32_t setup_2d_ws(cpml_handle *h)
     t.ntx = (c.nx + t.tx - 1) / t.tx;
     // y chunks: rounds over the resident CTAs x (blocks per chunk + pipeline fill), finest within 3 % of the best
     const int resident = h->sm_count * std::min(occ_s, occ_v);
-    const int cmax = std::max(1, c.ny / (16 * t.rb));
+    const int cmax = std::max(1, c.ny / (8 * t.rb));
     auto cost_of = [&](int nc) {
         const int rows = ((c.ny + nc - 1) / nc + t.rb - 1) / t.rb * t.rb;
         const int ncr = (c.ny + rows - 1) / rows;

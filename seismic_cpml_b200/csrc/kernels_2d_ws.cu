@@ -356,15 +356,16 @@ k_velocity2d_ws(const __grid_constant__ Params2D p, const __grid_constant__ TmaM
 }
 
 // ---- launch dispatch ---------------------------------------------------------------
+// Geometry: 64-column strips in 4-row blocks (default) or 128-column strips in 2-row blocks (CPML_2D_WS_TX=128: longer
+// contiguous row segments per TMA box, twice the marching iterations); four ring stages, three CTAs per SM either way.
 
-constexpr int k2TX = 64, k2RB = 4, k2SLOTS = 4;
+constexpr int k2SLOTS = 4;
 
-template <int ORDER>
-static size_t ws2_smem(bool stress)
+static int ws2_tx()
 {
-    using G = Geom2<k2TX, k2RB>;
-    const size_t stage = stress ? 4 * G::TAP + 3 * G::PLAIN : 3 * G::TAP + 3 * G::PLAIN;
-    return kBarBytes + 128 + stage * k2SLOTS;
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("CPML_2D_WS_TX"); v = e ? atoi(e) : 64; if (v != 64 && v != 128) v = 64; }
+    return v;
 }
 
 static int ws2_minb()
@@ -374,35 +375,40 @@ static int ws2_minb()
     return v;
 }
 
-template <int ORDER, int MINB>
+template <int ORDER, int TX, int RB, int MINB>
 static cudaError_t ws2_launch(const Params2D &p, const TmaMaps &tm, const Tile2D &t, cudaStream_t s, bool stress, int *occ)
 {
-    const size_t smem = ws2_smem<ORDER>(stress);
-    constexpr int NT = (k2TX / 2) * k2RB + 32;
-    const void *fn = stress ? (const void *)k_stress2d_ws<ORDER, k2TX, k2RB, k2SLOTS, MINB> : (const void *)k_velocity2d_ws<ORDER, k2TX, k2RB, k2SLOTS, MINB>;
+    using G = Geom2<TX, RB>;
+    const size_t stage = stress ? 4 * G::TAP + 3 * G::PLAIN : 3 * G::TAP + 3 * G::PLAIN;
+    const size_t smem = kBarBytes + 128 + stage * k2SLOTS;
+    constexpr int NT = (TX / 2) * RB + 32;
+    const void *fn = stress ? (const void *)k_stress2d_ws<ORDER, TX, RB, k2SLOTS, MINB> : (const void *)k_velocity2d_ws<ORDER, TX, RB, k2SLOTS, MINB>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (occ) {
-        if (stress) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_stress2d_ws<ORDER, k2TX, k2RB, k2SLOTS, MINB>, NT, smem);
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_velocity2d_ws<ORDER, k2TX, k2RB, k2SLOTS, MINB>, NT, smem);
+        if (stress) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_stress2d_ws<ORDER, TX, RB, k2SLOTS, MINB>, NT, smem);
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_velocity2d_ws<ORDER, TX, RB, k2SLOTS, MINB>, NT, smem);
     }
     const int grid = stress ? t.grid_stress : t.grid_velocity;
-    if (stress) k_stress2d_ws<ORDER, k2TX, k2RB, k2SLOTS, MINB><<<grid, NT, smem, s>>>(p, tm, t);
-    else        k_velocity2d_ws<ORDER, k2TX, k2RB, k2SLOTS, MINB><<<grid, NT, smem, s>>>(p, tm, t);
+    if (stress) k_stress2d_ws<ORDER, TX, RB, k2SLOTS, MINB><<<grid, NT, smem, s>>>(p, tm, t);
+    else        k_velocity2d_ws<ORDER, TX, RB, k2SLOTS, MINB><<<grid, NT, smem, s>>>(p, tm, t);
     return cudaGetLastError();
 }
 
 template <int ORDER>
 static cudaError_t ws2_launch(const Params2D &p, const TmaMaps &tm, const Tile2D &t, cudaStream_t s, bool stress, int *occ)
 {
-    return ws2_minb() == 3 ? ws2_launch<ORDER, 3>(p, tm, t, s, stress, occ) : ws2_launch<ORDER, 2>(p, tm, t, s, stress, occ);
+    if (ws2_tx() == 128)
+        return ws2_minb() == 3 ? ws2_launch<ORDER, 128, 2, 3>(p, tm, t, s, stress, occ) : ws2_launch<ORDER, 128, 2, 2>(p, tm, t, s, stress, occ);
+    return ws2_minb() == 3 ? ws2_launch<ORDER, 64, 4, 3>(p, tm, t, s, stress, occ) : ws2_launch<ORDER, 64, 4, 2>(p, tm, t, s, stress, occ);
 }
 
 void ws2_geometry(int *tx, int *rb, int (*box_stress)[2], int (*box_velocity)[2])
 {
-    *tx = k2TX; *rb = k2RB;
-    const int bs[7][2] = {{k2TX + 4, k2RB}, {k2TX + 4, k2RB}, {k2TX + 4, k2RB}, {k2TX + 4, k2RB}, {k2TX, k2RB}, {k2TX, k2RB}, {k2TX, k2RB}};
-    const int bv[6][2] = {{k2TX + 4, k2RB}, {k2TX + 4, k2RB}, {k2TX + 4, k2RB}, {k2TX, k2RB}, {k2TX, k2RB}, {k2TX, k2RB}};
+    const int TX = ws2_tx(), RB = TX == 128 ? 2 : 4;
+    *tx = TX; *rb = RB;
+    const int bs[7][2] = {{TX + 4, RB}, {TX + 4, RB}, {TX + 4, RB}, {TX + 4, RB}, {TX, RB}, {TX, RB}, {TX, RB}};
+    const int bv[6][2] = {{TX + 4, RB}, {TX + 4, RB}, {TX + 4, RB}, {TX, RB}, {TX, RB}, {TX, RB}};
     for (int m = 0; m < 7; m++) { box_stress[m][0] = bs[m][0]; box_stress[m][1] = bs[m][1]; }
     for (int m = 0; m < 6; m++) { box_velocity[m][0] = bv[m][0]; box_velocity[m][1] = bv[m][1]; }
 }
