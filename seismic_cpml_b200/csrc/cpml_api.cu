@@ -924,18 +924,14 @@ static int32_t setup_2d_ws(cpml_handle *h)
         FAIL(CPML_ECUDA, "the TMA-staged 2-D kernels do not fit on this device");
     }
     t.ntx = (c.nx + t.tx - 1) / t.tx;
-    // y chunks: rounds over the resident CTAs x (blocks per chunk + pipeline fill), finest within 3 % of the best
+    // y chunks: SHORT ones, about ten row blocks each.  Measured at 4096 x 4096 (profiles/r02_g_bench_2d.txt): 6 chunks (one
+    // round of long items) 16.9 Gpts/s, 27 chunks 25.3, 64 chunks 26.8, 100 chunks 27.6 -- although every chunk re-reads two
+    // blocks of taps.  With few long items the CTAs of an SM start together and stay in phase (all waiting for the ring,
+    // then all computing); many short items put them out of phase and spread the rows in flight over the DRAM channels.
     const int resident = h->sm_count * std::min(occ_s, occ_v);
     const int cmax = std::max(1, c.ny / (8 * t.rb));
-    auto cost_of = [&](int nc) {
-        const int rows = ((c.ny + nc - 1) / nc + t.rb - 1) / t.rb * t.rb;
-        const int ncr = (c.ny + rows - 1) / rows;
-        return (double)(((long long)t.ntx * ncr + resident - 1) / resident) * (rows / t.rb + 4.0);
-    };
-    double best_cost = 1e300;
-    for (int nc = 1; nc <= cmax; nc++) best_cost = std::min(best_cost, cost_of(nc));
-    int best = 1;
-    for (int nc = 1; nc <= cmax; nc++) if (cost_of(nc) <= 1.03 * best_cost) best = nc;
+    const int best = std::max(1, std::min(cmax, (c.ny + 10 * t.rb - 1) / (10 * t.rb)));
+    (void)resident;
     int nc = env_int("CPML_2D_CHUNKS", 0);
     if (nc <= 0) nc = best;
     nc = std::max(1, std::min(nc, cmax));
