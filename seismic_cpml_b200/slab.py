@@ -159,6 +159,17 @@ class SlabDriver:
         self.b.step_velocity(it)
         self.b.step_finish(it)
 
+    def reset(self):
+        """cpml_reset on every slab for a second run.  Nobody resets while a neighbour may still be storing into its
+        halo planes, and nobody steps before every slab is reset (its first step writes into the neighbours' halos):
+        barriers on both sides, like the synchronisation around the zeroing of :720-756 in an MPI run."""
+        self.b.synchronize()
+        if self.nslabs > 1:
+            dist.barrier(group=self.group)
+        self.b.reset()
+        if self.nslabs > 1:
+            dist.barrier(group=self.group)
+
     def run(self, it_begin: int, it_end: int):
         for it in range(it_begin, it_end + 1):
             self.step(it)
