@@ -67,7 +67,7 @@ struct cpml_handle {
     float *dprof_f[3][6] = {};     // single-precision copies of the profiles
     double *d_scratch = nullptr;   // one padded plane in double: single-precision planes are converted here for the getters
     bool use_ws = false;           // ... with a producer warp and in-kernel slab ordering (kernels_3d_ws.cu, the default)
-    unsigned int *d_bcount = nullptr;   // [2] boundary-item counters of the in-kernel slab ordering
+    unsigned int *d_bcount = nullptr;   // [0..1] boundary-item counters of the in-kernel slab ordering, [2..5] two work queues
     TmaMaps maps_stress{}, maps_velocity{};
     Tile3D tile{}, tile_stress{};        // velocity kernel (also: energy partial slots) / stress kernel
 
@@ -297,8 +297,8 @@ static int32_t create_impl(cpml_handle *h)
     CK(cudaMemset(h->flags, 0, 16 * sizeof(double)));          // zeroed once: cpml_reset leaves the flag words alone
     CK(cudaMalloc(&h->d_timeout, sizeof(unsigned int)));
     CK(cudaMemset(h->d_timeout, 0, sizeof(unsigned int)));
-    CK(cudaMalloc(&h->d_bcount, 2 * sizeof(unsigned int)));
-    CK(cudaMemset(h->d_bcount, 0, 2 * sizeof(unsigned int)));
+    CK(cudaMalloc(&h->d_bcount, 8 * sizeof(unsigned int)));
+    CK(cudaMemset(h->d_bcount, 0, 8 * sizeof(unsigned int)));
     if (c.ndim == 2)
         for (int m = 0; m < 3; m++) CK(cudaMalloc(&h->mat[m], h->field_doubles * sizeof(double)));
 
@@ -457,7 +457,7 @@ extern "C" int32_t cpml_reset(cpml_handle *h)
     // published there (slab drivers put a barrier between the last step of a run, the resets and the first step)
     CK(cudaMemsetAsync(h->arena, 0, h->flags_offset * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->d_timeout, 0, sizeof(unsigned int), h->stream));
-    CK(cudaMemsetAsync(h->d_bcount, 0, 2 * sizeof(unsigned int), h->stream));
+    CK(cudaMemsetAsync(h->d_bcount, 0, 8 * sizeof(unsigned int), h->stream));
     h->epoch++;
     if (h->finalized) {
         for (int m = 0; m < 6; m++) {
@@ -707,9 +707,18 @@ static int32_t encode_plane_map(cpml_handle *h, EncodeTiledFn enc, CUtensorMap *
 // 101-wide default grid the stress kernel is fastest on 104 x 7 tiles (384 threads = 12 warps, three per SM
 // sub-partition: 168 registers instead of 128, no spills; 1.02 ms against 1.12 ms), the velocity kernel on
 // 104 x 8 (1.04 ms against 1.10 ms) -- profiles/r01_v8_tile_104x7.txt.
+// Work queue `which` (0 / 1) of the persistent kernels, or null for static shares (CPML_SCHED=static).
+static unsigned int *work_queue(const cpml_handle *h, int which)
+{
+    const char *e = getenv("CPML_SCHED");
+    if (e && !strcmp(e, "static")) return nullptr;
+    return h->d_bcount + 2 + 2 * which;
+}
+
 static int32_t build_tile(cpml_handle *h, EncodeTiledFn enc, bool stress, Tile3D &t, TmaMaps &maps)
 {
     const cpml_config &c = h->cfg;
+    t.queue = h->use_ws ? work_queue(h, stress ? 1 : 0) : nullptr;
     // thread tile = TMA box.  Narrow grids (the reference's NX = 101) take one 104-wide tile per row, wide
     // grids 128 x 8: the width that wastes the fewest columns (ties: the wider one), measured in
     // profiles/r01_v5_tile_sweep.txt; one CTA per SM, two-plane ring.  CPML_TX / CPML_TY / CPML_STAGES /
@@ -834,6 +843,7 @@ static int32_t setup_visco_ws(cpml_handle *h)
     if (!fn || qres != cudaDriverEntryPointSuccess) FAIL(CPML_ECUDA, "driver does not export cuTensorMapEncodeTiled");
     const EncodeTiledFn enc = (EncodeTiledFn)fn;
     Tile3D &t = h->vtile;
+    t.queue = work_queue(h, 0);
     int best_tx = 104;
     for (int cand : {108, 64}) {      // the width that wastes the fewest columns
         const int w_best = (c.nx + best_tx - 1) / best_tx * best_tx, w = (c.nx + cand - 1) / cand * cand;
@@ -901,6 +911,7 @@ static int32_t setup_2d_ws(cpml_handle *h)
     if (!fn || qres != cudaDriverEntryPointSuccess) FAIL(CPML_ECUDA, "driver does not export cuTensorMapEncodeTiled");
     const EncodeTiledFn enc = (EncodeTiledFn)fn;
     Tile2D &t = h->tile2;
+    t.queue = work_queue(h, 0);
     int bs[7][2], bv[6][2];
     ws2_geometry(&t.tx, &t.rb, bs, bv);
     auto encode = [&](CUtensorMap *out, double *base, const int (&box)[2]) -> int32_t {

@@ -195,6 +195,7 @@ struct Tile3D {
     int minb;                 // resident CTAs per SM the kernel variant is compiled for
     int xm_bytes;             // per stage and variable: x-shell memory variables of the tile rows (0: no x shell)
     int grid_stress, grid_velocity;
+    unsigned int *queue;      // [2] work queue of the persistent kernels (tma_common.cuh: claim_item); null: static shares
 };
 
 // Slab-to-slab ordering done INSIDE the update kernels (kernels_3d_ws.cu): the work items that read a halo plane
@@ -216,6 +217,7 @@ struct Tile2D {
     int tx, rb;
     int ntx, rows, nchunks, nitems;
     int grid_stress, grid_velocity;
+    unsigned int *queue;      // work queue of the persistent kernels (see Tile3D)
 };
 
 // One launch region of a 3-D kernel: the box [i0,i1] x [j0,j1] x [k0,k1] (1-based, k local).

@@ -86,23 +86,32 @@ k_stress2d_ws(const __grid_constant__ Params2D p, const __grid_constant__ TmaMap
     constexpr int O_VX = 0, O_VY = G::TAP, O_LAM = 2 * G::TAP, O_MU = 3 * G::TAP, O_SXX = 4 * G::TAP, O_SYY = O_SXX + G::PLAIN,
                   O_SXY = O_SYY + G::PLAIN;
     __shared__ double red[NC / 32 + 1];
+    __shared__ unsigned long long item_bar;
+    __shared__ int item_slot[2];          // the producer posts the CTA's work items here (tma_common.cuh: claim_item)
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t sbase = (smem_u32(smem_dyn) + 127u) & ~127u;
     const unsigned char *gbase = smem_dyn + (sbase - smem_u32(smem_dyn));
     const uint32_t bar = sbase, ring = sbase + kBarBytes;
     const unsigned char *gring = gbase + kBarBytes;
 
+    const uint32_t barI = smem_u32(&item_bar);
+
     const int tid = (int)threadIdx.x;
     if (tid == 0) {
         for (int s = 0; s < SLOTS; s++) mbar_init(bar + 8 * s, 1);
+        mbar_init(barI, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     if (tid >= NC) {        // ================================================================ producer warp
         const bool lead = tid == NC;
-        uint32_t slot = 0, cnt = 0;
-        for (int item = blockIdx.x; item < t.nitems; item += gridDim.x) {
+        uint32_t slot = 0, cnt = 0, ip = 0;
+        int item = (int)blockIdx.x;
+        while (true) {
+            if (lead) { item_slot[ip & 1u] = item; mbar_arrive(barI); }     // slot ip & 1 was last read two items ago
+            ++ip;
+            if (item >= t.nitems) break;
             const int tix = item % t.ntx, yc = item / t.ntx;
             const int xt = 16 + tix * TX - 2;                     // tensor x of column i0 - 2 (padded arrays: x offset 16)
             const int jb = 1 + yc * t.rows;
@@ -127,13 +136,17 @@ k_stress2d_ws(const __grid_constant__ Params2D p, const __grid_constant__ TmaMap
                 uint32_t s = slot;
                 for (int l = 0; l < min(SLOTS, nb + 2); l++) { issue(s, l - 1); if (++s == SLOTS) s = 0; }
             }
+            int next = item + (int)gridDim.x;
+            if (lead) next = claim_item(t.queue, next);       // the answer is needed after the row-block loop
             // iteration n frees the stage of block n-1; iterations nb, nb+1 free the last two
             for (int n = 0; n < nb + 2; ++n, ++cnt) {
                 bar2_sync(k2RelBar0 + (int)(cnt & 3u), NALL);
                 if (lead && n - 1 + SLOTS <= nb) issue(slot, n - 1 + SLOTS);
                 if (++slot == SLOTS) slot = 0;
             }
+            item = __shfl_sync(0xffffffffu, next, 0);
         }
+        if (lead) retire_queue(t.queue);
         return;
     }
 
@@ -142,7 +155,10 @@ k_stress2d_ws(const __grid_constant__ Params2D p, const __grid_constant__ TmaMap
     const int cW = 2 * tx + 2, cP = 2 * tx;
     RingPos pos{0, 0};                    // stage of block -1 of the current item
     uint32_t cnt = 0;
-    for (int item = blockIdx.x; item < t.nitems; item += gridDim.x) {
+    for (uint32_t ip = 0;; ++ip) {
+        mbar_wait(barI, ip & 1u);
+        const int item = item_slot[ip & 1u];
+        if (item >= t.nitems) break;
         const int tix = item % t.ntx, yc = item / t.ntx;
         const int i = 1 + tix * TX + 2 * tx;                      // A; B = i + 1
         const int jb = 1 + yc * t.rows;
@@ -227,23 +243,32 @@ k_velocity2d_ws(const __grid_constant__ Params2D p, const __grid_constant__ TmaM
     constexpr int STAGE = 3 * G::TAP + 3 * G::PLAIN;
     constexpr int O_SXX = 0, O_SXY = G::TAP, O_RHO = 2 * G::TAP, O_SYY = 3 * G::TAP, O_VX = O_SYY + G::PLAIN, O_VY = O_VX + G::PLAIN;
     __shared__ double red[NC / 32 + 1];
+    __shared__ unsigned long long item_bar;
+    __shared__ int item_slot[2];          // the producer posts the CTA's work items here (tma_common.cuh: claim_item)
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t sbase = (smem_u32(smem_dyn) + 127u) & ~127u;
     const unsigned char *gbase = smem_dyn + (sbase - smem_u32(smem_dyn));
     const uint32_t bar = sbase, ring = sbase + kBarBytes;
     const unsigned char *gring = gbase + kBarBytes;
 
+    const uint32_t barI = smem_u32(&item_bar);
+
     const int tid = (int)threadIdx.x;
     if (tid == 0) {
         for (int s = 0; s < SLOTS; s++) mbar_init(bar + 8 * s, 1);
+        mbar_init(barI, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     if (tid >= NC) {        // ================================================================ producer warp
         const bool lead = tid == NC;
-        uint32_t slot = 0, cnt = 0;
-        for (int item = blockIdx.x; item < t.nitems; item += gridDim.x) {
+        uint32_t slot = 0, cnt = 0, ip = 0;
+        int item = (int)blockIdx.x;
+        while (true) {
+            if (lead) { item_slot[ip & 1u] = item; mbar_arrive(barI); }     // slot ip & 1 was last read two items ago
+            ++ip;
+            if (item >= t.nitems) break;
             const int tix = item % t.ntx, yc = item / t.ntx;
             const int xt = 16 + tix * TX - 2;
             const int jb = 1 + yc * t.rows;
@@ -267,12 +292,16 @@ k_velocity2d_ws(const __grid_constant__ Params2D p, const __grid_constant__ TmaM
                 uint32_t s = slot;
                 for (int l = 0; l < min(SLOTS, nb + 2); l++) { issue(s, l - 1); if (++s == SLOTS) s = 0; }
             }
+            int next = item + (int)gridDim.x;
+            if (lead) next = claim_item(t.queue, next);       // the answer is needed after the row-block loop
             for (int n = 0; n < nb + 2; ++n, ++cnt) {
                 bar2_sync(k2RelBar0 + (int)(cnt & 3u), NALL);
                 if (lead && n - 1 + SLOTS <= nb) issue(slot, n - 1 + SLOTS);
                 if (++slot == SLOTS) slot = 0;
             }
+            item = __shfl_sync(0xffffffffu, next, 0);
         }
+        if (lead) retire_queue(t.queue);
         return;
     }
 
@@ -281,7 +310,10 @@ k_velocity2d_ws(const __grid_constant__ Params2D p, const __grid_constant__ TmaM
     const int cW = 2 * tx + 2, cP = 2 * tx;
     RingPos pos{0, 0};
     uint32_t cnt = 0;
-    for (int item = blockIdx.x; item < t.nitems; item += gridDim.x) {
+    for (uint32_t ip = 0;; ++ip) {
+        mbar_wait(barI, ip & 1u);
+        const int item = item_slot[ip & 1u];
+        if (item >= t.nitems) break;
         const int tix = item % t.ntx, yc = item / t.ntx;
         const int i = 1 + tix * TX + 2 * tx;
         const int jb = 1 + yc * t.rows;

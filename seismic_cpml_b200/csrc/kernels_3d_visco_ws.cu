@@ -92,6 +92,8 @@ k_vvelocity3d_ws(const __grid_constant__ ParamsV3D p, const __grid_constant__ Tm
 
     __shared__ double red[NC / 32];
     __shared__ double Cx[8 * TX];        // a, b, K, 1/K, a_half, b_half, K_half, 1/K_half of the tile's columns
+    __shared__ unsigned long long item_bar;
+    __shared__ int item_slot[2];         // the producer posts the CTA's work items here (tma_common.cuh: claim_item)
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t sbase = (smem_u32(smem_dyn) + 127u) & ~127u;
     const unsigned char *gbase = smem_dyn + (sbase - smem_u32(smem_dyn));
@@ -100,10 +102,13 @@ k_vvelocity3d_ws(const __grid_constant__ ParamsV3D p, const __grid_constant__ Tm
     const uint32_t ringN = sbase + kBarBytes, ringC = ringN + SN * G::NBYTES;
     const unsigned char *gN = gbase + kBarBytes, *gC = gN + (size_t)SN * G::NBYTES;
 
+    const uint32_t barI = smem_u32(&item_bar);
+
     const int tid = (int)threadIdx.x;
     if (tid == 0) {
         for (uint32_t s = 0; s < SN; s++) mbar_init(barN + 8 * s, 1);
         for (uint32_t s = 0; s < SC; s++) mbar_init(barC + 8 * s, 1);
+        mbar_init(barI, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -111,8 +116,12 @@ k_vvelocity3d_ws(const __grid_constant__ ParamsV3D p, const __grid_constant__ Tm
     // ================================================================ producer warp
     if (tid >= NC) {
         const bool lead = tid == NC;
-        uint32_t sn = 0, sc = 0;
-        for (int item = blockIdx.x; item < t.nitems; item += gridDim.x) {
+        uint32_t sn = 0, sc = 0, ip = 0;
+        int item = (int)blockIdx.x;
+        while (true) {
+            if (lead) { item_slot[ip & 1u] = item; mbar_arrive(barI); }     // slot ip & 1 was last read two items ago
+            ++ip;
+            if (item >= t.nitems) break;
             const int tix = item % t.ntx, rest = item / t.ntx, tiy = rest % t.nty, zc = rest / t.nty;
             // tensor coordinates of element (i0, j0, k): x = 16 + (i0-1), y = 2 + (j0-1), z = k + 1 (padded arrays)
             const int xt = 16 + tix * TX, yt = 2 + tiy * TY, j0 = 1 + tiy * TY;
@@ -148,6 +157,8 @@ k_vvelocity3d_ws(const __grid_constant__ ParamsV3D p, const __grid_constant__ Tm
                 s = sc;
                 for (int l = 0; l < min((int)SC, np); l++) { issue_c(s, kb + l); if (++s == SC) s = 0; }
             }
+            int next = item + (int)gridDim.x;
+            if (lead) next = claim_item(t.queue, next);      // the answer is needed after the plane loop
             for (int n = 0; n < np; ++n) {
                 vbar_sync(kVRelBar0 + (int)sc, NALL);
                 if (lead) {
@@ -158,7 +169,9 @@ k_vvelocity3d_ws(const __grid_constant__ ParamsV3D p, const __grid_constant__ Tm
                 if (++sc == SC) sc = 0;
             }
             if (++sn == SN) sn = 0;
+            item = __shfl_sync(0xffffffffu, next, 0);
         }
+        if (lead) retire_queue(t.queue);
         return;
     }
 
@@ -173,7 +186,10 @@ k_vvelocity3d_ws(const __grid_constant__ ParamsV3D p, const __grid_constant__ Tm
     const double odx = p.odx, ody = p.ody, odz = p.odz, dt_r = p.dt_over_rho;
 
     RingPos rn{0, 0}, rc{0, 0};
-    for (int item = blockIdx.x; item < t.nitems; item += gridDim.x) {
+    for (uint32_t ip = 0;; ++ip) {
+        mbar_wait(barI, ip & 1u);
+        const int item = item_slot[ip & 1u];
+        if (item >= t.nitems) break;
         const int tix = item % t.ntx, rest = item / t.ntx, tiy = rest % t.nty, zc = rest / t.nty;
         const int i0 = 1 + tix * TX, j0 = 1 + tiy * TY;
         const int kb = 1 + zc * t.kchunk;

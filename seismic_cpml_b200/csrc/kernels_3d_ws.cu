@@ -127,6 +127,8 @@ k_stress3d_ws(const __grid_constant__ Params3DT<T> p, const __grid_constant__ Tm
     const uint32_t CSTAGE = CBYTES + 3 * XMB;
 
     __shared__ T Cx[6 * TX];                                   // x coefficients of the tile's columns
+    __shared__ unsigned long long item_bar;
+    __shared__ int item_slot[2];                               // the producer posts the CTA's work items here
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t sbase = (smem_u32(smem_dyn) + 127u) & ~127u;
     const unsigned char *gbase = smem_dyn + (sbase - smem_u32(smem_dyn));
@@ -135,10 +137,13 @@ k_stress3d_ws(const __grid_constant__ Params3DT<T> p, const __grid_constant__ Tm
     const uint32_t ringN = sbase + kBarBytes, ringC = ringN + SN * NBYTES;
     const unsigned char *gN = gbase + kBarBytes, *gC = gN + (size_t)SN * NBYTES;
 
+    const uint32_t barI = smem_u32(&item_bar);                      // "work item it & 1 has been posted"
+
     const int tid = (int)threadIdx.x;
     if (tid == 0) {
         for (uint32_t s = 0; s < SN; s++) mbar_init(barN + 8 * s, 1);
         for (uint32_t s = 0; s < SC; s++) mbar_init(barC + 8 * s, 1);
+        mbar_init(barI, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -146,8 +151,13 @@ k_stress3d_ws(const __grid_constant__ Params3DT<T> p, const __grid_constant__ Tm
     // ================================================================ producer warp
     if (tid >= NC) {
         const bool lead = tid == NC;
-        uint32_t sn = 0, sc = 0;
-        for (int item = blockIdx.x; item < t.nitems; item += gridDim.x) {
+        uint32_t sn = 0, sc = 0, ip = 0;
+        int item = (int)blockIdx.x;
+        while (true) {
+            // post the item (or the end mark) to the consumers; slot ip & 1 was last read two items ago
+            if (lead) { item_slot[ip & 1u] = item; mbar_arrive(barI); }
+            ++ip;
+            if (item >= t.nitems) break;
             const Item it = decode_item(item, t);
             const int x0 = it.tix * TX, y0 = it.tiy * TY, j0 = 1 + y0;
             const int kb = 1 + it.zc * t.kchunk;
@@ -181,6 +191,8 @@ k_stress3d_ws(const __grid_constant__ Params3DT<T> p, const __grid_constant__ Tm
                 s = sc;
                 for (int l = 0; l < min((int)SC, np); l++) { issue_c(s, kb + l); if (++s == SC) s = 0; }
             }
+            int next = item + (int)gridDim.x;
+            if (lead) next = claim_item(t.queue, next);      // the answer is needed after the plane loop
             for (int n = 0; n < np; ++n) {
                 bar_sync(kRelBar0 + (int)sc, NALL);                 // every consumer has read plane kb+n out of the stages
                 if (lead) {
@@ -191,7 +203,9 @@ k_stress3d_ws(const __grid_constant__ Params3DT<T> p, const __grid_constant__ Tm
                 if (++sc == SC) sc = 0;
             }
             if (++sn == SN) sn = 0;        // plane ke+1 of ring N has been consumed as "next" only
+            item = __shfl_sync(0xffffffffu, next, 0);
         }
+        if (lead) retire_queue(t.queue);
         return;
     }
 
@@ -206,7 +220,10 @@ k_stress3d_ws(const __grid_constant__ Params3DT<T> p, const __grid_constant__ Tm
     const int oc = ty * TX + 2 * tx;     // plain tile
 
     RingPos rn{0, 0}, rc{0, 0};          // stage of the current plane in each ring
-    for (int item = blockIdx.x; item < t.nitems; item += gridDim.x) {
+    for (uint32_t ip = 0;; ++ip) {
+        mbar_wait(barI, ip & 1u);
+        const int item = item_slot[ip & 1u];
+        if (item >= t.nitems) break;
         const Item itm = decode_item(item, t);
         const int i0 = 1 + itm.tix * TX, j0 = 1 + itm.tiy * TY;
         const int kb = 1 + itm.zc * t.kchunk;
@@ -373,6 +390,8 @@ k_velocity3d_ws(const __grid_constant__ Params3DT<T> p, const __grid_constant__ 
 
     __shared__ double red[2 * (NC / 32)];
     __shared__ T Cx[6 * TX];                                   // x coefficients of the tile's columns
+    __shared__ unsigned long long item_bar;
+    __shared__ int item_slot[2];                               // the producer posts the CTA's work items here
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t sbase = (smem_u32(smem_dyn) + 127u) & ~127u;
     const unsigned char *gbase = smem_dyn + (sbase - smem_u32(smem_dyn));
@@ -381,10 +400,13 @@ k_velocity3d_ws(const __grid_constant__ Params3DT<T> p, const __grid_constant__ 
     const uint32_t ringN = sbase + kBarBytes, ringC = ringN + SN * NBYTES;
     const unsigned char *gN = gbase + kBarBytes, *gC = gN + (size_t)SN * NBYTES;
 
+    const uint32_t barI = smem_u32(&item_bar);                      // "work item it & 1 has been posted"
+
     const int tid = (int)threadIdx.x;
     if (tid == 0) {
         for (uint32_t s = 0; s < SN; s++) mbar_init(barN + 8 * s, 1);
         for (uint32_t s = 0; s < SC; s++) mbar_init(barC + 8 * s, 1);
+        mbar_init(barI, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -392,8 +414,13 @@ k_velocity3d_ws(const __grid_constant__ Params3DT<T> p, const __grid_constant__ 
     // ================================================================ producer warp
     if (tid >= NC) {
         const bool lead = tid == NC;
-        uint32_t sn = 0, sc = 0;
-        for (int item = blockIdx.x; item < t.nitems; item += gridDim.x) {
+        uint32_t sn = 0, sc = 0, ip = 0;
+        int item = (int)blockIdx.x;
+        while (true) {
+            // post the item (or the end mark) to the consumers; slot ip & 1 was last read two items ago
+            if (lead) { item_slot[ip & 1u] = item; mbar_arrive(barI); }
+            ++ip;
+            if (item >= t.nitems) break;
             const Item it = decode_item(item, t);
             const int x0 = it.tix * TX, y0 = it.tiy * TY, j0 = 1 + y0;
             const int kb = 1 + it.zc * t.kchunk;
@@ -430,6 +457,8 @@ k_velocity3d_ws(const __grid_constant__ Params3DT<T> p, const __grid_constant__ 
                 s = sc;
                 for (int l = 0; l < min((int)SC, np); l++) { issue_c(s, kb + l); if (++s == SC) s = 0; }
             }
+            int next = item + (int)gridDim.x;
+            if (lead) next = claim_item(t.queue, next);      // the answer is needed after the plane loop
             for (int n = 0; n < np; ++n) {
                 bar_sync(kRelBar0 + (int)sc, NALL);
                 if (lead) {
@@ -440,7 +469,9 @@ k_velocity3d_ws(const __grid_constant__ Params3DT<T> p, const __grid_constant__ 
                 if (++sc == SC) sc = 0;
             }
             if (++sn == SN) sn = 0;
+            item = __shfl_sync(0xffffffffu, next, 0);
         }
+        if (lead) retire_queue(t.queue);
         return;
     }
 
@@ -455,7 +486,10 @@ k_velocity3d_ws(const __grid_constant__ Params3DT<T> p, const __grid_constant__ 
     const int oc = ty * TX + 2 * tx;
 
     RingPos rn{0, 0}, rc{0, 0};
-    for (int item = blockIdx.x; item < t.nitems; item += gridDim.x) {
+    for (uint32_t ip = 0;; ++ip) {
+        mbar_wait(barI, ip & 1u);
+        const int item = item_slot[ip & 1u];
+        if (item >= t.nitems) break;
         const Item itm = decode_item(item, t);
         const int i0 = 1 + itm.tix * TX, j0 = 1 + itm.tiy * TY;
         const int kb = 1 + itm.zc * t.kchunk;

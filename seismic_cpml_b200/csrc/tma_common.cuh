@@ -51,6 +51,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 // Bounded wait: a TMA that never lands (bad descriptor) traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
@@ -58,6 +62,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     while (!mbar_try_wait(bar, parity))
         if (++spins > (1u << 24)) __trap();
 }
+// Work items of the persistent kernels are handed out through a queue in global memory (queue[0]: items claimed
+// beyond the first one of every CTA, queue[1]: CTAs that have finished): an SM that gets more of the HBM bandwidth
+// takes more items, so the CTAs finish within one item of each other instead of idling behind the slowest static
+// share (ncu, static shares: the SMs were idle 6-19 % of a kernel).  Items are claimed in increasing order, which
+// keeps "boundary chunks first".  queue == nullptr: static shares (item += gridDim.x).
+__device__ __forceinline__ int claim_item(unsigned int *queue, int static_next)
+{
+    return queue ? (int)(gridDim.x + atomicAdd(queue, 1u)) : static_next;
+}
+// One thread per CTA, after the CTA's last claim: the last CTA to retire re-arms the queue for the next launch
+// (kernels sharing a queue never overlap).
+__device__ __forceinline__ void retire_queue(unsigned int *queue)
+{
+    if (!queue) return;
+    const unsigned int done = atomicAdd(queue + 1, 1u);
+    if (done == gridDim.x - 1) { queue[0] = 0u; queue[1] = 0u; }
+}
+
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int x, int y, int z, uint32_t bar)
 {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
