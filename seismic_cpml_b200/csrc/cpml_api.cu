@@ -812,7 +812,21 @@ static int32_t build_tile(cpml_handle *h, EncodeTiledFn enc, bool stress, Tile3D
     nzc = std::max(1, std::min(nzc, h->nzl));
     t.kchunk = (h->nzl + nzc - 1) / nzc;
     t.nzc = (h->nzl + t.kchunk - 1) / t.kchunk;
-    t.nitems = tiles * t.nzc;
+    // finer tail (producer-warp kernels with the work queue): the last 1.5 x resident-CTAs coarse items (measured:
+    // profiles/r02_k_bench_finer_tail.txt; CPML_TAIL_ITEMS_PCT, CPML_TAIL_SPLIT for A/B runs) -- never the two
+    // boundary chunks, which are first in the list -- are split into items of >= 8 planes (decode_item)
+    const int coarse = tiles * t.nzc;
+    t.split = 1;
+    t.fine_from = coarse;
+    if (h->use_ws && t.queue && t.nzc >= 3) {
+        const int sp = env_int("CPML_TAIL_SPLIT", std::min(4, t.kchunk / 8));       // (1: no finer tail)
+        if (sp >= 2 && sp <= 8 && (sp - 1) * ((t.kchunk + sp - 1) / sp) < t.kchunk) {  // every part holds a plane
+            t.split = sp;
+            const int pct = std::max(0, env_int("CPML_TAIL_ITEMS_PCT", 150));      // coarse items split, % of the resident CTAs
+            t.fine_from = coarse - std::min(coarse - 2 * tiles, (int)((long long)resident * pct / 100));
+        }
+    }
+    t.nitems = t.fine_from + (coarse - t.fine_from) * t.split;
     t.grid_stress = t.grid_velocity = std::min(t.nitems, h->sm_count * occ);
     return CPML_OK;
 }

@@ -190,7 +190,8 @@ struct Tile3D {
     int tx, ty;               // thread tile = box size
     int ntx, nty;             // tiles per plane
     int kchunk, nzc;          // planes per item, z chunks
-    int nitems;               // ntx * nty * nzc (= energy partial slots)
+    int nitems;               // work items (= energy partial slots): ntx * nty * nzc, more with a finer tail
+    int fine_from, split;     // kernels_3d_ws.cu: coarse items >= fine_from are `split` items each (split = 1: none)
     int stages;               // shared-memory ring depth (planes)
     int minb;                 // resident CTAs per SM the kernel variant is compiled for
     int xm_bytes;             // per stage and variable: x-shell memory variables of the tile rows (0: no x shell)

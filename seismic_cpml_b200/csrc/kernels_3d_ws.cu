@@ -90,17 +90,34 @@ __device__ __forceinline__ void publish_side(unsigned int *counter, int n_items,
     }
 }
 
-// Work item -> (x tile, y tile, z chunk).  Chunk order 0, nzc-1, 1, 2, ...: both boundary chunks first (see above).
-struct Item { int tix, tiy, zc; };
-__device__ __forceinline__ Item decode_item(int item, const Tile3D &t)
+// Work item -> (x tile, y tile, planes kb..ke).  Chunk order 0, nzc-1, 1, 2, ...: both boundary chunks first (see
+// above).  The items at the END of the list are finer: every coarse item from t.fine_from on is t.split items of
+// kchunk / split planes.  With the queue the CTAs finish within one item of each other, so the idle tail of a launch is
+// about half an item per SM; short items at the end cut it without paying their start-up cost everywhere.
+struct Item { int tix, tiy, kb, ke; };
+__device__ __forceinline__ Item decode_item(int item, const Tile3D &t, int nzl)
 {
-    Item r;
-    r.tix = item % t.ntx;
-    const int rest = item / t.ntx;
-    r.tiy = rest % t.nty;
+    int ci = item, part = 0;
+    const bool fine = item >= t.fine_from;
+    if (fine) {
+        const int r = item - t.fine_from, c = r / t.split;
+        ci = t.fine_from + c;
+        part = r - c * t.split;
+    }
+    Item it;
+    it.tix = ci % t.ntx;
+    const int rest = ci / t.ntx;
+    it.tiy = rest % t.nty;
     const int o = rest / t.nty;
-    r.zc = (o == 0) ? 0 : (o == 1) ? t.nzc - 1 : o - 1;
-    return r;
+    const int zc = (o == 0) ? 0 : (o == 1) ? t.nzc - 1 : o - 1;
+    it.kb = 1 + zc * t.kchunk;
+    it.ke = min(nzl, it.kb + t.kchunk - 1);
+    if (fine) {     // (never a boundary chunk, never the short last chunk: the host keeps those whole)
+        const int sub = (t.kchunk + t.split - 1) / t.split;
+        it.kb += part * sub;
+        it.ke = min(it.ke, it.kb + sub - 1);
+    }
+    return it;
 }
 
 }  // namespace
@@ -158,10 +175,9 @@ k_stress3d_ws(const __grid_constant__ Params3DT<T> p, const __grid_constant__ Tm
             if (lead) { item_slot[ip & 1u] = item; mbar_arrive(barI); }
             ++ip;
             if (item >= t.nitems) break;
-            const Item it = decode_item(item, t);
+            const Item it = decode_item(item, t, p.nzl);
             const int x0 = it.tix * TX, y0 = it.tiy * TY, j0 = 1 + y0;
-            const int kb = 1 + it.zc * t.kchunk;
-            const int ke = min(p.nzl, kb + t.kchunk - 1);
+            const int kb = it.kb, ke = it.ke;
             const int np = ke - kb + 1;
             const bool tile_xpml = XMB != 0 && ((x0 + 1 <= p.xlo) || (x0 + TX >= p.xhi));
             auto issue_n = [&](uint32_t s, int kk) {
@@ -224,10 +240,9 @@ k_stress3d_ws(const __grid_constant__ Params3DT<T> p, const __grid_constant__ Tm
         mbar_wait(barI, ip & 1u);
         const int item = item_slot[ip & 1u];
         if (item >= t.nitems) break;
-        const Item itm = decode_item(item, t);
+        const Item itm = decode_item(item, t, p.nzl);
         const int i0 = 1 + itm.tix * TX, j0 = 1 + itm.tiy * TY;
-        const int kb = 1 + itm.zc * t.kchunk;
-        const int ke = min(p.nzl, kb + t.kchunk - 1);
+        const int kb = itm.kb, ke = itm.ke;
         const int np = ke - kb + 1;
         const bool tile_xpml = XMB != 0 && ((i0 <= p.xlo) || (i0 + TX - 1 >= p.xhi));
         // plane 0 (vz of the lower neighbour) is read straight from global memory below
@@ -421,10 +436,9 @@ k_velocity3d_ws(const __grid_constant__ Params3DT<T> p, const __grid_constant__ 
             if (lead) { item_slot[ip & 1u] = item; mbar_arrive(barI); }
             ++ip;
             if (item >= t.nitems) break;
-            const Item it = decode_item(item, t);
+            const Item it = decode_item(item, t, p.nzl);
             const int x0 = it.tix * TX, y0 = it.tiy * TY, j0 = 1 + y0;
-            const int kb = 1 + it.zc * t.kchunk;
-            const int ke = min(p.nzl, kb + t.kchunk - 1);
+            const int kb = it.kb, ke = it.ke;
             const int np = ke - kb + 1;
             const bool tile_xpml = XMB != 0 && ((x0 + 1 <= p.xlo) || (x0 + TX >= p.xhi));
             auto issue_n = [&](uint32_t s, int kk) {
@@ -490,10 +504,9 @@ k_velocity3d_ws(const __grid_constant__ Params3DT<T> p, const __grid_constant__ 
         mbar_wait(barI, ip & 1u);
         const int item = item_slot[ip & 1u];
         if (item >= t.nitems) break;
-        const Item itm = decode_item(item, t);
+        const Item itm = decode_item(item, t, p.nzl);
         const int i0 = 1 + itm.tix * TX, j0 = 1 + itm.tiy * TY;
-        const int kb = 1 + itm.zc * t.kchunk;
-        const int ke = min(p.nzl, kb + t.kchunk - 1);
+        const int kb = itm.kb, ke = itm.ke;
         const int np = ke - kb + 1;
         const bool tile_xpml = XMB != 0 && ((i0 <= p.xlo) || (i0 + TX - 1 >= p.xhi));
         // plane 0 (sigmaxz, sigmayz of the lower neighbour) is read straight from global memory below

@@ -216,6 +216,25 @@ def test_multi_handle_isotropic_matches_oracle(ngpus, spread):
         assert np.array_equal(m.get_seismograms()[0], sx1)
 
 
+def test_multi_handle_isotropic_finer_tail(monkeypatch):
+    """Slabs whose middle z chunk is split into finer work items (CPML_TAIL_SPLIT): the boundary chunks stay whole and
+    first, so the in-kernel slab ordering is untouched; two slabs on one device, bit-identical to the oracle."""
+    import refcfg
+    from oracle import oracle as O
+    monkeypatch.setenv("CPML_ZCHUNKS", "3")
+    monkeypatch.setenv("CPML_TAIL_SPLIT", "2")
+    c = refcfg.cfg3d(nx=40, ny=37, nz=48, npml=5, nstep=80)
+    o = O.run_3d_iso(**c, nproc=2, want_fields=True)
+    with _multi_iso(c, 2, [0, 0]) as m:
+        assert m.slab_launch_info(0) == {"tma": 2, "peer_sides": 2}
+        m.run(1, c["nstep"])
+        sx, sy = m.get_seismograms()
+        assert np.array_equal(sx, o["sisvx"]) and np.array_equal(sy, o["sisvy"])
+        assert refcfg.rel_l2(m.get_energy()[0], o["total_energy"]) <= 1e-11
+        for f, name in ((0, "vx"), (2, "vz"), (5, "sigmazz"), (7, "sigmaxz")):
+            assert np.array_equal(m.get_field(f), o[name]), name
+
+
 @pytest.mark.parametrize("emulate", [1, 4])
 @pytest.mark.parametrize("ngpus,spread", [(2, False), (4, False), (2, True), (8, True)])
 def test_multi_handle_viscoelastic_matches_oracle(ngpus, spread, emulate):

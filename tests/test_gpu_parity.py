@@ -259,6 +259,31 @@ def test_3d_tma_tiles_and_ring_depths(kernel, tile, stages, monkeypatch):
         assert refcfg.rel_l2(s.get_energy()[0], o["total_energy"]) <= TOL_ENERGY
 
 
+@pytest.mark.parametrize("zchunks,split", [(4, 2), (3, 4), (5, 3), (4, 1)])
+@pytest.mark.parametrize("sched", ["queue", "static"])
+def test_3d_work_queue_and_finer_tail(zchunks, split, sched, monkeypatch):
+    """The persistent kernels' work distribution must not show in the results: items claimed from the queue or in
+    static shares, the last coarse items split into 2..4 finer ones (CPML_TAIL_SPLIT; the default only splits chunks
+    of >= 16 planes, which the small test grids never have), ragged chunk lengths -- bit-identical to the oracle
+    either way, energies to 1e-11 (the partial sums are per work item)."""
+    c = refcfg.cfg3d(nx=37, ny=45, nz=42, npml=6, nstep=90)
+    o = O.run_3d_iso(**c, nproc=2, want_fields=True)
+    monkeypatch.setenv("CPML_ZCHUNKS", str(zchunks))
+    monkeypatch.setenv("CPML_ZCHUNKS_STRESS", str(zchunks + 1))
+    monkeypatch.setenv("CPML_TAIL_SPLIT", str(split))
+    if sched == "static":
+        monkeypatch.setenv("CPML_SCHED", "static")
+    with solver3d(c) as s:
+        assert s.launch_info()["tma"] == 2
+        s.run(1, c["nstep"])
+        sx, sy = s.get_seismograms()
+        assert np.abs(o["sisvx"]).max() > 1e-4
+        assert np.array_equal(sx, o["sisvx"]) and np.array_equal(sy, o["sisvy"])
+        for f, name in enumerate(F3):
+            assert np.array_equal(s.get_field(f), o[name]), name
+        assert refcfg.rel_l2(s.get_energy()[0], o["total_energy"]) <= 1e-11
+
+
 def test_3d_register_kernels_still_match(monkeypatch):
     """CPML_KERNEL=reg: the register-marching kernels kept for A/B measurements."""
     monkeypatch.setenv("CPML_KERNEL", "reg")
