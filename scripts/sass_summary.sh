@@ -4,7 +4,7 @@
 # Usage: scripts/sass_summary.sh > profiles/r02_sass_summary.txt
 so=seismic_cpml_b200/libcpml_b200.so
 echo "# $so : $(cuobjdump -lelf $so | head -3 | tr '\n' ' ')"
-echo "# default kernels per workload: cfg3 / cfg4 k_{stress,velocity}3d_ws<double,1,104,8>; cfg3f <float,1,104,8>; cfg5 k_vstress3d<32,8,2,0> + k_vvelocity3d_ws<104,8>"
+echo "# default kernels per workload: cfg3 / cfg4 k_{stress,velocity}3d_ws<double,1,104,8>; cfg3f <float,1,104,8>; cfg5 k_vstress3d<32,8,2,0> + k_vvelocity3d_ws<64,8> (1024-wide slabs; cfg5d, 210 wide: <108,8>)"
 echo
 printf "%-100s %8s %8s %8s %8s %8s %8s\n" "kernel (cuobjdump -sass)" UTMALDG UBLKCP SYNCS BAR.ARV BAR.SYNC STG.EF
 for fn in $(cuobjdump -sass $so | grep -oE "Function : \S+" | awk '{print $3}' | grep -E "3d_ws|3d_tmaILb1ELi104ELi8ELi1|k_vstress3dILi32ELi8ELi2ELi0|k_vvelocity3dILi32ELi8ELi2|2d_pairILi4ELi32ELi8ELi2" | grep -vE "Lb0E" | sort -u); do
