@@ -99,7 +99,8 @@ struct cpml_handle {
     bool rho_exact = true;     // no density / interpolated density with an all-ones significand
 
     // source / receivers / traces
-    double *d_src_x = nullptr, *d_src_y = nullptr;
+    double *d_src_x = nullptr, *d_src_y = nullptr;      // one allocation [2][nstep] (d_src_y = d_src_x + nstep)
+    double *d_step_out = nullptr;  // [nstep][4] kinetic, potential, sisvx(it,1), sisvy(it,1): what cpml_fetch_step pulls
     bool have_source = false;
     int *d_ix_rec = nullptr, *d_iy_rec = nullptr;
     bool have_receivers = false;
@@ -303,10 +304,12 @@ static int32_t create_impl(cpml_handle *h)
         for (int m = 0; m < 3; m++) CK(cudaMalloc(&h->mat[m], h->field_doubles * sizeof(double)));
 
     const size_t nt = (size_t)c.nstep;
-    CK(cudaMalloc(&h->d_src_x, nt * sizeof(double)));
-    CK(cudaMalloc(&h->d_src_y, nt * sizeof(double)));
-    CK(cudaMemset(h->d_src_x, 0, nt * sizeof(double)));      // steps beyond a short series inject nothing
-    CK(cudaMemset(h->d_src_y, 0, nt * sizeof(double)));
+    // (x and y series in one allocation, like the pinned staging: cpml_set_source_step is ONE strided copy)
+    CK(cudaMalloc(&h->d_src_x, 2 * nt * sizeof(double)));
+    h->d_src_y = h->d_src_x + nt;
+    CK(cudaMemset(h->d_src_x, 0, 2 * nt * sizeof(double)));  // steps beyond a short series inject nothing
+    CK(cudaMalloc(&h->d_step_out, 4 * nt * sizeof(double)));
+    CK(cudaMemset(h->d_step_out, 0, 4 * nt * sizeof(double)));
     CK(cudaMalloc(&h->d_ek, nt * sizeof(double)));
     CK(cudaMalloc(&h->d_ep, nt * sizeof(double)));
     const size_t ns = std::max<size_t>(1, nt * (size_t)c.nrec);
@@ -432,7 +435,7 @@ extern "C" int32_t cpml_destroy(cpml_handle *h)
     for (auto &p : h->mx) cudaFree(p);
     for (auto &p : h->my) cudaFree(p);
     for (auto &p : h->mz) cudaFree(p);
-    cudaFree(h->d_src_x); cudaFree(h->d_src_y); cudaFree(h->d_ix_rec); cudaFree(h->d_iy_rec);
+    cudaFree(h->d_src_x); cudaFree(h->d_step_out); cudaFree(h->d_ix_rec); cudaFree(h->d_iy_rec);
     cudaFree(h->d_sisvx); cudaFree(h->d_sisvy); cudaFree(h->d_sisp); cudaFree(h->d_sisvz); cudaFree(h->d_ek); cudaFree(h->d_ep);
     cudaFree(h->d_partials); cudaFree(h->d_maxbits);
     cudaFreeHost(h->pin_src); cudaFreeHost(h->pin_out);
@@ -469,6 +472,7 @@ extern "C" int32_t cpml_reset(cpml_handle *h)
     const size_t nt = (size_t)c.nstep;
     CK(cudaMemsetAsync(h->d_ek, 0, nt * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->d_ep, 0, nt * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->d_step_out, 0, 4 * nt * sizeof(double), h->stream));
     const size_t ns = std::max<size_t>(1, nt * (size_t)c.nrec);
     CK(cudaMemsetAsync(h->d_sisvx, 0, ns * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->d_sisvy, 0, ns * sizeof(double), h->stream));
@@ -642,8 +646,9 @@ extern "C" int32_t cpml_set_source_step(cpml_handle *h, int32_t it, double force
     double *sx = h->pin_src + (it - 1), *sy = h->pin_src + c.nstep + (it - 1);
     *sx = c.ndim == 3 ? force_x * c.deltat / c.rho : force_x;      // :1080-1081
     *sy = c.ndim == 3 ? force_y * c.deltat / c.rho : force_y;
-    CK(cudaMemcpyAsync(h->d_src_x + (it - 1), sx, sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_src_y + (it - 1), sy, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    // both components in one copy operation: two 8-byte rows NSTEP doubles apart, on the host and on the device
+    CK(cudaMemcpy2DAsync(h->d_src_x + (it - 1), (size_t)c.nstep * sizeof(double), sx, (size_t)c.nstep * sizeof(double),
+                         sizeof(double), 2, cudaMemcpyHostToDevice, h->stream));
     h->have_source = true;
     return CPML_OK;
 }
@@ -654,13 +659,9 @@ extern "C" int32_t cpml_fetch_step(cpml_handle *h, int32_t it)
     const cpml_config &c = h->cfg;
     if (it < 1 || it > c.nstep) FAIL(CPML_EINVAL, "time step outside 1..NSTEP");
     CK(cudaSetDevice(h->device));
-    double *o = h->pin_out + 4 * (size_t)(it - 1);
-    CK(cudaMemcpyAsync(o + 0, h->d_ek + (it - 1), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(o + 1, h->d_ep + (it - 1), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (c.nrec > 0) {
-        CK(cudaMemcpyAsync(o + 2, h->d_sisvx + (it - 1), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(o + 3, h->d_sisvy + (it - 1), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    }
+    // the finisher kernel of the step (k_post3d) left the four values side by side: one 32-byte copy
+    CK(cudaMemcpyAsync(h->pin_out + 4 * (size_t)(it - 1), h->d_step_out + 4 * (size_t)(it - 1), 4 * sizeof(double),
+                       cudaMemcpyDeviceToHost, h->stream));
     return CPML_OK;
 }
 
@@ -1436,6 +1437,7 @@ extern "C" int32_t cpml_step_finish(cpml_handle *h, int32_t it)
     p.partials = h->d_partials; p.nblocks = h->nblocks;
     p.npot = h->visco ? 2 * h->nblocks : h->nblocks;
     p.energy_k = h->d_ek; p.energy_p = h->d_ep;
+    p.step_out = h->d_step_out + 4 * (size_t)(it - 1);
     p.it = it; p.nstep = c.nstep; p.nrec = c.nrec;
     p.ix_rec = h->d_ix_rec; p.iy_rec = h->d_iy_rec;
     p.vx = h->f0[0]; p.vy = h->f0[1];

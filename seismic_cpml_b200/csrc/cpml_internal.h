@@ -239,6 +239,7 @@ struct Post3D {
     int nblocks;                   // kinetic partials [0, nblocks)
     int npot;                      // potential partials [nblocks, nblocks + npot)
     double *energy_k, *energy_p;   // traces, slot it-1 is written
+    double *step_out;              // [4] this step's kinetic, potential, sisvx(it,1), sisvy(it,1) side by side (cpml_fetch_step)
     int it, nstep, nrec;
     const int *ix_rec, *iy_rec;
     const double *vx, *vy;         // element (1,1,0)

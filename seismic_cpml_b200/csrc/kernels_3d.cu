@@ -372,6 +372,8 @@ __global__ void __launch_bounds__(256) k_post3d(const __grid_constant__ Post3D p
     if (threadIdx.x == 0) {
         p.energy_k[p.it - 1] = a;
         p.energy_p[p.it - 1] = b;
+        p.step_out[0] = a;
+        p.step_out[1] = b;
     }
     if (p.krec > 0) {
         for (int r = threadIdx.x; r < p.nrec; r += 256) {
@@ -379,8 +381,10 @@ __global__ void __launch_bounds__(256) k_post3d(const __grid_constant__ Post3D p
             // (single-precision fields: the traces are still double, like sisvx(NSTEP,NREC) of a build that only
             // demotes the wavefields)
             auto at = [&](const double *f) { return p.f32 ? (double)reinterpret_cast<const float *>(f)[q] : f[q]; };
-            p.sisvx[(long long)r * p.nstep + (p.it - 1)] = at(p.vx);
-            p.sisvy[(long long)r * p.nstep + (p.it - 1)] = at(p.vy);
+            const double sx = at(p.vx), sy = at(p.vy);
+            p.sisvx[(long long)r * p.nstep + (p.it - 1)] = sx;
+            p.sisvy[(long long)r * p.nstep + (p.it - 1)] = sy;
+            if (r == 0) { p.step_out[2] = sx; p.step_out[3] = sy; }
             // not in the reference (it records Vx and Vy only although its plot script reads Vz files, quirk
             // B7): vz at the same array indices, vz(ix_rec, iy_rec, NZ/2)
             if (p.vz) p.sisvz[(long long)r * p.nstep + (p.it - 1)] = at(p.vz);

@@ -538,6 +538,49 @@ def test_3d_default_grid_450_steps_vs_timed_oracle():
     assert refcfg.rel_l2(pvx, o["plane_vx"]) <= TOL and refcfg.rel_l2(pvy, o["plane_vy"]) <= TOL
 
 
+def test_per_step_source_upload_and_result_fetch():
+    """The per-step host API a driver's `do it` body uses (bench.py's e2e leg): cpml_set_source_step uploads the source
+    term of step `it` (one strided copy from pinned memory), cpml_fetch_step queues the read of that step's kinetic /
+    potential energy and first-receiver sample (one 32-byte copy of what k_post3d left side by side).  Same bits as
+    the whole-series path, 3-D and 2-D."""
+    c = refcfg.cfg3d(nx=37, ny=45, nz=40, npml=6, nstep=60)
+    with solver3d(c) as whole:
+        whole.run(1, c["nstep"])
+        wx, wy = whole.get_seismograms()
+        we = whole.get_energy()
+    s = L.Solver(ndim=3, order=2, nx=c["nx"], ny=c["ny"], nz=c["nz"], nstep=c["nstep"], npoints_pml=c["npoints_pml"],
+                 nrec=len(c["ix_rec"]), isource=c["isource"], jsource=c["jsource"], deltax=c["deltax"], deltay=c["deltay"],
+                 deltaz=c["deltaz"], deltat=c["deltat"], lam=c["lam"], mu=c["mu"], lambdaplustwomu=c["lambdaplustwomu"],
+                 rho=c["rho"], cp=3300.0)
+    with s:
+        s.set_profiles(L.AXIS_X, c["prof_x"]); s.set_profiles(L.AXIS_Y, c["prof_y"]); s.set_profiles(L.AXIS_Z, c["prof_z"])
+        s.set_receivers(c["ix_rec"], c["iy_rec"])
+        for it in range(1, c["nstep"] + 1):
+            s.set_source_step(it, c["force_x"][it - 1], c["force_y"][it - 1])
+            s.step_stress(it); s.step_velocity(it); s.step_finish(it)
+            s.fetch_step(it)
+        sx, sy = s.get_seismograms()
+        e = s.get_energy()
+        assert np.abs(wx).max() > 1e-4
+        assert np.array_equal(sx, wx) and np.array_equal(sy, wy)
+        assert np.array_equal(e[1], we[1]) and np.array_equal(e[2], we[2])
+        for it in (1, 17, c["nstep"]):
+            f = s.get_fetched_step(it)
+            assert f[0] == e[1][it - 1] and f[1] == e[2][it - 1] and f[2] == sx[0, it - 1] and f[3] == sy[0, it - 1], (it, f)
+
+    c2 = refcfg.cfg2d(4, nx=90, ny=70, nstep=50, npml=6)
+    o2 = O.run_2d(**c2)
+    p2 = solver2d(c2)
+    with p2:
+        for it in range(1, c2["nstep"] + 1):
+            p2.step_stress(it); p2.step_velocity(it); p2.step_finish(it)
+            p2.fetch_step(it)
+        sx2, sy2 = p2.get_seismograms()
+        assert np.array_equal(sx2, o2["sisvx"])
+        f = p2.get_fetched_step(33)
+        assert f[2] == sx2[0, 32] and f[3] == sy2[0, 32]
+
+
 def test_asynchronous_snapshot_planes():
     """cpml_snapshot_begin / _end: the plane is the one of the step at which the pull was STARTED, however far the loop
     has moved on when it is collected (device-side copy first); slots are independent; misuse is refused."""
