@@ -120,6 +120,40 @@ __device__ __forceinline__ Item decode_item(int item, const Tile3D &t, int nzl)
     return it;
 }
 
+// Single precision only: consumer thread -> (pair of the tile row, row of the tile), recomputed per work item.  The
+// pairs of a row are [0, nl) in the left x shell, [nl, nr) interior, [nr, TX/2) in the right x shell or beyond NX.
+// Threads are dealt to the interior pairs first, row by row, then to the others: a warp then holds x-shell lanes or
+// interior lanes, rarely both, and only the warps that hold shell lanes run the x part of the C-PML code (warp-uniform
+// `ux`): on the 101-wide default grid 3 of the 13 consumer warps instead of all of them (velocity kernel 0.610 ->
+// 0.555 ms, profiles/r02_n_bench_lane_map.txt).  Any 0 <= nl <= nr <= TX/2 gives a one-to-one map, so the
+// classification is a matter of speed only: the per-point predicates are computed from (i, j) as before.  The
+// double-precision kernels keep the fixed row-major map: at their 128-register cap the per-item map costs more in
+// spills than it saves, and their stress kernel wants whole sectors per warp (same file).
+struct Lane { int tx, ty; bool ok; };
+template <int TX, int TY>
+__device__ __forceinline__ Lane map_lane_packed(int tid, int i0, int xlo, int xhi, int nx)
+{
+    constexpr int HP = TX / 2;
+    const int nl = (xlo >= i0) ? min(HP, (xlo - i0) / 2 + 1) : 0;            // pairs whose first column is <= xlo
+    const int nr = max(nl, min(HP, max(0, min(xhi, nx + 1) - i0) / 2));      // first pair whose last column is >= xhi or > NX
+    const int ni = nr - nl, ns = HP - ni;
+    int tx = 0, tyr = TY;                                                    // (idle thread)
+    if (tid < ni * TY) {
+        tyr = tid / ni;
+        tx = nl + (tid - tyr * ni);
+    } else if (ns > 0) {
+        const int u = tid - ni * TY;
+        tyr = u / ns;
+        const int e = u - tyr * ns;
+        tx = e < nl ? e : nr + (e - nl);
+    }
+    Lane l;
+    l.ok = tyr < TY;
+    l.ty = min(tyr, TY - 1);
+    l.tx = tx;
+    return l;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------- stress
@@ -226,14 +260,13 @@ k_stress3d_ws(const __grid_constant__ Params3DT<T> p, const __grid_constant__ Tm
     }
 
     // ================================================================ consumer warps
-    const int tx = tid % (TX / 2);
+    constexpr bool PACK = sizeof(T) == 4;                           // per-item thread map (map_lane_packed)
+    const int tx_rm = tid % (TX / 2);                               // the fixed row-major map
     const int ty_raw = tid / (TX / 2);
-    const bool lane_ok = ty_raw < TY;                               // tiles whose pair count is not a multiple of 32
-    const int ty = min(ty_raw, TY - 1);                             // idle threads read row TY-1 and store nothing
+    const bool ok_rm = ty_raw < TY;                                 // tiles whose pair count is not a multiple of 32
+    const int ty_rm = min(ty_raw, TY - 1);                          // idle threads read row TY-1 and store nothing
     const int pitch = p.pitch;
     const unsigned pl = (unsigned)p.plane;      // element offsets fit 32 bits (checked on the host)
-    const int oh = ty * W + 2 * tx;      // halo tile, box origin (0,0): first point of the pair
-    const int oc = ty * TX + 2 * tx;     // plain tile
 
     RingPos rn{0, 0}, rc{0, 0};          // stage of the current plane in each ring
     for (uint32_t ip = 0;; ++ip) {
@@ -249,8 +282,13 @@ k_stress3d_ws(const __grid_constant__ Params3DT<T> p, const __grid_constant__ Tm
         if (ss.wait_lo && kb == 1 && tid == 0) poll_flag(ss.wait_lo, ss.wait_value, ss.timeout);
 
         // the pair: points A = (i, j) and B = (i+1, j); i-1 is even, so B shares A's 16 bytes
+        Lane ln{tx_rm, ty_rm, ok_rm};
+        if constexpr (PACK) ln = map_lane_packed<TX, TY>(tid, i0, p.xlo, p.xhi, p.nx);
+        const int tx = ln.tx, ty = ln.ty;
+        const int oh = ty * W + 2 * tx;      // halo tile, box origin (0,0): first point of the pair
+        const int oc = ty * TX + 2 * tx;     // plain tile
         const int i = i0 + 2 * tx, j = j0 + ty;
-        const bool row = lane_ok && (j <= p.ny);
+        const bool row = ln.ok && (j <= p.ny);
         const bool validA = row && (i <= p.nx), validB = row && (i + 1 <= p.nx);
         const bool storeA = row && (i + 1 <= pitch);                // validA or a pad pair of the row
         unsigned q = (unsigned)kb * pl + (unsigned)((j - 1) * pitch + (i - 1));
@@ -490,14 +528,13 @@ k_velocity3d_ws(const __grid_constant__ Params3DT<T> p, const __grid_constant__ 
     }
 
     // ================================================================ consumer warps
-    const int tx = tid % (TX / 2);
+    constexpr bool PACK = sizeof(T) == 4;       // per-item thread map (map_lane_packed), see k_stress3d_ws
+    const int tx_rm = tid % (TX / 2);
     const int ty_raw = tid / (TX / 2);
-    const bool lane_ok = ty_raw < TY;
-    const int ty = min(ty_raw, TY - 1);
+    const bool ok_rm = ty_raw < TY;
+    const int ty_rm = min(ty_raw, TY - 1);
     const int pitch = p.pitch;
     const unsigned pl = (unsigned)p.plane;      // element offsets fit 32 bits (checked on the host)
-    const int oh = ty * W + 2 * tx;
-    const int oc = ty * TX + 2 * tx;
 
     RingPos rn{0, 0}, rc{0, 0};
     for (uint32_t ip = 0;; ++ip) {
@@ -512,8 +549,13 @@ k_velocity3d_ws(const __grid_constant__ Params3DT<T> p, const __grid_constant__ 
         // plane 0 (sigmaxz, sigmayz of the lower neighbour) is read straight from global memory below
         if (ss.wait_lo && kb == 1 && tid == 0) poll_flag(ss.wait_lo, ss.wait_value, ss.timeout);
 
+        Lane ln{tx_rm, ty_rm, ok_rm};
+        if constexpr (PACK) ln = map_lane_packed<TX, TY>(tid, i0, p.xlo, p.xhi, p.nx);
+        const int tx = ln.tx, ty = ln.ty;
+        const int oh = ty * W + 2 * tx;
+        const int oc = ty * TX + 2 * tx;
         const int i = i0 + 2 * tx, j = j0 + ty;
-        const bool row = lane_ok && (j <= p.ny);
+        const bool row = ln.ok && (j <= p.ny);
         const bool validA = row && (i <= p.nx), validB = row && (i + 1 <= p.nx);
         const bool storeA = row && (i + 1 <= pitch);                // validA or a pad pair of the row
         unsigned q = (unsigned)kb * pl + (unsigned)((j - 1) * pitch + (i - 1));
