@@ -95,7 +95,7 @@ __device__ __forceinline__ void publish_side(unsigned int *counter, int n_items,
 // kchunk / split planes.  With the queue the CTAs finish within one item of each other, so the idle tail of a launch is
 // about half an item per SM; short items at the end cut it without paying their start-up cost everywhere.
 struct Item { int tix, tiy, kb, ke; };
-__device__ __forceinline__ Item decode_item(int item, const Tile3D &t, int nzl)
+__host__ __device__ __forceinline__ Item decode_item(int item, const Tile3D &t, int nzl)
 {
     int ci = item, part = 0;
     const bool fine = item >= t.fine_from;
@@ -131,7 +131,7 @@ __device__ __forceinline__ Item decode_item(int item, const Tile3D &t, int nzl)
 // spills than it saves, and their stress kernel wants whole sectors per warp (same file).
 struct Lane { int tx, ty; bool ok; };
 template <int TX, int TY>
-__device__ __forceinline__ Lane map_lane_packed(int tid, int i0, int xlo, int xhi, int nx)
+__host__ __device__ __forceinline__ Lane map_lane_packed(int tid, int i0, int xlo, int xhi, int nx)
 {
     constexpr int HP = TX / 2;
     const int nl = (xlo >= i0) ? min(HP, (xlo - i0) / 2 + 1) : 0;            // pairs whose first column is <= xlo
@@ -793,3 +793,31 @@ cudaError_t launch_velocity3d_ws(const Params3DF &p, const TmaMaps &tm, const Ti
 }
 
 }  // namespace cpml
+
+// Test hooks, not part of the ABI of include/cpml_b200.h (tests/test_work_items.py, no GPU needed): the work
+// decomposition of the persistent kernels exactly as the device code computes it -- the same functions, compiled for
+// the host.  tile6 = ntx, nty, kchunk, nzc, fine_from, split; out4 = tix, tiy, kb, ke.
+extern "C" int32_t cpml_debug_work_item(const int32_t *tile6, int32_t nzl, int32_t item, int32_t *out4)
+{
+    if (!tile6 || !out4) return -1;
+    cpml::Tile3D t{};
+    t.ntx = tile6[0]; t.nty = tile6[1]; t.kchunk = tile6[2]; t.nzc = tile6[3]; t.fine_from = tile6[4]; t.split = tile6[5];
+    const cpml::Item it = cpml::decode_item(item, t, nzl);
+    out4[0] = it.tix; out4[1] = it.tiy; out4[2] = it.kb; out4[3] = it.ke;
+    return 0;
+}
+
+// The packed thread map of the single-precision kernels for tile tx x ty: out3 = pair of the row, row, active.
+extern "C" int32_t cpml_debug_lane(int32_t tx, int32_t ty, int32_t tid, int32_t i0, int32_t xlo, int32_t xhi, int32_t nx, int32_t *out3)
+{
+    if (!out3) return -1;
+    cpml::Lane l{};
+    switch (tx * 100 + ty) {
+    case 6408:  l = cpml::map_lane_packed<64, 8>(tid, i0, xlo, xhi, nx); break;
+    case 10408: l = cpml::map_lane_packed<104, 8>(tid, i0, xlo, xhi, nx); break;
+    case 12807: l = cpml::map_lane_packed<128, 7>(tid, i0, xlo, xhi, nx); break;
+    default: return -1;
+    }
+    out3[0] = l.tx; out3[1] = l.ty; out3[2] = l.ok ? 1 : 0;
+    return 0;
+}
