@@ -20,6 +20,13 @@
 // variables staged in the ring with the tiles, coefficient table in shared memory, branch-free over the lanes) /
 // general (y or z shell too: those memory variables come from global memory, loads hoisted above the waits).
 //
+// Work distribution (persistent CTAs, one per SM): the producer's lead lane claims work items from a queue in global
+// memory (tma_common.cuh: claim_item) and posts them to the consumers through item_slot[] / item_bar -- SMs that get
+// more of the HBM bandwidth take more items, instead of idling behind the slowest static share -- and the items at the
+// end of the list are shorter (decode_item), so the launch ends within a short item on every SM.  The
+// single-precision kernels also re-deal the threads of a tile per item so that the x-shell lanes sit in their own
+// warps (map_lane_packed).
+//
 // Slab decomposition: the boundary planes every neighbour needs (:811-823, :951-963) are stored by the same
 // kernels straight into the neighbour GPU's halo planes over NVLink, AND the ordering between slabs is done
 // inside the kernels as well (SlabSync): only the work items that read a halo plane poll the neighbour's flag
