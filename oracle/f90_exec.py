@@ -1,0 +1,533 @@
+"""Runs a reference PROGRAM from its own Fortran source text (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+
+The image has no Fortran compiler, so the reference cannot be built here.  This module is the next best pin for the
+oracle: it reads a reference `.f90` file where it lies (/root/reference, never copied into the repo), transliterates the
+small statement subset those programs use -- declarations, `do` / `if`, assignments to scalars, array elements and array
+sections, a handful of intrinsics, and the MPI calls of the slab exchange -- statement by statement into Python, and
+executes the result: every arithmetic expression is the reference's own text, evaluated in IEEE double precision in
+source order (numpy float64 scalars; no FMA, no reassociation).  `parameter` constants can be overridden (a smaller
+grid, fewer steps), which is what the reference expects its users to do by editing those lines.
+
+MPI programs run as NPROC Python threads, one per rank, with MPI_SENDRECV / MPI_REDUCE emulated by queues.
+
+What is NOT taken from the reference: I/O (print / write / open / close and the image and seismogram writers are skipped;
+results are read from the program's variables after it ends) and date_and_time.
+
+Used by tests/golden/make_reference_vectors.py to produce the golden vectors the oracle is checked against
+(tests/test_reference_vectors.py).  Nothing here runs at test time on a box without /root/reference.
+"""
+from __future__ import annotations
+
+import ast
+import math
+import queue
+import re
+import threading
+
+import numpy as np
+
+
+class FortranStop(Exception):
+    pass
+
+
+# ------------------------------------------------------------------------------------------------ source -> logical lines
+
+def _strip_comment(line: str) -> str:
+    q = None
+    for n, ch in enumerate(line):
+        if q:
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+        elif ch == "!":
+            return line[:n]
+    return line
+
+
+def _lower_outside_quotes(s: str) -> str:
+    out, q = [], None
+    for ch in s:
+        if q:
+            out.append(ch)
+            if ch == q:
+                q = None
+        else:
+            if ch in "'\"":
+                q = ch
+                out.append(ch)
+            else:
+                out.append(ch.lower())
+    return "".join(out)
+
+
+def logical_lines(path: str) -> list[str]:
+    """The statements of the main program (from `program` to `end program`), comments and OpenMP directives removed,
+    continuation lines joined, lower-cased outside character strings (Fortran is case-insensitive)."""
+    raw = open(path).read().split("\n")
+    start = next(n for n, l in enumerate(raw) if re.match(r"^\s*program\b", l, re.I))
+    end = next(n for n, l in enumerate(raw) if re.match(r"^\s*end\s+program\b", l, re.I))
+    out, cur = [], ""
+    for line in raw[start + 1:end]:
+        s = _strip_comment(line).rstrip()
+        if not s.strip():
+            continue
+        body = s.strip()
+        if cur:
+            if body.startswith("&"):
+                body = body[1:]
+            cur = cur + " " + body
+        else:
+            cur = body
+        if cur.endswith("&"):
+            cur = cur[:-1].rstrip()
+            continue
+        out.append(_lower_outside_quotes(cur))
+        cur = ""
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ expressions
+
+def _match_paren(s: str, i: int) -> int:
+    """Index of the parenthesis that closes s[i] == '('."""
+    depth, q = 0, None
+    for n in range(i, len(s)):
+        ch = s[n]
+        if q:
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+        elif ch == "(":
+            depth += 1
+        elif ch == ")":
+            depth -= 1
+            if depth == 0:
+                return n
+    raise ValueError("unbalanced parentheses: " + s)
+
+
+def _split_top(s: str, sep: str = ",") -> list[str]:
+    parts, depth, q, cur = [], 0, None, []
+    for ch in s:
+        if q:
+            cur.append(ch)
+            if ch == q:
+                q = None
+            continue
+        if ch in "'\"":
+            q = ch
+        elif ch in "([":
+            depth += 1
+        elif ch in ")]":
+            depth -= 1
+        if ch == sep and depth == 0:
+            parts.append("".join(cur).strip())
+            cur = []
+        else:
+            cur.append(ch)
+    parts.append("".join(cur).strip())
+    return parts
+
+
+_NUM_D = re.compile(r"(?<![\w.])(\d+\.?\d*|\.\d+)d([+-]?\d+)")
+_IDENT = re.compile(r"[a-z_]\w*")
+
+
+_PY_KEYWORDS = {"lambda", "in", "is", "from", "pass", "global", "class", "def", "del", "as", "with", "yield", "try",
+                "except", "raise", "import", "assert", "async", "await", "nonlocal", "while", "for", "return", "break",
+                "continue", "finally", "none"}
+
+
+def _rename_keywords(s: str) -> str:
+    """Fortran names that are Python keywords (the programs have a variable called lambda) get a trailing underscore."""
+    return re.sub(r"(?<![\w.'\"])([a-z_]\w*)(?![\w'\"])", lambda m: m.group(1) + "_" if m.group(1) in _PY_KEYWORDS else m.group(1), s)
+
+
+class _DivPow(ast.NodeTransformer):
+    """a / b -> _div(a, b) (integer division truncates when both operands are integers); a ** b -> _pow(a, b)
+    (x**2 and x**2.d0 are x*x, as gfortran compiles them)."""
+
+    def visit_BinOp(self, node):
+        self.generic_visit(node)
+        if isinstance(node.op, ast.Div):
+            return ast.Call(func=ast.Name(id="_div", ctx=ast.Load()), args=[node.left, node.right], keywords=[])
+        if isinstance(node.op, ast.Pow):
+            return ast.Call(func=ast.Name(id="_pow", ctx=ast.Load()), args=[node.left, node.right], keywords=[])
+        return node
+
+
+class Translator:
+    def __init__(self, overrides: dict[str, str] | None = None, externals=()):
+        self.overrides = {k.lower(): v for k, v in (overrides or {}).items()}
+        self.externals = {e.lower() for e in externals}          # external subroutines supplied by the caller
+        self.bounds: dict[str, list[tuple[str, str]]] = {}      # array name -> [(lo, hi)] as Python expressions
+        self.int_scalars: set[str] = set()                       # assignment to these truncates, as in Fortran
+        self.code: list[str] = []
+        self.depth = 0
+
+    # ---- expressions
+    def expr(self, s: str) -> str:
+        s = _rename_keywords(s.strip())
+        s = _NUM_D.sub(r"\1e\2", s)
+        for a, b in ((".and.", " and "), (".or.", " or "), (".not.", " not "), (".true.", " True "), (".false.", " False "),
+                     (".eq.", "=="), (".ne.", "!="), (".lt.", "<"), (".le.", "<="), (".gt.", ">"), (".ge.", ">=")):
+            s = s.replace(a, b)
+        s = s.replace("/=", "!=")
+        s = self._arrays(s)
+        tree = ast.parse(s.strip(), mode="eval")
+        tree = ast.fix_missing_locations(_DivPow().visit(tree))
+        return ast.unparse(tree)
+
+    def _arrays(self, s: str) -> str:
+        out, n = [], 0
+        while n < len(s):
+            m = _IDENT.match(s, n)
+            if m and (n == 0 or not (s[n - 1].isalnum() or s[n - 1] in "_.")):
+                name = m.group(0)
+                k = m.end()
+                while k < len(s) and s[k] == " ":
+                    k += 1
+                if name in self.bounds and k < len(s) and s[k] == "(":
+                    close = _match_paren(s, k)
+                    out.append(self._subscript(name, s[k + 1:close]))
+                    n = close + 1
+                    continue
+                out.append(name)
+                n = m.end()
+                continue
+            out.append(s[n])
+            n += 1
+        return "".join(out)
+
+    def _subscript(self, name: str, args: str) -> str:
+        idx = []
+        for (lo, _hi), a in zip(self.bounds[name], _split_top(args)):
+            parts = _split_top(a, ":")
+            if len(parts) == 1:
+                idx.append(f"({self._arrays(a)})-({lo})")
+            else:
+                b = f"({self._arrays(parts[0])})-({lo})" if parts[0] else ""
+                e = f"({self._arrays(parts[1])})-({lo})+1" if parts[1] else ""
+                idx.append(f"{b}:{e}")
+        return f"{name}[{', '.join(idx)}]"
+
+    # ---- output
+    def emit(self, line: str) -> None:
+        self.code.append("    " * self.depth + line)
+
+    # ---- declarations
+    _DECL = re.compile(r"^(integer|double precision|logical|real|character)\b")
+
+    def declaration(self, s: str) -> bool:
+        m = self._DECL.match(s)
+        if not m:
+            return False
+        kind = m.group(1)
+        rest = s[m.end():].strip()
+        if kind == "character":
+            return True
+        if rest.startswith("("):                                   # kind selector
+            rest = rest[_match_paren(rest, 0) + 1:].strip()
+        attrs, ents = "", rest
+        if "::" in rest:
+            attrs, ents = rest.split("::", 1)
+        is_param = "parameter" in attrs
+        dims = None
+        dm = re.search(r"dimension\s*\(", attrs)
+        if dm:
+            o = attrs.index("(", dm.start())
+            dims = attrs[o + 1:_match_paren(attrs, o)]
+        zero = "0" if kind == "integer" else ("False" if kind == "logical" else "0.0")
+        dtype = "np.int64" if kind == "integer" else "np.float64"
+        for ent in _split_top(_rename_keywords(ents)):
+            if not ent:
+                continue
+            if "=" in ent and is_param:
+                name, val = ent.split("=", 1)
+                name = name.strip()
+                val = self.overrides.get(name, val)
+                self.emit(f"{name} = _toint({self.expr(val)})" if kind == "integer" else f"{name} = {self.expr(val)}")
+                continue
+            edims = dims
+            name = ent.strip()
+            if "(" in name:
+                o = name.index("(")
+                edims = name[o + 1:_match_paren(name, o)]
+                name = name[:o].strip()
+            if edims is None:
+                if kind == "integer":
+                    self.int_scalars.add(name)
+                self.emit(f"{name} = {zero}")
+            else:
+                b = []
+                for d in _split_top(edims):
+                    p = _split_top(d, ":")
+                    b.append(("1", p[0]) if len(p) == 1 else (p[0], p[1]))
+                self.bounds[name] = [(self.expr(lo), self.expr(hi)) for lo, hi in b]
+                shape = ", ".join(f"({hi})-({lo})+1" for lo, hi in self.bounds[name])
+                self.emit(f"{name} = np.zeros(({shape},), dtype={dtype})")
+        return True
+
+    # ---- MPI
+    def mpi_call(self, name: str, args: list[str]) -> None:
+        if name in ("mpi_init", "mpi_finalize"):
+            return
+        if name == "mpi_barrier":
+            self.emit("_mpi.barrier()")
+        elif name == "mpi_comm_size":
+            self.emit(f"{args[1]} = _mpi.size")
+        elif name == "mpi_comm_rank":
+            self.emit(f"{args[1]} = _mpi.rank")
+        elif name == "mpi_sendrecv":
+            send, dest, recv, src = args[0], args[3], args[5], args[8]
+            self.emit(f"_t = _mpi.sendrecv({self.expr(send)}, {self.expr(dest)}, {self.expr(src)})")
+            self.emit("if _t is not None:")
+            self.emit(f"    {self.expr(recv)} = _t")
+        elif name == "mpi_reduce":
+            val, target, op, root = args[0], args[1], args[4], args[5]
+            self.emit(f"_t = _mpi.reduce({self.expr(val)}, '{op.strip()}', {self.expr(root)})")
+            self.emit("if _t is not None:")
+            self.emit(f"    {self.expr(target)} = _t")
+        else:
+            raise NotImplementedError(name)
+
+    # ---- statements
+    SKIP_CALLS = ("date_and_time", "write_seismograms", "create_color_image", "create_2d_image", "system_clock", "cpu_time",
+                  "system")
+
+    def statement(self, s: str) -> None:
+        if self.declaration(s):
+            return
+        if re.match(r"^(implicit|include|use|print|write|open|close|format|\d+\s+format)\b", s):
+            return
+        m = re.match(r"^do\s+(\w+)\s*=\s*(.*)$", s)
+        if m:
+            r = _split_top(m.group(2))
+            step = f", {self.expr(r[2])}" if len(r) > 2 else ""
+            self.emit(f"for {m.group(1)} in _range({self.expr(r[0])}, {self.expr(r[1])}{step}):")
+            self.depth += 1
+            return
+        if re.match(r"^end\s*do$", s):
+            self.depth -= 1
+            return
+        if re.match(r"^end\s*if$", s):
+            self.depth -= 1
+            return
+        if s == "else":
+            self.depth -= 1
+            self.emit("else:")
+            self.depth += 1
+            return
+        m = re.match(r"^(else\s*)?if\s*\(", s)
+        if m:
+            o = s.index("(", m.start())
+            c = _match_paren(s, o)
+            cond, tail = s[o + 1:c], s[c + 1:].strip()
+            if tail == "then":
+                if m.group(1):
+                    self.depth -= 1
+                    self.emit(f"elif {self.expr(cond)}:")
+                else:
+                    self.emit(f"if {self.expr(cond)}:")
+                self.depth += 1
+            else:
+                self.emit(f"if {self.expr(cond)}:")
+                self.depth += 1
+                n0 = len(self.code)
+                self.statement(tail)
+                if len(self.code) == n0:
+                    self.emit("pass")
+                self.depth -= 1
+            return
+        m = re.match(r"^stop\b(.*)$", s)
+        if m:
+            self.emit(f"raise FortranStop({m.group(1).strip() or repr('stop')})")
+            return
+        m = re.match(r"^call\s+(\w+)\s*(\(.*\))?$", s)
+        if m:
+            name = m.group(1)
+            if name in self.SKIP_CALLS:
+                return
+            args = _split_top(m.group(2)[1:-1]) if m.group(2) else []
+            if name.startswith("mpi_"):
+                self.mpi_call(name, args)
+                return
+            if name in self.externals:        # arrays go by reference (numpy), scalars by value: inputs only
+                self.emit(f"_ext_{name}({', '.join(self.expr(a) for a in args)})")
+                return
+            raise NotImplementedError("call " + name)
+        # assignment: the first '=' at depth 0 that is not part of ==, /=, <=, >=
+        depth = 0
+        for n, ch in enumerate(s):
+            if ch == "(":
+                depth += 1
+            elif ch == ")":
+                depth -= 1
+            elif ch == "=" and depth == 0 and s[n + 1:n + 2] != "=" and s[n - 1] not in "=/<>":
+                lhs, rhs = s[:n].strip(), s[n + 1:].strip()
+                if lhs in self.int_scalars:
+                    self.emit(f"{lhs} = _toint({self.expr(rhs)})")
+                else:
+                    self.emit(f"{self._arrays(_rename_keywords(lhs))} = {self.expr(rhs)}")
+                return
+        raise NotImplementedError("statement: " + s)
+
+    def translate(self, lines: list[str]) -> str:
+        for s in lines:
+            n0 = len(self.code)
+            self.statement(s)
+            # a block opener whose body turned out empty (only skipped statements) needs a `pass`: add one after every
+            # opener and let it be harmless
+            if len(self.code) > n0 and self.code[-1].rstrip().endswith(":"):
+                self.emit("pass")
+        assert self.depth == 0, "unbalanced blocks"
+        return "\n".join(self.code) + "\n"
+
+
+# ------------------------------------------------------------------------------------------------ run time
+
+def _div(a, b):
+    if isinstance(a, (int, np.integer)) and isinstance(b, (int, np.integer)) and not isinstance(a, bool):
+        q = abs(int(a)) // abs(int(b))
+        return q if (a >= 0) == (b >= 0) else -q          # Fortran integer division truncates towards zero
+    return np.float64(a) / np.float64(b) if not isinstance(a, np.ndarray) and not isinstance(b, np.ndarray) else a / b
+
+
+def _toint(x):
+    """Assignment of a real value to an integer truncates towards zero."""
+    return x if isinstance(x, (int, np.integer)) else int(x)
+
+
+def _pow(a, b):
+    if isinstance(b, (int, np.integer)) or float(b) == int(b):
+        n = int(b)
+        if isinstance(a, (int, np.integer)) and n >= 0:
+            return int(a) ** n
+        if n == 2:
+            return a * a
+        if n == 1:
+            return a
+        if n == 3:
+            return a * a * a
+    return np.float64(math.pow(float(a), float(b)))
+
+
+def _range(a, b, step=1):
+    return range(int(a), int(b) + (1 if step > 0 else -1), int(step))
+
+
+def _mod(a, b):
+    if isinstance(a, (int, np.integer)) and isinstance(b, (int, np.integer)):
+        return int(math.fmod(int(a), int(b)))
+    return np.float64(math.fmod(a, b))
+
+
+def _elementwise(f_scalar, f_array):
+    def f(x):
+        return f_array(x) if isinstance(x, np.ndarray) else np.float64(f_scalar(x))
+    return f
+
+
+def _sum(a):
+    """SUM of an array expression the way a compiler without -ffast-math does it: one accumulator, array element order
+    (first index fastest)."""
+    a = np.asarray(a, dtype=np.float64)
+    return np.float64(np.cumsum(a.T.ravel())[-1]) if a.size else np.float64(0.0)
+
+
+RUNTIME = {
+    "np": np, "FortranStop": FortranStop, "_div": _div, "_pow": _pow, "_range": _range, "_toint": _toint,
+    "dble": lambda x: np.float64(x), "real": lambda x: np.float64(x), "sngl": lambda x: np.float32(x), "int": lambda x: int(x),
+    "exp": _elementwise(math.exp, np.exp), "log": _elementwise(math.log, np.log), "sqrt": _elementwise(math.sqrt, np.sqrt),
+    "sin": _elementwise(math.sin, np.sin), "cos": _elementwise(math.cos, np.cos), "abs": abs, "max": max, "min": min,
+    "dsqrt": _elementwise(math.sqrt, np.sqrt), "dexp": _elementwise(math.exp, np.exp), "dlog": _elementwise(math.log, np.log),
+    "dsin": _elementwise(math.sin, np.sin), "dcos": _elementwise(math.cos, np.cos), "dabs": abs, "atan": _elementwise(math.atan, np.arctan),
+    "dmax1": max, "dmin1": min, "nint": lambda x: int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5)), "float": lambda x: np.float64(x),
+    "mod": _mod, "sum": _sum, "maxval": lambda a: np.float64(np.max(a)), "minval": lambda a: np.float64(np.min(a)),
+    "mpi_proc_null": -1, "mpi_comm_world": 0, "mpi_double_precision": 0, "mpi_sum": "mpi_sum", "mpi_max": "mpi_max",
+    "mpi_status_size": 1,
+}
+
+
+class _Comm:
+    """MPI_COMM_WORLD of NPROC threads."""
+
+    def __init__(self, size: int):
+        self.size = size
+        self.p2p = {(s, d): queue.Queue() for s in range(size) for d in range(size)}
+        self.red: dict[int, dict[int, object]] = {}       # reduction number -> {rank: value}
+        self.red_cv = threading.Condition()
+        self.bar = threading.Barrier(size)
+
+
+class _Rank:
+    def __init__(self, comm: _Comm, rank: int):
+        self.comm, self.rank, self.size = comm, rank, comm.size
+        self.nred = 0                                      # reductions this rank has entered (collectives are ordered)
+
+    def sendrecv(self, sendbuf, dest, src):
+        if dest >= 0:
+            self.comm.p2p[(self.rank, dest)].put(np.array(sendbuf, copy=True))
+        return self.comm.p2p[(src, self.rank)].get(timeout=600) if src >= 0 else None
+
+    def reduce(self, value, op, root):
+        seq, self.nred = self.nred, self.nred + 1
+        with self.comm.red_cv:
+            self.comm.red.setdefault(seq, {})[self.rank] = value
+            self.comm.red_cv.notify_all()
+            if self.rank != root:
+                return None
+            if not self.comm.red_cv.wait_for(lambda: len(self.comm.red[seq]) == self.size, timeout=600):
+                raise RuntimeError("MPI_REDUCE: a rank never arrived")
+            vals = self.comm.red.pop(seq)
+        acc = vals[0]
+        for r in range(1, self.size):                     # rank order (two ranks: the only order there is)
+            acc = acc + vals[r] if op == "mpi_sum" else max(acc, vals[r])
+        return acc
+
+    def barrier(self):
+        self.comm.bar.wait()
+
+
+def run_program(path: str, overrides: dict[str, str] | None = None, nproc: int = 1, externals: dict | None = None,
+                edits: list[tuple[str, str]] | None = None) -> list[dict]:
+    """Executes the main program of `path`; returns the variables of every rank after `end program`.
+    overrides: {parameter name: Fortran expression} replacing the value of a `parameter` declaration;
+    edits: [(regex, replacement)] applied to the (lower-cased) statements first -- for values the reference sets by
+    assignment rather than by parameter (the viscoelastic program's receiver positions);
+    externals: {subroutine name: Python callable} for subroutines that live in another file of the reference (the
+    SolvOpt attenuation fit, which is pinned separately); array arguments are passed by reference."""
+    externals = externals or {}
+    tr = Translator(overrides, externals)
+    lines = logical_lines(path)
+    for pat, repl in edits or []:
+        lines = [re.sub(pat, repl, l) for l in lines]
+    src = tr.translate(lines)
+    code = compile(src, "<transliterated " + path.rsplit("/", 1)[-1] + ">", "exec")
+    comm = _Comm(nproc)
+    spaces, errors = [dict(RUNTIME) for _ in range(nproc)], []
+    for sp in spaces:
+        for name, fn in externals.items():
+            sp["_ext_" + name.lower()] = fn
+
+    def body(r):
+        try:
+            spaces[r]["_mpi"] = _Rank(comm, r)
+            with np.errstate(all="ignore"):
+                exec(code, spaces[r])
+        except BaseException as e:                       # noqa: BLE001 -- reported to the caller below
+            errors.append((r, e))
+
+    threads = [threading.Thread(target=body, args=(r,)) for r in range(nproc)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise RuntimeError(f"rank {errors[0][0]} failed: {errors[0][1]!r}") from errors[0][1]
+    for sp in spaces:
+        sp["_bounds"] = tr.bounds
+    return spaces

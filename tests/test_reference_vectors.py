@@ -1,0 +1,187 @@
+"""The oracle (and the CUDA kernels) against vectors computed by the REFERENCE PROGRAMS THEMSELVES.
+
+tests/golden/ref_*.npz hold what the six reference programs of the hot path computed on reduced grids when their own
+source text was executed (oracle/f90_exec.py: statement-by-statement transliteration of the Fortran main program, IEEE
+double, MPI ranks as threads; generator: tests/golden/make_reference_vectors.py, run where /root/reference exists).
+Everything is compared bit for bit: the C-PML profiles of the set-up, source and receiver indices, seismograms,
+energies, the final wavefields.  (Energy of the four-rank 3-D case: 1e-13 -- MPI_REDUCE does not fix the order in which
+more than two ranks are summed.)
+
+This is the pin of the oracle: the reference holds no golden vectors and cannot be compiled in this image.
+Reference loops: seismic_CPML_3D_isotropic_MPI_OpenMP.f90:399-1181, seismic_CPML_3D_viscoelastic_MPI.f90:476-1440,
+seismic_CPML_2D_isotropic_{second,fourth}_order.f90:270-760,
+seismic_CPML_2D_velocity_and_stress_{second,fourth}_order_viscoelastic.f90:330-1060.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import refcfg
+from oracle import oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = ["ref_3d_iso_np2", "ref_3d_iso_kmax3_np2", "ref_3d_iso_np4", "ref_2d_second", "ref_2d_fourth", "ref_3d_visco_np2",
+         "ref_2d_visco_second", "ref_2d_visco_fourth"]
+F3 = ("vx", "vy", "vz", "sigmaxx", "sigmayy", "sigmazz", "sigmaxy", "sigmaxz", "sigmayz")
+F2 = ("vx", "vy", "sigmaxx", "sigmayy", "sigmaxy")
+
+
+def load(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return g, json.loads(str(g["meta"]))
+
+
+def config(m):
+    """The same reduced configuration, built by the oracle's own set-up functions."""
+    if m["kind"] == "3d_iso":
+        return refcfg.cfg3d(nx=m["nx"], ny=m["ny"], nz=m["nz"], nstep=m["nstep"], npml=m["npml"], k_max=m["k_max"])
+    if m["kind"] == "2d_iso":
+        return refcfg.cfg2d(m["order"], nx=m["nx"], ny=m["ny"], nstep=m["nstep"], npml=m["npml"], ydeb=m["ydeb"], yfin=m["yfin"])
+    if m["kind"] == "3d_visco":
+        return refcfg.cfgv3d(nx=m["nx"], ny=m["ny"], nz=m["nz"], nstep=m["nstep"], npml=m["npml"], rec_scale=m["rec_scale"])
+    return refcfg.cfgv2d(m["order"], nx=m["nx"], ny=m["ny"], nstep=m["nstep"], npml=m["npml"])
+
+
+def check_setup(g, m, c):
+    """Profiles (:399-667 of the 3-D program, the same text in all six), source and receivers of the set-up."""
+    assert (int(g["isource"]), int(g["jsource"])) == (c["isource"], c["jsource"])
+    assert list(g["ix_rec"]) == list(c["ix_rec"]) and list(g["iy_rec"]) == list(c["iy_rec"])
+    assert float(g["deltat"]) == c["deltat"]
+    for ax in ("x", "y", "z") if "nz" in m else ("x", "y"):
+        for k in ("a", "b", "K", "a_half", "b_half", "K_half"):
+            assert np.array_equal(g[f"prof_{ax}_{k}"], np.asarray(c["prof_" + ax][k])), (ax, k)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_equals_the_reference_program(name):
+    g, m = load(name)
+    c = config(m)
+    check_setup(g, m, c)
+    if m["kind"] == "3d_iso":
+        o = O.run_3d_iso(**c, nproc=m["nproc"], want_fields=True)
+        fields = F3
+    elif m["kind"] == "2d_iso":
+        o = O.run_2d(**c, want_fields=True)
+        fields = F2
+    elif m["kind"] == "3d_visco":
+        o = O.run_3d_visco(**{k: v for k, v in c.items() if k != "cp_eff"}, nproc=m["nproc"], want_fields=True)
+        fields = F3
+    else:
+        o = O.run_2d_visco(**c, want_fields=True, compute_energy=True)
+        fields = F2
+    assert np.abs(g["sisvx"]).max() > 0 and np.abs(g["sisvy"]).max() > 0
+    assert np.array_equal(o["sisvx"], g["sisvx"]) and np.array_equal(o["sisvy"], g["sisvy"])
+    if "sispressure" in g:
+        assert np.array_equal(o["sispressure"], g["sispressure"])
+    for f in fields:
+        assert np.abs(g[f]).max() > 0
+        assert np.array_equal(np.asarray(o[f]).reshape(g[f].shape), g[f]), f
+    for k in ("total_energy", "energy_kinetic", "energy_potential"):
+        if k in g and k in o:
+            assert np.abs(g[k]).max() > 0
+            if m.get("nproc", 1) > 2:
+                assert refcfg.rel_l2(o[k], g[k]) <= 1e-13, k
+            else:
+                assert np.array_equal(o[k], g[k]), k
+
+
+# ------------------------------------------------------------------------------------------------ CUDA path
+
+def _solver3d(L, c, **kw):
+    s = L.Solver(ndim=3, order=2, nx=c["nx"], ny=c["ny"], nz=c["nz"], nstep=c["nstep"], npoints_pml=c["npoints_pml"],
+                 nrec=len(c["ix_rec"]), isource=c["isource"], jsource=c["jsource"], deltax=c["deltax"], deltay=c["deltay"],
+                 deltaz=c["deltaz"], deltat=c["deltat"], lam=c["lam"], mu=c["mu"], lambdaplustwomu=c["lambdaplustwomu"],
+                 rho=c["rho"], cp=3300.0, **kw)
+    s.set_profiles(L.AXIS_X, c["prof_x"]); s.set_profiles(L.AXIS_Y, c["prof_y"]); s.set_profiles(L.AXIS_Z, c["prof_z"])
+    s.set_source_series(c["force_x"], c["force_y"])
+    s.set_receivers(c["ix_rec"], c["iy_rec"])
+    return s
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ref_3d_iso_np2", "ref_3d_iso_kmax3_np2", "ref_3d_iso_np4"])
+def test_cuda_3d_isotropic_equals_the_reference_program(name):
+    """The C ABI on the GPU against the reference program's own numbers: fields and seismograms bit for bit, energy to
+    1e-11 (its sum is ordered differently, quirk B11)."""
+    from seismic_cpml_b200 import lib as L
+    g, m = load(name)
+    c = config(m)
+    with _solver3d(L, c) as s:
+        s.run(1, c["nstep"])
+        sx, sy = s.get_seismograms()
+        assert np.array_equal(sx, g["sisvx"]) and np.array_equal(sy, g["sisvy"])
+        for f, fname in enumerate(F3):
+            assert np.array_equal(s.get_field(f), g[fname]), fname
+        assert refcfg.rel_l2(s.get_energy()[0], g["total_energy"]) <= 1e-11
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ref_2d_second", "ref_2d_fourth"])
+def test_cuda_2d_isotropic_equals_the_reference_program(name):
+    from seismic_cpml_b200 import lib as L
+    g, m = load(name)
+    c = config(m)
+    s = L.Solver(ndim=2, order=c["order"], nx=c["nx"], ny=c["ny"], nstep=c["nstep"], npoints_pml=c["npoints_pml"],
+                 nrec=len(c["ix_rec"]), isource=c["isource"], jsource=c["jsource"], deltax=c["deltax"], deltay=c["deltay"],
+                 deltat=c["deltat"], cp=3300.0)
+    with s:
+        s.set_profiles(L.AXIS_X, c["prof_x"]); s.set_profiles(L.AXIS_Y, c["prof_y"])
+        s.set_material_2d(c["lam"], c["mu"], c["rho"])
+        s.set_source_series(c["force_x"], c["force_y"])
+        s.set_receivers(c["ix_rec"], c["iy_rec"])
+        s.run(1, c["nstep"])
+        sx, sy = s.get_seismograms()
+        assert np.array_equal(sx, g["sisvx"]) and np.array_equal(sy, g["sisvy"])
+        for f, fname in enumerate(F2):
+            assert np.array_equal(s.get_field(f), g[fname]), fname
+        _, ek, ep = s.get_energy()
+        assert refcfg.rel_l2(ek, g["energy_kinetic"]) <= 1e-11 and refcfg.rel_l2(ep, g["energy_potential"]) <= 1e-11
+
+
+@pytest.mark.gpu
+def test_cuda_3d_viscoelastic_equals_the_reference_program():
+    from seismic_cpml_b200 import lib as L
+    g, m = load("ref_3d_visco_np2")
+    c = config(m)
+    s = L.Solver(ndim=3, order=4, rheology=1, emulate_nproc=m["nproc"], nx=c["nx"], ny=c["ny"], nz=c["nz"], nstep=c["nstep"],
+                 npoints_pml=c["npoints_pml"], nrec=len(c["ix_rec"]), isource=c["isource"], jsource=c["jsource"],
+                 deltax=c["deltax"], deltay=c["deltay"], deltaz=c["deltaz"], deltat=c["deltat"], lam=c["lam"], mu=c["mu"],
+                 rho=c["rho"], cp=c["cp_eff"])
+    with s:
+        s.set_profiles(L.AXIS_X, c["prof_x"]); s.set_profiles(L.AXIS_Y, c["prof_y"]); s.set_profiles(L.AXIS_Z, c["prof_z"])
+        s.set_attenuation(c["tau_epsilon_nu1"], c["tau_sigma_nu1"], c["tau_epsilon_nu2"], c["tau_sigma_nu2"])
+        s.set_source_series(c["force_x"], c["force_y"])
+        s.set_receivers(c["ix_rec"], c["iy_rec"])
+        s.run(1, c["nstep"])
+        sx, sy = s.get_seismograms()
+        assert np.array_equal(sx, g["sisvx"]) and np.array_equal(sy, g["sisvy"])
+        for f, fname in enumerate(F3):
+            assert np.array_equal(s.get_field(f), g[fname]), fname
+        assert refcfg.rel_l2(s.get_energy()[0], g["total_energy"]) <= 1e-11
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ref_2d_visco_second", "ref_2d_visco_fourth"])
+def test_cuda_2d_viscoelastic_equals_the_reference_program(name):
+    from seismic_cpml_b200 import lib as L
+    g, m = load(name)
+    c = config(m)
+    s = L.Solver(ndim=2, order=c["order"], rheology=1, compute_energy=True, nx=c["nx"], ny=c["ny"], nstep=c["nstep"],
+                 npoints_pml=c["npoints_pml"], nrec=len(c["ix_rec"]), isource=c["isource"], jsource=c["jsource"],
+                 deltax=c["deltax"], deltay=c["deltay"], deltat=c["deltat"], cp=0.0)
+    with s:
+        s.set_profiles(L.AXIS_X, c["prof_x"]); s.set_profiles(L.AXIS_Y, c["prof_y"])
+        s.set_material_2d(c["lam"], c["mu"], c["rho"])
+        s.set_attenuation(c["tau_epsilon_nu1"], c["tau_sigma_nu1"], c["tau_epsilon_nu2"], c["tau_sigma_nu2"])
+        s.set_source_series(c["force_x"], c["force_y"])
+        s.set_receivers(c["ix_rec"], c["iy_rec"])
+        s.run(1, c["nstep"])
+        sx, sy = s.get_seismograms()
+        assert np.array_equal(sx, g["sisvx"]) and np.array_equal(sy, g["sisvy"])
+        assert np.array_equal(s.get_pressure_seismograms(), g["sispressure"])
+        for f, fname in enumerate(F2):
+            assert np.array_equal(s.get_field(f), g[fname]), fname
+        _, ek, ep = s.get_energy()
+        assert refcfg.rel_l2(ek, g["energy_kinetic"]) <= 1e-11 and refcfg.rel_l2(ep, g["energy_potential"]) <= 1e-11
