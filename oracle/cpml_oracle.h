@@ -6,13 +6,21 @@
  * --impl reference legs.  Nothing under seismic_cpml_b200/ may include, link
  * or call this.
  *
- * PARITY UNPINNED: the reference is Fortran90 and no Fortran compiler (nor MPI)
- * exists in this image or on the GPU box, and the reference ships no golden
- * vectors, so this restatement cannot be checked against reference output.
- * It is pinned instead by (i) closed-form setup constants,
- * (ii) an independent numpy restatement (oracle/np_restatement.py) that must
- * agree bit-for-bit on the seismograms, (iii) slab-count invariance of the 3-D
- * code.  Every function cites the reference file:line it follows.
+ * PARITY PINNED BY AN EXECUTION OF THE REFERENCE SOURCE: the reference is
+ * Fortran90, no Fortran compiler (nor MPI) exists in this image or on the GPU
+ * box, and the reference ships no golden vectors.  oracle/f90_exec.py therefore
+ * executes the main program of each reference .f90 file from its own source
+ * text (statement-by-statement transliteration to Python, IEEE double, source
+ * order, MPI ranks as threads); tests/golden/ref_*.npz hold what the six
+ * programs computed that way on reduced grids, and this restatement reproduces
+ * every one of them bit for bit (tests/test_reference_vectors.py: profiles,
+ * receivers, seismograms, energies, final fields).  It is not the compiled
+ * reference: a gfortran build could differ where a compiler contracts or
+ * reassociates.  Further pins: (i) closed-form setup constants (SURVEY.md App.
+ * C.1), (ii) an independent numpy restatement (oracle/np_restatement.py) that
+ * agrees bit-for-bit, (iii) slab-count invariance of the 3-D code, (iv)
+ * closed-form physical solutions.  Every function cites the reference
+ * file:line it follows.
  *
  * All arrays are Fortran-ordered (i fastest) so that they can be compared with
  * the reference's arrays index by index.  All indices crossing this API are

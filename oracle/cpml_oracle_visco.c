@@ -1,6 +1,6 @@
 /*
  * cpml_oracle_visco.c -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
- * See cpml_oracle.h for the contract and the "PARITY UNPINNED" statement.
+ * See cpml_oracle.h for the contract and how parity is pinned (an execution of the reference source, oracle/f90_exec.py).
  *
  * Restates, loop nest by loop nest and operation by operation, the hot path of
  *   /root/reference/seismic_CPML_3D_viscoelastic_MPI.f90   (3D-visco)

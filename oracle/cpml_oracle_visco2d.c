@@ -1,6 +1,6 @@
 /*
  * cpml_oracle_visco2d.c -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
- * See cpml_oracle.h for the contract and the "PARITY UNPINNED" statement.
+ * See cpml_oracle.h for the contract and how parity is pinned (an execution of the reference source, oracle/f90_exec.py).
  *
  * Restates, loop nest by loop nest and operation by operation, the hot paths of
  *   /root/reference/seismic_CPML_2D_velocity_and_stress_fourth_order_viscoelastic.f90  (2D-visco-4th)

@@ -1,7 +1,8 @@
 """ctypes front-end of the CPU oracle (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
-legs may import this module.  PARITY UNPINNED -- see oracle/cpml_oracle.h.
+legs may import this module.  Parity is pinned by an execution of the reference source (oracle/f90_exec.py,
+tests/test_reference_vectors.py) -- see oracle/cpml_oracle.h.
 
 Two builds of the same C file (oracle/Makefile):
   golden -- gcc -O2 -ffp-contract=off, serial: the parity checker;
