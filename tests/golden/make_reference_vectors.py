@@ -45,6 +45,8 @@ CASES = {
                           nx=30, ny=44, npml=5, nstep=150, ydeb=300.0, yfin=80.0),
     "ref_3d_visco_np2": dict(kind="3d_visco", program="seismic_CPML_3D_viscoelastic_MPI.f90",
                              nx=32, ny=30, nz=12, npml=4, nstep=60, nproc=2, rec_scale=0.04),
+    "ref_3d_visco_np4": dict(kind="3d_visco", program="seismic_CPML_3D_viscoelastic_MPI.f90",       # quirk B6 depends on NPROC
+                             nx=32, ny=30, nz=16, npml=4, nstep=50, nproc=4, rec_scale=0.04),
     "ref_2d_visco_second": dict(kind="2d_visco", program="seismic_CPML_2D_velocity_and_stress_second_order_viscoelastic.f90",
                                 order=2, nx=61, ny=71, npml=5, nstep=220),
     "ref_2d_visco_fourth": dict(kind="2d_visco", program="seismic_CPML_2D_velocity_and_stress_fourth_order_viscoelastic.f90",
