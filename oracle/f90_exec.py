@@ -160,7 +160,12 @@ class _DivPow(ast.NodeTransformer):
 
 
 class Translator:
-    def __init__(self, overrides: dict[str, str] | None = None, externals=()):
+    def __init__(self, overrides: dict[str, str] | None = None, externals=(), single: bool = False):
+        # single: the reference's single-precision build ("declare everything real", 3D-iso :114-116): every
+        # `double precision` entity is a 4-byte real; literals keep their own kind (1.d0 stays double), so mixed
+        # expressions are evaluated in double and rounded when they are assigned, as the compiled program would
+        self.single = single
+        self.real_scalars: set[str] = set()
         self.overrides = {k.lower(): v for k, v in (overrides or {}).items()}
         self.externals = {e.lower() for e in externals}          # external subroutines supplied by the caller
         self.bounds: dict[str, list[tuple[str, str]]] = {}      # array name -> [(lo, hi)] as Python expressions
@@ -171,7 +176,7 @@ class Translator:
     # ---- expressions
     def expr(self, s: str) -> str:
         s = _rename_keywords(s.strip())
-        s = _NUM_D.sub(r"\1e\2", s)
+        s = _NUM_D.sub(r"_dbl(\1e\2)" if self.single else r"\1e\2", s)
         for a, b in ((".and.", " and "), (".or.", " or "), (".not.", " not "), (".true.", " True "), (".false.", " False "),
                      (".eq.", "=="), (".ne.", "!="), (".lt.", "<"), (".le.", "<="), (".gt.", ">"), (".ge.", ">=")):
             s = s.replace(a, b)
@@ -240,8 +245,9 @@ class Translator:
         if dm:
             o = attrs.index("(", dm.start())
             dims = attrs[o + 1:_match_paren(attrs, o)]
-        zero = "0" if kind == "integer" else ("False" if kind == "logical" else "0.0")
-        dtype = "np.int64" if kind == "integer" else "np.float64"
+        real = kind in ("double precision", "real")
+        zero = "0" if kind == "integer" else ("False" if kind == "logical" else ("np.float32(0.0)" if self.single else "0.0"))
+        dtype = "np.int64" if kind == "integer" else ("np.float32" if self.single else "np.float64")
         for ent in _split_top(_rename_keywords(ents)):
             if not ent:
                 continue
@@ -249,7 +255,12 @@ class Translator:
                 name, val = ent.split("=", 1)
                 name = name.strip()
                 val = self.overrides.get(name, val)
-                self.emit(f"{name} = _toint({self.expr(val)})" if kind == "integer" else f"{name} = {self.expr(val)}")
+                if kind == "integer":
+                    self.emit(f"{name} = _toint({self.expr(val)})")
+                elif real and self.single:
+                    self.emit(f"{name} = np.float32({self.expr(val)})")
+                else:
+                    self.emit(f"{name} = {self.expr(val)}")
                 continue
             edims = dims
             name = ent.strip()
@@ -260,6 +271,8 @@ class Translator:
             if edims is None:
                 if kind == "integer":
                     self.int_scalars.add(name)
+                elif real:
+                    self.real_scalars.add(name)
                 self.emit(f"{name} = {zero}")
             else:
                 b = []
@@ -370,6 +383,8 @@ class Translator:
                 lhs, rhs = s[:n].strip(), s[n + 1:].strip()
                 if lhs in self.int_scalars:
                     self.emit(f"{lhs} = _toint({self.expr(rhs)})")
+                elif self.single and _rename_keywords(lhs) in self.real_scalars:
+                    self.emit(f"{_rename_keywords(lhs)} = np.float32({self.expr(rhs)})")
                 else:
                     self.emit(f"{self._arrays(_rename_keywords(lhs))} = {self.expr(rhs)}")
                 return
@@ -393,7 +408,9 @@ def _div(a, b):
     if isinstance(a, (int, np.integer)) and isinstance(b, (int, np.integer)) and not isinstance(a, bool):
         q = abs(int(a)) // abs(int(b))
         return q if (a >= 0) == (b >= 0) else -q          # Fortran integer division truncates towards zero
-    return np.float64(a) / np.float64(b) if not isinstance(a, np.ndarray) and not isinstance(b, np.ndarray) else a / b
+    if isinstance(a, (np.ndarray, np.floating)) or isinstance(b, (np.ndarray, np.floating)):
+        return a / b                                      # numpy kinds: real / real stays real, real / double is double
+    return np.float64(a) / np.float64(b)
 
 
 def _toint(x):
@@ -412,7 +429,7 @@ def _pow(a, b):
             return a
         if n == 3:
             return a * a * a
-    return np.float64(math.pow(float(a), float(b)))
+    return type(a)(math.pow(float(a), float(b))) if isinstance(a, np.floating) else np.float64(math.pow(float(a), float(b)))
 
 
 def _range(a, b, step=1):
@@ -427,26 +444,29 @@ def _mod(a, b):
 
 def _elementwise(f_scalar, f_array):
     def f(x):
-        return f_array(x) if isinstance(x, np.ndarray) else np.float64(f_scalar(x))
+        if isinstance(x, np.ndarray) or isinstance(x, np.float32):
+            return f_array(x)                             # the 4-byte routine for a 4-byte argument
+        return np.float64(f_scalar(x))
     return f
 
 
 def _sum(a):
     """SUM of an array expression the way a compiler without -ffast-math does it: one accumulator, array element order
     (first index fastest)."""
-    a = np.asarray(a, dtype=np.float64)
-    return np.float64(np.cumsum(a.T.ravel())[-1]) if a.size else np.float64(0.0)
+    a = np.asarray(a)
+    return np.cumsum(a.T.ravel(), dtype=a.dtype)[-1] if a.size else a.dtype.type(0.0)
 
 
 RUNTIME = {
     "np": np, "FortranStop": FortranStop, "_div": _div, "_pow": _pow, "_range": _range, "_toint": _toint,
     "dble": lambda x: np.float64(x), "real": lambda x: np.float64(x), "sngl": lambda x: np.float32(x), "int": lambda x: int(x),
+    "_dbl": np.float64,
     "exp": _elementwise(math.exp, np.exp), "log": _elementwise(math.log, np.log), "sqrt": _elementwise(math.sqrt, np.sqrt),
     "sin": _elementwise(math.sin, np.sin), "cos": _elementwise(math.cos, np.cos), "abs": abs, "max": max, "min": min,
     "dsqrt": _elementwise(math.sqrt, np.sqrt), "dexp": _elementwise(math.exp, np.exp), "dlog": _elementwise(math.log, np.log),
     "dsin": _elementwise(math.sin, np.sin), "dcos": _elementwise(math.cos, np.cos), "dabs": abs, "atan": _elementwise(math.atan, np.arctan),
     "dmax1": max, "dmin1": min, "nint": lambda x: int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5)), "float": lambda x: np.float64(x),
-    "mod": _mod, "sum": _sum, "maxval": lambda a: np.float64(np.max(a)), "minval": lambda a: np.float64(np.min(a)),
+    "mod": _mod, "sum": _sum, "maxval": lambda a: np.max(a), "minval": lambda a: np.min(a),
     "mpi_proc_null": -1, "mpi_comm_world": 0, "mpi_double_precision": 0, "mpi_sum": "mpi_sum", "mpi_max": "mpi_max",
     "mpi_status_size": 1,
 }
@@ -493,15 +513,16 @@ class _Rank:
 
 
 def run_program(path: str, overrides: dict[str, str] | None = None, nproc: int = 1, externals: dict | None = None,
-                edits: list[tuple[str, str]] | None = None) -> list[dict]:
+                edits: list[tuple[str, str]] | None = None, single: bool = False) -> list[dict]:
     """Executes the main program of `path`; returns the variables of every rank after `end program`.
     overrides: {parameter name: Fortran expression} replacing the value of a `parameter` declaration;
     edits: [(regex, replacement)] applied to the (lower-cased) statements first -- for values the reference sets by
     assignment rather than by parameter (the viscoelastic program's receiver positions);
+    single: the single-precision build the reference endorses (every `double precision` entity a 4-byte real);
     externals: {subroutine name: Python callable} for subroutines that live in another file of the reference (the
     SolvOpt attenuation fit, which is pinned separately); array arguments are passed by reference."""
     externals = externals or {}
-    tr = Translator(overrides, externals)
+    tr = Translator(overrides, externals, single)
     lines = logical_lines(path)
     for pat, repl in edits or []:
         lines = [re.sub(pat, repl, l) for l in lines]

@@ -39,6 +39,10 @@ CASES = {
                                  nx=16, ny=18, nz=12, npml=3, nstep=40, nproc=2, k_max=3.0),
     "ref_3d_iso_np4": dict(kind="3d_iso", program="seismic_CPML_3D_isotropic_MPI_OpenMP.f90",
                            nx=16, ny=18, nz=16, npml=3, nstep=30, nproc=4, k_max=1.0),
+    # the single-precision build the reference endorses (:114-116, "declare everything real"): every double precision
+    # entity a 4-byte real, literals keep their kind -- the tolerance datum of cpml_config.precision = 1
+    "ref_3d_iso_single_np2": dict(kind="3d_iso", program="seismic_CPML_3D_isotropic_MPI_OpenMP.f90",
+                                  nx=20, ny=24, nz=12, npml=4, nstep=80, nproc=2, k_max=1.0, single=True),
     "ref_2d_second": dict(kind="2d_iso", program="seismic_CPML_2D_isotropic_second_order.f90", order=2,
                           nx=30, ny=44, npml=5, nstep=150, ydeb=300.0, yfin=80.0),
     "ref_2d_fourth": dict(kind="2d_iso", program="seismic_CPML_2D_isotropic_fourth_order.f90", order=4,
@@ -85,7 +89,7 @@ def run_case(name):
     if c["kind"] == "3d_iso":
         ov = {"NX": c["nx"], "NY": c["ny"], "NZ": c["nz"], "NPROC": c["nproc"], "NSTEP": c["nstep"], "NPOINTS_PML": c["npml"],
               "K_MAX_PML": f"{c['k_max']!r}d0", "ydeb": f"{(c['ny'] // 3) * 10}.d0", "yfin": "30.d0"}     # receivers as in refcfg.cfg3d
-        sp = F.run_program(path, {k: str(v) for k, v in ov.items()}, nproc=c["nproc"])
+        sp = F.run_program(path, {k: str(v) for k, v in ov.items()}, nproc=c["nproc"], single=c.get("single", False))
         r = sp[sp[0]["rank_cut_plane"]]
         nzl = c["nz"] // c["nproc"]
         out.update(_profiles(r, "xyz"))

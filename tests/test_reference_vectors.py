@@ -188,3 +188,28 @@ def test_cuda_2d_viscoelastic_equals_the_reference_program(name):
             assert np.array_equal(s.get_field(f), g[fname]), fname
         _, ek, ep = s.get_energy()
         assert refcfg.rel_l2(ek, g["energy_kinetic"]) <= 1e-11 and refcfg.rel_l2(ep, g["energy_potential"]) <= 1e-11
+
+
+def test_fp32_mode_against_the_reference_single_precision_build():
+    """cpml_config.precision = 1 and the single-precision build the reference endorses (3D-iso :114-116: "declare
+    everything real") are two different roundings of the same program: in the reference build the set-up runs in single
+    precision too and the energy is accumulated in single; here profiles and constants are rounded once from their double
+    values and the energy is summed in double.  The FP32 restatement (which the CUDA kernels match bit for bit,
+    tests/test_gpu_f32.py) must agree with the reference build, executed from its source with every `double precision`
+    entity as a 4-byte real, to north_star's 1e-5 -- and sits closer to the double-precision reference than that build."""
+    from oracle.np_restatement import run_3d_iso_np
+    g, m = load("ref_3d_iso_single_np2")
+    assert g["vx"].dtype == np.float32 and g["sisvx"].dtype == np.float32
+    c = config(m)
+    o32 = run_3d_iso_np(**c, dtype=np.float32)
+    o64 = O.run_3d_iso(**c, nproc=m["nproc"], want_fields=True)
+    d = lambda a: np.asarray(a, dtype=np.float64)
+    ours_vs_build = max(refcfg.rel_l2(d(o32[k]), d(g[k])) for k in ("sisvx", "sisvy") + F3)
+    build_vs_double = max(refcfg.rel_l2(d(g[k]), o64[k]) for k in ("sisvx", "sisvy") + F3)
+    ours_vs_double = max(refcfg.rel_l2(d(o32[k]), o64[k]) for k in ("sisvx", "sisvy") + F3)
+    e_build, e_ours = refcfg.rel_l2(d(g["total_energy"]), o64["total_energy"]), refcfg.rel_l2(o32["total_energy"], o64["total_energy"])
+    print(f"FP32 mode vs reference single-precision build {ours_vs_build:.2e}; vs the double-precision reference: build "
+          f"{build_vs_double:.2e}, FP32 mode {ours_vs_double:.2e}; energy: build {e_build:.2e}, FP32 mode {e_ours:.2e}")
+    assert np.abs(o64["sisvx"]).max() > 1e-3
+    assert ours_vs_build <= 1e-5 and build_vs_double <= 1e-5 and ours_vs_double <= 1e-5
+    assert ours_vs_double <= build_vs_double and e_ours <= e_build
