@@ -213,3 +213,27 @@ def test_fp32_mode_against_the_reference_single_precision_build():
     assert np.abs(o64["sisvx"]).max() > 1e-3
     assert ours_vs_build <= 1e-5 and build_vs_double <= 1e-5 and ours_vs_double <= 1e-5
     assert ours_vs_double <= build_vs_double and e_ours <= e_build
+
+
+@pytest.mark.parametrize("name", ["ref_2d_second_default", "ref_2d_fourth_default_1500"])
+def test_oracle_equals_the_2d_reference_programs_at_their_default_configuration(name):
+    """The two 2-D programs exactly as shipped -- 101 x 641 points, the reference's source and receivers, all 2000 time
+    steps of the second-order program (the fourth-order one stopped after 1500 of its 4000: the wave has passed both
+    receivers) -- executed from their source text (hours of Python, done once: tests/golden/make_reference_vectors.py).
+    Seismograms and energies bit for bit; the final fields through their SHA-256."""
+    import hashlib
+    fn = os.path.join(GOLDEN, name + ".npz")
+    if not os.path.exists(fn):
+        pytest.skip("vector not generated")
+    g, m = load(name)
+    assert (m["nx"], m["ny"], m["npml"]) == (101, 641, 10)
+    c = refcfg.cfg2d(m["order"], nstep=m["nstep"])
+    check_setup(g, m, c)
+    assert list(g["ix_rec"]) == [70, 80] and list(g["iy_rec"]) == [231, 31]          # SURVEY.md App. C.1
+    o = O.run_2d(**c, want_fields=True)
+    assert np.abs(g["sisvx"][1]).max() > 1e-3                    # the far receiver has seen the wave
+    assert np.array_equal(o["sisvx"], g["sisvx"]) and np.array_equal(o["sisvy"], g["sisvy"])
+    assert np.array_equal(o["energy_kinetic"], g["energy_kinetic"]) and np.array_equal(o["energy_potential"], g["energy_potential"])
+    for f in F2:
+        h = hashlib.sha256(np.ascontiguousarray(np.asarray(o[f]).reshape(m["ny"], m["nx"]), dtype=np.float64).tobytes()).hexdigest()
+        assert h == str(g["sha256_" + f]), f
