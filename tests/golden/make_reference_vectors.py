@@ -47,12 +47,16 @@ CASES = {
                           nx=30, ny=44, npml=5, nstep=150, ydeb=300.0, yfin=80.0),
     "ref_2d_fourth": dict(kind="2d_iso", program="seismic_CPML_2D_isotropic_fourth_order.f90", order=4,
                           nx=30, ny=44, npml=5, nstep=150, ydeb=300.0, yfin=80.0),
-    # the 2-D programs AT THEIR DEFAULT CONFIGURATION (101 x 641, the receivers of the reference): hours of Python, so
-    # they are not part of a plain run of this script (name them on the command line); fields are stored as SHA-256
+    # the programs AT THEIR DEFAULT CONFIGURATION: the 2-D ones exactly as shipped (101 x 641, all 2000 / 4000 steps), the
+    # 3-D one on its own x-y grid, source and receivers with NZ = 32 on two ranks for 1000 steps (both receivers have
+    # seen the wave).  These use the vectorising mode of f90_exec (bit-identical to the scalar one, checked on every
+    # array of the small cases) and take minutes to an hour: name them on the command line.  Fields: SHA-256.
     "ref_2d_second_default": dict(kind="2d_iso", program="seismic_CPML_2D_isotropic_second_order.f90", order=2,
                                   default=True, slow=True),
-    "ref_2d_fourth_default_1500": dict(kind="2d_iso", program="seismic_CPML_2D_isotropic_fourth_order.f90", order=4,
-                                       default=True, nstep=1500, slow=True),
+    "ref_2d_fourth_default": dict(kind="2d_iso", program="seismic_CPML_2D_isotropic_fourth_order.f90", order=4,
+                                  default=True, slow=True),
+    "ref_3d_iso_xy_default": dict(kind="3d_iso", program="seismic_CPML_3D_isotropic_MPI_OpenMP.f90", default=True, slow=True,
+                                  nz=32, nproc=2, nstep=1000, k_max=1.0),
     "ref_3d_visco_np2": dict(kind="3d_visco", program="seismic_CPML_3D_viscoelastic_MPI.f90",
                              nx=32, ny=30, nz=12, npml=4, nstep=60, nproc=2, rec_scale=0.04),
     "ref_3d_visco_np4": dict(kind="3d_visco", program="seismic_CPML_3D_viscoelastic_MPI.f90",       # quirk B6 depends on NPROC
@@ -93,10 +97,15 @@ def run_case(name):
     path = os.path.join(REF, c["program"])
     out = {}
     if c["kind"] == "3d_iso":
-        ov = {"NX": c["nx"], "NY": c["ny"], "NZ": c["nz"], "NPROC": c["nproc"], "NSTEP": c["nstep"], "NPOINTS_PML": c["npml"],
-              "K_MAX_PML": f"{c['k_max']!r}d0", "ydeb": f"{(c['ny'] // 3) * 10}.d0", "yfin": "30.d0"}     # receivers as in refcfg.cfg3d
-        sp = F.run_program(path, {k: str(v) for k, v in ov.items()}, nproc=c["nproc"], single=c.get("single", False))
+        if c.get("default"):          # the program's own x-y grid, source and receivers; only NZ, NPROC, NSTEP differ
+            ov = {"NZ": c["nz"], "NPROC": c["nproc"], "NSTEP": c["nstep"]}
+        else:
+            ov = {"NX": c["nx"], "NY": c["ny"], "NZ": c["nz"], "NPROC": c["nproc"], "NSTEP": c["nstep"], "NPOINTS_PML": c["npml"],
+                  "K_MAX_PML": f"{c['k_max']!r}d0", "ydeb": f"{(c['ny'] // 3) * 10}.d0", "yfin": "30.d0"}     # receivers as in refcfg.cfg3d
+        sp = F.run_program(path, {k: str(v) for k, v in ov.items()}, nproc=c["nproc"], single=c.get("single", False),
+                           vectorize=c.get("default", False))
         r = sp[sp[0]["rank_cut_plane"]]
+        c = dict(c, nx=int(r["nx"]), ny=int(r["ny"]), npml=int(r["npoints_pml"]))
         nzl = c["nz"] // c["nproc"]
         out.update(_profiles(r, "xyz"))
         out.update(sisvx=r["sisvx"].T, sisvy=r["sisvy"].T, total_energy=r["total_energy"])
@@ -108,7 +117,7 @@ def run_case(name):
         else:
             ov = {"NX": c["nx"], "NY": c["ny"], "NSTEP": c["nstep"], "NPOINTS_PML": c["npml"],
                   "ydeb": f"{c['ydeb']!r}d0", "yfin": f"{c['yfin']!r}d0"}
-        r = F.run_program(path, {k: str(v) for k, v in ov.items()})[0]
+        r = F.run_program(path, {k: str(v) for k, v in ov.items()}, vectorize=c.get("default", False))[0]
         c = dict(c, nx=int(r["nx"]), ny=int(r["ny"]), nstep=int(r["nstep"]), npml=int(r["npoints_pml"]))
         out.update(_profiles(r, "xy"))
         out.update(sisvx=r["sisvx"].T, sisvy=r["sisvy"].T, energy_kinetic=r["total_energy_kinetic"],
@@ -148,8 +157,9 @@ def run_case(name):
                deltat=float(r["deltat"]))
     if c.get("default"):              # full-size fields: their SHA-256 instead of the arrays
         import hashlib
-        for f in ("vx", "vy", "sigmaxx", "sigmayy", "sigmaxy"):
-            out["sha256_" + f] = hashlib.sha256(np.ascontiguousarray(out.pop(f), dtype=np.float64).tobytes()).hexdigest()
+        for f in ("vx", "vy", "vz", "sigmaxx", "sigmayy", "sigmazz", "sigmaxy", "sigmaxz", "sigmayz"):
+            if f in out:
+                out["sha256_" + f] = hashlib.sha256(np.ascontiguousarray(out.pop(f), dtype=np.float64).tobytes()).hexdigest()
     out["meta"] = json.dumps(dict(case=name, **c))
     return out
 

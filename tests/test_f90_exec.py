@@ -164,3 +164,68 @@ def test_live_reference_run_equals_the_oracle():
     for f in ("vx", "vz", "sigmaxx", "sigmayz"):
         g = np.concatenate([q[f][:, :, 1:nz // 2 + 1] for q in sp], axis=2).transpose(2, 1, 0)
         assert np.array_equal(g, o[f]), f
+
+
+VEC_SRC = """
+  program t
+  implicit none
+  integer, parameter :: NX = 7, NY = 5
+  double precision, dimension(0:NX+1,0:NY+1) :: u, w
+  double precision, dimension(NX) :: bx
+  double precision, dimension(NY) :: acc
+  double precision :: d, total, chain
+  integer :: i, j
+  do j = 0,NY+1
+    do i = 0,NX+1
+      u(i,j) = 1.d0 / dble(3 + i + 10*j)
+    enddo
+  enddo
+  do i = 1,NX
+    bx(i) = 0.5d0 + 0.1d0*dble(i)
+  enddo
+  total = 0.d0
+  acc(:) = 0.d0
+  do j = 1,NY
+    do i = 1,NX
+      d = (u(i+1,j) - u(i-1,j)) * bx(i)           ! private scalar, neighbours of an array that is not written
+      w(i,j) = bx(i) * w(i,j) + d / 3.d0          ! read-modify-write at (i,j) itself
+      d = d + u(i,j+1)
+      total = total + d * 1.d16                   ! ordered accumulation into a scalar
+      acc(3) = acc(3) + d                         ! ... and into one array element
+    enddo
+  enddo
+  chain = 0.d0
+  do i = 1,NX
+    w(i,1) = w(i-1,1) + u(i,1)                    ! a true dependence between iterations: must stay a loop
+  enddo
+  end program t
+  """
+
+
+def test_vectorised_loops_give_the_same_bits_and_keep_true_dependences_sequential(tmp_path):
+    a = run(tmp_path, VEC_SRC)[0]
+    b = run(tmp_path, VEC_SRC, vectorize=True)[0]
+    for k in ("u", "w", "bx", "acc"):
+        assert np.array_equal(a[k], b[k]), k
+    # (the private scalar d holds an array after a vectorised loop: like the PRIVATE variables of the reference's OpenMP
+    # loops it is undefined afterwards, and no program reads one)
+    assert a["total"] == b["total"] and a["total"] != 0.0
+    assert a["w"][7, 1] == sum(a["u"][1:8, 1].tolist()) or abs(a["w"][7, 1] - a["u"][1:8, 1].sum()) < 1e-15
+    p = tmp_path / "t.f90"
+    tr = F.Translator(vectorize=True)
+    src = tr.translate(F.logical_lines(str(p)))
+    assert src.count("np.arange(") == 5            # the u nest (2), the bx loop (1), the w nest (2); not the chain loop
+    assert src.count("_accumulate(") == 2
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "seismic_CPML_3D_isotropic_MPI_OpenMP.f90")),
+                    reason="the reference tree is not on this machine")
+def test_live_vectorised_run_equals_the_statement_by_statement_run_on_every_array():
+    ov = {"NX": "12", "NY": "14", "NZ": "8", "NPROC": "2", "NSTEP": "10", "NPOINTS_PML": "2", "ydeb": "40.d0", "yfin": "30.d0"}
+    path = os.path.join(REF, "seismic_CPML_3D_isotropic_MPI_OpenMP.f90")
+    a = F.run_program(path, ov, nproc=2)
+    b = F.run_program(path, ov, nproc=2, vectorize=True)
+    for r in range(2):
+        for k in a[r]["_bounds"]:
+            assert np.array_equal(a[r][k], b[r][k]), (r, k)
+    assert np.abs(a[0]["sisvx"]).max() > 0

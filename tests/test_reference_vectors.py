@@ -215,18 +215,22 @@ def test_fp32_mode_against_the_reference_single_precision_build():
     assert ours_vs_double <= build_vs_double and e_ours <= e_build
 
 
-@pytest.mark.parametrize("name", ["ref_2d_second_default", "ref_2d_fourth_default_1500"])
-def test_oracle_equals_the_2d_reference_programs_at_their_default_configuration(name):
-    """The two 2-D programs exactly as shipped -- 101 x 641 points, the reference's source and receivers, all 2000 time
-    steps of the second-order program (the fourth-order one stopped after 1500 of its 4000: the wave has passed both
-    receivers) -- executed from their source text (hours of Python, done once: tests/golden/make_reference_vectors.py).
-    Seismograms and energies bit for bit; the final fields through their SHA-256."""
+def _sha(a, shape):
     import hashlib
+    return hashlib.sha256(np.ascontiguousarray(np.asarray(a).reshape(shape), dtype=np.float64).tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("name", ["ref_2d_second_default", "ref_2d_fourth_default"])
+def test_oracle_equals_the_2d_reference_programs_at_their_default_configuration(name):
+    """The two 2-D programs exactly as shipped -- 101 x 641 points, the reference's source and receivers, all 2000 /
+    4000 time steps -- executed from their source text (f90_exec in its vectorising mode, which is bit-identical to the
+    statement-by-statement one on every array of the small cases).  Seismograms and energies bit for bit; the final
+    fields through their SHA-256."""
     fn = os.path.join(GOLDEN, name + ".npz")
     if not os.path.exists(fn):
         pytest.skip("vector not generated")
     g, m = load(name)
-    assert (m["nx"], m["ny"], m["npml"]) == (101, 641, 10)
+    assert (m["nx"], m["ny"], m["npml"], m["nstep"]) == (101, 641, 10, 2000 if m["order"] == 2 else 4000)
     c = refcfg.cfg2d(m["order"], nstep=m["nstep"])
     check_setup(g, m, c)
     assert list(g["ix_rec"]) == [70, 80] and list(g["iy_rec"]) == [231, 31]          # SURVEY.md App. C.1
@@ -235,5 +239,27 @@ def test_oracle_equals_the_2d_reference_programs_at_their_default_configuration(
     assert np.array_equal(o["sisvx"], g["sisvx"]) and np.array_equal(o["sisvy"], g["sisvy"])
     assert np.array_equal(o["energy_kinetic"], g["energy_kinetic"]) and np.array_equal(o["energy_potential"], g["energy_potential"])
     for f in F2:
-        h = hashlib.sha256(np.ascontiguousarray(np.asarray(o[f]).reshape(m["ny"], m["nx"]), dtype=np.float64).tobytes()).hexdigest()
-        assert h == str(g["sha256_" + f]), f
+        assert _sha(o[f], (m["ny"], m["nx"])) == str(g["sha256_" + f]), f
+
+
+def test_oracle_equals_the_3d_reference_program_on_its_own_xy_grid():
+    """seismic_CPML_3D_isotropic_MPI_OpenMP.f90 with its own NX x NY = 101 x 641 grid, source (80, 428) and receivers
+    (70, 231), (80, 31); NZ = 32 on two ranks instead of 640 on 64, 1000 of the 2500 steps: first arrivals and the main
+    pulse at both receivers, every shell touched.  2.1 million points x 1000 steps executed from the source text."""
+    fn = os.path.join(GOLDEN, "ref_3d_iso_xy_default.npz")
+    if not os.path.exists(fn):
+        pytest.skip("vector not generated")
+    g, m = load("ref_3d_iso_xy_default")
+    assert (m["nx"], m["ny"], m["nz"], m["npml"], m["nstep"]) == (101, 641, 32, 10, 1000)
+    c = refcfg.cfg3d(nx=101, ny=641, nz=32, nstep=1000, npml=10)
+    # the reference's receiver line (ydeb = 2300, yfin = 300), not refcfg's reduced-grid one
+    c["ix_rec"], c["iy_rec"], _ = O.find_receivers(101, 641, 10.0, 10.0, 2, (c["isource"] - 1) * 10.0 - 100.0, 2300.0,
+                                                   (c["isource"] - 1) * 10.0, 300.0)
+    check_setup(g, m, c)
+    assert list(g["ix_rec"]) == [70, 80] and list(g["iy_rec"]) == [231, 31] and (c["isource"], c["jsource"]) == (80, 428)
+    o = O.run_3d_iso(**c, nproc=2, want_fields=True)
+    assert np.abs(g["sisvx"][0]).max() > 1e-3 and np.abs(g["sisvy"][1]).max() > 1e-4
+    assert np.array_equal(o["sisvx"], g["sisvx"]) and np.array_equal(o["sisvy"], g["sisvy"])
+    assert np.array_equal(o["total_energy"], g["total_energy"])
+    for f in F3:
+        assert _sha(o[f], (32, 641, 101)) == str(g["sha256_" + f]), f
