@@ -263,3 +263,16 @@ def test_oracle_equals_the_3d_reference_program_on_its_own_xy_grid():
     assert np.array_equal(o["total_energy"], g["total_energy"])
     for f in F3:
         assert _sha(o[f], (32, 641, 101)) == str(g["sha256_" + f]), f
+
+
+@pytest.mark.parametrize("order,old", [(2, "cpml2d_second_default"), (4, "cpml2d_fourth_default")])
+def test_round1_golden_files_are_what_the_reference_programs_compute(order, old):
+    """tests/golden/cpml2d_{second,fourth}_default.npz were generated from the C oracle in round 1 and are what the GPU
+    full-run test (tests/test_gpu_parity.py::test_2d_shipped_configuration_full_run) compares the CUDA kernels with,
+    bit for bit.  They equal, bit for bit, what the reference programs compute when run from their source."""
+    fn = os.path.join(GOLDEN, f"ref_2d_{'second' if order == 2 else 'fourth'}_default.npz")
+    if not os.path.exists(fn):
+        pytest.skip("vector not generated")
+    ref, mine = np.load(fn), np.load(os.path.join(GOLDEN, old + ".npz"))
+    for k in ("sisvx", "sisvy", "energy_kinetic", "energy_potential"):
+        assert np.array_equal(ref[k], mine[k]), k
