@@ -57,6 +57,14 @@ CASES = {
                                   default=True, slow=True),
     "ref_3d_iso_xy_default": dict(kind="3d_iso", program="seismic_CPML_3D_isotropic_MPI_OpenMP.f90", default=True, slow=True,
                                   nz=32, nproc=2, nstep=1000, k_max=1.0),
+    # mid-size viscoelastic runs (vectorising mode, fields as SHA-256): long enough for the wave to cross the receivers
+    # and enter every shell
+    "ref_3d_visco_mid_np2": dict(kind="3d_visco", program="seismic_CPML_3D_viscoelastic_MPI.f90", slow=True, fast=True, hash_fields=True,
+                                 nx=64, ny=72, nz=24, npml=6, nstep=300, nproc=2, rec_scale=0.08),
+    "ref_2d_visco_second_mid": dict(kind="2d_visco", program="seismic_CPML_2D_velocity_and_stress_second_order_viscoelastic.f90",
+                                    order=2, nx=201, ny=201, npml=10, nstep=1200, slow=True, fast=True, hash_fields=True),
+    "ref_2d_visco_fourth_mid": dict(kind="2d_visco", program="seismic_CPML_2D_velocity_and_stress_fourth_order_viscoelastic.f90",
+                                    order=4, nx=201, ny=201, npml=10, nstep=1200, slow=True, fast=True, hash_fields=True),
     "ref_3d_visco_np2": dict(kind="3d_visco", program="seismic_CPML_3D_viscoelastic_MPI.f90",
                              nx=32, ny=30, nz=12, npml=4, nstep=60, nproc=2, rec_scale=0.04),
     "ref_3d_visco_np4": dict(kind="3d_visco", program="seismic_CPML_3D_viscoelastic_MPI.f90",       # quirk B6 depends on NPROC
@@ -131,7 +139,7 @@ def run_case(name):
         sc = f"{c['rec_scale']!r}d0"
         edits = [(r"^(xrec|yrec)\((\d)\)\s*=\s*(\w+)\s*\+\s*(\d+\.d0)\s*$", r"\1(\2)=\3+\4*" + sc)]
         sp = F.run_program(path, {k: str(v) for k, v in ov.items()}, nproc=c["nproc"],
-                           externals={"compute_attenuation_coeffs": _fit_from(tau)}, edits=edits)
+                           externals={"compute_attenuation_coeffs": _fit_from(tau)}, edits=edits, vectorize=c.get("fast", False))
         r = sp[sp[0]["rank_cut_plane"]]
         nzl = c["nz"] // c["nproc"]
         out.update(_profiles(r, "xyz"))
@@ -147,7 +155,7 @@ def run_case(name):
               "xdeb": "xsource + 20*deltax", "ydeb": "ysource + 20*deltax", "xfin": "xsource + 10*deltax",
               "yfin": "ysource - 25*deltax", "COMPUTE_ENERGY": ".true."}                                 # as in refcfg.cfgv2d
         r = F.run_program(path, {k: str(v) for k, v in ov.items()},
-                          externals={"compute_attenuation_coeffs": _fit_from(tau)})[0]
+                          externals={"compute_attenuation_coeffs": _fit_from(tau)}, vectorize=c.get("fast", False))[0]
         out.update(_profiles(r, "xy"))
         out.update(sisvx=r["sisvx"].T, sisvy=r["sisvy"].T, sispressure=r["sispressure"].T,
                    energy_kinetic=r["total_energy_kinetic"], energy_potential=r["total_energy_potential"])
@@ -155,7 +163,7 @@ def run_case(name):
             out[mine] = _interior(r, f, (c["nx"], c["ny"])).T
     out.update(isource=int(r["isource"]), jsource=int(r["jsource"]), ix_rec=np.array(r["ix_rec"]), iy_rec=np.array(r["iy_rec"]),
                deltat=float(r["deltat"]))
-    if c.get("default"):              # full-size fields: their SHA-256 instead of the arrays
+    if c.get("default") or c.get("hash_fields"):              # large fields: their SHA-256 instead of the arrays
         import hashlib
         for f in ("vx", "vy", "vz", "sigmaxx", "sigmayy", "sigmazz", "sigmaxy", "sigmaxz", "sigmayz"):
             if f in out:

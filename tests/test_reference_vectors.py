@@ -23,7 +23,10 @@ from oracle import oracle as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["ref_3d_iso_np2", "ref_3d_iso_kmax3_np2", "ref_3d_iso_np4", "ref_2d_second", "ref_2d_fourth", "ref_3d_visco_np2",
-         "ref_3d_visco_np4", "ref_2d_visco_second", "ref_2d_visco_fourth"]
+         "ref_3d_visco_np4", "ref_2d_visco_second", "ref_2d_visco_fourth",
+         # mid-size viscoelastic runs, long enough for the wave to cross the receivers and enter every shell (vectorising
+         # mode of f90_exec; fields compared through their SHA-256)
+         "ref_3d_visco_mid_np2", "ref_2d_visco_second_mid", "ref_2d_visco_fourth_mid"]
 F3 = ("vx", "vy", "vz", "sigmaxx", "sigmayy", "sigmazz", "sigmaxy", "sigmaxz", "sigmayz")
 F2 = ("vx", "vy", "sigmaxx", "sigmayy", "sigmaxy")
 
@@ -54,8 +57,15 @@ def check_setup(g, m, c):
             assert np.array_equal(g[f"prof_{ax}_{k}"], np.asarray(c["prof_" + ax][k])), (ax, k)
 
 
+def _sha(a, shape):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(np.asarray(a).reshape(shape), dtype=np.float64).tobytes()).hexdigest()
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_oracle_equals_the_reference_program(name):
+    if not os.path.exists(os.path.join(GOLDEN, name + ".npz")):
+        pytest.skip("vector not generated")
     g, m = load(name)
     c = config(m)
     check_setup(g, m, c)
@@ -75,9 +85,13 @@ def test_oracle_equals_the_reference_program(name):
     assert np.array_equal(o["sisvx"], g["sisvx"]) and np.array_equal(o["sisvy"], g["sisvy"])
     if "sispressure" in g:
         assert np.array_equal(o["sispressure"], g["sispressure"])
+    shape = (m["nz"], m["ny"], m["nx"]) if "nz" in m else (m["ny"], m["nx"])
     for f in fields:
-        assert np.abs(g[f]).max() > 0
-        assert np.array_equal(np.asarray(o[f]).reshape(g[f].shape), g[f]), f
+        if "sha256_" + f in g:
+            assert _sha(o[f], shape) == str(g["sha256_" + f]), f
+        else:
+            assert np.abs(g[f]).max() > 0
+            assert np.array_equal(np.asarray(o[f]).reshape(g[f].shape), g[f]), f
     for k in ("total_energy", "energy_kinetic", "energy_potential"):
         if k in g and k in o:
             assert np.abs(g[k]).max() > 0
@@ -213,11 +227,6 @@ def test_fp32_mode_against_the_reference_single_precision_build():
     assert np.abs(o64["sisvx"]).max() > 1e-3
     assert ours_vs_build <= 1e-5 and build_vs_double <= 1e-5 and ours_vs_double <= 1e-5
     assert ours_vs_double <= build_vs_double and e_ours <= e_build
-
-
-def _sha(a, shape):
-    import hashlib
-    return hashlib.sha256(np.ascontiguousarray(np.asarray(a).reshape(shape), dtype=np.float64).tobytes()).hexdigest()
 
 
 @pytest.mark.parametrize("name", ["ref_2d_second_default", "ref_2d_fourth_default"])
