@@ -417,12 +417,29 @@ class Translator:
             pos += 1
         if not loops:
             return None
-        end = pos
+        # the body: assignments, and loops over OTHER variables whose bodies are assignments (do i_sls = 1,N_SLS): those
+        # stay loops, with vector statements inside
+        end, items, body = pos, [], []
         while end < len(lines) and not re.match(r"^end\s*do$", lines[end]):
-            if re.match(r"^(do|if|else|end\s*if|call|stop|print|write)\b", lines[end]):
+            m2 = DO.match(lines[end])
+            if m2:
+                r2 = _split_top(m2.group(2))
+                k = end + 1
+                while k < len(lines) and not re.match(r"^end\s*do$", lines[k]):
+                    if re.match(r"^(do|if|else|end\s*if|call|stop|print|write)\b", lines[k]):
+                        return None
+                    k += 1
+                if len(r2) != 2 or k >= len(lines) or k == end + 1:
+                    return None
+                items.append((m2.group(1), r2, lines[end + 1:k]))
+                body += lines[end + 1:k]
+                end = k + 1
+                continue
+            if re.match(r"^(if|else|end\s*if|call|stop|print|write)\b", lines[end]):
                 return None
+            items.append((None, None, [lines[end]]))
+            body.append(lines[end])
             end += 1
-        body = lines[pos:end]
         # a nest of two must be perfect: the outer loop closes right after the inner one
         last = end
         if len(loops) == 2:
@@ -433,6 +450,10 @@ class Translator:
             return None
         names = [v for v, _ in loops]
         uses = lambda text, name: re.search(r"(?<![\w.])" + re.escape(name) + r"(?!\w)", text) is not None
+        for v2, r2, _ in items:              # inner loops: another variable, bounds that do not depend on the vector ones
+            if v2 is not None and (v2 in names or any(uses(b, v) for b in r2 for v in names)):
+                return None
+        inner_statements = {st for v2, _, sts in items if v2 is not None for st in sts}
         parsed = []
         for st in body:
             a = self._ASSIGN.match(st)
@@ -449,7 +470,7 @@ class Translator:
                 if not any(uses(lhs_args, v) for v in names):
                     # the same element in every iteration: only the accumulation A(k) = A(k) + expr is handled
                     ref = lhs + lhs_args
-                    if self.single or not rhs.strip().startswith(ref):
+                    if self.single or not rhs.strip().startswith(ref) or st in inner_statements:
                         return None
                     rest = rhs.strip()[len(ref):].lstrip()
                     if not rest.startswith("+") or uses(rest, lhs):
@@ -462,7 +483,7 @@ class Translator:
                 return None
             if carried:
                 mm = re.match(r"^\s*" + re.escape(lhs) + r"\s*\+(.*)$", rhs)
-                if carried != [lhs] or not mm or self.single or uses(mm.group(1), lhs):
+                if carried != [lhs] or not mm or self.single or uses(mm.group(1), lhs) or st in inner_statements:
                     return None
                 accum[st] = (lhs, mm.group(1))
             else:
@@ -484,14 +505,20 @@ class Translator:
         size = f"{inner}.size * {outer}.size" if outer else f"{inner}.size"
         self.emit(f"if {size}:")
         self.depth += 1
-        for st in body:
-            if st in accum:
-                lhs, term = accum[st]
-                shape = f"({inner}.size, {outer}.size)" if outer else f"({inner}.size,)"
-                target = self._arrays(_rename_keywords(lhs))          # a scalar or one array element
-                self.emit(f"{target} = _accumulate({target}, {self.expr(term)}, {shape})")
-            else:
-                self.statement(st)
+        for v2, r2, sts in items:
+            if v2 is not None:
+                self.emit(f"for {v2} in _range({self.expr(r2[0])}, {self.expr(r2[1])}):")
+                self.depth += 1
+            for st in sts:
+                if st in accum:
+                    lhs, term = accum[st]
+                    shape = f"({inner}.size, {outer}.size)" if outer else f"({inner}.size,)"
+                    target = self._arrays(_rename_keywords(lhs))          # a scalar or one array element
+                    self.emit(f"{target} = _accumulate({target}, {self.expr(term)}, {shape})")
+                else:
+                    self.statement(st)
+            if v2 is not None:
+                self.depth -= 1
         self.depth -= 1
         self.emit(f"{inner} = ({bounds[-1][1]}) + 1")
         if outer:

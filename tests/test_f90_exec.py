@@ -173,8 +173,10 @@ VEC_SRC = """
   double precision, dimension(0:NX+1,0:NY+1) :: u, w
   double precision, dimension(NX) :: bx
   double precision, dimension(NY) :: acc
-  double precision :: d, total, chain
-  integer :: i, j
+  double precision, dimension(NX,NY,2) :: r
+  double precision, dimension(2) :: phi
+  double precision :: d, total, chain, ssum
+  integer :: i, j, m
   do j = 0,NY+1
     do i = 0,NX+1
       u(i,j) = 1.d0 / dble(3 + i + 10*j)
@@ -194,6 +196,19 @@ VEC_SRC = """
       acc(3) = acc(3) + d                         ! ... and into one array element
     enddo
   enddo
+  phi(1) = 0.25d0
+  phi(2) = 0.75d0
+  r(:,:,:) = 0.d0
+  do j = 1,NY
+    do i = 1,NX
+      ssum = 0.d0
+      do m = 1,2                                  ! a loop over another variable inside the nest stays a loop
+        r(i,j,m) = (r(i,j,m) + u(i,j) * phi(m)) / (1.d0 + phi(m))
+        ssum = ssum + r(i,j,m)
+      enddo
+      w(i,j) = w(i,j) + ssum
+    enddo
+  enddo
   chain = 0.d0
   do i = 1,NX
     w(i,1) = w(i-1,1) + u(i,1)                    ! a true dependence between iterations: must stay a loop
@@ -205,7 +220,7 @@ VEC_SRC = """
 def test_vectorised_loops_give_the_same_bits_and_keep_true_dependences_sequential(tmp_path):
     a = run(tmp_path, VEC_SRC)[0]
     b = run(tmp_path, VEC_SRC, vectorize=True)[0]
-    for k in ("u", "w", "bx", "acc"):
+    for k in ("u", "w", "bx", "acc", "r"):
         assert np.array_equal(a[k], b[k]), k
     # (the private scalar d holds an array after a vectorised loop: like the PRIVATE variables of the reference's OpenMP
     # loops it is undefined afterwards, and no program reads one)
@@ -214,7 +229,8 @@ def test_vectorised_loops_give_the_same_bits_and_keep_true_dependences_sequentia
     p = tmp_path / "t.f90"
     tr = F.Translator(vectorize=True)
     src = tr.translate(F.logical_lines(str(p)))
-    assert src.count("np.arange(") == 5            # the u nest (2), the bx loop (1), the w nest (2); not the chain loop
+    assert src.count("np.arange(") == 7            # the u, w and r nests (2 each), the bx loop (1); not the chain loop
+    assert "for m in _range(1, 2):" in src
     assert src.count("_accumulate(") == 2
 
 
