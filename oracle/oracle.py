@@ -6,6 +6,8 @@ tests/test_reference_vectors.py) -- see oracle/cpml_oracle.h.
 
 Two builds of the same C file (oracle/Makefile):
   golden -- gcc -O2 -ffp-contract=off, serial: the parity checker;
+  golden_omp -- the same strict arithmetic with the OpenMP loops on: identical fields and seismograms, energy sums in
+            another order (used by the one large reference-vector test);
   timed  -- gcc -O3 -march=x86-64-v3 -fopenmp: the CPU baseline that is timed.
 """
 from __future__ import annotations
@@ -65,7 +67,7 @@ class OracleV2DConfig(C.Structure):
 
 def build(force: bool = False) -> None:
     """Compile both oracle libraries (no-op when they are already there)."""
-    names = ["liboracle_golden.so", "liboracle_timed.so"]
+    names = ["liboracle_golden.so", "liboracle_golden_omp.so", "liboracle_timed.so"]
     srcs = ["cpml_oracle.c", "cpml_oracle_visco.c", "cpml_oracle_visco2d.c", "cpml_oracle.h", "oracle_internal.h", "Makefile"]
     if not force and all(os.path.exists(os.path.join(_HERE, n)) for n in names):
         # prebuilt libraries travel to the GPU box; rebuild only when a source is newer

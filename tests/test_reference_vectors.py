@@ -266,10 +266,16 @@ def test_oracle_equals_the_3d_reference_program_on_its_own_xy_grid():
                                                    (c["isource"] - 1) * 10.0, 300.0)
     check_setup(g, m, c)
     assert list(g["ix_rec"]) == [70, 80] and list(g["iy_rec"]) == [231, 31] and (c["isource"], c["jsource"]) == (80, 428)
-    o = O.run_3d_iso(**c, nproc=2, want_fields=True)
+    # the strict-arithmetic oracle with its OpenMP loops on (oracle/Makefile: golden_omp): every point sees the same
+    # operations as in the serial build -- fields and seismograms bit-identical, checked here on a small grid -- and only
+    # the energy reduction is summed in another order; 45 s instead of two minutes
+    small = refcfg.cfg3d(nx=24, ny=30, nz=16, nstep=40, npml=4)
+    a, b = O.run_3d_iso(**small, nproc=2, want_fields=True), O.run_3d_iso(**small, nproc=2, want_fields=True, kind="golden_omp")
+    assert all(np.array_equal(a[k], b[k]) for k in ("sisvx", "sisvy") + F3)
+    o = O.run_3d_iso(**c, nproc=2, want_fields=True, kind="golden_omp")
     assert np.abs(g["sisvx"][0]).max() > 1e-3 and np.abs(g["sisvy"][1]).max() > 1e-4
     assert np.array_equal(o["sisvx"], g["sisvx"]) and np.array_equal(o["sisvy"], g["sisvy"])
-    assert np.array_equal(o["total_energy"], g["total_energy"])
+    assert refcfg.rel_l2(o["total_energy"], g["total_energy"]) <= 1e-13
     for f in F3:
         assert _sha(o[f], (32, 641, 101)) == str(g["sha256_" + f]), f
 
