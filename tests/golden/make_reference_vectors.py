@@ -57,6 +57,9 @@ CASES = {
                                   default=True, slow=True),
     "ref_3d_iso_xy_default": dict(kind="3d_iso", program="seismic_CPML_3D_isotropic_MPI_OpenMP.f90", default=True, slow=True,
                                   nz=32, nproc=2, nstep=1000, k_max=1.0),
+    # ... and for all 2500 steps of the program (two hours)
+    "ref_3d_iso_xy_default_full": dict(kind="3d_iso", program="seismic_CPML_3D_isotropic_MPI_OpenMP.f90", default=True, slow=True,
+                                       nz=32, nproc=2, nstep=2500, k_max=1.0),
     # mid-size viscoelastic runs (vectorising mode, fields as SHA-256): long enough for the wave to cross the receivers
     # and enter every shell
     "ref_3d_visco_mid_np2": dict(kind="3d_visco", program="seismic_CPML_3D_viscoelastic_MPI.f90", slow=True, fast=True, hash_fields=True,

@@ -251,16 +251,19 @@ def test_oracle_equals_the_2d_reference_programs_at_their_default_configuration(
         assert _sha(o[f], (m["ny"], m["nx"])) == str(g["sha256_" + f]), f
 
 
-def test_oracle_equals_the_3d_reference_program_on_its_own_xy_grid():
+@pytest.mark.parametrize("name", ["ref_3d_iso_xy_default", "ref_3d_iso_xy_default_full"])
+def test_oracle_equals_the_3d_reference_program_on_its_own_xy_grid(name):
     """seismic_CPML_3D_isotropic_MPI_OpenMP.f90 with its own NX x NY = 101 x 641 grid, source (80, 428) and receivers
-    (70, 231), (80, 31); NZ = 32 on two ranks instead of 640 on 64, 1000 of the 2500 steps: first arrivals and the main
-    pulse at both receivers, every shell touched.  2.1 million points x 1000 steps executed from the source text."""
-    fn = os.path.join(GOLDEN, "ref_3d_iso_xy_default.npz")
+    (70, 231), (80, 31); NZ = 32 on two ranks instead of 640 on 64; 1000 steps (first arrivals and the main pulse at both
+    receivers) or, in the _full vector, all 2500 steps of the program.  2.1 million points executed from the source
+    text (46 minutes / two hours of vectorised Python)."""
+    fn = os.path.join(GOLDEN, name + ".npz")
     if not os.path.exists(fn):
-        pytest.skip("vector not generated")
-    g, m = load("ref_3d_iso_xy_default")
-    assert (m["nx"], m["ny"], m["nz"], m["npml"], m["nstep"]) == (101, 641, 32, 10, 1000)
-    c = refcfg.cfg3d(nx=101, ny=641, nz=32, nstep=1000, npml=10)
+        pytest.skip("vector not generated (the _full one replaces the 1000-step one)")
+    g, m = load(name)
+    nstep = m["nstep"]
+    assert (m["nx"], m["ny"], m["nz"], m["npml"]) == (101, 641, 32, 10) and nstep in (1000, 2500)
+    c = refcfg.cfg3d(nx=101, ny=641, nz=32, nstep=nstep, npml=10)
     # the reference's receiver line (ydeb = 2300, yfin = 300), not refcfg's reduced-grid one
     c["ix_rec"], c["iy_rec"], _ = O.find_receivers(101, 641, 10.0, 10.0, 2, (c["isource"] - 1) * 10.0 - 100.0, 2300.0,
                                                    (c["isource"] - 1) * 10.0, 300.0)
@@ -268,7 +271,7 @@ def test_oracle_equals_the_3d_reference_program_on_its_own_xy_grid():
     assert list(g["ix_rec"]) == [70, 80] and list(g["iy_rec"]) == [231, 31] and (c["isource"], c["jsource"]) == (80, 428)
     # the strict-arithmetic oracle with its OpenMP loops on (oracle/Makefile: golden_omp): every point sees the same
     # operations as in the serial build -- fields and seismograms bit-identical, checked here on a small grid -- and only
-    # the energy reduction is summed in another order; 45 s instead of two minutes
+    # the energy reduction is summed in another order
     small = refcfg.cfg3d(nx=24, ny=30, nz=16, nstep=40, npml=4)
     a, b = O.run_3d_iso(**small, nproc=2, want_fields=True), O.run_3d_iso(**small, nproc=2, want_fields=True, kind="golden_omp")
     assert all(np.array_equal(a[k], b[k]) for k in ("sisvx", "sisvy") + F3)
