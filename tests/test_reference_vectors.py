@@ -39,7 +39,11 @@ def load(name):
 def config(m):
     """The same reduced configuration, built by the oracle's own set-up functions."""
     if m["kind"] == "3d_iso":
-        return refcfg.cfg3d(nx=m["nx"], ny=m["ny"], nz=m["nz"], nstep=m["nstep"], npml=m["npml"], k_max=m["k_max"])
+        c = refcfg.cfg3d(nx=m["nx"], ny=m["ny"], nz=m["nz"], nstep=m["nstep"], npml=m["npml"], k_max=m["k_max"])
+        if m.get("default"):      # the reference's own receiver line (ydeb = 2300, yfin = 300), not refcfg's reduced-grid one
+            xs = (c["isource"] - 1) * c["deltax"]
+            c["ix_rec"], c["iy_rec"], _ = O.find_receivers(m["nx"], m["ny"], c["deltax"], c["deltay"], 2, xs - 100.0, 2300.0, xs, 300.0)
+        return c
     if m["kind"] == "2d_iso":
         return refcfg.cfg2d(m["order"], nx=m["nx"], ny=m["ny"], nstep=m["nstep"], npml=m["npml"], ydeb=m["ydeb"], yfin=m["yfin"])
     if m["kind"] == "3d_visco":
@@ -115,11 +119,16 @@ def _solver3d(L, c, **kw):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["ref_3d_iso_np2", "ref_3d_iso_kmax3_np2", "ref_3d_iso_np4"])
+@pytest.mark.parametrize("name", ["ref_3d_iso_np2", "ref_3d_iso_kmax3_np2", "ref_3d_iso_np4",
+                                  "ref_3d_iso_xy_default", "ref_3d_iso_xy_default_full"])
 def test_cuda_3d_isotropic_equals_the_reference_program(name):
     """The C ABI on the GPU against the reference program's own numbers: fields and seismograms bit for bit, energy to
-    1e-11 (its sum is ordered differently, quirk B11)."""
+    1e-11 (its sum is ordered differently, quirk B11).  The last two: the program's own 101 x 641 grid, source and
+    receivers with NZ = 32 (added after this round's GPU budget was spent: the three small cases ran green on B200, these
+    follow from oracle == vector on the CPU and CUDA == oracle everywhere else)."""
     from seismic_cpml_b200 import lib as L
+    if not os.path.exists(os.path.join(GOLDEN, name + ".npz")):
+        pytest.skip("vector not generated")
     g, m = load(name)
     c = config(m)
     with _solver3d(L, c) as s:
@@ -127,7 +136,10 @@ def test_cuda_3d_isotropic_equals_the_reference_program(name):
         sx, sy = s.get_seismograms()
         assert np.array_equal(sx, g["sisvx"]) and np.array_equal(sy, g["sisvy"])
         for f, fname in enumerate(F3):
-            assert np.array_equal(s.get_field(f), g[fname]), fname
+            if "sha256_" + fname in g:
+                assert _sha(s.get_field(f), (m["nz"], m["ny"], m["nx"])) == str(g["sha256_" + fname]), fname
+            else:
+                assert np.array_equal(s.get_field(f), g[fname]), fname
         assert refcfg.rel_l2(s.get_energy()[0], g["total_energy"]) <= 1e-11
 
 
@@ -263,10 +275,7 @@ def test_oracle_equals_the_3d_reference_program_on_its_own_xy_grid(name):
     g, m = load(name)
     nstep = m["nstep"]
     assert (m["nx"], m["ny"], m["nz"], m["npml"]) == (101, 641, 32, 10) and nstep in (1000, 2500)
-    c = refcfg.cfg3d(nx=101, ny=641, nz=32, nstep=nstep, npml=10)
-    # the reference's receiver line (ydeb = 2300, yfin = 300), not refcfg's reduced-grid one
-    c["ix_rec"], c["iy_rec"], _ = O.find_receivers(101, 641, 10.0, 10.0, 2, (c["isource"] - 1) * 10.0 - 100.0, 2300.0,
-                                                   (c["isource"] - 1) * 10.0, 300.0)
+    c = config(m)
     check_setup(g, m, c)
     assert list(g["ix_rec"]) == [70, 80] and list(g["iy_rec"]) == [231, 31] and (c["isource"], c["jsource"]) == (80, 428)
     # the strict-arithmetic oracle with its OpenMP loops on (oracle/Makefile: golden_omp): every point sees the same
