@@ -271,7 +271,7 @@ def test_oracle_equals_the_3d_reference_program_on_its_own_xy_grid(name):
     text (46 minutes / two hours of vectorised Python)."""
     fn = os.path.join(GOLDEN, name + ".npz")
     if not os.path.exists(fn):
-        pytest.skip("vector not generated (the _full one replaces the 1000-step one)")
+        pytest.skip("vector not in the tree (the 2500-step one replaced the 1000-step one; the generator makes either)")
     g, m = load(name)
     nstep = m["nstep"]
     assert (m["nx"], m["ny"], m["nz"], m["npml"]) == (101, 641, 32, 10) and nstep in (1000, 2500)
