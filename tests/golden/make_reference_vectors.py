@@ -64,6 +64,8 @@ CASES = {
     # and enter every shell
     "ref_3d_visco_mid_np2": dict(kind="3d_visco", program="seismic_CPML_3D_viscoelastic_MPI.f90", slow=True, fast=True, hash_fields=True,
                                  nx=64, ny=72, nz=24, npml=6, nstep=300, nproc=2, rec_scale=0.08),
+    "ref_3d_visco_mid_np4": dict(kind="3d_visco", program="seismic_CPML_3D_viscoelastic_MPI.f90", slow=True, fast=True, hash_fields=True,
+                                 nx=64, ny=72, nz=32, npml=6, nstep=300, nproc=4, rec_scale=0.08),
     "ref_2d_visco_second_mid": dict(kind="2d_visco", program="seismic_CPML_2D_velocity_and_stress_second_order_viscoelastic.f90",
                                     order=2, nx=201, ny=201, npml=10, nstep=1200, slow=True, fast=True, hash_fields=True),
     "ref_2d_visco_fourth_mid": dict(kind="2d_visco", program="seismic_CPML_2D_velocity_and_stress_fourth_order_viscoelastic.f90",

@@ -26,7 +26,7 @@ CASES = ["ref_3d_iso_np2", "ref_3d_iso_kmax3_np2", "ref_3d_iso_np4", "ref_2d_sec
          "ref_3d_visco_np4", "ref_2d_visco_second", "ref_2d_visco_fourth",
          # mid-size viscoelastic runs, long enough for the wave to cross the receivers and enter every shell (vectorising
          # mode of f90_exec; fields compared through their SHA-256)
-         "ref_3d_visco_mid_np2", "ref_2d_visco_second_mid", "ref_2d_visco_fourth_mid"]
+         "ref_3d_visco_mid_np2", "ref_3d_visco_mid_np4", "ref_2d_visco_second_mid", "ref_2d_visco_fourth_mid"]
 F3 = ("vx", "vy", "vz", "sigmaxx", "sigmayy", "sigmazz", "sigmaxy", "sigmaxz", "sigmayz")
 F2 = ("vx", "vy", "sigmaxx", "sigmayy", "sigmaxy")
 
